@@ -1,0 +1,121 @@
+"""ctypes binding of libb200olap.so — the same C ABI (include/b200olap.h) the C++ host links.
+
+There is deliberately NO fallback: if the CUDA library is missing or fails to load, importing
+the operators raises, and every non-OK status raises B2Error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libb200olap.so"
+HEADER = PKG_DIR.parent / "include" / "b200olap.h"
+
+B2_OK = 0
+STATUS_NAMES = {0: "B2_OK", 1: "B2_ERR_INVALID", 2: "B2_ERR_CUDA", 3: "B2_ERR_OOM",
+                4: "B2_ERR_UNSUPPORTED", 5: "B2_ERR_WORKSPACE", 6: "B2_ERR_OVERFLOW"}
+
+
+class B2Error(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        super().__init__(f"{where}: {STATUS_NAMES.get(status, status)} {detail}".strip())
+
+
+class Timings(C.Structure):
+    _fields_ = [("copy_to_dev_ms", C.c_double), ("dev_work_ms", C.c_double),
+                ("copy_from_dev_ms", C.c_double), ("total_ms", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("kernel_launches", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_vp, _i64, _u64, _u32, _int, _sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
+_pp = C.POINTER(C.c_void_p)          # array of pointers
+_pi64 = C.POINTER(C.c_int64)
+_pu64 = C.POINTER(C.c_uint64)
+_pu32 = C.POINTER(C.c_uint32)
+_pt = C.POINTER(Timings)
+
+# name -> (restype, argtypes); must cover every function include/b200olap.h declares
+SIGNATURES = {
+    "b2_version": (_int, []),
+    "b2_strerror": (C.c_char_p, [_int]),
+    "b2_device_count": (_int, [C.POINTER(C.c_int)]),
+    "b2_ctx_create": (_int, [_int, C.POINTER(_vp)]),
+    "b2_ctx_destroy": (_int, [_vp]),
+    "b2_last_error": (C.c_char_p, [_vp]),
+    "b2_launch_count": (_i64, [_vp]),
+    "b2_ctx_device": (_int, [_vp]),
+    "b2_ctx_sm_count": (_int, [_vp]),
+    "b2_gen_u32_dev": (_int, [_vp, _pu64, _pu32, _pu32, _i64, _i64, _vp, _vp]),
+    "b2_iota_u32_dev": (_int, [_vp, _u64, _i64, _vp, _vp]),
+    "b2_sum_u32_dev": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "b2_sum_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pu64, _pt]),
+    "b2_filter_ws_bytes": (_sz, [_i64, _i64]),
+    "b2_filter_lt_u32_dev": (_int, [_vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b2_filter_ragged_ws_bytes": (_sz, [_pi64, _i64]),
+    "b2_filter_lt_u32_ragged_dev": (_int, [_vp, _vp, _pi64, _vp, _i64, _u32, _vp, _vp, _vp, _vp,
+                                           _vp, _sz, _vp]),
+    "b2_filter_lt_u32_host": (_int, [_vp, _pp, _pi64, _i64, _u32, _pi64, _pu64, _pt]),
+    "b2_filter_fetch_host": (_int, [_vp, _pp, _i64, _pt]),
+    "b2_take_u32_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "b2_take_u32_ragged_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "b2_take_u32_host": (_int, [_vp, _pp, _pi64, _pp, _pi64, _i64, _pp, _pt]),
+    "b2_wang_hash_u32": (_u32, [_u32]),
+    "b2_partition_ws_bytes": (_sz, [_i64, _int]),
+    "b2_partition_u32_dev": (_int, [_vp, _pp, _pp, _int, _i64, _int, _int, _vp, _vp, _sz, _vp]),
+    "b2_partition_u32_host": (_int, [_vp, _pp, _pi64, _i64, _int, _int, _int, _pi64, _pt]),
+    "b2_partition_fetch_host": (_int, [_vp, _pp, _int, _int, _pt]),
+    "b2_join_ws_bytes": (_sz, [_i64, _i64]),
+    "b2_join_min_ws_bytes": (_sz, [_i64, _i64]),
+    "b2_join_u32_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp,
+                               _int, _vp, _sz, _vp]),
+    "b2_join_pairs_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _int, _vp,
+                                 _sz, _vp]),
+    "b2_join_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pp, _pi64, _i64, _pu64, _pt]),
+    "b2_join_fetch_host": (_int, [_vp, _vp, _vp, _vp, _i64, _pt]),
+    "b2_join_dest_rank": (_int, [_u32, _int]),
+    "b2_shuffle_ws_bytes": (_sz, [_i64, _int]),
+    "b2_shuffle_partition_u32_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+}
+
+
+def header_functions() -> list[str]:
+    """Names of every function declared in include/b200olap.h (used by the export test)."""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200olap.so (built in-tree by dpu_olap_b200/build.py). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m dpu_olap_b200.build` "
+            "(there is no CPU fallback for the operator path)")
+    handle = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return handle
+
+
+def check(status: int, where: str, ctx: C.c_void_p | None = None) -> None:
+    if status != B2_OK:
+        detail = ""
+        if ctx:
+            detail = lib().b2_last_error(ctx).decode(errors="replace")
+        raise B2Error(status, where, detail)

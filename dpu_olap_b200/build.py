@@ -1,0 +1,75 @@
+"""Build recipe for libb200olap.so (hand-written sm_100a CUDA, C ABI in include/b200olap.h).
+
+nvcc cross-compiles without a GPU, so this runs in the CPU-only build container; the resulting
+.so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO = PKG_DIR.parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libb200olap.so"
+STAMP = PKG_DIR / ".libb200olap.stamp"
+
+SOURCES = ["ctx.cu", "sum.cu", "filter.cu", "take.cu", "gen.cu", "scan.cu", "partition.cu",
+           "join.cu", "api_host.cu", "api_host_join.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
+    "--shared", "-cudart", "shared",
+    "-Xptxas", "-v",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _sources() -> list[Path]:
+    return [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    files = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [REPO / "include" / "b200olap.h"])
+    for f in files:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every .cu in csrc/ into dpu_olap_b200/libb200olap.so (skips if up to date)."""
+    digest = _digest()
+    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
+        return LIB_PATH
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", str(REPO / "include"), "-o", str(LIB_PATH),
+           *[str(s) for s in _sources()]]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    log = proc.stdout + proc.stderr
+    (PKG_DIR / "build.log").write_text(" ".join(cmd) + "\n" + log)
+    if proc.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libb200olap.so")
+    if verbose:
+        sys.stderr.write(log)
+    STAMP.write_text(digest)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose=True)
+    print(p)

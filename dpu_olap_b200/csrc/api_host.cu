@@ -1,0 +1,462 @@
+// api_host.cu — the host-buffer entry points: what the reference's *Dpu operator classes did with
+// dpu::DpuSet + arrow_copy_to_dpus / arrow_copy_from_dpus (host/dpuext/arrow_utils.cc:47-73,
+// 147-266) now happens behind one C call per operator: upload the record batches' data buffers,
+// run the kernels, hand the result back.
+//
+// The reference processes `nr_dpus` batches at a time (copy -> exec -> copy back per group,
+// host/filter/filter_dpu.cc:128-157). Here a "group" is a chunk of consecutive batches (~64 MiB):
+// chunk k+1 is uploaded on the copy stream while chunk k is processed on the compute stream and,
+// where the result size is known up front (take), chunk k-1 is downloaded on a third stream.
+// Consecutive batches that are adjacent in host memory are merged into one copy.
+#include <chrono>
+#include <vector>
+
+#include "common.cuh"
+#include "pending.h"
+
+int b2_ctx_reserve_ws(b2_ctx* ctx, size_t bytes);  // gen.cu
+
+void b2_pending_free(b2_ctx* ctx) {
+  if (!ctx || !ctx->pending) return;
+  for (void* p : ctx->pending->dev) cudaFree(p);
+  delete ctx->pending;
+  ctx->pending = nullptr;
+}
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+}
+
+constexpr int64_t kChunkBytes = 64ll << 20;
+
+int ensure_streams(b2_ctx* ctx) {
+  B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->s_compute) B2_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+  if (!ctx->s_copy_in) B2_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_copy_in, cudaStreamNonBlocking));
+  if (!ctx->s_copy_out) B2_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_copy_out, cudaStreamNonBlocking));
+  return B2_OK;
+}
+
+int dev_alloc(b2_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 256;
+  B2_CUDA_OK(ctx, cudaMalloc(p, bytes));
+  return B2_OK;
+}
+
+// RAII list of scratch device allocations and events of one call.
+struct Scratch {
+  std::vector<void*> dev;
+  std::vector<cudaEvent_t> events;
+  ~Scratch() {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    for (void* p : dev) cudaFree(p);
+  }
+  int alloc(b2_ctx* ctx, void** p, size_t bytes) {
+    B2_RETURN_NOT_OK(dev_alloc(ctx, p, bytes));
+    dev.push_back(*p);
+    return B2_OK;
+  }
+  int event(b2_ctx* ctx, cudaEvent_t* e, bool timing) {
+    B2_CUDA_OK(ctx, cudaEventCreateWithFlags(e, timing ? cudaEventDefault : cudaEventDisableTiming));
+    events.push_back(*e);
+    return B2_OK;
+  }
+  void* release(void* p) {  // hand ownership to someone else
+    for (auto& q : dev)
+      if (q == p) q = nullptr;
+    return p;
+  }
+};
+
+struct Layout {
+  std::vector<int64_t> off;  // nbatches+1 row offsets of the packed device column
+  bool uniform = true;
+  int64_t batch_len = 0;
+  int64_t rows() const { return off.back(); }
+};
+
+int make_layout(b2_ctx* ctx, const uint32_t* const* ptrs, const int64_t* lens, int64_t nbatches,
+                Layout* L) {
+  B2_REQUIRE(ctx, nbatches >= 0, "negative batch count");
+  B2_REQUIRE(ctx, nbatches == 0 || (ptrs && lens), "null batch table");
+  L->off.assign((size_t)nbatches + 1, 0);
+  L->batch_len = nbatches > 0 ? lens[0] : 0;
+  for (int64_t b = 0; b < nbatches; ++b) {
+    B2_REQUIRE(ctx, lens[b] >= 0, "negative batch length");
+    B2_REQUIRE(ctx, lens[b] == 0 || ptrs[b] != nullptr, "null batch pointer");
+    if (lens[b] != L->batch_len) L->uniform = false;
+    L->off[(size_t)b + 1] = L->off[(size_t)b] + lens[b];
+  }
+  return B2_OK;
+}
+
+// Chunk boundaries: consecutive batches, about kChunkBytes each, at least one batch per chunk.
+std::vector<int64_t> make_chunks(const Layout& L, int64_t nbatches) {
+  std::vector<int64_t> c{0};
+  int64_t acc = 0;
+  for (int64_t b = 0; b < nbatches; ++b) {
+    const int64_t bytes = (L.off[(size_t)b + 1] - L.off[(size_t)b]) * 4;
+    if (acc > 0 && acc + bytes > kChunkBytes) {
+      c.push_back(b);
+      acc = 0;
+    }
+    acc += bytes;
+  }
+  if (nbatches > 0) c.push_back(nbatches);
+  return c;
+}
+
+// Upload batches [b0,b1) to their packed positions, merging host-adjacent batches.
+int upload(b2_ctx* ctx, uint32_t* d_col, const Layout& L, const uint32_t* const* ptrs, int64_t b0,
+           int64_t b1, cudaStream_t s, int64_t* bytes) {
+  int64_t b = b0;
+  while (b < b1) {
+    int64_t e = b + 1;
+    while (e < b1 && ptrs[e] == ptrs[e - 1] + (L.off[(size_t)e] - L.off[(size_t)e - 1])) ++e;
+    const int64_t rows = L.off[(size_t)e] - L.off[(size_t)b];
+    if (rows > 0) {
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_col + L.off[(size_t)b], ptrs[b], (size_t)rows * 4,
+                                      cudaMemcpyHostToDevice, s));
+      *bytes += rows * 4;
+    }
+    b = e;
+  }
+  return B2_OK;
+}
+
+// Download packed rows [L.off[b0], L.off[b1]) to per-batch host pointers (merging adjacent ones).
+int download(b2_ctx* ctx, const uint32_t* d_col, const Layout& L, uint32_t* const* ptrs, int64_t b0,
+             int64_t b1, cudaStream_t s, int64_t* bytes) {
+  int64_t b = b0;
+  while (b < b1) {
+    int64_t e = b + 1;
+    while (e < b1 && ptrs[e] == ptrs[e - 1] + (L.off[(size_t)e] - L.off[(size_t)e - 1])) ++e;
+    const int64_t rows = L.off[(size_t)e] - L.off[(size_t)b];
+    if (rows > 0) {
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(ptrs[b], d_col + L.off[(size_t)b], (size_t)rows * 4,
+                                      cudaMemcpyDeviceToHost, s));
+      *bytes += rows * 4;
+    }
+    b = e;
+  }
+  return B2_OK;
+}
+
+struct PhaseTimer {  // sums CUDA-event intervals recorded on one stream
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+  double total_ms() const {
+    double t = 0;
+    for (auto& sp : spans) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, sp.first, sp.second) == cudaSuccess) t += ms;
+    }
+    return t;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---- Sum ----------------------------------------------------------------------------------
+int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
+                    int64_t nbatches, uint64_t* sum, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, sum != nullptr, "sum is null");
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout L;
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
+  const std::vector<int64_t> chunks = make_chunks(L, nbatches);
+  const size_t nchunks = chunks.size() - 1;
+  *sum = 0;
+  b2_timings tm{};
+  if (nchunks > 0 && L.rows() > 0) {
+    Scratch sc;
+    // double-buffered chunk slots + one partial per chunk
+    int64_t slot_rows = 0;
+    for (size_t k = 0; k < nchunks; ++k)
+      slot_rows = std::max(slot_rows, L.off[(size_t)chunks[k + 1]] - L.off[(size_t)chunks[k]]);
+    const int nslots = nchunks > 1 ? 3 : 1;
+    uint32_t* d_slots = nullptr;
+    uint64_t* d_part = nullptr;
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_slots, (size_t)slot_rows * 4 * nslots));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_part, nchunks * 8));
+    std::vector<cudaEvent_t> up_done(nchunks), k_begin(nchunks), k_end(nchunks);
+    cudaEvent_t c_begin, c_end;
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_begin, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_end, true));
+    PhaseTimer work;
+    B2_CUDA_OK(ctx, cudaEventRecord(c_begin, ctx->s_copy_in));
+    for (size_t k = 0; k < nchunks; ++k) {
+      B2_RETURN_NOT_OK(sc.event(ctx, &up_done[k], false));
+      B2_RETURN_NOT_OK(sc.event(ctx, &k_begin[k], true));
+      B2_RETURN_NOT_OK(sc.event(ctx, &k_end[k], true));
+      uint32_t* slot = d_slots + (size_t)(k % nslots) * slot_rows;
+      // the slot is free once the kernel that used it (chunk k - nslots) has finished
+      if (k >= (size_t)nslots) B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_copy_in, k_end[k - nslots], 0));
+      // upload with a layout rebased to the slot
+      const int64_t row0 = L.off[(size_t)chunks[k]];
+      B2_RETURN_NOT_OK(upload(ctx, slot - row0, L, batch_ptrs, chunks[k], chunks[k + 1],
+                              ctx->s_copy_in, &tm.h2d_bytes));
+      B2_CUDA_OK(ctx, cudaEventRecord(up_done[k], ctx->s_copy_in));
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_compute, up_done[k], 0));
+      B2_CUDA_OK(ctx, cudaEventRecord(k_begin[k], ctx->s_compute));
+      B2_RETURN_NOT_OK(b2_sum_u32_dev(ctx, slot, L.off[(size_t)chunks[k + 1]] - row0, d_part + k,
+                                      ctx->s_compute));
+      B2_CUDA_OK(ctx, cudaEventRecord(k_end[k], ctx->s_compute));
+      work.spans.push_back({k_begin[k], k_end[k]});
+    }
+    B2_CUDA_OK(ctx, cudaEventRecord(c_end, ctx->s_copy_in));
+    std::vector<uint64_t> parts(nchunks);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(parts.data(), d_part, nchunks * 8, cudaMemcpyDeviceToHost,
+                                    ctx->s_compute));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_compute));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_copy_in));
+    for (uint64_t p : parts) *sum += p;  // host adds the partials, as aggr_dpu.cc:82-84
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c_begin, c_end);
+    tm.copy_to_dev_ms = ms;
+    tm.dev_work_ms = work.total_ms();
+    tm.d2h_bytes = (int64_t)nchunks * 8;
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+// ---- Filter -------------------------------------------------------------------------------
+int b2_filter_lt_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
+                          const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                          int64_t* out_counts, uint64_t* total, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, nbatches == 0 || out_counts != nullptr, "out_counts is null");
+  Layout L;
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
+  const std::vector<int64_t> chunks = make_chunks(L, nbatches);
+  const size_t nchunks = chunks.size() - 1;
+  b2_timings tm{};
+  b2_pending* pend = new b2_pending();
+  pend->kind = b2_pending::kFilter;
+  pend->batch_end.assign((size_t)nbatches, 0);
+  ctx->pending = pend;
+  if (total) *total = 0;
+  if (nbatches > 0) {
+    Scratch sc;
+    const int64_t n = L.rows();
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    int64_t *d_end = nullptr, *d_off = nullptr, *d_carry = nullptr;
+    void* d_ws = nullptr;
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_in, (size_t)n * 4));
+    B2_RETURN_NOT_OK(dev_alloc(ctx, (void**)&d_out, (size_t)n * 4));
+    pend->dev.push_back(d_out);
+    pend->d_out = d_out;
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_end, (size_t)nbatches * 8));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_carry, (nchunks + 1) * 8));
+    B2_CUDA_OK(ctx, cudaMemsetAsync(d_carry, 0, 8, ctx->s_compute));
+    size_t ws_bytes = 0;
+    for (size_t k = 0; k < nchunks; ++k) {
+      const int64_t nb = chunks[k + 1] - chunks[k];
+      const size_t w = L.uniform ? b2_filter_ws_bytes(nb, L.batch_len)
+                                 : b2_filter_ragged_ws_bytes(&L.off[(size_t)chunks[k]], nb);
+      ws_bytes = std::max(ws_bytes, b2_align_up(w, 256));
+    }
+    B2_RETURN_NOT_OK(sc.alloc(ctx, &d_ws, ws_bytes * 2));  // alternate: memset of k+1 vs kernel k
+    if (!L.uniform) {
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_off, (size_t)(nbatches + 1) * 8));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_off, L.off.data(), (size_t)(nbatches + 1) * 8,
+                                      cudaMemcpyHostToDevice, ctx->s_compute));
+    }
+    cudaEvent_t c_begin, c_end;
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_begin, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_end, true));
+    PhaseTimer work;
+    B2_CUDA_OK(ctx, cudaEventRecord(c_begin, ctx->s_copy_in));
+    for (size_t k = 0; k < nchunks; ++k) {
+      cudaEvent_t up_done, kb, ke;
+      B2_RETURN_NOT_OK(sc.event(ctx, &up_done, false));
+      B2_RETURN_NOT_OK(sc.event(ctx, &kb, true));
+      B2_RETURN_NOT_OK(sc.event(ctx, &ke, true));
+      B2_RETURN_NOT_OK(upload(ctx, d_in, L, batch_ptrs, chunks[k], chunks[k + 1], ctx->s_copy_in,
+                              &tm.h2d_bytes));
+      B2_CUDA_OK(ctx, cudaEventRecord(up_done, ctx->s_copy_in));
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_compute, up_done, 0));
+      B2_CUDA_OK(ctx, cudaEventRecord(kb, ctx->s_compute));
+      const int64_t b0 = chunks[k], nb = chunks[k + 1] - chunks[k];
+      void* ws_k = static_cast<char*>(d_ws) + (k & 1) * ws_bytes;
+      int rc;
+      // chunk k continues the output where chunk k-1 stopped: its running count is seeded from
+      // d_carry[k] (device side, no host round trip) and it leaves its own total in d_carry[k+1]
+      if (L.uniform) {
+        rc = b2_filter_lt_u32_dev(ctx, d_in + L.off[(size_t)b0], nb, L.batch_len, threshold, d_out,
+                                  d_end + b0, d_carry + k + 1, d_carry + k, ws_k, ws_bytes,
+                                  ctx->s_compute);
+      } else {
+        rc = b2_filter_lt_u32_ragged_dev(ctx, d_in, &L.off[(size_t)b0], d_off + b0, nb, threshold,
+                                         d_out, d_end + b0, d_carry + k + 1, d_carry + k, ws_k,
+                                         ws_bytes, ctx->s_compute);
+      }
+      B2_RETURN_NOT_OK(rc);
+      B2_CUDA_OK(ctx, cudaEventRecord(ke, ctx->s_compute));
+      work.spans.push_back({kb, ke});
+    }
+    B2_CUDA_OK(ctx, cudaEventRecord(c_end, ctx->s_copy_in));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(pend->batch_end.data(), d_end, (size_t)nbatches * 8,
+                                    cudaMemcpyDeviceToHost, ctx->s_compute));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_compute));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_copy_in));
+    int64_t prev = 0;
+    for (int64_t b = 0; b < nbatches; ++b) {
+      out_counts[b] = pend->batch_end[(size_t)b] - prev;
+      prev = pend->batch_end[(size_t)b];
+    }
+    if (total) *total = (uint64_t)prev;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c_begin, c_end);
+    tm.copy_to_dev_ms = ms;
+    tm.dev_work_ms = work.total_ms();
+    tm.d2h_bytes = nbatches * 8;
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_filter_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int64_t nbatches,
+                         b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  b2_pending* pend = ctx->pending;
+  if (!pend || pend->kind != b2_pending::kFilter)
+    return b2_set_error(ctx, B2_ERR_INVALID, "b2_filter_fetch_host", "no pending filter result");
+  B2_REQUIRE(ctx, nbatches == (int64_t)pend->batch_end.size(), "batch count differs from the run");
+  B2_REQUIRE(ctx, nbatches == 0 || out_ptrs != nullptr, "out_ptrs is null");
+  b2_timings tm{};
+  if (nbatches > 0) {
+    Layout R;  // layout of the compacted result: batch b = [end[b-1], end[b])
+    R.off.assign((size_t)nbatches + 1, 0);
+    for (int64_t b = 0; b < nbatches; ++b) R.off[(size_t)b + 1] = pend->batch_end[(size_t)b];
+    for (int64_t b = 0; b < nbatches; ++b)
+      B2_REQUIRE(ctx, R.off[(size_t)b + 1] == R.off[(size_t)b] || out_ptrs[b] != nullptr,
+                 "null output pointer for a non-empty chunk");
+    cudaEvent_t e0, e1;
+    Scratch sc;
+    B2_RETURN_NOT_OK(sc.event(ctx, &e0, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &e1, true));
+    B2_CUDA_OK(ctx, cudaEventRecord(e0, ctx->s_copy_out));
+    B2_RETURN_NOT_OK(download(ctx, pend->d_out, R, out_ptrs, 0, nbatches, ctx->s_copy_out, &tm.d2h_bytes));
+    B2_CUDA_OK(ctx, cudaEventRecord(e1, ctx->s_copy_out));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_copy_out));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    tm.copy_from_dev_ms = ms;
+  }
+  tm.total_ms = ms_since(t0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+// ---- Take ---------------------------------------------------------------------------------
+int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64_t* value_lens,
+                     const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
+                     uint32_t* const* out_ptrs, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout V, I;
+  B2_RETURN_NOT_OK(make_layout(ctx, value_ptrs, value_lens, nbatches, &V));
+  B2_RETURN_NOT_OK(make_layout(ctx, idx_ptrs, idx_lens, nbatches, &I));
+  B2_REQUIRE(ctx, nbatches == 0 || out_ptrs != nullptr, "out_ptrs is null");
+  for (int64_t b = 0; b < nbatches; ++b) {
+    B2_REQUIRE(ctx, idx_lens[b] == 0 || out_ptrs[b] != nullptr, "null output pointer");
+    B2_REQUIRE(ctx, idx_lens[b] == 0 || value_lens[b] > 0, "indices into an empty values batch");
+  }
+  b2_timings tm{};
+  if (nbatches > 0 && I.rows() > 0) {
+    Scratch sc;
+    const bool uniform = V.uniform && I.uniform;
+    // chunk on the values layout (the larger side); indices follow the same batch ranges
+    const std::vector<int64_t> chunks = make_chunks(V, nbatches);
+    const size_t nchunks = chunks.size() - 1;
+    uint32_t *d_v = nullptr, *d_i = nullptr, *d_o = nullptr;
+    int64_t *d_voff = nullptr, *d_ioff = nullptr;
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_v, (size_t)V.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_i, (size_t)I.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_o, (size_t)I.rows() * 4));
+    if (!uniform) {
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_voff, (size_t)(nbatches + 1) * 8));
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_ioff, (size_t)(nbatches + 1) * 8));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_voff, V.off.data(), (size_t)(nbatches + 1) * 8,
+                                      cudaMemcpyHostToDevice, ctx->s_compute));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_ioff, I.off.data(), (size_t)(nbatches + 1) * 8,
+                                      cudaMemcpyHostToDevice, ctx->s_compute));
+    }
+    cudaEvent_t c_begin, c_end, o_begin, o_end;
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_begin, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_end, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &o_begin, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &o_end, true));
+    PhaseTimer work;
+    B2_CUDA_OK(ctx, cudaEventRecord(c_begin, ctx->s_copy_in));
+    for (size_t k = 0; k < nchunks; ++k) {
+      cudaEvent_t up_done, kb, ke;
+      B2_RETURN_NOT_OK(sc.event(ctx, &up_done, false));
+      B2_RETURN_NOT_OK(sc.event(ctx, &kb, true));
+      B2_RETURN_NOT_OK(sc.event(ctx, &ke, true));
+      const int64_t b0 = chunks[k], b1 = chunks[k + 1];
+      B2_RETURN_NOT_OK(upload(ctx, d_v, V, value_ptrs, b0, b1, ctx->s_copy_in, &tm.h2d_bytes));
+      B2_RETURN_NOT_OK(upload(ctx, d_i, I, idx_ptrs, b0, b1, ctx->s_copy_in, &tm.h2d_bytes));
+      B2_CUDA_OK(ctx, cudaEventRecord(up_done, ctx->s_copy_in));
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_compute, up_done, 0));
+      B2_CUDA_OK(ctx, cudaEventRecord(kb, ctx->s_compute));
+      if (uniform) {
+        B2_RETURN_NOT_OK(b2_take_u32_dev(ctx, d_v + V.off[(size_t)b0], V.batch_len,
+                                         d_i + I.off[(size_t)b0], I.batch_len, b1 - b0,
+                                         d_o + I.off[(size_t)b0], ctx->s_compute));
+      } else if (I.off[(size_t)b1] > I.off[(size_t)b0]) {
+        // offset tables are global, so run over [0, idx_off[b1]) restricted by pointer shift:
+        // the ragged kernel binary-searches the global table, so pass the whole table and range
+        B2_RETURN_NOT_OK(b2_take_u32_ragged_dev(ctx, d_v, d_voff, d_i, d_ioff, nbatches,
+                                                      I.off[(size_t)b0], I.off[(size_t)b1], d_o,
+                                                      ctx->s_compute));
+      }
+      B2_CUDA_OK(ctx, cudaEventRecord(ke, ctx->s_compute));
+      work.spans.push_back({kb, ke});
+      // download this chunk's result while the next chunk uploads / computes
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_copy_out, ke, 0));
+      if (k == 0) B2_CUDA_OK(ctx, cudaEventRecord(o_begin, ctx->s_copy_out));
+      B2_RETURN_NOT_OK(download(ctx, d_o, I, out_ptrs, b0, b1, ctx->s_copy_out, &tm.d2h_bytes));
+    }
+    B2_CUDA_OK(ctx, cudaEventRecord(c_end, ctx->s_copy_in));
+    B2_CUDA_OK(ctx, cudaEventRecord(o_end, ctx->s_copy_out));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_copy_out));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_compute));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_copy_in));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c_begin, c_end);
+    tm.copy_to_dev_ms = ms;
+    cudaEventElapsedTime(&ms, o_begin, o_end);
+    tm.copy_from_dev_ms = ms;
+    tm.dev_work_ms = work.total_ms();
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+}  // extern "C"

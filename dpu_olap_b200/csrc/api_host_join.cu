@@ -1,0 +1,312 @@
+// api_host_join.cu — host-buffer entry points of Partition and Join: what PartitionDpu::Run
+// (host/partition/partition_dpu.cc:31-135) and JoinDpu::Run (host/join/join_dpu.cc:158-400) did
+// with DpuSet transfers. Columns are uploaded once, the whole operator runs on the device, and
+// the result stays there until the caller — who can only size its buffers afterwards — fetches it.
+#include <chrono>
+#include <vector>
+
+#include "common.cuh"
+#include "pending.h"
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+}
+
+int ensure_streams(b2_ctx* ctx) {
+  B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->s_compute) B2_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+  if (!ctx->s_copy_in) B2_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_copy_in, cudaStreamNonBlocking));
+  if (!ctx->s_copy_out) B2_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->s_copy_out, cudaStreamNonBlocking));
+  return B2_OK;
+}
+
+struct DevBufs {  // frees everything not released
+  std::vector<void*> bufs;
+  ~DevBufs() {
+    for (void* p : bufs)
+      if (p) cudaFree(p);
+  }
+  int alloc(b2_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    B2_CUDA_OK(ctx, cudaMalloc(p, bytes ? bytes : 256));
+    bufs.push_back(*p);
+    return B2_OK;
+  }
+  void release(void* p) {
+    for (auto& q : bufs)
+      if (q == p) q = nullptr;
+  }
+};
+
+// Upload one column given as nbatches host buffers into a packed device column.
+int upload_column(b2_ctx* ctx, uint32_t* d_col, const uint32_t* const* ptrs, const int64_t* lens,
+                  int64_t nbatches, cudaStream_t s, int64_t* bytes) {
+  int64_t off = 0, b = 0;
+  while (b < nbatches) {
+    int64_t e = b + 1, rows = lens[b];
+    while (e < nbatches && ptrs[e] == ptrs[e - 1] + lens[e - 1]) rows += lens[e++];
+    if (rows > 0) {
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_col + off, ptrs[b], (size_t)rows * 4, cudaMemcpyHostToDevice, s));
+      *bytes += rows * 4;
+    }
+    off += rows;
+    b = e;
+  }
+  return B2_OK;
+}
+
+int total_rows(b2_ctx* ctx, const int64_t* lens, int64_t nbatches, int64_t* n) {
+  *n = 0;
+  for (int64_t b = 0; b < nbatches; ++b) {
+    B2_REQUIRE(ctx, lens[b] >= 0, "negative batch length");
+    *n += lens[b];
+  }
+  return B2_OK;
+}
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+  int init(b2_ctx* ctx) {
+    B2_CUDA_OK(ctx, cudaEventCreate(&a));
+    B2_CUDA_OK(ctx, cudaEventCreate(&b));
+    return B2_OK;
+  }
+  double ms() const {
+    float t = 0;
+    cudaEventElapsedTime(&t, a, b);
+    return t;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int b2_partition_u32_host(b2_ctx* ctx, const uint32_t* const* col_batch_ptrs,
+                          const int64_t* batch_lens, int64_t nbatches, int ncols, int key_col,
+                          int nparts, int64_t* part_rows, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, nbatches >= 0 && ncols >= 1 && ncols <= 16, "bad shape");
+  B2_REQUIRE(ctx, key_col >= 0 && key_col < ncols, "key column out of range");
+  B2_REQUIRE(ctx, nparts >= 1 && (nparts & (nparts - 1)) == 0, "nparts must be a power of two");
+  B2_REQUIRE(ctx, part_rows != nullptr, "part_rows is null");
+  B2_REQUIRE(ctx, nbatches == 0 || (col_batch_ptrs && batch_lens), "null batch table");
+  int64_t n = 0;
+  B2_RETURN_NOT_OK(total_rows(ctx, batch_lens, nbatches, &n));
+  b2_timings tm{};
+  DevBufs bufs;
+  EventPair up, work;
+  B2_RETURN_NOT_OK(up.init(ctx));
+  B2_RETURN_NOT_OK(work.init(ctx));
+  cudaStream_t s = ctx->s_compute;
+  std::vector<uint32_t*> d_in((size_t)ncols), d_out((size_t)ncols);
+  B2_CUDA_OK(ctx, cudaEventRecord(up.a, s));
+  for (int c = 0; c < ncols; ++c) {
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_in[(size_t)c], (size_t)n * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_out[(size_t)c], (size_t)n * 4));
+    B2_RETURN_NOT_OK(upload_column(ctx, d_in[(size_t)c], col_batch_ptrs + (size_t)c * nbatches,
+                                   batch_lens, nbatches, s, &tm.h2d_bytes));
+  }
+  B2_CUDA_OK(ctx, cudaEventRecord(up.b, s));
+  // the C ABI wants the key column first
+  std::vector<const uint32_t*> in_order;
+  std::vector<uint32_t*> out_order;
+  in_order.push_back(d_in[(size_t)key_col]);
+  out_order.push_back(d_out[(size_t)key_col]);
+  for (int c = 0; c < ncols; ++c)
+    if (c != key_col) {
+      in_order.push_back(d_in[(size_t)c]);
+      out_order.push_back(d_out[(size_t)c]);
+    }
+  void* d_ws = nullptr;
+  int64_t* d_off = nullptr;
+  const size_t ws_bytes = b2_partition_ws_bytes(n, nparts);
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_ws, ws_bytes));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_off, ((size_t)nparts + 1) * 8));
+  B2_CUDA_OK(ctx, cudaEventRecord(work.a, s));
+  B2_RETURN_NOT_OK(b2_partition_u32_dev(ctx, in_order.data(), out_order.data(), ncols, n, nparts, 0,
+                                        d_off, d_ws, ws_bytes, s));
+  B2_CUDA_OK(ctx, cudaEventRecord(work.b, s));
+  b2_pending* pend = new b2_pending();
+  pend->kind = b2_pending::kPartition;
+  pend->ncols = ncols;
+  pend->part_off.assign((size_t)nparts + 1, 0);
+  ctx->pending = pend;
+  B2_CUDA_OK(ctx, cudaMemcpyAsync(pend->part_off.data(), d_off, ((size_t)nparts + 1) * 8,
+                                  cudaMemcpyDeviceToHost, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  for (int p = 0; p < nparts; ++p) part_rows[p] = pend->part_off[(size_t)p + 1] - pend->part_off[(size_t)p];
+  for (int c = 0; c < ncols; ++c) {
+    pend->d_cols.push_back(d_out[(size_t)c]);
+    pend->dev.push_back(d_out[(size_t)c]);
+    bufs.release(d_out[(size_t)c]);
+  }
+  tm.copy_to_dev_ms = up.ms();
+  tm.dev_work_ms = work.ms();
+  tm.d2h_bytes = ((int64_t)nparts + 1) * 8;
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_partition_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int nparts, int ncols,
+                            b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  b2_pending* pend = ctx->pending;
+  if (!pend || pend->kind != b2_pending::kPartition)
+    return b2_set_error(ctx, B2_ERR_INVALID, "b2_partition_fetch_host", "no pending partition result");
+  B2_REQUIRE(ctx, nparts + 1 == (int)pend->part_off.size() && ncols == pend->ncols,
+             "shape differs from the run");
+  B2_REQUIRE(ctx, out_ptrs != nullptr, "out_ptrs is null");
+  b2_timings tm{};
+  EventPair ev;
+  B2_RETURN_NOT_OK(ev.init(ctx));
+  cudaStream_t s = ctx->s_copy_out;
+  B2_CUDA_OK(ctx, cudaEventRecord(ev.a, s));
+  for (int p = 0; p < nparts; ++p) {
+    const int64_t r0 = pend->part_off[(size_t)p], rows = pend->part_off[(size_t)p + 1] - r0;
+    if (rows == 0) continue;
+    for (int c = 0; c < ncols; ++c) {
+      uint32_t* dst = out_ptrs[(size_t)p * ncols + c];
+      B2_REQUIRE(ctx, dst != nullptr, "null output pointer for a non-empty partition");
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(dst, pend->d_cols[(size_t)c] + r0, (size_t)rows * 4,
+                                      cudaMemcpyDeviceToHost, s));
+      tm.d2h_bytes += rows * 4;
+    }
+  }
+  B2_CUDA_OK(ctx, cudaEventRecord(ev.b, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  tm.copy_from_dev_ms = ev.ms();
+  tm.total_ms = ms_since(t0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* l_lens,
+                     int64_t nl_batches, const uint32_t* const* r_ptrs, const int64_t* r_lens,
+                     int64_t nr_batches, uint64_t* out_rows, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, nl_batches >= 0 && nr_batches >= 0, "negative batch count");
+  B2_REQUIRE(ctx, out_rows != nullptr, "out_rows is null");
+  B2_REQUIRE(ctx, nl_batches == 0 || (l_ptrs && l_lens), "null left batch table");
+  B2_REQUIRE(ctx, nr_batches == 0 || (r_ptrs && r_lens), "null right batch table");
+  int64_t nl = 0, nr = 0;
+  B2_RETURN_NOT_OK(total_rows(ctx, l_lens, nl_batches, &nl));
+  B2_RETURN_NOT_OK(total_rows(ctx, r_lens, nr_batches, &nr));
+  b2_timings tm{};
+  DevBufs bufs;
+  EventPair up, work;
+  B2_RETURN_NOT_OK(up.init(ctx));
+  B2_RETURN_NOT_OK(work.init(ctx));
+  cudaStream_t s = ctx->s_compute;
+  uint32_t *d_fk, *d_y, *d_pk, *d_x;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_fk, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_y, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_pk, (size_t)nr * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_x, (size_t)nr * 4));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.a, s));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_fk, l_ptrs, l_lens, nl_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_y, l_ptrs + nl_batches, l_lens, nl_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_pk, r_ptrs, r_lens, nr_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_x, r_ptrs + nr_batches, r_lens, nr_batches, s, &tm.h2d_bytes));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.b, s));
+
+  // PK-FK joins produce at most nl rows; duplicate build keys can produce more, in which case the
+  // join is re-run with the exact capacity it reported.
+  int64_t cap = nl;
+  void* d_ws = nullptr;
+  const size_t ws_bytes = b2_join_ws_bytes(nl, nr);
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_ws, ws_bytes));
+  uint64_t* d_rows = nullptr;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_rows, 8));
+  uint32_t *o_fk = nullptr, *o_y = nullptr, *o_x = nullptr;
+  uint64_t rows = 0;
+  B2_CUDA_OK(ctx, cudaEventRecord(work.a, s));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_fk, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_y, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_x, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(b2_join_u32_dev(ctx, d_fk, d_y, nl, d_pk, d_x, nr, o_fk, o_y, o_x, cap, d_rows,
+                                     0, d_ws, ws_bytes, s));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(&rows, d_rows, 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    if (rows == ~0ull) return b2_set_error(ctx, B2_ERR_WORKSPACE, "join", "slice overflow");
+    if ((int64_t)rows <= cap) break;
+    if (attempt == 1) return b2_set_error(ctx, B2_ERR_OVERFLOW, "join", "output larger than reported");
+    for (uint32_t* p : {o_fk, o_y, o_x}) {
+      bufs.release(p);
+      cudaFree(p);
+    }
+    cap = (int64_t)rows;
+  }
+  B2_CUDA_OK(ctx, cudaEventRecord(work.b, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  b2_pending* pend = new b2_pending();
+  pend->kind = b2_pending::kJoin;
+  pend->d_fk = o_fk;
+  pend->d_y = o_y;
+  pend->d_x = o_x;
+  pend->rows = rows;
+  for (uint32_t* p : {o_fk, o_y, o_x}) {
+    pend->dev.push_back(p);
+    bufs.release(p);
+  }
+  ctx->pending = pend;
+  *out_rows = rows;
+  tm.copy_to_dev_ms = up.ms();
+  tm.dev_work_ms = work.ms();
+  tm.d2h_bytes = 8;
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
+                       int64_t capacity_rows, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  b2_pending* pend = ctx->pending;
+  if (!pend || pend->kind != b2_pending::kJoin)
+    return b2_set_error(ctx, B2_ERR_INVALID, "b2_join_fetch_host", "no pending join result");
+  if ((uint64_t)capacity_rows < pend->rows)
+    return b2_set_error(ctx, B2_ERR_OVERFLOW, "b2_join_fetch_host", "capacity_rows < result rows");
+  b2_timings tm{};
+  if (pend->rows > 0) {
+    B2_REQUIRE(ctx, out_fk && out_y && out_x, "null output column");
+    EventPair ev;
+    B2_RETURN_NOT_OK(ev.init(ctx));
+    cudaStream_t s = ctx->s_copy_out;
+    const size_t bytes = (size_t)pend->rows * 4;
+    B2_CUDA_OK(ctx, cudaEventRecord(ev.a, s));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(out_fk, pend->d_fk, bytes, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(out_y, pend->d_y, bytes, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(out_x, pend->d_x, bytes, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaEventRecord(ev.b, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    tm.copy_from_dev_ms = ev.ms();
+    tm.d2h_bytes = (int64_t)bytes * 3;
+  }
+  tm.total_ms = ms_since(t0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+}  // extern "C"

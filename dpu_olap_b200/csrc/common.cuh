@@ -1,0 +1,143 @@
+// common.cuh — shared device helpers and the context object of libb200olap.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/b200olap.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb200olap is written for sm_100a (B200) only"
+#endif
+
+// ---- context -----------------------------------------------------------------------------
+struct b2_pending;  // device-resident result of the last *_host call (api_host.cu)
+
+struct b2_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string last_error;
+  // small persistent device scratch: [0..4095] sum partials (u64) | ticket counters
+  void* d_small = nullptr;
+  size_t small_bytes = 0;
+  // growable device workspace used by the *_host layer
+  void* d_ws = nullptr;
+  size_t ws_bytes = 0;
+  // host layer
+  cudaStream_t s_compute = nullptr;
+  cudaStream_t s_copy_in = nullptr;
+  cudaStream_t s_copy_out = nullptr;
+  void* h_pinned = nullptr;  // pinned staging ring
+  size_t pinned_bytes = 0;
+  b2_pending* pending = nullptr;
+};
+
+int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail);
+
+#define B2_CUDA_OK(ctx, expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      return b2_set_error((ctx), _e == cudaErrorMemoryAllocation ? B2_ERR_OOM : B2_ERR_CUDA, \
+                          #expr, cudaGetErrorString(_e));                            \
+    }                                                                                \
+  } while (0)
+
+#define B2_RETURN_NOT_OK(expr) \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != B2_OK) return _s; \
+  } while (0)
+
+#define B2_REQUIRE(ctx, cond, msg)                                        \
+  do {                                                                    \
+    if (!(cond)) return b2_set_error((ctx), B2_ERR_INVALID, #cond, (msg)); \
+  } while (0)
+
+#define B2_LAUNCH_CHECK(ctx, name)                                             \
+  do {                                                                         \
+    cudaError_t _e = cudaGetLastError();                                       \
+    if (_e != cudaSuccess)                                                     \
+      return b2_set_error((ctx), B2_ERR_CUDA, name, cudaGetErrorString(_e));   \
+    (ctx)->launches++;                                                         \
+  } while (0)
+
+static inline size_t b2_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers ----------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Streaming 128-bit load: read-only path, do not allocate in L1 (each byte is touched once).
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_stream_v2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+// Streaming stores: write-once data, keep it out of L1.
+__device__ __forceinline__ void st_stream_v4(uint4* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream_v2(uint2* p, uint2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Single-word (status|value) tile descriptors of the decoupled look-back scan: a relaxed
+// gpu-scope 64-bit access is atomic, so no fence is needed between status and value.
+__device__ __forceinline__ uint64_t ld_relaxed_gpu_u64(const uint64_t* p) {
+  uint64_t r;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Thomas Wang's 32-bit integer hash exactly as the reference uses it for partitioning and for
+// its hash table (dpu/shared/kernels/partition.c:20-28, dpu/shared/hashtable/hashtable.c:29-37).
+__host__ __device__ __forceinline__ uint32_t wang_hash_u32(uint32_t key) {
+  key += ~(key << 15);
+  key ^= (key >> 10);
+  key += (key << 3);
+  key ^= (key >> 6);
+  key += ~(key << 11);
+  key ^= (key >> 16);
+  return key;
+}
+
+__device__ __forceinline__ uint64_t warp_reduce_sum_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_reduce_sum_u32(uint32_t v) {
+  return __reduce_add_sync(0xffffffffu, v);
+}
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+#endif  // __CUDACC__

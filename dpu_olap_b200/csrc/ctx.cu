@@ -1,0 +1,91 @@
+// ctx.cu — context lifetime, status strings. Replaces dpu::DpuSet::allocate/load/~DpuSet
+// (reference host/dpuext/dpuext.hpp:669-739): a ctx is bound to one B200 and owns its streams,
+// scratch and any pending device-resident result.
+#include "common.cuh"
+
+void b2_pending_free(b2_ctx* ctx);  // api_host.cu
+
+int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail) {
+  if (ctx) {
+    ctx->last_error = std::string(b2_strerror(status)) + ": " + (what ? what : "") +
+                      (detail ? std::string(" — ") + detail : std::string());
+  }
+  return status;
+}
+
+extern "C" {
+
+int b2_version(void) { return B2_VERSION; }
+
+const char* b2_strerror(int status) {
+  switch (status) {
+    case B2_OK: return "ok";
+    case B2_ERR_INVALID: return "invalid argument";
+    case B2_ERR_CUDA: return "CUDA error";
+    case B2_ERR_OOM: return "out of memory";
+    case B2_ERR_UNSUPPORTED: return "unsupported";
+    case B2_ERR_WORKSPACE: return "workspace too small";
+    case B2_ERR_OVERFLOW: return "output capacity exceeded";
+    default: return "unknown status";
+  }
+}
+
+int b2_device_count(int* count) {
+  if (!count) return B2_ERR_INVALID;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return B2_ERR_CUDA;
+  }
+  *count = n;
+  return B2_OK;
+}
+
+int b2_ctx_create(int device, b2_ctx** out) {
+  if (!out) return B2_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return B2_ERR_CUDA;
+  if (device < 0 || device >= n) return B2_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2_ERR_CUDA;
+  if (prop.major < 10) {
+    fprintf(stderr, "b200olap: device %d is sm_%d%d; this library is built for sm_100a only\n",
+            device, prop.major, prop.minor);
+    return B2_ERR_UNSUPPORTED;
+  }
+  b2_ctx* ctx = new b2_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->small_bytes = 64 * 1024;
+  if (cudaMalloc(&ctx->d_small, ctx->small_bytes) != cudaSuccess ||
+      cudaMemset(ctx->d_small, 0, ctx->small_bytes) != cudaSuccess) {
+    delete ctx;
+    return B2_ERR_OOM;
+  }
+  *out = ctx;
+  return B2_OK;
+}
+
+int b2_ctx_destroy(b2_ctx* ctx) {
+  if (!ctx) return B2_OK;
+  cudaSetDevice(ctx->device);
+  b2_pending_free(ctx);
+  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->s_copy_in) cudaStreamDestroy(ctx->s_copy_in);
+  if (ctx->s_copy_out) cudaStreamDestroy(ctx->s_copy_out);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->d_ws) cudaFree(ctx->d_ws);
+  if (ctx->d_small) cudaFree(ctx->d_small);
+  delete ctx;
+  return B2_OK;
+}
+
+const char* b2_last_error(const b2_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+int64_t b2_launch_count(const b2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int b2_ctx_device(const b2_ctx* ctx) { return ctx ? ctx->device : -1; }
+int b2_ctx_sm_count(const b2_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// join.cu — inner equi-join L.fk = R.pk over uint32 keys with one uint32 payload per side.
+//
+// Replaces the reference's DPU join: JoinDpu::Run_internal (host/join/join_dpu.cc:168-400) moves
+// every column four times across the DDR bus (partition, take, build/probe, take); on the DPU,
+// kernel_hash_build (dpu/shared/kernels/hash_build.c:9-35) inserts key -> row index into an
+// MRAM linear-probing table under 16 hardware mutexes (ht_put, dpu/shared/hashtable/
+// hashtable.c:89-165, duplicate keys overwrite :133), kernel_hash_probe (hash_probe.c:9-46,
+// ht_get hashtable.c:167-192) emits the matching row index and ASSERTS every probe hits
+// (hash_probe.c:32-33), and a separate take pass gathers the payload (join_dpu.cc:303-368).
+//
+// Semantics here are Arrow's inner hash join (host/join/join_native.cc:31-36), which the
+// reference's tests use as the oracle: unmatched probe rows are dropped, duplicate build keys
+// produce one output row per duplicate. Output columns (fk, y, x); row order unspecified.
+//
+// B200 design:
+//   1. both sides are radix-partitioned on the same hash bits (partition.cu) into partitions of
+//      ~4096 build rows, carrying (key, payload) pairs — the payload travels with the key, so
+//      there is no row-index vector and no take pass;
+//   2. join_probe_kernel: one CTA per partition builds a linear-probing table of the build side
+//      in SHARED memory (8192 slots, 64 KB, load factor ~0.5; 32-bit atomicCAS on the key word),
+//      then streams the probe side through it and writes (fk, y, x) with coalesced stores; the
+//      output range of every 2048-row probe tile is reserved with one 64-bit atomicAdd.
+//      The "empty" marker of a partition's table is a key that hashes to ANOTHER partition
+//      (wang_hash is a bijection), so all 2^32 key values are legal.
+//      Build partitions larger than the table (skew, heavy duplicates) are processed in chunks,
+//      each chunk probed by the whole probe partition.
+//   3. when the workspace is too small to hold both partitioned sides at once (SF=2048 on one
+//      GPU), the join runs in hash-space slices: slice s only partitions and joins the rows whose
+//      top hash bits equal s.
+#include <algorithm>
+
+#include "partition.cuh"
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSlotBits = 13;
+constexpr int kSlots = 1 << kSlotBits;         // 8192 slots = 64 KB (keys + values)
+constexpr int kMaxBuild = (kSlots * 3) / 4;    // rows per build chunk (load factor <= 0.75)
+constexpr int kTargetBuild = 4096;             // mean build rows per partition
+constexpr int kProbeItems = 4;                 // probe rows per thread per tile
+constexpr int kProbeTile = kThreads * kProbeItems;
+
+struct JoinState {  // lives in the workspace header
+  unsigned long long out_rows;
+  unsigned int overflow;
+  unsigned int pad;
+};
+
+__device__ __forceinline__ uint32_t slot_hash(uint32_t key) {
+  // partition bits are the TOP bits of wang_hash, identical inside a partition; the multiply
+  // folds the remaining low bits into the top kSlotBits
+  return (wang_hash_u32(key) * 0x9E3779B1u) >> (32 - kSlotBits);
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ roff,
+                  const uint2* __restrict__ lpairs, const int64_t* __restrict__ loff,
+                  int64_t nparts, int part_shl, int part_bits, uint32_t* __restrict__ out_fk,
+                  uint32_t* __restrict__ out_y, uint32_t* __restrict__ out_x, int64_t out_cap,
+                  JoinState* __restrict__ st) {
+  extern __shared__ __align__(16) uint32_t tab[];  // keys [kSlots] | values [kSlots]
+  uint32_t* __restrict__ tk = tab;
+  uint32_t* __restrict__ tv = tab + kSlots;
+  __shared__ uint32_t seg_cnt[kWarps * kProbeItems];
+  __shared__ uint32_t seg_off[kWarps * kProbeItems];
+  __shared__ unsigned long long s_base;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = lanemask_lt();
+
+  for (int64_t p = blockIdx.x; p < nparts; p += gridDim.x) {
+    const int64_t r0 = roff[p], r1 = roff[p + 1];
+    const int64_t l0 = loff[p], l1 = loff[p + 1];
+    if (r1 == r0 || l1 == l0) continue;  // inner join: nothing to emit
+    // a key that belongs to a different partition marks empty slots
+    uint32_t empty = 0xffffffffu;
+    while (part_bucket(wang_hash_u32(empty), part_shl, part_bits) == (uint32_t)p) --empty;
+
+    for (int64_t c0 = r0; c0 < r1; c0 += kMaxBuild) {
+      const int nbuild = (int)min((int64_t)kMaxBuild, r1 - c0);
+      __syncthreads();  // previous probe phase is done with the table
+      for (int i = tid; i < kSlots; i += kThreads) tk[i] = empty;
+      __syncthreads();
+      for (int i = tid; i < nbuild; i += kThreads) {
+        const uint2 kv = ld_stream_v2(rpairs + c0 + i);
+        uint32_t slot = slot_hash(kv.x);
+        while (atomicCAS(&tk[slot], empty, kv.x) != empty) slot = (slot + 1) & (kSlots - 1);
+        tv[slot] = kv.y;  // duplicates of a key take separate slots
+      }
+      __syncthreads();
+
+      for (int64_t t0 = l0; t0 < l1; t0 += kProbeTile) {
+        uint32_t key[kProbeItems], y[kProbeItems], x0[kProbeItems], m[kProbeItems];
+#pragma unroll
+        for (int q = 0; q < kProbeItems; ++q) {
+          const int64_t row = t0 + q * kThreads + tid;
+          m[q] = 0;
+          x0[q] = 0;
+          key[q] = 0;
+          y[q] = 0;
+          if (row < l1) {
+            const uint2 kv = ld_stream_v2(lpairs + row);
+            key[q] = kv.x;
+            y[q] = kv.y;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kProbeItems; ++q) {
+          const int64_t row = t0 + q * kThreads + tid;
+          if (row < l1) {
+            uint32_t slot = slot_hash(key[q]);
+            uint32_t k;
+            while ((k = tk[slot]) != empty) {
+              if (k == key[q]) {
+                if (m[q] == 0) x0[q] = tv[slot];
+                ++m[q];
+              }
+              slot = (slot + 1) & (kSlots - 1);
+            }
+          }
+        }
+        // ---- output positions: order (q, warp, lane) so stores of one q are contiguous ----
+        uint32_t lane_excl[kProbeItems];
+#pragma unroll
+        for (int q = 0; q < kProbeItems; ++q) {
+          uint32_t incl = m[q];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          lane_excl[q] = incl - m[q];
+          if (lane == 31) seg_cnt[q * kWarps + warp] = incl;
+        }
+        __syncthreads();
+        if (warp == 0) {
+          const uint32_t c0_ = seg_cnt[2 * lane], c1_ = seg_cnt[2 * lane + 1];
+          uint32_t incl = c0_ + c1_;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const uint32_t excl = incl - (c0_ + c1_);
+          seg_off[2 * lane] = excl;
+          seg_off[2 * lane + 1] = excl + c0_;
+          if (lane == 31) s_base = atomicAdd(&st->out_rows, (unsigned long long)incl);
+        }
+        __syncthreads();
+        const unsigned long long base = s_base;
+#pragma unroll
+        for (int q = 0; q < kProbeItems; ++q) {
+          if (m[q] == 0) continue;
+          unsigned long long pos = base + seg_off[q * kWarps + warp] + lane_excl[q];
+          if (m[q] == 1) {
+            if ((int64_t)pos < out_cap) {
+              st_stream_u32(out_fk + pos, key[q]);
+              st_stream_u32(out_y + pos, y[q]);
+              st_stream_u32(out_x + pos, x0[q]);
+            }
+          } else {  // duplicate build keys: enumerate every match
+            uint32_t slot = slot_hash(key[q]);
+            uint32_t k;
+            while ((k = tk[slot]) != empty) {
+              if (k == key[q]) {
+                if ((int64_t)pos < out_cap) {
+                  out_fk[pos] = key[q];
+                  out_y[pos] = y[q];
+                  out_x[pos] = tv[slot];
+                }
+                ++pos;
+              }
+              slot = (slot + 1) & (kSlots - 1);
+            }
+          }
+        }
+        // seg_cnt / seg_off / s_base are rewritten only after the next tile's first barrier
+      }
+    }
+    __syncthreads();
+  }
+  (void)lt;
+}
+
+__global__ void join_init_kernel(JoinState* st) {
+  st->out_rows = 0;
+  st->overflow = 0;
+}
+__global__ void join_finish_kernel(const JoinState* __restrict__ st, uint64_t* __restrict__ out_rows) {
+  // a partition buffer that overflowed (skewed slice) makes the result invalid: report ~0
+  *out_rows = st->overflow ? ~0ull : st->out_rows;
+}
+
+int ceil_log2_i64(int64_t v) {
+  int b = 0;
+  while (((int64_t)1 << b) < v) ++b;
+  return b;
+}
+
+struct JoinPlan {
+  int bits;        // fine partition bits
+  int slice_bits;  // log2 number of hash-space slices
+  int64_t cap_r, cap_l, cap_tmp;
+  bool two_pass;
+  size_t off_state, off_roff, off_loff, off_rout, off_lout, off_tmp, off_part, part_bytes, total;
+};
+
+JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits) {
+  JoinPlan P;
+  P.slice_bits = slice_bits;
+  const int64_t nslices = (int64_t)1 << slice_bits;
+  const int64_t nr_slice = (nr + nslices - 1) / nslices;
+  int bits = ceil_log2_i64((nr_slice + kTargetBuild - 1) / kTargetBuild);
+  bits = std::max(bits, 1);
+  bits = std::min(bits, 2 * kPartMaxBits);
+  bits = std::min(bits, 32 - skip_bits - slice_bits);
+  P.bits = std::max(bits, 1);
+  P.two_pass = P.bits > kPartMaxBits;
+  // slices are hash-uniform in expectation; leave 12.5 % + 64 Ki rows of slack for skew
+  auto cap = [&](int64_t n) {
+    if (slice_bits == 0) return n;
+    const int64_t per = (n + nslices - 1) / nslices;
+    return std::min(n, per + per / 8 + 65536);
+  };
+  P.cap_r = cap(nr);
+  P.cap_l = cap(nl);
+  P.cap_tmp = P.two_pass ? std::max(P.cap_r, P.cap_l) : 0;
+  const size_t noff = (((size_t)1 << P.bits) + 1) * 8;
+  size_t o = 0;
+  P.off_state = o; o += 256;
+  P.off_roff = o;  o += b2_align_up(noff, 256);
+  P.off_loff = o;  o += b2_align_up(noff, 256);
+  P.off_rout = o;  o += b2_align_up((size_t)P.cap_r * 8, 256);
+  P.off_lout = o;  o += b2_align_up((size_t)P.cap_l * 8, 256);
+  P.off_tmp = o;   o += b2_align_up((size_t)P.cap_tmp * 8, 256);
+  P.part_bytes = std::max(part_full_ws_bytes(nr, P.bits), part_full_ws_bytes(nl, P.bits));
+  P.off_part = o;  o += b2_align_up(P.part_bytes, 256);
+  P.total = o;
+  return P;
+}
+
+constexpr int kMaxSliceBits = 6;
+
+int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& rin, int64_t nr,
+              uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+              uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+  B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
+  B2_REQUIRE(ctx, skip_bits >= 0 && skip_bits <= 8, "hash_skip_bits must be in 0..8");
+  B2_REQUIRE(ctx, d_out_rows != nullptr, "d_out_rows is null");
+  B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
+             "workspace must be 256 B aligned");
+  B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
+  // pick the smallest number of slices whose plan fits the workspace
+  JoinPlan P = make_plan(nl, nr, skip_bits, 0);
+  int sb = 0;
+  while (P.total > ws_bytes && sb < kMaxSliceBits) P = make_plan(nl, nr, skip_bits, ++sb);
+  if (P.total > ws_bytes)
+    return b2_set_error(ctx, B2_ERR_WORKSPACE, "join workspace", "see b2_join_min_ws_bytes()");
+  char* base = static_cast<char*>(d_ws);
+  JoinState* st = reinterpret_cast<JoinState*>(base + P.off_state);
+  int64_t* roff = reinterpret_cast<int64_t*>(base + P.off_roff);
+  int64_t* loff = reinterpret_cast<int64_t*>(base + P.off_loff);
+  uint2* rout = reinterpret_cast<uint2*>(base + P.off_rout);
+  uint2* lout = reinterpret_cast<uint2*>(base + P.off_lout);
+  uint2* tmp = P.two_pass ? reinterpret_cast<uint2*>(base + P.off_tmp) : nullptr;
+  void* pws = base + P.off_part;
+
+  join_init_kernel<<<1, 1, 0, s>>>(st);
+  B2_LAUNCH_CHECK(ctx, "join_init_kernel");
+  if (nl > 0 && nr > 0) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSlots * 8));
+      attr_done = true;
+    }
+    const int64_t nparts = (int64_t)1 << P.bits;
+    const int part_shl = skip_bits + P.slice_bits;
+    for (uint32_t slice = 0; slice < (1u << P.slice_bits); ++slice) {
+      B2_RETURN_NOT_OK(part_full(ctx, rin, nr, P.bits, part_shl, skip_bits, P.slice_bits, slice,
+                                 rout, tmp, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
+      B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
+                                 lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s));
+      int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * 3);
+      join_probe_kernel<<<(unsigned)grid, kThreads, kSlots * 8, s>>>(
+          rout, roff, lout, loff, nparts, part_shl, P.bits, d_out_fk, d_out_y, d_out_x,
+          out_capacity, st);
+      B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
+    }
+  }
+  join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows);
+  B2_LAUNCH_CHECK(ctx, "join_finish_kernel");
+  return B2_OK;
+}
+
+// ---- standalone partition: permutation + gather (PartitionDpu) ------------------------------
+__global__ void __launch_bounds__(256)
+part_gather_kernel(const uint2* __restrict__ pairs, int64_t n, const uint32_t* __restrict__ col_in,
+                   uint32_t* __restrict__ col_out, int take_key) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const uint2 kv = pairs[i];
+    col_out[i] = take_key ? kv.x : __ldg(col_in + kv.y);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_pairs_kernel(const uint2* __restrict__ pairs, int64_t n, uint32_t* __restrict__ keys,
+                   uint32_t* __restrict__ vals) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const uint2 kv = pairs[i];
+    keys[i] = kv.x;
+    vals[i] = kv.y;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t b2_wang_hash_u32(uint32_t key) { return wang_hash_u32(key); }
+
+int b2_join_dest_rank(uint32_t key, int nranks) {
+  if (nranks <= 1) return 0;
+  int bits = 0;
+  while ((1 << bits) < nranks) ++bits;
+  return (int)(wang_hash_u32(key) >> (32 - bits));
+}
+
+size_t b2_join_ws_bytes(int64_t nl, int64_t nr) {
+  if (nl < 0 || nr < 0) return 0;
+  return make_plan(nl, nr, 0, 0).total;
+}
+size_t b2_join_min_ws_bytes(int64_t nl, int64_t nr) {
+  if (nl < 0 || nr < 0) return 0;
+  return make_plan(nl, nr, 0, kMaxSliceBits).total;
+}
+
+int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
+                    const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, uint32_t* d_out_fk,
+                    uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                    uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
+                    void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, nl == 0 || (d_fk && d_y), "null left column");
+  B2_REQUIRE(ctx, nr == 0 || (d_pk && d_x), "null right column");
+  PartInput lin, rin;
+  lin.keys = d_fk;
+  lin.vals = d_y;
+  rin.keys = d_pk;
+  rin.vals = d_x;
+  return join_impl(ctx, lin, nl, rin, nr, d_out_fk, d_out_y, d_out_x, out_capacity, d_out_rows,
+                   hash_skip_bits, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b2_join_pairs_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, int64_t nl, const uint64_t* d_r_pairs,
+                      int64_t nr, uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x,
+                      int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits, void* d_ws,
+                      size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, nl == 0 || d_l_pairs, "null left pairs");
+  B2_REQUIRE(ctx, nr == 0 || d_r_pairs, "null right pairs");
+  PartInput lin, rin;
+  lin.pairs = reinterpret_cast<const uint2*>(d_l_pairs);
+  rin.pairs = reinterpret_cast<const uint2*>(d_r_pairs);
+  // an empty side has no pairs pointer; part_full is never reached then (nl == 0 || nr == 0)
+  return join_impl(ctx, lin, nl, rin, nr, d_out_fk, d_out_y, d_out_x, out_capacity, d_out_rows,
+                   hash_skip_bits, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- multi-GPU shuffle: route rows to the GPU that owns their hash range --------------------
+size_t b2_shuffle_ws_bytes(int64_t n, int nranks) {
+  if (n < 0 || nranks < 1) return 0;
+  int bits = 0;
+  while ((1 << bits) < nranks) ++bits;
+  return part_full_ws_bytes(n, bits) + 256;
+}
+
+int b2_shuffle_partition_u32_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
+                                 int nranks, uint64_t* d_pairs_out, int64_t* d_dest_off, void* d_ws,
+                                 size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, n >= 0, "negative size");
+  B2_REQUIRE(ctx, nranks >= 1 && nranks <= 256 && (nranks & (nranks - 1)) == 0,
+             "nranks must be a power of two <= 256");
+  B2_REQUIRE(ctx, d_dest_off != nullptr, "d_dest_off is null");
+  B2_REQUIRE(ctx, n == 0 || (d_key && d_val && d_pairs_out), "null pointer");
+  int bits = 0;
+  while ((1 << bits) < nranks) ++bits;
+  PartInput in;
+  in.keys = d_key;
+  in.vals = d_val;
+  return part_full(ctx, in, n, bits, 0, 0, 0, 0, reinterpret_cast<uint2*>(d_pairs_out), nullptr, n,
+                   d_dest_off, nullptr, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- standalone partition (PartitionDpu) ----------------------------------------------------
+size_t b2_partition_ws_bytes(int64_t n, int nparts) {
+  if (n < 0 || nparts < 1) return 0;
+  int bits = 0;
+  while ((1 << bits) < nparts) ++bits;
+  const size_t pairs = b2_align_up((size_t)n * 8, 256);
+  return part_full_ws_bytes(n, bits) + pairs * (bits > kPartMaxBits ? 2 : 1) + 256;
+}
+
+int b2_partition_u32_dev(b2_ctx* ctx, const uint32_t* const* d_cols_in, uint32_t* const* d_cols_out,
+                         int ncols, int64_t n, int nparts, int skip_bits, int64_t* d_part_off,
+                         void* d_ws, size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, n >= 0 && n < (1ll << 32), "row count must fit the 32-bit row index");
+  B2_REQUIRE(ctx, ncols >= 1 && ncols <= 16, "1..16 columns");
+  B2_REQUIRE(ctx, nparts >= 1 && nparts <= (1 << (2 * kPartMaxBits)) && (nparts & (nparts - 1)) == 0,
+             "nparts must be a power of two <= 2^20");
+  B2_REQUIRE(ctx, skip_bits >= 0 && skip_bits <= 16, "skip_bits out of range");
+  B2_REQUIRE(ctx, d_cols_in && d_cols_out && d_part_off, "null pointer");
+  B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
+             "workspace must be 256 B aligned");
+  if (ws_bytes < b2_partition_ws_bytes(n, nparts))
+    return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition workspace", "use b2_partition_ws_bytes()");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int bits = 0;
+  while ((1 << bits) < nparts) ++bits;
+  B2_REQUIRE(ctx, bits + skip_bits <= 32, "not enough hash bits");
+  char* base = static_cast<char*>(d_ws);
+  const size_t pairs_bytes = b2_align_up((size_t)n * 8, 256);
+  uint2* pairs = reinterpret_cast<uint2*>(base);
+  uint2* tmp = bits > kPartMaxBits ? reinterpret_cast<uint2*>(base + pairs_bytes) : nullptr;
+  char* pws = base + pairs_bytes * (tmp ? 2 : 1);
+  PartInput in;
+  in.keys = d_cols_in[0];
+  in.vals = nullptr;  // carry the row index: the permutation (selection_indices_vector)
+  B2_RETURN_NOT_OK(part_full(ctx, in, n, bits, skip_bits, 0, 0, 0, pairs, tmp, n, d_part_off,
+                             nullptr, pws, ws_bytes - (size_t)(pws - base), s));
+  if (n > 0) {
+    int64_t grid = std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    for (int c = 0; c < ncols; ++c) {
+      B2_REQUIRE(ctx, d_cols_in[c] && d_cols_out[c], "null column pointer");
+      part_gather_kernel<<<(unsigned)grid, 256, 0, s>>>(pairs, n, d_cols_in[c], d_cols_out[c],
+                                                        c == 0 ? 1 : 0);
+      B2_LAUNCH_CHECK(ctx, "part_gather_kernel");
+    }
+  }
+  return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,481 @@
+// partition.cu — radix hash partitioning of (key, value) rows.
+//
+// Replaces the reference's DPU partition program (dpu/shared/kernels/partition.c:296-341):
+// build_histogram (:67-92, one mutex-protected increment per row), prefix_sum (:94-137) and
+// partition_array / write_new_output (:167-294, a mutex per row, 8-byte MRAM read-modify-write),
+// plus the host-side offset bookkeeping (Partitioner::GetOffsets, partitioner.cc:280-312) and the
+// scatter-gather DMA that brings the pieces of a partition together (LoadPartitions, :350-375).
+// The hash and bucket are the reference's: wang_hash_uint32 (partition.c:20-28) and the top bits
+// of the hash (BUCKET_OF, partition.c:45-46).
+//
+// B200 design — three kernels per pass, every row read twice (once keys-only) and written once:
+//   1. part_hist_kernel     per work unit (a run of 8192-row tiles) a histogram over the 2^bits
+//                           buckets. No atomics: __match_any_sync groups the lanes of a warp that
+//                           hit the same bucket and the group leader bumps a WARP-PRIVATE
+//                           shared-memory counter.
+//   2. exclusive scan       the histogram is laid out (segment, bucket, unit)-major, so one flat
+//                           scan (scan.cu, decoupled look-back) yields the global destination of
+//                           every (bucket, unit) run — no per-partition mutex, no host round trip.
+//   3. part_scatter_kernel  per tile: rank rows inside their bucket with the same match_any /
+//                           warp-private-counter scheme, scan the 2^bits tile counts, stage the
+//                           tile SORTED BY BUCKET in shared memory, then stream it out so that
+//                           consecutive threads write consecutive addresses of a bucket's run.
+// A pass can be "segmented": each input segment (= a partition of the previous pass) is
+// partitioned independently, which is how the join refines 2^10 coarse partitions into up to
+// 2^20 shared-memory-sized ones while every pass keeps >= 64 B write runs.
+// Rows are carried as 8-byte (key, value) pairs between passes (one 8 B access per row instead
+// of two 4 B accesses to two columns).
+#include "partition.cuh"
+
+#include <vector>
+
+#include "scan.cuh"
+
+namespace {
+
+constexpr int kThreads = kPartThreads;
+constexpr int kWarps = kThreads / 32;
+constexpr int kItems = kPartTile / kThreads;  // 16 rows per thread per tile
+
+template <bool kAoS>
+__device__ __forceinline__ void load_row(const PartInput& in, int64_t row, uint32_t& k, uint32_t& v) {
+  if (kAoS) {
+    const uint2 p = ld_stream_v2(in.pairs + row);
+    k = p.x;
+    v = p.y;
+  } else {
+    k = ld_stream_u32(in.keys + row);
+    v = in.vals ? ld_stream_u32(in.vals + row) : (uint32_t)row;
+  }
+}
+template <bool kAoS>
+__device__ __forceinline__ uint32_t load_key(const PartInput& in, int64_t row) {
+  return kAoS ? ld_stream_u32(reinterpret_cast<const uint32_t*>(in.pairs + row))
+              : ld_stream_u32(in.keys + row);
+}
+
+struct Unit {
+  int64_t row0, row1;  // rows of this unit
+  int64_t hbase;       // histogram entry of (bucket 0, this unit); bucket p is at hbase + p*ustride
+  int64_t ustride;     // units in this unit's segment
+  bool valid;
+};
+
+// Work unit u -> (segment, k-th unit of the segment). unit_first[s] = number of units in the
+// segments before s; empty segments own no unit.
+__device__ __forceinline__ Unit find_unit(const int64_t* __restrict__ seg_off,
+                                          const int64_t* __restrict__ unit_first, int64_t nseg,
+                                          int64_t unit_rows, int P) {
+  Unit u;
+  const int64_t id = blockIdx.x;
+  u.valid = id < unit_first[nseg];
+  if (!u.valid) return u;
+  int64_t lo = 0, hi = nseg;  // last s with unit_first[s] <= id
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (unit_first[mid] <= id) lo = mid; else hi = mid;
+  }
+  const int64_t k = id - unit_first[lo];
+  u.ustride = unit_first[lo + 1] - unit_first[lo];
+  u.row0 = seg_off[lo] + k * unit_rows;
+  u.row1 = min(u.row0 + unit_rows, seg_off[lo + 1]);
+  u.hbase = unit_first[lo] * P + k;
+  return u;
+}
+
+// unit_first[s] for all segments (one CTA; nseg <= a few thousand).
+__global__ void part_unit_table_kernel(const int64_t* __restrict__ seg_off, int64_t nseg,
+                                       int64_t unit_rows, int64_t* __restrict__ unit_first) {
+  __shared__ int64_t carry;
+  __shared__ int64_t warp_tot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nseg; base += blockDim.x) {
+    const int64_t s = base + threadIdx.x;
+    int64_t c = 0;
+    if (s < nseg) c = (seg_off[s + 1] - seg_off[s] + unit_rows - 1) / unit_rows;
+    int64_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+      int64_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const int64_t excl = carry + warp_tot[warp] + incl - c;
+    if (s < nseg) unit_first[s] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + c;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) unit_first[nseg] = carry;
+}
+
+template <bool kAoS>
+__global__ void __launch_bounds__(kThreads)
+part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
+                 const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
+                 PartGeom g, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t whist32[];  // [kWarps][P]
+  const int P = 1 << g.bits;
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
+  if (!u.valid) return;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kWarps * P; i += kThreads) whist32[i] = 0;
+  __syncthreads();
+  uint32_t* __restrict__ mine = whist32 + warp * P;
+  for (int64_t base = u.row0; base < u.row1; base += kThreads) {
+    const int64_t row = base + tid;
+    bool sel = row < u.row1;
+    uint32_t b = 0xffffffffu;
+    if (sel) {
+      const uint32_t h = wang_hash_u32(load_key<kAoS>(in, row));
+      sel = part_selected(h, g.sel_shl, g.sel_bits, g.sel_val);
+      if (sel) b = part_bucket(h, g.shl, g.bits);
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, b);
+    if (sel && lane == (uint32_t)(__ffs(peers) - 1)) mine[b] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int p = tid; p < P; p += kThreads) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) c += whist32[w * P + p];
+    hist[u.hbase + (int64_t)p * u.ustride] = c;
+  }
+}
+
+template <bool kAoS>
+__global__ void __launch_bounds__(kThreads, 2)
+part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
+                    const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
+                    PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
+                    int64_t out_cap, unsigned int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int P = 1 << g.bits;
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
+  if (!u.valid) return;
+  // shared-memory carve-up
+  uint2* stage = reinterpret_cast<uint2*>(smem);                                   // [kPartTile]
+  uint64_t* gbase = reinterpret_cast<uint64_t*>(smem + sizeof(uint2) * kPartTile);  // [P]
+  uint32_t* tile_start = reinterpret_cast<uint32_t*>(gbase + P);                    // [P]
+  uint32_t* tile_cnt = tile_start + P;                                              // [P]
+  uint16_t* whist = reinterpret_cast<uint16_t*>(tile_cnt + P);                      // [kWarps][P]
+  __shared__ uint32_t warp_tot[kWarps];
+  __shared__ uint32_t s_tile_total;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = lanemask_lt();
+  for (int p = tid; p < P; p += kThreads) gbase[p] = scanned[u.hbase + (int64_t)p * u.ustride];
+  for (int i = tid; i < kWarps * P / 2; i += kThreads) reinterpret_cast<uint32_t*>(whist)[i] = 0;
+  __syncthreads();
+  uint16_t* __restrict__ mine = whist + warp * P;
+
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kPartTile) {
+    // ---- load, hash, rank inside (warp, bucket) ----
+    uint32_t key[kItems], val[kItems], packed[kItems];  // packed = bucket | rank << 16
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      const int64_t row = t0 + it * kThreads + tid;
+      key[it] = 0;
+      val[it] = 0;
+      if (row < u.row1) load_row<kAoS>(in, row, key[it], val[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      const int64_t row = t0 + it * kThreads + tid;
+      bool sel = row < u.row1;
+      uint32_t b = 0xffffffffu;
+      if (sel) {
+        const uint32_t h = wang_hash_u32(key[it]);
+        sel = part_selected(h, g.sel_shl, g.sel_bits, g.sel_val);
+        if (sel) b = part_bucket(h, g.shl, g.bits);
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, b);
+      const int leader = __ffs(peers) - 1;
+      uint32_t before = 0;
+      if (sel && (int)lane == leader) {
+        before = mine[b];
+        mine[b] = (uint16_t)(before + __popc(peers));
+      }
+      before = __shfl_sync(0xffffffffu, before, leader);
+      packed[it] = sel ? (b | ((before + __popc(peers & lt)) << 16)) : 0xffffffffu;
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per bucket: exclusive offsets of the warps, tile count; then scan the tile counts ----
+    uint32_t c[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int p = 2 * tid + q;
+      if (p < P) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const uint32_t t = whist[w * P + p];
+          whist[w * P + p] = (uint16_t)run;
+          run += t;
+        }
+        c[q] = run;
+      }
+    }
+    uint32_t incl = c[0] + c[1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = lane < kWarps ? warp_tot[lane] : 0;
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      if (lane < kWarps) warp_tot[lane] = wi - w;
+      if (lane == 31) s_tile_total = wi;
+    }
+    __syncthreads();
+    {
+      const uint32_t excl = warp_tot[warp] + incl - (c[0] + c[1]);
+      const int p = 2 * tid;
+      if (p < P) {
+        tile_start[p] = excl;
+        tile_cnt[p] = c[0];
+      }
+      if (p + 1 < P) {
+        tile_start[p + 1] = excl + c[0];
+        tile_cnt[p + 1] = c[1];
+      }
+    }
+    __syncthreads();
+
+    // ---- stage the tile sorted by bucket ----
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      if (packed[it] != 0xffffffffu) {
+        const uint32_t b = packed[it] & 0xffffu;
+        const uint32_t pos = tile_start[b] + mine[b] + (packed[it] >> 16);
+        stage[pos] = make_uint2(key[it], val[it]);
+      }
+    }
+    __syncthreads();
+
+    // ---- stream out: consecutive threads -> consecutive rows of a bucket's run ----
+    const uint32_t total = s_tile_total;
+    for (uint32_t j = tid; j < total; j += kThreads) {
+      const uint2 kv = stage[j];
+      const uint32_t b = part_bucket(wang_hash_u32(kv.x), g.shl, g.bits);
+      const uint64_t dst = gbase[b] + (j - tile_start[b]);
+      if ((int64_t)dst < out_cap) {
+        st_stream_v2(out + dst, kv);
+      } else if (overflow) {
+        *overflow = 1u;
+      }
+    }
+    __syncthreads();
+    // ---- advance the running destinations, clear the counters ----
+    for (int p = tid; p < P; p += kThreads) gbase[p] += tile_cnt[p];
+    for (int i = tid; i < kWarps * P / 2; i += kThreads) reinterpret_cast<uint32_t*>(whist)[i] = 0;
+    __syncthreads();
+  }
+}
+
+// part_off[s*P + p] = first output row of (segment s, bucket p); part_off[nseg*P] = total rows.
+__global__ void part_offsets_kernel(const uint64_t* __restrict__ scanned,
+                                    const int64_t* __restrict__ unit_first, int64_t nseg, int P,
+                                    int64_t* __restrict__ part_off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = nseg * P;
+  if (i > n) return;
+  if (i == n) {
+    part_off[n] = (int64_t)scanned[unit_first[nseg] * P];
+    return;
+  }
+  const int64_t s = i / P, p = i - s * P;
+  const int64_t ustride = unit_first[s + 1] - unit_first[s];
+  part_off[i] = (int64_t)scanned[unit_first[s] * P + p * ustride];
+}
+
+size_t scatter_smem_bytes(int bits) {
+  const size_t P = (size_t)1 << bits;
+  return sizeof(uint2) * kPartTile + P * 8 + P * 4 + P * 4 + (size_t)kWarps * P * 2;
+}
+
+int64_t choose_unit_rows(int64_t n, int64_t nseg) {
+  int64_t tiles = n / ((int64_t)kPartTile * 2048);
+  const int64_t avg_seg_tiles = nseg > 0 ? (n / nseg) / kPartTile : 1;
+  if (tiles > avg_seg_tiles) tiles = avg_seg_tiles;
+  if (tiles < 1) tiles = 1;
+  if (tiles > 32) tiles = 32;
+  return tiles * kPartTile;
+}
+
+struct PassLayout {
+  int64_t unit_rows, max_units, n_entries;  // n_entries includes the trailing total slot
+  size_t off_unit_first, off_hist, off_scanned, off_scanws, total;
+};
+
+PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
+  PassLayout L;
+  L.unit_rows = choose_unit_rows(n, nseg);
+  L.max_units = n / L.unit_rows + nseg;
+  L.n_entries = L.max_units * ((int64_t)1 << bits) + 1;
+  size_t o = 0;
+  L.off_unit_first = o; o += b2_align_up((size_t)(nseg + 1) * 8, 256);
+  L.off_hist = o;       o += b2_align_up((size_t)L.n_entries * 4, 256);
+  L.off_scanned = o;    o += b2_align_up((size_t)L.n_entries * 8, 256);
+  L.off_scanws = o;     o += b2_align_up(b2_scan_ws_bytes(L.n_entries), 256);
+  L.total = o;
+  return L;
+}
+
+template <bool kAoS>
+int part_pass_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off,
+                   int64_t nseg, const PartGeom& g, uint2* d_out, int64_t out_cap,
+                   int64_t* d_part_off, unsigned int* d_overflow, void* d_ws, size_t ws_bytes,
+                   cudaStream_t s) {
+  const int P = 1 << g.bits;
+  const PassLayout L = pass_layout(n, nseg, g.bits);
+  if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition pass", "workspace");
+  char* base = static_cast<char*>(d_ws);
+  int64_t* unit_first = reinterpret_cast<int64_t*>(base + L.off_unit_first);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base + L.off_hist);
+  uint64_t* scanned = reinterpret_cast<uint64_t*>(base + L.off_scanned);
+  B2_REQUIRE(ctx, L.max_units < (1ll << 31), "too many work units");
+
+  part_unit_table_kernel<<<1, 1024, 0, s>>>(d_seg_off, nseg, L.unit_rows, unit_first);
+  B2_LAUNCH_CHECK(ctx, "part_unit_table_kernel");
+  B2_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (size_t)L.n_entries * 4, s));
+  if (L.max_units > 0) {
+    const size_t hsmem = (size_t)kWarps * P * 4;
+    static bool attr_done_h[2] = {false, false};
+    if (!attr_done_h[kAoS]) {
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_hist_kernel<kAoS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)scatter_smem_bytes(kPartMaxBits)));
+      attr_done_h[kAoS] = true;
+    }
+    part_hist_kernel<kAoS><<<(unsigned)L.max_units, kThreads, hsmem, s>>>(
+        in, d_seg_off, unit_first, nseg, L.unit_rows, g, hist);
+    B2_LAUNCH_CHECK(ctx, "part_hist_kernel");
+  }
+  B2_RETURN_NOT_OK(b2_exclusive_scan_u32_u64(ctx, hist, scanned, L.n_entries, base + L.off_scanws,
+                                             ws_bytes - L.off_scanws, s));
+  if (L.max_units > 0) {
+    part_scatter_kernel<kAoS><<<(unsigned)L.max_units, kThreads, scatter_smem_bytes(g.bits), s>>>(
+        in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
+    B2_LAUNCH_CHECK(ctx, "part_scatter_kernel");
+  }
+  if (d_part_off) {
+    const int64_t cnt = nseg * P + 1;
+    part_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(scanned, unit_first, nseg, P,
+                                                                      d_part_off);
+    B2_LAUNCH_CHECK(ctx, "part_offsets_kernel");
+  }
+  return B2_OK;
+}
+
+}  // namespace
+
+size_t part_pass_ws_bytes(int64_t n, int64_t nseg, int bits) { return pass_layout(n, nseg, bits).total; }
+
+int part_pass(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
+              const PartGeom& g, uint2* d_out, int64_t out_cap, int64_t* d_part_off,
+              unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+  B2_REQUIRE(ctx, g.bits >= 0 && g.bits <= kPartMaxBits, "fan-out per pass is limited to 2^10");
+  B2_REQUIRE(ctx, nseg >= 1, "at least one segment");
+  if (in.pairs)
+    return part_pass_impl<true>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_part_off,
+                                d_overflow, d_ws, ws_bytes, s);
+  return part_pass_impl<false>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_part_off,
+                               d_overflow, d_ws, ws_bytes, s);
+}
+
+// ---- one- or two-pass driver ------------------------------------------------------------------
+namespace {
+
+__global__ void set_single_segment_kernel(int64_t* seg_off, int64_t n) {
+  seg_off[0] = 0;
+  seg_off[1] = n;
+}
+
+struct FullLayout {
+  int bits1, bits2;
+  size_t off_seg, off_off1, off_pass, pass_bytes, total;
+};
+
+FullLayout full_layout(int64_t n, int bits) {
+  FullLayout F;
+  F.bits1 = bits <= kPartMaxBits ? bits : (bits + 1) / 2;
+  F.bits2 = bits - F.bits1;
+  size_t o = 0;
+  F.off_seg = o;  o += 256;
+  F.off_off1 = o; o += b2_align_up((((size_t)1 << F.bits1) + 1) * 8, 256);
+  F.pass_bytes = part_pass_ws_bytes(n, 1, F.bits1);
+  if (F.bits2 > 0) {
+    const size_t p2 = part_pass_ws_bytes(n, (int64_t)1 << F.bits1, F.bits2);
+    if (p2 > F.pass_bytes) F.pass_bytes = p2;
+  }
+  F.off_pass = o; o += b2_align_up(F.pass_bytes, 256);
+  F.total = o;
+  return F;
+}
+
+}  // namespace
+
+size_t part_full_ws_bytes(int64_t n, int bits) { return full_layout(n, bits).total; }
+
+int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, int sel_shl,
+              int sel_bits, uint32_t sel_val, uint2* d_out, uint2* d_tmp, int64_t cap,
+              int64_t* d_off, unsigned int* d_overflow, void* d_ws, size_t ws_bytes,
+              cudaStream_t s) {
+  B2_REQUIRE(ctx, bits >= 0 && bits <= 2 * kPartMaxBits, "at most 2^20 partitions");
+  const FullLayout F = full_layout(n, bits);
+  if (ws_bytes < F.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition", "workspace");
+  char* base = static_cast<char*>(d_ws);
+  int64_t* seg = reinterpret_cast<int64_t*>(base + F.off_seg);
+  int64_t* off1 = reinterpret_cast<int64_t*>(base + F.off_off1);
+  set_single_segment_kernel<<<1, 1, 0, s>>>(seg, n);
+  B2_LAUNCH_CHECK(ctx, "set_single_segment_kernel");
+  PartGeom g1;
+  g1.bits = F.bits1;
+  g1.shl = shl;
+  g1.sel_bits = sel_bits;
+  g1.sel_shl = sel_shl;
+  g1.sel_val = sel_val;
+  if (F.bits2 == 0) {
+    return part_pass(ctx, in, n, seg, 1, g1, d_out, cap, d_off, d_overflow, base + F.off_pass,
+                     F.pass_bytes, s);
+  }
+  B2_REQUIRE(ctx, d_tmp != nullptr, "two-pass partitioning needs a temporary buffer");
+  B2_RETURN_NOT_OK(part_pass(ctx, in, n, seg, 1, g1, d_tmp, cap, off1, d_overflow,
+                             base + F.off_pass, F.pass_bytes, s));
+  PartInput in2;
+  in2.pairs = d_tmp;
+  PartGeom g2;
+  g2.bits = F.bits2;
+  g2.shl = shl + F.bits1;
+  // n is only used to size the work units (an upper bound on the rows that survived pass 1)
+  return part_pass(ctx, in2, n, off1, (int64_t)1 << F.bits1, g2, d_out, cap, d_off,
+                   d_overflow, base + F.off_pass, F.pass_bytes, s);
+}

@@ -1,0 +1,24 @@
+// pending.h — device-resident result of the last *_host call (internal, non-ABI).
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+struct b2_ctx;
+struct b2_pending {
+  enum Kind { kNone, kFilter, kPartition, kJoin } kind = kNone;
+  std::vector<void*> dev;          // device allocations owned by the pending result
+  // filter
+  uint32_t* d_out = nullptr;
+  std::vector<int64_t> batch_end;  // inclusive running counts per batch
+  // partition
+  std::vector<uint32_t*> d_cols;
+  std::vector<int64_t> part_off;
+  int ncols = 0;
+  // join
+  uint32_t* d_fk = nullptr;
+  uint32_t* d_y = nullptr;
+  uint32_t* d_x = nullptr;
+  uint64_t rows = 0;
+};
+void b2_pending_free(b2_ctx* ctx);

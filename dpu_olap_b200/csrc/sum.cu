@@ -1,0 +1,115 @@
+// sum.cu — Sum aggregate of a uint32 column into uint64.
+//
+// Replaces the reference's DPU aggregate program: per-tasklet partial sums over 256-element
+// blocks (dpu/shared/kernels/aggr.c:16-33, `sum` dpu/aggr/main.c:44-51), tasklet 0 adding the 16
+// partials (main.c:75-89) and the host adding one partial per DPU (host/aggr/aggr_dpu.cc:82-84).
+//
+// B200 design: the op is a pure HBM read stream (4 B/row). One persistent grid of
+// 2 CTAs x 512 threads per SM; every thread keeps 8 independent 128-bit streaming loads in flight
+// (128 KB per SM outstanding), accumulates in 64-bit registers, reduces by warp shuffle, and the
+// last CTA to finish (atomic ticket) folds the per-CTA partials — one launch, no memset, and the
+// result is written (not accumulated), so the call is idempotent.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSumThreads = 512;
+constexpr int kSumUnroll = 8;               // uint4 loads in flight per thread
+constexpr int kSumMaxCtas = 4096;           // partial slots in ctx->d_small
+constexpr size_t kTicketOffset = 40 * 1024; // byte offset of the ticket in ctx->d_small
+
+__device__ __forceinline__ uint64_t sum4(uint4 v) {
+  return ((uint64_t)v.x + v.y) + ((uint64_t)v.z + v.w);
+}
+
+__global__ void __launch_bounds__(kSumThreads, 2)
+sum_u32_kernel(const uint32_t* __restrict__ in, int64_t n, uint64_t* __restrict__ partials,
+               unsigned int* __restrict__ ticket, uint64_t* __restrict__ out) {
+  // Split [0,n) into a scalar head (to reach 16 B alignment), a vector body and a scalar tail.
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(in);
+  int64_t head = (int64_t)(((16 - (addr & 15)) & 15) >> 2);
+  if (head > n) head = n;
+  const int64_t nvec = (n - head) >> 2;
+  const int64_t tail_start = head + (nvec << 2);
+  const uint4* __restrict__ vin = reinterpret_cast<const uint4*>(in + head);
+
+  uint64_t acc = 0;
+  const int64_t chunk = (int64_t)kSumThreads * kSumUnroll;  // uint4 per CTA iteration
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < nvec; base += (int64_t)gridDim.x * chunk) {
+    uint4 v[kSumUnroll];
+    if (base + chunk <= nvec) {
+#pragma unroll
+      for (int u = 0; u < kSumUnroll; ++u) v[u] = ld_stream_v4(vin + base + u * kSumThreads + threadIdx.x);
+#pragma unroll
+      for (int u = 0; u < kSumUnroll; ++u) acc += sum4(v[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kSumUnroll; ++u) {
+        const int64_t i = base + u * kSumThreads + threadIdx.x;
+        if (i < nvec) acc += sum4(ld_stream_v4(vin + i));
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = threadIdx.x; i < head; i += kSumThreads) acc += in[i];
+    for (int64_t i = tail_start + threadIdx.x; i < n; i += kSumThreads) acc += in[i];
+  }
+
+  __shared__ uint64_t warp_sums[kSumThreads / 32];
+  __shared__ bool is_last;
+  acc = warp_reduce_sum_u64(acc);
+  if (lane_id() == 0) warp_sums[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint64_t v = threadIdx.x < kSumThreads / 32 ? warp_sums[threadIdx.x] : 0;
+    v = warp_reduce_sum_u64(v);
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = v;
+      __threadfence();
+      const unsigned int t = atomicAdd(ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    uint64_t v = 0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kSumThreads)
+      v += *reinterpret_cast<volatile uint64_t*>(partials + i);
+    v = warp_reduce_sum_u64(v);
+    __syncthreads();
+    if (lane_id() == 0) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint64_t w = threadIdx.x < kSumThreads / 32 ? warp_sums[threadIdx.x] : 0;
+      w = warp_reduce_sum_u64(w);
+      if (threadIdx.x == 0) {
+        *out = w;
+        *ticket = 0;  // re-arm for the next launch on this ctx
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int b2_sum_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint64_t* d_sum,
+                              void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, n >= 0, "n must be >= 0");
+  B2_REQUIRE(ctx, d_sum != nullptr, "d_sum is null");
+  B2_REQUIRE(ctx, n == 0 || d_in != nullptr, "d_in is null");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_in) & 3) == 0, "d_in must be 4-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t chunk_elems = (int64_t)kSumThreads * kSumUnroll * 4;
+  int64_t want = (n + chunk_elems - 1) / chunk_elems;
+  int grid = ctx->sm_count * 2;
+  if (want < grid) grid = want > 0 ? (int)want : 1;
+  if (grid > kSumMaxCtas) grid = kSumMaxCtas;
+  uint64_t* partials = static_cast<uint64_t*>(ctx->d_small);
+  unsigned int* ticket =
+      reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->d_small) + kTicketOffset);
+  sum_u32_kernel<<<grid, kSumThreads, 0, s>>>(d_in, n, partials, ticket, d_sum);
+  B2_LAUNCH_CHECK(ctx, "sum_u32_kernel");
+  return B2_OK;
+}

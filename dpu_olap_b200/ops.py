@@ -1,0 +1,549 @@
+"""Host-side mirror of dpu_olap's operator API for the GPU path.
+
+Same duck-typed surface as the reference's *Dpu classes — constructor, ``Prepare()``, ``Run()``
+(+ ``GetResult()`` for the filter), ``Timers()`` — with the DpuSet replaced by a :class:`Context`
+bound to one B200:
+
+    reference (C++)                                   here
+    FilterDpu(system, batches)      filter_dpu.h:14   FilterGpu(ctx, batches)
+    SumDpu(system, batches)         aggr_dpu.h:14     SumGpu(ctx, batches)
+    TakeDpu(system, b, idx)         take_dpu.h:14     TakeGpu(ctx, batches, indices_batches)
+    JoinDpu(system, ls, rs, lb, rb) join_dpu.h:14     JoinGpu(ctx, left_batches, right_batches)
+    PartitionDpu(system, s, b, n, k) partition_dpu.h:15  PartitionGpu(ctx, batches, nr_partitions, key)
+
+Batches are "record batches" in the loosest useful sense: a ``pyarrow.RecordBatch``, a dict
+``{column name: uint32 array}`` or (single-column operators) a bare uint32 ``numpy``/``pyarrow``
+array. Only the raw data buffers cross the C ABI (include/b200olap.h); nothing here computes —
+if the CUDA library is missing these classes cannot be constructed.
+
+The ``*_dev`` functions of :class:`Context` are the device-resident entry points (torch CUDA
+tensors in, torch CUDA tensors out) used by bench.py and the parity tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Timings, check
+
+try:  # pyarrow is optional for the package, present in the image
+    import pyarrow as pa
+except Exception:  # pragma: no cover
+    pa = None
+
+
+class Timers(dict):
+    """Named timers in milliseconds, reference names (filter_dpu.cc:107-110)."""
+
+    @classmethod
+    def from_timings(cls, *ts: Timings) -> "Timers":
+        out = cls({"copy-to-dpu": 0.0, "dpu-work": 0.0, "copy-from-dpu": 0.0, "total": 0.0})
+        for t in ts:
+            out["copy-to-dpu"] += t.copy_to_dev_ms
+            out["dpu-work"] += t.dev_work_ms
+            out["copy-from-dpu"] += t.copy_from_dev_ms
+            out["total"] += t.total_ms
+        return out
+
+    def get(self, *a):  # reference: timers->get() returns the map
+        return self if not a else dict.get(self, *a)
+
+
+# ---------------------------------------------------------------------------------------------
+# batch plumbing
+# ---------------------------------------------------------------------------------------------
+def _as_u32(col: Any) -> np.ndarray:
+    """Zero-copy uint32 numpy view of one column of one batch."""
+    if pa is not None and isinstance(col, (pa.Array, pa.ChunkedArray)):
+        if isinstance(col, pa.ChunkedArray):
+            col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
+        if col.null_count:
+            raise ValueError("nullable columns are not supported (the reference assumes non-null)")
+        if col.type != pa.uint32():
+            raise TypeError(f"expected uint32 column, got {col.type}")
+        return col.to_numpy(zero_copy_only=True)
+    a = np.asarray(col)
+    if a.dtype != np.uint32:
+        raise TypeError(f"expected uint32 column, got {a.dtype}")
+    return np.ascontiguousarray(a)
+
+
+def _column(batch: Any, name_or_index) -> np.ndarray:
+    if pa is not None and isinstance(batch, pa.RecordBatch):
+        if isinstance(name_or_index, str):
+            return _as_u32(batch.column(batch.schema.get_field_index(name_or_index)))
+        return _as_u32(batch.column(name_or_index))
+    if isinstance(batch, dict):
+        if isinstance(name_or_index, str):
+            return _as_u32(batch[name_or_index])
+        return _as_u32(list(batch.values())[name_or_index])
+    if name_or_index not in (0, None):
+        raise KeyError("a bare array batch has a single column")
+    return _as_u32(batch)
+
+
+def _column_names(batch: Any) -> list[str]:
+    if pa is not None and isinstance(batch, pa.RecordBatch):
+        return list(batch.schema.names)
+    if isinstance(batch, dict):
+        return list(batch.keys())
+    return ["v"]
+
+
+class _PtrTable:
+    """(const uint32_t* const*, const int64_t*) view of a list of arrays; keeps them alive."""
+
+    def __init__(self, arrays: Sequence[np.ndarray]):
+        self.arrays = list(arrays)
+        n = len(self.arrays)
+        self.ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in self.arrays])
+        self.lens = (C.c_int64 * max(n, 1))(*[int(a.size) for a in self.arrays])
+        self.n = n
+
+
+def _dptr(t) -> int:
+    return 0 if t is None else int(t.data_ptr())
+
+
+# ---------------------------------------------------------------------------------------------
+# context
+# ---------------------------------------------------------------------------------------------
+class Context:
+    """One B200. Replaces ``dpu::DpuSet::allocate(nr_dpus)`` (dpuext.hpp:710)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.lib()  # raises if libb200olap.so is absent — no fallback
+        h = C.c_void_p()
+        check(self._lib.b2_ctx_create(int(device), C.byref(h)), "b2_ctx_create")
+        self._h = h
+        self.device = int(device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.b2_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, status: int, where: str) -> None:
+        check(status, where, self._h)
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.b2_launch_count(self._h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self._lib.b2_ctx_sm_count(self._h))
+
+    # ---- device-resident entry points (torch CUDA tensors) --------------------------------
+    @staticmethod
+    def _stream() -> int:
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+
+    def gen_dev(self, data_seeds, nbatches: int, batch_len: int, lo=None, hi=None, out=None):
+        """RandomArrayGenerator data for nbatches arrays (seeds = the pcg32_fast seeds)."""
+        import torch
+        if out is None:
+            out = torch.empty(nbatches * batch_len, dtype=torch.int32, device=f"cuda:{self.device}")
+        seeds = np.ascontiguousarray(np.asarray(data_seeds, dtype=np.uint64))
+        assert seeds.size == nbatches
+        lo_p = hi_p = None
+        if lo is not None:
+            lo_a = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.uint32), (nbatches,)))
+            hi_a = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.uint32), (nbatches,)))
+            lo_p = lo_a.ctypes.data_as(C.POINTER(C.c_uint32))
+            hi_p = hi_a.ctypes.data_as(C.POINTER(C.c_uint32))
+        self._ck(self._lib.b2_gen_u32_dev(self._h, seeds.ctypes.data_as(C.POINTER(C.c_uint64)), lo_p,
+                                          hi_p, nbatches, batch_len, _dptr(out), self._stream()),
+                 "b2_gen_u32_dev")
+        return out
+
+    def iota_dev(self, start: int, n: int, out=None):
+        import torch
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=f"cuda:{self.device}")
+        self._ck(self._lib.b2_iota_u32_dev(self._h, start, n, _dptr(out), self._stream()), "b2_iota_u32_dev")
+        return out
+
+    def sum_dev(self, col, out=None):
+        import torch
+        if out is None:
+            out = torch.empty(1, dtype=torch.int64, device=col.device)
+        self._ck(self._lib.b2_sum_u32_dev(self._h, _dptr(col), col.numel(), _dptr(out), self._stream()),
+                 "b2_sum_u32_dev")
+        return out
+
+    def filter_ws_bytes(self, nbatches: int, batch_len: int) -> int:
+        return int(self._lib.b2_filter_ws_bytes(nbatches, batch_len))
+
+    def filter_dev(self, col, nbatches: int, batch_len: int, threshold: int, out=None, batch_end=None,
+                   total=None, ws=None, carry_in=None):
+        """Returns (out, batch_end, total) device tensors; nothing is synchronised."""
+        import torch
+        dev = col.device
+        if out is None:
+            out = torch.empty(nbatches * batch_len, dtype=torch.int32, device=dev)
+        if batch_end is None:
+            batch_end = torch.empty(max(nbatches, 1), dtype=torch.int64, device=dev)
+        if total is None:
+            total = torch.empty(1, dtype=torch.int64, device=dev)
+        need = self.filter_ws_bytes(nbatches, batch_len)
+        if ws is None:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._ck(self._lib.b2_filter_lt_u32_dev(self._h, _dptr(col), nbatches, batch_len, threshold,
+                                                _dptr(out), _dptr(batch_end), _dptr(total),
+                                                _dptr(carry_in), _dptr(ws), ws.numel(), self._stream()),
+                 "b2_filter_lt_u32_dev")
+        return out, batch_end, total
+
+    def filter_ragged_dev(self, col, batch_off: np.ndarray, threshold: int):
+        import torch
+        dev = col.device
+        off = np.ascontiguousarray(np.asarray(batch_off, dtype=np.int64))
+        nb = off.size - 1
+        d_off = torch.from_numpy(off).to(dev)
+        out = torch.empty(max(int(off[-1]), 1), dtype=torch.int32, device=dev)
+        batch_end = torch.empty(max(nb, 1), dtype=torch.int64, device=dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        p_off = off.ctypes.data_as(C.POINTER(C.c_int64))
+        need = int(self._lib.b2_filter_ragged_ws_bytes(p_off, nb))
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._ck(self._lib.b2_filter_lt_u32_ragged_dev(self._h, _dptr(col), p_off, _dptr(d_off), nb,
+                                                       threshold, _dptr(out), _dptr(batch_end),
+                                                       _dptr(total), 0, _dptr(ws), ws.numel(),
+                                                       self._stream()),
+                 "b2_filter_lt_u32_ragged_dev")
+        return out, batch_end, total
+
+    def take_dev(self, values, values_len: int, indices, idx_len: int, nbatches: int, out=None):
+        import torch
+        if out is None:
+            out = torch.empty(nbatches * idx_len, dtype=torch.int32, device=values.device)
+        self._ck(self._lib.b2_take_u32_dev(self._h, _dptr(values), values_len, _dptr(indices), idx_len,
+                                           nbatches, _dptr(out), self._stream()), "b2_take_u32_dev")
+        return out
+
+    def take_ragged_dev(self, values, values_off: np.ndarray, indices, idx_off: np.ndarray):
+        import torch
+        dev = values.device
+        voff = torch.from_numpy(np.ascontiguousarray(values_off, dtype=np.int64)).to(dev)
+        ioff = torch.from_numpy(np.ascontiguousarray(idx_off, dtype=np.int64)).to(dev)
+        nb = len(idx_off) - 1
+        n = int(idx_off[-1])
+        out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self._ck(self._lib.b2_take_u32_ragged_dev(self._h, _dptr(values), _dptr(voff), _dptr(indices),
+                                                  _dptr(ioff), nb, 0, n, _dptr(out), self._stream()),
+                 "b2_take_u32_ragged_dev")
+        return out[:n]
+
+    def partition_dev(self, cols: Sequence, nparts: int, skip_bits: int = 0):
+        """cols[0] is the key column. Returns (partitioned cols, part_off[nparts+1])."""
+        import torch
+        dev = cols[0].device
+        n = cols[0].numel()
+        outs = [torch.empty(max(n, 1), dtype=torch.int32, device=dev) for _ in cols]
+        off = torch.empty(nparts + 1, dtype=torch.int64, device=dev)
+        need = int(self._lib.b2_partition_ws_bytes(n, nparts))
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (_dptr(ws) + 255) // 256 * 256
+        pin = (C.c_void_p * len(cols))(*[_dptr(c) for c in cols])
+        pout = (C.c_void_p * len(cols))(*[_dptr(c) for c in outs])
+        self._ck(self._lib.b2_partition_u32_dev(self._h, pin, pout, len(cols), n, nparts, skip_bits,
+                                                _dptr(off), ws_ptr, need, self._stream()),
+                 "b2_partition_u32_dev")
+        return [o[:n] for o in outs], off
+
+    def join_ws_bytes(self, nl: int, nr: int) -> int:
+        return int(self._lib.b2_join_ws_bytes(nl, nr))
+
+    def join_min_ws_bytes(self, nl: int, nr: int) -> int:
+        return int(self._lib.b2_join_min_ws_bytes(nl, nr))
+
+    def join_dev(self, fk, y, pk, x, out_capacity: int | None = None, ws=None, outs=None,
+                 out_rows=None, skip_bits: int = 0):
+        """Returns (out_fk, out_y, out_x, out_rows[1] uint64-as-int64 device tensor)."""
+        import torch
+        dev = fk.device
+        nl, nr = fk.numel(), pk.numel()
+        cap = nl if out_capacity is None else int(out_capacity)
+        if outs is None:
+            outs = [torch.empty(max(cap, 1), dtype=torch.int32, device=dev) for _ in range(3)]
+        if out_rows is None:
+            out_rows = torch.empty(1, dtype=torch.int64, device=dev)
+        if ws is None:
+            ws = torch.empty(self.join_ws_bytes(nl, nr) + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (_dptr(ws) + 255) // 256 * 256
+        ws_bytes = ws.numel() - (ws_ptr - _dptr(ws))
+        self._ck(self._lib.b2_join_u32_dev(self._h, _dptr(fk), _dptr(y), nl, _dptr(pk), _dptr(x), nr,
+                                           _dptr(outs[0]), _dptr(outs[1]), _dptr(outs[2]), cap,
+                                           _dptr(out_rows), skip_bits, ws_ptr, ws_bytes, self._stream()),
+                 "b2_join_u32_dev")
+        return outs[0], outs[1], outs[2], out_rows
+
+    def join_pairs_dev(self, l_pairs, r_pairs, out_capacity: int, skip_bits: int, ws=None, outs=None,
+                       out_rows=None):
+        import torch
+        dev = l_pairs.device
+        nl, nr = l_pairs.numel(), r_pairs.numel()
+        cap = int(out_capacity)
+        if outs is None:
+            outs = [torch.empty(max(cap, 1), dtype=torch.int32, device=dev) for _ in range(3)]
+        if out_rows is None:
+            out_rows = torch.empty(1, dtype=torch.int64, device=dev)
+        if ws is None:
+            ws = torch.empty(self.join_ws_bytes(nl, nr) + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (_dptr(ws) + 255) // 256 * 256
+        ws_bytes = ws.numel() - (ws_ptr - _dptr(ws))
+        self._ck(self._lib.b2_join_pairs_dev(self._h, _dptr(l_pairs), nl, _dptr(r_pairs), nr,
+                                             _dptr(outs[0]), _dptr(outs[1]), _dptr(outs[2]), cap,
+                                             _dptr(out_rows), skip_bits, ws_ptr, ws_bytes, self._stream()),
+                 "b2_join_pairs_dev")
+        return outs[0], outs[1], outs[2], out_rows
+
+    def shuffle_partition_dev(self, key, val, nranks: int, pairs_out=None, dest_off=None, ws=None):
+        """Route (key, val) rows by destination rank. Returns (pairs int64[n], dest_off int64[nranks+1])."""
+        import torch
+        dev = key.device
+        n = key.numel()
+        if pairs_out is None:
+            pairs_out = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        if dest_off is None:
+            dest_off = torch.empty(nranks + 1, dtype=torch.int64, device=dev)
+        need = int(self._lib.b2_shuffle_ws_bytes(n, nranks))
+        if ws is None:
+            ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (_dptr(ws) + 255) // 256 * 256
+        self._ck(self._lib.b2_shuffle_partition_u32_dev(self._h, _dptr(key), _dptr(val), n, nranks,
+                                                        _dptr(pairs_out), _dptr(dest_off), ws_ptr,
+                                                        ws.numel() - (ws_ptr - _dptr(ws)), self._stream()),
+                 "b2_shuffle_partition_u32_dev")
+        return pairs_out[:n], dest_off
+
+
+def wang_hash(key: int) -> int:
+    return int(_lib.lib().b2_wang_hash_u32(int(key) & 0xFFFFFFFF))
+
+
+def join_dest_rank(key: int, nranks: int) -> int:
+    return int(_lib.lib().b2_join_dest_rank(int(key) & 0xFFFFFFFF, int(nranks)))
+
+
+# ---------------------------------------------------------------------------------------------
+# operators (host batches in, host results out) — the reference's *Dpu classes
+# ---------------------------------------------------------------------------------------------
+FILTER_THRESHOLD = 1 << 30  # predicate v < 2^30: filter.c:25, filter_native.cc:59
+
+
+class FilterGpu:
+    """FilterDpu (host/filter/filter_dpu.cc:23-174): order-preserving ``v < threshold``."""
+
+    def __init__(self, ctx: Context, batches: Sequence[Any], threshold: int = FILTER_THRESHOLD):
+        self.ctx = ctx
+        self._cols = [_column(b, 0) for b in batches]
+        self.threshold = int(threshold)
+        self._timers = None
+
+    def Prepare(self) -> None:  # the reference loads the DPU binary here (filter_dpu.cc:23-32)
+        self._timers = Timers()
+
+    def _run(self):
+        tab = _PtrTable(self._cols)
+        counts = (C.c_int64 * max(tab.n, 1))()
+        total = C.c_uint64(0)
+        t1 = Timings()
+        lib, h = self.ctx._lib, self.ctx._h
+        self.ctx._ck(lib.b2_filter_lt_u32_host(h, tab.ptrs, tab.lens, tab.n, self.threshold, counts,
+                                               C.byref(total), C.byref(t1)), "b2_filter_lt_u32_host")
+        return tab, counts, total.value, t1
+
+    def Run(self) -> int:
+        """Number of selected rows (FilterDpu::Run, filter_dpu.cc:171-173)."""
+        return self.GetResult(_count_only=True)
+
+    def GetResult(self, _count_only: bool = False):
+        """One uint32 array per input batch, in batch order (ChunkedArray chunks, :162-166)."""
+        tab, counts, total, t1 = self._run()
+        # the reference's Run() is GetResult()->length(): the result is always pulled back
+        flat = np.empty(total, dtype=np.uint32)
+        ptrs = (C.c_void_p * max(tab.n, 1))()
+        off = 0
+        for b in range(tab.n):
+            ptrs[b] = flat.ctypes.data + 4 * off
+            off += counts[b]
+        t2 = Timings()
+        self.ctx._ck(self.ctx._lib.b2_filter_fetch_host(self.ctx._h, ptrs, tab.n, C.byref(t2)),
+                     "b2_filter_fetch_host")
+        self._timers = Timers.from_timings(t1, t2)
+        self._last = (t1, t2)
+        if _count_only:
+            return int(total)
+        bounds = np.concatenate([[0], np.cumsum(np.frombuffer(counts, dtype=np.int64, count=tab.n))])
+        return [flat[bounds[b]:bounds[b + 1]] for b in range(tab.n)]
+
+    def Timers(self):
+        return self._timers
+
+
+class SumGpu:
+    """SumDpu (host/aggr/aggr_dpu.cc:31-89): sum of a uint32 column as uint64."""
+
+    def __init__(self, ctx: Context, batches: Sequence[Any]):
+        self.ctx = ctx
+        self._cols = [_column(b, 0) for b in batches]
+        self._timers = None
+
+    def Prepare(self) -> None:
+        self._timers = Timers()
+
+    def Run(self) -> int:
+        tab = _PtrTable(self._cols)
+        out = C.c_uint64(0)
+        t = Timings()
+        self.ctx._ck(self.ctx._lib.b2_sum_u32_host(self.ctx._h, tab.ptrs, tab.lens, tab.n, C.byref(out),
+                                                   C.byref(t)), "b2_sum_u32_host")
+        self._timers = Timers.from_timings(t)
+        self._last = (t,)
+        return int(out.value)
+
+    def Timers(self):
+        return self._timers
+
+
+class TakeGpu:
+    """TakeDpu (host/take/take_dpu.cc:34-104): batch-local gather, no bounds check."""
+
+    def __init__(self, ctx: Context, batches: Sequence[Any], indices_batches: Sequence[Any]):
+        if len(batches) != len(indices_batches):
+            raise ValueError("values and indices must have the same number of batches")
+        self.ctx = ctx
+        self._vals = [_column(b, 0) for b in batches]
+        self._idx = [_column(b, 0) for b in indices_batches]
+        self._timers = None
+
+    def Prepare(self) -> None:
+        self._timers = Timers()
+
+    def Run(self):
+        """One uint32 array per batch (the reference returns a Table of one chunk per batch)."""
+        v, i = _PtrTable(self._vals), _PtrTable(self._idx)
+        total = sum(a.size for a in self._idx)
+        flat = np.empty(total, dtype=np.uint32)
+        ptrs = (C.c_void_p * max(i.n, 1))()
+        bounds = [0]
+        for b, a in enumerate(self._idx):
+            ptrs[b] = flat.ctypes.data + 4 * bounds[-1]
+            bounds.append(bounds[-1] + a.size)
+        t = Timings()
+        self.ctx._ck(self.ctx._lib.b2_take_u32_host(self.ctx._h, v.ptrs, v.lens, i.ptrs, i.lens, i.n,
+                                                    ptrs, C.byref(t)), "b2_take_u32_host")
+        self._timers = Timers.from_timings(t)
+        self._last = (t,)
+        return [flat[bounds[b]:bounds[b + 1]] for b in range(i.n)]
+
+    def Timers(self):
+        return self._timers
+
+
+class JoinGpu:
+    """JoinDpu (host/join/join_dpu.cc:144-400): inner join L.fk = R.pk, output (fk, y, x).
+
+    left batches have columns (fk_name, left payload), right batches (pk_name, right payload);
+    the payload is "the other column", whatever it is called (y / x in the benchmark,
+    v_l / v_r in JoinTest.SimpleTest, join_test.cc:45-64).
+    """
+
+    def __init__(self, ctx: Context, left_batches: Sequence[Any], right_batches: Sequence[Any],
+                 fk: str = "fk", pk: str = "pk"):
+        self.ctx = ctx
+        self.fk, self.pk = fk, pk
+        ln = _column_names(left_batches[0]) if len(left_batches) else [fk, "y"]
+        rn = _column_names(right_batches[0]) if len(right_batches) else [pk, "x"]
+        if len(ln) != 2 or len(rn) != 2:
+            raise ValueError("JoinGpu handles one key and one payload column per side")
+        self.lpay = [c for c in ln if c != fk][0]
+        self.rpay = [c for c in rn if c != pk][0]
+        self._l = ([_column(b, fk) for b in left_batches], [_column(b, self.lpay) for b in left_batches])
+        self._r = ([_column(b, pk) for b in right_batches], [_column(b, self.rpay) for b in right_batches])
+        self._timers = None
+
+    def Prepare(self) -> None:
+        self._timers = Timers()
+
+    def Run(self) -> dict:
+        """{fk: array, left payload: array, right payload: array}, row order unspecified."""
+        lt, rt = _PtrTable(self._l[0] + self._l[1]), _PtrTable(self._r[0] + self._r[1])
+        nlb, nrb = len(self._l[0]), len(self._r[0])
+        rows = C.c_uint64(0)
+        t1, t2 = Timings(), Timings()
+        lib, h = self.ctx._lib, self.ctx._h
+        self.ctx._ck(lib.b2_join_u32_host(h, lt.ptrs, lt.lens, nlb, rt.ptrs, rt.lens, nrb,
+                                          C.byref(rows), C.byref(t1)), "b2_join_u32_host")
+        n = int(rows.value)
+        out = [np.empty(n, dtype=np.uint32) for _ in range(3)]
+        self.ctx._ck(lib.b2_join_fetch_host(h, out[0].ctypes.data, out[1].ctypes.data,
+                                            out[2].ctypes.data, n, C.byref(t2)), "b2_join_fetch_host")
+        self._timers = Timers.from_timings(t1, t2)
+        self._last = (t1, t2)
+        return {self.fk: out[0], self.lpay: out[1], self.rpay: out[2]}
+
+    def Timers(self):
+        return self._timers
+
+
+class PartitionGpu:
+    """PartitionDpu (host/partition/partition_dpu.h:15-28): hash-partition record batches.
+
+    Run() returns ``nr_partitions`` record batches (dict column -> array); partition of a row =
+    top log2(nr_partitions) bits of wang_hash(key) (partition.c:20-28,45-46)."""
+
+    def __init__(self, ctx: Context, batches: Sequence[Any], nr_partitions: int, partition_key: str):
+        self.ctx = ctx
+        self.names = _column_names(batches[0]) if len(batches) else [partition_key]
+        self.key = partition_key
+        self.nparts = int(nr_partitions)
+        self._cols = {n: [_column(b, n) for b in batches] for n in self.names}
+        self._nb = len(batches)
+        self._timers = None
+
+    def Prepare(self) -> None:
+        self._timers = Timers()
+
+    def Run(self) -> list[dict]:
+        names = self.names
+        ncols = len(names)
+        arrays = [a for n in names for a in self._cols[n]]  # column-major
+        tab = _PtrTable(arrays)
+        lens = (C.c_int64 * max(self._nb, 1))(*[int(a.size) for a in self._cols[names[0]]])
+        rows = (C.c_int64 * self.nparts)()
+        t1, t2 = Timings(), Timings()
+        lib, h = self.ctx._lib, self.ctx._h
+        self.ctx._ck(lib.b2_partition_u32_host(h, tab.ptrs, lens, self._nb, ncols, names.index(self.key),
+                                               self.nparts, rows, C.byref(t1)), "b2_partition_u32_host")
+        outs = [{n: np.empty(rows[p], dtype=np.uint32) for n in names} for p in range(self.nparts)]
+        ptrs = (C.c_void_p * (self.nparts * ncols))()
+        for p in range(self.nparts):
+            for c, n in enumerate(names):
+                ptrs[p * ncols + c] = outs[p][n].ctypes.data
+        self.ctx._ck(lib.b2_partition_fetch_host(h, ptrs, self.nparts, ncols, C.byref(t2)),
+                     "b2_partition_fetch_host")
+        self._timers = Timers.from_timings(t1, t2)
+        self._last = (t1, t2)
+        return outs
+
+    def Timers(self):
+        return self._timers

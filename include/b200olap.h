@@ -1,0 +1,231 @@
+/*
+ * b200olap.h — C ABI of the B200 columnar-operator library (libb200olap.so).
+ *
+ * This header is the drop-in boundary that replaces dpu_olap's device layer:
+ *   - host/dpuext/dpuext.hpp      (dpu::DpuSet::allocate :710, load :739, exec :638,
+ *                                  copy :163/:277/:442-533, async().call/sync :860-898)
+ *   - host/dpuext/arrow_utils.cc  (arrow_copy_to_dpus :47-73, arrow_copy_from_dpus* :147-266)
+ *   - shared/umq/kernels.h        (enum Kernel :12-20, param structs :27-51)
+ *   - dpu/{filter,aggr,take,partition,join}/main.c + dpu/shared/kernels/ (the DPU programs)
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only. No C++/torch/Arrow types cross this boundary.
+ *   - Every entry point returns an int status (B2_OK == 0). No exception crosses the ABI.
+ *     (Reference convention: dpu_error_t + DPU_RETURN_NOT_OK, host/dpuext/status.h:7-12.)
+ *   - "_dev" entry points take DEVICE pointers and a cudaStream_t (as void*); they only enqueue
+ *     work on that stream and never synchronise (this is the reference's "dpu-work" leg).
+ *   - "_host" entry points take HOST pointers, one per Arrow record batch (data buffer #1 of a
+ *     non-nullable uint32 column, host/dpuext/arrow_utils.cc:23,60-66); they upload, run and
+ *     download inside the call and are synchronous at return (the reference's
+ *     copy-to-dpu / dpu-work / copy-from-dpu legs, reported in b2_timings).
+ *   - A b2_ctx is bound to ONE GPU and is NOT thread-safe (one ctx per host thread / per rank).
+ *   - Memory the library allocates is owned by the ctx / result handle and released by the
+ *     matching b2_*_free / b2_ctx_destroy; callers never free() library memory.
+ *   - Validity bitmaps are not supported: columns must be non-null, as the reference assumes
+ *     (it passes a nullptr bitmap, host/filter/filter_dpu.cc:91).
+ */
+#ifndef B200OLAP_H_
+#define B200OLAP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes (stable) ------------------------------------------------------------- */
+enum b2_status {
+  B2_OK = 0,
+  B2_ERR_INVALID = 1,      /* bad argument (null pointer, negative size, misaligned buffer) */
+  B2_ERR_CUDA = 2,         /* a CUDA runtime call failed; see b2_last_error */
+  B2_ERR_OOM = 3,          /* device or pinned-host allocation failed */
+  B2_ERR_UNSUPPORTED = 4,  /* valid request this build does not implement */
+  B2_ERR_WORKSPACE = 5,    /* caller-provided workspace too small */
+  B2_ERR_OVERFLOW = 6      /* result does not fit the caller-provided output capacity */
+};
+
+typedef struct b2_ctx b2_ctx;
+
+/* Phase timings of the last *_host call, in milliseconds. Names follow the reference's timers
+ * (host/filter/filter_dpu.cc:107-110): copy-to-dpu / dpu-work / copy-from-dpu / build-result. */
+typedef struct b2_timings {
+  double copy_to_dev_ms;   /* host->device, wall time the copies occupied their stream */
+  double dev_work_ms;      /* kernels (CUDA events on the compute stream) */
+  double copy_from_dev_ms; /* device->host */
+  double total_ms;         /* wall clock of the whole call */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t kernel_launches; /* kernels of this library launched by the call */
+  int32_t reserved;
+} b2_timings;
+
+/* ---- context (replaces dpu::DpuSet::allocate / load / dtor, dpuext.hpp:669-739) ---------- */
+int b2_version(void);
+const char* b2_strerror(int status);
+int b2_device_count(int* count);
+int b2_ctx_create(int device, b2_ctx** out);
+int b2_ctx_destroy(b2_ctx* ctx);
+/* Human-readable detail for the last non-OK status returned on this ctx (never NULL). */
+const char* b2_last_error(const b2_ctx* ctx);
+/* Kernels launched by this library on this ctx since creation (all entry points). */
+int64_t b2_launch_count(const b2_ctx* ctx);
+int b2_ctx_device(const b2_ctx* ctx);
+int b2_ctx_sm_count(const b2_ctx* ctx);
+
+/* ---- synthetic inputs (replaces host/generator for device-resident benchmarks) ----------- */
+/* One array per batch, bit-identical to arrow::random::RandomArrayGenerator's
+ * GenerateTypedDataNoNan for uint32 (host/generator/random.cc:103-109):
+ *   pcg32_fast rng(data_seed[b]);  std::uniform_int_distribution<uint32_t> dist(lo[b], hi[b]);
+ * data_seeds are the seeds ACTUALLY fed to pcg32_fast (i.e. seed()+1, random.cc:111-125,190-196).
+ * lo/hi may be NULL (full range). hi-lo+1 must be 2^32 or a power of two (the only shapes the
+ * reference's fixtures use; other ranges reject draws and cannot be generated in parallel)
+ * else B2_ERR_UNSUPPORTED. data_seeds/lo/hi are HOST arrays of length nbatches. */
+int b2_gen_u32_dev(b2_ctx* ctx, const uint64_t* data_seeds, const uint32_t* lo, const uint32_t* hi,
+                   int64_t nbatches, int64_t batch_len, uint32_t* d_out, void* stream);
+/* out[i] = (uint32_t)(start + i)   — generator::MakeIndexColumn, host/generator/generator.cc:59-71 */
+int b2_iota_u32_dev(b2_ctx* ctx, uint64_t start, int64_t n, uint32_t* d_out, void* stream);
+
+/* ---- Sum (replaces dpu/aggr/main.c:44-89 + dpu/shared/kernels/aggr.c:16-33) -------------- */
+/* *d_sum = sum of d_in[0..n) as uint64 (mod 2^64). One kernel launch. */
+int b2_sum_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint64_t* d_sum, void* stream);
+/* SumDpu::Run (host/aggr/aggr_dpu.cc:31-89): batches on the host, result on the host. */
+int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
+                    int64_t nbatches, uint64_t* sum, b2_timings* timings);
+
+/* ---- Filter (replaces dpu/shared/kernels/filter.c:57-177, predicate :25) ----------------- */
+/* Order-preserving selection of d_in[i] < threshold over nbatches equal-length batches packed
+ * back to back in d_in. Output rows are written compacted, in input order, to d_out (capacity
+ * must be >= nbatches*batch_len rows unless the caller knows a tighter bound);
+ * d_batch_end[b] (int64, nbatches entries) = number of selected rows in batches 0..b, so chunk b
+ * of the result (FilterDpu::GetResult returns one chunk per batch, filter_dpu.cc:89-96,162-166)
+ * is d_out[d_batch_end[b-1] .. d_batch_end[b]). d_total (may be NULL) receives the grand total.
+ * d_carry_in (may be NULL = 0): device int64 holding the output row at which this call starts;
+ * d_out indices, d_batch_end and d_total are all offset by it, so a column can be filtered in
+ * several calls (streamed chunks) that append to one compacted result without a host round trip
+ * (pass call k's d_total as call k+1's d_carry_in).
+ * d_ws: workspace of b2_filter_ws_bytes() bytes. */
+size_t b2_filter_ws_bytes(int64_t nbatches, int64_t batch_len);
+int b2_filter_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t batch_len,
+                         uint32_t threshold, uint32_t* d_out, int64_t* d_batch_end,
+                         int64_t* d_total, const int64_t* d_carry_in, void* d_ws, size_t ws_bytes,
+                         void* stream);
+/* Ragged variant: batch b occupies d_in[d_batch_off[b] .. d_batch_off[b+1]) (int64 device array
+ * of nbatches+1 entries; host copy h_batch_off is needed to size the launch). Empty batches ok. */
+size_t b2_filter_ragged_ws_bytes(const int64_t* h_batch_off, int64_t nbatches);
+int b2_filter_lt_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_in, const int64_t* h_batch_off,
+                                const int64_t* d_batch_off, int64_t nbatches, uint32_t threshold,
+                                uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
+                                const int64_t* d_carry_in, void* d_ws, size_t ws_bytes,
+                                void* stream);
+/* FilterDpu::GetResult (host/filter/filter_dpu.cc:104-169) in two steps, because the caller can
+ * only size its result buffers once the per-batch counts are known (the reference reads
+ * "output_buffer_length" first, then allocates and pulls "output_buffer", :57-83):
+ *   b2_filter_lt_u32_host  uploads, filters, keeps the result on the device, returns the
+ *                          per-batch selected counts in out_counts[nbatches];
+ *   b2_filter_fetch_host   downloads chunk b into out_ptrs[b] (capacity out_counts[b] rows).
+ * The pending result is dropped by the next *_host call on the ctx or b2_ctx_destroy. */
+int b2_filter_lt_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
+                          const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                          int64_t* out_counts, uint64_t* total, b2_timings* timings);
+int b2_filter_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int64_t nbatches,
+                         b2_timings* timings);
+
+/* ---- Take (replaces dpu/shared/kernels/take.c:12-47) ------------------------------------- */
+/* Batch-local gather, no bounds check (take.c:36, TakeOptions::NoBoundsCheck take_native.cc:27):
+ *   d_out[b*idx_len + j] = d_values[b*values_len + d_indices[b*idx_len + j]]. */
+int b2_take_u32_dev(b2_ctx* ctx, const uint32_t* d_values, int64_t values_len,
+                    const uint32_t* d_indices, int64_t idx_len, int64_t nbatches, uint32_t* d_out,
+                    void* stream);
+/* Ragged variant: device offset tables of nbatches+1 int64 each; processes the packed index
+ * positions [idx_begin, idx_end) (0 .. idx_off[nbatches] for the whole column). */
+int b2_take_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_values, const int64_t* d_values_off,
+                           const uint32_t* d_indices, const int64_t* d_idx_off, int64_t nbatches,
+                           int64_t idx_begin, int64_t idx_end, uint32_t* d_out, void* stream);
+/* TakeDpu::Run (host/take/take_dpu.cc:34-104): out_ptrs[b] has capacity idx_lens[b]. */
+int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64_t* value_lens,
+                     const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
+                     uint32_t* const* out_ptrs, b2_timings* timings);
+
+/* ---- Partition (replaces dpu/shared/kernels/partition.c:296-341) ------------------------- */
+/* The reference's hash and bucket: wang_hash_uint32 (partition.c:20-28), radix bucket =
+ * hash >> (32 - log2 P) (BUCKET_OF, partition.c:45-46). Host-callable so tests can pin it. */
+uint32_t b2_wang_hash_u32(uint32_t key);
+/* Radix-partition n rows into nparts (power of two, 1..2^20) partitions:
+ *   bucket(key) = (wang_hash(key) << skip_bits) >> (32 - log2 nparts)
+ * skip_bits > 0 skips hash bits already consumed by an outer partitioning (GPU id, pass 1).
+ * ncols columns (1..16): d_cols_in[0] is the key column; all columns are permuted alike into
+ * d_cols_out (key column + permutation first, then one gather per column — the reference's
+ * PartitionKernel + TakeKernel split, partitioner.cc:119-207). n must be < 2^32. d_part_off (int64, nparts+1) receives the partition boundaries in rows.
+ * Row order inside a partition is unspecified (as in the reference, which scatters under a
+ * mutex, partition.c:174-231). d_cols_in/d_cols_out are HOST arrays of device pointers. */
+size_t b2_partition_ws_bytes(int64_t n, int nparts);
+int b2_partition_u32_dev(b2_ctx* ctx, const uint32_t* const* d_cols_in, uint32_t* const* d_cols_out,
+                         int ncols, int64_t n, int nparts, int skip_bits, int64_t* d_part_off,
+                         void* d_ws, size_t ws_bytes, void* stream);
+/* PartitionDpu::Run (host/partition/partition_dpu.cc:31-135): host batches in; the library keeps
+ * the partitioned columns on the device until fetched. part_rows[nparts] receives the sizes;
+ * b2_partition_fetch_host copies partition p / column c into out_ptrs[p*ncols + c]. */
+int b2_partition_u32_host(b2_ctx* ctx, const uint32_t* const* col_batch_ptrs /*[ncols*nbatches], column-major*/,
+                          const int64_t* batch_lens, int64_t nbatches, int ncols, int key_col,
+                          int nparts, int64_t* part_rows, b2_timings* timings);
+int b2_partition_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int nparts, int ncols,
+                            b2_timings* timings);
+
+/* ---- Join (replaces kernel_hash_build/probe hash_build.c:9-35, hash_probe.c:9-46,
+ *            ht_put/ht_get hashtable.c:89-192, and JoinDpu::Run_internal join_dpu.cc:168-400) -- */
+/* Inner equi-join L.fk = R.pk with Arrow hash-join semantics (join_native.cc:31-36): every
+ * (l, r) pair with equal keys yields one output row (fk, y, x); unmatched rows are dropped;
+ * duplicate build keys yield one row per duplicate. Output row order is unspecified
+ * (partition-major, as JoinDpu's); parity is on the sorted multiset.
+ *   L = (d_fk, d_y) nl rows; R = (d_pk, d_x) nr rows; output columns d_out_fk/d_out_y/d_out_x
+ *   with capacity out_capacity rows each; *d_out_rows (uint64 on the device) = rows produced.
+ * If more than out_capacity rows match, the rows beyond capacity are not written but
+ * *d_out_rows still holds the true count (caller compares it with its capacity).
+ * *d_out_rows == UINT64_MAX reports that a hash-space slice overflowed its buffer (only possible
+ * when the workspace forced slicing and the key distribution is heavily skewed).
+ * hash_skip_bits: top hash bits already consumed by an outer routing step (log2 #GPUs in the
+ * sharded join, 0 otherwise).
+ * d_ws: 256 B aligned workspace. b2_join_ws_bytes() is the size at which the join runs in one
+ * go; with less (down to b2_join_min_ws_bytes()) it runs in 2..64 hash-space slices, re-reading
+ * the inputs once per slice. */
+size_t b2_join_ws_bytes(int64_t nl, int64_t nr);
+size_t b2_join_min_ws_bytes(int64_t nl, int64_t nr);
+int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
+                    const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, uint32_t* d_out_fk,
+                    uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                    uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
+                    void* stream);
+/* Same join over rows packed as 8-byte pairs, key in the low and payload in the high 32 bits
+ * (little endian: {uint32 key; uint32 payload}) — the layout the multi-GPU shuffle delivers. */
+int b2_join_pairs_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, int64_t nl, const uint64_t* d_r_pairs,
+                      int64_t nr, uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x,
+                      int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits, void* d_ws,
+                      size_t ws_bytes, void* stream);
+/* JoinDpu::Run: host batches in; result stays on the device until fetched.
+ * l_ptrs = [fk batches..., y batches...] (2*nl_batches), r_ptrs = [pk..., x...] (2*nr_batches). */
+int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* l_lens,
+                     int64_t nl_batches, const uint32_t* const* r_ptrs, const int64_t* r_lens,
+                     int64_t nr_batches, uint64_t* out_rows, b2_timings* timings);
+int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
+                       int64_t capacity_rows, b2_timings* timings);
+
+/* ---- multi-GPU join exchange (the step that replaces the reference's host-mediated
+ *      DPU->host->DPU repartition, partitioner.cc:350-375 + join_dpu.cc:269,293) -------------- */
+/* Destination rank of a key when the join is sharded over nranks (power of two) GPUs:
+ * top log2(nranks) bits of wang_hash(key). */
+int b2_join_dest_rank(uint32_t key, int nranks);
+/* Route n (key, val) rows by destination rank: d_pairs_out receives the rows as 8-byte pairs
+ * grouped by destination, d_dest_off (int64, nranks+1) the group boundaries — the send counts of
+ * the all-to-all. The receiver joins with b2_join_pairs_dev(hash_skip_bits = log2 nranks). */
+size_t b2_shuffle_ws_bytes(int64_t n, int nranks);
+int b2_shuffle_partition_u32_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
+                                 int nranks, uint64_t* d_pairs_out, int64_t* d_dest_off, void* d_ws,
+                                 size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OLAP_H_ */

@@ -1,0 +1,437 @@
+"""GPU parity tests of the device-resident C-ABI entry points (b2_*_dev) against the CPU oracle.
+
+Bit-exact everywhere (integer work): filter output + per-batch chunk boundaries, sum, take and the
+generator must match exactly; partition must route every row to the oracle's bucket and keep the
+columns aligned; join must match as a sorted multiset of (fk, y, x) rows (join_test.cc:27-38).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def sha(*arrays) -> str:
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a, dtype=np.uint32).tobytes())
+    return h.hexdigest()
+
+
+# ---- generator ----------------------------------------------------------------------------------
+def test_gen_matches_real_libstdcxx_vectors(ctx, golden):
+    for name, v in golden["generator_golden"].items():
+        if not isinstance(v, dict):
+            continue
+        span = v["hi"] - v["lo"] + 1
+        if span & (span - 1):
+            continue  # rejection-sampled spans are refused by the device generator (tested below)
+        a = host(ctx.gen_dev([v["seed"] + 1], 1, v["n"], v["lo"], v["hi"]))
+        assert list(a[:8]) == v["first"], name
+        assert int(a[-1]) == v["last"], name
+        assert int(a.astype(np.uint64).sum()) == v["sum"], name
+
+
+def test_gen_refuses_rejection_spans(ctx):
+    from dpu_olap_b200._lib import B2Error
+    with pytest.raises(B2Error) as e:
+        ctx.gen_dev([5], 1, 16, 10, 1009)
+    assert e.value.status == 4  # B2_ERR_UNSUPPORTED
+
+
+def test_gen_batches_vs_oracle(ctx):
+    g = oracle.RandomArrayGenerator(42)
+    seeds = [g.data_seed() for _ in range(5)]
+    for batch_len in (1, 1000, 65536, 200_000):
+        got = host(ctx.gen_dev(seeds, 5, batch_len)).reshape(5, batch_len)
+        for b, s in enumerate(seeds):
+            assert np.array_equal(got[b], oracle.gen_u32(s, batch_len)), (batch_len, b)
+    lo = np.array([i << 21 for i in range(5)], dtype=np.uint32)
+    hi = lo + ((1 << 21) - 1)
+    got = host(ctx.gen_dev(seeds, 5, 4096, lo, hi)).reshape(5, 4096)
+    for b, s in enumerate(seeds):
+        assert np.array_equal(got[b], oracle.gen_u32(s, 4096, int(lo[b]), int(hi[b])))
+
+
+def test_iota(ctx):
+    assert np.array_equal(host(ctx.iota_dev(2**32 - 5, 10)), oracle.iota_u32(2**32 - 5, 10))
+
+
+# ---- sum ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 5, 4095, 4096, 4097, 65536, 1_000_003, 8 * 1024 * 1024 + 3])
+def test_sum_sizes(ctx, n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    out = ctx.sum_dev(dev(a) if n else torch.empty(0, dtype=torch.int32, device="cuda"))
+    assert int(out.cpu().numpy().view(np.uint64)[0]) == oracle.sum_u32(a)
+
+
+def test_sum_unaligned_and_max(ctx):
+    a = np.full(1_000_000, 0xFFFFFFFF, dtype=np.uint32)
+    d = dev(a)
+    for off in (0, 1, 2, 3, 5):
+        out = ctx.sum_dev(d[off:])
+        assert int(out.cpu().numpy().view(np.uint64)[0]) == oracle.sum_u32(a[off:])
+
+
+def test_sum_reference_kats(ctx, golden):
+    assert int(ctx.sum_dev(dev([0, 2, 3, 8, 9])).cpu().numpy().view(np.uint64)[0]) == 22  # aggr_test.cc:24-35
+    g = oracle.RandomArrayGenerator(42)
+    seeds = [g.data_seed() for _ in range(128)]
+    col = ctx.gen_dev(seeds, 128, 65536)
+    assert int(ctx.sum_dev(col).cpu().numpy().view(np.uint64)[0]) == golden["arrow_golden"]["sum_128x65536"]["sum"]
+
+
+def test_sum_idempotent_relaunch(ctx):
+    a = dev(np.arange(100_000, dtype=np.uint32))
+    r = [int(ctx.sum_dev(a).cpu().numpy()[0]) for _ in range(3)]
+    assert r[0] == r[1] == r[2] == 99_999 * 100_000 // 2
+
+
+# ---- filter ---------------------------------------------------------------------------------------
+def run_filter(ctx, batches, thr=1 << 30):
+    nb = len(batches)
+    bl = batches[0].size if nb else 0
+    col = dev(np.concatenate(batches)) if nb and bl else torch.empty(0, dtype=torch.int32, device="cuda")
+    out, end, total = ctx.filter_dev(col, nb, bl, thr)
+    torch.cuda.synchronize()
+    end = end.cpu().numpy()[:nb]
+    total = int(total.cpu().numpy()[0])
+    flat = host(out)[:total]
+    return flat, end, total
+
+
+def check_filter(ctx, batches, thr=1 << 30):
+    flat, end, total = run_filter(ctx, batches, thr)
+    exp = [oracle.filter_lt(b, thr) for b in batches]
+    exp_end = np.cumsum([e.size for e in exp]) if batches else np.array([], dtype=np.int64)
+    assert total == (int(exp_end[-1]) if len(exp_end) else 0)
+    assert np.array_equal(end, exp_end)
+    if exp:
+        assert np.array_equal(flat, np.concatenate(exp))
+
+
+def test_filter_reference_kats(ctx):
+    check_filter(ctx, [np.array([0, 2, 3, 8, 9], dtype=np.uint32)])  # filter_test.cc:24-31
+    keep = {5, 8, 9, 100, 270}  # filter_test.cc:33-61
+    v = np.array([i if i in keep else i + (1 << 30) for i in range(4096)], dtype=np.uint32)
+    flat, end, total = run_filter(ctx, [v])
+    assert list(flat) == [5, 8, 9, 100, 270] and total == 5
+
+
+def test_filter_longer_test_vs_arrow_digest(ctx, golden):  # filter_test.cc:63-78 + 128-batch digest
+    ref = golden["arrow_golden"]["filter_128x65536"]
+    g = oracle.RandomArrayGenerator(42)
+    seeds = [g.data_seed() for _ in range(128)]
+    col = ctx.gen_dev(seeds, 128, 65536)
+    out, end, total = ctx.filter_dev(col, 128, 65536, 1 << 30)
+    torch.cuda.synchronize()
+    end = end.cpu().numpy()
+    assert int(total.cpu()[0]) == ref["rows"]
+    assert np.diff(np.concatenate([[0], end]))[:8].tolist() == ref["per_batch_first8"]
+    flat = host(out)[: ref["rows"]]
+    assert sha(flat) == ref["sha256"]
+    assert sha(flat[: end[0]]) == ref["batch0_sha256"]
+
+
+@pytest.mark.parametrize("nb,bl", [(0, 0), (1, 0), (3, 1), (1, 8191), (1, 8192), (1, 8193), (7, 1000),
+                                   (5, 65536), (3, 65537), (2, 100_003), (40, 8192)])
+def test_filter_shapes(ctx, nb, bl):
+    rng = np.random.default_rng(nb * 1000 + bl)
+    check_filter(ctx, [rng.integers(0, 2**32, size=bl, dtype=np.uint32) for _ in range(nb)])
+
+
+@pytest.mark.parametrize("thr", [0, 1, 42_949_673, 429_496_730, 1 << 31, 0xFFFFFFFF])
+def test_filter_selectivities(ctx, thr):  # 0 %, ~0 %, 1 %, 10 %, 50 %, ~100 %
+    rng = np.random.default_rng(thr % 1000)
+    batches = [rng.integers(0, 2**32, size=65536, dtype=np.uint32) for _ in range(20)]
+    batches[3][:] = 0xFFFFFFFF  # a batch that selects nothing (unless thr is max) ...
+    batches[4][:] = 0           # ... and one that selects everything (unless thr is 0)
+    check_filter(ctx, batches, thr)
+
+
+def test_filter_many_tiles_lookback_chain(ctx):
+    """> 32 tiles per look-back window and thousands of tiles: every tile's prefix must chain."""
+    rng = np.random.default_rng(7)
+    batches = [rng.integers(0, 2**32, size=65536, dtype=np.uint32) for _ in range(512)]
+    check_filter(ctx, batches)
+
+
+def test_filter_ragged(ctx):
+    rng = np.random.default_rng(11)
+    lens = [0, 5, 8192, 0, 8193, 1, 70_000, 0, 4096, 3]
+    batches = [rng.integers(0, 2**32, size=n, dtype=np.uint32) for n in lens]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    col = dev(np.concatenate(batches))
+    out, end, total = ctx.filter_ragged_dev(col, off, 1 << 30)
+    torch.cuda.synchronize()
+    exp = [oracle.filter_lt(b) for b in batches]
+    assert np.array_equal(end.cpu().numpy()[: len(lens)], np.cumsum([e.size for e in exp]))
+    assert np.array_equal(host(out)[: int(total.cpu()[0])], np.concatenate(exp))
+
+
+def test_filter_carry_in_appends(ctx):
+    """Two calls chained through d_carry_in produce one compacted result (streaming upload path)."""
+    rng = np.random.default_rng(5)
+    a = [rng.integers(0, 2**32, size=8192 * 3, dtype=np.uint32) for _ in range(2)]
+    b = [rng.integers(0, 2**32, size=8192 * 3, dtype=np.uint32) for _ in range(3)]
+    out = torch.empty(5 * 8192 * 3, dtype=torch.int32, device="cuda")
+    _, end_a, tot_a = ctx.filter_dev(dev(np.concatenate(a)), 2, 8192 * 3, 1 << 30, out=out)
+    _, end_b, tot_b = ctx.filter_dev(dev(np.concatenate(b)), 3, 8192 * 3, 1 << 30, out=out, carry_in=tot_a)
+    torch.cuda.synchronize()
+    exp = [oracle.filter_lt(x) for x in a + b]
+    ends = np.concatenate([end_a.cpu().numpy()[:2], end_b.cpu().numpy()[:3]])
+    assert np.array_equal(ends, np.cumsum([e.size for e in exp]))
+    assert np.array_equal(host(out)[: int(tot_b.cpu()[0])], np.concatenate(exp))
+
+
+def test_filter_idempotent_and_sorted_property(ctx):
+    """filter(filter(x)) == filter(x); the output of a sorted column is a prefix of it."""
+    col = np.sort(np.random.default_rng(3).integers(0, 2**32, size=8 * 65536, dtype=np.uint32))
+    flat, _, total = run_filter(ctx, list(col.reshape(8, 65536)))
+    assert np.array_equal(flat, col[:total])
+    pad = (-total) % 8
+    again = np.concatenate([flat, np.full(pad, 0xFFFFFFFF, dtype=np.uint32)])
+    flat2, _, total2 = run_filter(ctx, list(again.reshape(8, -1)))
+    assert total2 == total and np.array_equal(flat2, flat)
+
+
+# ---- take -----------------------------------------------------------------------------------------
+def test_take_reference_kats(ctx, golden):
+    out = ctx.take_dev(dev([0, 2, 3, 8, 9]), 5, dev([0, 1, 4]), 3, 1)  # take_test.cc:24-46
+    assert list(host(out)) == [0, 2, 9]
+    ref = golden["arrow_golden"]["take_128x65536_8192"]  # take_test.cc:48-72
+    g = oracle.RandomArrayGenerator(42)
+    vseeds = [g.data_seed() for _ in range(128)]
+    iseeds = [g.data_seed() for _ in range(128)]
+    vals = ctx.gen_dev(vseeds, 128, 65536)
+    idx = ctx.gen_dev(iseeds, 128, 8192, 0, 65535)
+    out = host(ctx.take_dev(vals, 65536, idx, 8192, 128))
+    assert sha(out) == ref["sha256"]
+    assert [int(v) for v in out[:8]] == ref["batch0_first8"]
+
+
+@pytest.mark.parametrize("nb,vl,il", [(1, 1, 1), (3, 7, 5), (4, 1000, 4096), (2, 4 << 20, 512 << 10),
+                                      (5, 65536, 8190), (3, 10, 0)])
+def test_take_shapes(ctx, nb, vl, il):
+    rng = np.random.default_rng(nb + vl + il)
+    vals = rng.integers(0, 2**32, size=(nb, vl), dtype=np.uint32)
+    idx = rng.integers(0, vl, size=(nb, il), dtype=np.uint32)
+    out = ctx.take_dev(dev(vals), vl, dev(idx) if il else torch.empty(0, dtype=torch.int32, device="cuda"), il, nb)
+    exp = np.concatenate([oracle.take(vals[b], idx[b]) for b in range(nb)]) if il else np.array([], np.uint32)
+    assert np.array_equal(host(out)[: nb * il], exp)
+
+
+def test_take_ragged(ctx):
+    rng = np.random.default_rng(9)
+    vlens, ilens = [5, 1000, 1, 70_000], [3, 0, 10, 12_345]
+    vals = [rng.integers(0, 2**32, size=n, dtype=np.uint32) for n in vlens]
+    idx = [rng.integers(0, v, size=n, dtype=np.uint32) for v, n in zip(vlens, ilens)]
+    voff = np.concatenate([[0], np.cumsum(vlens)])
+    ioff = np.concatenate([[0], np.cumsum(ilens)])
+    out = ctx.take_ragged_dev(dev(np.concatenate(vals)), voff, dev(np.concatenate(idx)), ioff)
+    assert np.array_equal(host(out), np.concatenate([oracle.take(v, i) for v, i in zip(vals, idx)]))
+
+
+# ---- partition ------------------------------------------------------------------------------------
+def check_partition(ctx, cols, nparts, skip_bits=0):
+    outs, off = ctx.partition_dev([dev(c) for c in cols], nparts, skip_bits)
+    torch.cuda.synchronize()
+    off = off.cpu().numpy()
+    outs = [host(o) for o in outs]
+    n = cols[0].size
+    assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) >= 0)
+    ids = oracle.partition_ids(cols[0], nparts, skip_bits)
+    assert np.array_equal(np.diff(off), np.bincount(ids, minlength=nparts))
+    # every output row sits in the partition its key hashes to
+    got_ids = oracle.partition_ids(outs[0], nparts, skip_bits)
+    assert np.array_equal(got_ids, np.repeat(np.arange(nparts, dtype=np.uint32), np.diff(off)))
+    # rows are permuted as a whole: same multiset of full rows
+    a = oracle.sort_rows(*cols)
+    b = oracle.sort_rows(*outs)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    return outs, off
+
+
+def test_partition_reference_kat(ctx):  # partition_test.cc:21-57
+    outs, off = check_partition(ctx, [np.array([0, 2, 3, 8], np.uint32), np.array([100, 101, 102, 103], np.uint32)], 2)
+    assert np.diff(off).tolist() == [3, 1]
+    assert int(outs[0].astype(np.uint64).sum()) == 13 and int(outs[1].astype(np.uint64).sum()) == 406
+
+
+@pytest.mark.parametrize("n,nparts,ncols", [(0, 4, 2), (1, 1, 1), (1000, 2, 3), (8192, 1024, 2), (8193, 32, 2),
+                                            (300_000, 1024, 2), (1_000_003, 64, 3), (2_000_000, 4096, 2),
+                                            (3_000_000, 1 << 14, 2)])
+def test_partition_shapes(ctx, n, nparts, ncols):
+    rng = np.random.default_rng(n + nparts)
+    cols = [rng.integers(0, 2**32, size=n, dtype=np.uint32) for _ in range(ncols)]
+    check_partition(ctx, cols, nparts)
+
+
+def test_partition_large_test_balance(ctx):  # partition_test.cc:59-92 (128 x 65536, 32 partitions)
+    g = oracle.RandomArrayGenerator(42)
+    cols = [np.concatenate([g.uint32(65536) for _ in range(16)]) for _ in range(3)]
+    _, off = check_partition(ctx, cols, 32)
+    cnt = np.diff(off)
+    assert np.all(np.abs(cnt - cols[0].size / 32) / (cols[0].size / 32) <= 0.1)
+
+
+def test_partition_skew_and_skip_bits(ctx):
+    rng = np.random.default_rng(1)
+    keys = rng.integers(0, 50, size=500_000, dtype=np.uint32)  # 50 distinct keys: heavy skew
+    check_partition(ctx, [keys, np.arange(keys.size, dtype=np.uint32)], 256)
+    keys = rng.integers(0, 2**32, size=200_000, dtype=np.uint32)
+    check_partition(ctx, [keys, keys ^ 0x5A5A5A5A], 128, skip_bits=3)
+
+
+# ---- join -----------------------------------------------------------------------------------------
+def run_join(ctx, fk, y, pk, x, cap=None, ws_bytes=None, skip_bits=0):
+    ws = None
+    if ws_bytes is not None:
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+    e = lambda a: dev(a) if len(a) else torch.empty(0, dtype=torch.int32, device="cuda")
+    o_fk, o_y, o_x, rows = ctx.join_dev(e(fk), e(y), e(pk), e(x), out_capacity=cap, ws=ws, skip_bits=skip_bits)
+    torch.cuda.synchronize()
+    n = int(rows.cpu().numpy().view(np.uint64)[0])
+    return host(o_fk)[:n], host(o_y)[:n], host(o_x)[:n], n
+
+
+def check_join(ctx, fk, y, pk, x, **kw):
+    exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))
+    g_fk, g_y, g_x, n = run_join(ctx, fk, y, pk, x, cap=max(exp[0].size, 1), **kw)
+    assert n == exp[0].size
+    got = oracle.sort_rows(g_fk, g_y, g_x)
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b)
+
+
+def test_join_simple_test(ctx):  # join_test.cc:40-80
+    fk = np.array([0, 2, 3, 8, 9, 10, 12, 13, 18, 19], np.uint32)
+    vl = fk + 100
+    pk = np.array([3, 8, 9, 0, 12, 13, 18, 19, 10, 2], np.uint32)
+    vr = pk + 50
+    check_join(ctx, fk, vl, pk, vr)
+
+
+def test_join_large_test_vs_arrow_digest(ctx, golden):  # join_test.cc:82-121
+    ref = golden["arrow_golden"]["join_128x65536"]
+    g = oracle.RandomArrayGenerator(42)
+    nb, bs = 128, 65536
+    xs = [g.data_seed() for _ in range(nb)]
+    ys = [g.data_seed() for _ in range(nb)]
+    fs = [g.data_seed() for _ in range(nb)]
+    x = ctx.gen_dev(xs, nb, bs)
+    pk = ctx.iota_dev(0, nb * bs)
+    y = ctx.gen_dev(ys, nb, bs)
+    lo = np.array([i * bs for i in range(nb)], dtype=np.uint32)
+    fk = ctx.gen_dev(fs, nb, bs, lo, lo + (bs - 1))
+    o_fk, o_y, o_x, rows = ctx.join_dev(fk, y, pk, x)
+    torch.cuda.synchronize()
+    n = int(rows.cpu()[0])
+    assert n == ref["rows"] == nb * bs  # join_test.cc:115-116
+    got = oracle.sort_rows(host(o_fk)[:n], host(o_y)[:n], host(o_x)[:n])
+    assert sha(*got) == ref["sorted_sha256"]
+    assert oracle.triple_checksum(*got) == ref["checksum"]
+
+
+@pytest.mark.parametrize("nl,nr", [(0, 0), (0, 10), (10, 0), (1, 1), (100, 7), (7, 100), (5000, 5000),
+                                   (100_000, 30_000), (1 << 20, 1 << 20), (3_000_000, 500_000)])
+def test_join_shapes_unique_build(ctx, nl, nr):
+    rng = np.random.default_rng(nl * 7 + nr)
+    pk = rng.permutation(np.arange(nr, dtype=np.uint32) * 3 + 1) if nr else np.array([], np.uint32)
+    x = rng.integers(0, 2**32, size=nr, dtype=np.uint32)
+    # half of the probe keys miss (inner join drops them; the DPU path would assert)
+    fk = rng.integers(0, max(3 * nr, 1) * 2, size=nl, dtype=np.uint32)
+    y = rng.integers(0, 2**32, size=nl, dtype=np.uint32)
+    check_join(ctx, fk, y, pk, x)
+
+
+def test_join_duplicates_both_sides(ctx):
+    rng = np.random.default_rng(2)
+    pk = rng.integers(0, 2000, size=20_000, dtype=np.uint32)   # ~10 duplicates per build key
+    x = np.arange(pk.size, dtype=np.uint32)
+    fk = rng.integers(0, 2500, size=30_000, dtype=np.uint32)
+    y = np.arange(fk.size, dtype=np.uint32) + 7
+    check_join(ctx, fk, y, pk, x)
+
+
+def test_join_heavy_skew_oversized_partition(ctx):
+    """One build key repeated 20000 times: its partition exceeds the shared-memory table and is
+    built in chunks; extreme key values exercise the empty-slot marker."""
+    pk = np.concatenate([np.full(20_000, 12345, np.uint32), np.array([0, 0xFFFFFFFF, 0xFFFFFFFE, 1], np.uint32)])
+    x = np.arange(pk.size, dtype=np.uint32)
+    fk = np.array([12345, 0xFFFFFFFF, 0, 5, 12345, 0xFFFFFFFE], np.uint32)
+    y = np.arange(fk.size, dtype=np.uint32)
+    check_join(ctx, fk, y, pk, x)
+
+
+def test_join_capacity_overflow_reports_true_count(ctx):
+    pk = np.zeros(100, np.uint32)
+    fk = np.zeros(100, np.uint32)
+    _, _, _, n = run_join(ctx, fk, fk, pk, pk, cap=10)
+    assert n == 10_000  # true match count although only 10 rows were written
+
+
+def test_join_sliced_small_workspace(ctx):
+    """With a workspace below b2_join_ws_bytes the join runs in hash-space slices."""
+    rng = np.random.default_rng(4)
+    nr = nl = 1 << 21
+    pk = rng.permutation(nr).astype(np.uint32)
+    x = rng.integers(0, 2**32, size=nr, dtype=np.uint32)
+    fk = rng.integers(0, nr, size=nl, dtype=np.uint32)
+    y = rng.integers(0, 2**32, size=nl, dtype=np.uint32)
+    full, small = ctx.join_ws_bytes(nl, nr), ctx.join_min_ws_bytes(nl, nr)
+    assert small < full
+    check_join(ctx, fk, y, pk, x, ws_bytes=(full + small) // 3)
+    from dpu_olap_b200._lib import B2Error
+    with pytest.raises(B2Error) as e:
+        run_join(ctx, fk, y, pk, x, ws_bytes=small // 2)
+    assert e.value.status == 5  # B2_ERR_WORKSPACE
+
+
+def test_join_skip_bits_matches_shuffle_routing(ctx):
+    """Sharded join building blocks: route rows by b2_shuffle_partition (top hash bits), join each
+    rank's share with hash_skip_bits, and the union equals the unsharded join."""
+    from dpu_olap_b200.ops import join_dest_rank
+    rng = np.random.default_rng(8)
+    nr = nl = 300_000
+    pk = rng.permutation(nr).astype(np.uint32)
+    x = rng.integers(0, 2**32, size=nr, dtype=np.uint32)
+    fk = rng.integers(0, nr, size=nl, dtype=np.uint32)
+    y = rng.integers(0, 2**32, size=nl, dtype=np.uint32)
+    G = 4
+    lp, loff = ctx.shuffle_partition_dev(dev(fk), dev(y), G)
+    rp, roff = ctx.shuffle_partition_dev(dev(pk), dev(x), G)
+    torch.cuda.synchronize()
+    loff, roff = loff.cpu().numpy(), roff.cpu().numpy()
+    assert loff[-1] == nl and roff[-1] == nr
+    lkeys = (lp.cpu().numpy().view(np.uint64) & 0xFFFFFFFF).astype(np.uint32)
+    for r in range(G):
+        seg = lkeys[loff[r]:loff[r + 1]]
+        assert all(join_dest_rank(int(k), G) == r for k in seg[:50])
+        assert np.array_equal(oracle.partition_ids(seg, G), np.full(seg.size, r, np.uint32))
+    parts = []
+    for r in range(G):
+        l_r, r_r = lp[loff[r]:loff[r + 1]], rp[roff[r]:roff[r + 1]]
+        o = ctx.join_pairs_dev(l_r, r_r, out_capacity=max(l_r.numel(), 1), skip_bits=2)
+        torch.cuda.synchronize()
+        n = int(o[3].cpu()[0])
+        parts.append([host(t)[:n] for t in o[:3]])
+    got = oracle.sort_rows(*[np.concatenate([p[c] for p in parts]) for c in range(3)])
+    exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b)
