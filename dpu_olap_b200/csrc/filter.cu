@@ -7,14 +7,15 @@
 // predicate is `item < (1 << 30)` (filter.c:25; Acero side: filter_native.cc:59).
 //
 // B200 design: ONE pass over the column (4 B read per row + 4 B written per selected row):
-//   * a tile is 8192 rows = 512 threads x 4 x 128-bit streaming loads, laid out so every warp
+//   * a tile is 4096 rows = 256 threads x 4 x 128-bit streaming loads, laid out so every warp
 //     owns 512 consecutive rows (each warp-level load is one fully coalesced 512 B request);
-//   * ranks inside a warp come from __ballot_sync/__popc (no shuffles), the 64 (warp,segment)
-//     counts of the CTA are scanned by warp 0;
+//     six CTAs are resident per SM so the phases of different tiles overlap;
+//   * ranks inside a warp come from __ballot_sync/__popc (no shuffles); the 32 (warp,segment)
+//     counts of the CTA are scanned redundantly by every warp (one count per lane);
 //   * tiles are chained by a decoupled look-back over single-word 64-bit descriptors
-//     (2 status bits | 62-bit running count, so 2^34-row columns need no second level);
-//     tile ids are handed out by an atomic ticket so a tile's predecessors are always running
-//     or finished (forward progress);
+//     (2 status bits | 62-bit running count, so 2^34-row columns need no second level), run by
+//     warp 0 WHILE the other warps already compact the tile into shared memory — tile-local
+//     positions do not depend on the running count;
 //   * selected rows are staged in shared memory and written with fully coalesced stores.
 // Tiles never straddle a batch boundary, so the inclusive count of the last tile of batch b is
 // the end offset of result chunk b (FilterDpu::GetResult returns one chunk per input batch,
@@ -24,39 +25,44 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 256;
 constexpr int kVecPerThread = 4;                       // uint4 loads per thread
-constexpr int kTile = kThreads * kVecPerThread * 4;    // 8192 rows
+constexpr int kTile = kThreads * kVecPerThread * 4;    // 4096 rows
 constexpr int kWarps = kThreads / 32;
-constexpr int kSegs = kWarps * kVecPerThread;          // 64 (warp, segment) counts per tile
+constexpr int kSegs = kWarps * kVecPerThread;          // 32 (warp, segment) counts per tile
+static_assert(kSegs == 32, "one (warp, segment) count per lane");
 
-struct FilterWs {           // header of the caller workspace
-  unsigned long long ticket;
-  unsigned long long pad[7];
+struct FilterWs {           // header of the caller workspace (reserved)
+  unsigned long long pad[8];
 };
 
 static inline int64_t tiles_of(int64_t len) { return (len + kTile - 1) / kTile; }
 
+// 1 if a < b (unsigned) else 0, as an INTEGER: keeps the 16 per-row predicate results of a thread
+// in one mask register instead of 16 predicate registers (ptxas has 7 and gives up otherwise).
+__device__ __forceinline__ uint32_t lt_bit(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r & 1u;
+}
+
+// Tile id = blockIdx.x: CTAs are dispatched in increasing block order, so every predecessor of a
+// tile that waits in the look-back is already resident or finished (the same assumption CUB's
+// single-pass scan and select make).
 template <bool kUniform>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 6)
 filter_lt_u32_kernel(const uint32_t* __restrict__ in, uint32_t thr, uint32_t* __restrict__ out,
                      int64_t batch_len, int64_t tiles_per_batch,          // uniform layout
                      const int64_t* __restrict__ batch_off,               // ragged layout
                      const int64_t* __restrict__ tile_first, int64_t nbatches,
-                     const int64_t* __restrict__ carry_in, FilterWs* __restrict__ ws,
-                     uint64_t* __restrict__ desc) {
+                     const int64_t* __restrict__ carry_in, uint64_t* __restrict__ desc) {
   __shared__ uint32_t stage[kTile];
   __shared__ uint32_t seg_cnt[kSegs];
-  __shared__ uint32_t seg_off[kSegs];
-  __shared__ int64_t s_tile;
   __shared__ uint64_t s_excl;
-  __shared__ uint32_t s_total;
+  __shared__ uint32_t seg_off[kSegs];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) s_tile = (int64_t)atomicAdd(&ws->ticket, 1ull);
-  __syncthreads();
-  const int64_t tile = s_tile;
+  const int64_t tile = blockIdx.x;
 
   // tile -> rows [row0, row0 + len)
   int64_t row0, len;
@@ -76,7 +82,7 @@ filter_lt_u32_kernel(const uint32_t* __restrict__ in, uint32_t thr, uint32_t* __
   }
   if (len > kTile) len = kTile;
 
-  // ---- load + predicate ----
+  // ---- load + predicate: warp w owns rows [w*512, w*512+512), segment j = 128 rows ----
   uint32_t v[kVecPerThread][4];
   uint32_t mask = 0;  // bit (j*4+e) set <=> element selected
   const uint32_t* __restrict__ src = in + row0;
@@ -90,7 +96,7 @@ filter_lt_u32_kernel(const uint32_t* __restrict__ in, uint32_t thr, uint32_t* __
     for (int j = 0; j < kVecPerThread; ++j) {
       v[j][0] = q[j].x; v[j][1] = q[j].y; v[j][2] = q[j].z; v[j][3] = q[j].w;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) mask |= (uint32_t)(v[j][e] < thr) << (j * 4 + e);
+      for (int e = 0; e < 4; ++e) mask |= lt_bit(v[j][e], thr) << (j * 4 + e);
     }
   } else {
 #pragma unroll
@@ -101,7 +107,7 @@ filter_lt_u32_kernel(const uint32_t* __restrict__ in, uint32_t thr, uint32_t* __
         v[j][e] = 0;
         if ((int64_t)i < len) {
           v[j][e] = ld_stream_u32(src + i);
-          mask |= (uint32_t)(v[j][e] < thr) << (j * 4 + e);
+          mask |= lt_bit(v[j][e], thr) << (j * 4 + e);
         }
       }
     }
@@ -124,28 +130,26 @@ filter_lt_u32_kernel(const uint32_t* __restrict__ in, uint32_t thr, uint32_t* __
   }
   __syncthreads();
 
-  // ---- warp 0: scan the 64 segment counts, then chain with the previous tiles ----
-  if (warp == 0) {
-    const uint32_t c0 = seg_cnt[2 * lane], c1 = seg_cnt[2 * lane + 1];
-    uint32_t incl = c0 + c1;
+  // ---- every warp scans the 32 segment counts itself (one per lane; warp 0 needs the total) ----
+  const uint32_t c = seg_cnt[lane];
+  uint32_t incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const uint32_t excl = incl - (c0 + c1);
-    seg_off[2 * lane] = excl;
-    seg_off[2 * lane + 1] = excl + c0;
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint64_t prefix = lookback(desc, tile, total, carry_in);
-    if (lane == 0) {
-      s_excl = prefix;
-      s_total = total;
-    }
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  // (offsets go through shared memory: fetching them with a shuffle from a warp-uniform lane
+  //  index makes ptxas 12.9 fail register allocation for this kernel)
+  if (warp == 1) seg_off[lane] = incl - c;
   __syncthreads();
+  // warp 0 chains the tile with its predecessors while the other warps already compact
+  if (warp == 0) {
+    const uint64_t prefix = lookback(desc, tile, total, carry_in);
+    if (lane == 0) s_excl = prefix;
+  }
 
-  // ---- compact into shared memory ----
+  // ---- compact into shared memory (positions are tile-local: no dependence on the look-back) ----
 #pragma unroll
   for (int j = 0; j < kVecPerThread; ++j) {
     uint32_t p = seg_off[warp * kVecPerThread + j] + lane_excl[j];
@@ -157,7 +161,6 @@ filter_lt_u32_kernel(const uint32_t* __restrict__ in, uint32_t thr, uint32_t* __
   __syncthreads();
 
   // ---- coalesced write-out ----
-  const uint32_t total = s_total;
   uint32_t* __restrict__ dst = out + s_excl;
   for (uint32_t i = tid; i < total; i += kThreads) st_stream_u32(dst + i, stage[i]);
 }
@@ -199,11 +202,10 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t b
     return b2_set_error(ctx, B2_ERR_WORKSPACE, "filter workspace", "use b2_filter_ws_bytes()");
   B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_ws) & 15) == 0, "workspace must be 16 B aligned");
   char* base = static_cast<char*>(d_ws);
-  FilterWs* ws = reinterpret_cast<FilterWs*>(base);
   uint64_t* desc = reinterpret_cast<uint64_t*>(base + sizeof(FilterWs));
   int64_t* tile_first = uniform ? nullptr : reinterpret_cast<int64_t*>(base + sizeof(FilterWs) + desc_bytes);
 
-  // zero the ticket and every descriptor (status 0 = not published)
+  // zero every descriptor (status 0 = not published)
   B2_CUDA_OK(ctx, cudaMemsetAsync(base, 0, sizeof(FilterWs) + desc_bytes, s));
   if (!uniform) {
     // tile_first is tiny; build it on the host and ship it (pageable copy is staged before return)
@@ -218,10 +220,10 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t b
     if (uniform) {
       filter_lt_u32_kernel<true><<<(unsigned)ntiles, kThreads, 0, s>>>(
           d_in, thr, d_out, batch_len, tiles_of(batch_len), nullptr, nullptr, nbatches, d_carry_in,
-          ws, desc);
+          desc);
     } else {
       filter_lt_u32_kernel<false><<<(unsigned)ntiles, kThreads, 0, s>>>(
-          d_in, thr, d_out, 0, 0, d_batch_off, tile_first, nbatches, d_carry_in, ws, desc);
+          d_in, thr, d_out, 0, 0, d_batch_off, tile_first, nbatches, d_carry_in, desc);
     }
     B2_LAUNCH_CHECK(ctx, "filter_lt_u32_kernel");
   }

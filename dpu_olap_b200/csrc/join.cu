@@ -39,8 +39,9 @@ constexpr int kSlotBits = 13;
 constexpr int kSlots = 1 << kSlotBits;         // 8192 slots = 64 KB (keys + values)
 constexpr int kMaxBuild = (kSlots * 3) / 4;    // rows per build chunk (load factor <= 0.75)
 constexpr int kTargetBuild = 4096;             // mean build rows per partition
-constexpr int kProbeItems = 4;                 // probe rows per thread per tile
-constexpr int kProbeTile = kThreads * kProbeItems;
+constexpr int kItems = 8;                      // rows per thread per round (build and probe)
+constexpr int kRound = kThreads * kItems;      // 4096 rows: a typical partition in one round
+constexpr int kSegs = kWarps * kItems;         // 128 (item, warp) match counts per probe tile
 
 struct JoinState {  // lives in the workspace header
   unsigned long long out_rows;
@@ -54,7 +55,25 @@ __device__ __forceinline__ uint32_t slot_hash(uint32_t key) {
   return (wang_hash_u32(key) * 0x9E3779B1u) >> (32 - kSlotBits);
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+__device__ __forceinline__ void load_round(const uint2* __restrict__ src, int64_t n, uint32_t tid,
+                                           uint32_t (&k)[kItems], uint32_t (&v)[kItems]) {
+#pragma unroll
+  for (int q = 0; q < kItems; ++q) {
+    const int64_t i = (int64_t)q * kThreads + tid;
+    k[q] = 0;
+    v[q] = 0;
+    if (i < n) {
+      const uint2 kv = ld_stream_v2(src + i);
+      k[q] = kv.x;
+      v[q] = kv.y;
+    }
+  }
+}
+
+// One CTA per partition. All global loads of a partition (its build rows and the first 4096
+// probe rows) are issued before anything else, so each CTA keeps up to 64 KB in flight and the
+// table clear, the inserts and the probes run under that latency.
+__global__ void __launch_bounds__(kThreads, 2)
 join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ roff,
                   const uint2* __restrict__ lpairs, const int64_t* __restrict__ loff,
                   int64_t nparts, int part_shl, int part_bits, uint32_t* __restrict__ out_fk,
@@ -63,11 +82,10 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
   extern __shared__ __align__(16) uint32_t tab[];  // keys [kSlots] | values [kSlots]
   uint32_t* __restrict__ tk = tab;
   uint32_t* __restrict__ tv = tab + kSlots;
-  __shared__ uint32_t seg_cnt[kWarps * kProbeItems];
-  __shared__ uint32_t seg_off[kWarps * kProbeItems];
+  __shared__ uint32_t seg_cnt[kSegs];
+  __shared__ uint32_t seg_off[kSegs];
   __shared__ unsigned long long s_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt = lanemask_lt();
 
   for (int64_t p = blockIdx.x; p < nparts; p += gridDim.x) {
     const int64_t r0 = roff[p], r1 = roff[p + 1];
@@ -79,40 +97,43 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
 
     for (int64_t c0 = r0; c0 < r1; c0 += kMaxBuild) {
       const int nbuild = (int)min((int64_t)kMaxBuild, r1 - c0);
-      __syncthreads();  // previous probe phase is done with the table
-      for (int i = tid; i < kSlots; i += kThreads) tk[i] = empty;
+      uint32_t rk[kItems], rv[kItems], lk[kItems], ly[kItems];
+      load_round(rpairs + c0, nbuild, tid, rk, rv);
+      load_round(lpairs + l0, l1 - l0, tid, lk, ly);
+
+      __syncthreads();  // the previous probe phase is done with the table
+      {
+        const uint4 e4 = make_uint4(empty, empty, empty, empty);
+        uint4* tk4 = reinterpret_cast<uint4*>(tk);
+#pragma unroll
+        for (int i = 0; i < kSlots / 4 / kThreads; ++i) tk4[i * kThreads + tid] = e4;
+      }
       __syncthreads();
-      for (int i = tid; i < nbuild; i += kThreads) {
-        const uint2 kv = ld_stream_v2(rpairs + c0 + i);
-        uint32_t slot = slot_hash(kv.x);
-        while (atomicCAS(&tk[slot], empty, kv.x) != empty) slot = (slot + 1) & (kSlots - 1);
-        tv[slot] = kv.y;  // duplicates of a key take separate slots
+      for (int base = 0; base < nbuild; base += kRound) {
+        if (base > 0) load_round(rpairs + c0 + base, nbuild - base, tid, rk, rv);
+#pragma unroll
+        for (int q = 0; q < kItems; ++q) {
+          if (base + q * kThreads + (int)tid < nbuild) {
+            uint32_t slot = slot_hash(rk[q]);
+            while (atomicCAS(&tk[slot], empty, rk[q]) != empty) slot = (slot + 1) & (kSlots - 1);
+            tv[slot] = rv[q];  // duplicates of a key take separate slots
+          }
+        }
       }
       __syncthreads();
 
-      for (int64_t t0 = l0; t0 < l1; t0 += kProbeTile) {
-        uint32_t key[kProbeItems], y[kProbeItems], x0[kProbeItems], m[kProbeItems];
+      for (int64_t t0 = l0; t0 < l1; t0 += kRound) {
+        if (t0 > l0) load_round(lpairs + t0, l1 - t0, tid, lk, ly);
+        uint32_t x0[kItems], m[kItems];
 #pragma unroll
-        for (int q = 0; q < kProbeItems; ++q) {
-          const int64_t row = t0 + q * kThreads + tid;
+        for (int q = 0; q < kItems; ++q) {
           m[q] = 0;
           x0[q] = 0;
-          key[q] = 0;
-          y[q] = 0;
-          if (row < l1) {
-            const uint2 kv = ld_stream_v2(lpairs + row);
-            key[q] = kv.x;
-            y[q] = kv.y;
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < kProbeItems; ++q) {
-          const int64_t row = t0 + q * kThreads + tid;
-          if (row < l1) {
-            uint32_t slot = slot_hash(key[q]);
+          if (t0 + q * kThreads + tid < l1) {
+            uint32_t slot = slot_hash(lk[q]);
             uint32_t k;
             while ((k = tk[slot]) != empty) {
-              if (k == key[q]) {
+              if (k == lk[q]) {
                 if (m[q] == 0) x0[q] = tv[slot];
                 ++m[q];
               }
@@ -120,10 +141,10 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
             }
           }
         }
-        // ---- output positions: order (q, warp, lane) so stores of one q are contiguous ----
-        uint32_t lane_excl[kProbeItems];
+        // ---- output positions: order (q, warp, lane) so the stores of one q are contiguous ----
+        uint32_t lane_excl[kItems];
 #pragma unroll
-        for (int q = 0; q < kProbeItems; ++q) {
+        for (int q = 0; q < kItems; ++q) {
           uint32_t incl = m[q];
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
@@ -135,38 +156,46 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
         }
         __syncthreads();
         if (warp == 0) {
-          const uint32_t c0_ = seg_cnt[2 * lane], c1_ = seg_cnt[2 * lane + 1];
-          uint32_t incl = c0_ + c1_;
+          uint32_t c[4], sum = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            c[i] = seg_cnt[4 * lane + i];
+            sum += c[i];
+          }
+          uint32_t incl = sum;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
           }
-          const uint32_t excl = incl - (c0_ + c1_);
-          seg_off[2 * lane] = excl;
-          seg_off[2 * lane + 1] = excl + c0_;
+          uint32_t run = incl - sum;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            seg_off[4 * lane + i] = run;
+            run += c[i];
+          }
           if (lane == 31) s_base = atomicAdd(&st->out_rows, (unsigned long long)incl);
         }
         __syncthreads();
         const unsigned long long base = s_base;
 #pragma unroll
-        for (int q = 0; q < kProbeItems; ++q) {
+        for (int q = 0; q < kItems; ++q) {
           if (m[q] == 0) continue;
           unsigned long long pos = base + seg_off[q * kWarps + warp] + lane_excl[q];
           if (m[q] == 1) {
             if ((int64_t)pos < out_cap) {
-              st_stream_u32(out_fk + pos, key[q]);
-              st_stream_u32(out_y + pos, y[q]);
+              st_stream_u32(out_fk + pos, lk[q]);
+              st_stream_u32(out_y + pos, ly[q]);
               st_stream_u32(out_x + pos, x0[q]);
             }
           } else {  // duplicate build keys: enumerate every match
-            uint32_t slot = slot_hash(key[q]);
+            uint32_t slot = slot_hash(lk[q]);
             uint32_t k;
             while ((k = tk[slot]) != empty) {
-              if (k == key[q]) {
+              if (k == lk[q]) {
                 if ((int64_t)pos < out_cap) {
-                  out_fk[pos] = key[q];
-                  out_y[pos] = y[q];
+                  out_fk[pos] = lk[q];
+                  out_y[pos] = ly[q];
                   out_x[pos] = tv[slot];
                 }
                 ++pos;
@@ -180,7 +209,6 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
     }
     __syncthreads();
   }
-  (void)lt;
 }
 
 __global__ void join_init_kernel(JoinState* st) {
@@ -283,7 +311,7 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
                                  rout, tmp, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
       B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
                                  lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s));
-      int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * 3);
+      int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * 2);
       join_probe_kernel<<<(unsigned)grid, kThreads, kSlots * 8, s>>>(
           rout, roff, lout, loff, nparts, part_shl, P.bits, d_out_fk, d_out_y, d_out_x,
           out_capacity, st);
