@@ -6,167 +6,357 @@
 // a `write_carry` fix-up for 8-byte MRAM alignment (:109-131) and two barriers per round. The
 // predicate is `item < (1 << 30)` (filter.c:25; Acero side: filter_native.cc:59).
 //
-// B200 design: ONE pass over the column (4 B read per row + 4 B written per selected row):
-//   * a tile is 4096 rows = 256 threads x 4 x 128-bit streaming loads, laid out so every warp
-//     owns 512 consecutive rows (each warp-level load is one fully coalesced 512 B request);
-//     six CTAs are resident per SM so the phases of different tiles overlap;
-//   * ranks inside a warp come from __ballot_sync/__popc (no shuffles); the 32 (warp,segment)
-//     counts of the CTA are scanned redundantly by every warp (one count per lane);
-//   * tiles are chained by a decoupled look-back over single-word 64-bit descriptors
-//     (2 status bits | 62-bit running count, so 2^34-row columns need no second level), run by
-//     warp 0 WHILE the other warps already compact the tile into shared memory — tile-local
-//     positions do not depend on the running count;
-//   * selected rows are staged in shared memory and written with fully coalesced stores.
+// B200 design: ONE pass over the column (4 B read per row + 4 B written per selected row), run by
+// a persistent, warp-specialised kernel (a few CTAs per SM, each looping over tiles):
+//   * tiles are dealt round-robin: the CTA that started v-th (an atomic ticket taken once per CTA)
+//     owns tiles v, v+G, v+2G, ... (G = grid size). All CTAs therefore work on the same
+//     "generation" of G consecutive tiles at the same time, which keeps every look-back short.
+//     (Dealing TILE tickets at prefetch time instead looked natural and ran 18x slower: a CTA then
+//     holds several consecutive tiles it will only reach iterations later, and every successor's
+//     look-back convoys behind it.)
+//   * PRODUCER warp (one lane): streams the CTA's tiles into a ring of shared-memory stages with
+//     TMA bulk copies (cp.async.bulk + mbarrier complete_tx). Bytes in flight per SM =
+//     (stages - 1 - lag) x tile x CTAs, independent of what the compute warps are doing.
+//   * COMPUTE warps: read their 16 rows per thread from shared memory (128-bit, conflict free),
+//     count matches four segments at a time in ONE packed register (4 x 8-bit counters), so the
+//     ranks of a warp's 512 rows cost a single 5-step shuffle scan; one CTA barrier per tile gives
+//     the warp bases; selected rows are compacted IN PLACE into the stage buffer and written out
+//     with fully coalesced stores `lag` iterations later, when the tile's global offset is known.
+//   * PREFIX warp: turns tile counts into global output offsets WITHOUT a look-back chain. Each
+//     tile adds its count to the word of its group (32 tiles) and super-group (1024 tiles) with a
+//     fire-and-forget atomic; a word is final when its contributor count is complete. A tile's
+//     offset = running sum of full super-groups (kept in a register by the owning CTA) + <= 31
+//     full groups + <= 31 tile counts of its own group: two loads per lane, and nothing it waits
+//     for depends on another tile's prefix being finished, only on earlier tiles having been
+//     counted. The warp runs `lag` tiles behind the compute warps, which hides its L2 round trip.
+//     (History, profiles/r1_filter.md: a classic decoupled look-back, 32 descriptors per round
+//     from inside the compute path, capped the first version at 30 % of HBM peak; a 256-wide
+//     look-back in a separate warp reached 45 % — the chain through "inclusive" descriptors kept
+//     falling generations behind.)
 // Tiles never straddle a batch boundary, so the inclusive count of the last tile of batch b is
 // the end offset of result chunk b (FilterDpu::GetResult returns one chunk per input batch,
 // host/filter/filter_dpu.cc:89-96,162-166) — a tiny second kernel collects those.
 #include "common.cuh"
 #include "lookback.cuh"
+#include "tma.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kVecPerThread = 4;                       // uint4 loads per thread
-constexpr int kTile = kThreads * kVecPerThread * 4;    // 4096 rows
-constexpr int kWarps = kThreads / 32;
-constexpr int kSegs = kWarps * kVecPerThread;          // 32 (warp, segment) counts per tile
-static_assert(kSegs == 32, "one (warp, segment) count per lane");
+constexpr int kVecPerThread = 4;  // uint4 per compute thread and tile (16 rows)
 
-struct FilterWs {           // header of the caller workspace (reserved)
-  unsigned long long pad[8];
+struct FilterWs {  // header of the caller workspace; zeroed with the count words on every launch
+  unsigned long long ticket;       // CTA start ranks (static dealing) or tile tickets (dynamic)
+  unsigned long long pad[7];
 };
 
-static inline int64_t tiles_of(int64_t len) { return (len + kTile - 1) / kTile; }
+struct FilterArgs {
+  const uint32_t* in;
+  uint32_t* out;
+  uint32_t thr;
+  int64_t ntiles;
+  int64_t batch_len, tiles_per_batch;  // uniform layout
+  const int64_t* tile_row0;            // ragged layout: per-tile geometry (filter_geom_kernel)
+  const int32_t* tile_len;
+  const int64_t* carry_in;
+  FilterWs* ws;
+  uint32_t* agg;    // [ntiles]        kAggFlag | rows selected in the tile
+  uint64_t* grp;    // [ntiles >> 5]   contributors << 48 | rows selected in the group of 32 tiles
+  uint64_t* sgrp;   // [ntiles >> 10]  same for the super-group of 1024 tiles
+  uint64_t* incl;   // [ntiles]        out: rows selected in tiles 0..t (+ carry), plain values
+  int debug;  // lab only: 1 = no prefix (wrong offsets), 2 = no TMA, 4 = dynamic tile tickets
+};
 
-// 1 if a < b (unsigned) else 0, as an INTEGER: keeps the 16 per-row predicate results of a thread
-// in one mask register instead of 16 predicate registers (ptxas has 7 and gives up otherwise).
-__device__ __forceinline__ uint32_t lt_bit(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r & 1u;
-}
+// Compile-time shape of one kernel variant.
+template <int kComputeThreads_, int kStages_, int kCtasPerSm_, int kLag_>
+struct FilterCfg {
+  static constexpr int kLag = kLag_;  // iterations between compacting a tile and writing it out
+  static_assert(kLag_ >= 1 && kStages_ >= kLag_ + 2, "need a stage in flight besides the held ones");
+  static constexpr int kComputeThreads = kComputeThreads_;
+  static constexpr int kStages = kStages_;
+  static constexpr int kCtasPerSm = kCtasPerSm_;
+  static constexpr int kWarps = kComputeThreads / 32;
+  static constexpr int kThreads = kComputeThreads + 64;  // + producer warp + look-back warp
+  static constexpr int kTile = kComputeThreads * kVecPerThread * 4;  // rows
+  static constexpr int kStageBytes = kTile * 4;
+  // dynamic shared memory: stages | per-stage info | barriers | warp totals
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+};
 
-// Tile id = blockIdx.x: CTAs are dispatched in increasing block order, so every predecessor of a
-// tile that waits in the look-back is already resident or finished (the same assumption CUB's
-// single-pass scan and select make).
-template <bool kUniform>
-__global__ void __launch_bounds__(kThreads, 6)
-filter_lt_u32_kernel(const uint32_t* __restrict__ in, uint32_t thr, uint32_t* __restrict__ out,
-                     int64_t batch_len, int64_t tiles_per_batch,          // uniform layout
-                     const int64_t* __restrict__ batch_off,               // ragged layout
-                     const int64_t* __restrict__ tile_first, int64_t nbatches,
-                     const int64_t* __restrict__ carry_in, uint64_t* __restrict__ desc) {
-  __shared__ uint32_t stage[kTile];
-  __shared__ uint32_t seg_cnt[kSegs];
-  __shared__ uint64_t s_excl;
-  __shared__ uint32_t seg_off[kSegs];
+struct StageInfo {  // written by the producer before it completes full[s]
+  int64_t tile;     // -1: no more tiles
+  int64_t row0;
+  int32_t len;
+  int32_t tma;      // 1: the rows are in the stage buffer; 0: compute warps load them from global
+};
+
+constexpr int kMaxStages = 8;
+struct FilterSmemCtl {
+  StageInfo info[kMaxStages];
+  uint64_t full[kMaxStages];    // producer -> everyone: stage filled (TMA complete_tx or plain arrive)
+  uint64_t empty[kMaxStages];   // compute warps -> producer: stage drained (count = kWarps)
+  uint64_t tot[kMaxStages];     // compute thread 0 -> look-back warp: tile total posted
+  uint64_t pre[kMaxStages];     // look-back warp -> compute warps: exclusive prefix posted
+  uint32_t total[kMaxStages];
+  uint64_t prefix[kMaxStages];
+  uint32_t wtot[2][32];
+  uint32_t vcta;                // this CTA's start rank
+};
+static_assert(sizeof(FilterSmemCtl) <= 1024, "control block must fit its reservation");
+
+// 1 if a < b (unsigned) else 0.
+__device__ __forceinline__ uint32_t lt_u32(uint32_t a, uint32_t b) { return a < b ? 1u : 0u; }
+
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kCtasPerSm)
+filter_lt_u32_kernel(const FilterArgs a) {
+  constexpr int kCT = Cfg::kComputeThreads, kS = Cfg::kStages, kW = Cfg::kWarps, kTile = Cfg::kTile;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint32_t* const bufs = reinterpret_cast<uint32_t*>(smem_raw);
+  FilterSmemCtl& ctl = *reinterpret_cast<FilterSmemCtl*>(smem_raw + kS * Cfg::kStageBytes);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = blockIdx.x;
 
-  // tile -> rows [row0, row0 + len)
-  int64_t row0, len;
-  if (kUniform) {
-    const int64_t b = tile / tiles_per_batch, k = tile - b * tiles_per_batch;
-    row0 = b * batch_len + k * kTile;
-    len = batch_len - k * kTile;
-  } else {
-    int64_t lo = 0, hi = nbatches;  // last b with tile_first[b] <= tile
-    while (hi - lo > 1) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (tile_first[mid] <= tile) lo = mid; else hi = mid;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kS; ++s) {
+      mbar_init(&ctl.full[s], 1);
+      mbar_init(&ctl.empty[s], kW);
+      mbar_init(&ctl.tot[s], 1);
+      mbar_init(&ctl.pre[s], 1);
     }
-    const int64_t k = tile - tile_first[lo];
-    row0 = batch_off[lo] + k * kTile;
-    len = batch_off[lo + 1] - row0;
+    fence_mbar_init();
+    ctl.vcta = (a.debug & 4) ? 0u : (uint32_t)atomicAdd(&a.ws->ticket, 1ull);
   }
-  if (len > kTile) len = kTile;
+  __syncthreads();
+  const int64_t first_tile = ctl.vcta, tile_stride = gridDim.x;
 
-  // ---- load + predicate: warp w owns rows [w*512, w*512+512), segment j = 128 rows ----
-  uint32_t v[kVecPerThread][4];
-  uint32_t mask = 0;  // bit (j*4+e) set <=> element selected
-  const uint32_t* __restrict__ src = in + row0;
-  const uint32_t e0 = warp * (kTile / kWarps) + lane * 4;  // + j*128 + e
-  if (len == kTile && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    const uint4* __restrict__ vsrc = reinterpret_cast<const uint4*>(src);
-    uint4 q[kVecPerThread];
-#pragma unroll
-    for (int j = 0; j < kVecPerThread; ++j) q[j] = ld_stream_v4(vsrc + ((e0 + j * 128) >> 2));
-#pragma unroll
-    for (int j = 0; j < kVecPerThread; ++j) {
-      v[j][0] = q[j].x; v[j][1] = q[j].y; v[j][2] = q[j].z; v[j][3] = q[j].w;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) mask |= lt_bit(v[j][e], thr) << (j * 4 + e);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < kVecPerThread; ++j) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t i = e0 + j * 128 + e;
-        v[j][e] = 0;
-        if ((int64_t)i < len) {
-          v[j][e] = ld_stream_u32(src + i);
-          mask |= lt_bit(v[j][e], thr) << (j * 4 + e);
+  if (warp == kW) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      const uint64_t policy = l2_evict_first_policy();
+      for (int64_t n = 0;; ++n) {
+        const int s = (int)(n % kS);
+        if (n >= kS) mbar_wait(&ctl.empty[s], (uint32_t)(((n / kS) - 1) & 1));
+        const int64_t tile = (a.debug & 4) ? (int64_t)atomicAdd(&a.ws->ticket, 1ull)
+                                           : first_tile + n * tile_stride;
+        StageInfo& si = ctl.info[s];
+        if (tile >= a.ntiles) {
+          si.tile = -1;
+          mbar_arrive(&ctl.full[s]);
+          break;
+        }
+        int64_t row0;
+        int32_t len;
+        if (a.tile_row0) {
+          row0 = a.tile_row0[tile];
+          len = a.tile_len[tile];
+        } else {
+          const int64_t b = tile / a.tiles_per_batch, k = tile - b * a.tiles_per_batch;
+          row0 = b * a.batch_len + k * kTile;
+          const int64_t rest = a.batch_len - k * kTile;
+          len = rest < kTile ? (int32_t)rest : kTile;
+        }
+        const uint32_t* src = a.in + row0;
+        const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((len & 3) == 0) &&
+                         !(a.debug & 2);
+        si.tile = tile;
+        si.row0 = row0;
+        si.len = len;
+        si.tma = tma ? 1 : 0;
+        if (tma) {
+          fence_proxy_async();  // the stage was last touched through the generic proxy
+          mbar_arrive_expect_tx(&ctl.full[s], (uint32_t)len * 4u);
+          tma_load_1d(bufs + (size_t)s * kTile, src, (uint32_t)len * 4u, &ctl.full[s], policy);
+        } else {
+          mbar_arrive(&ctl.full[s]);
         }
       }
     }
+    return;
   }
 
-  // ---- ranks inside the warp: order is (segment j, lane, element e) ----
-  uint32_t lane_excl[kVecPerThread];
-  const uint32_t lt = lanemask_lt();
-#pragma unroll
-  for (int j = 0; j < kVecPerThread; ++j) {
-    uint32_t below = 0, total = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const uint32_t b = __ballot_sync(0xffffffffu, (mask >> (j * 4 + e)) & 1u);
-      below += __popc(b & lt);
-      total += __popc(b);
+  if (warp == kW + 1) {
+    // ================================ prefix warp ================================
+    uint64_t base = a.carry_in ? (uint64_t)*a.carry_in : 0ull;  // rows before super-group `sg`
+    int64_t sg = 0;
+    for (int64_t n = 0;; ++n) {
+      const int s = (int)(n % kS);
+      const uint32_t par = (uint32_t)((n / kS) & 1);
+      mbar_wait(&ctl.full[s], par);
+      const int64_t tile = ctl.info[s].tile;
+      if (tile < 0) break;
+      mbar_wait(&ctl.tot[s], par);
+      const uint32_t total = ctl.total[s];
+      uint64_t prefix;
+      if (a.debug & 1) {
+        prefix = (uint64_t)tile * kTile;
+      } else {
+        // full super-groups this CTA has not folded into its base yet (at most one per iteration
+        // with static dealing, since the grid is smaller than a super-group)
+        while (sg < (tile >> kSuperShift)) {
+          uint64_t w = 0;
+          if (lane == 0) {
+            while (((w = ld_relaxed_gpu_u64(a.sgrp + sg)) >> 48) != (1u << kSuperShift)) __nanosleep(100);
+          }
+          base += __shfl_sync(0xffffffffu, w, 0) & kSumMask;
+          ++sg;
+        }
+        const int64_t g0 = sg << (kSuperShift - kGroupShift);   // first group of the super-group
+        const int ng = (int)((tile >> kGroupShift) - g0);        // full groups before tile's group
+        const int64_t t0 = (tile >> kGroupShift) << kGroupShift; // first tile of tile's group
+        const int na = (int)(tile - t0);                         // tiles of the group before tile
+        uint32_t ns = 32;
+        while (true) {
+          uint64_t gw = 0;
+          uint32_t aw = kAggFlag;
+          if ((int)lane < ng) gw = ld_relaxed_gpu_u64(a.grp + g0 + lane);
+          if ((int)lane < na) aw = ld_relaxed_gpu_u32(a.agg + t0 + lane);
+          const bool ok = ((int)lane >= ng || (gw >> 48) == (1u << kGroupShift)) && (aw & kAggFlag);
+          if (__all_sync(0xffffffffu, ok)) {
+            prefix = base + warp_reduce_sum_u64((gw & kSumMask) + (aw & ~kAggFlag));
+            break;
+          }
+          __nanosleep(ns);
+          if (ns < 256) ns <<= 1;
+        }
+      }
+      if (lane == 0) {
+        a.incl[tile] = prefix + total;
+        ctl.prefix[s] = prefix;
+        mbar_arrive(&ctl.pre[s]);
+      }
+      __syncwarp();
     }
-    lane_excl[j] = below;
-    if (lane == 0) seg_cnt[warp * kVecPerThread + j] = total;
-  }
-  __syncthreads();
-
-  // ---- every warp scans the 32 segment counts itself (one per lane; warp 0 needs the total) ----
-  const uint32_t c = seg_cnt[lane];
-  uint32_t incl = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  // (offsets go through shared memory: fetching them with a shuffle from a warp-uniform lane
-  //  index makes ptxas 12.9 fail register allocation for this kernel)
-  if (warp == 1) seg_off[lane] = incl - c;
-  __syncthreads();
-  // warp 0 chains the tile with its predecessors while the other warps already compact
-  if (warp == 0) {
-    const uint64_t prefix = lookback(desc, tile, total, carry_in);
-    if (lane == 0) s_excl = prefix;
+    return;
   }
 
-  // ---- compact into shared memory (positions are tile-local: no dependence on the look-back) ----
+  // ================================ compute warps ================================
+  for (int64_t n = 0;; ++n) {
+    const int s = (int)(n % kS);
+    const uint32_t par = (uint32_t)((n / kS) & 1);
+    uint32_t* const buf = bufs + (size_t)s * kTile;
+    mbar_wait(&ctl.full[s], par);
+    const StageInfo si = ctl.info[s];
+    const bool valid = si.tile >= 0;
+
+    // ---- load 16 rows: warp w owns rows [w*512, w*512+512), segment j = 128 rows, lane-striped ----
+    uint32_t v[kVecPerThread][4];
+    uint32_t cnt = 0;  // four 8-bit counters: matches of this lane in segment j at bits 8j..8j+7
+    const uint32_t e0 = warp * 512 + lane * 4;  // + j*128 + e
+    if (valid) {
+      if (si.tma && si.len == kTile) {
 #pragma unroll
-  for (int j = 0; j < kVecPerThread; ++j) {
-    uint32_t p = seg_off[warp * kVecPerThread + j] + lane_excl[j];
+        for (int j = 0; j < kVecPerThread; ++j) {
+          const uint4 q = *reinterpret_cast<const uint4*>(buf + e0 + j * 128);
+          v[j][0] = q.x; v[j][1] = q.y; v[j][2] = q.z; v[j][3] = q.w;
+        }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if ((mask >> (j * 4 + e)) & 1u) stage[p++] = v[j][e];
+        for (int j = 0; j < kVecPerThread; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cnt += lt_u32(v[j][e], a.thr) << (8 * j);
+      } else {
+        const uint32_t* __restrict__ src = a.in + si.row0;
+#pragma unroll
+        for (int j = 0; j < kVecPerThread; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t i = e0 + j * 128 + e;
+            // rows past the end of the tile never match (0xffffffff < thr is false for every thr)
+            v[j][e] = 0xffffffffu;
+            if ((int32_t)i < si.len) v[j][e] = si.tma ? buf[i] : ld_stream_u32(src + i);
+            cnt += ((int32_t)i < si.len ? lt_u32(v[j][e], a.thr) : 0u) << (8 * j);
+          }
+        }
+      }
+    }
+    // ---- ranks inside the warp: one scan of the packed counters covers all four segments ----
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - cnt;                           // packed, per segment
+    const uint32_t seg = __shfl_sync(0xffffffffu, incl, 31);    // packed segment totals (<= 128 each)
+    const uint32_t b1 = seg & 0xffu, b2 = b1 + ((seg >> 8) & 0xffu), b3 = b2 + ((seg >> 16) & 0xffu);
+    const uint32_t wtotal = b3 + (seg >> 24);
+    if (lane == 0) ctl.wtot[n & 1][warp] = wtotal;
+
+    named_bar_sync(1, kCT);  // (A) the only CTA-wide barrier per tile (compute warps only)
+
+    // ---- warp base and tile total ----
+    uint32_t wv = lane < kW ? ctl.wtot[n & 1][lane] : 0u;
+    uint32_t winc = wv;
+#pragma unroll
+    for (int o = 1; o < kW; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, winc, kW - 1);
+    const uint32_t wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
+    if (valid && tid == 0) {
+      // publish the count at all three levels as early as possible (fire and forget)
+      st_relaxed_gpu_u32(a.agg + si.tile, kAggFlag | total);
+      red_add_relaxed_gpu_u64(a.grp + (si.tile >> kGroupShift), (1ull << 48) | total);
+      red_add_relaxed_gpu_u64(a.sgrp + (si.tile >> kSuperShift), (1ull << 48) | total);
+      ctl.total[s] = total;
+      mbar_arrive(&ctl.tot[s]);
+    }
+
+    // ---- write out the tile compacted kLag iterations ago (its global offset is known by now) ----
+    auto write_out = [&](int64_t m) {
+      const int ps = (int)(m % kS);
+      mbar_wait(&ctl.pre[ps], (uint32_t)((m / kS) & 1));
+      const uint32_t* __restrict__ stg = bufs + (size_t)ps * kTile;
+      uint32_t* __restrict__ dst = a.out + ctl.prefix[ps];
+      const uint32_t cnt_m = ctl.total[ps];
+      for (uint32_t i = tid; i < cnt_m; i += kCT) st_stream_u32(dst + i, stg[i]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.empty[ps]);
+    };
+    if (n >= Cfg::kLag) write_out(n - Cfg::kLag);
+    if (!valid) {  // drain: tiles n-kLag+1 .. n-1 were compacted before barrier A
+      for (int64_t m = n - Cfg::kLag + 1; m < n; ++m)
+        if (m >= 0) write_out(m);
+      break;
+    }
+
+    // ---- compact this tile in place (every thread read its rows before barrier A) ----
+#pragma unroll
+    for (int j = 0; j < kVecPerThread; ++j) {
+      const uint32_t segbase = j == 0 ? 0u : (j == 1 ? b1 : (j == 2 ? b2 : b3));
+      uint32_t p = wbase + segbase + ((excl >> (8 * j)) & 0xffu);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (v[j][e] < a.thr) buf[p++] = v[j][e];
+      }
     }
   }
-  __syncthreads();
+}
 
-  // ---- coalesced write-out ----
-  uint32_t* __restrict__ dst = out + s_excl;
-  for (uint32_t i = tid; i < total; i += kThreads) st_stream_u32(dst + i, stage[i]);
+// Per-tile geometry of a ragged column: tile -> (first row, rows). tile_first[b] = first tile of
+// batch b (exclusive prefix of the per-batch tile counts), nbatches+1 entries.
+__global__ void filter_geom_kernel(const int64_t* __restrict__ batch_off,
+                                   const int64_t* __restrict__ tile_first, int64_t nbatches,
+                                   int64_t ntiles, int tile_rows, int64_t* __restrict__ tile_row0,
+                                   int32_t* __restrict__ tile_len) {
+  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  int64_t lo = 0, hi = nbatches;  // last b with tile_first[b] <= tile
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (tile_first[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const int64_t k = tile - tile_first[lo];
+  const int64_t row0 = batch_off[lo] + k * tile_rows;
+  const int64_t rest = batch_off[lo + 1] - row0;
+  tile_row0[tile] = row0;
+  tile_len[tile] = (int32_t)(rest < tile_rows ? rest : tile_rows);
 }
 
 // batch_end[b] = inclusive count at the last tile of batch b (carried over empty batches).
-__global__ void filter_batch_end_kernel(const uint64_t* __restrict__ desc, int64_t nbatches,
+__global__ void filter_batch_end_kernel(const uint64_t* __restrict__ incl, int64_t nbatches,
                                         int64_t tiles_per_batch,
                                         const int64_t* __restrict__ tile_first,
                                         const int64_t* __restrict__ carry_in,
@@ -176,12 +366,75 @@ __global__ void filter_batch_end_kernel(const uint64_t* __restrict__ desc, int64
   const int64_t carry = carry_in ? *carry_in : 0;
   if (b < nbatches) {
     const int64_t last = tile_first ? tile_first[b + 1] : (b + 1) * tiles_per_batch;  // exclusive
-    batch_end[b] = last > 0 ? (int64_t)(desc[last - 1] & kValMask) : carry;
+    batch_end[b] = last > 0 ? (int64_t)incl[last - 1] : carry;
   }
   if (b == 0 && total) {
     const int64_t ntiles = tile_first ? tile_first[nbatches] : nbatches * tiles_per_batch;
-    *total = ntiles > 0 ? (int64_t)(desc[ntiles - 1] & kValMask) : carry;
+    *total = ntiles > 0 ? (int64_t)incl[ntiles - 1] : carry;
   }
+}
+
+// ---- variants -----------------------------------------------------------------------------
+// All variants share kTileRows so that the workspace size does not depend on the variant.
+using Cfg0 = FilterCfg<256, 3, 4, 1>;   // 4096-row tiles, 3 x 16 KB stages, 4 CTAs/SM
+using Cfg1 = FilterCfg<256, 4, 3, 1>;
+using Cfg2 = FilterCfg<256, 4, 3, 2>;
+using Cfg3 = FilterCfg<256, 5, 2, 2>;
+using Cfg4 = FilterCfg<256, 5, 2, 1>;
+using Cfg5 = FilterCfg<256, 6, 2, 3>;
+constexpr int kNumVariants = 6;
+constexpr int kTileRows = Cfg0::kTile;
+
+int g_filter_variant = 2;  // <256 threads, 4 stages, 3 CTAs/SM, lag 2>: best on B200 (profiles/r1_filter.md)
+int g_filter_debug = 0;  // tools/filter_lab.py switches this through b200olap_tune_filter_variant()
+
+static inline int64_t tiles_of(int64_t len) { return (len + kTileRows - 1) / kTileRows; }
+
+template <typename Cfg>
+int launch_variant(b2_ctx* ctx, const FilterArgs& a, cudaStream_t s) {
+  static int max_ctas = 0;  // per process; every B200 is the same
+  if (max_ctas == 0) {
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    int per_sm = 0;
+    B2_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &per_sm, filter_lt_u32_kernel<Cfg>, Cfg::kThreads, Cfg::kSmemBytes));
+    if (per_sm < 1) return b2_set_error(ctx, B2_ERR_CUDA, "filter kernel", "does not fit an SM");
+    if (per_sm > Cfg::kCtasPerSm) per_sm = Cfg::kCtasPerSm;
+    max_ctas = per_sm * ctx->sm_count;
+  }
+  const int64_t grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
+  filter_lt_u32_kernel<Cfg><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(a);
+  B2_LAUNCH_CHECK(ctx, "filter_lt_u32_kernel");
+  return B2_OK;
+}
+
+// Workspace layout: header | agg | grp | sgrp  (all zeroed per launch)  | incl | ragged tables.
+struct WsLayout {
+  int64_t ntiles;
+  size_t agg_off, grp_off, sgrp_off, zero_bytes, incl_off, tf_off, row0_off, len_off, total;
+};
+WsLayout ws_layout(int64_t ntiles, int64_t ragged_nbatches /* < 0: uniform */) {
+  WsLayout w{};
+  w.ntiles = ntiles;
+  size_t o = sizeof(FilterWs);
+  w.agg_off = o;   o += b2_align_up((size_t)ntiles * 4, 256);
+  w.grp_off = o;   o += b2_align_up((size_t)((ntiles >> kGroupShift) + 1) * 8, 256);
+  w.sgrp_off = o;  o += b2_align_up((size_t)((ntiles >> kSuperShift) + 1) * 8, 256);
+  w.zero_bytes = o;
+  w.incl_off = o;  o += b2_align_up((size_t)ntiles * 8, 256);
+  if (ragged_nbatches >= 0) {
+    w.tf_off = o;    o += b2_align_up((size_t)(ragged_nbatches + 1) * 8, 256);
+    w.row0_off = o;  o += b2_align_up((size_t)ntiles * 8, 256);
+    w.len_off = o;   o += b2_align_up((size_t)ntiles * 4, 256);
+  }
+  w.total = o;
+  return w;
+}
+int64_t ragged_tiles(const int64_t* h_batch_off, int64_t nbatches) {
+  int64_t n = 0;
+  for (int64_t b = 0; b < nbatches; ++b) n += tiles_of(h_batch_off[b + 1] - h_batch_off[b]);
+  return n;
 }
 
 int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t batch_len,
@@ -189,24 +442,24 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t b
                   uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
                   const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, cudaStream_t s) {
   const bool uniform = (h_batch_off == nullptr);
-  int64_t ntiles = 0;
-  if (uniform) {
-    ntiles = nbatches * tiles_of(batch_len);
-  } else {
-    for (int64_t b = 0; b < nbatches; ++b) ntiles += tiles_of(h_batch_off[b + 1] - h_batch_off[b]);
-  }
-  const size_t desc_bytes = b2_align_up((size_t)ntiles * 8, 256);
-  const size_t tf_bytes = uniform ? 0 : b2_align_up((size_t)(nbatches + 1) * 8, 256);
-  const size_t need = sizeof(FilterWs) + desc_bytes + tf_bytes;
-  if (ws_bytes < need || (need > 0 && d_ws == nullptr))
+  const int64_t ntiles = uniform ? nbatches * tiles_of(batch_len) : ragged_tiles(h_batch_off, nbatches);
+  const WsLayout w = ws_layout(ntiles, uniform ? -1 : nbatches);
+  if (ws_bytes < w.total || d_ws == nullptr)
     return b2_set_error(ctx, B2_ERR_WORKSPACE, "filter workspace", "use b2_filter_ws_bytes()");
   B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_ws) & 15) == 0, "workspace must be 16 B aligned");
   char* base = static_cast<char*>(d_ws);
-  uint64_t* desc = reinterpret_cast<uint64_t*>(base + sizeof(FilterWs));
-  int64_t* tile_first = uniform ? nullptr : reinterpret_cast<int64_t*>(base + sizeof(FilterWs) + desc_bytes);
+  uint64_t* incl = reinterpret_cast<uint64_t*>(base + w.incl_off);
+  int64_t* tile_first = nullptr;
+  int64_t* tile_row0 = nullptr;
+  int32_t* tile_len = nullptr;
+  if (!uniform) {
+    tile_first = reinterpret_cast<int64_t*>(base + w.tf_off);
+    tile_row0 = reinterpret_cast<int64_t*>(base + w.row0_off);
+    tile_len = reinterpret_cast<int32_t*>(base + w.len_off);
+  }
 
-  // zero every descriptor (status 0 = not published)
-  B2_CUDA_OK(ctx, cudaMemsetAsync(base, 0, sizeof(FilterWs) + desc_bytes, s));
+  // zero the ticket and the count words of all three levels
+  B2_CUDA_OK(ctx, cudaMemsetAsync(base, 0, w.zero_bytes, s));
   if (!uniform) {
     // tile_first is tiny; build it on the host and ship it (pageable copy is staged before return)
     std::string buf((size_t)(nbatches + 1) * 8, '\0');
@@ -214,23 +467,42 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t b
     tf[0] = 0;
     for (int64_t b = 0; b < nbatches; ++b) tf[b + 1] = tf[b] + tiles_of(h_batch_off[b + 1] - h_batch_off[b]);
     B2_CUDA_OK(ctx, cudaMemcpyAsync(tile_first, tf, (size_t)(nbatches + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (ntiles > 0) {
+      filter_geom_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(
+          d_batch_off, tile_first, nbatches, ntiles, kTileRows, tile_row0, tile_len);
+      B2_LAUNCH_CHECK(ctx, "filter_geom_kernel");
+    }
   }
   if (ntiles > 0) {
-    B2_REQUIRE(ctx, ntiles < (1ll << 31), "too many tiles for one launch");
-    if (uniform) {
-      filter_lt_u32_kernel<true><<<(unsigned)ntiles, kThreads, 0, s>>>(
-          d_in, thr, d_out, batch_len, tiles_of(batch_len), nullptr, nullptr, nbatches, d_carry_in,
-          desc);
-    } else {
-      filter_lt_u32_kernel<false><<<(unsigned)ntiles, kThreads, 0, s>>>(
-          d_in, thr, d_out, 0, 0, d_batch_off, tile_first, nbatches, d_carry_in, desc);
+    FilterArgs a{};
+    a.in = d_in;
+    a.out = d_out;
+    a.thr = thr;
+    a.ntiles = ntiles;
+    a.batch_len = batch_len;
+    a.tiles_per_batch = uniform ? tiles_of(batch_len) : 0;
+    a.tile_row0 = tile_row0;
+    a.tile_len = tile_len;
+    a.carry_in = d_carry_in;
+    a.ws = reinterpret_cast<FilterWs*>(base);
+    a.agg = reinterpret_cast<uint32_t*>(base + w.agg_off);
+    a.grp = reinterpret_cast<uint64_t*>(base + w.grp_off);
+    a.sgrp = reinterpret_cast<uint64_t*>(base + w.sgrp_off);
+    a.incl = incl;
+    a.debug = g_filter_debug;
+    switch (g_filter_variant) {
+      case 1: B2_RETURN_NOT_OK(launch_variant<Cfg1>(ctx, a, s)); break;
+      case 2: B2_RETURN_NOT_OK(launch_variant<Cfg2>(ctx, a, s)); break;
+      case 3: B2_RETURN_NOT_OK(launch_variant<Cfg3>(ctx, a, s)); break;
+      case 4: B2_RETURN_NOT_OK(launch_variant<Cfg4>(ctx, a, s)); break;
+      case 5: B2_RETURN_NOT_OK(launch_variant<Cfg5>(ctx, a, s)); break;
+      default: B2_RETURN_NOT_OK(launch_variant<Cfg0>(ctx, a, s)); break;
     }
-    B2_LAUNCH_CHECK(ctx, "filter_lt_u32_kernel");
   }
   if (nbatches > 0 || d_total) {
     const int64_t nb = nbatches > 0 ? nbatches : 1;
     filter_batch_end_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(
-        desc, nbatches, tiles_of(batch_len), tile_first, d_carry_in, d_batch_end, d_total);
+        incl, nbatches, tiles_of(batch_len), tile_first, d_carry_in, d_batch_end, d_total);
     B2_LAUNCH_CHECK(ctx, "filter_batch_end_kernel");
   }
   return B2_OK;
@@ -240,17 +512,22 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t b
 
 extern "C" {
 
+// Tuning hook (not part of include/b200olap.h): selects the kernel shape used by later calls.
+int b200olap_tune_filter_variant(int variant) {
+  if (variant < 0 || (variant & 0xff) >= kNumVariants) return B2_ERR_INVALID;
+  g_filter_variant = variant & 0xff;
+  g_filter_debug = variant >> 8;
+  return B2_OK;
+}
+
 size_t b2_filter_ws_bytes(int64_t nbatches, int64_t batch_len) {
   if (nbatches < 0 || batch_len < 0) return 0;
-  return sizeof(FilterWs) + b2_align_up((size_t)(nbatches * tiles_of(batch_len)) * 8, 256);
+  return ws_layout(nbatches * tiles_of(batch_len), -1).total;
 }
 
 size_t b2_filter_ragged_ws_bytes(const int64_t* h_batch_off, int64_t nbatches) {
   if (nbatches < 0 || (nbatches > 0 && !h_batch_off)) return 0;
-  int64_t ntiles = 0;
-  for (int64_t b = 0; b < nbatches; ++b) ntiles += tiles_of(h_batch_off[b + 1] - h_batch_off[b]);
-  return sizeof(FilterWs) + b2_align_up((size_t)ntiles * 8, 256) +
-         b2_align_up((size_t)(nbatches + 1) * 8, 256);
+  return ws_layout(ragged_tiles(h_batch_off, nbatches), nbatches).total;
 }
 
 int b2_filter_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t batch_len,

@@ -47,3 +47,31 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* __restrict__ desc, int64_
   if (lane == 0) st_relaxed_gpu_u64(desc + tile, kFlagInc | (excl + own_count));
   return excl;
 }
+
+// ---- hierarchical counted sums ----------------------------------------------------------------
+// The filter does not walk descriptors at all (filter.cu): every tile adds (1 << 48 | count) to
+// the word of its group of 32 tiles and of its super-group of 1024 tiles with one fire-and-forget
+// atomic each. A word whose contributor count (bits 63:48) has reached the group size holds the
+// final sum (bits 47:0). The exclusive prefix of tile t is then
+//     sum of full super-groups before t  (kept as a running base by the owning CTA)
+//   + sum of the <= 31 full groups between the super-group boundary and t's group
+//   + sum of the <= 31 tile counts of t's own group before t,
+// i.e. two loads per lane, and — unlike a look-back chain — nothing a tile waits for depends on
+// another tile's look-back having finished, only on earlier tiles having been COUNTED.
+constexpr int kGroupShift = 5;         // 32 tiles per group
+constexpr int kSuperShift = 10;        // 1024 tiles per super-group
+constexpr uint64_t kSumMask = (1ull << 48) - 1;
+constexpr uint32_t kAggFlag = 0x80000000u;  // per-tile count word: published flag | count
+
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Fire-and-forget relaxed gpu-scope add (no return value: compiles to RED, nothing to wait for).
+__device__ __forceinline__ void red_add_relaxed_gpu_u64(uint64_t* p, uint64_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
