@@ -13,7 +13,7 @@ scaling); value = total rows / max-over-ranks device time.
 
 One JSON line on stdout (rank 0). Besides the driver's keys it carries
   roofline      achieved HBM GB/s of the filter kernel vs the measured peak
-  e2e           same metric through the host-buffer C ABI (b2_filter_lt_u32_host + fetch):
+  e2e           same metric through the host-buffer C ABI (b2_filter_lt_u32_host_into):
                 pinned host batches in, host result out, copies inside the timed region
   cpu_baseline  Arrow Acero (the reference's CPU engine) on this box's host cores, bounded sample
   ops           the other operators of the path (sum, take, join) and the selectivity sweep,
@@ -331,6 +331,7 @@ def bench_join(ctx, D, args):
         info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
         out_rows = int(rows_t.cpu().numpy().view("uint64")[0])
         o_fk, o_y, o_x = outs
+        del ws
     else:
         G = D.world
         skip = G.bit_length() - 1
@@ -375,17 +376,20 @@ def bench_join(ctx, D, args):
         info["shuffle_bytes_sent_per_rank"] = state["sent"] * 8
         info["shuffle"] = "b2_shuffle_partition + NCCL all_to_all_single (NVLink)"
         o_fk, o_y, o_x = outs
+        del lp, rp, lrecv, rrecv, sws, jws
     # self-check: pk is the global row index and x is drawn per pk batch, so x must equal the R.x
     # row fk points at — verified here for the rows whose pk batch this rank generated
     # (N=1: all of them), plus the row count: every fk matches exactly one pk.
     total_rows = D.sum_int(out_rows)
     if total_rows != nb_total * JOIN_BATCH:
         raise SystemExit(f"join self-check failed: {total_rows} rows, expected {nb_total * JOIN_BATCH}")
+    del fk, y, pk  # the check needs x and the output only; free the rest (SF=2048 fills the HBM)
+    free_all()
     lo_pk = first * JOIN_BATCH
     bad = 0
-    for s in range(0, out_rows, 1 << 27):
-        kf = o_fk[s:min(s + (1 << 27), out_rows)].to(torch.int64) & 0xFFFFFFFF
-        xo = o_x[s:min(s + (1 << 27), out_rows)]
+    for s in range(0, out_rows, 1 << 26):
+        kf = o_fk[s:min(s + (1 << 26), out_rows)].to(torch.int64) & 0xFFFFFFFF
+        xo = o_x[s:min(s + (1 << 26), out_rows)]
         m = (kf >= lo_pk) & (kf < lo_pk + n)
         bad += int((x[(kf[m] - lo_pk)] != xo[m]).sum())
     if bad:
@@ -396,7 +400,7 @@ def bench_join(ctx, D, args):
            "items_per_s_reference_convention": 4 * rows / (ms * 1e-3),  # join_benchmark.cc:114-125
            "algorithmic_bytes_per_row": 28, "achieved_gbs_algorithmic": 28 * rows / D.world / (ms * 1e-3) / 1e9}
     res.update(info)
-    del x, pk, y, fk, outs
+    del x, outs, o_fk, o_y, o_x
     free_all()
     return res
 
@@ -437,21 +441,15 @@ def bench_e2e_filter(ctx, D, args):
     ptrs = (C.c_void_p * nb)(*[base_in + 4 * FILTER_BATCH * b for b in range(nb)])
     lens = (C.c_int64 * nb)(*([FILTER_BATCH] * nb))
     counts = (C.c_int64 * nb)()
-    optrs = (C.c_void_p * nb)()
     total = C.c_uint64(0)
-    t1, t2 = Timings(), Timings()
+    t1 = Timings()
     lib, h = ctx._lib, ctx._h
     acc = {"h2d": 0, "d2h": 0, "launches": 0, "sel": 0}
 
     def step():
-        ctx._ck(lib.b2_filter_lt_u32_host(h, ptrs, lens, nb, 1 << 30, counts, C.byref(total), C.byref(t1)),
-                "b2_filter_lt_u32_host")
-        off = 0
-        for b in range(nb):
-            optrs[b] = base_out + 4 * off
-            off += counts[b]
-        ctx._ck(lib.b2_filter_fetch_host(h, optrs, nb, C.byref(t2)), "b2_filter_fetch_host")
-        acc["h2d"], acc["d2h"] = t1.h2d_bytes + t2.h2d_bytes, t1.d2h_bytes + t2.d2h_bytes
+        ctx._ck(lib.b2_filter_lt_u32_host_into(h, ptrs, lens, nb, 1 << 30, base_out, n, counts,
+                                               C.byref(total), C.byref(t1)), "b2_filter_lt_u32_host_into")
+        acc["h2d"], acc["d2h"] = t1.h2d_bytes, t1.d2h_bytes
         acc["launches"], acc["sel"] = t1.kernel_launches, total.value
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -472,9 +470,11 @@ def bench_e2e_filter(ctx, D, args):
     rows = nb_total * FILTER_BATCH
     res = {"value": rows / (ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": acc["h2d"],
            "d2h_bytes_per_step": acc["d2h"], "ms_per_step": ms, "sf": args.e2e_sf, "rows": rows,
-           "api": "b2_filter_lt_u32_host + b2_filter_fetch_host (pinned host buffers)",
+           "api": "b2_filter_lt_u32_host_into (pinned host batches in, pinned host result out; "
+                  "upload / kernels / download of 64 MiB groups overlap)",
            "phases_ms": {"copy-to-dpu": t1.copy_to_dev_ms, "dpu-work": t1.dev_work_ms,
-                         "copy-from-dpu": t2.copy_from_dev_ms}}
+                         "copy-from-dpu": t1.copy_from_dev_ms},
+           "gpu_launches_per_step": acc["launches"]}
     del h_in, h_out
     return res
 

@@ -368,6 +368,164 @@ int b2_filter_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int64_t nbatche
   return B2_OK;
 }
 
+// Streaming variant: upload chunk k+1 | filter chunk k | download the output of chunk k-1 all
+// overlap (PCIe is full duplex), and nothing is allocated per call. The only host round trip per
+// chunk is the 8-byte running count that sizes its download.
+int b2_filter_lt_u32_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
+                               const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                               uint32_t* out, int64_t out_capacity, int64_t* out_counts,
+                               uint64_t* total, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, nbatches == 0 || out_counts != nullptr, "out_counts is null");
+  B2_REQUIRE(ctx, out_capacity >= 0 && (out_capacity == 0 || out != nullptr), "bad output buffer");
+  Layout L;
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
+  const std::vector<int64_t> chunks = make_chunks(L, nbatches);
+  const size_t nchunks = chunks.size() - 1;
+  b2_timings tm{};
+  if (total) *total = 0;
+  int status = B2_OK;
+  if (nbatches > 0) {
+    Scratch sc;  // events only
+    const int64_t n = L.rows();
+    constexpr int kSlots = 3;
+    int64_t slot_rows = 0;
+    size_t ws_bytes = 0;
+    for (size_t k = 0; k < nchunks; ++k) {
+      const int64_t nb = chunks[k + 1] - chunks[k];
+      slot_rows = std::max(slot_rows, L.off[(size_t)chunks[k + 1]] - L.off[(size_t)chunks[k]]);
+      const size_t w = L.uniform ? b2_filter_ws_bytes(nb, L.batch_len)
+                                 : b2_filter_ragged_ws_bytes(&L.off[(size_t)chunks[k]], nb);
+      ws_bytes = std::max(ws_bytes, b2_align_up(w, 256));
+    }
+    slot_rows = (int64_t)b2_align_up((size_t)slot_rows, 64);
+    // cache slot 0: input ring | 1: compacted output | 2: small tables + workspaces
+    void *p_in = nullptr, *p_out = nullptr, *p_misc = nullptr;
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 0, (size_t)slot_rows * 4 * kSlots, &p_in));
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 1, (size_t)std::max<int64_t>(n, 1) * 4, &p_out));
+    const size_t end_bytes = b2_align_up((size_t)nbatches * 8, 256);
+    const size_t carry_bytes = b2_align_up((nchunks + 1) * 8, 256);
+    const size_t off_bytes = L.uniform ? 0 : b2_align_up((size_t)kSlots * (size_t)(nbatches + 1) * 8, 256);
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 2, end_bytes + carry_bytes + off_bytes + ws_bytes * kSlots, &p_misc));
+    uint32_t* d_in = static_cast<uint32_t*>(p_in);
+    uint32_t* d_out = static_cast<uint32_t*>(p_out);
+    char* misc = static_cast<char*>(p_misc);
+    int64_t* d_end = reinterpret_cast<int64_t*>(misc);
+    int64_t* d_carry = reinterpret_cast<int64_t*>(misc + end_bytes);
+    int64_t* d_off = reinterpret_cast<int64_t*>(misc + end_bytes + carry_bytes);
+    char* d_ws = misc + end_bytes + carry_bytes + off_bytes;
+    // pinned mirror of the running counts (one per chunk) so the host can size the downloads
+    if (ctx->pinned_bytes < (nchunks + 1) * 8) {
+      if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+      ctx->h_pinned = nullptr;
+      ctx->pinned_bytes = 0;
+      const size_t want = b2_align_up((nchunks + 1) * 8, 4096);
+      B2_CUDA_OK(ctx, cudaMallocHost(&ctx->h_pinned, want));
+      ctx->pinned_bytes = want;
+    }
+    volatile int64_t* h_carry = static_cast<volatile int64_t*>(ctx->h_pinned);
+    h_carry[0] = 0;
+    B2_CUDA_OK(ctx, cudaMemsetAsync(d_carry, 0, 8, ctx->s_compute));
+    std::vector<int64_t> rel;  // ragged: chunk-relative offsets
+    std::vector<cudaEvent_t> k_end(nchunks), c_ready(nchunks);
+    cudaEvent_t c_begin, c_end, o_begin, o_end;
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_begin, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &c_end, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &o_begin, true));
+    B2_RETURN_NOT_OK(sc.event(ctx, &o_end, true));
+    PhaseTimer work;
+    B2_CUDA_OK(ctx, cudaEventRecord(c_begin, ctx->s_copy_in));
+    B2_CUDA_OK(ctx, cudaEventRecord(o_begin, ctx->s_copy_out));
+    size_t drained = 0;  // chunks whose output download has been issued
+    auto drain = [&](size_t upto) -> int {  // issue the downloads of chunks [drained, upto)
+      for (; drained < upto; ++drained) {
+        B2_CUDA_OK(ctx, cudaEventSynchronize(c_ready[drained]));
+        const int64_t lo = h_carry[drained], hi = h_carry[drained + 1];
+        if (hi > out_capacity) { status = B2_ERR_OVERFLOW; continue; }
+        if (hi > lo) {
+          B2_CUDA_OK(ctx, cudaMemcpyAsync(out + lo, d_out + lo, (size_t)(hi - lo) * 4,
+                                          cudaMemcpyDeviceToHost, ctx->s_copy_out));
+          tm.d2h_bytes += (hi - lo) * 4;
+        }
+      }
+      return B2_OK;
+    };
+    for (size_t k = 0; k < nchunks; ++k) {
+      cudaEvent_t up_done, kb;
+      B2_RETURN_NOT_OK(sc.event(ctx, &up_done, false));
+      B2_RETURN_NOT_OK(sc.event(ctx, &kb, true));
+      B2_RETURN_NOT_OK(sc.event(ctx, &k_end[k], true));
+      B2_RETURN_NOT_OK(sc.event(ctx, &c_ready[k], false));
+      const int64_t b0 = chunks[k], b1 = chunks[k + 1], nb = b1 - b0;
+      const int64_t row0 = L.off[(size_t)b0];
+      uint32_t* slot = d_in + (size_t)(k % kSlots) * slot_rows;
+      if (k >= (size_t)kSlots) B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_copy_in, k_end[k - kSlots], 0));
+      B2_RETURN_NOT_OK(upload(ctx, slot - row0, L, batch_ptrs, b0, b1, ctx->s_copy_in, &tm.h2d_bytes));
+      int64_t* d_off_k = nullptr;
+      if (!L.uniform) {
+        rel.resize((size_t)nb + 1);
+        for (int64_t b = 0; b <= nb; ++b) rel[(size_t)b] = L.off[(size_t)(b0 + b)] - row0;
+        d_off_k = d_off + (size_t)(k % kSlots) * (size_t)(nbatches + 1);
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_off_k, rel.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice,
+                                        ctx->s_copy_in));  // pageable: staged before the call returns
+      }
+      B2_CUDA_OK(ctx, cudaEventRecord(up_done, ctx->s_copy_in));
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_compute, up_done, 0));
+      B2_CUDA_OK(ctx, cudaEventRecord(kb, ctx->s_compute));
+      void* ws_k = d_ws + (k % kSlots) * ws_bytes;
+      int rc;
+      if (L.uniform) {
+        rc = b2_filter_lt_u32_dev(ctx, slot, nb, L.batch_len, threshold, d_out, d_end + b0,
+                                  d_carry + k + 1, d_carry + k, ws_k, ws_bytes, ctx->s_compute);
+      } else {
+        rc = b2_filter_lt_u32_ragged_dev(ctx, slot, rel.data(), d_off_k, nb, threshold, d_out,
+                                         d_end + b0, d_carry + k + 1, d_carry + k, ws_k, ws_bytes,
+                                         ctx->s_compute);
+      }
+      B2_RETURN_NOT_OK(rc);
+      B2_CUDA_OK(ctx, cudaEventRecord(k_end[k], ctx->s_compute));
+      work.spans.push_back({kb, k_end[k]});
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(const_cast<int64_t*>(h_carry) + k + 1, d_carry + k + 1, 8,
+                                      cudaMemcpyDeviceToHost, ctx->s_compute));
+      B2_CUDA_OK(ctx, cudaEventRecord(c_ready[k], ctx->s_compute));
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->s_copy_out, k_end[k], 0));
+      // keep two chunks queued ahead of the one whose output we wait for
+      if (k >= 2) B2_RETURN_NOT_OK(drain(k - 1));
+    }
+    B2_CUDA_OK(ctx, cudaEventRecord(c_end, ctx->s_copy_in));
+    B2_RETURN_NOT_OK(drain(nchunks));
+    B2_CUDA_OK(ctx, cudaEventRecord(o_end, ctx->s_copy_out));
+    std::vector<int64_t> ends((size_t)nbatches);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(ends.data(), d_end, (size_t)nbatches * 8, cudaMemcpyDeviceToHost,
+                                    ctx->s_compute));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_compute));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_copy_out));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->s_copy_in));
+    int64_t prev = 0;
+    for (int64_t b = 0; b < nbatches; ++b) {
+      out_counts[b] = ends[(size_t)b] - prev;
+      prev = ends[(size_t)b];
+    }
+    if (total) *total = (uint64_t)prev;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c_begin, c_end);
+    tm.copy_to_dev_ms = ms;
+    cudaEventElapsedTime(&ms, o_begin, o_end);
+    tm.copy_from_dev_ms = ms;
+    tm.dev_work_ms = work.total_ms();
+    tm.d2h_bytes += nbatches * 8 + (int64_t)nchunks * 8;
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  if (status != B2_OK) return b2_set_error(ctx, status, "b2_filter_lt_u32_host_into", "output buffer too small");
+  return B2_OK;
+}
+
 // ---- Take ---------------------------------------------------------------------------------
 int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64_t* value_lens,
                      const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,

@@ -34,7 +34,14 @@ struct b2_ctx {
   void* h_pinned = nullptr;  // pinned staging ring
   size_t pinned_bytes = 0;
   b2_pending* pending = nullptr;
+  // grow-only device buffers of the streaming host entry points (a cudaMalloc + cudaFree of a few
+  // GiB per call costs more than the kernels they feed)
+  static constexpr int kCacheSlots = 4;
+  void* cache_ptr[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cache_bytes[kCacheSlots] = {0, 0, 0, 0};
 };
+// Returns a device buffer of at least `bytes` that stays owned by the ctx (slot 0..kCacheSlots-1).
+int b2_ctx_cached(b2_ctx* ctx, int slot, size_t bytes, void** out);
 
 int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail);
 

@@ -13,6 +13,24 @@ int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail) 
   return status;
 }
 
+int b2_ctx_cached(b2_ctx* ctx, int slot, size_t bytes, void** out) {
+  *out = nullptr;
+  if (slot < 0 || slot >= b2_ctx::kCacheSlots) return b2_set_error(ctx, B2_ERR_INVALID, "cache slot", nullptr);
+  if (ctx->cache_bytes[slot] < bytes) {
+    if (ctx->cache_ptr[slot]) {
+      cudaDeviceSynchronize();
+      cudaFree(ctx->cache_ptr[slot]);
+      ctx->cache_ptr[slot] = nullptr;
+      ctx->cache_bytes[slot] = 0;
+    }
+    const size_t want = b2_align_up(bytes, (size_t)1 << 20);
+    B2_CUDA_OK(ctx, cudaMalloc(&ctx->cache_ptr[slot], want));
+    ctx->cache_bytes[slot] = want;
+  }
+  *out = ctx->cache_ptr[slot];
+  return B2_OK;
+}
+
 extern "C" {
 
 int b2_version(void) { return B2_VERSION; }
@@ -78,6 +96,8 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   if (ctx->s_copy_out) cudaStreamDestroy(ctx->s_copy_out);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->d_ws) cudaFree(ctx->d_ws);
+  for (void* p : ctx->cache_ptr)
+    if (p) cudaFree(p);
   if (ctx->d_small) cudaFree(ctx->d_small);
   delete ctx;
   return B2_OK;

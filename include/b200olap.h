@@ -132,6 +132,17 @@ int b2_filter_lt_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
                           int64_t* out_counts, uint64_t* total, b2_timings* timings);
 int b2_filter_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int64_t nbatches,
                          b2_timings* timings);
+/* One-call streaming form for callers that can offer ONE result buffer up front (capacity
+ * out_capacity rows; nbatches*batch_len always suffices): the compacted result of all batches
+ * is written to out[0 .. *total), chunk b being out[sum(out_counts[0..b)) ..) — the buffers an
+ * Arrow ChunkedArray would slice. Upload, kernels and download of successive 64 MiB groups of
+ * batches overlap (the reference's per-rank copy/exec/copy-back callbacks, filter_dpu.cc:128-157),
+ * and no device memory is allocated after the first call. Use pinned host memory for full PCIe
+ * speed. B2_ERR_OVERFLOW if the result does not fit (counts and *total are still valid). */
+int b2_filter_lt_u32_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
+                               const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                               uint32_t* out, int64_t out_capacity, int64_t* out_counts,
+                               uint64_t* total, b2_timings* timings);
 
 /* ---- Take (replaces dpu/shared/kernels/take.c:12-47) ------------------------------------- */
 /* Batch-local gather, no bounds check (take.c:36, TakeOptions::NoBoundsCheck take_native.cc:27):
