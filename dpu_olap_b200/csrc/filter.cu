@@ -106,6 +106,15 @@ static_assert(sizeof(FilterSmemCtl) <= 1024, "control block must fit its reserva
 // 1 if a < b (unsigned) else 0.
 __device__ __forceinline__ uint32_t lt_u32(uint32_t a, uint32_t b) { return a < b ? 1u : 0u; }
 
+// acc += inc if v < thr: compare + predicated add, two instructions per row.
+__device__ __forceinline__ void count_lt(uint32_t& acc, uint32_t v, uint32_t thr, uint32_t inc) {
+  asm("{\n\t.reg .pred q;\n\t"
+      "setp.lt.u32 q, %1, %2;\n\t"
+      "@q add.u32 %0, %0, %3;\n\t}"
+      : "+r"(acc)
+      : "r"(v), "r"(thr), "r"(inc));
+}
+
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kCtasPerSm)
 filter_lt_u32_kernel(const FilterArgs a) {
@@ -250,10 +259,12 @@ filter_lt_u32_kernel(const FilterArgs a) {
           const uint4 q = *reinterpret_cast<const uint4*>(buf + e0 + j * 128);
           v[j][0] = q.x; v[j][1] = q.y; v[j][2] = q.z; v[j][3] = q.w;
         }
+        uint32_t cnt_hi = 0;  // two chains halve the dependent-add latency
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) cnt += lt_u32(v[j][e], a.thr) << (8 * j);
+          for (int e = 0; e < 4; ++e) count_lt(j < 2 ? cnt : cnt_hi, v[j][e], a.thr, 1u << (8 * j));
+        cnt += cnt_hi;
       } else {
         const uint32_t* __restrict__ src = a.in + si.row0;
 #pragma unroll
@@ -323,13 +334,23 @@ filter_lt_u32_kernel(const FilterArgs a) {
     }
 
     // ---- compact this tile in place (every thread read its rows before barrier A) ----
+    // Hand-scheduled: compare, predicated store, predicated pointer bump — three instructions per
+    // row on a byte address (the compiler's version recomputed the address per row: six).
+    const uint32_t buf_s = smem_addr(buf);
 #pragma unroll
     for (int j = 0; j < kVecPerThread; ++j) {
       const uint32_t segbase = j == 0 ? 0u : (j == 1 ? b1 : (j == 2 ? b2 : b3));
-      uint32_t p = wbase + segbase + ((excl >> (8 * j)) & 0xffu);
+      uint32_t p = buf_s + 4u * (wbase + segbase + ((excl >> (8 * j)) & 0xffu));
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (v[j][e] < a.thr) buf[p++] = v[j][e];
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t"
+            "setp.lt.u32 q, %1, %2;\n\t"
+            "@q st.shared.u32 [%0], %1;\n\t"
+            "@q add.u32 %0, %0, 4;\n\t}"
+            : "+r"(p)
+            : "r"(v[j][e]), "r"(a.thr)
+            : "memory");
       }
     }
   }

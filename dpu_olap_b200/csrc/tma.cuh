@@ -33,6 +33,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// Suspend-time hint of try_wait: without it a waiting warp re-issues the try every few cycles and
+// takes issue slots from the warps it is waiting for (26 % of all issued instructions in the first
+// profile of the filter kernel).
+constexpr uint32_t kMbarSuspendNs = 2000;
 // Blocks until the phase with the given parity has completed (try_wait suspends in hardware for a
 // bounded time, so this loop does not burn issue slots).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -40,12 +44,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(smem_addr(bar)),
-      "r"(parity)
+      "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
 }
 // L2 eviction-priority policy for data that is read exactly once.
