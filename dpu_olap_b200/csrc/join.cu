@@ -16,10 +16,11 @@
 //   1. both sides are radix-partitioned on the same hash bits (partition.cu) into partitions of
 //      ~4096 build rows, carrying (key, payload) pairs — the payload travels with the key, so
 //      there is no row-index vector and no take pass;
-//   2. join_probe_kernel: one CTA per partition builds a linear-probing table of the build side
-//      in SHARED memory (8192 slots, 64 KB, load factor ~0.5; 32-bit atomicCAS on the key word),
-//      then streams the probe side through it and writes (fk, y, x) with coalesced stores; the
-//      output range of every 2048-row probe tile is reserved with one 64-bit atomicAdd.
+//   2. join_probe_kernel: one CTA per partition builds a bucketised table of the build side in
+//      SHARED memory (2048 buckets x 4 keys, 64 KB with the values, load factor ~0.5; 32-bit
+//      atomicCAS on the key word), then streams the probe side through it — one 128-bit read
+//      resolves a row — and writes (fk, y, x) with coalesced stores; the output range of every
+//      4608-row probe round is reserved with one 64-bit atomicAdd.
 //      The "empty" marker of a partition's table is a key that hashes to ANOTHER partition
 //      (wang_hash is a bijection), so all 2^32 key values are legal.
 //      Build partitions larger than the table (skew, heavy duplicates) are processed in chunks,
@@ -35,13 +36,15 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSlotBits = 13;
-constexpr int kSlots = 1 << kSlotBits;         // 8192 slots = 64 KB (keys + values)
+constexpr int kBucketBits = 11;
+constexpr int kBuckets = 1 << kBucketBits;     // 2048 buckets of 4 keys: one 128-bit read each
+constexpr int kSlots = kBuckets * 4;           // 8192 slots = 32 KB keys + 32 KB values
 constexpr int kMaxBuild = (kSlots * 3) / 4;    // rows per build chunk (load factor <= 0.75)
 constexpr int kTargetBuild = 4096;             // mean build rows per partition
-constexpr int kItems = 8;                      // rows per thread per round (build and probe)
-constexpr int kRound = kThreads * kItems;      // 4096 rows: a typical partition in one round
-constexpr int kSegs = kWarps * kItems;         // 128 (item, warp) match counts per probe tile
+constexpr int kItems = 9;                      // rows per thread per round (build and probe)
+constexpr int kRound = kThreads * kItems;      // 4608 rows: mean partition + 8 sigma in one round
+constexpr int kSegs = kWarps * kItems;         // (item, warp) match counts per probe round
+constexpr int kSegsPerLane = (kSegs + 31) / 32;
 
 struct JoinState {  // lives in the workspace header
   unsigned long long out_rows;
@@ -49,10 +52,10 @@ struct JoinState {  // lives in the workspace header
   unsigned int pad;
 };
 
-__device__ __forceinline__ uint32_t slot_hash(uint32_t key) {
-  // partition bits are the TOP bits of wang_hash, identical inside a partition; the multiply
-  // folds the remaining low bits into the top kSlotBits
-  return (wang_hash_u32(key) * 0x9E3779B1u) >> (32 - kSlotBits);
+// Bucket inside a partition's table. All keys of a partition share the TOP bits of wang_hash, so
+// the table uses an independent multiplicative hash of the key itself (two instructions).
+__device__ __forceinline__ uint32_t bucket_hash(uint32_t key) {
+  return (key * 0x9E3779B1u) >> (32 - kBucketBits);
 }
 
 __device__ __forceinline__ void load_round(const uint2* __restrict__ src, int64_t n, uint32_t tid,
@@ -70,9 +73,29 @@ __device__ __forceinline__ void load_round(const uint2* __restrict__ src, int64_
   }
 }
 
-// One CTA per partition. All global loads of a partition (its build rows and the first 4096
-// probe rows) are issued before anything else, so each CTA keeps up to 64 KB in flight and the
-// table clear, the inserts and the probes run under that latency.
+// The build phase re-reads buckets that other threads are filling with atomics: force a real load.
+__device__ __forceinline__ uint4 lds128_volatile(const uint32_t* p) {
+  uint4 r;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(p))
+               : "memory");
+  return r;
+}
+
+// Number of slots of bucket `cur` holding `key`, as a 4-bit mask.
+__device__ __forceinline__ uint32_t hit_mask(const uint4& cur, uint32_t key) {
+  return (cur.x == key ? 1u : 0u) | (cur.y == key ? 2u : 0u) | (cur.z == key ? 4u : 0u) |
+         (cur.w == key ? 8u : 0u);
+}
+
+// One CTA per partition. The table is bucketised: a probe reads a whole 4-key bucket with one
+// 128-bit shared-memory load and only moves on when the bucket is full, so nearly every row is
+// resolved in ONE iteration and the lanes of a warp do not wait for each other's probe chains
+// (the first version probed slot by slot: 13 iterations per warp on average, 465 instructions
+// per row, profiles/r1_join.md). All global loads of a partition (its build rows and the first
+// round of probe rows) are issued before anything else, so the table clear and the inserts run
+// under that latency.
 __global__ void __launch_bounds__(kThreads, 2)
 join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ roff,
                   const uint2* __restrict__ lpairs, const int64_t* __restrict__ loff,
@@ -80,12 +103,15 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
                   uint32_t* __restrict__ out_y, uint32_t* __restrict__ out_x, int64_t out_cap,
                   JoinState* __restrict__ st) {
   extern __shared__ __align__(16) uint32_t tab[];  // keys [kSlots] | values [kSlots]
-  uint32_t* __restrict__ tk = tab;
-  uint32_t* __restrict__ tv = tab + kSlots;
-  __shared__ uint32_t seg_cnt[kSegs];
-  __shared__ uint32_t seg_off[kSegs];
+  uint32_t* tk = tab;
+  uint32_t* tv = tab + kSlots;
+  const uint4* tk4 = reinterpret_cast<const uint4*>(tab);
+  __shared__ uint32_t seg_cnt[kSegsPerLane * 32];
+  __shared__ uint32_t seg_off[kSegsPerLane * 32];
   __shared__ unsigned long long s_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = lanemask_lt();
+  for (int i = tid; i < kSegsPerLane * 32; i += kThreads) seg_cnt[i] = 0;  // padding entries stay 0
 
   for (int64_t p = blockIdx.x; p < nparts; p += gridDim.x) {
     const int64_t r0 = roff[p], r1 = roff[p + 1];
@@ -97,26 +123,40 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
 
     for (int64_t c0 = r0; c0 < r1; c0 += kMaxBuild) {
       const int nbuild = (int)min((int64_t)kMaxBuild, r1 - c0);
-      uint32_t rk[kItems], rv[kItems], lk[kItems], ly[kItems];
-      load_round(rpairs + c0, nbuild, tid, rk, rv);
-      load_round(lpairs + l0, l1 - l0, tid, lk, ly);
-
-      __syncthreads();  // the previous probe phase is done with the table
+      uint32_t lk[kItems], ly[kItems];
       {
-        const uint4 e4 = make_uint4(empty, empty, empty, empty);
-        uint4* tk4 = reinterpret_cast<uint4*>(tk);
+        uint32_t rk[kItems], rv[kItems];
+        load_round(rpairs + c0, nbuild, tid, rk, rv);
+        load_round(lpairs + l0, l1 - l0, tid, lk, ly);
+
+        __syncthreads();  // the previous probe phase is done with the table
+        {
+          const uint4 e4 = make_uint4(empty, empty, empty, empty);
+          uint4* w4 = reinterpret_cast<uint4*>(tk);
 #pragma unroll
-        for (int i = 0; i < kSlots / 4 / kThreads; ++i) tk4[i * kThreads + tid] = e4;
-      }
-      __syncthreads();
-      for (int base = 0; base < nbuild; base += kRound) {
-        if (base > 0) load_round(rpairs + c0 + base, nbuild - base, tid, rk, rv);
+          for (int i = 0; i < kBuckets / kThreads; ++i) w4[i * kThreads + tid] = e4;
+        }
+        __syncthreads();
+        for (int base = 0; base < nbuild; base += kRound) {
+          if (base > 0) load_round(rpairs + c0 + base, nbuild - base, tid, rk, rv);
 #pragma unroll
-        for (int q = 0; q < kItems; ++q) {
-          if (base + q * kThreads + (int)tid < nbuild) {
-            uint32_t slot = slot_hash(rk[q]);
-            while (atomicCAS(&tk[slot], empty, rk[q]) != empty) slot = (slot + 1) & (kSlots - 1);
-            tv[slot] = rv[q];  // duplicates of a key take separate slots
+          for (int q = 0; q < kItems; ++q) {
+            if (base + q * kThreads + (int)tid < nbuild) {
+              uint32_t b = bucket_hash(rk[q]);
+              while (true) {
+                const uint4 cur = lds128_volatile(tk + b * 4);
+                // slots of a bucket fill in index order, so the first empty one is the target
+                const int sidx = cur.x == empty ? 0 : cur.y == empty ? 1 : cur.z == empty ? 2 : cur.w == empty ? 3 : 4;
+                if (sidx == 4) {
+                  b = (b + 1) & (kBuckets - 1);
+                  continue;
+                }
+                if (atomicCAS(&tk[b * 4 + sidx], empty, rk[q]) == empty) {
+                  tv[b * 4 + sidx] = rv[q];  // duplicates of a key take separate slots
+                  break;
+                }
+              }
+            }
           }
         }
       }
@@ -130,14 +170,16 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
           m[q] = 0;
           x0[q] = 0;
           if (t0 + q * kThreads + tid < l1) {
-            uint32_t slot = slot_hash(lk[q]);
-            uint32_t k;
-            while ((k = tk[slot]) != empty) {
-              if (k == lk[q]) {
-                if (m[q] == 0) x0[q] = tv[slot];
-                ++m[q];
+            uint32_t b = bucket_hash(lk[q]);
+            while (true) {
+              const uint4 cur = tk4[b];
+              const uint32_t hit = hit_mask(cur, lk[q]);
+              if (hit) {
+                if (m[q] == 0) x0[q] = tv[b * 4 + (__ffs(hit) - 1)];
+                m[q] += __popc(hit);
               }
-              slot = (slot + 1) & (kSlots - 1);
+              if (cur.w == empty) break;  // bucket not full: the chain ends here
+              b = (b + 1) & (kBuckets - 1);
             }
           }
         }
@@ -145,21 +187,30 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
         uint32_t lane_excl[kItems];
 #pragma unroll
         for (int q = 0; q < kItems; ++q) {
-          uint32_t incl = m[q];
+          const uint32_t one = __ballot_sync(0xffffffffu, m[q] == 1);
+          const uint32_t multi = __ballot_sync(0xffffffffu, m[q] > 1);
+          uint32_t total;
+          if (multi == 0) {  // unique build keys: ranks come from one ballot
+            lane_excl[q] = __popc(one & lt);
+            total = __popc(one);
+          } else {
+            uint32_t incl = m[q];
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            lane_excl[q] = incl - m[q];
+            total = __shfl_sync(0xffffffffu, incl, 31);
           }
-          lane_excl[q] = incl - m[q];
-          if (lane == 31) seg_cnt[q * kWarps + warp] = incl;
+          if (lane == 0) seg_cnt[q * kWarps + warp] = total;
         }
         __syncthreads();
         if (warp == 0) {
-          uint32_t c[4], sum = 0;
+          uint32_t c[kSegsPerLane], sum = 0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            c[i] = seg_cnt[4 * lane + i];
+          for (int i = 0; i < kSegsPerLane; ++i) {
+            c[i] = seg_cnt[kSegsPerLane * lane + i];
             sum += c[i];
           }
           uint32_t incl = sum;
@@ -170,8 +221,8 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
           }
           uint32_t run = incl - sum;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            seg_off[4 * lane + i] = run;
+          for (int i = 0; i < kSegsPerLane; ++i) {
+            seg_off[kSegsPerLane * lane + i] = run;
             run += c[i];
           }
           if (lane == 31) s_base = atomicAdd(&st->out_rows, (unsigned long long)incl);
@@ -189,22 +240,26 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
               st_stream_u32(out_x + pos, x0[q]);
             }
           } else {  // duplicate build keys: enumerate every match
-            uint32_t slot = slot_hash(lk[q]);
-            uint32_t k;
-            while ((k = tk[slot]) != empty) {
-              if (k == lk[q]) {
+            uint32_t b = bucket_hash(lk[q]);
+            while (true) {
+              const uint4 cur = tk4[b];
+              uint32_t hit = hit_mask(cur, lk[q]);
+              while (hit) {
+                const int sidx = __ffs(hit) - 1;
+                hit &= hit - 1;
                 if ((int64_t)pos < out_cap) {
                   out_fk[pos] = lk[q];
                   out_y[pos] = ly[q];
-                  out_x[pos] = tv[slot];
+                  out_x[pos] = tv[b * 4 + sidx];
                 }
                 ++pos;
               }
-              slot = (slot + 1) & (kSlots - 1);
+              if (cur.w == empty) break;
+              b = (b + 1) & (kBuckets - 1);
             }
           }
         }
-        // seg_cnt / seg_off / s_base are rewritten only after the next tile's first barrier
+        // seg_cnt / seg_off / s_base are rewritten only after the next round's first barrier
       }
     }
     __syncthreads();
