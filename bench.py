@@ -345,7 +345,12 @@ def bench_join(ctx, D, args):
         outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
         sws = torch.empty(int(ctx._lib.b2_shuffle_ws_bytes(n, G)) + 512, dtype=torch.uint8, device="cuda")
-        jws = torch.empty(ctx.join_ws_bytes(cap, cap) + 256, dtype=torch.uint8, device="cuda")
+        free, _ = torch.cuda.mem_get_info()
+        full = ctx.join_ws_bytes(cap, cap)
+        jws_bytes = min(full, max(free - (3 << 30), ctx.join_min_ws_bytes(cap, cap)))
+        jws = torch.empty(jws_bytes + 256, dtype=torch.uint8, device="cuda")
+        info["workspace_gib"] = round(jws_bytes / 2**30, 2)
+        info["sliced"] = jws_bytes < full
         counts = torch.empty(2 * G, dtype=torch.int64, device="cuda")
         rcounts = torch.empty(2 * G, dtype=torch.int64, device="cuda")
         state = {}
