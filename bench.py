@@ -334,7 +334,6 @@ def bench_join(ctx, D, args):
         del ws
     else:
         G = D.world
-        skip = G.bit_length() - 1
         lp = torch.empty(n, dtype=torch.int64, device="cuda")
         rp = torch.empty(n, dtype=torch.int64, device="cuda")
         loff = torch.empty(G + 1, dtype=torch.int64, device="cuda")
@@ -351,35 +350,29 @@ def bench_join(ctx, D, args):
         jws = torch.empty(jws_bytes + 256, dtype=torch.uint8, device="cuda")
         info["workspace_gib"] = round(jws_bytes / 2**30, 2)
         info["sliced"] = jws_bytes < full
-        counts = torch.empty(2 * G, dtype=torch.int64, device="cuda")
-        rcounts = torch.empty(2 * G, dtype=torch.int64, device="cuda")
-        state = {}
+        from dpu_olap_b200.sharded import ShardedJoin
+
+        def route_l(key, val):
+            ctx.shuffle_partition_dev(key, val, G, pairs_out=lp, dest_off=loff, ws=sws)
+            return lp, loff
+
+        def route_r(key, val):
+            ctx.shuffle_partition_dev(key, val, G, pairs_out=rp, dest_off=roff, ws=sws)
+            return rp, roff
+
+        def local_join(lr, rr, skip_bits):
+            ctx.join_pairs_dev(lr, rr, out_capacity=cap, skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t)
+
+        sj = ShardedJoin(D.dist, D.rank, G, route_l, local_join, route_r=route_r, recv_l=lrecv, recv_r=rrecv)
 
         def step():
-            ctx.shuffle_partition_dev(fk, y, G, pairs_out=lp, dest_off=loff, ws=sws)
-            ctx.shuffle_partition_dev(pk, x, G, pairs_out=rp, dest_off=roff, ws=sws)
-            counts[:G] = loff[1:] - loff[:-1]
-            counts[G:] = roff[1:] - roff[:-1]
-            # counts exchange: rank r learns how many rows every peer sends it
-            D.dist.all_to_all_single(rcounts, _interleave(counts, G))
-            h_send = counts.cpu().tolist()
-            h_recv = _deinterleave(rcounts, G).cpu().tolist()
-            ls, rs = h_send[:G], h_send[G:]
-            lr, rr = h_recv[:G], h_recv[G:]
-            nl_r, nr_r = sum(lr), sum(rr)
-            if nl_r > cap or nr_r > cap:
-                raise SystemExit("shuffle receive buffer overflow (skewed keys)")
-            D.dist.all_to_all_single(lrecv[:nl_r], lp, output_split_sizes=lr, input_split_sizes=ls)
-            D.dist.all_to_all_single(rrecv[:nr_r], rp, output_split_sizes=rr, input_split_sizes=rs)
-            ctx.join_pairs_dev(lrecv[:nl_r], rrecv[:nr_r], out_capacity=cap, skip_bits=skip, ws=jws,
-                               outs=outs, out_rows=rows_t)
-            state["nl_r"], state["sent"] = nl_r, sum(ls) - ls[D.rank] + sum(rs) - rs[D.rank]
+            sj.step(fk, y, pk, x)
         l0 = ctx.launches
         ms = timed_steps(D, step, args.steps, args.warmup)
         info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
         out_rows = int(rows_t.cpu().numpy().view("uint64")[0])
-        info["shuffle_bytes_sent_per_rank"] = state["sent"] * 8
-        info["shuffle"] = "b2_shuffle_partition + NCCL all_to_all_single (NVLink)"
+        info["shuffle_bytes_sent_per_rank"] = sj.bytes_sent()
+        info["shuffle"] = "b2_shuffle_partition + NCCL all_to_all_single (NVLink), dpu_olap_b200.sharded.ShardedJoin"
         o_fk, o_y, o_x = outs
         del lp, rp, lrecv, rrecv, sws, jws
     # self-check: pk is the global row index and x is drawn per pk batch, so x must equal the R.x
@@ -408,15 +401,6 @@ def bench_join(ctx, D, args):
     del x, outs, o_fk, o_y, o_x
     free_all()
     return res
-
-
-def _interleave(counts, G):
-    """[L counts to 0..G-1, R counts to 0..G-1] -> per destination (L, R) pairs for all_to_all."""
-    return counts.view(2, G).t().contiguous().view(-1)
-
-
-def _deinterleave(rcounts, G):
-    return rcounts.view(G, 2).t().contiguous().view(-1)
 
 
 # ------------------------------------------------------------------------------------------------

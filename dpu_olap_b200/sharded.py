@@ -1,0 +1,139 @@
+"""Multi-GPU orchestration of the operator path (one process per GPU, torch.distributed).
+
+What shards how (the reference's only parallelism is "batch i -> DPU i",
+filter_dpu.cc:127, and a host-mediated repartition for the join, partitioner.cc:350-375):
+
+* filter / sum / take: contiguous batch ranges per rank, no data-path collective
+  (:func:`shard_range`); the sum adds one partial per rank (:func:`all_sum_u64`).
+* join: both sides are routed by the top log2(G) bits of wang_hash(key), the (key, payload) pairs
+  cross NVLink in ONE exchange per side, every rank joins what it received
+  (:class:`ShardedJoin`).
+
+The device work (routing kernel, local join) is injected, so the exchange plumbing — counts,
+split sizes, capacity checks, the all-to-all itself — runs unchanged on CPU tensors over gloo
+(tests/test_sharded_gloo.py) and on CUDA tensors over NCCL (bench.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Callable
+
+
+def shard_range(nbatches: int, rank: int, world: int) -> tuple[int, int]:
+    """(first batch, batch count) of `rank`: contiguous ranges, remainder to the low ranks."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    per, rem = divmod(nbatches, world)
+    first = rank * per + min(rank, rem)
+    return first, per + (1 if rank < rem else 0)
+
+
+def log2_exact(n: int) -> int:
+    if n < 1 or n & (n - 1):
+        raise ValueError(f"the sharded join needs a power-of-two number of ranks, got {n}")
+    return n.bit_length() - 1
+
+
+def all_sum_u64(dist: Any, partial: int, device: Any = "cpu") -> int:
+    """Sum of uint64 partials over all ranks, mod 2^64 (SumDpu adds per-DPU partials on the host,
+    aggr_dpu.cc:82-84). int64 two's-complement addition wraps exactly like uint64."""
+    import torch
+    if dist is None:
+        return partial & 0xFFFFFFFFFFFFFFFF
+    v = partial & 0xFFFFFFFFFFFFFFFF
+    t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item()) & 0xFFFFFFFFFFFFFFFF
+
+
+@dataclass
+class ExchangeCounts:
+    send_l: list[int]
+    send_r: list[int]
+    recv_l: list[int]
+    recv_r: list[int]
+
+    @property
+    def nl(self) -> int:
+        return sum(self.recv_l)
+
+    @property
+    def nr(self) -> int:
+        return sum(self.recv_r)
+
+
+@dataclass
+class ShardedJoin:
+    """One join step of rank `rank` of `world`.
+
+    route(key, val) -> (pairs int64[n], dest_off int64[G+1]): rows grouped by destination rank
+        (b2_shuffle_partition_u32_dev on the GPU);
+    local_join(l_pairs, r_pairs, skip_bits) -> result: joins the received pairs, ignoring the
+        top skip_bits hash bits (b2_join_pairs_dev on the GPU).
+    """
+    dist: Any
+    rank: int
+    world: int
+    route: Callable
+    local_join: Callable
+    capacity: int | None = None          # rows each receive buffer can hold (None: allocate exactly)
+    route_r: Callable | None = None      # separate routing step for the build side (own buffers)
+    recv_l: Any = None                   # optional preallocated int64 receive buffers
+    recv_r: Any = None
+    last: ExchangeCounts | None = field(default=None, init=False)
+
+    def exchange_counts(self, l_off, r_off) -> ExchangeCounts:
+        """Every rank learns how many L and R rows each peer sends it: one all-to-all of (L, R)
+        count pairs (the reference reads the per-DPU histograms back to the host instead,
+        partitioner.cc:167-180,280-312)."""
+        import torch
+        G = self.world
+        counts = torch.stack([l_off[1:] - l_off[:-1], r_off[1:] - r_off[:-1]], dim=1).contiguous()  # [G, 2]
+        if self.dist is None:
+            got = counts.clone()
+        else:
+            got = torch.empty_like(counts)
+            self.dist.all_to_all_single(got.view(-1), counts.view(-1))
+        send = counts.cpu().tolist()
+        recv = got.cpu().tolist()
+        return ExchangeCounts([s[0] for s in send], [s[1] for s in send], [r[0] for r in recv],
+                              [r[1] for r in recv])
+
+    def _recv_buffer(self, pre, n, like):
+        import torch
+        if pre is not None:
+            if n > pre.numel():
+                raise OverflowError(f"rank {self.rank}: receive buffer holds {pre.numel()} rows, {n} arrive "
+                                    "(skewed keys)")
+            return pre[:n]
+        if self.capacity is not None and n > self.capacity:
+            raise OverflowError(f"rank {self.rank}: {n} rows arrive, capacity {self.capacity} (skewed keys)")
+        return torch.empty(n, dtype=like.dtype, device=like.device)
+
+    def exchange(self, pairs, send, recv, pre=None):
+        """All-to-all of 8-byte pairs with the given per-peer split sizes."""
+        out = self._recv_buffer(pre, sum(recv), pairs)
+        if self.dist is None:
+            out.copy_(pairs[: sum(send)])
+        else:
+            self.dist.all_to_all_single(out, pairs[: sum(send)], output_split_sizes=recv,
+                                        input_split_sizes=send)
+        return out
+
+    def step(self, fk, y, pk, x):
+        """route L and R, exchange, join locally. Returns local_join's result."""
+        skip = log2_exact(self.world)
+        lp, l_off = self.route(fk, y)
+        rp, r_off = (self.route_r or self.route)(pk, x)
+        c = self.exchange_counts(l_off, r_off)
+        self.last = c
+        lrecv = self.exchange(lp, c.send_l, c.recv_l, self.recv_l)
+        rrecv = self.exchange(rp, c.send_r, c.recv_r, self.recv_r)
+        return self.local_join(lrecv, rrecv, skip)
+
+    def bytes_sent(self) -> int:
+        """Bytes this rank put on the wire in the last step (pairs to OTHER ranks)."""
+        c = self.last
+        if c is None:
+            return 0
+        return 8 * (sum(c.send_l) - c.send_l[self.rank] + sum(c.send_r) - c.send_r[self.rank])
