@@ -1,0 +1,279 @@
+// host_test.cc — the reference's GoogleTests (host/filter/filter_test.cc, host/aggr/aggr_test.cc,
+// host/take/take_test.cc, host/join/join_test.cc, host/partition/partition_test.cc) restated over
+// the *Gpu operators: every case compares the device operator with the Native (Arrow Acero)
+// operator on the same input. GoogleTest is not in the image, so a 30-line harness stands in.
+// Exit code 0 iff every case passes. Needs a B200.
+#include <arrow/api.h>
+#include <arrow/compute/api.h>
+
+#include <cstdio>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "generator.h"
+#include "native.h"
+#include "operators.h"
+
+using namespace upmemeval;
+using namespace upmemeval::generator;
+
+static int g_failed = 0;
+#define EXPECT_TRUE(cond)                                                     \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      std::printf("    EXPECT_TRUE(%s) failed at %s:%d\n", #cond, __FILE__, __LINE__); \
+      ++g_failed;                                                             \
+    }                                                                         \
+  } while (0)
+#define EXPECT_EQ(a, b) EXPECT_TRUE((a) == (b))
+
+static std::shared_ptr<arrow::Schema> VSchema(const char* name = "v") {
+  return arrow::schema({arrow::field(name, arrow::uint32(), /*nullable=*/false)});
+}
+
+// sort a table by the given columns (join_test.cc:27-38)
+static std::shared_ptr<arrow::Table> Sorted(const std::shared_ptr<arrow::Table>& t,
+                                            std::vector<std::string> keys) {
+  std::vector<arrow::compute::SortKey> sk;
+  for (auto& k : keys) sk.emplace_back(k);
+  auto idx = arrow::compute::SortIndices(arrow::Datum(t), arrow::compute::SortOptions(sk)).ValueOrDie();
+  return arrow::compute::Take(arrow::Datum(t), arrow::Datum(idx)).ValueOrDie().table()->CombineChunks().ValueOrDie();
+}
+
+// ---- FilterTest ------------------------------------------------------------------------------------
+static void FilterSimpleTest(gpu::GpuSet& sys) {  // filter_test.cc:24-31
+  auto rb = RecordBatchOf({"v"}, {ArrayOf({0, 2, 3, 8, 9})});
+  filter::FilterGpu g{sys, {rb}};
+  EXPECT_TRUE(g.Prepare().ok());
+  filter::FilterNative n{rb->schema(), {rb}};
+  EXPECT_TRUE(n.Prepare().ok());
+  EXPECT_EQ(g.Run().ValueOrDie(), n.Run().ValueOrDie());
+}
+static void FilterResultTest(gpu::GpuSet& sys) {  // filter_test.cc:33-61
+  std::vector<uint32_t> v(4096);
+  for (int i = 0; i < 4096; ++i) v[i] = (i == 5 || i == 8 || i == 9 || i == 100 || i == 270) ? i : i + (1u << 30);
+  auto rb = RecordBatchOf({"v"}, {ArrayOf(v)});
+  filter::FilterGpu g{sys, {rb}};
+  EXPECT_TRUE(g.Prepare().ok());
+  auto gr = g.GetResult().ValueOrDie();
+  filter::FilterNative n{rb->schema(), {rb}};
+  auto nr = n.GetResult().ValueOrDie()->column(0);
+  EXPECT_TRUE(gr->Equals(nr));
+  EXPECT_EQ(gr->length(), 5);
+}
+static void FilterLongerTest(gpu::GpuSet& sys) {  // filter_test.cc:63-78, plus a multi-batch case
+  for (int nb : {1, 128}) {
+    RandomArrayGenerator rng(42);
+    auto schema = VSchema();
+    auto batches = MakeRandomRecordBatches(rng, schema, nb, 1 << 16);
+    filter::FilterGpu g{sys, batches};
+    EXPECT_TRUE(g.Prepare().ok());
+    auto gr = g.GetResult().ValueOrDie();
+    if (nb == 1) {
+      filter::FilterNative n{schema, batches};
+      EXPECT_TRUE(gr->Equals(n.GetResult().ValueOrDie()->column(0)));
+      EXPECT_EQ(gr->length(), 16358);  // SURVEY.md §8(c) fingerprint of generator(42)
+    } else {  // Acero does not keep batch order with threads: compare chunk by chunk instead
+      EXPECT_EQ(gr->num_chunks(), nb);
+      for (int b = 0; b < nb; ++b) {
+        filter::FilterNative n{schema, {batches[b]}};
+        EXPECT_TRUE(gr->chunk(b)->Equals(n.GetResult().ValueOrDie()->column(0)->chunk(0)));
+      }
+    }
+  }
+}
+
+// ---- SumTest ----------------------------------------------------------------------------------------
+static void SumSimpleTest(gpu::GpuSet& sys) {  // aggr_test.cc:24-36
+  auto rb = RecordBatchOf({"v"}, {ArrayOf({0, 2, 3, 8, 9})});
+  aggr::SumGpu g{sys, {rb}};
+  EXPECT_TRUE(g.Prepare().ok());
+  EXPECT_EQ(g.Run().ValueOrDie(), 22u);
+  aggr::SumNative n{rb->schema(), {rb}};
+  EXPECT_EQ(n.Run().ValueOrDie(), 22u);
+}
+static void SumLargeTest(gpu::GpuSet& sys) {  // aggr_test.cc:38-49
+  RandomArrayGenerator rng(42);
+  auto schema = VSchema();
+  auto batches = MakeRandomRecordBatches(rng, schema, 128, 1 << 16);
+  aggr::SumGpu g{sys, batches};
+  EXPECT_TRUE(g.Prepare().ok());
+  aggr::SumNative n{schema, batches};
+  EXPECT_EQ(g.Run().ValueOrDie(), n.Run().ValueOrDie());
+}
+
+// ---- TakeTest ---------------------------------------------------------------------------------------
+static void TakeSimpleTest(gpu::GpuSet& sys) {  // take_test.cc:24-46
+  auto rb = RecordBatchOf({"v"}, {ArrayOf({0, 2, 3, 8, 9})});
+  auto idx = RecordBatchOf({"i"}, {ArrayOf({0, 1, 4})});
+  take::TakeGpu g{sys, {rb}, {idx}};
+  EXPECT_TRUE(g.Prepare().ok());
+  auto t = g.Run().ValueOrDie();
+  auto a = std::static_pointer_cast<arrow::UInt32Array>(t->column(0)->chunk(0));
+  EXPECT_EQ(a->length(), 3);
+  EXPECT_EQ(a->Value(0), 0u);
+  EXPECT_EQ(a->Value(1), 2u);
+  EXPECT_EQ(a->Value(2), 9u);
+}
+static void TakeLargeTest(gpu::GpuSet& sys) {  // take_test.cc:48-72
+  const int nb = 128, bs = 64 << 10, ibs = 8 << 10;
+  RandomArrayGenerator rng(42);
+  auto schema = VSchema();
+  auto batches = MakeRandomRecordBatches(rng, schema, nb, bs);
+  auto md = arrow::key_value_metadata({{"min", "0"}, {"max", std::to_string(bs - 1)}});
+  auto ischema = arrow::schema({arrow::field("i", arrow::uint32(), false, md)});
+  auto indices = MakeRandomRecordBatches(rng, ischema, nb, ibs);
+  take::TakeGpu g{sys, batches, indices};
+  EXPECT_TRUE(g.Prepare().ok());
+  take::TakeNative n{schema, batches, indices};
+  EXPECT_TRUE(n.Run().ValueOrDie()->Equals(*g.Run().ValueOrDie()));
+}
+
+// ---- JoinTest ---------------------------------------------------------------------------------------
+static void JoinSimpleTest(gpu::GpuSet& sys) {  // join_test.cc:40-80
+  arrow::RecordBatchVector left = {
+      RecordBatchOf({"fk", "v"}, {ArrayOf({0, 2, 3, 8, 9}), ArrayOf({100, 102, 103, 108, 109})}),
+      RecordBatchOf({"fk", "v"}, {ArrayOf({10, 12, 13, 18, 19}), ArrayOf({110, 112, 113, 118, 119})})};
+  arrow::RecordBatchVector right = {
+      RecordBatchOf({"pk", "v"}, {ArrayOf({3, 8, 9, 0, 2}), ArrayOf({53, 58, 59, 50, 52})}),
+      RecordBatchOf({"pk", "v"}, {ArrayOf({12, 13, 18, 19, 10}), ArrayOf({62, 63, 68, 69, 60})})};
+  join::JoinGpu g{sys, left[0]->schema(), right[0]->schema(), left, right};
+  EXPECT_TRUE(g.Prepare().ok());
+  auto gt = g.Run().ValueOrDie();
+  EXPECT_EQ(gt->num_rows(), 10);
+  join::JoinNative n{left[0]->schema(), right[0]->schema(), left, right};
+  auto nt = n.Run().ValueOrDie();
+  // Acero names the clashing payload columns v_l / v_r; compare positionally after sorting
+  auto gs = Sorted(gt->RenameColumns({"fk", "a", "b"}).ValueOrDie(), {"a", "fk"});
+  auto ns = Sorted(nt->RenameColumns({"fk", "a", "b"}).ValueOrDie(), {"a", "fk"});
+  for (int c = 0; c < 3; ++c) EXPECT_TRUE(gs->column(c)->Equals(ns->column(c)));
+}
+static void JoinLargeTest(gpu::GpuSet& sys) {  // join_test.cc:82-121 (128 x 65536 per side)
+  const int nb = 128, bs = 64 << 10;
+  RandomArrayGenerator rng(42);
+  auto rschema0 = VSchema("x"), lschema0 = VSchema("y");
+  auto right = AddColumn("pk", MakeRandomRecordBatches(rng, rschema0, nb, bs), MakeIndexColumn(nb, bs).ValueOrDie());
+  auto lefty = MakeRandomRecordBatches(rng, lschema0, nb, bs);
+  auto left = AddColumn("fk", lefty, MakeForeignKeyColumn(rng, bs, nb, bs).ValueOrDie());
+  join::JoinGpu g{sys, left[0]->schema(), right[0]->schema(), left, right};
+  EXPECT_TRUE(g.Prepare().ok());
+  auto gt = g.Run().ValueOrDie();
+  EXPECT_EQ(gt->num_rows(), static_cast<int64_t>(nb) * bs);  // :115-116
+  join::JoinNative n{left[0]->schema(), right[0]->schema(), left, right};
+  auto nt = n.Run().ValueOrDie();
+  auto gs = Sorted(gt, {"fk", "y"}), ns = Sorted(nt, {"fk", "y"});
+  for (const char* c : {"fk", "y", "x"}) EXPECT_TRUE(gs->GetColumnByName(c)->Equals(ns->GetColumnByName(c)));
+}
+
+// ---- PartitionTest (GTEST_SKIP in the reference) ------------------------------------------------------
+static void PartitionSimpleTest(gpu::GpuSet& sys) {  // partition_test.cc:21-57
+  arrow::RecordBatchVector batches = {RecordBatchOf({"pk", "x"}, {ArrayOf({0, 2}), ArrayOf({100, 101})}),
+                                      RecordBatchOf({"pk", "x"}, {ArrayOf({3, 8}), ArrayOf({102, 103})})};
+  partition::PartitionGpu p{sys, batches[0]->schema(), batches, 2, "pk"};
+  EXPECT_TRUE(p.Prepare().ok());
+  auto parts = p.Run().ValueOrDie();
+  EXPECT_EQ(parts.size(), 2u);
+  int64_t sizes[2] = {parts[0]->num_rows(), parts[1]->num_rows()};
+  EXPECT_TRUE((sizes[0] == 3 && sizes[1] == 1) || (sizes[0] == 1 && sizes[1] == 3));
+  uint64_t spk = 0, sx = 0;
+  for (auto& b : parts)
+    for (int64_t i = 0; i < b->num_rows(); ++i) {
+      spk += std::static_pointer_cast<arrow::UInt32Array>(b->column(0))->Value(i);
+      sx += std::static_pointer_cast<arrow::UInt32Array>(b->column(1))->Value(i);
+    }
+  EXPECT_EQ(spk, 13u);
+  EXPECT_EQ(sx, 406u);
+}
+static void PartitionLargeTest(gpu::GpuSet& sys) {  // partition_test.cc:59-92
+  const int nb = 128, bs = 64 << 10, nparts = 32;
+  RandomArrayGenerator rng(42);
+  auto batches = AddColumn("pk", MakeRandomRecordBatches(rng, VSchema("x"), nb, bs), MakeIndexColumn(nb, bs).ValueOrDie());
+  partition::PartitionGpu p{sys, batches[0]->schema(), batches, nparts, "pk"};
+  EXPECT_TRUE(p.Prepare().ok());
+  auto parts = p.Run().ValueOrDie();
+  const double mean = static_cast<double>(nb) * bs / nparts;
+  int64_t total = 0;
+  for (auto& b : parts) {
+    total += b->num_rows();
+    EXPECT_TRUE(std::abs(b->num_rows() - mean) < 0.1 * mean);
+    auto pk = std::static_pointer_cast<arrow::UInt32Array>(b->column(0));
+    for (int64_t i = 0; i < b->num_rows(); i += 997)
+      EXPECT_EQ(static_cast<int>(b2_wang_hash_u32(pk->Value(i)) >> 27), static_cast<int>(&b - &parts[0]));
+  }
+  EXPECT_EQ(total, static_cast<int64_t>(nb) * bs);
+}
+
+// ---- CPU-only cases (--cpu): the generator restatement and the Native plans ---------------------------
+static int RunCpuCases() {
+  RandomArrayGenerator rng(42);
+  auto schema = VSchema();
+  auto batches = MakeRandomRecordBatches(rng, schema, 1, 1 << 16);
+  auto v = std::static_pointer_cast<arrow::UInt32Array>(batches[0]->column(0));
+  // fingerprints of RandomArrayGenerator(42) produced by the real libstdc++/PCG headers
+  // (tests/golden/generator_golden.json)
+  EXPECT_EQ(v->Value(0), 268u);
+  EXPECT_EQ(v->Value(1), 2955549055u);
+  EXPECT_EQ(v->Value(2), 1465994917u);
+  uint64_t sum = 0, cnt = 0;
+  for (int64_t i = 0; i < v->length(); ++i) {
+    sum += v->Value(i);
+    cnt += v->Value(i) < (1u << 30);
+  }
+  EXPECT_EQ(sum, 141101534903199ull);
+  EXPECT_EQ(cnt, 16358u);
+  filter::FilterNative f{schema, batches};
+  EXPECT_EQ(f.Run().ValueOrDie(), 16358u);
+  aggr::SumNative s{schema, batches};
+  EXPECT_EQ(s.Run().ValueOrDie(), 141101534903199ull);
+  auto rb = RecordBatchOf({"v"}, {ArrayOf({0, 2, 3, 8, 9})});
+  auto idx = RecordBatchOf({"i"}, {ArrayOf({0, 1, 4})});
+  take::TakeNative t{rb->schema(), {rb}, {idx}};
+  auto ta = std::static_pointer_cast<arrow::UInt32Array>(t.Run().ValueOrDie()->column(0)->chunk(0));
+  EXPECT_TRUE(ta->length() == 3 && ta->Value(0) == 0 && ta->Value(1) == 2 && ta->Value(2) == 9);
+  arrow::RecordBatchVector left = {RecordBatchOf({"fk", "y"}, {ArrayOf({0, 2, 3, 8, 9}), ArrayOf({100, 102, 103, 108, 109})})};
+  arrow::RecordBatchVector right = {RecordBatchOf({"pk", "x"}, {ArrayOf({3, 8, 9, 0, 2, 7}), ArrayOf({53, 58, 59, 50, 52, 57})})};
+  join::JoinNative j{left[0]->schema(), right[0]->schema(), left, right};
+  auto jt = Sorted(j.Run().ValueOrDie(), {"fk"});
+  EXPECT_EQ(jt->num_rows(), 5);
+  EXPECT_EQ(jt->schema()->field_names(), (std::vector<std::string>{"fk", "y", "x"}));
+  EXPECT_EQ(std::static_pointer_cast<arrow::UInt32Array>(jt->column(2)->chunk(0))->Value(4), 59u);
+  // the pk counter and the fk ranges of the generator (generator.cc:46-71)
+  auto pk = MakeIndexColumn(2, 4).ValueOrDie();
+  EXPECT_EQ(std::static_pointer_cast<arrow::UInt32Array>(pk[1])->Value(3), 7u);
+  auto fk = MakeForeignKeyColumn(rng, 1 << 21, 3, 1000).ValueOrDie();
+  for (int b = 0; b < 3; ++b) {
+    auto a = std::static_pointer_cast<arrow::UInt32Array>(fk[b]);
+    for (int64_t i = 0; i < a->length(); ++i)
+      EXPECT_TRUE(a->Value(i) >= (uint32_t)b << 21 && a->Value(i) < (uint32_t)(b + 1) << 21);
+  }
+  std::printf("[%s] cpu cases (generator fingerprints, Native known answers)\n", g_failed ? "FAILED" : "  OK  ");
+  return g_failed ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+  if (!InitNative(0).ok()) return 2;
+  if (argc > 1 && std::string(argv[1]) == "--cpu") return RunCpuCases();
+  auto sys = gpu::GpuSet::allocate(0);
+  if (!sys.ok()) {
+    std::printf("no GPU: %s\n", sys.status().ToString().c_str());
+    return 3;
+  }
+  struct Case { const char* name; std::function<void(gpu::GpuSet&)> fn; };
+  std::vector<Case> cases = {
+      {"FilterTest.SimpleTest", FilterSimpleTest}, {"FilterTest.ResultTest", FilterResultTest},
+      {"FilterTest.LongerTest", FilterLongerTest}, {"SumTest.SimpleTest", SumSimpleTest},
+      {"SumTest.LargeTest", SumLargeTest},         {"TakeTest.SimpleTest", TakeSimpleTest},
+      {"TakeTest.LargeTest", TakeLargeTest},       {"JoinTest.SimpleTest", JoinSimpleTest},
+      {"JoinTest.LargeTest", JoinLargeTest},       {"PartitionTest.SimpleTest", PartitionSimpleTest},
+      {"PartitionTest.LargeTest", PartitionLargeTest}};
+  int bad = 0;
+  for (auto& c : cases) {
+    const int before = g_failed;
+    c.fn(**sys);
+    std::printf("[%s] %s\n", g_failed == before ? "  OK  " : "FAILED", c.name);
+    bad += g_failed != before;
+  }
+  std::printf("%d of %zu cases failed\n", bad, cases.size());
+  return bad ? 1 : 0;
+}

@@ -1,0 +1,220 @@
+// operators.cc — the *Gpu operator classes: Arrow record batches in, Arrow results out, one C-ABI
+// call per leg. Column access follows the reference (data buffer #1 of a non-null fixed-width
+// column, host/dpuext/arrow_utils.cc:23,60-66); result buffers are allocated by the caller with
+// arrow::AllocateBuffer and filled by the library (filter_dpu.cc:34-39,79-83).
+#include "operators.h"
+
+#include <vector>
+
+namespace upmemeval {
+namespace {
+
+arrow::Result<const uint32_t*> U32Values(const std::shared_ptr<arrow::Array>& col) {
+  if (col->type_id() != arrow::Type::UINT32)
+    return arrow::Status::TypeError("expected a uint32 column, got ", col->type()->ToString());
+  if (col->null_count() != 0)
+    return arrow::Status::NotImplemented("nullable columns are not supported (the reference passes "
+                                         "a nullptr validity bitmap, filter_dpu.cc:91)");
+  return col->data()->GetValues<uint32_t>(1);
+}
+
+struct ColumnPtrs {
+  std::vector<const uint32_t*> ptrs;
+  std::vector<int64_t> lens;
+  arrow::Status Append(const arrow::RecordBatchVector& batches, int column) {
+    for (const auto& b : batches) {
+      if (column < 0 || column >= b->num_columns()) return arrow::Status::Invalid("no such column");
+      ARROW_ASSIGN_OR_RAISE(const uint32_t* p, U32Values(b->column(column)));
+      ptrs.push_back(p);
+      lens.push_back(b->num_rows());
+    }
+    return arrow::Status::OK();
+  }
+};
+
+arrow::Result<std::shared_ptr<arrow::Array>> AllocU32(int64_t rows, uint32_t** data) {
+  ARROW_ASSIGN_OR_RAISE(auto buf, arrow::AllocateBuffer(rows * 4));
+  *data = reinterpret_cast<uint32_t*>(buf->mutable_data());
+  return std::make_shared<arrow::UInt32Array>(rows, std::shared_ptr<arrow::Buffer>(std::move(buf)));
+}
+
+}  // namespace
+
+// ---- Filter (FilterDpu, host/filter/filter_dpu.cc:23-174) ---------------------------------------
+namespace filter {
+
+arrow::Status FilterGpu::Prepare() {
+  timers_ = std::make_shared<timer::Timers>();
+  return arrow::Status::OK();
+}
+
+arrow::Result<std::shared_ptr<arrow::ChunkedArray>> FilterGpu::GetResult() {
+  b2_ctx* ctx = system_.ctx();
+  if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  ColumnPtrs in;
+  ARROW_RETURN_NOT_OK(in.Append(batches_, 0));
+  const int64_t nb = static_cast<int64_t>(in.ptrs.size());
+  std::vector<int64_t> counts(nb > 0 ? nb : 1);
+  uint64_t total = 0;
+  b2_timings t1{}, t2{};
+  B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_u32_host(ctx, in.ptrs.data(), in.lens.data(), nb, threshold_,
+                                                    counts.data(), &total, &t1));
+  arrow::ArrayVector chunks;
+  std::vector<uint32_t*> outs(nb > 0 ? nb : 1);
+  for (int64_t b = 0; b < nb; ++b) {  // one chunk per input batch, in batch order (:89-96,162-166)
+    ARROW_ASSIGN_OR_RAISE(auto arr, AllocU32(counts[b], &outs[b]));
+    chunks.push_back(std::move(arr));
+  }
+  B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_fetch_host(ctx, outs.data(), nb, &t2));
+  timers_->Add(t1);
+  timers_->Add(t2);
+  return arrow::ChunkedArray::Make(std::move(chunks), arrow::uint32());
+}
+
+arrow::Result<uint64_t> FilterGpu::Run() {
+  ARROW_ASSIGN_OR_RAISE(auto result, GetResult());
+  return static_cast<uint64_t>(result->length());
+}
+
+}  // namespace filter
+
+// ---- Sum (SumDpu, host/aggr/aggr_dpu.cc:31-89) --------------------------------------------------
+namespace aggr {
+
+arrow::Status SumGpu::Prepare() {
+  timers_ = std::make_shared<timer::Timers>();
+  return arrow::Status::OK();
+}
+
+arrow::Result<uint64_t> SumGpu::Run() {
+  b2_ctx* ctx = system_.ctx();
+  if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  ColumnPtrs in;
+  ARROW_RETURN_NOT_OK(in.Append(batches_, 0));
+  uint64_t sum = 0;
+  b2_timings t{};
+  B2_ARROW_RETURN_NOT_OK(ctx, b2_sum_u32_host(ctx, in.ptrs.data(), in.lens.data(),
+                                              static_cast<int64_t>(in.ptrs.size()), &sum, &t));
+  timers_->Add(t);
+  return sum;
+}
+
+}  // namespace aggr
+
+// ---- Take (TakeDpu, host/take/take_dpu.cc:34-104) -----------------------------------------------
+namespace take {
+
+arrow::Status TakeGpu::Prepare() {
+  timers_ = std::make_shared<timer::Timers>();
+  return arrow::Status::OK();
+}
+
+arrow::Result<std::shared_ptr<arrow::Table>> TakeGpu::Run() {
+  b2_ctx* ctx = system_.ctx();
+  if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  if (batches_.size() != indices_batches_.size())
+    return arrow::Status::Invalid("values and indices must have the same number of batches");
+  if (batches_.empty()) return arrow::Status::Invalid("no batches");
+  ColumnPtrs v, i;
+  ARROW_RETURN_NOT_OK(v.Append(batches_, 0));
+  ARROW_RETURN_NOT_OK(i.Append(indices_batches_, 0));
+  const int64_t nb = static_cast<int64_t>(v.ptrs.size());
+  std::vector<uint32_t*> outs(nb);
+  arrow::RecordBatchVector result;
+  auto schema = batches_[0]->schema();
+  for (int64_t b = 0; b < nb; ++b) {
+    ARROW_ASSIGN_OR_RAISE(auto arr, AllocU32(i.lens[b], &outs[b]));
+    result.push_back(arrow::RecordBatch::Make(schema, i.lens[b], {std::move(arr)}));
+  }
+  b2_timings t{};
+  B2_ARROW_RETURN_NOT_OK(ctx, b2_take_u32_host(ctx, v.ptrs.data(), v.lens.data(), i.ptrs.data(),
+                                               i.lens.data(), nb, outs.data(), &t));
+  timers_->Add(t);
+  return arrow::Table::FromRecordBatches(schema, result);
+}
+
+}  // namespace take
+
+// ---- Join (JoinDpu, host/join/join_dpu.cc:144-400) ----------------------------------------------
+namespace join {
+
+arrow::Status JoinGpu::Prepare() {
+  timers_ = std::make_shared<timer::Timers>();
+  return arrow::Status::OK();
+}
+
+arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
+  b2_ctx* ctx = system_.ctx();
+  if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  const int fk = left_schema_->GetFieldIndex("fk"), pk = right_schema_->GetFieldIndex("pk");
+  if (fk < 0 || pk < 0) return arrow::Status::Invalid("join keys are named fk / pk (join_native.cc:31-36)");
+  if (left_schema_->num_fields() != 2 || right_schema_->num_fields() != 2)
+    return arrow::Status::NotImplemented("one key and one payload column per side");
+  const int ly = 1 - fk, rx = 1 - pk;
+  ColumnPtrs l, r;  // [key batches..., payload batches...]
+  ARROW_RETURN_NOT_OK(l.Append(left_batches_, fk));
+  ARROW_RETURN_NOT_OK(l.Append(left_batches_, ly));
+  ARROW_RETURN_NOT_OK(r.Append(right_batches_, pk));
+  ARROW_RETURN_NOT_OK(r.Append(right_batches_, rx));
+  uint64_t rows = 0;
+  b2_timings t1{}, t2{};
+  B2_ARROW_RETURN_NOT_OK(
+      ctx, b2_join_u32_host(ctx, l.ptrs.data(), l.lens.data(), static_cast<int64_t>(left_batches_.size()),
+                            r.ptrs.data(), r.lens.data(), static_cast<int64_t>(right_batches_.size()),
+                            &rows, &t1));
+  uint32_t *o_fk, *o_y, *o_x;
+  ARROW_ASSIGN_OR_RAISE(auto a_fk, AllocU32(static_cast<int64_t>(rows), &o_fk));
+  ARROW_ASSIGN_OR_RAISE(auto a_y, AllocU32(static_cast<int64_t>(rows), &o_y));
+  ARROW_ASSIGN_OR_RAISE(auto a_x, AllocU32(static_cast<int64_t>(rows), &o_x));
+  B2_ARROW_RETURN_NOT_OK(ctx, b2_join_fetch_host(ctx, o_fk, o_y, o_x, static_cast<int64_t>(rows), &t2));
+  timers_->Add(t1);
+  timers_->Add(t2);
+  // JoinNative drops pk and keeps (fk, left payload, right payload) (join_native.cc:75)
+  auto schema = arrow::schema({left_schema_->field(fk), left_schema_->field(ly), right_schema_->field(rx)});
+  return arrow::Table::Make(schema, {a_fk, a_y, a_x}, static_cast<int64_t>(rows));
+}
+
+}  // namespace join
+
+// ---- Partition (PartitionDpu, host/partition/partition_dpu.cc:31-135) ---------------------------
+namespace partition {
+
+arrow::Status PartitionGpu::Prepare() {
+  timers_ = std::make_shared<timer::Timers>();
+  return arrow::Status::OK();
+}
+
+arrow::Result<arrow::RecordBatchVector> PartitionGpu::Run() {
+  b2_ctx* ctx = system_.ctx();
+  if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  const int ncols = schema_->num_fields();
+  const int key = schema_->GetFieldIndex(partition_key_);
+  if (key < 0) return arrow::Status::Invalid("no column named ", partition_key_);
+  const int nparts = static_cast<int>(nr_partitions_);
+  ColumnPtrs cols;  // column-major: all batches of column 0, then column 1, ...
+  for (int c = 0; c < ncols; ++c) ARROW_RETURN_NOT_OK(cols.Append(batches_, c));
+  std::vector<int64_t> lens;
+  for (const auto& b : batches_) lens.push_back(b->num_rows());
+  std::vector<int64_t> part_rows(nparts);
+  b2_timings t1{}, t2{};
+  B2_ARROW_RETURN_NOT_OK(
+      ctx, b2_partition_u32_host(ctx, cols.ptrs.data(), lens.data(), static_cast<int64_t>(batches_.size()),
+                                 ncols, key, nparts, part_rows.data(), &t1));
+  std::vector<uint32_t*> outs(static_cast<size_t>(nparts) * ncols);
+  arrow::RecordBatchVector result;
+  for (int p = 0; p < nparts; ++p) {
+    arrow::ArrayVector arrays;
+    for (int c = 0; c < ncols; ++c) {
+      ARROW_ASSIGN_OR_RAISE(auto arr, AllocU32(part_rows[p], &outs[static_cast<size_t>(p) * ncols + c]));
+      arrays.push_back(std::move(arr));
+    }
+    result.push_back(arrow::RecordBatch::Make(schema_, part_rows[p], std::move(arrays)));
+  }
+  B2_ARROW_RETURN_NOT_OK(ctx, b2_partition_fetch_host(ctx, outs.data(), nparts, ncols, &t2));
+  timers_->Add(t1);
+  timers_->Add(t2);
+  return result;
+}
+
+}  // namespace partition
+}  // namespace upmemeval
