@@ -78,7 +78,7 @@ static void FilterLongerTest(gpu::GpuSet& sys) {  // filter_test.cc:63-78, plus 
       EXPECT_EQ(gr->num_chunks(), nb);
       for (int b = 0; b < nb; ++b) {
         filter::FilterNative n{schema, {batches[b]}};
-        EXPECT_TRUE(gr->chunk(b)->Equals(n.GetResult().ValueOrDie()->column(0)->chunk(0)));
+        EXPECT_TRUE(arrow::ChunkedArray(gr->chunk(b)).Equals(*n.GetResult().ValueOrDie()->column(0)));
       }
     }
   }
