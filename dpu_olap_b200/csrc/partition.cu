@@ -124,6 +124,13 @@ __global__ void part_unit_table_kernel(const int64_t* __restrict__ seg_off, int6
   if (threadIdx.x == 0) unit_first[nseg] = carry;
 }
 
+// Hash + selection + bucket of one key; returns 0xffffffff for rows outside the hash-space slice.
+__device__ __forceinline__ uint32_t bucket_or_skip(uint32_t key, const PartGeom& g) {
+  const uint32_t h = wang_hash_u32(key);
+  const uint32_t b = part_bucket(h, g.shl, g.bits);
+  return part_selected(h, g.sel_shl, g.sel_bits, g.sel_val) ? b : 0xffffffffu;
+}
+
 template <bool kAoS>
 __global__ void __launch_bounds__(kThreads, 4)
 part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
@@ -137,27 +144,32 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   for (int i = tid; i < P; i += kThreads) cnt[i] = 0;
   __syncthreads();
   constexpr int kU = 8;  // independent loads in flight per thread
-  for (int64_t base = u.row0; base < u.row1; base += (int64_t)kThreads * kU) {
+  int64_t base = u.row0;
+  // full blocks: no per-row bounds checks
+  for (; base + (int64_t)kThreads * kU <= u.row1; base += (int64_t)kThreads * kU) {
     uint32_t key[kU];
 #pragma unroll
-    for (int q = 0; q < kU; ++q) {
-      const int64_t row = base + q * kThreads + tid;
-      key[q] = row < u.row1 ? load_key<kAoS>(in, row) : 0u;
-    }
+    for (int q = 0; q < kU; ++q) key[q] = load_key<kAoS>(in, base + q * kThreads + tid);
 #pragma unroll
     for (int q = 0; q < kU; ++q) {
-      const int64_t row = base + q * kThreads + tid;
-      if (row < u.row1) {
-        const uint32_t h = wang_hash_u32(key[q]);
-        if (part_selected(h, g.sel_shl, g.sel_bits, g.sel_val))
-          atomicAdd(&cnt[part_bucket(h, g.shl, g.bits)], 1u);
-      }
+      const uint32_t b = bucket_or_skip(key[q], g);
+      if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
     }
+  }
+  for (int64_t row = base + tid; row < u.row1; row += kThreads) {
+    const uint32_t b = bucket_or_skip(load_key<kAoS>(in, row), g);
+    if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
   }
   __syncthreads();
   for (int p = tid; p < P; p += kThreads) hist[u.hbase + (int64_t)p * u.ustride] = cnt[p];
 }
 
+// Scatter. Per 8192-row tile: every row is hashed ONCE; its rank inside its bucket comes from a
+// shared-memory atomicAdd; after a scan of the tile's bucket counts the rows are staged in shared
+// memory sorted by bucket TOGETHER with their 16-bit bucket id, so the stream-out needs one
+// 8-byte table read (destination of the bucket's run minus its position in the tile) per row
+// instead of hashing the key again. The first version of this kernel spent 105-111
+// lane-instructions per row (profiles/r1_join.md).
 template <bool kAoS>
 __global__ void __launch_bounds__(kThreads, 2)
 part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
@@ -170,9 +182,11 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   if (!u.valid) return;
   // shared-memory carve-up
   uint2* stage = reinterpret_cast<uint2*>(smem);                                   // [kPartTile]
-  uint64_t* gbase = reinterpret_cast<uint64_t*>(smem + sizeof(uint2) * kPartTile);  // [P]
-  uint32_t* tile_start = reinterpret_cast<uint32_t*>(gbase + P);                    // [P]
+  uint64_t* gbase = reinterpret_cast<uint64_t*>(smem + sizeof(uint2) * kPartTile);  // [P] next global row
+  uint64_t* delta = gbase + P;                                                      // [P] gbase - tile_start
+  uint32_t* tile_start = reinterpret_cast<uint32_t*>(delta + P);                    // [P]
   uint32_t* tile_cnt = tile_start + P;                                              // [P]
+  uint16_t* sbucket = reinterpret_cast<uint16_t*>(tile_cnt + P);                    // [kPartTile]
   __shared__ uint32_t warp_tot[kWarps];
   __shared__ uint32_t s_tile_total;
 
@@ -184,25 +198,28 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   __syncthreads();
 
   for (int64_t t0 = u.row0; t0 < u.row1; t0 += kPartTile) {
-    // ---- load, hash, rank inside the bucket (shared-memory atomics are near-free on sm_100:
-    //      measured 1.3e12 lane-ops/s chip-wide, vs 0.15e12 for __match_any_sync) ----
+    // ---- load, hash once, rank inside the bucket ----
     uint32_t key[kItems], val[kItems], packed[kItems];  // packed = bucket | rank << 16
+    if (t0 + kPartTile <= u.row1) {  // full tile: no bounds checks
 #pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      const int64_t row = t0 + it * kThreads + tid;
-      key[it] = 0;
-      val[it] = 0;
-      if (row < u.row1) load_row<kAoS>(in, row, key[it], val[it]);
-    }
+      for (int it = 0; it < kItems; ++it) load_row<kAoS>(in, t0 + it * kThreads + tid, key[it], val[it]);
 #pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      const int64_t row = t0 + it * kThreads + tid;
-      packed[it] = 0xffffffffu;
-      if (row < u.row1) {
-        const uint32_t h = wang_hash_u32(key[it]);
-        if (part_selected(h, g.sel_shl, g.sel_bits, g.sel_val)) {
-          const uint32_t b = part_bucket(h, g.shl, g.bits);
-          packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192 fits 16 bits
+      for (int it = 0; it < kItems; ++it) {
+        const uint32_t b = bucket_or_skip(key[it], g);
+        packed[it] = b;
+        if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < kItems; ++it) {
+        const int64_t row = t0 + it * kThreads + tid;
+        key[it] = 0;
+        val[it] = 0;
+        packed[it] = 0xffffffffu;
+        if (row < u.row1) {
+          load_row<kAoS>(in, row, key[it], val[it]);
+          const uint32_t b = bucket_or_skip(key[it], g);
+          if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);
         }
       }
     }
@@ -223,32 +240,39 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
+    {
+      // every warp scans the 16 warp totals itself (no second barrier for a one-warp scan)
       const uint32_t w = lane < kWarps ? warp_tot[lane] : 0;
       uint32_t wi = w;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
+      for (int o = 1; o < kWarps; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
         if (lane >= o) wi += t;
       }
-      if (lane < kWarps) warp_tot[lane] = wi - w;
-      if (lane == 31) s_tile_total = wi;
-    }
-    __syncthreads();
-    {
-      const uint32_t excl = warp_tot[warp] + incl - (c[0] + c[1]);
+      const uint32_t wbase = __shfl_sync(0xffffffffu, wi - w, warp);
+      const uint32_t tile_total = __shfl_sync(0xffffffffu, wi, kWarps - 1);
+      if (tid == 0) s_tile_total = tile_total;
+      const uint32_t excl = wbase + incl - (c[0] + c[1]);
       const int p = 2 * tid;
-      if (p < P) tile_start[p] = excl;
-      if (p + 1 < P) tile_start[p + 1] = excl + c[0];
+      if (p < P) {
+        tile_start[p] = excl;
+        delta[p] = gbase[p] - excl;
+      }
+      if (p + 1 < P) {
+        tile_start[p + 1] = excl + c[0];
+        delta[p + 1] = gbase[p + 1] - (excl + c[0]);
+      }
     }
     __syncthreads();
 
-    // ---- stage the tile sorted by bucket ----
+    // ---- stage the tile sorted by bucket, bucket id beside the row ----
 #pragma unroll
     for (int it = 0; it < kItems; ++it) {
       if (packed[it] != 0xffffffffu) {
         const uint32_t b = packed[it] & 0xffffu;
-        stage[tile_start[b] + (packed[it] >> 16)] = make_uint2(key[it], val[it]);
+        const uint32_t pos = tile_start[b] + (packed[it] >> 16);
+        stage[pos] = make_uint2(key[it], val[it]);
+        sbucket[pos] = (uint16_t)b;
       }
     }
     __syncthreads();
@@ -257,8 +281,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     const uint32_t total = s_tile_total;
     for (uint32_t j = tid; j < total; j += kThreads) {
       const uint2 kv = stage[j];
-      const uint32_t b = part_bucket(wang_hash_u32(kv.x), g.shl, g.bits);
-      const uint64_t dst = gbase[b] + (j - tile_start[b]);
+      const uint64_t dst = delta[sbucket[j]] + j;
       if ((int64_t)dst < out_cap) {
         st_stream_v2(out + dst, kv);
       } else if (overflow) {
@@ -293,7 +316,7 @@ __global__ void part_offsets_kernel(const uint64_t* __restrict__ scanned,
 
 size_t scatter_smem_bytes(int bits) {
   const size_t P = (size_t)1 << bits;
-  return sizeof(uint2) * kPartTile + P * 8 + P * 4 + P * 4;
+  return sizeof(uint2) * kPartTile + P * 8 + P * 8 + P * 4 + P * 4 + sizeof(uint16_t) * kPartTile;
 }
 
 int64_t choose_unit_rows(int64_t n, int64_t nseg) {
