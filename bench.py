@@ -534,11 +534,34 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def protect_stdout():
+    """Libraries print banners on stdout (NCCL: "NCCL version ..."); the contract is ONE JSON line
+    there. Everything else this process writes to fd 1 goes to stderr; emit() uses the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
     args = parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -607,7 +630,7 @@ def main():
             "cpu_baseline": cpu,
             "ops": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     D.close()
 

@@ -82,22 +82,18 @@ class ShardedJoin:
     recv_r: Any = None
     last: ExchangeCounts | None = field(default=None, init=False)
 
-    def exchange_counts(self, l_off, r_off) -> ExchangeCounts:
-        """Every rank learns how many L and R rows each peer sends it: one all-to-all of (L, R)
-        count pairs (the reference reads the per-DPU histograms back to the host instead,
-        partitioner.cc:167-180,280-312)."""
+    def exchange_counts(self, off) -> tuple[list[int], list[int]]:
+        """(send, recv) row counts per peer for one side: one tiny all-to-all plus the host read
+        that sizes the pair exchange (the reference reads the per-DPU histograms back to the host
+        for the same purpose, partitioner.cc:167-180,280-312)."""
         import torch
-        G = self.world
-        counts = torch.stack([l_off[1:] - l_off[:-1], r_off[1:] - r_off[:-1]], dim=1).contiguous()  # [G, 2]
+        counts = (off[1:] - off[:-1]).contiguous()
         if self.dist is None:
             got = counts.clone()
         else:
             got = torch.empty_like(counts)
-            self.dist.all_to_all_single(got.view(-1), counts.view(-1))
-        send = counts.cpu().tolist()
-        recv = got.cpu().tolist()
-        return ExchangeCounts([s[0] for s in send], [s[1] for s in send], [r[0] for r in recv],
-                              [r[1] for r in recv])
+            self.dist.all_to_all_single(got, counts)
+        return counts.cpu().tolist(), got.cpu().tolist()
 
     def _recv_buffer(self, pre, n, like):
         import torch
@@ -111,24 +107,31 @@ class ShardedJoin:
         return torch.empty(n, dtype=like.dtype, device=like.device)
 
     def exchange(self, pairs, send, recv, pre=None):
-        """All-to-all of 8-byte pairs with the given per-peer split sizes."""
+        """All-to-all of 8-byte pairs with the given per-peer split sizes, started asynchronously:
+        returns (receive buffer, work handle or None). Work enqueued on the caller's stream after
+        this call overlaps with the transfer until handle.wait()."""
         out = self._recv_buffer(pre, sum(recv), pairs)
         if self.dist is None:
             out.copy_(pairs[: sum(send)])
-        else:
-            self.dist.all_to_all_single(out, pairs[: sum(send)], output_split_sizes=recv,
-                                        input_split_sizes=send)
-        return out
+            return out, None
+        work = self.dist.all_to_all_single(out, pairs[: sum(send)], output_split_sizes=recv,
+                                           input_split_sizes=send, async_op=True)
+        return out, work
 
     def step(self, fk, y, pk, x):
-        """route L and R, exchange, join locally. Returns local_join's result."""
+        """route L | exchange L (async) overlapped with route R | exchange R | local join.
+        Returns local_join's result."""
         skip = log2_exact(self.world)
         lp, l_off = self.route(fk, y)
-        rp, r_off = (self.route_r or self.route)(pk, x)
-        c = self.exchange_counts(l_off, r_off)
-        self.last = c
-        lrecv = self.exchange(lp, c.send_l, c.recv_l, self.recv_l)
-        rrecv = self.exchange(rp, c.send_r, c.recv_r, self.recv_r)
+        send_l, recv_l = self.exchange_counts(l_off)
+        lrecv, wl = self.exchange(lp, send_l, recv_l, self.recv_l)
+        rp, r_off = (self.route_r or self.route)(pk, x)   # runs while the L pairs cross NVLink
+        send_r, recv_r = self.exchange_counts(r_off)
+        rrecv, wr = self.exchange(rp, send_r, recv_r, self.recv_r)
+        self.last = ExchangeCounts(send_l, send_r, recv_l, recv_r)
+        for w in (wl, wr):
+            if w is not None:
+                w.wait()
         return self.local_join(lrecv, rrecv, skip)
 
     def bytes_sent(self) -> int:
