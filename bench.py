@@ -53,6 +53,8 @@ def parse_args():
     p.add_argument("--cpu-sf", type=int, default=int(os.environ.get("CPU_SF", 64)),
                    help="scale factor of the CPU (Arrow Acero) sample: BASELINE.json configs[0]")
     p.add_argument("--cpu-seconds", type=float, default=15.0)
+    p.add_argument("--join-exchange", default="p2p", choices=["p2p", "nccl"],
+                   help="multi-GPU join: fused peer-memory shuffle (default) or routing + NCCL all-to-all")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     return p.parse_args()
@@ -334,47 +336,75 @@ def bench_join(ctx, D, args):
         del ws
     else:
         G = D.world
-        lp = torch.empty(n, dtype=torch.int64, device="cuda")
-        rp = torch.empty(n, dtype=torch.int64, device="cuda")
-        loff = torch.empty(G + 1, dtype=torch.int64, device="cuda")
-        roff = torch.empty(G + 1, dtype=torch.int64, device="cuda")
         cap = n + n // 8 + 65536  # received rows: hash-uniform, 12.5 % slack
-        lrecv = torch.empty(cap, dtype=torch.int64, device="cuda")
-        rrecv = torch.empty(cap, dtype=torch.int64, device="cuda")
         outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
-        sws = torch.empty(int(ctx._lib.b2_shuffle_ws_bytes(n, G)) + 512, dtype=torch.uint8, device="cuda")
-        free, _ = torch.cuda.mem_get_info()
-        full = ctx.join_ws_bytes(cap, cap)
-        jws_bytes = min(full, max(free - (3 << 30), ctx.join_min_ws_bytes(cap, cap)))
-        jws = torch.empty(jws_bytes + 256, dtype=torch.uint8, device="cuda")
-        info["workspace_gib"] = round(jws_bytes / 2**30, 2)
-        info["sliced"] = jws_bytes < full
-        from dpu_olap_b200.sharded import ShardedJoin
+        if args.join_exchange == "p2p":
+            # fused shuffle: the routing kernel stores straight into the peers' receive buffers
+            from dpu_olap_b200.sharded import P2PShuffleJoin
+            pj = P2PShuffleJoin(ctx, D.dist, D.rank, G, n, cap)
+            jws_bytes = ctx.join_seg_ws_bytes(cap, cap, pj.skip, pj.seg_bits)
+            if jws_bytes == 0:
+                raise SystemExit("segmented join unsupported at this size; use --join-exchange nccl")
+            jws = torch.empty(jws_bytes + 256, dtype=torch.uint8, device="cuda")
+            info["workspace_gib"] = round(jws_bytes / 2**30, 2)
+            info["sliced"] = False
 
-        def route_l(key, val):
-            ctx.shuffle_partition_dev(key, val, G, pairs_out=lp, dest_off=loff, ws=sws)
-            return lp, loff
+            def local_join(lr, lseg, rr, rseg, seg_bits, skip_bits):
+                ctx.join_pairs_seg_dev(lr, lseg, rr, rseg, seg_bits, out_capacity=cap, skip_bits=skip_bits,
+                                       ws=jws, outs=outs, out_rows=rows_t)
 
-        def route_r(key, val):
-            ctx.shuffle_partition_dev(key, val, G, pairs_out=rp, dest_off=roff, ws=sws)
-            return rp, roff
+            def step():
+                pj.step(fk, y, pk, x, local_join)
+            l0 = ctx.launches
+            ms = timed_steps(D, step, args.steps, args.warmup)
+            info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
+            nl_r, nr_r = pj.last_recv
+            info["shuffle_rows_received_rank0"] = [nl_r, nr_r]
+            info["shuffle_bytes_sent_per_rank"] = int(16 * n * (G - 1) / G)  # expectation: hash-uniform
+            info["shuffle"] = ("fused: b2_shuffle_p2p_scatter stores (key, payload) pairs over NVLink into the "
+                               "peers' symmetric-memory receive buffers, pre-partitioned; collectives left: one "
+                               "all-gather of 2 x 1024 counts + one barrier (dpu_olap_b200.sharded.P2PShuffleJoin)")
+            del jws, pj
+        else:
+            lp = torch.empty(n, dtype=torch.int64, device="cuda")
+            rp = torch.empty(n, dtype=torch.int64, device="cuda")
+            loff = torch.empty(G + 1, dtype=torch.int64, device="cuda")
+            roff = torch.empty(G + 1, dtype=torch.int64, device="cuda")
+            lrecv = torch.empty(cap, dtype=torch.int64, device="cuda")
+            rrecv = torch.empty(cap, dtype=torch.int64, device="cuda")
+            sws = torch.empty(int(ctx._lib.b2_shuffle_ws_bytes(n, G)) + 512, dtype=torch.uint8, device="cuda")
+            free, _ = torch.cuda.mem_get_info()
+            full = ctx.join_ws_bytes(cap, cap)
+            jws_bytes = min(full, max(free - (3 << 30), ctx.join_min_ws_bytes(cap, cap)))
+            jws = torch.empty(jws_bytes + 256, dtype=torch.uint8, device="cuda")
+            info["workspace_gib"] = round(jws_bytes / 2**30, 2)
+            info["sliced"] = jws_bytes < full
+            from dpu_olap_b200.sharded import ShardedJoin
 
-        def local_join(lr, rr, skip_bits):
-            ctx.join_pairs_dev(lr, rr, out_capacity=cap, skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t)
+            def route_l(key, val):
+                ctx.shuffle_partition_dev(key, val, G, pairs_out=lp, dest_off=loff, ws=sws)
+                return lp, loff
 
-        sj = ShardedJoin(D.dist, D.rank, G, route_l, local_join, route_r=route_r, recv_l=lrecv, recv_r=rrecv)
+            def route_r(key, val):
+                ctx.shuffle_partition_dev(key, val, G, pairs_out=rp, dest_off=roff, ws=sws)
+                return rp, roff
 
-        def step():
-            sj.step(fk, y, pk, x)
-        l0 = ctx.launches
-        ms = timed_steps(D, step, args.steps, args.warmup)
-        info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
+            def local_join(lr, rr, skip_bits):
+                ctx.join_pairs_dev(lr, rr, out_capacity=cap, skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t)
+
+            sj = ShardedJoin(D.dist, D.rank, G, route_l, local_join, route_r=route_r, recv_l=lrecv, recv_r=rrecv)
+
+            def step():
+                sj.step(fk, y, pk, x)
+            l0 = ctx.launches
+            ms = timed_steps(D, step, args.steps, args.warmup)
+            info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
+            info["shuffle_bytes_sent_per_rank"] = sj.bytes_sent()
+            info["shuffle"] = "b2_shuffle_partition + NCCL all_to_all_single (NVLink), dpu_olap_b200.sharded.ShardedJoin"
+            del lp, rp, lrecv, rrecv, sws, jws
         out_rows = int(rows_t.cpu().numpy().view("uint64")[0])
-        info["shuffle_bytes_sent_per_rank"] = sj.bytes_sent()
-        info["shuffle"] = "b2_shuffle_partition + NCCL all_to_all_single (NVLink), dpu_olap_b200.sharded.ShardedJoin"
         o_fk, o_y, o_x = outs
-        del lp, rp, lrecv, rrecv, sws, jws
     # self-check: pk is the global row index and x is drawn per pk batch, so x must equal the R.x
     # row fk points at — verified here for the rows whose pk batch this rank generated
     # (N=1: all of them), plus the row count: every fk matches exactly one pk.

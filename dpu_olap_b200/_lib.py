@@ -63,6 +63,12 @@ SIGNATURES = {
                                            _vp, _sz, _vp]),
     "b2_filter_lt_u32_host": (_int, [_vp, _pp, _pi64, _i64, _u32, _pi64, _pu64, _pt]),
     "b2_filter_fetch_host": (_int, [_vp, _pp, _i64, _pt]),
+    "b2_shuffle_p2p_ws_bytes": (_sz, [_i64, _int]),
+    "b2_shuffle_p2p_count_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "b2_shuffle_p2p_scatter_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "b2_join_seg_ws_bytes": (_sz, [_i64, _i64, _int, _int]),
+    "b2_join_pairs_seg_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _i64, _vp, _int,
+                                     _vp, _sz, _vp]),
     "b2_filter_lt_u32_host_into": (_int, [_vp, _pp, _pi64, _i64, _u32, _vp, _i64, _pi64, _pu64, _pt]),
     "b2_take_u32_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
     "b2_take_u32_ragged_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),

@@ -398,6 +398,100 @@ split_pairs_kernel(const uint2* __restrict__ pairs, int64_t n, uint32_t* __restr
   }
 }
 
+// ---- join of pre-partitioned sides (the fused multi-GPU shuffle delivers them) -------------------
+// Both sides arrive grouped into 2^seg_bits coarse buckets on hash bits [skip, skip + seg_bits),
+// bucket boundaries in d_*_seg_off. Only the fine pass is left (or nothing at all when the coarse
+// buckets are already table-sized).
+struct SegPlan {
+  int total_bits, fine_bits;
+  size_t off_state, off_roff, off_loff, off_rout, off_lout, off_part, part_bytes, total;
+};
+
+bool make_seg_plan(int64_t nl, int64_t nr, int skip_bits, int seg_bits, SegPlan* P) {
+  int bits = ceil_log2_i64((nr + kTargetBuild - 1) / kTargetBuild);
+  bits = std::max(bits, seg_bits);
+  bits = std::min(bits, 32 - skip_bits);
+  // one fine pass refines a coarse bucket at most 2^10-fold; beyond that partitions simply get
+  // larger than the table and the probe kernel builds them in chunks
+  bits = std::min(bits, seg_bits + kPartMaxBits);
+  P->total_bits = bits;
+  P->fine_bits = bits - seg_bits;
+  const size_t noff = (((size_t)1 << bits) + 1) * 8;
+  size_t o = 0;
+  P->off_state = o; o += 256;
+  P->off_roff = o;  o += b2_align_up(noff, 256);
+  P->off_loff = o;  o += b2_align_up(noff, 256);
+  const bool fine = P->fine_bits > 0;
+  P->off_rout = o;  o += fine ? b2_align_up((size_t)nr * 8, 256) : 0;
+  P->off_lout = o;  o += fine ? b2_align_up((size_t)nl * 8, 256) : 0;
+  const int64_t nseg = (int64_t)1 << seg_bits;
+  P->part_bytes = fine ? std::max(part_pass_ws_bytes(nr, nseg, P->fine_bits),
+                                  part_pass_ws_bytes(nl, nseg, P->fine_bits)) : 0;
+  P->off_part = o;  o += b2_align_up(P->part_bytes, 256);
+  P->total = o;
+  return true;
+}
+
+int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, int64_t nl,
+                  const uint2* rpairs, const int64_t* r_seg_off, int64_t nr, int seg_bits,
+                  uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                  uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+  B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
+  B2_REQUIRE(ctx, seg_bits >= 0 && seg_bits <= kPartMaxBits && skip_bits >= 0 && skip_bits + seg_bits <= 20,
+             "bad skip/segment bits");
+  B2_REQUIRE(ctx, d_out_rows && l_seg_off && r_seg_off, "null pointer");
+  B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
+             "workspace must be 256 B aligned");
+  SegPlan P;
+  if (!make_seg_plan(nl, nr, skip_bits, seg_bits, &P))
+    return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "segmented join",
+                        "build side too large for one fine pass; use b2_join_pairs_dev");
+  if (P.total > ws_bytes)
+    return b2_set_error(ctx, B2_ERR_WORKSPACE, "segmented join workspace", "see b2_join_seg_ws_bytes()");
+  char* base = static_cast<char*>(d_ws);
+  JoinState* st = reinterpret_cast<JoinState*>(base + P.off_state);
+  join_init_kernel<<<1, 1, 0, s>>>(st);
+  B2_LAUNCH_CHECK(ctx, "join_init_kernel");
+  if (nl > 0 && nr > 0) {
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSlots * 8));
+    const int64_t nseg = (int64_t)1 << seg_bits;
+    const int64_t nparts = (int64_t)1 << P.total_bits;
+    const uint2 *rp = rpairs, *lp = lpairs;
+    const int64_t *roff = r_seg_off, *loff = l_seg_off;
+    if (P.fine_bits > 0) {
+      PartGeom g;
+      g.bits = P.fine_bits;
+      g.shl = skip_bits + seg_bits;
+      PartInput rin, lin;
+      rin.pairs = rpairs;
+      lin.pairs = lpairs;
+      uint2* rout = reinterpret_cast<uint2*>(base + P.off_rout);
+      uint2* lout = reinterpret_cast<uint2*>(base + P.off_lout);
+      int64_t* roff_w = reinterpret_cast<int64_t*>(base + P.off_roff);
+      int64_t* loff_w = reinterpret_cast<int64_t*>(base + P.off_loff);
+      void* pws = base + P.off_part;
+      B2_RETURN_NOT_OK(part_pass(ctx, rin, nr, r_seg_off, nseg, g, rout, nr, roff_w, &st->overflow, pws,
+                                 P.part_bytes, s));
+      B2_RETURN_NOT_OK(part_pass(ctx, lin, nl, l_seg_off, nseg, g, lout, nl, loff_w, &st->overflow, pws,
+                                 P.part_bytes, s));
+      rp = rout; lp = lout; roff = roff_w; loff = loff_w;
+    }
+    const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * 2);
+    join_probe_kernel<<<(unsigned)grid, kThreads, kSlots * 8, s>>>(
+        rp, roff, lp, loff, nparts, skip_bits, P.total_bits, d_out_fk, d_out_y, d_out_x, out_capacity, st);
+    B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
+  }
+  join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows);
+  B2_LAUNCH_CHECK(ctx, "join_finish_kernel");
+  return B2_OK;
+}
+
+__global__ void set_segment_kernel(int64_t* seg_off, int64_t n) {
+  seg_off[0] = 0;
+  seg_off[1] = n;
+}
+
 }  // namespace
 
 extern "C" {
@@ -476,6 +570,74 @@ int b2_shuffle_partition_u32_dev(b2_ctx* ctx, const uint32_t* d_key, const uint3
   in.vals = d_val;
   return part_full(ctx, in, n, bits, 0, 0, 0, 0, reinterpret_cast<uint2*>(d_pairs_out), nullptr, n,
                    d_dest_off, nullptr, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- fused multi-GPU shuffle: count, then scatter straight into the peers' receive buffers -----
+size_t b2_shuffle_p2p_ws_bytes(int64_t n, int bits) {
+  if (n < 0 || bits < 0 || bits > kPartMaxBits) return 0;
+  return 256 + b2_align_up(part_pass_ws_bytes(n, 1, bits), 256);
+}
+
+int b2_shuffle_p2p_count_dev(b2_ctx* ctx, const uint32_t* d_key, int64_t n, int bits, int64_t* d_bucket_off,
+                             void* d_ws, size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, n >= 0 && bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
+  B2_REQUIRE(ctx, d_bucket_off != nullptr && (n == 0 || d_key != nullptr), "null pointer");
+  B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
+             "workspace must be 256 B aligned");
+  if (ws_bytes < b2_shuffle_p2p_ws_bytes(n, bits))
+    return b2_set_error(ctx, B2_ERR_WORKSPACE, "p2p shuffle workspace", "use b2_shuffle_p2p_ws_bytes()");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(d_ws);
+  int64_t* seg = reinterpret_cast<int64_t*>(base);
+  set_segment_kernel<<<1, 1, 0, s>>>(seg, n);
+  B2_LAUNCH_CHECK(ctx, "set_segment_kernel");
+  PartInput in;
+  in.keys = d_key;
+  PartGeom g;
+  g.bits = bits;
+  return part_count(ctx, in, n, seg, 1, g, d_bucket_off, base + 256, ws_bytes - 256, s);
+}
+
+int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
+                               int bits, const uint64_t* d_bucket_addr, void* d_ws, size_t ws_bytes,
+                               void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, n >= 0 && bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
+  B2_REQUIRE(ctx, d_bucket_addr != nullptr && (n == 0 || (d_key && d_val)), "null pointer");
+  B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
+             "workspace must be 256 B aligned");
+  if (ws_bytes < b2_shuffle_p2p_ws_bytes(n, bits))
+    return b2_set_error(ctx, B2_ERR_WORKSPACE, "p2p shuffle workspace", "use b2_shuffle_p2p_ws_bytes()");
+  char* base = static_cast<char*>(d_ws);
+  PartInput in;
+  in.keys = d_key;
+  in.vals = d_val;
+  PartGeom g;
+  g.bits = bits;
+  return part_scatter(ctx, in, n, reinterpret_cast<const int64_t*>(base), 1, g, nullptr, 0, d_bucket_addr,
+                      nullptr, base + 256, ws_bytes - 256, static_cast<cudaStream_t>(stream));
+}
+
+size_t b2_join_seg_ws_bytes(int64_t nl, int64_t nr, int hash_skip_bits, int seg_bits) {
+  SegPlan P;
+  if (nl < 0 || nr < 0 || !make_seg_plan(nl, nr, hash_skip_bits, seg_bits, &P)) return 0;
+  return P.total;
+}
+
+int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl,
+                          const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr, int seg_bits,
+                          uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                          uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
+                          void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, nl == 0 || d_l_pairs, "null left pairs");
+  B2_REQUIRE(ctx, nr == 0 || d_r_pairs, "null right pairs");
+  B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
+  return join_seg_impl(ctx, reinterpret_cast<const uint2*>(d_l_pairs), d_l_seg_off, nl,
+                       reinterpret_cast<const uint2*>(d_r_pairs), d_r_seg_off, nr, seg_bits, d_out_fk,
+                       d_out_y, d_out_x, out_capacity, d_out_rows, hash_skip_bits, d_ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
 }
 
 // ---- standalone partition (PartitionDpu) ----------------------------------------------------

@@ -59,6 +59,7 @@ struct Unit {
   int64_t row0, row1;  // rows of this unit
   int64_t hbase;       // histogram entry of (bucket 0, this unit); bucket p is at hbase + p*ustride
   int64_t ustride;     // units in this unit's segment
+  int64_t hbase0;      // histogram entry of (bucket 0, first unit of the segment)
   bool valid;
 };
 
@@ -80,7 +81,8 @@ __device__ __forceinline__ Unit find_unit(const int64_t* __restrict__ seg_off,
   u.ustride = unit_first[lo + 1] - unit_first[lo];
   u.row0 = seg_off[lo] + k * unit_rows;
   u.row1 = min(u.row0 + unit_rows, seg_off[lo + 1]);
-  u.hbase = unit_first[lo] * P + k;
+  u.hbase0 = unit_first[lo] * P;
+  u.hbase = u.hbase0 + k;
   return u;
 }
 
@@ -175,15 +177,16 @@ __global__ void __launch_bounds__(kThreads, 2)
 part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                     const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
                     PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
-                    int64_t out_cap, unsigned int* __restrict__ overflow) {
+                    int64_t out_cap, const uint64_t* __restrict__ bucket_addr,
+                    unsigned int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int P = 1 << g.bits;
   const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
   if (!u.valid) return;
   // shared-memory carve-up
   uint2* stage = reinterpret_cast<uint2*>(smem);                                   // [kPartTile]
-  uint64_t* gbase = reinterpret_cast<uint64_t*>(smem + sizeof(uint2) * kPartTile);  // [P] next global row
-  uint64_t* delta = gbase + P;                                                      // [P] gbase - tile_start
+  uint64_t* gbase = reinterpret_cast<uint64_t*>(smem + sizeof(uint2) * kPartTile);  // [P] next BYTE address
+  uint64_t* delta = gbase + P;                                                      // [P] gbase - 8*tile_start
   uint32_t* tile_start = reinterpret_cast<uint32_t*>(delta + P);                    // [P]
   uint32_t* tile_cnt = tile_start + P;                                              // [P]
   uint16_t* sbucket = reinterpret_cast<uint16_t*>(tile_cnt + P);                    // [kPartTile]
@@ -191,8 +194,15 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   __shared__ uint32_t s_tile_total;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Destinations are byte addresses. Local mode: out + 8 * (flat scan position). Peer mode
+  // (bucket_addr != nullptr, the fused multi-GPU shuffle): bucket p of THIS rank starts at
+  // bucket_addr[p] — an address inside another GPU's receive buffer, written over NVLink — and
+  // this unit's run starts where the units before it in the segment end.
+  const uint64_t cap_addr = bucket_addr ? ~0ull : reinterpret_cast<uint64_t>(out) + 8ull * (uint64_t)out_cap;
   for (int p = tid; p < P; p += kThreads) {
-    gbase[p] = scanned[u.hbase + (int64_t)p * u.ustride];
+    const uint64_t pos = scanned[u.hbase + (int64_t)p * u.ustride];
+    gbase[p] = bucket_addr ? bucket_addr[p] + 8ull * (pos - scanned[u.hbase0 + (int64_t)p * u.ustride])
+                           : reinterpret_cast<uint64_t>(out) + 8ull * pos;
     tile_cnt[p] = 0;
   }
   __syncthreads();
@@ -256,11 +266,11 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
       const int p = 2 * tid;
       if (p < P) {
         tile_start[p] = excl;
-        delta[p] = gbase[p] - excl;
+        delta[p] = gbase[p] - 8ull * excl;
       }
       if (p + 1 < P) {
         tile_start[p + 1] = excl + c[0];
-        delta[p + 1] = gbase[p + 1] - (excl + c[0]);
+        delta[p + 1] = gbase[p + 1] - 8ull * (excl + c[0]);
       }
     }
     __syncthreads();
@@ -281,9 +291,9 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     const uint32_t total = s_tile_total;
     for (uint32_t j = tid; j < total; j += kThreads) {
       const uint2 kv = stage[j];
-      const uint64_t dst = delta[sbucket[j]] + j;
-      if ((int64_t)dst < out_cap) {
-        st_stream_v2(out + dst, kv);
+      const uint64_t dst = delta[sbucket[j]] + 8ull * j;
+      if (dst < cap_addr) {
+        st_stream_v2(reinterpret_cast<uint2*>(dst), kv);
       } else if (overflow) {
         *overflow = 1u;
       }
@@ -291,7 +301,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     __syncthreads();
     // ---- advance the running destinations, clear the counters ----
     for (int p = tid; p < P; p += kThreads) {
-      gbase[p] += tile_cnt[p];
+      gbase[p] += 8ull * tile_cnt[p];
       tile_cnt[p] = 0;
     }
     __syncthreads();
@@ -347,11 +357,12 @@ PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
   return L;
 }
 
+// Phase 1 of a pass: unit table, histogram, flat scan, partition boundaries. Leaves the scanned
+// histogram in the workspace for part_scatter_impl (same n / nseg / geometry / workspace).
 template <bool kAoS>
-int part_pass_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off,
-                   int64_t nseg, const PartGeom& g, uint2* d_out, int64_t out_cap,
-                   int64_t* d_part_off, unsigned int* d_overflow, void* d_ws, size_t ws_bytes,
-                   cudaStream_t s) {
+int part_count_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off,
+                    int64_t nseg, const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes,
+                    cudaStream_t s) {
   const int P = 1 << g.bits;
   const PassLayout L = pass_layout(n, nseg, g.bits);
   if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition pass", "workspace");
@@ -365,24 +376,12 @@ int part_pass_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d
   B2_LAUNCH_CHECK(ctx, "part_unit_table_kernel");
   B2_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (size_t)L.n_entries * 4, s));
   if (L.max_units > 0) {
-    static bool attr_done_h[2] = {false, false};
-    if (!attr_done_h[kAoS]) {
-      B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)scatter_smem_bytes(kPartMaxBits)));
-      attr_done_h[kAoS] = true;
-    }
     part_hist_kernel<kAoS><<<(unsigned)L.max_units, kThreads, 0, s>>>(
         in, d_seg_off, unit_first, nseg, L.unit_rows, g, hist);
     B2_LAUNCH_CHECK(ctx, "part_hist_kernel");
   }
   B2_RETURN_NOT_OK(b2_exclusive_scan_u32_u64(ctx, hist, scanned, L.n_entries, base + L.off_scanws,
                                              ws_bytes - L.off_scanws, s));
-  if (L.max_units > 0) {
-    part_scatter_kernel<kAoS><<<(unsigned)L.max_units, kThreads, scatter_smem_bytes(g.bits), s>>>(
-        in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
-    B2_LAUNCH_CHECK(ctx, "part_scatter_kernel");
-  }
   if (d_part_off) {
     const int64_t cnt = nseg * P + 1;
     part_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(scanned, unit_first, nseg, P,
@@ -392,20 +391,61 @@ int part_pass_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d
   return B2_OK;
 }
 
+// Phase 2: scatter, to d_out (local) or to the per-bucket byte addresses in d_bucket_addr (peer).
+template <bool kAoS>
+int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off,
+                      int64_t nseg, const PartGeom& g, uint2* d_out, int64_t out_cap,
+                      const uint64_t* d_bucket_addr, unsigned int* d_overflow, void* d_ws,
+                      size_t ws_bytes, cudaStream_t s) {
+  const PassLayout L = pass_layout(n, nseg, g.bits);
+  if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition pass", "workspace");
+  char* base = static_cast<char*>(d_ws);
+  const int64_t* unit_first = reinterpret_cast<const int64_t*>(base + L.off_unit_first);
+  const uint64_t* scanned = reinterpret_cast<const uint64_t*>(base + L.off_scanned);
+  if (L.max_units > 0) {
+    static bool attr_done_h[2] = {false, false};
+    if (!attr_done_h[kAoS]) {
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)scatter_smem_bytes(kPartMaxBits)));
+      attr_done_h[kAoS] = true;
+    }
+    part_scatter_kernel<kAoS><<<(unsigned)L.max_units, kThreads, scatter_smem_bytes(g.bits), s>>>(
+        in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_bucket_addr,
+        d_overflow);
+    B2_LAUNCH_CHECK(ctx, "part_scatter_kernel");
+  }
+  return B2_OK;
+}
+
 }  // namespace
 
 size_t part_pass_ws_bytes(int64_t n, int64_t nseg, int bits) { return pass_layout(n, nseg, bits).total; }
 
+int part_count(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
+               const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+  B2_REQUIRE(ctx, g.bits >= 0 && g.bits <= kPartMaxBits, "fan-out per pass is limited to 2^10");
+  B2_REQUIRE(ctx, nseg >= 1, "at least one segment");
+  if (in.pairs) return part_count_impl<true>(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s);
+  return part_count_impl<false>(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s);
+}
+
+int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
+                 const PartGeom& g, uint2* d_out, int64_t out_cap, const uint64_t* d_bucket_addr,
+                 unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+  if (in.pairs)
+    return part_scatter_impl<true>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_bucket_addr,
+                                   d_overflow, d_ws, ws_bytes, s);
+  return part_scatter_impl<false>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_bucket_addr,
+                                  d_overflow, d_ws, ws_bytes, s);
+}
+
 int part_pass(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
               const PartGeom& g, uint2* d_out, int64_t out_cap, int64_t* d_part_off,
               unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s) {
-  B2_REQUIRE(ctx, g.bits >= 0 && g.bits <= kPartMaxBits, "fan-out per pass is limited to 2^10");
-  B2_REQUIRE(ctx, nseg >= 1, "at least one segment");
-  if (in.pairs)
-    return part_pass_impl<true>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_part_off,
-                                d_overflow, d_ws, ws_bytes, s);
-  return part_pass_impl<false>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_part_off,
-                               d_overflow, d_ws, ws_bytes, s);
+  B2_RETURN_NOT_OK(part_count(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s));
+  return part_scatter(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, nullptr, d_overflow, d_ws,
+                      ws_bytes, s);
 }
 
 // ---- one- or two-pass driver ------------------------------------------------------------------

@@ -49,6 +49,16 @@ int part_pass(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_
               const PartGeom& g, uint2* d_out, int64_t out_cap, int64_t* d_part_off,
               unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s);
 
+// The two phases of part_pass, separately: count (unit table, histogram, scan, boundaries) and
+// scatter. Between them the caller may turn the boundaries into per-bucket destination ADDRESSES
+// (d_bucket_addr, 2^bits byte addresses, single segment only): the fused multi-GPU shuffle points
+// them into the peers' receive buffers. Same n / segments / geometry / workspace for both calls.
+int part_count(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
+               const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes, cudaStream_t s);
+int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
+                 const PartGeom& g, uint2* d_out, int64_t out_cap, const uint64_t* d_bucket_addr,
+                 unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s);
+
 // Full partitioning by `bits` hash bits (after discarding `shl`), in one pass (bits <= 10) or two
 // (coarse pass + segmented fine pass). Result: d_out holds the rows grouped into 2^bits
 // partitions, d_off (2^bits + 1 int64) their boundaries. d_tmp (capacity cap rows) is only used

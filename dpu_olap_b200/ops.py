@@ -334,6 +334,57 @@ class Context:
                  "b2_shuffle_partition_u32_dev")
         return pairs_out[:n], dest_off
 
+    # ---- fused multi-GPU shuffle over peer memory --------------------------------------------------
+    def shuffle_p2p_ws_bytes(self, n: int, bits: int) -> int:
+        return int(self._lib.b2_shuffle_p2p_ws_bytes(n, bits))
+
+    @staticmethod
+    def _aligned(ws):
+        ptr = (_dptr(ws) + 255) // 256 * 256
+        return ptr, ws.numel() - (ptr - _dptr(ws))
+
+    def shuffle_p2p_count_dev(self, key, bits: int, ws, bucket_off=None):
+        """Rows per bucket (top `bits` bits of wang_hash): returns int64[2^bits + 1] boundaries."""
+        import torch
+        if bucket_off is None:
+            bucket_off = torch.empty((1 << bits) + 1, dtype=torch.int64, device=key.device)
+        ptr, nbytes = self._aligned(ws)
+        self._ck(self._lib.b2_shuffle_p2p_count_dev(self._h, _dptr(key), key.numel(), bits, _dptr(bucket_off),
+                                                    ptr, nbytes, self._stream()), "b2_shuffle_p2p_count_dev")
+        return bucket_off
+
+    def shuffle_p2p_scatter_dev(self, key, val, bits: int, bucket_addr, ws):
+        """Writes the (key, val) pairs of bucket b contiguously from byte address bucket_addr[b]
+        (int64 device tensor of 2^bits addresses — local or peer memory)."""
+        ptr, nbytes = self._aligned(ws)
+        self._ck(self._lib.b2_shuffle_p2p_scatter_dev(self._h, _dptr(key), _dptr(val), key.numel(), bits,
+                                                      _dptr(bucket_addr), ptr, nbytes, self._stream()),
+                 "b2_shuffle_p2p_scatter_dev")
+
+    def join_seg_ws_bytes(self, nl: int, nr: int, skip_bits: int, seg_bits: int) -> int:
+        return int(self._lib.b2_join_seg_ws_bytes(nl, nr, skip_bits, seg_bits))
+
+    def join_pairs_seg_dev(self, l_pairs, l_seg_off, r_pairs, r_seg_off, seg_bits: int, out_capacity: int,
+                           skip_bits: int, ws=None, outs=None, out_rows=None):
+        """Join of sides already grouped into 2^seg_bits coarse buckets (see b2_join_pairs_seg_dev)."""
+        import torch
+        dev = l_pairs.device
+        nl, nr = l_pairs.numel(), r_pairs.numel()
+        cap = int(out_capacity)
+        if outs is None:
+            outs = [torch.empty(max(cap, 1), dtype=torch.int32, device=dev) for _ in range(3)]
+        if out_rows is None:
+            out_rows = torch.empty(1, dtype=torch.int64, device=dev)
+        if ws is None:
+            ws = torch.empty(self.join_seg_ws_bytes(nl, nr, skip_bits, seg_bits) + 256, dtype=torch.uint8,
+                             device=dev)
+        ptr, nbytes = self._aligned(ws)
+        self._ck(self._lib.b2_join_pairs_seg_dev(self._h, _dptr(l_pairs), _dptr(l_seg_off), nl, _dptr(r_pairs),
+                                                 _dptr(r_seg_off), nr, seg_bits, _dptr(outs[0]), _dptr(outs[1]),
+                                                 _dptr(outs[2]), cap, _dptr(out_rows), skip_bits, ptr, nbytes,
+                                                 self._stream()), "b2_join_pairs_seg_dev")
+        return outs[0], outs[1], outs[2], out_rows
+
 
 def wang_hash(key: int) -> int:
     return int(_lib.lib().b2_wang_hash_u32(int(key) & 0xFFFFFFFF))

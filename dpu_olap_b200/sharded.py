@@ -140,3 +140,88 @@ class ShardedJoin:
         if c is None:
             return 0
         return 8 * (sum(c.send_l) - c.send_l[self.rank] + sum(c.send_r) - c.send_r[self.rank])
+
+
+# -------------------------------------------------------------------------------------------------
+# Fused shuffle over peer memory
+# -------------------------------------------------------------------------------------------------
+def p2p_plan(all_counts, peer_ptrs, rank: int, world: int):
+    """Destination addresses of one side of the fused shuffle.
+
+    all_counts int64[G, B]: rows of source rank s in bucket b (B = G * C buckets: destination rank
+    b // C, coarse bucket b % C there); peer_ptrs int64[G]: base address of every rank's receive
+    buffer. The receive buffer of rank r is laid out bucket-major, source-minor, so every coarse
+    bucket is contiguous. Returns
+      addr    int64[B]   byte address where THIS rank's rows of bucket b go,
+      seg_off int64[C+1] boundaries (rows) of the coarse buckets THIS rank receives,
+      n_recv  int64[]    rows THIS rank receives,
+      max_recv int64[]   largest receive count over all ranks (for the capacity check).
+    Pure tensor arithmetic: runs on the device without a host round trip, and on CPU tensors in
+    the tests."""
+    import torch
+    G = world
+    B = all_counts.shape[1]
+    C = B // G
+    tot = all_counts.sum(0).view(G, C)                        # rows per (destination, coarse bucket)
+    base_in_dest = (tot.cumsum(1) - tot).reshape(B)           # rows before bucket b at its destination
+    src_off = (all_counts.cumsum(0) - all_counts)[rank]       # rows of lower source ranks in bucket b
+    addr = peer_ptrs.repeat_interleave(C) + 8 * (base_in_dest + src_off)
+    seg_off = torch.zeros(C + 1, dtype=torch.int64, device=all_counts.device)
+    seg_off[1:] = tot[rank].cumsum(0)
+    per_rank = tot.sum(1)
+    return addr, seg_off, per_rank[rank], per_rank.max()
+
+
+class P2PShuffleJoin:
+    """Sharded join whose exchange is FUSED into the routing kernel: every rank scatters its
+    (key, payload) pairs straight into the peers' receive buffers with NVLink stores
+    (b2_shuffle_p2p_scatter_dev), already grouped into coarse partitions, so there is no separate
+    all-to-all and the receiver skips its first partitioning pass (b2_join_pairs_seg_dev).
+    Receive buffers are torch symmetric-memory allocations; their peer addresses come from the
+    rendezvous handle. Collectives left: one all-gather of 2 x 1024 counts and one barrier."""
+
+    BITS = 10  # log2(G) destination bits + coarse bits: one radix pass
+
+    def __init__(self, ctx, dist, rank: int, world: int, n_local: int, capacity: int):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
+        self.skip = log2_exact(world)
+        self.seg_bits = self.BITS - self.skip
+        self.capacity = capacity
+        dev = torch.device("cuda", torch.cuda.current_device())
+        group = dist.group.WORLD.group_name
+        self.recv, self.peers = [], []
+        for _ in range(2):  # L, R
+            t = symm.empty(capacity, dtype=torch.int64, device=dev)
+            hdl = symm.rendezvous(t, group)
+            self.recv.append(t)
+            self.peers.append(torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev))
+        nbytes = ctx.shuffle_p2p_ws_bytes(n_local, self.BITS) + 256
+        self.ws = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.off = [torch.empty((1 << self.BITS) + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.last_recv = (0, 0)
+
+    def step(self, fk, y, pk, x, local_join):
+        """local_join(l_pairs, l_seg_off, r_pairs, r_seg_off, seg_bits, skip_bits) -> result."""
+        import torch
+        ctx, G = self.ctx, self.world
+        ctx.shuffle_p2p_count_dev(fk, self.BITS, self.ws[0], self.off[0])
+        ctx.shuffle_p2p_count_dev(pk, self.BITS, self.ws[1], self.off[1])
+        counts = torch.stack([self.off[0][1:] - self.off[0][:-1], self.off[1][1:] - self.off[1][:-1]])
+        allc = torch.empty((G,) + tuple(counts.shape), dtype=torch.int64, device=counts.device)
+        # also a barrier: nobody scatters before every rank is done reading its receive buffers
+        self.dist.all_gather_into_tensor(allc, counts)
+        plans = [p2p_plan(allc[:, side, :].contiguous(), self.peers[side], self.rank, G) for side in range(2)]
+        sizes = torch.stack([plans[0][2], plans[1][2], plans[0][3], plans[1][3]]).cpu().tolist()
+        if max(sizes[2], sizes[3]) > self.capacity:
+            raise OverflowError(f"rank {self.rank}: a rank would receive {max(sizes[2], sizes[3])} rows, "
+                                f"capacity {self.capacity} (skewed keys)")
+        ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, plans[0][0], self.ws[0])
+        ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, plans[1][0], self.ws[1])
+        self.dist.all_reduce(self.flag)  # every rank's stores have landed when this completes
+        nl, nr = int(sizes[0]), int(sizes[1])
+        self.last_recv = (nl, nr)
+        return local_join(self.recv[0][:nl], plans[0][1], self.recv[1][:nr], plans[1][1], self.seg_bits,
+                          self.skip)

@@ -236,6 +236,41 @@ int b2_shuffle_partition_u32_dev(b2_ctx* ctx, const uint32_t* d_key, const uint3
                                  int nranks, uint64_t* d_pairs_out, int64_t* d_dest_off, void* d_ws,
                                  size_t ws_bytes, void* stream);
 
+/* ---- fused multi-GPU shuffle over peer memory (NVLink stores from inside the scatter kernel) ----
+ * Instead of grouping rows by destination and handing them to an all-to-all, every rank
+ *   1. counts its rows per bucket, bucket = top `bits` bits of wang_hash(key), where
+ *      bits = log2(nranks) + coarse_bits <= 10: the top log2(nranks) bits pick the destination
+ *      rank, the next coarse_bits the coarse partition there (b2_shuffle_p2p_count_dev;
+ *      d_bucket_off int64[2^bits + 1] = boundaries of the local buckets);
+ *   2. after the ranks have exchanged these counts (one small all-gather) and turned them into
+ *      destination addresses, scatters its (key, payload) pairs DIRECTLY to
+ *      d_bucket_addr[b] (device array of 2^bits byte addresses, usually inside the peers' receive
+ *      buffers: CUDA IPC / symmetric-memory pointers) — b2_shuffle_p2p_scatter_dev. Rows of bucket
+ *      b are written contiguously from d_bucket_addr[b] on; nothing is bounds-checked, the caller
+ *      sizes the receive buffers from the exchanged counts.
+ * The receiver therefore finds its rows ALREADY partitioned into 2^coarse_bits coarse buckets
+ * (bucket-major, source-rank-minor) and joins them with b2_join_pairs_seg_dev, which only runs
+ * the fine partitioning pass. This replaces b2_shuffle_partition + all-to-all + the receiver's
+ * first partitioning pass, i.e. the host-mediated repartition of partitioner.cc:350-375.
+ * Both calls must use the same n / bits / workspace; scatter reuses the scanned histogram. */
+size_t b2_shuffle_p2p_ws_bytes(int64_t n, int bits);
+int b2_shuffle_p2p_count_dev(b2_ctx* ctx, const uint32_t* d_key, int64_t n, int bits, int64_t* d_bucket_off,
+                             void* d_ws, size_t ws_bytes, void* stream);
+int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
+                               int bits, const uint64_t* d_bucket_addr, void* d_ws, size_t ws_bytes,
+                               void* stream);
+/* Join of sides that are already grouped into 2^seg_bits coarse buckets on hash bits
+ * [hash_skip_bits, hash_skip_bits + seg_bits); d_*_seg_off (int64, 2^seg_bits + 1, device) hold the
+ * bucket boundaries in rows. Same output contract as b2_join_pairs_dev. One fine pass refines a
+ * coarse bucket at most 2^10-fold; build sides beyond 2^(seg_bits + 22) rows still join correctly
+ * (oversized partitions are built in chunks) but more slowly. */
+size_t b2_join_seg_ws_bytes(int64_t nl, int64_t nr, int hash_skip_bits, int seg_bits);
+int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl,
+                          const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr, int seg_bits,
+                          uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                          uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -435,3 +435,98 @@ def test_join_skip_bits_matches_shuffle_routing(ctx):
     exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))
     for a, b in zip(got, exp):
         assert np.array_equal(a, b)
+
+
+# ---- fused multi-GPU shuffle, emulated with virtual ranks on one GPU -------------------------------
+@pytest.mark.parametrize("G,rows_per_rank", [(2, 70_000), (4, 300_000), (8, 40_000), (1, 50_000)])
+def test_p2p_shuffle_and_segmented_join_virtual_ranks(ctx, G, rows_per_rank):
+    """Every virtual rank counts, scatters straight into the (local stand-ins for the) peers'
+    receive buffers, and joins what it received with the segmented join; the union of the G
+    results must equal the oracle join of the whole input, and every received row must belong to
+    its rank and sit in its coarse bucket."""
+    from dpu_olap_b200.sharded import log2_exact, p2p_plan
+    BITS = 10
+    skip = log2_exact(G)
+    seg_bits = BITS - skip
+    C = 1 << seg_bits
+    rng = np.random.default_rng(G)
+    n = G * rows_per_rank
+    pk = rng.permutation(np.arange(n, dtype=np.uint32) * 7 + 3)            # unique build keys
+    x = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    fk = pk[rng.integers(0, n, size=n)]                                      # every probe row matches
+    fk[:100] = 1                                                             # ... except these
+    y = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    sl = lambda a, r: a[r * rows_per_rank:(r + 1) * rows_per_rank]
+    cap = rows_per_rank * 2 + 1024
+    recv = [[torch.zeros(cap, dtype=torch.int64, device="cuda") for _ in range(G)] for _ in range(2)]
+    peers = [torch.tensor([t.data_ptr() for t in recv[s]], dtype=torch.int64, device="cuda") for s in range(2)]
+    d = {r: [dev(sl(a, r)) for a in (fk, y, pk, x)] for r in range(G)}
+    wss = {(r, s): torch.empty(ctx.shuffle_p2p_ws_bytes(rows_per_rank, BITS) + 256, dtype=torch.uint8, device="cuda")
+           for r in range(G) for s in range(2)}
+    offs = {}
+    for r in range(G):
+        offs[r, 0] = ctx.shuffle_p2p_count_dev(d[r][0], BITS, wss[r, 0])
+        offs[r, 1] = ctx.shuffle_p2p_count_dev(d[r][2], BITS, wss[r, 1])
+    allc = [torch.stack([offs[r, s][1:] - offs[r, s][:-1] for r in range(G)]) for s in range(2)]
+    # counts agree with the oracle's routing
+    assert np.array_equal(allc[0][0].cpu().numpy(), np.bincount(oracle.partition_ids(sl(fk, 0), 1 << BITS), minlength=1 << BITS))
+    plans = {(r, s): p2p_plan(allc[s], peers[s], r, G) for r in range(G) for s in range(2)}
+    for r in range(G):
+        ctx.shuffle_p2p_scatter_dev(d[r][0], d[r][1], BITS, plans[r, 0][0], wss[r, 0])
+        ctx.shuffle_p2p_scatter_dev(d[r][2], d[r][3], BITS, plans[r, 1][0], wss[r, 1])
+    torch.cuda.synchronize()
+    got = [[], [], []]
+    for r in range(G):
+        nl, nr = int(plans[r, 0][2]), int(plans[r, 1][2])
+        lrecv, rrecv = recv[0][r][:nl], recv[1][r][:nr]
+        # received rows: right rank, right coarse bucket
+        k = (lrecv.cpu().numpy().view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        ids = oracle.partition_ids(k, 1 << BITS)
+        assert np.all(ids >> seg_bits == r) if G > 1 else True
+        seg = plans[r, 0][1].cpu().numpy()
+        assert np.array_equal(np.bincount(ids & (C - 1), minlength=C), np.diff(seg))
+        assert np.all(np.diff(ids) >= 0)  # bucket-major
+        o_fk, o_y, o_x, rows = ctx.join_pairs_seg_dev(lrecv, plans[r, 0][1], rrecv, plans[r, 1][1], seg_bits,
+                                                      out_capacity=max(nl, 1), skip_bits=skip)
+        torch.cuda.synchronize()
+        m = int(rows.cpu().numpy().view(np.uint64)[0])
+        for i, t in enumerate((o_fk, o_y, o_x)):
+            got[i].append(host(t)[:m])
+    got = oracle.sort_rows(*[np.concatenate(g) for g in got])
+    exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))
+    assert got[0].size == exp[0].size
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b)
+
+
+def test_segmented_join_large_needs_fine_pass(ctx):
+    """2^22 rows per side in 128 coarse buckets: the fine pass (2^3 per bucket) must run."""
+    BITS, G = 10, 8
+    n = 1 << 25
+    rng = np.random.default_rng(11)
+    pk = rng.permutation(n).astype(np.uint32)
+    x = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    fk = rng.integers(0, n, size=n, dtype=np.uint32)
+    y = np.arange(n, dtype=np.uint32)
+    # keep only the rows virtual rank 5 of 8 would own, pre-grouped by the scatter kernel itself
+    keep_l = oracle.partition_ids(fk, G) == 5
+    keep_r = oracle.partition_ids(pk, G) == 5
+    fk, y, pk, x = fk[keep_l], y[keep_l], pk[keep_r], x[keep_r]
+    out = {}
+    for side, (k, v) in enumerate(((fk, y), (pk, x))):
+        ws = torch.empty(ctx.shuffle_p2p_ws_bytes(k.size, BITS) + 256, dtype=torch.uint8, device="cuda")
+        dk, dv = dev(k), dev(v)
+        off = ctx.shuffle_p2p_count_dev(dk, BITS, ws)
+        buf = torch.zeros(k.size, dtype=torch.int64, device="cuda")
+        addr = buf.data_ptr() + 8 * off[:-1]
+        ctx.shuffle_p2p_scatter_dev(dk, dv, BITS, addr.contiguous(), ws)
+        out[side] = (buf, off[5 * 128: 6 * 128 + 1] - off[5 * 128])
+    o_fk, o_y, o_x, rows = ctx.join_pairs_seg_dev(out[0][0], out[0][1].contiguous(), out[1][0],
+                                                  out[1][1].contiguous(), 7, out_capacity=fk.size, skip_bits=3)
+    torch.cuda.synchronize()
+    m = int(rows.cpu().numpy().view(np.uint64)[0])
+    got = oracle.sort_rows(host(o_fk)[:m], host(o_y)[:m], host(o_x)[:m])
+    exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))
+    assert m == exp[0].size
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b)

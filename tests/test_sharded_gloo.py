@@ -174,3 +174,34 @@ def test_all_sum_u64_wraps_like_uint64():
     out = _run("body_sum")
     exp = (((1 << 63) + 5) + ((1 << 63) + 6)) & 0xFFFFFFFFFFFFFFFF
     assert out[0] == out[1] == exp
+
+
+def test_p2p_plan_layout_is_a_partition_of_every_receive_buffer():
+    """Addresses from p2p_plan: at every destination the (bucket, source) runs tile the buffer
+    exactly, bucket-major and source-minor, and seg_off bounds the coarse buckets."""
+    from dpu_olap_b200.sharded import p2p_plan
+    G, C = 4, 8
+    B = G * C
+    rng = np.random.default_rng(3)
+    counts = torch.from_numpy(rng.integers(0, 50, size=(G, B)).astype(np.int64))
+    counts[1, 5] = 0
+    bases = torch.tensor([1 << 40, 2 << 40, 3 << 40, 4 << 40], dtype=torch.int64)
+    plans = [p2p_plan(counts, bases, r, G) for r in range(G)]
+    for dest in range(G):
+        runs = []  # (start row, rows, bucket, source) of everything written into dest's buffer
+        for src in range(G):
+            addr = plans[src][0]
+            for b in range(dest * C, (dest + 1) * C):
+                start = (int(addr[b]) - int(bases[dest]))
+                assert start % 8 == 0
+                runs.append((start // 8, int(counts[src, b]), b, src))
+        runs.sort(key=lambda r: (r[2], r[3]))
+        pos = 0
+        for start, rows, b, src in runs:
+            assert start == pos, (dest, b, src)
+            pos += rows
+        seg_off, n_recv, max_recv = plans[dest][1], plans[dest][2], plans[dest][3]
+        assert int(n_recv) == pos == int(seg_off[-1])
+        for c in range(C):
+            assert int(seg_off[c + 1] - seg_off[c]) == int(counts[:, dest * C + c].sum())
+        assert int(max_recv) == max(int(counts[:, r * C:(r + 1) * C].sum()) for r in range(G))
