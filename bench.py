@@ -359,6 +359,9 @@ def bench_join(ctx, D, args):
             l0 = ctx.launches
             ms = timed_steps(D, step, args.steps, args.warmup)
             info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
+            ph = {}
+            pj.step(fk, y, pk, x, local_join, phases=ph)  # one extra, synchronised step: where the time goes
+            info["phases_ms_rank0_serialised"] = {k: round(v, 3) for k, v in ph.items()}
             nl_r, nr_r = pj.last_recv
             info["shuffle_rows_received_rank0"] = [nl_r, nr_r]
             info["shuffle_bytes_sent_per_rank"] = int(16 * n * (G - 1) / G)  # expectation: hash-uniform

@@ -172,25 +172,31 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 // 8-byte table read (destination of the bucket's run minus its position in the tile) per row
 // instead of hashing the key again. The first version of this kernel spent 105-111
 // lane-instructions per row (profiles/r1_join.md).
-template <bool kAoS>
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool kAoS, int kT>
+__global__ void __launch_bounds__(kT, 1024 / kT)
 part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                     const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
                     PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
                     int64_t out_cap, const uint64_t* __restrict__ bucket_addr,
                     unsigned int* __restrict__ overflow) {
+  // kT threads handle tiles of kT * 16 rows: 512 threads / 8192 rows (two CTAs per SM) for local
+  // destinations; 1024 threads / 16384 rows (one CTA per SM) for peer destinations, where a
+  // bucket's run per tile is twice as long (128 B at 1024 buckets) and NVLink packets fill up.
+  constexpr int kTileRows = kT * kItems;
+  constexpr int kW = kT / 32;
+  constexpr int kBpt = (1 << kPartMaxBits) / kT;  // buckets per thread in the tile scan
   extern __shared__ __align__(16) unsigned char smem[];
   const int P = 1 << g.bits;
   const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
   if (!u.valid) return;
   // shared-memory carve-up
-  uint2* stage = reinterpret_cast<uint2*>(smem);                                   // [kPartTile]
-  uint64_t* gbase = reinterpret_cast<uint64_t*>(smem + sizeof(uint2) * kPartTile);  // [P] next BYTE address
+  uint2* stage = reinterpret_cast<uint2*>(smem);                                   // [kTileRows]
+  uint64_t* gbase = reinterpret_cast<uint64_t*>(smem + sizeof(uint2) * kTileRows);  // [P] next BYTE address
   uint64_t* delta = gbase + P;                                                      // [P] gbase - 8*tile_start
   uint32_t* tile_start = reinterpret_cast<uint32_t*>(delta + P);                    // [P]
   uint32_t* tile_cnt = tile_start + P;                                              // [P]
-  uint16_t* sbucket = reinterpret_cast<uint16_t*>(tile_cnt + P);                    // [kPartTile]
-  __shared__ uint32_t warp_tot[kWarps];
+  uint16_t* sbucket = reinterpret_cast<uint16_t*>(tile_cnt + P);                    // [kTileRows]
+  __shared__ uint32_t warp_tot[kW];
   __shared__ uint32_t s_tile_total;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -199,7 +205,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   // bucket_addr[p] — an address inside another GPU's receive buffer, written over NVLink — and
   // this unit's run starts where the units before it in the segment end.
   const uint64_t cap_addr = bucket_addr ? ~0ull : reinterpret_cast<uint64_t>(out) + 8ull * (uint64_t)out_cap;
-  for (int p = tid; p < P; p += kThreads) {
+  for (int p = tid; p < P; p += kT) {
     const uint64_t pos = scanned[u.hbase + (int64_t)p * u.ustride];
     gbase[p] = bucket_addr ? bucket_addr[p] + 8ull * (pos - scanned[u.hbase0 + (int64_t)p * u.ustride])
                            : reinterpret_cast<uint64_t>(out) + 8ull * pos;
@@ -207,12 +213,12 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   }
   __syncthreads();
 
-  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kPartTile) {
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kTileRows) {
     // ---- load, hash once, rank inside the bucket ----
     uint32_t key[kItems], val[kItems], packed[kItems];  // packed = bucket | rank << 16
-    if (t0 + kPartTile <= u.row1) {  // full tile: no bounds checks
+    if (t0 + kTileRows <= u.row1) {  // full tile: no bounds checks
 #pragma unroll
-      for (int it = 0; it < kItems; ++it) load_row<kAoS>(in, t0 + it * kThreads + tid, key[it], val[it]);
+      for (int it = 0; it < kItems; ++it) load_row<kAoS>(in, t0 + it * kT + tid, key[it], val[it]);
 #pragma unroll
       for (int it = 0; it < kItems; ++it) {
         const uint32_t b = bucket_or_skip(key[it], g);
@@ -222,7 +228,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     } else {
 #pragma unroll
       for (int it = 0; it < kItems; ++it) {
-        const int64_t row = t0 + it * kThreads + tid;
+        const int64_t row = t0 + it * kT + tid;
         key[it] = 0;
         val[it] = 0;
         packed[it] = 0xffffffffu;
@@ -235,14 +241,16 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     }
     __syncthreads();
 
-    // ---- exclusive scan of the tile counts (two buckets per thread) ----
-    uint32_t c[2] = {0, 0};
+    // ---- exclusive scan of the tile counts (kBpt buckets per thread) ----
+    uint32_t c[kBpt];
+    uint32_t csum = 0;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int p = 2 * tid + q;
-      if (p < P) c[q] = tile_cnt[p];
+    for (int q = 0; q < kBpt; ++q) {
+      const int p = kBpt * tid + q;
+      c[q] = p < P ? tile_cnt[p] : 0;
+      csum += c[q];
     }
-    uint32_t incl = c[0] + c[1];
+    uint32_t incl = csum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -252,25 +260,25 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     __syncthreads();
     {
       // every warp scans the 16 warp totals itself (no second barrier for a one-warp scan)
-      const uint32_t w = lane < kWarps ? warp_tot[lane] : 0;
+      const uint32_t w = lane < kW ? warp_tot[lane] : 0;
       uint32_t wi = w;
 #pragma unroll
-      for (int o = 1; o < kWarps; o <<= 1) {
+      for (int o = 1; o < kW; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
         if (lane >= o) wi += t;
       }
       const uint32_t wbase = __shfl_sync(0xffffffffu, wi - w, warp);
-      const uint32_t tile_total = __shfl_sync(0xffffffffu, wi, kWarps - 1);
+      const uint32_t tile_total = __shfl_sync(0xffffffffu, wi, kW - 1);
       if (tid == 0) s_tile_total = tile_total;
-      const uint32_t excl = wbase + incl - (c[0] + c[1]);
-      const int p = 2 * tid;
-      if (p < P) {
-        tile_start[p] = excl;
-        delta[p] = gbase[p] - 8ull * excl;
-      }
-      if (p + 1 < P) {
-        tile_start[p + 1] = excl + c[0];
-        delta[p + 1] = gbase[p + 1] - 8ull * (excl + c[0]);
+      uint32_t excl = wbase + incl - csum;
+#pragma unroll
+      for (int q = 0; q < kBpt; ++q) {
+        const int p = kBpt * tid + q;
+        if (p < P) {
+          tile_start[p] = excl;
+          delta[p] = gbase[p] - 8ull * excl;
+        }
+        excl += c[q];
       }
     }
     __syncthreads();
@@ -289,7 +297,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 
     // ---- stream out: consecutive threads -> consecutive rows of a bucket's run ----
     const uint32_t total = s_tile_total;
-    for (uint32_t j = tid; j < total; j += kThreads) {
+    for (uint32_t j = tid; j < total; j += kT) {
       const uint2 kv = stage[j];
       const uint64_t dst = delta[sbucket[j]] + 8ull * j;
       if (dst < cap_addr) {
@@ -300,7 +308,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     }
     __syncthreads();
     // ---- advance the running destinations, clear the counters ----
-    for (int p = tid; p < P; p += kThreads) {
+    for (int p = tid; p < P; p += kT) {
       gbase[p] += 8ull * tile_cnt[p];
       tile_cnt[p] = 0;
     }
@@ -324,9 +332,10 @@ __global__ void part_offsets_kernel(const uint64_t* __restrict__ scanned,
   part_off[i] = (int64_t)scanned[unit_first[s] * P + p * ustride];
 }
 
-size_t scatter_smem_bytes(int bits) {
+size_t scatter_smem_bytes(int bits, int threads) {
   const size_t P = (size_t)1 << bits;
-  return sizeof(uint2) * kPartTile + P * 8 + P * 8 + P * 4 + P * 4 + sizeof(uint16_t) * kPartTile;
+  const size_t tile = (size_t)threads * kItems;
+  return sizeof(uint2) * tile + P * 8 + P * 8 + P * 4 + P * 4 + sizeof(uint16_t) * tile;
 }
 
 int64_t choose_unit_rows(int64_t n, int64_t nseg) {
@@ -403,16 +412,31 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
   const int64_t* unit_first = reinterpret_cast<const int64_t*>(base + L.off_unit_first);
   const uint64_t* scanned = reinterpret_cast<const uint64_t*>(base + L.off_scanned);
   if (L.max_units > 0) {
-    static bool attr_done_h[2] = {false, false};
-    if (!attr_done_h[kAoS]) {
-      B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)scatter_smem_bytes(kPartMaxBits)));
-      attr_done_h[kAoS] = true;
+    if (d_bucket_addr) {  // peer destinations: 16384-row tiles, 128 B runs
+      constexpr int kT = 2 * kThreads;
+      static bool attr_done_p[2] = {false, false};
+      if (!attr_done_p[kAoS]) {
+        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)scatter_smem_bytes(kPartMaxBits, kT)));
+        attr_done_p[kAoS] = true;
+      }
+      part_scatter_kernel<kAoS, kT><<<(unsigned)L.max_units, kT, scatter_smem_bytes(g.bits, kT), s>>>(
+          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_bucket_addr,
+          d_overflow);
+    } else {
+      static bool attr_done_h[2] = {false, false};
+      if (!attr_done_h[kAoS]) {
+        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kThreads>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)scatter_smem_bytes(kPartMaxBits, kThreads)));
+        attr_done_h[kAoS] = true;
+      }
+      part_scatter_kernel<kAoS, kThreads><<<(unsigned)L.max_units, kThreads,
+                                            scatter_smem_bytes(g.bits, kThreads), s>>>(
+          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_bucket_addr,
+          d_overflow);
     }
-    part_scatter_kernel<kAoS><<<(unsigned)L.max_units, kThreads, scatter_smem_bytes(g.bits), s>>>(
-        in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_bucket_addr,
-        d_overflow);
     B2_LAUNCH_CHECK(ctx, "part_scatter_kernel");
   }
   return B2_OK;

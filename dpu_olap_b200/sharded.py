@@ -203,12 +203,29 @@ class P2PShuffleJoin:
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.last_recv = (0, 0)
 
-    def step(self, fk, y, pk, x, local_join):
-        """local_join(l_pairs, l_seg_off, r_pairs, r_seg_off, seg_bits, skip_bits) -> result."""
+    def step(self, fk, y, pk, x, local_join, phases: dict | None = None):
+        """local_join(l_pairs, l_seg_off, r_pairs, r_seg_off, seg_bits, skip_bits) -> result.
+        phases: if given, every phase is synchronised and its wall time (ms) stored there
+        (diagnostics only — the synchronisation removes all overlap)."""
+        import time
+
         import torch
         ctx, G = self.ctx, self.world
+        t0 = [time.perf_counter()]
+
+        def mark(name):
+            if phases is not None:
+                torch.cuda.synchronize()
+                now = time.perf_counter()
+                phases[name] = phases.get(name, 0.0) + (now - t0[0]) * 1e3
+                t0[0] = now
+
+        if phases is not None:
+            torch.cuda.synchronize()
+            t0[0] = time.perf_counter()
         ctx.shuffle_p2p_count_dev(fk, self.BITS, self.ws[0], self.off[0])
         ctx.shuffle_p2p_count_dev(pk, self.BITS, self.ws[1], self.off[1])
+        mark("count")
         counts = torch.stack([self.off[0][1:] - self.off[0][:-1], self.off[1][1:] - self.off[1][:-1]])
         allc = torch.empty((G,) + tuple(counts.shape), dtype=torch.int64, device=counts.device)
         # also a barrier: nobody scatters before every rank is done reading its receive buffers
@@ -218,10 +235,15 @@ class P2PShuffleJoin:
         if max(sizes[2], sizes[3]) > self.capacity:
             raise OverflowError(f"rank {self.rank}: a rank would receive {max(sizes[2], sizes[3])} rows, "
                                 f"capacity {self.capacity} (skewed keys)")
+        mark("allgather+plan")
         ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, plans[0][0], self.ws[0])
         ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, plans[1][0], self.ws[1])
+        mark("scatter_nvlink")
         self.dist.all_reduce(self.flag)  # every rank's stores have landed when this completes
+        mark("barrier")
         nl, nr = int(sizes[0]), int(sizes[1])
         self.last_recv = (nl, nr)
-        return local_join(self.recv[0][:nl], plans[0][1], self.recv[1][:nr], plans[1][1], self.seg_bits,
-                          self.skip)
+        out = local_join(self.recv[0][:nl], plans[0][1], self.recv[1][:nr], plans[1][1], self.seg_bits,
+                         self.skip)
+        mark("local_join")
+        return out
