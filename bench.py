@@ -449,7 +449,10 @@ def bench_e2e_filter(ctx, D, args):
 
     from dpu_olap_b200._lib import Timings
     from dpu_olap_b200.generator import RandomArrayGenerator
-    nb_total = args.e2e_sf << 7
+    # every rank streams e2e_sf worth of batches through its own PCIe link (the host buffers of a
+    # 64 GiB column do not fit this leg's time budget): total = e2e_sf x N
+    e2e_sf = args.e2e_sf * D.world
+    nb_total = e2e_sf << 7
     first, nb = shard(nb_total, D)
     n = nb * FILTER_BATCH
     g = RandomArrayGenerator(ctx, 42)
@@ -490,8 +493,8 @@ def bench_e2e_filter(ctx, D, args):
     if exp.size != got.size or not np.array_equal(exp, got):
         raise SystemExit("e2e filter self-check failed")
     rows = nb_total * FILTER_BATCH
-    res = {"value": rows / (ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": acc["h2d"],
-           "d2h_bytes_per_step": acc["d2h"], "ms_per_step": ms, "sf": args.e2e_sf, "rows": rows,
+    res = {"value": rows / (ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": acc["h2d"] * D.world,
+           "d2h_bytes_per_step": acc["d2h"] * D.world, "ms_per_step": ms, "sf": e2e_sf, "rows": rows,
            "api": "b2_filter_lt_u32_host_into (pinned host batches in, pinned host result out; "
                   "upload / kernels / download of 64 MiB groups overlap)",
            "phases_ms": {"copy-to-dpu": t1.copy_to_dev_ms, "dpu-work": t1.dev_work_ms,
