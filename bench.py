@@ -295,6 +295,9 @@ def bench_take(ctx, D, args):
     return {"ms_per_step": ms, "indices": nidx, "value_rows": nb_total * TAKE_BATCH,
             "rows_per_s": nidx / (ms * 1e-3), "algorithmic_bytes_per_index": 12,
             "achieved_gbs": 12 * nidx / D.world / (ms * 1e-3) / 1e9,
+            # what HBM really moves: at 1 index per 8 values nearly every 64 B unit of the batch
+            # window is touched (profiles/r1_sum_take.md), so the window itself is the traffic
+            "window_gbs": (4 * nb_total * TAKE_BATCH + 8 * nidx) / D.world / (ms * 1e-3) / 1e9,
             "reference_convention_rows_per_s": nb_total * TAKE_BATCH / (ms * 1e-3)}
 
 
