@@ -657,7 +657,14 @@ def main():
                        "sharding": "contiguous batch ranges per GPU, no collective",
                        "l2": "inputs (>= 8 GiB per GPU) far exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         # DRAM bytes per launch per GPU: ncu --set full at SF=128 measured
+                         # dram__bytes_read + dram__bytes_write = 0.993 x the algorithmic bytes
+                         # (profiles/r1_ncu_full_final_sf128.csv); scaled to this launch's rows
+                         "traffic": 0.993 * fres["algorithmic_bytes"] / D.world,
+                         "traffic_source": "ncu dram__bytes_{read,write}.sum at SF=128 (0.993 x algorithmic), scaled by rows",
+                         "algorithmic_bytes_per_launch": fres["algorithmic_bytes"] / D.world,
+                         "peak_source": peak_src,
                          "kernel": "filter_lt_u32_kernel",
                          "algorithmic_bytes_per_row": fres["algorithmic_bytes"] / fres["rows"],
                          "note": "bytes = 4 B read per row + 4 B written per selected row, per GPU; "

@@ -45,6 +45,7 @@ constexpr int kItems = 9;                      // rows per thread per round (bui
 constexpr int kRound = kThreads * kItems;      // 4608 rows: mean partition + 8 sigma in one round
 constexpr int kSegs = kWarps * kItems;         // (item, warp) match counts per probe round
 constexpr int kSegsPerLane = (kSegs + 31) / 32;
+constexpr int kProbeCtasPerSm = 2;             // 3 CTAs/SM (40 registers, spills) measured 5 % slower
 
 struct JoinState {  // lives in the workspace header
   unsigned long long out_rows;
@@ -96,7 +97,7 @@ __device__ __forceinline__ uint32_t hit_mask(const uint4& cur, uint32_t key) {
 // per row, profiles/r1_join.md). All global loads of a partition (its build rows and the first
 // round of probe rows) are issued before anything else, so the table clear and the inserts run
 // under that latency.
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kProbeCtasPerSm)
 join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ roff,
                   const uint2* __restrict__ lpairs, const int64_t* __restrict__ loff,
                   int64_t nparts, int part_shl, int part_bits, uint32_t* __restrict__ out_fk,
@@ -366,7 +367,7 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
                                  rout, tmp, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
       B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
                                  lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s));
-      int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * 2);
+      int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
       join_probe_kernel<<<(unsigned)grid, kThreads, kSlots * 8, s>>>(
           rout, roff, lout, loff, nparts, part_shl, P.bits, d_out_fk, d_out_y, d_out_x,
           out_capacity, st);
@@ -477,7 +478,7 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
                                  P.part_bytes, s));
       rp = rout; lp = lout; roff = roff_w; loff = loff_w;
     }
-    const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * 2);
+    const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
     join_probe_kernel<<<(unsigned)grid, kThreads, kSlots * 8, s>>>(
         rp, roff, lp, loff, nparts, skip_bits, P.total_bits, d_out_fk, d_out_y, d_out_x, out_capacity, st);
     B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
