@@ -316,6 +316,176 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   }
 }
 
+// ---- peer-destination scatter with line carry --------------------------------------------------
+// NVLink peer stores run at ~670 GB/s when every warp-level store covers whole 128-byte lines of
+// the destination, but only ~380 GB/s for 128-byte runs that start 8 bytes off a line
+// (tools/p2p_write_probe.py, profiles/r1_nvlink_store_probe.log). Rows are packed densely at the
+// destination, so a bucket's run of one tile starts at an arbitrary 8-byte offset. This kernel
+// therefore keeps, per bucket, the rows that do not fill a whole 128-byte line (at most 15) in a
+// shared-memory carry buffer and prepends them to the bucket's rows of the next tile: only whole,
+// aligned lines are stored (one half-warp per line), plus one partial line per (unit, bucket) at
+// each end of the unit's region.
+constexpr int kLineRows = 16;                      // 128 B / 8 B
+constexpr int kLcThreads = 1024;
+constexpr int kLcItems = 8;
+constexpr int kLcTile = kLcThreads * kLcItems;     // 8192 rows
+constexpr int kLcMaxLines = kLcTile / kLineRows + (1 << kPartMaxBits);  // whole lines one tile can flush
+
+struct LcSmem {  // dynamic shared memory of part_scatter_lines_kernel (P = 1024 buckets)
+  uint2 stage[kLcTile];                                  // 64 KB: the tile sorted by bucket
+  uint2 carry[(1 << kPartMaxBits) * kLineRows];          // 128 KB: held-back rows, 16 slots per bucket
+  uint64_t gline[1 << kPartMaxBits];                     // aligned byte address of carry slot 0
+  uint32_t tile_start[1 << kPartMaxBits];
+  uint32_t tile_cnt[1 << kPartMaxBits];
+  uint32_t ccnt[1 << kPartMaxBits];                      // carried rows | ghost rows << 8
+  uint32_t line_off[1 << kPartMaxBits];                  // first flushed line of the bucket in this tile
+  uint16_t line_bucket[kLcMaxLines + 16];
+  uint32_t warp_tot[kLcThreads / 32];
+  uint32_t n_lines;
+};
+
+template <bool kAoS>
+__global__ void __launch_bounds__(kLcThreads, 1)
+part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
+                          const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
+                          PartGeom g, const uint64_t* __restrict__ scanned,
+                          const uint64_t* __restrict__ bucket_addr) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  LcSmem& sm = *reinterpret_cast<LcSmem*>(smem);
+  const int P = 1 << g.bits;
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
+  if (!u.valid) return;
+  constexpr int kW = kLcThreads / 32;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if ((int)tid < P) {
+    const int p = tid;
+    const uint64_t a0 = bucket_addr[p] +
+                        8ull * (scanned[u.hbase + (int64_t)p * u.ustride] - scanned[u.hbase0 + (int64_t)p * u.ustride]);
+    const uint32_t ghost = (uint32_t)((a0 >> 3) & (kLineRows - 1));  // rows of the line that are not ours
+    sm.gline[p] = a0 - 8ull * ghost;
+    sm.ccnt[p] = ghost | (ghost << 8);
+    sm.tile_cnt[p] = 0;
+  }
+  __syncthreads();
+
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kLcTile) {
+    // ---- load, hash once, rank inside the bucket ----
+    uint32_t key[kLcItems], val[kLcItems], packed[kLcItems];  // packed = bucket | rank << 16
+#pragma unroll
+    for (int it = 0; it < kLcItems; ++it) {
+      const int64_t row = t0 + it * kLcThreads + tid;
+      key[it] = 0;
+      val[it] = 0;
+      packed[it] = 0xffffffffu;
+      if (row < u.row1) load_row<kAoS>(in, row, key[it], val[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < kLcItems; ++it) {
+      const int64_t row = t0 + it * kLcThreads + tid;
+      if (row < u.row1) {
+        const uint32_t b = bucket_or_skip(key[it], g);
+        if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
+      }
+    }
+    __syncthreads();
+
+    // ---- one scan for both the staged position and the first flushed line of every bucket ----
+    uint32_t tc = 0, cc = 0, nl = 0;
+    if ((int)tid < P) {
+      tc = sm.tile_cnt[tid];
+      cc = sm.ccnt[tid] & 0xffu;
+      nl = (cc + tc) / kLineRows;
+    }
+    const uint32_t mine = tc | (nl << 16);  // rows <= 8192 and lines <= 1536 never carry into each other
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    __syncthreads();
+    {
+      const uint32_t w = sm.warp_tot[lane];  // kW == 32 warps
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < kW; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      const uint32_t wbase = __shfl_sync(0xffffffffu, wi - w, warp);
+      const uint32_t all = __shfl_sync(0xffffffffu, wi, kW - 1);
+      if (tid == 0) sm.n_lines = all >> 16;
+      const uint32_t excl = wbase + incl - mine;
+      if ((int)tid < P) {
+        sm.tile_start[tid] = excl & 0xffffu;
+        sm.line_off[tid] = excl >> 16;
+        for (uint32_t li = 0; li < nl; ++li) sm.line_bucket[(excl >> 16) + li] = (uint16_t)tid;
+      }
+    }
+    __syncthreads();
+
+    // ---- stage the tile sorted by bucket ----
+#pragma unroll
+    for (int it = 0; it < kLcItems; ++it) {
+      if (packed[it] != 0xffffffffu) {
+        const uint32_t b = packed[it] & 0xffffu;
+        sm.stage[sm.tile_start[b] + (packed[it] >> 16)] = make_uint2(key[it], val[it]);
+      }
+    }
+    __syncthreads();
+
+    // ---- flush whole lines: one half-warp per 128-byte line of the destination ----
+    {
+      const uint32_t n_lines = sm.n_lines;
+      const uint32_t hw = tid >> 4, l = tid & 15;
+      for (uint32_t i = hw; i < n_lines; i += kLcThreads / 16) {
+        const uint32_t b = sm.line_bucket[i];
+        const uint32_t li = i - sm.line_off[b];
+        const uint32_t cw = sm.ccnt[b];
+        const uint32_t c0 = cw & 0xffu, ghost = cw >> 8;
+        const uint32_t e = li * kLineRows + l;  // position in (carried rows ++ staged rows)
+        if (e >= ghost) {                       // ghost rows belong to the previous unit's region
+          const uint2 kv = e < c0 ? sm.carry[b * kLineRows + e] : sm.stage[sm.tile_start[b] + e - c0];
+          st_stream_v2(reinterpret_cast<uint2*>(sm.gline[b] + 8ull * e), kv);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- carry the rows that did not fill a line; advance; clear the counters ----
+    if ((int)tid < P) {
+      const uint32_t b = tid;
+      const uint32_t tot = cc + tc;
+      const uint32_t rem = tot & (kLineRows - 1);
+      uint32_t ghost = sm.ccnt[b] >> 8;
+      if (nl == 0) {  // nothing flushed: append the tile's rows to the carry
+        for (uint32_t k = 0; k < tc; ++k) sm.carry[b * kLineRows + cc + k] = sm.stage[sm.tile_start[b] + k];
+      } else {        // the tail comes from the staged rows (cc < 16 <= 16 * nl)
+        const uint32_t from = sm.tile_start[b] + nl * kLineRows - cc;
+        for (uint32_t k = 0; k < rem; ++k) sm.carry[b * kLineRows + k] = sm.stage[from + k];
+        sm.gline[b] += 128ull * nl;
+        ghost = 0;
+      }
+      sm.ccnt[b] = rem | (ghost << 8);
+      sm.tile_cnt[b] = 0;
+    }
+    __syncthreads();
+  }
+
+  // ---- end of the unit: the last, partial line of every bucket ----
+  {
+    const uint32_t hw = tid >> 4, l = tid & 15;
+    for (int b = hw; b < P; b += kLcThreads / 16) {
+      const uint32_t cw = sm.ccnt[b];
+      const uint32_t c0 = cw & 0xffu, ghost = cw >> 8;
+      if (l >= ghost && l < c0)
+        st_stream_v2(reinterpret_cast<uint2*>(sm.gline[b] + 8ull * l), sm.carry[b * kLineRows + l]);
+    }
+  }
+}
+
 // part_off[s*P + p] = first output row of (segment s, bucket p); part_off[nseg*P] = total rows.
 __global__ void part_offsets_kernel(const uint64_t* __restrict__ scanned,
                                     const int64_t* __restrict__ unit_first, int64_t nseg, int P,
@@ -412,18 +582,16 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
   const int64_t* unit_first = reinterpret_cast<const int64_t*>(base + L.off_unit_first);
   const uint64_t* scanned = reinterpret_cast<const uint64_t*>(base + L.off_scanned);
   if (L.max_units > 0) {
-    if (d_bucket_addr) {  // peer destinations: 16384-row tiles, 128 B runs
-      constexpr int kT = 2 * kThreads;
+    if (d_bucket_addr) {  // peer destinations: whole 128-byte lines only (line carry)
       static bool attr_done_p[2] = {false, false};
       if (!attr_done_p[kAoS]) {
-        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT>,
+        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_lines_kernel<kAoS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)scatter_smem_bytes(kPartMaxBits, kT)));
+                                             (int)sizeof(LcSmem)));
         attr_done_p[kAoS] = true;
       }
-      part_scatter_kernel<kAoS, kT><<<(unsigned)L.max_units, kT, scatter_smem_bytes(g.bits, kT), s>>>(
-          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_bucket_addr,
-          d_overflow);
+      part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
+          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr);
     } else {
       static bool attr_done_h[2] = {false, false};
       if (!attr_done_h[kAoS]) {
