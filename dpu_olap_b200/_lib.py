@@ -63,6 +63,10 @@ SIGNATURES = {
                                            _vp, _sz, _vp]),
     "b2_filter_lt_u32_host": (_int, [_vp, _pp, _pi64, _i64, _u32, _pi64, _pu64, _pt]),
     "b2_filter_fetch_host": (_int, [_vp, _pp, _i64, _pt]),
+    "b2_host_alloc_pinned": (_int, [_sz, C.POINTER(C.c_void_p)]),
+    "b2_host_free_pinned": (_int, [_vp]),
+    "b2_host_register": (_int, [_vp, _sz]),
+    "b2_host_unregister": (_int, [_vp]),
     "b2_shuffle_p2p_ws_bytes": (_sz, [_i64, _int]),
     "b2_shuffle_p2p_count_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "b2_shuffle_p2p_scatter_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),

@@ -186,8 +186,9 @@ int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_
     const int nslots = nchunks > 1 ? 3 : 1;
     uint32_t* d_slots = nullptr;
     uint64_t* d_part = nullptr;
-    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_slots, (size_t)slot_rows * 4 * nslots));
-    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_part, nchunks * 8));
+    // grow-only buffers owned by the ctx: no cudaMalloc / cudaFree per call
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 0, (size_t)slot_rows * 4 * nslots, (void**)&d_slots));
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 3, nchunks * 8, (void**)&d_part));
     std::vector<cudaEvent_t> up_done(nchunks), k_begin(nchunks), k_end(nchunks);
     cudaEvent_t c_begin, c_end;
     B2_RETURN_NOT_OK(sc.event(ctx, &c_begin, true));
@@ -552,12 +553,15 @@ int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64
     const size_t nchunks = chunks.size() - 1;
     uint32_t *d_v = nullptr, *d_i = nullptr, *d_o = nullptr;
     int64_t *d_voff = nullptr, *d_ioff = nullptr;
-    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_v, (size_t)V.rows() * 4));
-    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_i, (size_t)I.rows() * 4));
-    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_o, (size_t)I.rows() * 4));
+    // grow-only buffers owned by the ctx: no cudaMalloc / cudaFree per call
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 4, (size_t)V.rows() * 4, (void**)&d_v));
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 5, (size_t)I.rows() * 4, (void**)&d_i));
+    B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 6, (size_t)I.rows() * 4, (void**)&d_o));
     if (!uniform) {
-      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_voff, (size_t)(nbatches + 1) * 8));
-      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_ioff, (size_t)(nbatches + 1) * 8));
+      char* offs = nullptr;
+      B2_RETURN_NOT_OK(b2_ctx_cached(ctx, 7, (size_t)(nbatches + 1) * 16, (void**)&offs));
+      d_voff = reinterpret_cast<int64_t*>(offs);
+      d_ioff = d_voff + (nbatches + 1);
       B2_CUDA_OK(ctx, cudaMemcpyAsync(d_voff, V.off.data(), (size_t)(nbatches + 1) * 8,
                                       cudaMemcpyHostToDevice, ctx->s_compute));
       B2_CUDA_OK(ctx, cudaMemcpyAsync(d_ioff, I.off.data(), (size_t)(nbatches + 1) * 8,

@@ -36,9 +36,9 @@ struct b2_ctx {
   b2_pending* pending = nullptr;
   // grow-only device buffers of the streaming host entry points (a cudaMalloc + cudaFree of a few
   // GiB per call costs more than the kernels they feed)
-  static constexpr int kCacheSlots = 4;
-  void* cache_ptr[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr};
-  size_t cache_bytes[kCacheSlots] = {0, 0, 0, 0};
+  static constexpr int kCacheSlots = 8;
+  void* cache_ptr[kCacheSlots] = {};
+  size_t cache_bytes[kCacheSlots] = {};
 };
 // Returns a device buffer of at least `bytes` that stays owned by the ctx (slot 0..kCacheSlots-1).
 int b2_ctx_cached(b2_ctx* ctx, int slot, size_t bytes, void** out);

@@ -103,6 +103,38 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   return B2_OK;
 }
 
+int b2_host_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return B2_ERR_INVALID;
+  *out = nullptr;
+  if (bytes == 0) bytes = 64;
+  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  return e == cudaSuccess ? B2_OK : (e == cudaErrorMemoryAllocation ? B2_ERR_OOM : B2_ERR_CUDA);
+}
+int b2_host_free_pinned(void* p) {
+  if (!p) return B2_OK;
+  return cudaFreeHost(p) == cudaSuccess ? B2_OK : B2_ERR_CUDA;
+}
+int b2_host_register(const void* p, size_t bytes) {
+  if (!p || bytes == 0) return B2_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+  if (e == cudaSuccess) return B2_OK;
+  cudaGetLastError();  // clear the sticky-less error state
+  // read-only registration needs driver support; fall back to a plain registration
+  const cudaError_t e2 = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
+  if (e2 == cudaSuccess || e2 == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return B2_OK;
+  }
+  cudaGetLastError();
+  return B2_ERR_CUDA;
+}
+int b2_host_unregister(const void* p) {
+  if (!p) return B2_OK;
+  const cudaError_t e = cudaHostUnregister(const_cast<void*>(p));
+  cudaGetLastError();
+  return (e == cudaSuccess || e == cudaErrorHostMemoryNotRegistered) ? B2_OK : B2_ERR_CUDA;
+}
+
 const char* b2_last_error(const b2_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 int64_t b2_launch_count(const b2_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int b2_ctx_device(const b2_ctx* ctx) { return ctx ? ctx->device : -1; }

@@ -172,17 +172,15 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 // 8-byte table read (destination of the bucket's run minus its position in the tile) per row
 // instead of hashing the key again. The first version of this kernel spent 105-111
 // lane-instructions per row (profiles/r1_join.md).
-template <bool kAoS, int kT>
-__global__ void __launch_bounds__(kT, 1024 / kT)
+template <bool kAoS, int kT, int kI, int kCtas>
+__global__ void __launch_bounds__(kT, kCtas)
 part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                     const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
                     PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
                     int64_t out_cap, const uint64_t* __restrict__ bucket_addr,
                     unsigned int* __restrict__ overflow) {
-  // kT threads handle tiles of kT * 16 rows: 512 threads / 8192 rows (two CTAs per SM) for local
-  // destinations; 1024 threads / 16384 rows (one CTA per SM) for peer destinations, where a
-  // bucket's run per tile is twice as long (128 B at 1024 buckets) and NVLink packets fill up.
-  constexpr int kTileRows = kT * kItems;
+  // kT threads handle tiles of kT * kI rows, kCtas CTAs per SM (shape chosen by the launcher).
+  constexpr int kTileRows = kT * kI;
   constexpr int kW = kT / 32;
   constexpr int kBpt = (1 << kPartMaxBits) / kT;  // buckets per thread in the tile scan
   extern __shared__ __align__(16) unsigned char smem[];
@@ -215,19 +213,19 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 
   for (int64_t t0 = u.row0; t0 < u.row1; t0 += kTileRows) {
     // ---- load, hash once, rank inside the bucket ----
-    uint32_t key[kItems], val[kItems], packed[kItems];  // packed = bucket | rank << 16
+    uint32_t key[kI], val[kI], packed[kI];  // packed = bucket | rank << 16
     if (t0 + kTileRows <= u.row1) {  // full tile: no bounds checks
 #pragma unroll
-      for (int it = 0; it < kItems; ++it) load_row<kAoS>(in, t0 + it * kT + tid, key[it], val[it]);
+      for (int it = 0; it < kI; ++it) load_row<kAoS>(in, t0 + it * kT + tid, key[it], val[it]);
 #pragma unroll
-      for (int it = 0; it < kItems; ++it) {
+      for (int it = 0; it < kI; ++it) {
         const uint32_t b = bucket_or_skip(key[it], g);
         packed[it] = b;
         if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192
       }
     } else {
 #pragma unroll
-      for (int it = 0; it < kItems; ++it) {
+      for (int it = 0; it < kI; ++it) {
         const int64_t row = t0 + it * kT + tid;
         key[it] = 0;
         val[it] = 0;
@@ -285,7 +283,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 
     // ---- stage the tile sorted by bucket, bucket id beside the row ----
 #pragma unroll
-    for (int it = 0; it < kItems; ++it) {
+    for (int it = 0; it < kI; ++it) {
       if (packed[it] != 0xffffffffu) {
         const uint32_t b = packed[it] & 0xffffu;
         const uint32_t pos = tile_start[b] + (packed[it] >> 16);
@@ -502,9 +500,9 @@ __global__ void part_offsets_kernel(const uint64_t* __restrict__ scanned,
   part_off[i] = (int64_t)scanned[unit_first[s] * P + p * ustride];
 }
 
-size_t scatter_smem_bytes(int bits, int threads) {
+size_t scatter_smem_bytes(int bits, int tile_rows) {
   const size_t P = (size_t)1 << bits;
-  const size_t tile = (size_t)threads * kItems;
+  const size_t tile = (size_t)tile_rows;
   return sizeof(uint2) * tile + P * 8 + P * 8 + P * 4 + P * 4 + sizeof(uint16_t) * tile;
 }
 
@@ -534,6 +532,25 @@ PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
   L.off_scanws = o;     o += b2_align_up(b2_scan_ws_bytes(L.n_entries), 256);
   L.total = o;
   return L;
+}
+
+int g_scatter_variant = 0;  // tuning hook (b200olap_tune_scatter_variant)
+
+template <bool kAoS, int kT, int kI, int kCtas>
+int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const PartInput& in,
+                   const int64_t* d_seg_off, const int64_t* unit_first, int64_t nseg, int64_t unit_rows,
+                   const PartGeom& g, const uint64_t* scanned, uint2* d_out, int64_t out_cap,
+                   unsigned int* d_overflow) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT, kI, kCtas>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)scatter_smem_bytes(kPartMaxBits, kT * kI)));
+    attr_done = true;
+  }
+  part_scatter_kernel<kAoS, kT, kI, kCtas><<<(unsigned)units, kT, scatter_smem_bytes(bits, kT * kI), s>>>(
+      in, d_seg_off, unit_first, nseg, unit_rows, g, scanned, d_out, out_cap, nullptr, d_overflow);
+  return B2_OK;
 }
 
 // Phase 1 of a pass: unit table, histogram, flat scan, partition boundaries. Leaves the scanned
@@ -593,17 +610,12 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
           in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr);
     } else {
-      static bool attr_done_h[2] = {false, false};
-      if (!attr_done_h[kAoS]) {
-        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kThreads>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)scatter_smem_bytes(kPartMaxBits, kThreads)));
-        attr_done_h[kAoS] = true;
+      switch (g_scatter_variant) {
+        case 1: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 8, 3>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
+        case 2: B2_RETURN_NOT_OK((launch_scatter<kAoS, 256, 16, 4>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
+        case 3: B2_RETURN_NOT_OK((launch_scatter<kAoS, 1024, 8, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
+        default: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
       }
-      part_scatter_kernel<kAoS, kThreads><<<(unsigned)L.max_units, kThreads,
-                                            scatter_smem_bytes(g.bits, kThreads), s>>>(
-          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_bucket_addr,
-          d_overflow);
     }
     B2_LAUNCH_CHECK(ctx, "part_scatter_kernel");
   }
@@ -707,4 +719,10 @@ int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, in
   // n is only used to size the work units (an upper bound on the rows that survived pass 1)
   return part_pass(ctx, in2, n, off1, (int64_t)1 << F.bits1, g2, d_out, cap, d_off,
                    d_overflow, base + F.off_pass, F.pass_bytes, s);
+}
+
+extern "C" int b200olap_tune_scatter_variant(int v) {
+  if (v < 0 || v > 3) return B2_ERR_INVALID;
+  g_scatter_variant = v;
+  return B2_OK;
 }

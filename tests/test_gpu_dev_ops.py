@@ -530,3 +530,39 @@ def test_segmented_join_large_needs_fine_pass(ctx):
     assert m == exp[0].size
     for a, b in zip(got, exp):
         assert np.array_equal(a, b)
+
+
+def test_filter_unaligned_column_takes_the_non_tma_path(ctx):
+    """A column that starts 4, 8 or 12 bytes off a 16-byte boundary cannot be fetched with TMA bulk
+    copies; the kernel then loads those tiles with ordinary loads. Same result either way."""
+    rng = np.random.default_rng(17)
+    base = rng.integers(0, 2**32, size=3 * 65536 + 8, dtype=np.uint32)
+    d = dev(base)
+    for shift in (1, 2, 3):
+        col = d[shift: shift + 3 * 65536]
+        assert col.data_ptr() % 16 == 4 * shift
+        out, end, total = ctx.filter_dev(col, 3, 65536, 1 << 30)
+        torch.cuda.synchronize()
+        exp = [oracle.filter_lt(base[shift + b * 65536: shift + (b + 1) * 65536]) for b in range(3)]
+        n = int(total.cpu()[0])
+        assert n == sum(e.size for e in exp)
+        assert np.array_equal(host(out)[:n], np.concatenate(exp))
+        assert end.cpu().numpy().tolist() == np.cumsum([e.size for e in exp]).tolist()
+
+
+def test_pinned_host_memory_entry_points(ctx):
+    import ctypes as C
+    lib = ctx._lib
+    p = C.c_void_p()
+    assert lib.b2_host_alloc_pinned(1 << 20, C.byref(p)) == 0 and p.value
+    a = np.ctypeslib.as_array((C.c_uint32 * (1 << 18)).from_address(p.value))
+    a[:] = np.arange(1 << 18, dtype=np.uint32)
+    t = torch.from_numpy(a)
+    assert int(t.cuda().to(torch.int64).sum()) == int(a.astype(np.int64).sum())
+    del t, a
+    assert lib.b2_host_free_pinned(p) == 0
+    b = np.arange(1 << 18, dtype=np.uint32)
+    assert lib.b2_host_register(b.ctypes.data, b.nbytes) == 0
+    assert int(torch.from_numpy(b).cuda().to(torch.int64).sum()) == int(b.astype(np.int64).sum())
+    assert lib.b2_host_unregister(b.ctypes.data) == 0
+    assert lib.b2_host_unregister(b.ctypes.data) == 0  # idempotent
