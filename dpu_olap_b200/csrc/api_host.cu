@@ -65,11 +65,6 @@ struct Scratch {
     events.push_back(*e);
     return B2_OK;
   }
-  void* release(void* p) {  // hand ownership to someone else
-    for (auto& q : dev)
-      if (q == p) q = nullptr;
-    return p;
-  }
 };
 
 struct Layout {

@@ -389,16 +389,6 @@ part_gather_kernel(const uint2* __restrict__ pairs, int64_t n, const uint32_t* _
   }
 }
 
-__global__ void __launch_bounds__(256)
-split_pairs_kernel(const uint2* __restrict__ pairs, int64_t n, uint32_t* __restrict__ keys,
-                   uint32_t* __restrict__ vals) {
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const uint2 kv = pairs[i];
-    keys[i] = kv.x;
-    vals[i] = kv.y;
-  }
-}
-
 // ---- join of pre-partitioned sides (the fused multi-GPU shuffle delivers them) -------------------
 // Both sides arrive grouped into 2^seg_bits coarse buckets on hash bits [skip, skip + seg_bits),
 // bucket boundaries in d_*_seg_off. Only the fine pass is left (or nothing at all when the coarse

@@ -35,8 +35,6 @@
 namespace {
 
 constexpr int kThreads = kPartThreads;
-constexpr int kWarps = kThreads / 32;
-constexpr int kItems = kPartTile / kThreads;  // 16 rows per thread per tile
 
 template <bool kAoS>
 __device__ __forceinline__ void load_row(const PartInput& in, int64_t row, uint32_t& k, uint32_t& v) {

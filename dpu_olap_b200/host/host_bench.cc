@@ -202,6 +202,25 @@ int main(int argc, char** argv) {
                                }));
   }
 
+  // ---- partition: SF batches of 2 Mi rows into 32 partitions (partition_benchmark.cc:66 is
+  //      DISABLED_ in the reference: its DPU partition operator is broken, README.md:114-118) ----
+  if (want("BM_PartitionGpu") && sys) {
+    RandomArrayGenerator rng(42);
+    const int nb = sf, bs = 2 << 20;
+    auto batches = AddColumn("pk", MakeRandomRecordBatches(rng, vschema("x"), nb, bs), MakeIndexColumn(nb, bs).ValueOrDie());
+    gpu::PinnedBatches pinned(batches);
+    const double items = 2.0 * nb * bs;
+    results.push_back(TimeIt("PartitionFixture/BM_PartitionGpu/Batches:" + std::to_string(nb) + "/BatchSize:" +
+                                 std::to_string(bs) + "/Partitions:32",
+                             iters, items, items * 4, [&](Result& r) -> arrow::Status {
+                               partition::PartitionGpu p{*sys, batches[0]->schema(), batches, 32, "pk"};
+                               ARROW_RETURN_NOT_OK(p.Prepare());
+                               ARROW_RETURN_NOT_OK(p.Run().status());
+                               AddTimers(r, p.Timers());
+                               return arrow::Status::OK();
+                             }));
+  }
+
   // ---- gbench-shaped JSON ----
   std::printf("{\n  \"context\": {\"SF\": \"%d\", \"NR_GPUS\": \"%d\", \"host_threads\": \"%d\", \"arrow\": \"%s\"},\n",
               sf, sys ? 1 : 0, threads, ARROW_VERSION_STRING);

@@ -51,7 +51,8 @@ def test_cpp_bench_gpu_cases(host_bins):
     assert r.returncode == 0, r.stderr
     d = json.loads(r.stdout)
     names = {b["name"].split("/")[1] for b in d["benchmarks"]}
-    assert {"BM_FilterGpu", "BM_SumGpu", "BM_TakeGpu", "BM_JoinGpu", "BM_FilterNative", "BM_JoinNative"} <= names
+    assert {"BM_FilterGpu", "BM_SumGpu", "BM_TakeGpu", "BM_JoinGpu", "BM_PartitionGpu", "BM_FilterNative",
+            "BM_JoinNative"} <= names
     assert not any(b["error_occurred"] for b in d["benchmarks"])
     gpu = [b for b in d["benchmarks"] if b["name"].split("/")[1].endswith("Gpu")]
     assert all("dpu-work" in b and "copy-to-dpu" in b for b in gpu)
