@@ -77,12 +77,15 @@ static void AddTimers(Result& r, const std::shared_ptr<timer::Timers>& t) {
 }
 
 int main(int argc, char** argv) {
-  std::string filter;
+  std::string filter, out_path;
   int iters = 3;
-  for (int i = 1; i < argc; ++i) {
+  for (int i = 1; i < argc; ++i) {  // the Google Benchmark flags the reference's runners pass
     if (!std::strncmp(argv[i], "--benchmark_filter=", 19)) filter = argv[i] + 19;
+    if (!std::strncmp(argv[i], "--benchmark_out=", 16)) out_path = argv[i] + 16;
+    if (!std::strncmp(argv[i], "--benchmark_repetitions=", 24)) iters = std::atoi(argv[i] + 24);
     if (!std::strncmp(argv[i], "--iterations=", 13)) iters = std::atoi(argv[i] + 13);
   }
+  if (iters < 1) iters = 1;
   const int sf = EnvInt("SF", 1);
   const int threads = EnvInt("MAX_THREADS", static_cast<int>(std::thread::hardware_concurrency()));
   if (!InitNative(threads).ok()) return 2;
@@ -221,7 +224,8 @@ int main(int argc, char** argv) {
                              }));
   }
 
-  // ---- gbench-shaped JSON ----
+  // ---- gbench-shaped JSON (stdout, or --benchmark_out=FILE as scripts/run-*.sh use it) ----
+  if (!out_path.empty() && !std::freopen(out_path.c_str(), "w", stdout)) return 4;
   std::printf("{\n  \"context\": {\"SF\": \"%d\", \"NR_GPUS\": \"%d\", \"host_threads\": \"%d\", \"arrow\": \"%s\"},\n",
               sf, sys ? 1 : 0, threads, ARROW_VERSION_STRING);
   std::printf("  \"benchmarks\": [\n");

@@ -56,3 +56,26 @@ def test_cpp_bench_gpu_cases(host_bins):
     assert not any(b["error_occurred"] for b in d["benchmarks"])
     gpu = [b for b in d["benchmarks"] if b["name"].split("/")[1].endswith("Gpu")]
     assert all("dpu-work" in b and "copy-to-dpu" in b for b in gpu)
+
+
+def test_reference_parse_results_reads_our_benchmark_json(host_bins, tmp_path):
+    """The UNMODIFIED reference script scripts/parse_results.py turns the driver's JSON into the
+    CSV its plots are made from (operator column from name part [1], one column per Arg)."""
+    import csv
+    import sys
+    from pathlib import Path
+    script = Path("/root/reference/scripts/parse_results.py")
+    if not script.exists():
+        pytest.skip("the reference tree is not available here")
+    env = dict(os.environ, SF="1", MAX_THREADS="2")
+    out = tmp_path / "filter_native_1.json"
+    r = subprocess.run([str(host_bins["host_bench"]), "--benchmark_filter=BM_FilterNative",
+                        f"--benchmark_out={out}", "--benchmark_out_format=json", "--benchmark_repetitions=1"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and out.exists(), r.stderr
+    r = subprocess.run([sys.executable, str(script), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = list(csv.DictReader(open(tmp_path / "filter_native_1.csv")))
+    assert len(rows) == 1 and rows[0]["operator"] == "BM_FilterNative"
+    assert rows[0]["Batches"] == "128" and rows[0]["BatchSize"] == "65536" and rows[0]["Threads"] == "2"
+    assert float(rows[0]["items_per_second"]) > 0
