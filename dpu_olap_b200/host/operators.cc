@@ -33,10 +33,12 @@ struct ColumnPtrs {
   }
 };
 
-arrow::Result<std::shared_ptr<arrow::Array>> AllocU32(int64_t rows, uint32_t** data) {
-  ARROW_ASSIGN_OR_RAISE(auto buf, arrow::AllocateBuffer(rows * 4));
-  *data = reinterpret_cast<uint32_t*>(buf->mutable_data());
-  return std::make_shared<arrow::UInt32Array>(rows, std::shared_ptr<arrow::Buffer>(std::move(buf)));
+// Result array over page-locked memory from the GpuSet's recycling pool (a DMA target; pageable
+// Arrow buffers would be filled through the driver's staging copies and page faults).
+arrow::Result<std::shared_ptr<arrow::Array>> PinnedU32(gpu::GpuSet& sys, int64_t rows, uint32_t** data) {
+  ARROW_ASSIGN_OR_RAISE(auto buf, sys.pinned().Acquire(std::max<int64_t>(rows, 1) * 4));
+  *data = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(buf->data()));
+  return std::make_shared<arrow::UInt32Array>(rows, arrow::SliceBuffer(buf, 0, rows * 4));
 }
 
 }  // namespace
@@ -130,9 +132,15 @@ arrow::Result<std::shared_ptr<arrow::Table>> TakeGpu::Run() {
   std::vector<uint32_t*> outs(nb);
   arrow::RecordBatchVector result;
   auto schema = batches_[0]->schema();
-  for (int64_t b = 0; b < nb; ++b) {
-    ARROW_ASSIGN_OR_RAISE(auto arr, AllocU32(i.lens[b], &outs[b]));
+  int64_t total = 0;
+  for (int64_t l : i.lens) total += l;
+  ARROW_ASSIGN_OR_RAISE(auto slab, system_.pinned().Acquire(std::max<int64_t>(total, 1) * 4));
+  int64_t off = 0;
+  for (int64_t b = 0; b < nb; ++b) {  // one result batch per input batch: zero-copy slices of the slab
+    outs[b] = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(slab->data())) + off;
+    auto arr = std::make_shared<arrow::UInt32Array>(i.lens[b], arrow::SliceBuffer(slab, off * 4, i.lens[b] * 4));
     result.push_back(arrow::RecordBatch::Make(schema, i.lens[b], {std::move(arr)}));
+    off += i.lens[b];
   }
   b2_timings t{};
   B2_ARROW_RETURN_NOT_OK(ctx, b2_take_u32_host(ctx, v.ptrs.data(), v.lens.data(), i.ptrs.data(),
@@ -171,9 +179,9 @@ arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
                             r.ptrs.data(), r.lens.data(), static_cast<int64_t>(right_batches_.size()),
                             &rows, &t1));
   uint32_t *o_fk, *o_y, *o_x;
-  ARROW_ASSIGN_OR_RAISE(auto a_fk, AllocU32(static_cast<int64_t>(rows), &o_fk));
-  ARROW_ASSIGN_OR_RAISE(auto a_y, AllocU32(static_cast<int64_t>(rows), &o_y));
-  ARROW_ASSIGN_OR_RAISE(auto a_x, AllocU32(static_cast<int64_t>(rows), &o_x));
+  ARROW_ASSIGN_OR_RAISE(auto a_fk, PinnedU32(system_, static_cast<int64_t>(rows), &o_fk));
+  ARROW_ASSIGN_OR_RAISE(auto a_y, PinnedU32(system_, static_cast<int64_t>(rows), &o_y));
+  ARROW_ASSIGN_OR_RAISE(auto a_x, PinnedU32(system_, static_cast<int64_t>(rows), &o_x));
   B2_ARROW_RETURN_NOT_OK(ctx, b2_join_fetch_host(ctx, o_fk, o_y, o_x, static_cast<int64_t>(rows), &t2));
   timers_->Add(t1);
   timers_->Add(t2);
@@ -213,7 +221,7 @@ arrow::Result<arrow::RecordBatchVector> PartitionGpu::Run() {
   for (int p = 0; p < nparts; ++p) {
     arrow::ArrayVector arrays;
     for (int c = 0; c < ncols; ++c) {
-      ARROW_ASSIGN_OR_RAISE(auto arr, AllocU32(part_rows[p], &outs[static_cast<size_t>(p) * ncols + c]));
+      ARROW_ASSIGN_OR_RAISE(auto arr, PinnedU32(system_, part_rows[p], &outs[static_cast<size_t>(p) * ncols + c]));
       arrays.push_back(std::move(arr));
     }
     result.push_back(arrow::RecordBatch::Make(schema_, part_rows[p], std::move(arrays)));
