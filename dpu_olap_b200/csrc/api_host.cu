@@ -18,7 +18,7 @@ int b2_ctx_reserve_ws(b2_ctx* ctx, size_t bytes);  // gen.cu
 
 void b2_pending_free(b2_ctx* ctx) {
   if (!ctx || !ctx->pending) return;
-  for (void* p : ctx->pending->dev) cudaFree(p);
+  for (void* p : ctx->pending->dev) b2_dev_free(ctx, p);
   delete ctx->pending;
   ctx->pending = nullptr;
 }
@@ -43,19 +43,20 @@ int ensure_streams(b2_ctx* ctx) {
 int dev_alloc(b2_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 256;
-  B2_CUDA_OK(ctx, cudaMalloc(p, bytes));
-  return B2_OK;
+  return b2_dev_alloc(ctx, p, bytes);
 }
 
 // RAII list of scratch device allocations and events of one call.
 struct Scratch {
+  b2_ctx* owner = nullptr;
   std::vector<void*> dev;
   std::vector<cudaEvent_t> events;
   ~Scratch() {
     for (cudaEvent_t e : events) cudaEventDestroy(e);
-    for (void* p : dev) cudaFree(p);
+    for (void* p : dev) b2_dev_free(owner, p);  // back to the ctx's recycling pool
   }
   int alloc(b2_ctx* ctx, void** p, size_t bytes) {
+    owner = ctx;
     B2_RETURN_NOT_OK(dev_alloc(ctx, p, bytes));
     dev.push_back(*p);
     return B2_OK;
@@ -105,9 +106,98 @@ std::vector<int64_t> make_chunks(const Layout& L, int64_t nbatches) {
   return c;
 }
 
-// Upload batches [b0,b1) to their packed positions, merging host-adjacent batches.
+// ---- gather upload: one kernel reads a group of page-locked host batches over PCIe ------------
+constexpr int64_t kGatherPiece = 16384;  // rows per CTA (64 KB)
+struct GatherEntry {
+  const uint32_t* src;  // host pointer, device-accessible (mapped pinned memory)
+  uint32_t* dst;
+  int64_t rows;
+};
+
+__global__ void __launch_bounds__(256)
+gather_host_batches_kernel(const GatherEntry* __restrict__ tbl) {
+  const GatherEntry e = tbl[blockIdx.x];  // the table itself lives in pinned host memory
+  const uint32_t tid = threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(e.src) | reinterpret_cast<uintptr_t>(e.dst)) & 15) == 0) {
+    const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(e.src);
+    uint4* __restrict__ d4 = reinterpret_cast<uint4*>(e.dst);
+    const int64_t n4 = e.rows >> 2;
+    for (int64_t base = 0; base < n4; base += 256 * 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = base + u * 256 + tid;
+        if (i < n4) v[u] = ld_stream_v4(s4 + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = base + u * 256 + tid;
+        if (i < n4) d4[i] = v[u];
+      }
+    }
+    for (int64_t i = (n4 << 2) + tid; i < e.rows; i += 256) e.dst[i] = ld_stream_u32(e.src + i);
+  } else {
+    for (int64_t i = tid; i < e.rows; i += 256) e.dst[i] = ld_stream_u32(e.src + i);
+  }
+}
+
+// Reserves room for `entries` more gather entries in the ctx's pinned table (call before the first
+// upload of a *_host call, when nothing is in flight). Returns false if the gather path is off.
+bool gather_begin(b2_ctx* ctx, int64_t nbatches, int64_t total_rows) {
+  ctx->gather_used = 0;
+  if (!ctx->inputs_pinned) return false;
+  const size_t need = (size_t)(nbatches + total_rows / kGatherPiece + 16) * sizeof(GatherEntry);
+  if (ctx->gather_bytes < need) {
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+    ctx->h_gather = nullptr;
+    ctx->gather_bytes = 0;
+    const size_t want = b2_align_up(need, 1 << 16);
+    if (cudaHostAlloc(&ctx->h_gather, want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    ctx->gather_bytes = want;
+  }
+  return true;
+}
+
+// Upload batches [b0,b1) to their packed positions, merging host-adjacent batches. With
+// b2_ctx_set_inputs_pinned the group goes up through ONE gather kernel (no per-batch DMA set-up).
 int upload(b2_ctx* ctx, uint32_t* d_col, const Layout& L, const uint32_t* const* ptrs, int64_t b0,
            int64_t b1, cudaStream_t s, int64_t* bytes) {
+  // count the copies the DMA path would need
+  int64_t ncopies = 0, rows_total = L.off[(size_t)b1] - L.off[(size_t)b0];
+  for (int64_t b = b0; b < b1;) {
+    int64_t e = b + 1;
+    while (e < b1 && ptrs[e] == ptrs[e - 1] + (L.off[(size_t)e] - L.off[(size_t)e - 1])) ++e;
+    if (L.off[(size_t)e] > L.off[(size_t)b]) ++ncopies;
+    b = e;
+  }
+  const size_t max_entries = (size_t)(ncopies + rows_total / kGatherPiece + 1);
+  if (ctx->inputs_pinned && ncopies >= 4 && ctx->h_gather &&
+      ctx->gather_used + max_entries * sizeof(GatherEntry) <= ctx->gather_bytes) {
+    GatherEntry* tbl = reinterpret_cast<GatherEntry*>(static_cast<char*>(ctx->h_gather) + ctx->gather_used);
+    int64_t n = 0;
+    for (int64_t b = b0; b < b1;) {
+      int64_t e = b + 1;
+      while (e < b1 && ptrs[e] == ptrs[e - 1] + (L.off[(size_t)e] - L.off[(size_t)e - 1])) ++e;
+      const int64_t rows = L.off[(size_t)e] - L.off[(size_t)b];
+      for (int64_t r = 0; r < rows; r += kGatherPiece) {
+        tbl[n].src = ptrs[b] + r;
+        tbl[n].dst = d_col + L.off[(size_t)b] + r;
+        tbl[n].rows = std::min(kGatherPiece, rows - r);
+        ++n;
+      }
+      b = e;
+    }
+    ctx->gather_used += (size_t)n * sizeof(GatherEntry);
+    if (n > 0) {
+      gather_host_batches_kernel<<<(unsigned)n, 256, 0, s>>>(tbl);  // mapped: host pointer == device pointer
+      B2_LAUNCH_CHECK(ctx, "gather_host_batches_kernel");
+      *bytes += rows_total * 4;
+    }
+    return B2_OK;
+  }
   int64_t b = b0;
   while (b < b1) {
     int64_t e = b + 1;
@@ -170,6 +260,7 @@ int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_
   B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
   const std::vector<int64_t> chunks = make_chunks(L, nbatches);
   const size_t nchunks = chunks.size() - 1;
+  gather_begin(ctx, nbatches, L.rows());
   *sum = 0;
   b2_timings tm{};
   if (nchunks > 0 && L.rows() > 0) {
@@ -241,6 +332,7 @@ int b2_filter_lt_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
   Layout L;
   B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
   const std::vector<int64_t> chunks = make_chunks(L, nbatches);
+  gather_begin(ctx, nbatches, L.rows());
   const size_t nchunks = chunks.size() - 1;
   b2_timings tm{};
   b2_pending* pend = new b2_pending();
@@ -381,6 +473,7 @@ int b2_filter_lt_u32_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
   Layout L;
   B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
   const std::vector<int64_t> chunks = make_chunks(L, nbatches);
+  gather_begin(ctx, nbatches, L.rows());
   const size_t nchunks = chunks.size() - 1;
   b2_timings tm{};
   if (total) *total = 0;
@@ -545,6 +638,7 @@ int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64
     const bool uniform = V.uniform && I.uniform;
     // chunk on the values layout (the larger side); indices follow the same batch ranges
     const std::vector<int64_t> chunks = make_chunks(V, nbatches);
+    gather_begin(ctx, 2 * nbatches, V.rows() + I.rows());
     const size_t nchunks = chunks.size() - 1;
     uint32_t *d_v = nullptr, *d_i = nullptr, *d_o = nullptr;
     int64_t *d_voff = nullptr, *d_ioff = nullptr;

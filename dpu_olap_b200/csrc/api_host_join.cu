@@ -23,15 +23,16 @@ int ensure_streams(b2_ctx* ctx) {
   return B2_OK;
 }
 
-struct DevBufs {  // frees everything not released
+struct DevBufs {  // returns everything not released to the ctx's recycling pool
+  b2_ctx* owner = nullptr;
   std::vector<void*> bufs;
   ~DevBufs() {
     for (void* p : bufs)
-      if (p) cudaFree(p);
+      if (p) b2_dev_free(owner, p);
   }
   int alloc(b2_ctx* ctx, void** p, size_t bytes) {
-    *p = nullptr;
-    B2_CUDA_OK(ctx, cudaMalloc(p, bytes ? bytes : 256));
+    owner = ctx;
+    B2_RETURN_NOT_OK(b2_dev_alloc(ctx, p, bytes ? bytes : 256));
     bufs.push_back(*p);
     return B2_OK;
   }
@@ -252,7 +253,7 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
     if (attempt == 1) return b2_set_error(ctx, B2_ERR_OVERFLOW, "join", "output larger than reported");
     for (uint32_t* p : {o_fk, o_y, o_x}) {
       bufs.release(p);
-      cudaFree(p);
+      b2_dev_free(ctx, p);
     }
     cap = (int64_t)rows;
   }

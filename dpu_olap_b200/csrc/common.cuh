@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/b200olap.h"
 
@@ -33,13 +35,25 @@ struct b2_ctx {
   cudaStream_t s_copy_out = nullptr;
   void* h_pinned = nullptr;  // pinned staging ring
   size_t pinned_bytes = 0;
+  // b2_ctx_set_inputs_pinned: host inputs are page-locked and device-accessible, so a group of
+  // batches is uploaded by ONE gather kernel reading host memory instead of one DMA per batch
+  bool inputs_pinned = false;
+  void* h_gather = nullptr;   // pinned table of gather entries, bump-allocated per *_host call
+  size_t gather_bytes = 0, gather_used = 0;
   b2_pending* pending = nullptr;
   // grow-only device buffers of the streaming host entry points (a cudaMalloc + cudaFree of a few
   // GiB per call costs more than the kernels they feed)
   static constexpr int kCacheSlots = 8;
   void* cache_ptr[kCacheSlots] = {};
   size_t cache_bytes[kCacheSlots] = {};
+  std::vector<std::pair<void*, size_t>> pool_free;   // idle blocks of the recycling allocator
+  std::vector<std::pair<void*, size_t>> pool_live;   // blocks handed out
 };
+// Recycling device allocator of the *_host entry points: b2_dev_free keeps the block for the next
+// b2_dev_alloc of a similar size (cudaMalloc / cudaFree of GiB-sized buffers per call cost
+// milliseconds and occasionally much more); everything is released in b2_ctx_destroy.
+int b2_dev_alloc(b2_ctx* ctx, void** out, size_t bytes);
+void b2_dev_free(b2_ctx* ctx, void* p);
 // Returns a device buffer of at least `bytes` that stays owned by the ctx (slot 0..kCacheSlots-1).
 int b2_ctx_cached(b2_ctx* ctx, int slot, size_t bytes, void** out);
 

@@ -13,6 +13,50 @@ int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail) 
   return status;
 }
 
+int b2_dev_alloc(b2_ctx* ctx, void** out, size_t bytes) {
+  *out = nullptr;
+  if (bytes == 0) bytes = 256;
+  // best fit among the idle blocks, but never one more than twice the request
+  int best = -1;
+  for (size_t i = 0; i < ctx->pool_free.size(); ++i) {
+    const size_t cap = ctx->pool_free[i].second;
+    if (cap >= bytes && cap <= 2 * bytes + (1 << 20) && (best < 0 || cap < ctx->pool_free[(size_t)best].second))
+      best = (int)i;
+  }
+  if (best >= 0) {
+    *out = ctx->pool_free[(size_t)best].first;
+    ctx->pool_live.push_back(ctx->pool_free[(size_t)best]);
+    ctx->pool_free.erase(ctx->pool_free.begin() + best);
+    return B2_OK;
+  }
+  const size_t want = b2_align_up(bytes, (size_t)1 << 20);
+  cudaError_t e = cudaMalloc(out, want);
+  if (e != cudaSuccess && !ctx->pool_free.empty()) {  // give the idle blocks back and retry
+    cudaGetLastError();
+    for (auto& blk : ctx->pool_free) cudaFree(blk.first);
+    ctx->pool_free.clear();
+    e = cudaMalloc(out, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return b2_set_error(ctx, e == cudaErrorMemoryAllocation ? B2_ERR_OOM : B2_ERR_CUDA, "cudaMalloc",
+                        cudaGetErrorString(e));
+  }
+  ctx->pool_live.emplace_back(*out, want);
+  return B2_OK;
+}
+
+void b2_dev_free(b2_ctx* ctx, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < ctx->pool_live.size(); ++i)
+    if (ctx->pool_live[i].first == p) {
+      ctx->pool_free.push_back(ctx->pool_live[i]);
+      ctx->pool_live.erase(ctx->pool_live.begin() + (long)i);
+      return;
+    }
+  cudaFree(p);  // not from the pool
+}
+
 int b2_ctx_cached(b2_ctx* ctx, int slot, size_t bytes, void** out) {
   *out = nullptr;
   if (slot < 0 || slot >= b2_ctx::kCacheSlots) return b2_set_error(ctx, B2_ERR_INVALID, "cache slot", nullptr);
@@ -95,11 +139,20 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   if (ctx->s_copy_in) cudaStreamDestroy(ctx->s_copy_in);
   if (ctx->s_copy_out) cudaStreamDestroy(ctx->s_copy_out);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
   if (ctx->d_ws) cudaFree(ctx->d_ws);
   for (void* p : ctx->cache_ptr)
     if (p) cudaFree(p);
+  for (auto& blk : ctx->pool_free) cudaFree(blk.first);
+  for (auto& blk : ctx->pool_live) cudaFree(blk.first);
   if (ctx->d_small) cudaFree(ctx->d_small);
   delete ctx;
+  return B2_OK;
+}
+
+int b2_ctx_set_inputs_pinned(b2_ctx* ctx, int on) {
+  if (!ctx) return B2_ERR_INVALID;
+  ctx->inputs_pinned = on != 0;
   return B2_OK;
 }
 
@@ -107,7 +160,7 @@ int b2_host_alloc_pinned(size_t bytes, void** out) {
   if (!out) return B2_ERR_INVALID;
   *out = nullptr;
   if (bytes == 0) bytes = 64;
-  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
   return e == cudaSuccess ? B2_OK : (e == cudaErrorMemoryAllocation ? B2_ERR_OOM : B2_ERR_CUDA);
 }
 int b2_host_free_pinned(void* p) {
@@ -116,11 +169,11 @@ int b2_host_free_pinned(void* p) {
 }
 int b2_host_register(const void* p, size_t bytes) {
   if (!p || bytes == 0) return B2_ERR_INVALID;
-  const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+  const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable | cudaHostRegisterMapped | cudaHostRegisterReadOnly);
   if (e == cudaSuccess) return B2_OK;
   cudaGetLastError();  // clear the sticky-less error state
   // read-only registration needs driver support; fall back to a plain registration
-  const cudaError_t e2 = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
+  const cudaError_t e2 = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
   if (e2 == cudaSuccess || e2 == cudaErrorHostMemoryAlreadyRegistered) {
     cudaGetLastError();
     return B2_OK;

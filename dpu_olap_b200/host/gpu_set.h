@@ -112,6 +112,9 @@ class GpuSet {
   GpuSet& operator=(const GpuSet&) = delete;
   b2_ctx* ctx() const { return ctx_; }
   PinnedPool& pinned() { return *pinned_; }
+  // All record batches given to operators on this GpuSet are page-locked (gpu::PinnedBatches): groups
+  // of batches are then uploaded by one gather kernel instead of one DMA per batch.
+  void PromiseInputsPinned(bool on) { b2_ctx_set_inputs_pinned(ctx_, on ? 1 : 0); }
 
  private:
   explicit GpuSet(b2_ctx* ctx) : ctx_(ctx), pinned_(std::make_shared<PinnedPool>()) {}

@@ -91,6 +91,7 @@ int main(int argc, char** argv) {
   if (!InitNative(threads).ok()) return 2;
   auto sys_r = gpu::GpuSet::allocate(EnvInt("GPU", 0));
   gpu::GpuSet* sys = sys_r.ok() ? sys_r->get() : nullptr;
+  if (sys) sys->PromiseInputsPinned(true);  // every fixture below pins its batches (gpu::PinnedBatches)
   auto want = [&](const char* n) { return filter.empty() || std::strstr(n, filter.c_str()) != nullptr; };
   std::vector<Result> results;
   auto vschema = [](const char* n) { return arrow::schema({arrow::field(n, arrow::uint32(), false)}); };

@@ -84,6 +84,25 @@ static void FilterLongerTest(gpu::GpuSet& sys) {  // filter_test.cc:63-78, plus 
   }
 }
 
+static void FilterPinnedGatherTest(gpu::GpuSet& sys) {  // same inputs, page-locked: gather-kernel upload
+  RandomArrayGenerator rng(7);
+  auto schema = VSchema();
+  auto batches = MakeRandomRecordBatches(rng, schema, 300, 1 << 16);
+  filter::FilterGpu plain{sys, batches};
+  auto expect = plain.GetResult().ValueOrDie();
+  {
+    gpu::PinnedBatches pinned(batches);
+    EXPECT_EQ(pinned.regions(), 300u);
+    sys.PromiseInputsPinned(true);
+    filter::FilterGpu g{sys, batches};
+    EXPECT_TRUE(g.GetResult().ValueOrDie()->Equals(expect));
+    aggr::SumGpu s{sys, batches};
+    aggr::SumNative n{schema, batches};
+    EXPECT_EQ(s.Run().ValueOrDie(), n.Run().ValueOrDie());
+    sys.PromiseInputsPinned(false);
+  }
+}
+
 // ---- SumTest ----------------------------------------------------------------------------------------
 static void SumSimpleTest(gpu::GpuSet& sys) {  // aggr_test.cc:24-36
   auto rb = RecordBatchOf({"v"}, {ArrayOf({0, 2, 3, 8, 9})});
@@ -262,7 +281,8 @@ int main(int argc, char** argv) {
   struct Case { const char* name; std::function<void(gpu::GpuSet&)> fn; };
   std::vector<Case> cases = {
       {"FilterTest.SimpleTest", FilterSimpleTest}, {"FilterTest.ResultTest", FilterResultTest},
-      {"FilterTest.LongerTest", FilterLongerTest}, {"SumTest.SimpleTest", SumSimpleTest},
+      {"FilterTest.LongerTest", FilterLongerTest}, {"FilterTest.PinnedGather", FilterPinnedGatherTest},
+      {"SumTest.SimpleTest", SumSimpleTest},
       {"SumTest.LargeTest", SumLargeTest},         {"TakeTest.SimpleTest", TakeSimpleTest},
       {"TakeTest.LargeTest", TakeLargeTest},       {"JoinTest.SimpleTest", JoinSimpleTest},
       {"JoinTest.LargeTest", JoinLargeTest},       {"PartitionTest.SimpleTest", PartitionSimpleTest},

@@ -82,6 +82,12 @@ int b2_ctx_sm_count(const b2_ctx* ctx);
  * SetUp too); b2_host_alloc_pinned returns page-locked memory a caller can wrap in an
  * arrow::Buffer for results. Neither needs a ctx. The reference itself lists zero-copy transfers
  * as future work (host/dpuext/arrow_utils.h:28-29). */
+/* Promise that every host INPUT pointer later passed to this ctx's *_host calls is page-locked and
+ * device-accessible (b2_host_register, b2_host_alloc_pinned, cudaHostAlloc/cudaHostRegister with
+ * the mapped flag). A group of batches is then uploaded by ONE kernel that reads host memory over
+ * PCIe directly, instead of one DMA per record batch (at 256 KB per batch a DMA's set-up costs as
+ * much as its transfer). Breaking the promise faults the kernel; off by default. */
+int b2_ctx_set_inputs_pinned(b2_ctx* ctx, int on);
 int b2_host_alloc_pinned(size_t bytes, void** out);
 int b2_host_free_pinned(void* p);
 int b2_host_register(const void* p, size_t bytes);

@@ -210,3 +210,30 @@ def test_partition_large_test(ctx, ops):  # :59-92: 32 partitions within 10 % of
         assert abs(q["pk"].size - mean) < 0.1 * mean
         assert np.array_equal(oracle.partition_ids(q["pk"], 32), np.full(q["pk"].size, pid))
         assert np.array_equal(allx[q["pk"]], q["x"])  # columns stay aligned (pk is the row index)
+
+
+def test_filter_host_into_pinned_inputs_use_the_gather_upload(ctx):
+    """Separately allocated, page-locked batches: with b2_ctx_set_inputs_pinned one gather kernel per
+    group reads them over PCIe; the result is the same as with per-batch DMA copies."""
+    rng = np.random.default_rng(99)
+    batches = [rng.integers(0, 2**32, size=65536 if b % 7 else 12345, dtype=np.uint32) for b in range(200)]
+    exp = [oracle.filter_lt(b) for b in batches]
+    lib = ctx._lib
+    for b in batches:
+        assert lib.b2_host_register(b.ctypes.data, b.nbytes) == 0
+    try:
+        l0 = ctx.launches
+        rc, out, counts, total, t0 = _filter_into(ctx, batches)
+        plain_launches = ctx.launches - l0
+        assert rc == 0 and counts == [e.size for e in exp]
+        assert lib.b2_ctx_set_inputs_pinned(ctx._h, 1) == 0
+        l0 = ctx.launches
+        rc, out2, counts2, total2, t1 = _filter_into(ctx, batches)
+        assert rc == 0 and counts2 == counts and total2 == total
+        assert np.array_equal(out2[:total], np.concatenate(exp))
+        assert ctx.launches - l0 > plain_launches          # the gather kernels were launched
+        assert t1.h2d_bytes == t0.h2d_bytes
+    finally:
+        lib.b2_ctx_set_inputs_pinned(ctx._h, 0)
+        for b in batches:
+            lib.b2_host_unregister(b.ctypes.data)
