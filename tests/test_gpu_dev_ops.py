@@ -566,3 +566,84 @@ def test_pinned_host_memory_entry_points(ctx):
     assert int(torch.from_numpy(b).cuda().to(torch.int64).sum()) == int(b.astype(np.int64).sum())
     assert lib.b2_host_unregister(b.ctypes.data) == 0
     assert lib.b2_host_unregister(b.ctypes.data) == 0  # idempotent
+
+
+# ---- out-of-bounds canaries (compute-sanitizer is not available on the GPU pool) ---------------------
+GUARD = 4096  # elements of sentinel on both sides of every output
+
+
+def _guarded(n, dtype, fill):
+    t = torch.full((n + 2 * GUARD,), fill, dtype=dtype, device="cuda")
+    return t, t[GUARD: GUARD + n]
+
+
+def _guards_intact(t, n, fill):
+    return bool((t[:GUARD] == fill).all()) and bool((t[GUARD + n:] == fill).all())
+
+
+def test_kernels_never_write_outside_their_outputs(ctx):
+    """Every output buffer sits between sentinel guards; after each operator the guards must be
+    untouched (exact-size outputs, ragged / odd sizes, 100 % selectivity, partial tiles)."""
+    rng = np.random.default_rng(31)
+    S32, S64 = -559038737, -81985529216486896
+    # filter: 100 % selected, odd batch length, output capacity exactly n
+    nb, bl = 5, 8191 + 4096
+    col = dev(rng.integers(0, 2**32, size=nb * bl, dtype=np.uint32))
+    g_out, out = _guarded(nb * bl, torch.int32, S32)
+    g_end, end = _guarded(nb, torch.int64, S64)
+    g_tot, tot = _guarded(1, torch.int64, S64)
+    ws_n = ctx.filter_ws_bytes(nb, bl)
+    g_ws, ws = _guarded(ws_n, torch.uint8, 0x5A)
+    ctx.filter_dev(col, nb, bl, 0xFFFFFFFF, out=out, batch_end=end, total=tot, ws=ws)
+    torch.cuda.synchronize()
+    assert int(tot.cpu()[0]) == int((host(col) < 0xFFFFFFFF).sum())
+    assert _guards_intact(g_out, nb * bl, S32) and _guards_intact(g_end, nb, S64)
+    assert _guards_intact(g_tot, 1, S64) and _guards_intact(g_ws, ws_n, 0x5A)
+    # take: odd sizes
+    vals = dev(rng.integers(0, 2**32, size=3 * 1001, dtype=np.uint32))
+    idx = dev(rng.integers(0, 1001, size=3 * 77, dtype=np.uint32))
+    g_o, o = _guarded(3 * 77, torch.int32, S32)
+    ctx.take_dev(vals, 1001, idx, 77, 3, out=o)
+    torch.cuda.synchronize()
+    assert _guards_intact(g_o, 3 * 77, S32)
+    # join: exact output capacity, duplicates on the build side
+    n = 50_001
+    pk = rng.integers(0, 20_000, size=n, dtype=np.uint32)
+    fk = rng.integers(0, 25_000, size=n, dtype=np.uint32)
+    x, y = rng.integers(0, 2**32, size=n, dtype=np.uint32), rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    exp_rows = oracle.join(fk, y, pk, x)[0].size
+    guards = [_guarded(exp_rows, torch.int32, S32) for _ in range(3)]
+    g_r, r = _guarded(1, torch.int64, S64)
+    ctx.join_dev(dev(fk), dev(y), dev(pk), dev(x), out_capacity=exp_rows, outs=[g[1] for g in guards], out_rows=r)
+    torch.cuda.synchronize()
+    assert int(r.cpu()[0]) == exp_rows
+    assert all(_guards_intact(g[0], exp_rows, S32) for g in guards) and _guards_intact(g_r, 1, S64)
+    # same join with HALF the needed capacity: the true count is reported, nothing beyond capacity is written
+    cap = exp_rows // 2
+    guards = [_guarded(cap, torch.int32, S32) for _ in range(3)]
+    ctx.join_dev(dev(fk), dev(y), dev(pk), dev(x), out_capacity=cap, outs=[g[1] for g in guards], out_rows=r)
+    torch.cuda.synchronize()
+    assert int(r.cpu()[0]) == exp_rows and all(_guards_intact(g[0], cap, S32) for g in guards)
+    # fused shuffle scatter into an exactly sized receive buffer (line carry: partial first/last lines)
+    m = 123_457
+    k, v = dev(rng.integers(0, 2**32, size=m, dtype=np.uint32)), dev(np.arange(m, dtype=np.uint32))
+    sws = torch.empty(ctx.shuffle_p2p_ws_bytes(m, 10) + 256, dtype=torch.uint8, device="cuda")
+    off = ctx.shuffle_p2p_count_dev(k, 10, sws)
+    g_b, buf = _guarded(m, torch.int64, S64)
+    for shift in (0, 1):  # receive buffer 16-byte aligned and 8 bytes off
+        b2 = buf if shift == 0 else g_b[GUARD + 1: GUARD + 1 + m - 1]
+        cnt = m if shift == 0 else m - 1
+        if shift == 1:
+            k2, v2 = k[: m - 1].contiguous(), v[: m - 1].contiguous()
+            off = ctx.shuffle_p2p_count_dev(k2, 10, sws)
+        else:
+            k2, v2 = k, v
+        g_b.fill_(S64)
+        addr = (b2.data_ptr() + 8 * off[:-1]).contiguous()
+        ctx.shuffle_p2p_scatter_dev(k2, v2, 10, addr, sws)
+        torch.cuda.synchronize()
+        lo = GUARD + shift
+        assert bool((g_b[:lo] == S64).all()) and bool((g_b[lo + cnt:] == S64).all())
+        got = np.sort(b2.cpu().numpy().view(np.uint64))
+        expp = np.sort(host(k2).astype(np.uint64) | (host(v2).astype(np.uint64) << np.uint64(32)))
+        assert np.array_equal(got, expp)
