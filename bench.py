@@ -196,10 +196,19 @@ def shard(nbatches: int, D: Dist) -> tuple[int, int]:
 
 
 def free_all():
+    """Release this operator's columns before the next one allocates its own. Giving tens of GiB back
+    to the driver is not free: for a while afterwards (memory being scrubbed, power state of the
+    sustained run before) the next kernels ran ~20 % slower when they started immediately
+    (tools/sum_bench_probe.py: 7.2 TB/s cold vs 5.8 TB/s straight after the filter sweep). BENCH_SETTLE_S
+    (default 1 s) lets the device settle between OPERATORS; it is outside every timed region."""
     import gc
     import torch
     gc.collect()
+    torch.cuda.synchronize()
     torch.cuda.empty_cache()
+    settle = float(os.environ.get("BENCH_SETTLE_S", "1.0"))
+    if settle > 0:
+        time.sleep(settle)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -64,6 +64,7 @@ SIGNATURES = {
     "b2_filter_lt_u32_host": (_int, [_vp, _pp, _pi64, _i64, _u32, _pi64, _pu64, _pt]),
     "b2_filter_fetch_host": (_int, [_vp, _pp, _i64, _pt]),
     "b2_ctx_set_inputs_pinned": (_int, [_vp, _int]),
+    "b2_sum_lt_u32_dev": (_int, [_vp, _vp, _i64, _u32, _vp, _vp, _vp]),
     "b2_host_alloc_pinned": (_int, [_sz, C.POINTER(C.c_void_p)]),
     "b2_host_free_pinned": (_int, [_vp]),
     "b2_host_register": (_int, [_vp, _sz]),

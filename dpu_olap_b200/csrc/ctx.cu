@@ -121,7 +121,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   b2_ctx* ctx = new b2_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->small_bytes = 64 * 1024;
+  ctx->small_bytes = 128 * 1024;  // sum partials [4096] | filtered-sum counts [4096] | ticket
   if (cudaMalloc(&ctx->d_small, ctx->small_bytes) != cudaSuccess ||
       cudaMemset(ctx->d_small, 0, ctx->small_bytes) != cudaSuccess) {
     delete ctx;

@@ -188,6 +188,15 @@ class Context:
                  "b2_sum_u32_dev")
         return out
 
+    def sum_lt_dev(self, col, threshold: int):
+        """Fused filter(v < threshold) -> sum. Returns (sum, count) as uint64-in-int64 device tensors."""
+        import torch
+        out = torch.empty(1, dtype=torch.int64, device=col.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=col.device)
+        self._ck(self._lib.b2_sum_lt_u32_dev(self._h, _dptr(col), col.numel(), int(threshold), _dptr(out),
+                                             _dptr(cnt), self._stream()), "b2_sum_lt_u32_dev")
+        return out, cnt
+
     def filter_ws_bytes(self, nbatches: int, batch_len: int) -> int:
         return int(self._lib.b2_filter_ws_bytes(nbatches, batch_len))
 

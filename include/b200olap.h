@@ -109,6 +109,11 @@ int b2_iota_u32_dev(b2_ctx* ctx, uint64_t start, int64_t n, uint32_t* d_out, voi
 /* ---- Sum (replaces dpu/aggr/main.c:44-89 + dpu/shared/kernels/aggr.c:16-33) -------------- */
 /* *d_sum = sum of d_in[0..n) as uint64 (mod 2^64). One kernel launch. */
 int b2_sum_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint64_t* d_sum, void* stream);
+/* Fused pipeline filter(v < threshold) -> sum: *d_sum = sum of the rows below the threshold,
+ * *d_count (may be NULL) = how many there are. One read of the column, nothing materialised — the
+ * plan the reference keeps commented out in host/aggr/aggr_native.cc:59-65. */
+int b2_sum_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint32_t threshold, uint64_t* d_sum,
+                      uint64_t* d_count, void* stream);
 /* SumDpu::Run (host/aggr/aggr_dpu.cc:31-89): batches on the host, result on the host. */
 int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
                     int64_t nbatches, uint64_t* sum, b2_timings* timings);

@@ -647,3 +647,20 @@ def test_kernels_never_write_outside_their_outputs(ctx):
         got = np.sort(b2.cpu().numpy().view(np.uint64))
         expp = np.sort(host(k2).astype(np.uint64) | (host(v2).astype(np.uint64) << np.uint64(32)))
         assert np.array_equal(got, expp)
+
+
+@pytest.mark.parametrize("n,thr", [(0, 5), (1, 0), (7, 2**31), (4097, 1 << 30), (1_000_003, 42_949_673),
+                                   (8 * 1024 * 1024 + 3, 0xFFFFFFFF)])
+def test_fused_filter_sum(ctx, n, thr):
+    """filter(v < thr) -> sum in one pass equals summing the filter's output (and counting it)."""
+    rng = np.random.default_rng(n % 1000 + 7)
+    a = rng.integers(0, 2**32, size=n + 1, dtype=np.uint32)[1:]   # 4-byte-aligned but not 16
+    d = dev(np.concatenate([[0], a]))[1:]
+    s, c = ctx.sum_lt_dev(d, thr)
+    torch.cuda.synchronize()
+    sel = oracle.filter_lt(a, thr) if n else np.empty(0, np.uint32)
+    assert int(s.cpu().numpy().view(np.uint64)[0]) == oracle.sum_u32(sel) if sel.size else int(s.cpu()[0]) == 0
+    assert int(c.cpu()[0]) == sel.size
+    # the plain sum is unaffected by the template
+    p = ctx.sum_dev(d)
+    assert int(p.cpu().numpy().view(np.uint64)[0]) == (oracle.sum_u32(a) if n else 0)
