@@ -351,10 +351,22 @@ def bench_join(ctx, D, args):
         cap = n + n // 8 + 65536  # received rows: hash-uniform, 12.5 % slack
         outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
-        if args.join_exchange == "p2p":
-            # fused shuffle: the routing kernel stores straight into the peers' receive buffers
+        exchange = args.join_exchange
+        pj = None
+        if exchange == "p2p":
+            # fused shuffle: the routing kernel stores straight into the peers' receive buffers.
+            # Symmetric memory needs peer access between all ranks; if any rank cannot set it up,
+            # every rank takes the NCCL all-to-all path instead (both are GPU paths).
             from dpu_olap_b200.sharded import P2PShuffleJoin
-            pj = P2PShuffleJoin(ctx, D.dist, D.rank, G, n, cap)
+            ok = 1
+            try:
+                pj = P2PShuffleJoin(ctx, D.dist, D.rank, G, n, cap)
+            except Exception as e:  # noqa: BLE001 - reported below, and agreed on by all ranks
+                ok = 0
+                info["p2p_unavailable"] = f"{type(e).__name__}: {e}"[:200]
+            if D.sum_int(ok) != G:
+                pj, exchange = None, "nccl"
+        if exchange == "p2p":
             jws_bytes = ctx.join_seg_ws_bytes(cap, cap, pj.skip, pj.seg_bits)
             if jws_bytes == 0:
                 raise SystemExit("segmented join unsupported at this size; use --join-exchange nccl")
