@@ -30,7 +30,6 @@
 //      top hash bits equal s.
 #include <algorithm>
 
-#include "join_l2.cuh"
 #include "partition.cuh"
 
 namespace {
@@ -47,6 +46,12 @@ constexpr int kRound = kThreads * kItems;      // 4608 rows: mean partition + 8 
 constexpr int kSegs = kWarps * kItems;         // (item, warp) match counts per probe round
 constexpr int kSegsPerLane = (kSegs + 31) / 32;
 constexpr int kProbeCtasPerSm = 2;             // 3 CTAs/SM (40 registers, spills) measured 5 % slower
+
+struct JoinState {  // lives in the workspace header
+  unsigned long long out_rows;
+  unsigned int overflow;
+  unsigned int pad;
+};
 
 // Bucket inside a partition's table. All keys of a partition share the TOP bits of wang_hash, so
 // the table uses an independent multiplicative hash of the key itself (two instructions).
@@ -265,7 +270,6 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
 __global__ void join_init_kernel(JoinState* st) {
   st->out_rows = 0;
   st->overflow = 0;
-  for (int i = 0; i < 4; ++i) st->phase_ns[i] = 0;
 }
 __global__ void join_finish_kernel(const JoinState* __restrict__ st, uint64_t* __restrict__ out_rows) {
   // a partition buffer that overflowed (skewed slice) makes the result invalid: report ~0
@@ -278,49 +282,27 @@ int ceil_log2_i64(int64_t v) {
   return b;
 }
 
-// Which build/probe kernel the drivers use (b200olap_tune_join): 1 = table in L2, one partitioning
-// pass of <= 2^10 groups (join_l2.cu); 0 = table in shared memory, two passes down to ~4096-row
-// partitions (join_probe_kernel below).
-int g_join_l2 = 1;
-int64_t g_l2_group_rows = (int64_t)1 << 21;  // target build rows per group
-int g_l2_fill_x100 = 150;                    // mean rows per 3-slot bucket, x100
-
 struct JoinPlan {
-  int bits;        // partition bits (L2: groups; shared memory: fine partitions)
+  int bits;        // fine partition bits
   int slice_bits;  // log2 number of hash-space slices
   int64_t cap_r, cap_l, cap_tmp;
   bool two_pass;
-  bool l2;
-  JoinL2Geom geom;
-  size_t off_state, off_roff, off_loff, off_rout, off_lout, off_tmp, off_part, part_bytes, off_table, total;
+  size_t off_state, off_roff, off_loff, off_rout, off_lout, off_tmp, off_part, part_bytes, total;
 };
 
 JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits) {
   JoinPlan P;
   P.slice_bits = slice_bits;
-  P.l2 = g_join_l2 != 0;
   const int64_t nslices = (int64_t)1 << slice_bits;
   const int64_t nr_slice = (nr + nslices - 1) / nslices;
-  if (P.l2) {
-    int bits = ceil_log2_i64((nr_slice + g_l2_group_rows - 1) / g_l2_group_rows);
-    bits = std::min(bits, kPartMaxBits);
-    bits = std::min(bits, 32 - skip_bits - slice_bits);
-    if (slice_bits > 0) bits = std::max(bits, 1);  // the partitioning pass is what selects the slice
-    P.bits = std::max(bits, 0);
-    P.two_pass = false;
-    P.geom = join_l2_geom((nr_slice >> P.bits) + 1, g_l2_fill_x100);
-  } else {
-    int bits = ceil_log2_i64((nr_slice + kTargetBuild - 1) / kTargetBuild);
-    bits = std::max(bits, 1);
-    bits = std::min(bits, 2 * kPartMaxBits);
-    bits = std::min(bits, 32 - skip_bits - slice_bits);
-    P.bits = std::max(bits, 1);
-    P.two_pass = P.bits > kPartMaxBits;
-  }
-  const bool partitioned = !P.l2 || P.bits > 0;
+  int bits = ceil_log2_i64((nr_slice + kTargetBuild - 1) / kTargetBuild);
+  bits = std::max(bits, 1);
+  bits = std::min(bits, 2 * kPartMaxBits);
+  bits = std::min(bits, 32 - skip_bits - slice_bits);
+  P.bits = std::max(bits, 1);
+  P.two_pass = P.bits > kPartMaxBits;
   // slices are hash-uniform in expectation; leave 12.5 % + 64 Ki rows of slack for skew
   auto cap = [&](int64_t n) {
-    if (!partitioned) return (int64_t)0;  // small L2 join: the input columns are joined in place
     if (slice_bits == 0) return n;
     const int64_t per = (n + nslices - 1) / nslices;
     return std::min(n, per + per / 8 + 65536);
@@ -336,16 +318,10 @@ JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits) {
   P.off_rout = o;  o += b2_align_up((size_t)P.cap_r * 8, 256);
   P.off_lout = o;  o += b2_align_up((size_t)P.cap_l * 8, 256);
   P.off_tmp = o;   o += b2_align_up((size_t)P.cap_tmp * 8, 256);
-  P.part_bytes = partitioned ? std::max(part_full_ws_bytes(nr, P.bits), part_full_ws_bytes(nl, P.bits)) : 0;
+  P.part_bytes = std::max(part_full_ws_bytes(nr, P.bits), part_full_ws_bytes(nl, P.bits));
   P.off_part = o;  o += b2_align_up(P.part_bytes, 256);
-  P.off_table = o; o += P.l2 ? b2_align_up(P.geom.table_bytes, 256) : 0;
   P.total = o;
   return P;
-}
-
-__global__ void set_segment_kernel(int64_t* seg_off, int64_t n) {
-  seg_off[0] = 0;
-  seg_off[1] = n;
 }
 
 constexpr int kMaxSliceBits = 6;
@@ -376,28 +352,7 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
 
   join_init_kernel<<<1, 1, 0, s>>>(st);
   B2_LAUNCH_CHECK(ctx, "join_init_kernel");
-  if (nl > 0 && nr > 0 && P.l2) {
-    for (uint32_t slice = 0; slice < (1u << P.slice_bits); ++slice) {
-      PartInput r2 = rin, l2 = lin;
-      if (P.bits == 0 && P.slice_bits == 0) {
-        set_segment_kernel<<<1, 1, 0, s>>>(roff, nr);
-        set_segment_kernel<<<1, 1, 0, s>>>(loff, nl);
-        B2_LAUNCH_CHECK(ctx, "set_segment_kernel");
-      } else {
-        const int part_shl = skip_bits + P.slice_bits;
-        B2_RETURN_NOT_OK(part_full(ctx, rin, nr, P.bits, part_shl, skip_bits, P.slice_bits, slice,
-                                   rout, nullptr, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
-        B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
-                                   lout, nullptr, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s));
-        r2 = PartInput();
-        l2 = PartInput();
-        r2.pairs = rout;
-        l2.pairs = lout;
-      }
-      B2_RETURN_NOT_OK(join_l2_run(ctx, r2, roff, l2, loff, (int64_t)1 << P.bits, P.geom,
-                                   base + P.off_table, d_out_fk, d_out_y, d_out_x, out_capacity, st, s));
-    }
-  } else if (nl > 0 && nr > 0) {
+  if (nl > 0 && nr > 0) {
     static bool attr_done = false;
     if (!attr_done) {
       B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel,
@@ -523,27 +478,14 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   return B2_OK;
 }
 
+__global__ void set_segment_kernel(int64_t* seg_off, int64_t n) {
+  seg_off[0] = 0;
+  seg_off[1] = n;
+}
+
 }  // namespace
 
 extern "C" {
-
-// Diagnostics: phase clock of the last L2 join that used workspace d_ws (clear, build, probe ns and
-// the number of grid syncs). Synchronises the device.
-int b200olap_join_phases(const void* d_ws, uint64_t* out4) {
-  if (!d_ws || !out4) return B2_ERR_INVALID;
-  JoinState st;
-  if (cudaMemcpy(&st, d_ws, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return B2_ERR_CUDA;
-  for (int i = 0; i < 4; ++i) out4[i] = st.phase_ns[i];
-  return B2_OK;
-}
-
-int b200olap_tune_join(int l2, int64_t group_rows, int fill_x100) {
-  if (l2 < 0 || l2 > 1 || group_rows < 0 || fill_x100 < 0) return B2_ERR_INVALID;
-  g_join_l2 = l2;
-  if (group_rows > 0) g_l2_group_rows = group_rows;
-  if (fill_x100 > 0) g_l2_fill_x100 = fill_x100;
-  return B2_OK;
-}
 
 uint32_t b2_wang_hash_u32(uint32_t key) { return wang_hash_u32(key); }
 

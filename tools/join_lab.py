@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""join_lab.py — time the single-GPU join for each build/probe configuration (tuning aid).
+"""join_lab.py — time the single-GPU join for every scatter-kernel shape (tuning aid).
 
-    python tools/join_lab.py [--sf 64,512] [--configs smem,l2:21:150,l2:22:150]
+    python tools/join_lab.py [--sf 64,512] [--configs smem:0,smem:1,smem:2,smem:3]
 
-`smem[:v]` = shared-memory tables after two radix passes (scatter-kernel shape v);
-`l2:G:F`   = L2-resident table, 2^G build rows per group, F/100 rows per 3-slot bucket.
+`smem:v` = shared-memory tables after two radix passes, scatter-kernel shape v. (Commit 788c869
+also had `l2:G:F`, the L2-resident table experiment described in profiles/r1_join_l2.md.)
 """
-import argparse, ctypes as C, json, sys
+import argparse, json, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
@@ -17,12 +17,10 @@ def main():
     from dpu_olap_b200.ops import Context
     p = argparse.ArgumentParser()
     p.add_argument("--sf", default="64,512")
-    p.add_argument("--configs", default="smem,l2:21:150,l2:22:150,l2:20:150")
+    p.add_argument("--configs", default="smem:0,smem:1,smem:2,smem:3")
     p.add_argument("--reps", type=int, default=5)
     a = p.parse_args()
     ctx = Context(0)
-    tune = ctx._lib.b200olap_tune_join
-    tune.argtypes = [C.c_int, C.c_int64, C.c_int]
     B = 2 << 20
     for sf in [int(x) for x in a.sf.split(",")]:
         g = RandomArrayGenerator(ctx, 42)
@@ -36,11 +34,8 @@ def main():
         fk_sum = int(fk.to(torch.int64).sum())
         for cfg in a.configs.split(","):
             f = cfg.split(":")
-            if f[0] == "smem":
-                assert tune(0, 0, 0) == 0
-                assert ctx._lib.b200olap_tune_scatter_variant(int(f[1]) if len(f) > 1 else 0) == 0
-            else:
-                assert tune(1, 1 << int(f[1]), int(f[2])) == 0
+            assert f[0] == "smem", cfg
+            assert ctx._lib.b200olap_tune_scatter_variant(int(f[1]) if len(f) > 1 else 0) == 0
             ws = torch.empty(ctx.join_ws_bytes(n, n) + 256, dtype=torch.uint8, device="cuda")
             step = lambda: ctx.join_dev(fk, y, pk, x, out_capacity=n, ws=ws, outs=outs, out_rows=rows)
             for o in outs:
@@ -60,14 +55,7 @@ def main():
             ok = ok and int(outs[1].to(torch.int64).sum()) == int(y.to(torch.int64).sum())
             xs = x[outs[0].to(torch.int64)[: 1 << 20]]
             ok = ok and bool(torch.equal(xs, outs[2][: 1 << 20]))
-            ph = (C.c_uint64 * 4)()
-            phases = None
-            if f[0] != "smem":
-                fn = ctx._lib.b200olap_join_phases
-                fn.argtypes = [C.c_void_p, C.c_void_p]
-                assert fn((ws.data_ptr() + 255) // 256 * 256, ph) == 0
-                phases = {"clear_ms": ph[0] / 1e6, "build_ms": ph[1] / 1e6, "probe_ms": ph[2] / 1e6, "syncs": ph[3]}
-            print(json.dumps({"sf": sf, "config": cfg, "ms": round(ms, 3), "phases": phases, "ws_gib": round(ws.numel() / 2**30, 2),
+            print(json.dumps({"sf": sf, "config": cfg, "ms": round(ms, 3), "ws_gib": round(ws.numel() / 2**30, 2),
                               "rows_per_s": n / (ms * 1e-3), "ok": ok}), flush=True)
             del ws
         del x, pk, y, fk, outs
