@@ -19,7 +19,7 @@ LIB_PATH = PKG_DIR / "libb200olap.so"
 STAMP = PKG_DIR / ".libb200olap.stamp"
 
 SOURCES = ["ctx.cu", "sum.cu", "filter.cu", "take.cu", "gen.cu", "scan.cu", "partition.cu",
-           "join.cu", "api_host.cu", "api_host_join.cu"]
+           "join.cu", "nullable.cu", "api_host.cu", "api_host_join.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -710,4 +710,228 @@ int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64
   return B2_OK;
 }
 
+
+}  // extern "C"
+
+// ---- nullable columns ---------------------------------------------------------
+// Straightforward (unchunked) host entry points: the per-batch Arrow validity bitmaps are packed
+// into ONE bitmap over the packed device column on the host, uploaded with the values, and the
+// nullable kernels run on the whole column.
+namespace {
+
+void set_bits(uint8_t* dst, int64_t d0, int64_t n) {
+  for (int64_t i = 0; i < n;) {
+    const int64_t d = d0 + i;
+    if ((d & 7) == 0 && n - i >= 8) {
+      const int64_t nbytes = (n - i) >> 3;
+      memset(dst + (d >> 3), 0xff, (size_t)nbytes);
+      i += nbytes << 3;
+    } else {
+      dst[d >> 3] |= (uint8_t)(1u << (d & 7));
+      ++i;
+    }
+  }
+}
+
+// dst bits [d0, d0+n) = src bits [s0, s0+n); dst bits are zero beforehand.
+void copy_bits(uint8_t* dst, int64_t d0, const uint8_t* src, int64_t s0, int64_t n) {
+  int64_t i = 0;
+  if (((d0 | s0) & 7) == 0) {
+    const int64_t nbytes = n >> 3;
+    memcpy(dst + (d0 >> 3), src + (s0 >> 3), (size_t)nbytes);
+    i = nbytes << 3;
+  }
+  for (; i < n; ++i) {
+    const int64_t s = s0 + i, d = d0 + i;
+    if ((src[s >> 3] >> (s & 7)) & 1) dst[d >> 3] |= (uint8_t)(1u << (d & 7));
+  }
+}
+
+// One bitmap over the packed column (bit L.off[b] + r = row r of batch b), padded to 4 bytes.
+// valid_ptrs == NULL or valid_ptrs[b] == NULL: batch b has no nulls. Returns true if any batch
+// brought a bitmap.
+bool pack_validity(std::vector<uint8_t>* dst, const Layout& L, const uint8_t* const* valid_ptrs,
+                   const int64_t* bit_offsets, int64_t nbatches) {
+  dst->assign(b2_align_up((size_t)((L.rows() + 7) >> 3), 4) + 4, 0);
+  bool any = false;
+  for (int64_t b = 0; b < nbatches; ++b) {
+    const int64_t n = L.off[(size_t)b + 1] - L.off[(size_t)b];
+    if (valid_ptrs && valid_ptrs[b]) {
+      any = true;
+      copy_bits(dst->data(), L.off[(size_t)b], valid_ptrs[b], bit_offsets ? bit_offsets[b] : 0, n);
+    } else {
+      set_bits(dst->data(), L.off[(size_t)b], n);
+    }
+  }
+  return any;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const uint8_t* const* valid_ptrs,
+                     const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
+                     b2_aggr_u32* out, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, out != nullptr, "out is null");
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout L;
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
+  b2_timings tm{};
+  Scratch sc;
+  std::vector<uint8_t> bits;
+  const bool nullable = pack_validity(&bits, L, valid_ptrs, valid_bit_offsets, nbatches);
+  uint32_t* d_col = nullptr;
+  uint8_t* d_valid = nullptr;
+  b2_aggr_u32* d_out = nullptr;
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_col, (size_t)L.rows() * 4));
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_out, sizeof(b2_aggr_u32)));
+  cudaStream_t s = ctx->s_compute;
+  gather_begin(ctx, nbatches, L.rows());
+  B2_RETURN_NOT_OK(upload(ctx, d_col, L, batch_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+  if (nullable) {
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_valid, bits.size()));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
+    tm.h2d_bytes += (int64_t)bits.size();
+  }
+  B2_RETURN_NOT_OK(b2_aggr_u32_dev(ctx, d_col, d_valid, L.rows(), d_out, s));
+  B2_CUDA_OK(ctx, cudaMemcpyAsync(out, d_out, sizeof(b2_aggr_u32), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  tm.d2h_bytes = sizeof(b2_aggr_u32);
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
+                                        const uint8_t* const* valid_ptrs, const int64_t* valid_bit_offsets,
+                                        const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                                        uint32_t* out, int64_t out_capacity, int64_t* out_counts,
+                                        uint64_t* total, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, total != nullptr && out_capacity >= 0, "bad result arguments");
+  B2_REQUIRE(ctx, nbatches == 0 || out_counts != nullptr, "out_counts is null");
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout L;
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
+  if (!L.uniform)
+    return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "nullable filter", "batches must have equal lengths");
+  *total = 0;
+  b2_timings tm{};
+  if (L.rows() > 0) {
+    Scratch sc;
+    std::vector<uint8_t> bits;
+    const bool nullable = pack_validity(&bits, L, valid_ptrs, valid_bit_offsets, nbatches);
+    uint32_t *d_col = nullptr, *d_out = nullptr;
+    uint8_t* d_valid = nullptr;
+    int64_t* d_end = nullptr;
+    void* d_ws = nullptr;
+    const size_t ws_bytes = b2_filter_ws_bytes(nbatches, L.batch_len);
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_col, (size_t)L.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_out, (size_t)L.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_end, (size_t)(nbatches + 1) * 8));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, &d_ws, ws_bytes));
+    cudaStream_t s = ctx->s_compute;
+    gather_begin(ctx, nbatches, L.rows());
+    B2_RETURN_NOT_OK(upload(ctx, d_col, L, batch_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+    if (nullable) {
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_valid, bits.size()));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
+      tm.h2d_bytes += (int64_t)bits.size();
+    }
+    B2_RETURN_NOT_OK(b2_filter_lt_u32_nullable_dev(ctx, d_col, d_valid, nbatches, L.batch_len, threshold,
+                                                   d_out, d_end, d_end + nbatches, nullptr, d_ws, ws_bytes, s));
+    std::vector<int64_t> end((size_t)nbatches + 1);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(end.data(), d_end, (size_t)(nbatches + 1) * 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    for (int64_t b = 0; b < nbatches; ++b) out_counts[b] = end[(size_t)b] - (b ? end[(size_t)b - 1] : 0);
+    *total = (uint64_t)end[(size_t)nbatches];
+    tm.d2h_bytes = (nbatches + 1) * 8;
+    if ((int64_t)*total > out_capacity)
+      return b2_set_error(ctx, B2_ERR_OVERFLOW, "nullable filter", "result exceeds out_capacity");
+    if (*total > 0) {
+      B2_REQUIRE(ctx, out != nullptr, "out is null");
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(out, d_out, (size_t)*total * 4, cudaMemcpyDeviceToHost, s));
+      B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+      tm.d2h_bytes += (int64_t)*total * 4;
+    }
+  } else {
+    for (int64_t b = 0; b < nbatches; ++b) out_counts[b] = 0;
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_take_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* value_ptrs,
+                              const uint8_t* const* value_valid_ptrs, const int64_t* value_valid_bit_offsets,
+                              const int64_t* value_lens, const uint32_t* const* idx_ptrs,
+                              const uint8_t* const* idx_valid_ptrs, const int64_t* idx_valid_bit_offsets,
+                              const int64_t* idx_lens, int64_t nbatches, uint32_t* const* out_ptrs,
+                              uint8_t* const* out_valid_ptrs, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout LV, LI;
+  B2_RETURN_NOT_OK(make_layout(ctx, value_ptrs, value_lens, nbatches, &LV));
+  B2_RETURN_NOT_OK(make_layout(ctx, idx_ptrs, idx_lens, nbatches, &LI));
+  if (!LV.uniform || !LI.uniform)
+    return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "nullable take", "batches must have equal lengths");
+  B2_REQUIRE(ctx, nbatches == 0 || (out_ptrs && out_valid_ptrs), "null output tables");
+  b2_timings tm{};
+  if (LI.rows() > 0) {
+    Scratch sc;
+    std::vector<uint8_t> vbits, ibits;
+    const bool vnull = pack_validity(&vbits, LV, value_valid_ptrs, value_valid_bit_offsets, nbatches);
+    const bool inull = pack_validity(&ibits, LI, idx_valid_ptrs, idx_valid_bit_offsets, nbatches);
+    uint32_t *d_val = nullptr, *d_idx = nullptr, *d_out = nullptr;
+    uint8_t *d_vv = nullptr, *d_iv = nullptr, *d_ov = nullptr;
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_val, (size_t)LV.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_idx, (size_t)LI.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_out, (size_t)LI.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_ov, ibits.size()));
+    cudaStream_t s = ctx->s_compute;
+    gather_begin(ctx, 2 * nbatches, LV.rows() + LI.rows());
+    B2_RETURN_NOT_OK(upload(ctx, d_val, LV, value_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+    B2_RETURN_NOT_OK(upload(ctx, d_idx, LI, idx_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+    if (vnull) {
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_vv, vbits.size()));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_vv, vbits.data(), vbits.size(), cudaMemcpyHostToDevice, s));
+      tm.h2d_bytes += (int64_t)vbits.size();
+    }
+    if (inull) {
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_iv, ibits.size()));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_iv, ibits.data(), ibits.size(), cudaMemcpyHostToDevice, s));
+      tm.h2d_bytes += (int64_t)ibits.size();
+    }
+    B2_RETURN_NOT_OK(b2_take_u32_nullable_dev(ctx, d_val, d_vv, LV.batch_len, d_idx, d_iv, LI.batch_len,
+                                              nbatches, d_out, d_ov, s));
+    B2_RETURN_NOT_OK(download(ctx, d_out, LI, out_ptrs, 0, nbatches, s, &tm.d2h_bytes));
+    std::vector<uint8_t> obits(ibits.size());
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(obits.data(), d_ov, obits.size(), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    tm.d2h_bytes += (int64_t)obits.size();
+    for (int64_t b = 0; b < nbatches; ++b) {  // per-batch result bitmaps, bit offset 0
+      const int64_t n = LI.off[(size_t)b + 1] - LI.off[(size_t)b];
+      memset(out_valid_ptrs[b], 0, (size_t)((n + 7) >> 3));
+      copy_bits(out_valid_ptrs[b], 0, obits.data(), LI.off[(size_t)b], n);
+    }
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
 }  // extern "C"

@@ -36,6 +36,12 @@
 // Tiles never straddle a batch boundary, so the inclusive count of the last tile of batch b is
 // the end offset of result chunk b (FilterDpu::GetResult returns one chunk per input batch,
 // host/filter/filter_dpu.cc:89-96,162-166) — a tiny second kernel collects those.
+//
+// Nullable columns (the DPU path has none, it passes a nullptr bitmap,
+// filter_dpu.cc:91): Arrow's filter drops rows whose predicate is null, so a row is selected iff it
+// is valid AND v < threshold. The kNullable variant reads the packed validity bitmap (bit i = row i,
+// LSB first, as Arrow) — one 32-bit word per 8 lanes and segment — and turns null rows into
+// 0xffffffff, the value that never satisfies `< threshold`; counting and compaction are unchanged.
 #include "common.cuh"
 #include "lookback.cuh"
 #include "tma.cuh"
@@ -51,6 +57,7 @@ struct FilterWs {  // header of the caller workspace; zeroed with the count word
 
 struct FilterArgs {
   const uint32_t* in;
+  const uint32_t* valid;  // kNullable: validity bitmap over the packed rows, 4-byte words
   uint32_t* out;
   uint32_t thr;
   int64_t ntiles;
@@ -115,7 +122,7 @@ __device__ __forceinline__ void count_lt(uint32_t& acc, uint32_t v, uint32_t thr
       : "r"(v), "r"(thr), "r"(inc));
 }
 
-template <typename Cfg>
+template <typename Cfg, bool kNullable>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kCtasPerSm)
 filter_lt_u32_kernel(const FilterArgs a) {
   constexpr int kCT = Cfg::kComputeThreads, kS = Cfg::kStages, kW = Cfg::kWarps, kTile = Cfg::kTile;
@@ -253,11 +260,24 @@ filter_lt_u32_kernel(const FilterArgs a) {
     uint32_t cnt = 0;  // four 8-bit counters: matches of this lane in segment j at bits 8j..8j+7
     const uint32_t e0 = warp * 512 + lane * 4;  // + j*128 + e
     if (valid) {
-      if (si.tma && si.len == kTile) {
+      if (si.tma && si.len == kTile && (!kNullable || (si.row0 & 31) == 0)) {
+        uint32_t vw[kVecPerThread];  // validity of this lane's rows: a nibble of one word per segment
+        if (kNullable) {
+          const uint32_t* __restrict__ wp = a.valid + (si.row0 >> 5) + warp * 16 + (lane >> 3);
+#pragma unroll
+          for (int j = 0; j < kVecPerThread; ++j) vw[j] = __ldg(wp + j * 4) >> ((lane & 7) * 4);
+        }
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
           const uint4 q = *reinterpret_cast<const uint4*>(buf + e0 + j * 128);
           v[j][0] = q.x; v[j][1] = q.y; v[j][2] = q.z; v[j][3] = q.w;
+        }
+        if (kNullable) {
+#pragma unroll
+          for (int j = 0; j < kVecPerThread; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (!((vw[j] >> e) & 1u)) v[j][e] = 0xffffffffu;  // a null row never matches
         }
         uint32_t cnt_hi = 0;  // two chains halve the dependent-add latency
 #pragma unroll
@@ -274,7 +294,13 @@ filter_lt_u32_kernel(const FilterArgs a) {
             const uint32_t i = e0 + j * 128 + e;
             // rows past the end of the tile never match (0xffffffff < thr is false for every thr)
             v[j][e] = 0xffffffffu;
-            if ((int32_t)i < si.len) v[j][e] = si.tma ? buf[i] : ld_stream_u32(src + i);
+            if ((int32_t)i < si.len) {
+              v[j][e] = si.tma ? buf[i] : ld_stream_u32(src + i);
+              if (kNullable) {
+                const int64_t r = si.row0 + i;
+                if (!((__ldg(a.valid + (r >> 5)) >> (r & 31)) & 1u)) v[j][e] = 0xffffffffu;
+              }
+            }
             cnt += ((int32_t)i < si.len ? lt_u32(v[j][e], a.thr) : 0u) << (8 * j);
           }
         }
@@ -411,21 +437,21 @@ int g_filter_debug = 0;  // tools/filter_lab.py switches this through b200olap_t
 
 static inline int64_t tiles_of(int64_t len) { return (len + kTileRows - 1) / kTileRows; }
 
-template <typename Cfg>
+template <typename Cfg, bool kNullable = false>
 int launch_variant(b2_ctx* ctx, const FilterArgs& a, cudaStream_t s) {
   static int max_ctas = 0;  // per process; every B200 is the same
   if (max_ctas == 0) {
-    B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg>,
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg, kNullable>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     int per_sm = 0;
     B2_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                        &per_sm, filter_lt_u32_kernel<Cfg>, Cfg::kThreads, Cfg::kSmemBytes));
+                        &per_sm, filter_lt_u32_kernel<Cfg, kNullable>, Cfg::kThreads, Cfg::kSmemBytes));
     if (per_sm < 1) return b2_set_error(ctx, B2_ERR_CUDA, "filter kernel", "does not fit an SM");
     if (per_sm > Cfg::kCtasPerSm) per_sm = Cfg::kCtasPerSm;
     max_ctas = per_sm * ctx->sm_count;
   }
   const int64_t grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
-  filter_lt_u32_kernel<Cfg><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(a);
+  filter_lt_u32_kernel<Cfg, kNullable><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(a);
   B2_LAUNCH_CHECK(ctx, "filter_lt_u32_kernel");
   return B2_OK;
 }
@@ -458,7 +484,7 @@ int64_t ragged_tiles(const int64_t* h_batch_off, int64_t nbatches) {
   return n;
 }
 
-int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t batch_len,
+int filter_launch(b2_ctx* ctx, const uint32_t* d_in, const uint32_t* d_valid, int64_t nbatches, int64_t batch_len,
                   const int64_t* h_batch_off, const int64_t* d_batch_off, uint32_t thr,
                   uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
                   const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, cudaStream_t s) {
@@ -497,6 +523,7 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t b
   if (ntiles > 0) {
     FilterArgs a{};
     a.in = d_in;
+    a.valid = d_valid;
     a.out = d_out;
     a.thr = thr;
     a.ntiles = ntiles;
@@ -511,7 +538,9 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t b
     a.sgrp = reinterpret_cast<uint64_t*>(base + w.sgrp_off);
     a.incl = incl;
     a.debug = g_filter_debug;
-    switch (g_filter_variant) {
+    if (d_valid) {  // one shape for the nullable kernel: the default one
+      B2_RETURN_NOT_OK((launch_variant<Cfg2, true>(ctx, a, s)));
+    } else switch (g_filter_variant) {
       case 1: B2_RETURN_NOT_OK(launch_variant<Cfg1>(ctx, a, s)); break;
       case 2: B2_RETURN_NOT_OK(launch_variant<Cfg2>(ctx, a, s)); break;
       case 3: B2_RETURN_NOT_OK(launch_variant<Cfg3>(ctx, a, s)); break;
@@ -559,8 +588,22 @@ int b2_filter_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, in
   B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
   B2_REQUIRE(ctx, nbatches * batch_len == 0 || (d_in && d_out), "null column pointer");
-  return filter_launch(ctx, d_in, nbatches, batch_len, nullptr, nullptr, threshold, d_out,
+  return filter_launch(ctx, d_in, nullptr, nbatches, batch_len, nullptr, nullptr, threshold, d_out,
                        d_batch_end, d_total, d_carry_in, d_ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int b2_filter_lt_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid,
+                                  int64_t nbatches, int64_t batch_len, uint32_t threshold,
+                                  uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
+                                  const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
+  B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
+  B2_REQUIRE(ctx, nbatches * batch_len == 0 || (d_in && d_out), "null column pointer");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_valid) & 3) == 0, "validity bitmap must be 4-byte aligned");
+  return filter_launch(ctx, d_in, reinterpret_cast<const uint32_t*>(d_valid), nbatches, batch_len, nullptr,
+                       nullptr, threshold, d_out, d_batch_end, d_total, d_carry_in, d_ws, ws_bytes,
                        static_cast<cudaStream_t>(stream));
 }
 
@@ -575,7 +618,7 @@ int b2_filter_lt_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_in, const int64_t
   for (int64_t b = 0; b < nbatches; ++b)
     B2_REQUIRE(ctx, h_batch_off[b + 1] >= h_batch_off[b], "batch offsets must be non-decreasing");
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
-  return filter_launch(ctx, d_in, nbatches, 0, h_batch_off, d_batch_off, threshold, d_out,
+  return filter_launch(ctx, d_in, nullptr, nbatches, 0, h_batch_off, d_batch_off, threshold, d_out,
                        d_batch_end, d_total, d_carry_in, d_ws, ws_bytes,
                        static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,232 @@
+// nullable.cu — aggregate and take over columns WITH validity bitmaps.
+//
+// The reference's DPU path has neither: its kernels see raw uint32 buffers only (it hands Arrow a
+// nullptr bitmap, host/filter/filter_dpu.cc:91; `enum AggregatorType` holds only AggrSum,
+// shared/umq/kernels.h:22-25). What is restated here is the behaviour of the reference's ORACLE,
+// Arrow's compute kernels, which its Native classes call (aggr_native.cc:68-73, take_native.cc:27):
+//   * aggregates skip null rows: sum -> uint64, count = valid rows, min / max over valid rows
+//     (all four in one pass: the kernel is a 4 B/row read stream either way);
+//   * take: out[j] is null when the INDEX j is null or the VALUE it points at is null.
+// Bitmaps are Arrow's: bit i of the buffer = row i, least significant bit first; here one bitmap
+// spans the packed column (row i of the packed uint32[]), 4-byte aligned and padded to 4 bytes.
+// The nullable filter is a variant of the filter kernel itself (filter.cu).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kAggThreads = 512;
+constexpr int kAggUnroll = 4;
+
+struct AggAcc {
+  uint64_t sum = 0;
+  uint32_t cnt = 0;  // flushed into the 64-bit total by the caller's reduction
+  uint32_t mn = 0xffffffffu;
+  uint32_t mx = 0;
+};
+
+__device__ __forceinline__ void agg_row(AggAcc& a, uint32_t v, bool valid) {
+  if (valid) {
+    a.sum += v;
+    a.cnt += 1;
+    a.mn = min(a.mn, v);
+    a.mx = max(a.mx, v);
+  }
+}
+
+// One pass: 128-bit value loads, one 32-bit bitmap word per 8 threads (valid == nullptr: no nulls).
+// The first `head` rows (until 16 B alignment AND a nibble boundary of the bitmap) and the tail are
+// done row by row by CTA 0.
+__global__ void __launch_bounds__(kAggThreads, 2)
+aggr_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ valid, int64_t n,
+                int64_t head, b2_aggr_u32* __restrict__ out) {
+  const int64_t nvec = (n - head) >> 2;
+  const int64_t tail_start = head + (nvec << 2);
+  const uint4* __restrict__ vin = reinterpret_cast<const uint4*>(in + head);
+  AggAcc acc;
+  uint64_t cnt = 0;
+  const int64_t chunk = (int64_t)kAggThreads * kAggUnroll;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < nvec; base += (int64_t)gridDim.x * chunk) {
+    uint4 v[kAggUnroll];
+    uint32_t nib[kAggUnroll];
+#pragma unroll
+    for (int u = 0; u < kAggUnroll; ++u) {
+      const int64_t i = base + u * kAggThreads + threadIdx.x;
+      nib[u] = 0;
+      if (i < nvec) {
+        v[u] = ld_stream_v4(vin + i);
+        const int64_t r = head + (i << 2);  // head is a multiple of 4 rows when a bitmap is present
+        nib[u] = valid ? (__ldg(valid + (r >> 5)) >> (r & 31)) & 0xfu : 0xfu;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kAggUnroll; ++u) {
+      agg_row(acc, v[u].x, nib[u] & 1u);
+      agg_row(acc, v[u].y, nib[u] & 2u);
+      agg_row(acc, v[u].z, nib[u] & 4u);
+      agg_row(acc, v[u].w, nib[u] & 8u);
+    }
+    cnt += acc.cnt;
+    acc.cnt = 0;
+  }
+  // rows outside the vector body: all of them when the column cannot be vectorised (head == n,
+  // shared by the whole grid), else the few head / tail rows (CTA 0)
+  auto scalar_rows = [&](int64_t r0, int64_t r1, int64_t first, int64_t step) {
+    for (int64_t i = r0 + first; i < r1; i += step)
+      agg_row(acc, in[i], valid ? (__ldg(valid + (i >> 5)) >> (i & 31)) & 1u : 1u);
+  };
+  if (nvec == 0) {
+    scalar_rows(0, n, (int64_t)blockIdx.x * kAggThreads + threadIdx.x, (int64_t)gridDim.x * kAggThreads);
+  } else if (blockIdx.x == 0) {
+    scalar_rows(0, head, threadIdx.x, kAggThreads);
+    scalar_rows(tail_start, n, threadIdx.x, kAggThreads);
+  }
+  cnt += acc.cnt;
+  // CTA reduction, then four atomics per CTA on the (pre-initialised) result
+  __shared__ uint64_t s_sum[kAggThreads / 32], s_cnt[kAggThreads / 32];
+  __shared__ uint32_t s_mn[kAggThreads / 32], s_mx[kAggThreads / 32];
+  const uint64_t wsum = warp_reduce_sum_u64(acc.sum), wcnt = warp_reduce_sum_u64(cnt);
+  const uint32_t wmn = __reduce_min_sync(0xffffffffu, acc.mn), wmx = __reduce_max_sync(0xffffffffu, acc.mx);
+  if (lane_id() == 0) {
+    s_sum[threadIdx.x >> 5] = wsum;
+    s_cnt[threadIdx.x >> 5] = wcnt;
+    s_mn[threadIdx.x >> 5] = wmn;
+    s_mx[threadIdx.x >> 5] = wmx;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const bool in_range = threadIdx.x < kAggThreads / 32;
+    const uint64_t a = warp_reduce_sum_u64(in_range ? s_sum[threadIdx.x] : 0);
+    const uint64_t c = warp_reduce_sum_u64(in_range ? s_cnt[threadIdx.x] : 0);
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, in_range ? s_mn[threadIdx.x] : 0xffffffffu);
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, in_range ? s_mx[threadIdx.x] : 0u);
+    if (threadIdx.x == 0 && c > 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&out->sum), (unsigned long long)a);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&out->count), (unsigned long long)c);
+      atomicMin(&out->min, lo);
+      atomicMax(&out->max, hi);
+    }
+  }
+}
+
+__global__ void aggr_init_kernel(b2_aggr_u32* out) {
+  out->sum = 0;
+  out->count = 0;
+  out->min = 0xffffffffu;
+  out->max = 0;
+}
+
+// ---- take ------------------------------------------------------------------------------------
+constexpr int kTakeThreads = 256;
+constexpr int kTakeWords = 4;  // 32-output words per warp and iteration (independent gathers in flight)
+
+__device__ __forceinline__ bool bit_at(const uint32_t* __restrict__ bm, int64_t i) {
+  return (__ldg(bm + (i >> 5)) >> (i & 31)) & 1u;
+}
+
+// A warp owns whole 32-output words of the result bitmap: lane l handles output 32*w + l, the
+// validity word is one ballot. Null slots carry the value 0.
+__global__ void __launch_bounds__(kTakeThreads)
+take_u32_nullable_kernel(const uint32_t* __restrict__ values, const uint32_t* __restrict__ values_valid,
+                         int64_t values_len, const uint32_t* __restrict__ indices,
+                         const uint32_t* __restrict__ indices_valid, int64_t idx_len, int64_t n,
+                         uint32_t* __restrict__ out, uint32_t* __restrict__ out_valid) {
+  const uint32_t lane = threadIdx.x & 31;
+  const int64_t nwords = (n + 31) >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kTakeThreads + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kTakeThreads) >> 5;
+  for (int64_t w0 = warp0 * kTakeWords; w0 < nwords; w0 += nwarps * kTakeWords) {
+    uint32_t ix[kTakeWords], val[kTakeWords];
+    bool ok[kTakeWords];
+#pragma unroll
+    for (int u = 0; u < kTakeWords; ++u) {
+      const int64_t i = ((w0 + u) << 5) + lane;
+      ok[u] = i < n;
+      ix[u] = ok[u] ? ld_stream_u32(indices + i) : 0u;
+      if (ok[u] && indices_valid) ok[u] = bit_at(indices_valid, i);
+    }
+#pragma unroll
+    for (int u = 0; u < kTakeWords; ++u) {
+      const int64_t i = ((w0 + u) << 5) + lane;
+      val[u] = 0;
+      if (ok[u]) {
+        const int64_t r = (i / idx_len) * values_len + ix[u];  // batch-local gather (take_native.cc:27)
+        val[u] = __ldg(values + r);
+        if (values_valid && !bit_at(values_valid, r)) {
+          ok[u] = false;
+          val[u] = 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTakeWords; ++u) {
+      const int64_t i = ((w0 + u) << 5) + lane;
+      const uint32_t word = __ballot_sync(0xffffffffu, ok[u]);
+      if (i < n) st_stream_u32(out + i, val[u]);
+      if (out_valid && lane == 0 && w0 + u < nwords) out_valid[w0 + u] = word;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid, int64_t n,
+                    b2_aggr_u32* d_out, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, n >= 0, "n must be >= 0");
+  B2_REQUIRE(ctx, d_out != nullptr, "d_out is null");
+  B2_REQUIRE(ctx, n == 0 || d_in != nullptr, "d_in is null");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_in) & 3) == 0, "d_in must be 4-byte aligned");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_valid) & 3) == 0, "validity bitmap must be 4-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  aggr_init_kernel<<<1, 1, 0, s>>>(d_out);
+  B2_LAUNCH_CHECK(ctx, "aggr_init_kernel");
+  if (n == 0) return B2_OK;
+  // scalar head: rows until the values are 16 B aligned; with a bitmap the vector body must also
+  // start on a multiple of 4 rows, which a 16 B-aligned start of a 4 B-aligned array always is
+  // when the array itself starts on a 16 B boundary — otherwise fall back to all-scalar.
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(d_in);
+  int64_t head = (int64_t)(((16 - (addr & 15)) & 15) >> 2);
+  if (d_valid && head != 0) head = n;  // misaligned values with a bitmap: row-by-row path
+  if (head > n) head = n;
+  const int64_t chunk_rows = (int64_t)kAggThreads * kAggUnroll * 4;
+  int64_t want = (n - head + chunk_rows - 1) / chunk_rows;
+  if (head == n) want = (n + kAggThreads - 1) / kAggThreads;  // row-by-row path: one row per thread and step
+  int grid = ctx->sm_count * 2;
+  if (want < grid) grid = want > 0 ? (int)want : 1;
+  aggr_u32_kernel<<<grid, kAggThreads, 0, s>>>(d_in, reinterpret_cast<const uint32_t*>(d_valid), n, head, d_out);
+  B2_LAUNCH_CHECK(ctx, "aggr_u32_kernel");
+  return B2_OK;
+}
+
+int b2_take_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_values, const uint8_t* d_values_valid,
+                             int64_t values_len, const uint32_t* d_indices, const uint8_t* d_indices_valid,
+                             int64_t idx_len, int64_t nbatches, uint32_t* d_out, uint8_t* d_out_valid,
+                             void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, values_len >= 0 && idx_len >= 0 && nbatches >= 0, "negative size");
+  const int64_t n = nbatches * idx_len;
+  if (n == 0) return B2_OK;
+  B2_REQUIRE(ctx, d_values && d_indices && d_out, "null column pointer");
+  B2_REQUIRE(ctx, values_len > 0, "indices into an empty values batch");
+  B2_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(d_values_valid) | reinterpret_cast<uintptr_t>(d_indices_valid) |
+                    reinterpret_cast<uintptr_t>(d_out_valid)) & 3) == 0,
+             "validity bitmaps must be 4-byte aligned");
+  B2_REQUIRE(ctx, d_out_valid || (!d_values_valid && !d_indices_valid),
+             "nullable inputs need an output validity bitmap");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t nwords = (n + 31) >> 5;
+  const int64_t warps_per_cta = kTakeThreads / 32;
+  int64_t grid = (nwords + warps_per_cta * kTakeWords - 1) / (warps_per_cta * kTakeWords);
+  const int64_t cap = (int64_t)ctx->sm_count * 64;
+  if (grid > cap) grid = cap;
+  take_u32_nullable_kernel<<<(unsigned)grid, kTakeThreads, 0, s>>>(
+      d_values, reinterpret_cast<const uint32_t*>(d_values_valid), values_len, d_indices,
+      reinterpret_cast<const uint32_t*>(d_indices_valid), idx_len, n, d_out,
+      reinterpret_cast<uint32_t*>(d_out_valid));
+  B2_LAUNCH_CHECK(ctx, "take_u32_nullable_kernel");
+  return B2_OK;
+}
+
+}  // extern "C"

@@ -85,6 +85,66 @@ def _column(batch: Any, name_or_index) -> np.ndarray:
     return _as_u32(batch)
 
 
+class _NullableCol:
+    """One column of one batch that may carry an Arrow validity bitmap:
+    ``values`` is the uint32 data (null slots hold whatever the buffer holds), ``valid`` a uint8
+    array holding the bitmap (bit ``offset + r`` = row r, LSB first) or None when there are no nulls."""
+
+    __slots__ = ("values", "valid", "offset", "_keep")
+
+    def __init__(self, values: np.ndarray, valid=None, offset: int = 0, keep=None):
+        self.values, self.valid, self.offset, self._keep = values, valid, int(offset), keep
+
+
+def _as_nullable(col: Any) -> _NullableCol:
+    if pa is not None and isinstance(col, (pa.Array, pa.ChunkedArray)):
+        if isinstance(col, pa.ChunkedArray):
+            col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
+        if col.type != pa.uint32():
+            raise TypeError(f"expected uint32 column, got {col.type}")
+        if col.null_count == 0:
+            return _NullableCol(_as_u32(col))
+        vbuf, dbuf = col.buffers()[0], col.buffers()[1]
+        values = np.frombuffer(dbuf, dtype=np.uint32)[col.offset:col.offset + len(col)]
+        return _NullableCol(values, np.frombuffer(vbuf, dtype=np.uint8), col.offset, keep=col)
+    if isinstance(col, np.ma.MaskedArray):
+        data = np.ascontiguousarray(np.ma.getdata(col))
+        if data.dtype != np.uint32:
+            raise TypeError(f"expected uint32 column, got {data.dtype}")
+        mask = np.ma.getmaskarray(col)
+        if not mask.any():
+            return _NullableCol(data)
+        return _NullableCol(data, np.packbits(~mask, bitorder="little"), 0)
+    return _NullableCol(_as_u32(col))
+
+
+def _nullable_column(batch: Any, name_or_index) -> _NullableCol:
+    if pa is not None and isinstance(batch, pa.RecordBatch):
+        i = batch.schema.get_field_index(name_or_index) if isinstance(name_or_index, str) else name_or_index
+        return _as_nullable(batch.column(i))
+    if isinstance(batch, dict):
+        return _as_nullable(batch[name_or_index] if isinstance(name_or_index, str)
+                            else list(batch.values())[name_or_index])
+    return _as_nullable(batch)
+
+
+class _ValidTable:
+    """(const uint8_t* const* bitmaps, const int64_t* bit offsets) of a list of _NullableCol."""
+
+    def __init__(self, cols: Sequence[_NullableCol]):
+        n = len(cols)
+        self.any = any(c.valid is not None for c in cols)
+        self.ptrs = (C.c_void_p * max(n, 1))(*[c.valid.ctypes.data if c.valid is not None else None
+                                               for c in cols])
+        self.offs = (C.c_int64 * max(n, 1))(*[c.offset for c in cols])
+        self._keep = cols
+
+
+def _to_arrow(values: np.ndarray, valid_bytes: np.ndarray):
+    """uint32 pyarrow array over (data, validity bitmap with bit offset 0); no copy."""
+    return pa.Array.from_buffers(pa.uint32(), values.size, [pa.py_buffer(valid_bytes), pa.py_buffer(values)])
+
+
 def _column_names(batch: Any) -> list[str]:
     if pa is not None and isinstance(batch, pa.RecordBatch):
         return list(batch.schema.names)
@@ -219,6 +279,43 @@ class Context:
                                                 _dptr(carry_in), _dptr(ws), ws.numel(), self._stream()),
                  "b2_filter_lt_u32_dev")
         return out, batch_end, total
+
+    def filter_nullable_dev(self, col, valid, nbatches: int, batch_len: int, threshold: int):
+        """Nullable filter: `valid` is the packed validity bitmap (uint8 device tensor, padded to 4
+        bytes) or None. Returns (out, batch_end, total) device tensors."""
+        import torch
+        dev = col.device
+        out = torch.empty(max(nbatches * batch_len, 1), dtype=torch.int32, device=dev)
+        batch_end = torch.empty(max(nbatches, 1), dtype=torch.int64, device=dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        ws = torch.empty(self.filter_ws_bytes(nbatches, batch_len), dtype=torch.uint8, device=dev)
+        self._ck(self._lib.b2_filter_lt_u32_nullable_dev(self._h, _dptr(col), _dptr(valid), nbatches, batch_len,
+                                                         threshold, _dptr(out), _dptr(batch_end), _dptr(total),
+                                                         0, _dptr(ws), ws.numel(), self._stream()),
+                 "b2_filter_lt_u32_nullable_dev")
+        return out, batch_end, total
+
+    def aggr_dev(self, col, valid=None):
+        """sum / count / min / max of the valid rows in one pass; returns a 3 x int64 device tensor
+        laid out as b2_aggr_u32 (decode with :func:`decode_aggr`)."""
+        import torch
+        out = torch.empty(3, dtype=torch.int64, device=col.device)
+        self._ck(self._lib.b2_aggr_u32_dev(self._h, _dptr(col), _dptr(valid), col.numel(), _dptr(out),
+                                           self._stream()), "b2_aggr_u32_dev")
+        return out
+
+    def take_nullable_dev(self, values, values_valid, values_len: int, indices, indices_valid, idx_len: int,
+                          nbatches: int):
+        """Returns (out, out_valid bitmap as uint8 device tensor)."""
+        import torch
+        n = nbatches * idx_len
+        out = torch.empty(max(n, 1), dtype=torch.int32, device=values.device)
+        out_valid = torch.zeros(((n + 31) // 32) * 4 + 4, dtype=torch.uint8, device=values.device)
+        self._ck(self._lib.b2_take_u32_nullable_dev(self._h, _dptr(values), _dptr(values_valid), values_len,
+                                                    _dptr(indices), _dptr(indices_valid), idx_len, nbatches,
+                                                    _dptr(out), _dptr(out_valid), self._stream()),
+                 "b2_take_u32_nullable_dev")
+        return out[:n], out_valid
 
     def filter_ragged_dev(self, col, batch_off: np.ndarray, threshold: int):
         import torch
@@ -395,6 +492,23 @@ class Context:
         return outs[0], outs[1], outs[2], out_rows
 
 
+class AggrResult(C.Structure):
+    """b2_aggr_u32 (include/b200olap.h)."""
+    _fields_ = [("sum", C.c_uint64), ("count", C.c_uint64), ("min", C.c_uint32), ("max", C.c_uint32)]
+
+    def as_dict(self) -> dict:
+        """Arrow's scalars: every aggregate of zero valid rows is null (None); count never is."""
+        empty = self.count == 0
+        return {"sum": None if empty else int(self.sum), "count": int(self.count),
+                "min": None if empty else int(self.min), "max": None if empty else int(self.max)}
+
+
+def decode_aggr(t) -> dict:
+    """Decode the device tensor returned by :meth:`Context.aggr_dev`."""
+    raw = t.cpu().numpy().tobytes()
+    return AggrResult.from_buffer_copy(raw[:C.sizeof(AggrResult)]).as_dict()
+
+
 def wang_hash(key: int) -> int:
     return int(_lib.lib().b2_wang_hash_u32(int(key) & 0xFFFFFFFF))
 
@@ -414,7 +528,9 @@ class FilterGpu:
 
     def __init__(self, ctx: Context, batches: Sequence[Any], threshold: int = FILTER_THRESHOLD):
         self.ctx = ctx
-        self._cols = [_column(b, 0) for b in batches]
+        self._ncols = [_nullable_column(b, 0) for b in batches]
+        self._cols = [c.values for c in self._ncols]
+        self._valid = _ValidTable(self._ncols)
         self.threshold = int(threshold)
         self._timers = None
 
@@ -435,8 +551,29 @@ class FilterGpu:
         """Number of selected rows (FilterDpu::Run, filter_dpu.cc:171-173)."""
         return self.GetResult(_count_only=True)
 
+    def _get_result_nullable(self, _count_only: bool):
+        """Nullable input: a row is kept iff valid and below the threshold (Arrow's filter drops
+        null predicates); the result has no nulls."""
+        tab = _PtrTable(self._cols)
+        counts = (C.c_int64 * max(tab.n, 1))()
+        total = C.c_uint64(0)
+        flat = np.empty(sum(a.size for a in self._cols), dtype=np.uint32)
+        t = Timings()
+        self.ctx._ck(self.ctx._lib.b2_filter_lt_u32_nullable_host_into(
+            self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n, self.threshold,
+            flat.ctypes.data, flat.size, counts, C.byref(total), C.byref(t)),
+            "b2_filter_lt_u32_nullable_host_into")
+        self._timers = Timers.from_timings(t)
+        self._last = (t,)
+        if _count_only:
+            return int(total.value)
+        bounds = np.concatenate([[0], np.cumsum(np.frombuffer(counts, dtype=np.int64, count=tab.n))])
+        return [flat[bounds[b]:bounds[b + 1]] for b in range(tab.n)]
+
     def GetResult(self, _count_only: bool = False):
         """One uint32 array per input batch, in batch order (ChunkedArray chunks, :162-166)."""
+        if self._valid.any:
+            return self._get_result_nullable(_count_only)
         tab, counts, total, t1 = self._run()
         # the reference's Run() is GetResult()->length(): the result is always pulled back
         flat = np.empty(total, dtype=np.uint32)
@@ -464,13 +601,29 @@ class SumGpu:
 
     def __init__(self, ctx: Context, batches: Sequence[Any]):
         self.ctx = ctx
-        self._cols = [_column(b, 0) for b in batches]
+        self._ncols = [_nullable_column(b, 0) for b in batches]
+        self._cols = [c.values for c in self._ncols]
+        self._valid = _ValidTable(self._ncols)
         self._timers = None
 
     def Prepare(self) -> None:
         self._timers = Timers()
 
-    def Run(self) -> int:
+    def Aggregates(self) -> dict:
+        """sum / count / min / max over the valid rows (Arrow semantics: None when no row is valid)."""
+        tab = _PtrTable(self._cols)
+        out = AggrResult()
+        t = Timings()
+        self.ctx._ck(self.ctx._lib.b2_aggr_u32_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
+                                                    tab.lens, tab.n, C.byref(out), C.byref(t)),
+                     "b2_aggr_u32_host")
+        self._timers = Timers.from_timings(t)
+        self._last = (t,)
+        return out.as_dict()
+
+    def Run(self):
+        if self._valid.any:  # nullable column: Arrow's sum skips nulls, and is null if all rows are
+            return self.Aggregates()["sum"]
         tab = _PtrTable(self._cols)
         out = C.c_uint64(0)
         t = Timings()
@@ -491,15 +644,36 @@ class TakeGpu:
         if len(batches) != len(indices_batches):
             raise ValueError("values and indices must have the same number of batches")
         self.ctx = ctx
-        self._vals = [_column(b, 0) for b in batches]
-        self._idx = [_column(b, 0) for b in indices_batches]
+        self._nvals = [_nullable_column(b, 0) for b in batches]
+        self._nidx = [_nullable_column(b, 0) for b in indices_batches]
+        self._vals = [c.values for c in self._nvals]
+        self._idx = [c.values for c in self._nidx]
+        self._vvalid, self._ivalid = _ValidTable(self._nvals), _ValidTable(self._nidx)
         self._timers = None
 
     def Prepare(self) -> None:
         self._timers = Timers()
 
+    def _run_nullable(self):
+        """Nullable values and / or indices: one pyarrow uint32 array per batch; slot j is null when
+        index j is null or the value it selects is null (cp::Take)."""
+        v, i = _PtrTable(self._vals), _PtrTable(self._idx)
+        outs = [np.empty(a.size, dtype=np.uint32) for a in self._idx]
+        bits = [np.zeros((a.size + 7) // 8, dtype=np.uint8) for a in self._idx]
+        optrs = (C.c_void_p * max(i.n, 1))(*[o.ctypes.data for o in outs])
+        bptrs = (C.c_void_p * max(i.n, 1))(*[b.ctypes.data for b in bits])
+        t = Timings()
+        self.ctx._ck(self.ctx._lib.b2_take_u32_nullable_host(
+            self.ctx._h, v.ptrs, self._vvalid.ptrs, self._vvalid.offs, v.lens, i.ptrs, self._ivalid.ptrs,
+            self._ivalid.offs, i.lens, i.n, optrs, bptrs, C.byref(t)), "b2_take_u32_nullable_host")
+        self._timers = Timers.from_timings(t)
+        self._last = (t,)
+        return [_to_arrow(o, b) for o, b in zip(outs, bits)]
+
     def Run(self):
         """One uint32 array per batch (the reference returns a Table of one chunk per batch)."""
+        if self._vvalid.any or self._ivalid.any:
+            return self._run_nullable()
         v, i = _PtrTable(self._vals), _PtrTable(self._idx)
         total = sum(a.size for a in self._idx)
         flat = np.empty(total, dtype=np.uint32)

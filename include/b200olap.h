@@ -21,8 +21,10 @@
  *   - A b2_ctx is bound to ONE GPU and is NOT thread-safe (one ctx per host thread / per rank).
  *   - Memory the library allocates is owned by the ctx / result handle and released by the
  *     matching b2_*_free / b2_ctx_destroy; callers never free() library memory.
- *   - Validity bitmaps are not supported: columns must be non-null, as the reference assumes
- *     (it passes a nullptr bitmap, host/filter/filter_dpu.cc:91).
+ *   - Columns are non-null unless an entry point says "nullable" (the reference assumes non-null:
+ *     it passes a nullptr bitmap, host/filter/filter_dpu.cc:91). Nullable entry points take Arrow
+ *     validity bitmaps: bit i = row i of the packed column, least significant bit first, pointer
+ *     4-byte aligned, buffer padded to a multiple of 4 bytes; NULL = no nulls.
  */
 #ifndef B200OLAP_H_
 #define B200OLAP_H_
@@ -114,6 +116,25 @@ int b2_sum_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint64_t* d_sum
  * plan the reference keeps commented out in host/aggr/aggr_native.cc:59-65. */
 int b2_sum_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint32_t threshold, uint64_t* d_sum,
                       uint64_t* d_count, void* stream);
+/* Aggregates over a NULLABLE column in one pass, with the semantics of Arrow's compute kernels
+ * (the reference's oracle, host/aggr/aggr_native.cc:68-73): null rows are skipped. The reference's
+ * `enum AggregatorType` only has AggrSum (shared/umq/kernels.h:22-25); min / max / count come for
+ * free with the same 4 B/row read. count == 0 means every aggregate is null (min = 0xffffffff,
+ * max = 0 then). Two kernel launches (init + reduce). */
+typedef struct b2_aggr_u32 {
+  uint64_t sum;   /* sum of the valid rows, mod 2^64 */
+  uint64_t count; /* number of valid rows */
+  uint32_t min;
+  uint32_t max;
+} b2_aggr_u32;
+int b2_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid, int64_t n,
+                    b2_aggr_u32* d_out, void* stream);
+/* Host batches in, aggregates out. valid_ptrs[b] = validity bitmap of batch b starting at bit
+ * valid_bit_offsets[b] (Arrow buffer #0 and the array's offset); valid_ptrs, valid_ptrs[b] and
+ * valid_bit_offsets may each be NULL (no nulls / offset 0). */
+int b2_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const uint8_t* const* valid_ptrs,
+                     const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
+                     b2_aggr_u32* out, b2_timings* timings);
 /* SumDpu::Run (host/aggr/aggr_dpu.cc:31-89): batches on the host, result on the host. */
 int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
                     int64_t nbatches, uint64_t* sum, b2_timings* timings);
@@ -135,6 +156,14 @@ int b2_filter_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, in
                          uint32_t threshold, uint32_t* d_out, int64_t* d_batch_end,
                          int64_t* d_total, const int64_t* d_carry_in, void* d_ws, size_t ws_bytes,
                          void* stream);
+/* Nullable column: a row is selected iff it is valid AND below the threshold — Arrow's filter drops
+ * rows whose predicate is null (the semantics of the reference's oracle, filter_native.cc:52-66;
+ * the DPU path itself has no bitmaps). d_valid: validity bitmap over the packed column (see
+ * Conventions), NULL = b2_filter_lt_u32_dev. The result has no nulls. Everything else as above. */
+int b2_filter_lt_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid,
+                                  int64_t nbatches, int64_t batch_len, uint32_t threshold,
+                                  uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
+                                  const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, void* stream);
 /* Ragged variant: batch b occupies d_in[d_batch_off[b] .. d_batch_off[b+1]) (int64 device array
  * of nbatches+1 entries; host copy h_batch_off is needed to size the launch). Empty batches ok. */
 size_t b2_filter_ragged_ws_bytes(const int64_t* h_batch_off, int64_t nbatches);
@@ -166,6 +195,13 @@ int b2_filter_lt_u32_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
                                const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
                                uint32_t* out, int64_t out_capacity, int64_t* out_counts,
                                uint64_t* total, b2_timings* timings);
+/* Nullable form of b2_filter_lt_u32_host_into (validity arguments as b2_aggr_u32_host). Batches
+ * must have equal lengths (B2_ERR_UNSUPPORTED otherwise); not chunked. */
+int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
+                                        const uint8_t* const* valid_ptrs, const int64_t* valid_bit_offsets,
+                                        const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                                        uint32_t* out, int64_t out_capacity, int64_t* out_counts,
+                                        uint64_t* total, b2_timings* timings);
 
 /* ---- Take (replaces dpu/shared/kernels/take.c:12-47) ------------------------------------- */
 /* Batch-local gather, no bounds check (take.c:36, TakeOptions::NoBoundsCheck take_native.cc:27):
@@ -173,11 +209,28 @@ int b2_filter_lt_u32_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
 int b2_take_u32_dev(b2_ctx* ctx, const uint32_t* d_values, int64_t values_len,
                     const uint32_t* d_indices, int64_t idx_len, int64_t nbatches, uint32_t* d_out,
                     void* stream);
+/* Nullable take with Arrow's semantics (cp::Take, take_native.cc:27): output j is null when index
+ * j is null or the value it selects is null. d_values_valid spans the packed values column,
+ * d_indices_valid / d_out_valid the packed index / output positions; either input bitmap may be
+ * NULL (no nulls); d_out_valid (nbatches*idx_len bits, padded to 4 bytes) may only be NULL when
+ * both are. Null slots of d_out hold 0. */
+int b2_take_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_values, const uint8_t* d_values_valid,
+                             int64_t values_len, const uint32_t* d_indices, const uint8_t* d_indices_valid,
+                             int64_t idx_len, int64_t nbatches, uint32_t* d_out, uint8_t* d_out_valid,
+                             void* stream);
 /* Ragged variant: device offset tables of nbatches+1 int64 each; processes the packed index
  * positions [idx_begin, idx_end) (0 .. idx_off[nbatches] for the whole column). */
 int b2_take_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_values, const int64_t* d_values_off,
                            const uint32_t* d_indices, const int64_t* d_idx_off, int64_t nbatches,
                            int64_t idx_begin, int64_t idx_end, uint32_t* d_out, void* stream);
+/* Nullable take over host batches of equal lengths: out_ptrs[b] (idx_lens[b] rows) and
+ * out_valid_ptrs[b] ((idx_lens[b] + 7) / 8 bytes, bit offset 0) receive batch b's result. */
+int b2_take_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* value_ptrs,
+                              const uint8_t* const* value_valid_ptrs, const int64_t* value_valid_bit_offsets,
+                              const int64_t* value_lens, const uint32_t* const* idx_ptrs,
+                              const uint8_t* const* idx_valid_ptrs, const int64_t* idx_valid_bit_offsets,
+                              const int64_t* idx_lens, int64_t nbatches, uint32_t* const* out_ptrs,
+                              uint8_t* const* out_valid_ptrs, b2_timings* timings);
 /* TakeDpu::Run (host/take/take_dpu.cc:34-104): out_ptrs[b] has capacity idx_lens[b]. */
 int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64_t* value_lens,
                      const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,

@@ -16,7 +16,8 @@ LIB = HERE / "liboracle.so"
 
 __all__ = ["build", "RandomArrayGenerator", "gen_u32", "iota_u32", "filter_lt", "sum_u32", "take",
            "wang_hash", "bucket", "partition_ids", "join", "sort_rows", "triple_checksum",
-           "make_random_batches", "make_fk_batches", "make_index_batches"]
+           "make_random_batches", "make_fk_batches", "make_index_batches",
+           "filter_lt_nullable", "aggr_nullable", "take_nullable", "pack_bits", "unpack_bits"]
 
 _lib = None
 
@@ -173,3 +174,49 @@ def sort_rows(*cols):
 def triple_checksum(a, b, c) -> int:
     a, b, c = _u32(a), _u32(b), _u32(c)
     return int(lib().orc_triple_checksum(a.ctypes.data, b.ctypes.data, c.ctypes.data, a.size))
+
+
+# ---- nullable columns -------------------------------------------------------
+# The reference's DPU kernels know no nulls (nullptr bitmap, filter_dpu.cc:91); its ORACLE does:
+# the Native classes call Arrow's filter / sum / take (filter_native.cc:52-66, aggr_native.cc:68-73,
+# take_native.cc:27), whose null handling is restated here in numpy over (values, valid) pairs,
+# valid[i] = True where row i is non-null. tests/test_oracle_nullable.py pins these against
+# pyarrow.compute (Arrow 24), the same library the reference's plans run on.
+def filter_lt_nullable(values, valid, thr: int = 1 << 30) -> np.ndarray:
+    """Acero filter(less(v, thr)): a null predicate drops the row, so the result has no nulls."""
+    v = _u32(values)
+    keep = np.asarray(valid, dtype=bool) & (v < np.uint32(thr) if thr <= 0xFFFFFFFF else np.ones(v.size, bool))
+    return v[keep].copy()
+
+
+def aggr_nullable(values, valid) -> dict:
+    """cp::Sum / Count / MinMax with default options: nulls are skipped; with no valid row every
+    aggregate but the count is null (None)."""
+    v = _u32(values)[np.asarray(valid, dtype=bool)]
+    if v.size == 0:
+        return {"sum": None, "count": 0, "min": None, "max": None}
+    return {"sum": int(v.astype(np.uint64).sum(dtype=np.uint64)), "count": int(v.size),
+            "min": int(v.min()), "max": int(v.max())}
+
+
+def take_nullable(values, values_valid, indices, indices_valid):
+    """cp::Take(values, indices): slot j is null when index j is null or values[indices[j]] is null.
+    Returns (out, out_valid); null slots of out are 0 (the CUDA kernel's convention)."""
+    v, i = _u32(values), _u32(indices)
+    vv, iv = np.asarray(values_valid, dtype=bool), np.asarray(indices_valid, dtype=bool)
+    safe = np.where(iv, i, 0).astype(np.int64)
+    ok = iv & (vv[safe] if v.size else np.zeros(i.size, bool))
+    out = np.where(ok, v[safe] if v.size else 0, 0).astype(np.uint32)
+    return out, ok
+
+
+def pack_bits(valid) -> np.ndarray:
+    """Arrow validity bitmap (LSB first) of a boolean mask, padded to a multiple of 4 bytes + 4."""
+    b = np.packbits(np.asarray(valid, dtype=bool), bitorder="little")
+    out = np.zeros((b.size + 3) // 4 * 4 + 4, dtype=np.uint8)
+    out[:b.size] = b
+    return out
+
+
+def unpack_bits(bitmap, n: int, offset: int = 0) -> np.ndarray:
+    return np.unpackbits(np.asarray(bitmap, dtype=np.uint8), bitorder="little")[offset:offset + n].astype(bool)

@@ -1,0 +1,64 @@
+"""Pins the nullable restatements in oracle/oracle.py against Arrow's own kernels (pyarrow.compute,
+Arrow 24 — the library the reference's Native classes run their plans on: filter_native.cc:52-66,
+aggr_native.cc:68-73, take_native.cc:27). CPU only."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+import oracle
+
+
+def make(rng, n, null_frac, hi=2**32):
+    v = rng.integers(0, hi, size=n, dtype=np.uint32)
+    valid = rng.random(n) >= null_frac
+    return v, valid, pa.array(v, type=pa.uint32(), mask=~valid)
+
+
+@pytest.mark.parametrize("n,null_frac", [(0, 0.0), (1, 1.0), (1, 0.0), (1000, 0.1), (4097, 0.5), (70000, 0.9),
+                                         (5000, 1.0), (5000, 0.0)])
+def test_filter_matches_arrow(n, null_frac):
+    rng = np.random.default_rng(n + int(null_frac * 100))
+    v, valid, arr = make(rng, n, null_frac)
+    for thr in (1 << 30, 0, 1, 0xFFFFFFFF):
+        exp = pc.filter(arr, pc.less(arr, pa.scalar(thr, pa.uint32())))  # null predicate drops the row
+        assert exp.null_count == 0
+        got = oracle.filter_lt_nullable(v, valid, thr)
+        assert np.array_equal(got, exp.to_numpy(zero_copy_only=False).astype(np.uint32))
+
+
+@pytest.mark.parametrize("n,null_frac", [(0, 0.0), (7, 1.0), (1, 0.0), (1000, 0.1), (65536, 0.5), (70001, 0.99)])
+def test_aggregates_match_arrow(n, null_frac):
+    rng = np.random.default_rng(100 + n)
+    v, valid, arr = make(rng, n, null_frac)
+    got = oracle.aggr_nullable(v, valid)
+    assert got["sum"] == pc.sum(arr.cast(pa.uint64()) if n else arr).as_py()
+    assert got["count"] == pc.count(arr).as_py()
+    mm = pc.min_max(arr)
+    assert got["min"] == mm["min"].as_py() and got["max"] == mm["max"].as_py()
+
+
+@pytest.mark.parametrize("nv,ni,fv,fi", [(1, 0, 0.0, 0.0), (10, 30, 0.3, 0.3), (4096, 1000, 0.0, 0.5),
+                                          (4096, 5000, 0.5, 0.0), (100, 100, 1.0, 0.0), (100, 100, 0.0, 1.0)])
+def test_take_matches_arrow(nv, ni, fv, fi):
+    rng = np.random.default_rng(nv * 3 + ni)
+    v, vvalid, varr = make(rng, nv, fv)
+    i, ivalid, iarr = make(rng, ni, fi, hi=nv)
+    exp = pc.take(varr, iarr)
+    out, ok = oracle.take_nullable(v, vvalid, i, ivalid)
+    assert np.array_equal(ok, ~np.asarray(exp.is_null()))
+    assert np.array_equal(out[ok], exp.drop_null().to_numpy().astype(np.uint32))
+    assert not out[~ok].any()
+
+
+def test_bitmap_round_trip_and_arrow_layout():
+    rng = np.random.default_rng(9)
+    valid = rng.random(1003) > 0.4
+    bits = oracle.pack_bits(valid)
+    assert bits.size % 4 == 0 and np.array_equal(oracle.unpack_bits(bits, valid.size), valid)
+    arr = pa.array(np.arange(1003, dtype=np.uint32), mask=~valid)
+    arrow_bits = np.frombuffer(arr.buffers()[0], dtype=np.uint8)
+    assert np.array_equal(oracle.unpack_bits(arrow_bits, valid.size), valid)  # same bit order as Arrow
+    sl = arr.slice(5, 900)  # a sliced array keeps the buffer and carries a bit offset
+    assert np.array_equal(oracle.unpack_bits(np.frombuffer(sl.buffers()[0], dtype=np.uint8), 900, sl.offset),
+                          valid[5:905])
