@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — rows/s of the columnar operator hot path at SF=2048 on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--sf 2048] [--ops filter,sum,take,join]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--sf 2048] [--ops filter,sweep,sum,take,join,nullable]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference      # the reference's Arrow Acero CPU path on the host cores
 
@@ -47,7 +47,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--sf", type=int, default=int(os.environ.get("SF", 2048)))
-    p.add_argument("--ops", default="filter,sweep,sum,take,join")
+    p.add_argument("--ops", default="filter,sweep,sum,take,join,nullable")
     p.add_argument("--e2e-sf", type=int, default=int(os.environ.get("E2E_SF", 64)),
                    help="scale factor of the host-buffer (e2e) leg; bounded by host RAM and PCIe time")
     p.add_argument("--cpu-sf", type=int, default=int(os.environ.get("CPU_SF", 64)),
@@ -308,6 +308,100 @@ def bench_take(ctx, D, args):
             # window is touched (profiles/r1_sum_take.md), so the window itself is the traffic
             "window_gbs": (4 * nb_total * TAKE_BATCH + 8 * nidx) / D.world / (ms * 1e-3) / 1e9,
             "reference_convention_rows_per_s": nb_total * TAKE_BATCH / (ms * 1e-3)}
+
+
+def bench_nullable(ctx, D, args):
+    """The nullable variants on resident columns with 12.5 % nulls: filter
+    (valid AND v < 2^30), one-pass aggregates, take with nullable values and indices. Bounded at
+    SF=256 so the default run stays short; every result is checked against torch on the device."""
+    import torch
+    from dpu_olap_b200.generator import RandomArrayGenerator
+    from dpu_olap_b200.ops import decode_aggr
+    sf = min(args.sf, 256)
+    nb_total = sf << 7
+    first, nb = shard(nb_total, D)
+    g = RandomArrayGenerator(ctx, 42)
+    col = g.batches_dev(nb_total, FILTER_BATCH, take=(first, nb))
+    n = nb * FILTER_BATCH
+
+    def random_bitmap(bits: int, seed: int):
+        gen = torch.Generator(device="cuda").manual_seed(seed + D.rank)
+        nbytes = (bits + 31) // 32 * 4 + 4
+        b = torch.randint(0, 256, (3, nbytes), dtype=torch.uint8, device="cuda", generator=gen)
+        return b[0] | b[1] | b[2]  # a bit is set with probability 7/8
+
+    def expand(bitmap, lo: int, hi: int):  # rows [lo, hi) of the bitmap as bool, lo % 8 == 0
+        by = bitmap[lo // 8:(hi + 7) // 8]
+        sh = torch.arange(8, dtype=torch.uint8, device="cuda")
+        return ((by[:, None] >> sh) & 1).bool().reshape(-1)[: hi - lo]
+
+    valid = random_bitmap(n, 1)
+    res = {"sf": sf, "null_fraction": 0.125}
+    # ---- filter ----
+    thr = 1 << 30
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    end = torch.empty(nb, dtype=torch.int64, device="cuda")
+    total = torch.empty(1, dtype=torch.int64, device="cuda")
+    ws = torch.empty(ctx.filter_ws_bytes(nb, FILTER_BATCH), dtype=torch.uint8, device="cuda")
+    def fstep():
+        ctx.filter_nullable_dev(col, valid, nb, FILTER_BATCH, thr, out=out, batch_end=end, total=total, ws=ws)
+    ms = timed_steps(D, fstep, args.steps, args.warmup)
+    sel_local = int(total.cpu()[0])
+    flip = torch.tensor(-2**31, dtype=torch.int32, device="cuda")
+    cnt, vsum, vcnt = 0, 0, 0
+    step_rows = 1 << 26
+    for lo in range(0, n, step_rows):
+        hi = min(n, lo + step_rows)
+        c, bits = col[lo:hi], expand(valid, lo, hi)
+        cnt += int((((c ^ flip) < (thr - 2**31)) & bits).sum())
+        vsum += int(((c.to(torch.int64) & 0xFFFFFFFF) * bits).sum())
+        vcnt += int(bits.sum())
+    if cnt != sel_local:
+        raise SystemExit(f"nullable filter self-check failed on rank {D.rank}: {cnt} vs {sel_local}")
+    sel = D.sum_int(sel_local)
+    rows = nb_total * FILTER_BATCH
+    fbytes = (4 + 1 / 8) * rows + 4 * sel
+    res["filter"] = {"ms_per_step": ms, "rows": rows, "selected": sel, "rows_per_s": rows / (ms * 1e-3),
+                     "algorithmic_bytes_per_row": fbytes / rows,
+                     "achieved_gbs": fbytes / D.world / (ms * 1e-3) / 1e9}
+    del out, end, total, ws
+    # ---- aggregates ----
+    aout = torch.empty(3, dtype=torch.int64, device="cuda")
+    ms = timed_steps(D, lambda: ctx.aggr_dev(col, valid, out=aout), args.steps, args.warmup)
+    agg = decode_aggr(aout)
+    if agg["sum"] != vsum % (1 << 64) or agg["count"] != vcnt:
+        raise SystemExit(f"nullable aggregate self-check failed on rank {D.rank}")
+    res["aggregates"] = {"ms_per_step": ms, "rows": rows, "rows_per_s": rows / (ms * 1e-3),
+                         "algorithmic_bytes_per_row": 4 + 1 / 8,
+                         "achieved_gbs": (4 + 1 / 8) * rows / D.world / (ms * 1e-3) / 1e9,
+                         "result_rank0": agg}
+    del col, valid
+    free_all()
+    # ---- take ----
+    if sf >= D.world:
+        first, nbt = shard(sf, D)
+        vals = g.batches_dev(sf, TAKE_BATCH, take=(first, nbt))
+        idx = g.batches_dev(sf, TAKE_IDX, 0, TAKE_BATCH - 1, take=(first, nbt))
+        vvalid, ivalid = random_bitmap(nbt * TAKE_BATCH, 2), random_bitmap(nbt * TAKE_IDX, 3)
+        tout = torch.empty(nbt * TAKE_IDX, dtype=torch.int32, device="cuda")
+        tbits = torch.zeros(nbt * TAKE_IDX // 8 + 8, dtype=torch.uint8, device="cuda")
+        ms = timed_steps(D, lambda: ctx.take_nullable_dev(vals, vvalid, TAKE_BATCH, idx, ivalid, TAKE_IDX, nbt,
+                                                          out=tout, out_valid=tbits), args.steps, args.warmup)
+        b = nbt // 2
+        ii = idx[b * TAKE_IDX:(b + 1) * TAKE_IDX].to(torch.int64)
+        ok = expand(ivalid, b * TAKE_IDX, (b + 1) * TAKE_IDX) & \
+            expand(vvalid, b * TAKE_BATCH, (b + 1) * TAKE_BATCH)[ii]
+        ref = torch.where(ok, vals[b * TAKE_BATCH:(b + 1) * TAKE_BATCH][ii], torch.zeros_like(ii, dtype=torch.int32))
+        if not (torch.equal(ref, tout[b * TAKE_IDX:(b + 1) * TAKE_IDX]) and
+                torch.equal(ok, expand(tbits, b * TAKE_IDX, (b + 1) * TAKE_IDX))):
+            raise SystemExit(f"nullable take self-check failed on rank {D.rank}")
+        nidx = sf * TAKE_IDX
+        res["take"] = {"ms_per_step": ms, "indices": nidx, "rows_per_s": nidx / (ms * 1e-3),
+                       "algorithmic_bytes_per_index": 12 + 3 / 8,
+                       "achieved_gbs": (12 + 3 / 8) * nidx / D.world / (ms * 1e-3) / 1e9}
+        del vals, idx, vvalid, ivalid, tout, tbits
+        free_all()
+    return res
 
 
 def bench_join(ctx, D, args):
@@ -656,6 +750,8 @@ def main():
         extra["take"] = bench_take(ctx, D, args)
     if "join" in ops:
         extra["join"] = bench_join(ctx, D, args)
+    if "nullable" in ops:
+        extra["nullable"] = bench_nullable(ctx, D, args)
     e2e = None
     if not args.no_e2e:
         e2e = bench_e2e_filter(ctx, D, args)

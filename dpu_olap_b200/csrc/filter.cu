@@ -87,13 +87,17 @@ struct FilterCfg {
   static constexpr int kStageBytes = kTile * 4;
   // dynamic shared memory: stages | per-stage info | barriers | warp totals
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  // nullable variant: + one tile of validity bits per stage, filled by the same TMA producer
+  static constexpr int kValidBytes = kTile / 8;
+  static constexpr int kSmemBytesNullable = kSmemBytes + kStages * kValidBytes;
 };
 
 struct StageInfo {  // written by the producer before it completes full[s]
   int64_t tile;     // -1: no more tiles
   int64_t row0;
   int32_t len;
-  int32_t tma;      // 1: the rows are in the stage buffer; 0: compute warps load them from global
+  int32_t tma;      // bit 0: the rows are in the stage buffer (else compute warps load them from
+                    // global); bit 1 (nullable): so are the tile's validity bits
 };
 
 constexpr int kMaxStages = 8;
@@ -129,6 +133,7 @@ filter_lt_u32_kernel(const FilterArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint32_t* const bufs = reinterpret_cast<uint32_t*>(smem_raw);
   FilterSmemCtl& ctl = *reinterpret_cast<FilterSmemCtl*>(smem_raw + kS * Cfg::kStageBytes);
+  uint32_t* const vbufs = reinterpret_cast<uint32_t*>(smem_raw + Cfg::kSmemBytes);  // kNullable only
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -178,11 +183,17 @@ filter_lt_u32_kernel(const FilterArgs a) {
         si.tile = tile;
         si.row0 = row0;
         si.len = len;
-        si.tma = tma ? 1 : 0;
+        // the tile's 512 bytes of validity ride along when they start on a 16-byte boundary
+        const bool vtma = kNullable && tma && len == kTile && (row0 & 127) == 0 &&
+                          (reinterpret_cast<uintptr_t>(a.valid) & 15) == 0;
+        si.tma = (tma ? 1 : 0) | (vtma ? 2 : 0);
         if (tma) {
           fence_proxy_async();  // the stage was last touched through the generic proxy
-          mbar_arrive_expect_tx(&ctl.full[s], (uint32_t)len * 4u);
+          mbar_arrive_expect_tx(&ctl.full[s], (uint32_t)len * 4u + (vtma ? (uint32_t)Cfg::kValidBytes : 0u));
           tma_load_1d(bufs + (size_t)s * kTile, src, (uint32_t)len * 4u, &ctl.full[s], policy);
+          if (vtma)
+            tma_load_1d(vbufs + (size_t)s * (Cfg::kValidBytes / 4), a.valid + (row0 >> 5), Cfg::kValidBytes,
+                        &ctl.full[s], policy);
         } else {
           mbar_arrive(&ctl.full[s]);
         }
@@ -260,12 +271,18 @@ filter_lt_u32_kernel(const FilterArgs a) {
     uint32_t cnt = 0;  // four 8-bit counters: matches of this lane in segment j at bits 8j..8j+7
     const uint32_t e0 = warp * 512 + lane * 4;  // + j*128 + e
     if (valid) {
-      if (si.tma && si.len == kTile && (!kNullable || (si.row0 & 31) == 0)) {
+      if ((si.tma & 1) && si.len == kTile && (!kNullable || (si.row0 & 31) == 0)) {
         uint32_t vw[kVecPerThread];  // validity of this lane's rows: a nibble of one word per segment
         if (kNullable) {
-          const uint32_t* __restrict__ wp = a.valid + (si.row0 >> 5) + warp * 16 + (lane >> 3);
+          if (si.tma & 2) {
+            const uint32_t* wp = vbufs + (size_t)s * (Cfg::kValidBytes / 4) + warp * 16 + (lane >> 3);
 #pragma unroll
-          for (int j = 0; j < kVecPerThread; ++j) vw[j] = __ldg(wp + j * 4) >> ((lane & 7) * 4);
+            for (int j = 0; j < kVecPerThread; ++j) vw[j] = wp[j * 4] >> ((lane & 7) * 4);
+          } else {
+            const uint32_t* __restrict__ wp = a.valid + (si.row0 >> 5) + warp * 16 + (lane >> 3);
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) vw[j] = __ldg(wp + j * 4) >> ((lane & 7) * 4);
+          }
         }
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
@@ -295,7 +312,7 @@ filter_lt_u32_kernel(const FilterArgs a) {
             // rows past the end of the tile never match (0xffffffff < thr is false for every thr)
             v[j][e] = 0xffffffffu;
             if ((int32_t)i < si.len) {
-              v[j][e] = si.tma ? buf[i] : ld_stream_u32(src + i);
+              v[j][e] = (si.tma & 1) ? buf[i] : ld_stream_u32(src + i);
               if (kNullable) {
                 const int64_t r = si.row0 + i;
                 if (!((__ldg(a.valid + (r >> 5)) >> (r & 31)) & 1u)) v[j][e] = 0xffffffffu;
@@ -439,19 +456,20 @@ static inline int64_t tiles_of(int64_t len) { return (len + kTileRows - 1) / kTi
 
 template <typename Cfg, bool kNullable = false>
 int launch_variant(b2_ctx* ctx, const FilterArgs& a, cudaStream_t s) {
+  constexpr int kSmem = kNullable ? Cfg::kSmemBytesNullable : Cfg::kSmemBytes;
   static int max_ctas = 0;  // per process; every B200 is the same
   if (max_ctas == 0) {
     B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg, kNullable>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int per_sm = 0;
     B2_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                        &per_sm, filter_lt_u32_kernel<Cfg, kNullable>, Cfg::kThreads, Cfg::kSmemBytes));
+                        &per_sm, filter_lt_u32_kernel<Cfg, kNullable>, Cfg::kThreads, kSmem));
     if (per_sm < 1) return b2_set_error(ctx, B2_ERR_CUDA, "filter kernel", "does not fit an SM");
     if (per_sm > Cfg::kCtasPerSm) per_sm = Cfg::kCtasPerSm;
     max_ctas = per_sm * ctx->sm_count;
   }
   const int64_t grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
-  filter_lt_u32_kernel<Cfg, kNullable><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(a);
+  filter_lt_u32_kernel<Cfg, kNullable><<<(unsigned)grid, Cfg::kThreads, kSmem, s>>>(a);
   B2_LAUNCH_CHECK(ctx, "filter_lt_u32_kernel");
   return B2_OK;
 }

@@ -280,37 +280,45 @@ class Context:
                  "b2_filter_lt_u32_dev")
         return out, batch_end, total
 
-    def filter_nullable_dev(self, col, valid, nbatches: int, batch_len: int, threshold: int):
+    def filter_nullable_dev(self, col, valid, nbatches: int, batch_len: int, threshold: int, out=None,
+                            batch_end=None, total=None, ws=None):
         """Nullable filter: `valid` is the packed validity bitmap (uint8 device tensor, padded to 4
         bytes) or None. Returns (out, batch_end, total) device tensors."""
         import torch
         dev = col.device
-        out = torch.empty(max(nbatches * batch_len, 1), dtype=torch.int32, device=dev)
-        batch_end = torch.empty(max(nbatches, 1), dtype=torch.int64, device=dev)
-        total = torch.empty(1, dtype=torch.int64, device=dev)
-        ws = torch.empty(self.filter_ws_bytes(nbatches, batch_len), dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty(max(nbatches * batch_len, 1), dtype=torch.int32, device=dev)
+        if batch_end is None:
+            batch_end = torch.empty(max(nbatches, 1), dtype=torch.int64, device=dev)
+        if total is None:
+            total = torch.empty(1, dtype=torch.int64, device=dev)
+        if ws is None:
+            ws = torch.empty(self.filter_ws_bytes(nbatches, batch_len), dtype=torch.uint8, device=dev)
         self._ck(self._lib.b2_filter_lt_u32_nullable_dev(self._h, _dptr(col), _dptr(valid), nbatches, batch_len,
                                                          threshold, _dptr(out), _dptr(batch_end), _dptr(total),
                                                          0, _dptr(ws), ws.numel(), self._stream()),
                  "b2_filter_lt_u32_nullable_dev")
         return out, batch_end, total
 
-    def aggr_dev(self, col, valid=None):
+    def aggr_dev(self, col, valid=None, out=None):
         """sum / count / min / max of the valid rows in one pass; returns a 3 x int64 device tensor
         laid out as b2_aggr_u32 (decode with :func:`decode_aggr`)."""
         import torch
-        out = torch.empty(3, dtype=torch.int64, device=col.device)
+        if out is None:
+            out = torch.empty(3, dtype=torch.int64, device=col.device)
         self._ck(self._lib.b2_aggr_u32_dev(self._h, _dptr(col), _dptr(valid), col.numel(), _dptr(out),
                                            self._stream()), "b2_aggr_u32_dev")
         return out
 
     def take_nullable_dev(self, values, values_valid, values_len: int, indices, indices_valid, idx_len: int,
-                          nbatches: int):
+                          nbatches: int, out=None, out_valid=None):
         """Returns (out, out_valid bitmap as uint8 device tensor)."""
         import torch
         n = nbatches * idx_len
-        out = torch.empty(max(n, 1), dtype=torch.int32, device=values.device)
-        out_valid = torch.zeros(((n + 31) // 32) * 4 + 4, dtype=torch.uint8, device=values.device)
+        if out is None:
+            out = torch.empty(max(n, 1), dtype=torch.int32, device=values.device)
+        if out_valid is None:
+            out_valid = torch.zeros(((n + 31) // 32) * 4 + 4, dtype=torch.uint8, device=values.device)
         self._ck(self._lib.b2_take_u32_nullable_dev(self._h, _dptr(values), _dptr(values_valid), values_len,
                                                     _dptr(indices), _dptr(indices_valid), idx_len, nbatches,
                                                     _dptr(out), _dptr(out_valid), self._stream()),
