@@ -149,6 +149,68 @@ static void TakeLargeTest(gpu::GpuSet& sys) {  // take_test.cc:48-72
   EXPECT_TRUE(n.Run().ValueOrDie()->Equals(*g.Run().ValueOrDie()));
 }
 
+// ---- nullable columns: the Gpu operators against the Native (Arrow) ones ------
+// Batches of `rows` uint32 with every `null_every`-th row null; slice_off > 0 slices them so the
+// validity bitmap carries a bit offset.
+static arrow::RecordBatchVector NullableBatches(const char* name, int nb, int rows, int null_every,
+                                                uint32_t max_value, int slice_off, uint32_t seed) {
+  arrow::RecordBatchVector out;
+  auto schema = arrow::schema({arrow::field(name, arrow::uint32(), /*nullable=*/true)});
+  uint32_t x = seed;
+  for (int b = 0; b < nb; ++b) {
+    arrow::UInt32Builder bld;
+    for (int r = 0; r < rows + slice_off; ++r) {
+      x = x * 1664525u + 1013904223u;
+      if (null_every > 0 && (x >> 8) % null_every == 0) (void)bld.AppendNull();
+      else (void)bld.Append(max_value == 0xffffffffu ? x : (x >> 4) % (max_value + 1));
+    }
+    auto arr = bld.Finish().ValueOrDie()->Slice(slice_off, rows);
+    out.push_back(arrow::RecordBatch::Make(schema, rows, {arr}));
+  }
+  return out;
+}
+static void FilterNullableTest(gpu::GpuSet& sys) {
+  for (int slice_off : {0, 5}) {
+    auto batches = NullableBatches("v", 6, 8192, 3, 0xffffffffu, slice_off, 7);
+    filter::FilterGpu g{sys, batches};
+    EXPECT_TRUE(g.Prepare().ok());
+    auto gr = g.GetResult().ValueOrDie();
+    filter::FilterNative n{batches[0]->schema(), batches};
+    auto nr = n.GetResult().ValueOrDie()->column(0);
+    EXPECT_TRUE(gr->Equals(nr));
+    EXPECT_EQ(gr->null_count(), 0);
+    EXPECT_TRUE(gr->length() > 0 && gr->length() < 6 * 8192);
+  }
+}
+static void SumNullableTest(gpu::GpuSet& sys) {
+  auto batches = NullableBatches("v", 5, 50000, 4, 0xffffffffu, 3, 11);
+  aggr::SumGpu g{sys, batches};
+  EXPECT_TRUE(g.Prepare().ok());
+  aggr::SumNative n{batches[0]->schema(), batches};
+  EXPECT_EQ(g.Run().ValueOrDie(), n.Run().ValueOrDie());
+  auto table = arrow::Table::FromRecordBatches(batches).ValueOrDie();
+  auto mm = arrow::compute::MinMax(table->column(0)).ValueOrDie().scalar_as<arrow::StructScalar>();
+  const b2_aggr_u32 a = g.Aggregates().ValueOrDie();
+  EXPECT_EQ(a.count, (uint64_t)(table->num_rows() - table->column(0)->null_count()));
+  EXPECT_EQ(a.min, std::static_pointer_cast<arrow::UInt32Scalar>(mm.value[0])->value);
+  EXPECT_EQ(a.max, std::static_pointer_cast<arrow::UInt32Scalar>(mm.value[1])->value);
+}
+static void TakeNullableTest(gpu::GpuSet& sys) {
+  auto values = NullableBatches("v", 4, 4096, 3, 0xffffffffu, 2, 13);
+  auto indices = NullableBatches("i", 4, 1000, 5, 4095, 1, 17);
+  take::TakeGpu g{sys, values, indices};
+  EXPECT_TRUE(g.Prepare().ok());
+  auto gt = g.Run().ValueOrDie();
+  take::TakeNative n{values[0]->schema(), values, indices};
+  auto nt = n.Run().ValueOrDie();
+  EXPECT_TRUE(gt->column(0)->Equals(nt->column(0)));
+  EXPECT_TRUE(gt->column(0)->null_count() > 0);
+  // the join has no null semantics here: rejected loudly
+  auto l = NullableBatches("fk", 1, 10, 2, 100, 0, 1);
+  join::JoinGpu j{sys, l[0]->schema(), l[0]->schema(), l, l};
+  EXPECT_TRUE(!j.Run().ok());
+}
+
 // ---- JoinTest ---------------------------------------------------------------------------------------
 static void JoinSimpleTest(gpu::GpuSet& sys) {  // join_test.cc:40-80
   arrow::RecordBatchVector left = {
@@ -284,7 +346,9 @@ int main(int argc, char** argv) {
       {"FilterTest.LongerTest", FilterLongerTest}, {"FilterTest.PinnedGather", FilterPinnedGatherTest},
       {"SumTest.SimpleTest", SumSimpleTest},
       {"SumTest.LargeTest", SumLargeTest},         {"TakeTest.SimpleTest", TakeSimpleTest},
-      {"TakeTest.LargeTest", TakeLargeTest},       {"JoinTest.SimpleTest", JoinSimpleTest},
+      {"TakeTest.LargeTest", TakeLargeTest},       {"FilterTest.Nullable", FilterNullableTest},
+      {"SumTest.Nullable", SumNullableTest},       {"TakeTest.Nullable", TakeNullableTest},
+      {"JoinTest.SimpleTest", JoinSimpleTest},
       {"JoinTest.LargeTest", JoinLargeTest},       {"PartitionTest.SimpleTest", PartitionSimpleTest},
       {"PartitionTest.LargeTest", PartitionLargeTest}};
   int bad = 0;

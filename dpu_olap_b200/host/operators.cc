@@ -10,24 +10,34 @@
 namespace upmemeval {
 namespace {
 
-arrow::Result<const uint32_t*> U32Values(const std::shared_ptr<arrow::Array>& col) {
+arrow::Result<const uint32_t*> U32Values(const std::shared_ptr<arrow::Array>& col, bool allow_nulls) {
   if (col->type_id() != arrow::Type::UINT32)
     return arrow::Status::TypeError("expected a uint32 column, got ", col->type()->ToString());
-  if (col->null_count() != 0)
-    return arrow::Status::NotImplemented("nullable columns are not supported (the reference passes "
-                                         "a nullptr validity bitmap, filter_dpu.cc:91)");
+  if (!allow_nulls && col->null_count() != 0)
+    return arrow::Status::NotImplemented("join and partition columns must be non-null (the reference "
+                                         "passes a nullptr validity bitmap, filter_dpu.cc:91)");
   return col->data()->GetValues<uint32_t>(1);
 }
 
+// Per-batch data pointers and lengths; with allow_nulls also the validity bitmaps (buffer #0) and
+// their bit offsets (the array's offset), which the nullable entry points take.
 struct ColumnPtrs {
   std::vector<const uint32_t*> ptrs;
   std::vector<int64_t> lens;
-  arrow::Status Append(const arrow::RecordBatchVector& batches, int column) {
+  std::vector<const uint8_t*> valid;
+  std::vector<int64_t> valid_off;
+  bool has_nulls = false;
+  arrow::Status Append(const arrow::RecordBatchVector& batches, int column, bool allow_nulls = false) {
     for (const auto& b : batches) {
       if (column < 0 || column >= b->num_columns()) return arrow::Status::Invalid("no such column");
-      ARROW_ASSIGN_OR_RAISE(const uint32_t* p, U32Values(b->column(column)));
+      const auto& col = b->column(column);
+      ARROW_ASSIGN_OR_RAISE(const uint32_t* p, U32Values(col, allow_nulls));
       ptrs.push_back(p);
       lens.push_back(b->num_rows());
+      const bool nulls = col->null_count() != 0;
+      valid.push_back(nulls ? col->null_bitmap_data() : nullptr);
+      valid_off.push_back(nulls ? col->offset() : 0);
+      has_nulls = has_nulls || nulls;
     }
     return arrow::Status::OK();
   }
@@ -55,7 +65,7 @@ arrow::Result<std::shared_ptr<arrow::ChunkedArray>> FilterGpu::GetResult() {
   b2_ctx* ctx = system_.ctx();
   if (!timers_) timers_ = std::make_shared<timer::Timers>();
   ColumnPtrs in;
-  ARROW_RETURN_NOT_OK(in.Append(batches_, 0));
+  ARROW_RETURN_NOT_OK(in.Append(batches_, 0, /*allow_nulls=*/true));
   const int64_t nb = static_cast<int64_t>(in.ptrs.size());
   int64_t rows = 0;
   for (int64_t l : in.lens) rows += l;
@@ -66,10 +76,15 @@ arrow::Result<std::shared_ptr<arrow::ChunkedArray>> FilterGpu::GetResult() {
   std::vector<int64_t> counts(nb > 0 ? nb : 1);
   uint64_t total = 0;
   b2_timings t{};
-  B2_ARROW_RETURN_NOT_OK(
-      ctx, b2_filter_lt_u32_host_into(ctx, in.ptrs.data(), in.lens.data(), nb, threshold_,
-                                      reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(slab->data())), rows,
-                                      counts.data(), &total, &t));
+  uint32_t* out = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(slab->data()));
+  if (in.has_nulls) {  // Acero drops rows whose predicate is null: the result itself has no nulls
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_u32_nullable_host_into(
+                                    ctx, in.ptrs.data(), in.valid.data(), in.valid_off.data(), in.lens.data(),
+                                    nb, threshold_, out, rows, counts.data(), &total, &t));
+  } else {
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_u32_host_into(ctx, in.ptrs.data(), in.lens.data(), nb, threshold_,
+                                                           out, rows, counts.data(), &total, &t));
+  }
   arrow::ArrayVector chunks;
   int64_t off = 0;
   for (int64_t b = 0; b < nb; ++b) {
@@ -96,11 +111,28 @@ arrow::Status SumGpu::Prepare() {
   return arrow::Status::OK();
 }
 
+arrow::Result<b2_aggr_u32> SumGpu::Aggregates() {
+  b2_ctx* ctx = system_.ctx();
+  if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  ColumnPtrs in;
+  ARROW_RETURN_NOT_OK(in.Append(batches_, 0, /*allow_nulls=*/true));
+  b2_aggr_u32 out{};
+  b2_timings t{};
+  B2_ARROW_RETURN_NOT_OK(ctx, b2_aggr_u32_host(ctx, in.ptrs.data(), in.valid.data(), in.valid_off.data(),
+                                               in.lens.data(), static_cast<int64_t>(in.ptrs.size()), &out, &t));
+  timers_->Add(t);
+  return out;
+}
+
 arrow::Result<uint64_t> SumGpu::Run() {
   b2_ctx* ctx = system_.ctx();
   if (!timers_) timers_ = std::make_shared<timer::Timers>();
   ColumnPtrs in;
-  ARROW_RETURN_NOT_OK(in.Append(batches_, 0));
+  ARROW_RETURN_NOT_OK(in.Append(batches_, 0, /*allow_nulls=*/true));
+  if (in.has_nulls) {  // cp::Sum skips nulls; the uint64 result of no valid row is 0 here (Arrow: null)
+    ARROW_ASSIGN_OR_RAISE(b2_aggr_u32 a, Aggregates());
+    return a.sum;
+  }
   uint64_t sum = 0;
   b2_timings t{};
   B2_ARROW_RETURN_NOT_OK(ctx, b2_sum_u32_host(ctx, in.ptrs.data(), in.lens.data(),
@@ -126,8 +158,8 @@ arrow::Result<std::shared_ptr<arrow::Table>> TakeGpu::Run() {
     return arrow::Status::Invalid("values and indices must have the same number of batches");
   if (batches_.empty()) return arrow::Status::Invalid("no batches");
   ColumnPtrs v, i;
-  ARROW_RETURN_NOT_OK(v.Append(batches_, 0));
-  ARROW_RETURN_NOT_OK(i.Append(indices_batches_, 0));
+  ARROW_RETURN_NOT_OK(v.Append(batches_, 0, /*allow_nulls=*/true));
+  ARROW_RETURN_NOT_OK(i.Append(indices_batches_, 0, /*allow_nulls=*/true));
   const int64_t nb = static_cast<int64_t>(v.ptrs.size());
   std::vector<uint32_t*> outs(nb);
   arrow::RecordBatchVector result;
@@ -136,6 +168,33 @@ arrow::Result<std::shared_ptr<arrow::Table>> TakeGpu::Run() {
   for (int64_t l : i.lens) total += l;
   ARROW_ASSIGN_OR_RAISE(auto slab, system_.pinned().Acquire(std::max<int64_t>(total, 1) * 4));
   int64_t off = 0;
+  if (v.has_nulls || i.has_nulls) {
+    // cp::Take semantics: slot j is null when index j is null or the value it selects is null; one
+    // result batch per input batch over the slab, each with its own validity bitmap
+    std::vector<uint8_t*> out_valid(nb);
+    std::vector<std::shared_ptr<arrow::Buffer>> bitmaps(nb);
+    for (int64_t b = 0; b < nb; ++b) {
+      outs[b] = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(slab->data())) + off;
+      ARROW_ASSIGN_OR_RAISE(bitmaps[b], arrow::AllocateBitmap(std::max<int64_t>(i.lens[b], 1)));
+      out_valid[b] = bitmaps[b]->mutable_data();
+      off += i.lens[b];
+    }
+    b2_timings t{};
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_take_u32_nullable_host(ctx, v.ptrs.data(), v.valid.data(), v.valid_off.data(),
+                                                          v.lens.data(), i.ptrs.data(), i.valid.data(),
+                                                          i.valid_off.data(), i.lens.data(), nb, outs.data(),
+                                                          out_valid.data(), &t));
+    timers_->Add(t);
+    auto out_schema = arrow::schema({schema->field(0)->WithNullable(true)});
+    off = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+      auto arr = std::make_shared<arrow::UInt32Array>(i.lens[b], arrow::SliceBuffer(slab, off * 4, i.lens[b] * 4),
+                                                      bitmaps[b], arrow::kUnknownNullCount);
+      result.push_back(arrow::RecordBatch::Make(out_schema, i.lens[b], {std::move(arr)}));
+      off += i.lens[b];
+    }
+    return arrow::Table::FromRecordBatches(out_schema, result);
+  }
   for (int64_t b = 0; b < nb; ++b) {  // one result batch per input batch: zero-copy slices of the slab
     outs[b] = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(slab->data())) + off;
     auto arr = std::make_shared<arrow::UInt32Array>(i.lens[b], arrow::SliceBuffer(slab, off * 4, i.lens[b] * 4));

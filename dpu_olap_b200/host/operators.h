@@ -2,7 +2,9 @@
 // *Dpu operator classes with the same constructor arguments and Prepare() / Run() / Timers()
 // signatures (host/filter/filter_dpu.h:14-29, host/aggr/aggr_dpu.h:14-27,
 // host/take/take_dpu.h:14-29, host/join/join_dpu.h:14-48, host/partition/partition_dpu.h:13-38),
-// over libb200olap.so instead of dpu::DpuSet.
+// over libb200olap.so instead of dpu::DpuSet. Filter, Sum and Take also accept columns with nulls
+// (Arrow's semantics, i.e. what the reference's *Native classes compute); join and partition keys
+// must be non-null.
 #pragma once
 #include <arrow/api.h>
 
@@ -38,6 +40,9 @@ class SumGpu {
       : system_(system), batches_(std::move(batches)) {}
   arrow::Status Prepare();
   arrow::Result<uint64_t> Run();
+  // sum / count / min / max of the valid rows in one pass (nullable columns welcome; the reference's
+  // enum AggregatorType only has AggrSum, shared/umq/kernels.h:22-25)
+  arrow::Result<b2_aggr_u32> Aggregates();
   std::shared_ptr<timer::Timers> Timers() { return timers_; }
 
  private:
