@@ -39,12 +39,11 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kBucketBits = 11;
 constexpr int kBuckets = 1 << kBucketBits;     // 2048 buckets of 4 keys: one 128-bit read each
 constexpr int kSlots = kBuckets * 4;           // 8192 slots = 32 KB keys + 32 KB values
+constexpr int kTableBytes = (2 * kSlots + kBuckets) * 4;  // keys | values | per-bucket arrival counts
 constexpr int kMaxBuild = (kSlots * 3) / 4;    // rows per build chunk (load factor <= 0.75)
 constexpr int kTargetBuild = 4096;             // mean build rows per partition
 constexpr int kItems = 9;                      // rows per thread per round (build and probe)
 constexpr int kRound = kThreads * kItems;      // 4608 rows: mean partition + 8 sigma in one round
-constexpr int kSegs = kWarps * kItems;         // (item, warp) match counts per probe round
-constexpr int kSegsPerLane = (kSegs + 31) / 32;
 constexpr int kProbeCtasPerSm = 2;             // 3 CTAs/SM (40 registers, spills) measured 5 % slower
 
 struct JoinState {  // lives in the workspace header
@@ -58,12 +57,17 @@ struct JoinState {  // lives in the workspace header
 __device__ __forceinline__ uint32_t bucket_hash(uint32_t key) {
   return (key * 0x9E3779B1u) >> (32 - kBucketBits);
 }
+// Second candidate bucket (two-choice placement): another odd multiplier.
+__device__ __forceinline__ uint32_t bucket_hash2(uint32_t key) {
+  return (key * 0x85EBCA6Bu) >> (32 - kBucketBits);
+}
 
-__device__ __forceinline__ void load_round(const uint2* __restrict__ src, int64_t n, uint32_t tid,
+// Rows [0, n) of src, item q of thread tid = row q*kThreads + tid; n < 2^31.
+__device__ __forceinline__ void load_round(const uint2* __restrict__ src, uint32_t n, uint32_t tid,
                                            uint32_t (&k)[kItems], uint32_t (&v)[kItems]) {
 #pragma unroll
   for (int q = 0; q < kItems; ++q) {
-    const int64_t i = (int64_t)q * kThreads + tid;
+    const uint32_t i = q * kThreads + tid;
     k[q] = 0;
     v[q] = 0;
     if (i < n) {
@@ -74,89 +78,99 @@ __device__ __forceinline__ void load_round(const uint2* __restrict__ src, int64_
   }
 }
 
-// The build phase re-reads buckets that other threads are filling with atomics: force a real load.
-__device__ __forceinline__ uint4 lds128_volatile(const uint32_t* p) {
-  uint4 r;
-  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "r"((uint32_t)__cvta_generic_to_shared(p))
-               : "memory");
-  return r;
+// Slots of bucket `cur` that hold `key`, among its first min(n, 4) (the valid ones), as a 4-bit mask.
+__device__ __forceinline__ uint32_t hit_mask(const uint4& cur, uint32_t key, uint32_t n) {
+  const uint32_t hit = (cur.x == key ? 1u : 0u) | (cur.y == key ? 2u : 0u) | (cur.z == key ? 4u : 0u) |
+                       (cur.w == key ? 8u : 0u);
+  return hit & ((1u << min(n, 4u)) - 1u);
 }
 
-// Number of slots of bucket `cur` holding `key`, as a 4-bit mask.
-__device__ __forceinline__ uint32_t hit_mask(const uint4& cur, uint32_t key) {
-  return (cur.x == key ? 1u : 0u) | (cur.y == key ? 2u : 0u) | (cur.z == key ? 4u : 0u) |
-         (cur.w == key ? 8u : 0u);
-}
-
-// One CTA per partition. The table is bucketised: a probe reads a whole 4-key bucket with one
-// 128-bit shared-memory load and only moves on when the bucket is full, so nearly every row is
-// resolved in ONE iteration and the lanes of a warp do not wait for each other's probe chains
-// (the first version probed slot by slot: 13 iterations per warp on average, 465 instructions
-// per row, profiles/r1_join.md). All global loads of a partition (its build rows and the first
-// round of probe rows) are issued before anything else, so the table clear and the inserts run
-// under that latency.
+// One CTA per partition; the table lives in shared memory.
+//
+// Table: 2048 buckets of 4 slots plus one ARRIVAL COUNTER per bucket. An insert is one shared-memory
+// atomicAdd on the counter — the returned value is the slot, >= 4 sends the row on to the next
+// bucket — and two stores: no compare-and-swap, no re-read of the bucket, no retry, no empty-key
+// marker (so all 2^32 keys are legal and nothing but the 8 KB of counters is cleared per
+// partition). A probe reads the counter and the bucket's four keys (one 128-bit load); only the
+// first min(count, 4) slots are valid, and the chain continues in the next bucket only when
+// count > 4, i.e. when a row really overflowed. (The first version found a free slot by reading
+// the bucket and claiming it with atomicCAS, and probed until it met a bucket with a free slot:
+// 86 + 131 lane-instructions per build + probe row, 40 % of them in per-item retry / chain loops
+// that ran with 3-16 of 32 lanes active, profiles/r1_join.md.)
+// TWO-CHOICE placement: a row has two candidate buckets (two multiplicative hashes) and goes to the
+// emptier one, which keeps practically every bucket at <= 4 arrivals at a mean of 2 per bucket; a
+// probe always looks at both candidates, straight-line, and only rows whose two candidates BOTH
+// overflowed (count > 4) walk a chain (linear, from the second candidate). With one candidate
+// bucket 5 % of the probe rows and 14 % of the build rows had to walk on, so with 288 rows per warp
+// and round every per-item chain block ran ~2 times with ~3 of 32 lanes active: 75 + 40
+// lane-instructions per row pair (profiles/r1_join.md).
+// All global loads of a partition (its build rows and the first round of probe rows) are issued
+// before anything else, so the clear and the inserts run under that latency.
 __global__ void __launch_bounds__(kThreads, kProbeCtasPerSm)
 join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ roff,
                   const uint2* __restrict__ lpairs, const int64_t* __restrict__ loff,
-                  int64_t nparts, int part_shl, int part_bits, uint32_t* __restrict__ out_fk,
-                  uint32_t* __restrict__ out_y, uint32_t* __restrict__ out_x, int64_t out_cap,
-                  JoinState* __restrict__ st) {
-  extern __shared__ __align__(16) uint32_t tab[];  // keys [kSlots] | values [kSlots]
+                  int64_t nparts, uint32_t* __restrict__ out_fk, uint32_t* __restrict__ out_y,
+                  uint32_t* __restrict__ out_x, int64_t out_cap, JoinState* __restrict__ st) {
+  extern __shared__ __align__(16) uint32_t tab[];  // keys [kSlots] | values [kSlots] | counts [kBuckets]
   uint32_t* tk = tab;
   uint32_t* tv = tab + kSlots;
+  uint32_t* cnt = tab + 2 * kSlots;
   const uint4* tk4 = reinterpret_cast<const uint4*>(tab);
-  __shared__ uint32_t seg_cnt[kSegsPerLane * 32];
-  __shared__ uint32_t seg_off[kSegsPerLane * 32];
+  __shared__ uint32_t warp_cnt[kWarps];
   __shared__ unsigned long long s_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt = lanemask_lt();
-  for (int i = tid; i < kSegsPerLane * 32; i += kThreads) seg_cnt[i] = 0;  // padding entries stay 0
 
   for (int64_t p = blockIdx.x; p < nparts; p += gridDim.x) {
     const int64_t r0 = roff[p], r1 = roff[p + 1];
     const int64_t l0 = loff[p], l1 = loff[p + 1];
     if (r1 == r0 || l1 == l0) continue;  // inner join: nothing to emit
-    // a key that belongs to a different partition marks empty slots
-    uint32_t empty = 0xffffffffu;
-    while (part_bucket(wang_hash_u32(empty), part_shl, part_bits) == (uint32_t)p) --empty;
 
     for (int64_t c0 = r0; c0 < r1; c0 += kMaxBuild) {
-      const int nbuild = (int)min((int64_t)kMaxBuild, r1 - c0);
+      const uint32_t nbuild = (uint32_t)min((int64_t)kMaxBuild, r1 - c0);
       uint32_t lk[kItems], ly[kItems];
       {
         uint32_t rk[kItems], rv[kItems];
         load_round(rpairs + c0, nbuild, tid, rk, rv);
-        load_round(lpairs + l0, l1 - l0, tid, lk, ly);
+        load_round(lpairs + l0, (uint32_t)min(l1 - l0, (int64_t)kRound), tid, lk, ly);
 
         __syncthreads();  // the previous probe phase is done with the table
-        {
-          const uint4 e4 = make_uint4(empty, empty, empty, empty);
-          uint4* w4 = reinterpret_cast<uint4*>(tk);
-#pragma unroll
-          for (int i = 0; i < kBuckets / kThreads; ++i) w4[i * kThreads + tid] = e4;
-        }
+        if (tid < kBuckets / 4) reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        for (int base = 0; base < nbuild; base += kRound) {
+        for (uint32_t base = 0; base < nbuild; base += kRound) {
           if (base > 0) load_round(rpairs + c0 + base, nbuild - base, tid, rk, rv);
+          // e = stage << 16 | bucket * 8 + slot; slot 4 = "bucket was full, still looking";
+          // stage 0 = first candidate tried, 1 = second, 2 = walking the chain behind the second
+          uint32_t e[kItems];
+          uint32_t pend = 0;
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) {  // all first-choice counters are bumped back to back
+            const uint32_t h1 = bucket_hash(rk[q]), h2 = bucket_hash2(rk[q]);
+            const uint32_t b = cnt[h2] < cnt[h1] ? h2 : h1;  // racy read: only a placement heuristic
+            e[q] = b * 8;
+            if (base + q * kThreads + tid < nbuild) {
+              e[q] += min(atomicAdd(&cnt[b], 1u), 4u);
+              pend |= ((e[q] & 7u) == 4u ? 1u : 0u) << q;
+            }
+          }
+          while (pend) {  // rare: both candidates full
+#pragma unroll
+            for (int q = 0; q < kItems; ++q) {
+              if (pend >> q & 1) {
+                const uint32_t stage = e[q] >> 16, was = (e[q] & 0xffffu) >> 3;
+                const uint32_t h1 = bucket_hash(rk[q]), h2 = bucket_hash2(rk[q]);
+                const uint32_t b = stage == 0 ? (was ^ h1 ^ h2) : (stage == 1 ? h2 + 1 : was + 1) & (kBuckets - 1);
+                e[q] = (min(stage + 1, 2u) << 16) | (b * 8 + min(atomicAdd(&cnt[b], 1u), 4u));
+                if ((e[q] & 7u) != 4u) pend &= ~(1u << q);
+              }
+            }
+          }
 #pragma unroll
           for (int q = 0; q < kItems; ++q) {
-            if (base + q * kThreads + (int)tid < nbuild) {
-              uint32_t b = bucket_hash(rk[q]);
-              while (true) {
-                const uint4 cur = lds128_volatile(tk + b * 4);
-                // slots of a bucket fill in index order, so the first empty one is the target
-                const int sidx = cur.x == empty ? 0 : cur.y == empty ? 1 : cur.z == empty ? 2 : cur.w == empty ? 3 : 4;
-                if (sidx == 4) {
-                  b = (b + 1) & (kBuckets - 1);
-                  continue;
-                }
-                if (atomicCAS(&tk[b * 4 + sidx], empty, rk[q]) == empty) {
-                  tv[b * 4 + sidx] = rv[q];  // duplicates of a key take separate slots
-                  break;
-                }
-              }
+            if (base + q * kThreads + tid < nbuild) {
+              const uint32_t slot = ((e[q] & 0xffffu) >> 3) * 4 + (e[q] & 7u);
+              tk[slot] = rk[q];
+              tv[slot] = rv[q];  // duplicates of a key take separate slots
             }
           }
         }
@@ -164,103 +178,124 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
       __syncthreads();
 
       for (int64_t t0 = l0; t0 < l1; t0 += kRound) {
-        if (t0 > l0) load_round(lpairs + t0, l1 - t0, tid, lk, ly);
+        const uint32_t nprobe = (uint32_t)min(l1 - t0, (int64_t)kRound);
+        if (t0 > l0) load_round(lpairs + t0, nprobe, tid, lk, ly);
         uint32_t x0[kItems], m[kItems];
+        uint32_t pend = 0;
 #pragma unroll
-        for (int q = 0; q < kItems; ++q) {
-          m[q] = 0;
+        for (int q = 0; q < kItems; ++q) {  // both candidate buckets of every item: straight-line
+          const uint32_t h1 = bucket_hash(lk[q]), h2 = bucket_hash2(lk[q]);
+          const uint32_t n1 = cnt[h1], n2 = cnt[h2];
+          const uint4 c1 = tk4[h1], c2 = tk4[h2];
+          const bool active = q * kThreads + tid < nprobe;
+          const uint32_t hit1 = active ? hit_mask(c1, lk[q], n1) : 0u;
+          const uint32_t hit2 = (active && h2 != h1) ? hit_mask(c2, lk[q], n2) : 0u;
+          m[q] = __popc(hit1) + __popc(hit2);
           x0[q] = 0;
-          if (t0 + q * kThreads + tid < l1) {
-            uint32_t b = bucket_hash(lk[q]);
-            while (true) {
-              const uint4 cur = tk4[b];
-              const uint32_t hit = hit_mask(cur, lk[q]);
-              if (hit) {
-                if (m[q] == 0) x0[q] = tv[b * 4 + (__ffs(hit) - 1)];
-                m[q] += __popc(hit);
-              }
-              if (cur.w == empty) break;  // bucket not full: the chain ends here
-              b = (b + 1) & (kBuckets - 1);
+          if (hit1) x0[q] = tv[h1 * 4 + (__ffs(hit1) - 1)];
+          else if (hit2) x0[q] = tv[h2 * 4 + (__ffs(hit2) - 1)];
+          pend |= (active && n1 > 4u && n2 > 4u ? 1u : 0u) << q;  // rows overflowed out of both
+        }
+        if (pend) {  // rare: the chain behind the second candidate
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) {
+            if (pend >> q & 1) {
+              const uint32_t h1 = bucket_hash(lk[q]);
+              uint32_t b = bucket_hash2(lk[q]);
+              uint32_t n;
+              do {
+                b = (b + 1) & (kBuckets - 1);
+                n = cnt[b];
+                const uint4 cur = tk4[b];
+                // the chain may run through the first candidate, which has been looked at already
+                const uint32_t hit = b == h1 ? 0u : hit_mask(cur, lk[q], n);
+                if (hit) {
+                  if (m[q] == 0) x0[q] = tv[b * 4 + (__ffs(hit) - 1)];
+                  m[q] += __popc(hit);
+                }
+              } while (n > 4u);
             }
           }
         }
-        // ---- output positions: order (q, warp, lane) so the stores of one q are contiguous ----
-        uint32_t lane_excl[kItems];
+        // ---- output positions in (warp, item, lane) order: one 64-bit atomic per CTA and round ----
+        uint32_t wtotal = 0;
 #pragma unroll
         for (int q = 0; q < kItems; ++q) {
-          const uint32_t one = __ballot_sync(0xffffffffu, m[q] == 1);
           const uint32_t multi = __ballot_sync(0xffffffffu, m[q] > 1);
-          uint32_t total;
+          wtotal += multi ? __reduce_add_sync(0xffffffffu, m[q])
+                          : __popc(__ballot_sync(0xffffffffu, m[q] == 1));
+        }
+        if (lane == 0) warp_cnt[warp] = wtotal;
+        __syncthreads();
+        {
+          // every warp scans the 16 warp totals itself; warp 0 reserves the CTA's output range
+          const uint32_t w = lane < kWarps ? warp_cnt[lane] : 0;
+          uint32_t incl = w;
+#pragma unroll
+          for (int o = 1; o < kWarps; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const uint32_t total = __shfl_sync(0xffffffffu, incl, kWarps - 1);
+          wtotal = __shfl_sync(0xffffffffu, incl - w, warp);  // now: this warp's offset in the round
+          if (tid == 0 && total > 0) s_base = atomicAdd(&st->out_rows, (unsigned long long)total);
+        }
+        __syncthreads();
+        unsigned long long pos = s_base + wtotal;
+#pragma unroll
+        for (int q = 0; q < kItems; ++q) {
+          const uint32_t multi = __ballot_sync(0xffffffffu, m[q] > 1);
           if (multi == 0) {  // unique build keys: ranks come from one ballot
-            lane_excl[q] = __popc(one & lt);
-            total = __popc(one);
-          } else {
+            const uint32_t one = __ballot_sync(0xffffffffu, m[q] == 1);
+            const unsigned long long pp = pos + __popc(one & lt);
+            if (m[q] == 1 && (int64_t)pp < out_cap) {
+              st_stream_u32(out_fk + pp, lk[q]);
+              st_stream_u32(out_y + pp, ly[q]);
+              st_stream_u32(out_x + pp, x0[q]);
+            }
+            pos += __popc(one);
+          } else {  // duplicate build keys somewhere in this warp: enumerate every match
             uint32_t incl = m[q];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
               const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
               if (lane >= o) incl += t;
             }
-            lane_excl[q] = incl - m[q];
-            total = __shfl_sync(0xffffffffu, incl, 31);
-          }
-          if (lane == 0) seg_cnt[q * kWarps + warp] = total;
-        }
-        __syncthreads();
-        if (warp == 0) {
-          uint32_t c[kSegsPerLane], sum = 0;
-#pragma unroll
-          for (int i = 0; i < kSegsPerLane; ++i) {
-            c[i] = seg_cnt[kSegsPerLane * lane + i];
-            sum += c[i];
-          }
-          uint32_t incl = sum;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-          }
-          uint32_t run = incl - sum;
-#pragma unroll
-          for (int i = 0; i < kSegsPerLane; ++i) {
-            seg_off[kSegsPerLane * lane + i] = run;
-            run += c[i];
-          }
-          if (lane == 31) s_base = atomicAdd(&st->out_rows, (unsigned long long)incl);
-        }
-        __syncthreads();
-        const unsigned long long base = s_base;
-#pragma unroll
-        for (int q = 0; q < kItems; ++q) {
-          if (m[q] == 0) continue;
-          unsigned long long pos = base + seg_off[q * kWarps + warp] + lane_excl[q];
-          if (m[q] == 1) {
-            if ((int64_t)pos < out_cap) {
-              st_stream_u32(out_fk + pos, lk[q]);
-              st_stream_u32(out_y + pos, ly[q]);
-              st_stream_u32(out_x + pos, x0[q]);
-            }
-          } else {  // duplicate build keys: enumerate every match
-            uint32_t b = bucket_hash(lk[q]);
-            while (true) {
-              const uint4 cur = tk4[b];
-              uint32_t hit = hit_mask(cur, lk[q]);
-              while (hit) {
-                const int sidx = __ffs(hit) - 1;
-                hit &= hit - 1;
-                if ((int64_t)pos < out_cap) {
-                  out_fk[pos] = lk[q];
-                  out_y[pos] = ly[q];
-                  out_x[pos] = tv[b * 4 + sidx];
-                }
-                ++pos;
+            unsigned long long pp = pos + incl - m[q];
+            pos += __shfl_sync(0xffffffffu, incl, 31);
+            if (m[q] == 1) {
+              if ((int64_t)pp < out_cap) {
+                out_fk[pp] = lk[q];
+                out_y[pp] = ly[q];
+                out_x[pp] = x0[q];
               }
-              if (cur.w == empty) break;
-              b = (b + 1) & (kBuckets - 1);
+            } else if (m[q] > 1) {
+              // the same search path as above: first candidate, second, then the chain
+              const uint32_t h1 = bucket_hash(lk[q]), h2 = bucket_hash2(lk[q]);
+              const bool chain = cnt[h1] > 4u && cnt[h2] > 4u;
+              uint32_t b = h1;
+              for (int step = 0;; ++step) {
+                const uint32_t n = cnt[b];
+                const uint4 cur = tk4[b];
+                uint32_t hit = (step >= 1 && b == h1) ? 0u : hit_mask(cur, lk[q], n);
+                while (hit) {
+                  const int sidx = __ffs(hit) - 1;
+                  hit &= hit - 1;
+                  if ((int64_t)pp < out_cap) {
+                    out_fk[pp] = lk[q];
+                    out_y[pp] = ly[q];
+                    out_x[pp] = tv[b * 4 + sidx];
+                  }
+                  ++pp;
+                }
+                if (step == 0) { b = h2; continue; }
+                if (step == 1 ? !chain : n <= 4u) break;
+                b = (b + 1) & (kBuckets - 1);
+              }
             }
           }
         }
-        // seg_cnt / seg_off / s_base are rewritten only after the next round's first barrier
+        // warp_cnt / s_base are rewritten only after the next round's first barrier
       }
     }
     __syncthreads();
@@ -357,7 +392,7 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
     if (!attr_done) {
       B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSlots * 8));
+                                           kTableBytes));
       attr_done = true;
     }
     const int64_t nparts = (int64_t)1 << P.bits;
@@ -368,9 +403,8 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
       B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
                                  lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s));
       int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
-      join_probe_kernel<<<(unsigned)grid, kThreads, kSlots * 8, s>>>(
-          rout, roff, lout, loff, nparts, part_shl, P.bits, d_out_fk, d_out_y, d_out_x,
-          out_capacity, st);
+      join_probe_kernel<<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+          rout, roff, lout, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st);
       B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
     }
   }
@@ -445,7 +479,7 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   B2_LAUNCH_CHECK(ctx, "join_init_kernel");
   if (nl > 0 && nr > 0) {
     B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSlots * 8));
+                                         kTableBytes));
     const int64_t nseg = (int64_t)1 << seg_bits;
     const int64_t nparts = (int64_t)1 << P.total_bits;
     const uint2 *rp = rpairs, *lp = lpairs;
@@ -469,8 +503,8 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
       rp = rout; lp = lout; roff = roff_w; loff = loff_w;
     }
     const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
-    join_probe_kernel<<<(unsigned)grid, kThreads, kSlots * 8, s>>>(
-        rp, roff, lp, loff, nparts, skip_bits, P.total_bits, d_out_fk, d_out_y, d_out_x, out_capacity, st);
+    join_probe_kernel<<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+        rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st);
     B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
   }
   join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows);
