@@ -219,11 +219,17 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
         }
         // ---- output positions in (warp, item, lane) order: one 64-bit atomic per CTA and round ----
         uint32_t wtotal = 0;
+        uint32_t many = 0;
 #pragma unroll
-        for (int q = 0; q < kItems; ++q) {
-          const uint32_t multi = __ballot_sync(0xffffffffu, m[q] > 1);
-          wtotal += multi ? __reduce_add_sync(0xffffffffu, m[q])
-                          : __popc(__ballot_sync(0xffffffffu, m[q] == 1));
+        for (int q = 0; q < kItems; ++q) many |= m[q];
+        // duplicate build keys anywhere in this warp's round? (one vote instead of one per item)
+        const bool warp_multi = __any_sync(0xffffffffu, many > 1u);
+        if (!warp_multi) {
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) wtotal += __popc(__ballot_sync(0xffffffffu, m[q] == 1));
+        } else {
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) wtotal += __reduce_add_sync(0xffffffffu, m[q]);
         }
         if (lane == 0) warp_cnt[warp] = wtotal;
         __syncthreads();
@@ -242,19 +248,29 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
         }
         __syncthreads();
         unsigned long long pos = s_base + wtotal;
+        if (!warp_multi) {
+          // unique build keys (the common case): ranks come from one ballot per item, positions are
+          // 32-bit offsets from the warp's base, rows at or beyond out_cap are dropped
+          const uint32_t room = (int64_t)pos < out_cap ? (uint32_t)min(out_cap - (int64_t)pos, (int64_t)kRound) : 0u;
+          uint32_t* __restrict__ pf = out_fk + pos;
+          uint32_t* __restrict__ py = out_y + pos;
+          uint32_t* __restrict__ px = out_x + pos;
+          uint32_t run = 0;
 #pragma unroll
-        for (int q = 0; q < kItems; ++q) {
-          const uint32_t multi = __ballot_sync(0xffffffffu, m[q] > 1);
-          if (multi == 0) {  // unique build keys: ranks come from one ballot
+          for (int q = 0; q < kItems; ++q) {
             const uint32_t one = __ballot_sync(0xffffffffu, m[q] == 1);
-            const unsigned long long pp = pos + __popc(one & lt);
-            if (m[q] == 1 && (int64_t)pp < out_cap) {
-              st_stream_u32(out_fk + pp, lk[q]);
-              st_stream_u32(out_y + pp, ly[q]);
-              st_stream_u32(out_x + pp, x0[q]);
+            const uint32_t off = run + __popc(one & lt);
+            if (m[q] == 1 && off < room) {
+              st_stream_u32(pf + off, lk[q]);
+              st_stream_u32(py + off, ly[q]);
+              st_stream_u32(px + off, x0[q]);
             }
-            pos += __popc(one);
-          } else {  // duplicate build keys somewhere in this warp: enumerate every match
+            run += __popc(one);
+          }
+        } else {
+          // duplicate build keys somewhere in this warp's round: enumerate every match
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) {
             uint32_t incl = m[q];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
