@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — rows/s of the columnar operator hot path at SF=2048 on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--sf 2048] [--ops filter,sweep,sum,take,join,nullable]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--sf 2048] [--ops filter,sweep,sum,take,join,nullable,joinsum]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference      # the reference's Arrow Acero CPU path on the host cores
 
@@ -47,7 +47,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--sf", type=int, default=int(os.environ.get("SF", 2048)))
-    p.add_argument("--ops", default="filter,sweep,sum,take,join,nullable")
+    p.add_argument("--ops", default="filter,sweep,sum,take,join,nullable,joinsum")
     p.add_argument("--e2e-sf", type=int, default=int(os.environ.get("E2E_SF", 64)),
                    help="scale factor of the host-buffer (e2e) leg; bounded by host RAM and PCIe time")
     p.add_argument("--cpu-sf", type=int, default=int(os.environ.get("CPU_SF", 64)),
@@ -554,6 +554,56 @@ def bench_join(ctx, D, args):
     return res
 
 
+def bench_join_aggr(ctx, D, args):
+    """Fused pipeline [filter L.y < 2^30 ->] join -> COUNT / SUM(y) / SUM(x) on one GPU
+    (b2_join_aggr_u32_dev): same inputs as the join, nothing materialised — so at
+    SF=2048 the 48 GiB of output columns are not needed and the join runs in one hash-space slice."""
+    import torch
+    from dpu_olap_b200.generator import RandomArrayGenerator
+    if D.world != 1:
+        return None
+    nb = args.sf
+    g = RandomArrayGenerator(ctx, 42)
+    x = g.batches_dev(nb, JOIN_BATCH)
+    pk = g.index_column_dev(nb, JOIN_BATCH)
+    y = g.batches_dev(nb, JOIN_BATCH)
+    fk = g.foreign_key_dev(JOIN_BATCH, nb, JOIN_BATCH)
+    n = nb * JOIN_BATCH
+    free, _ = torch.cuda.mem_get_info()
+    full = ctx.join_ws_bytes(n, n)
+    ws_bytes = min(full, max(free - (3 << 30), ctx.join_min_ws_bytes(n, n)))
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+    out = torch.empty(3, dtype=torch.int64, device="cuda")
+    res = {"workspace_gib": round(ws_bytes / 2**30, 2), "sliced": ws_bytes < full, "rows_per_side": n}
+    # expected aggregates, computed with torch: every fk matches exactly one pk = its row number
+    thr = 1 << 30
+    flip = torch.tensor(-2**31, dtype=torch.int32, device="cuda")
+    exp = {None: [0, 0, 0], thr: [0, 0, 0]}
+    for s0 in range(0, n, 1 << 26):
+        s1 = min(n, s0 + (1 << 26))
+        yy = y[s0:s1].to(torch.int64) & 0xFFFFFFFF
+        xx = x[(fk[s0:s1].to(torch.int64) & 0xFFFFFFFF)].to(torch.int64) & 0xFFFFFFFF
+        keep = (y[s0:s1] ^ flip) < (thr - 2**31)
+        exp[None][0] += s1 - s0
+        exp[None][1] += int(yy.sum())
+        exp[None][2] += int(xx.sum())
+        exp[thr][0] += int(keep.sum())
+        exp[thr][1] += int((yy * keep).sum())
+        exp[thr][2] += int((xx * keep).sum())
+    for name, t in (("join_sum", None), ("filter_join_sum", thr)):
+        l0 = ctx.launches
+        ms = timed_steps(D, lambda: ctx.join_aggr_dev(fk, y, pk, x, y_threshold=t, ws=ws, out=out),
+                         args.steps, args.warmup)
+        got = [int(v) for v in out.cpu().numpy().view("uint64")]
+        if got != [v % (1 << 64) for v in exp[t]]:
+            raise SystemExit(f"{name} self-check failed: {got} vs {exp[t]}")
+        res[name] = {"ms_per_step": ms, "rows_per_s": n / (ms * 1e-3), "out_rows": got[0],
+                     "launches_per_step": (ctx.launches - l0) // (args.steps + args.warmup)}
+    del x, pk, y, fk, ws
+    free_all()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 # end-to-end (host buffers through the C ABI) and CPU baseline
 # ------------------------------------------------------------------------------------------------
@@ -752,6 +802,8 @@ def main():
         extra["join"] = bench_join(ctx, D, args)
     if "nullable" in ops:
         extra["nullable"] = bench_nullable(ctx, D, args)
+    if "joinsum" in ops:
+        extra["join_aggregate"] = bench_join_aggr(ctx, D, args)
     e2e = None
     if not args.no_e2e:
         e2e = bench_e2e_filter(ctx, D, args)

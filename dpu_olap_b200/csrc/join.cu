@@ -50,6 +50,15 @@ struct JoinState {  // lives in the workspace header
   unsigned long long out_rows;
   unsigned int overflow;
   unsigned int pad;
+  unsigned long long sum_y, sum_x;  // fused join -> aggregate (b2_join_aggr_u32_dev)
+};
+
+// Fused pipeline [filter L.y < y_thr ->] join -> aggregate: nothing is materialised, the probe
+// kernel adds every output row's y and x to per-thread sums instead of storing it.
+struct JoinAggCfg {
+  uint32_t y_thr = 0;
+  bool filter_y = false;
+  b2_join_aggr* d_out = nullptr;
 };
 
 // Bucket inside a partition's table. All keys of a partition share the TOP bits of wang_hash, so
@@ -85,6 +94,30 @@ __device__ __forceinline__ uint32_t hit_mask(const uint4& cur, uint32_t key, uin
   return hit & ((1u << min(n, 4u)) - 1u);
 }
 
+// Calls f(x) for the payload of every build row matching `key`, along the row's search path: first
+// candidate bucket, second, then the chain behind the second while buckets overflowed.
+template <typename F>
+__device__ __forceinline__ void for_each_match(const uint32_t* cnt, const uint4* tk4, const uint32_t* tv,
+                                               uint32_t key, F&& f) {
+  const uint32_t h1 = bucket_hash(key), h2 = bucket_hash2(key);
+  const bool chain = cnt[h1] > 4u && cnt[h2] > 4u;
+  uint32_t b = h1;
+  for (int step = 0;; ++step) {
+    const uint32_t n = cnt[b];
+    const uint4 cur = tk4[b];
+    // from the second step on, the first candidate has been looked at already
+    uint32_t hit = (step >= 1 && b == h1) ? 0u : hit_mask(cur, key, n);
+    while (hit) {
+      const int sidx = __ffs(hit) - 1;
+      hit &= hit - 1;
+      f(tv[b * 4 + sidx]);
+    }
+    if (step == 0) { b = h2; continue; }
+    if (step == 1 ? !chain : n <= 4u) break;
+    b = (b + 1) & (kBuckets - 1);
+  }
+}
+
 // One CTA per partition; the table lives in shared memory.
 //
 // Table: 2048 buckets of 4 slots plus one ARRIVAL COUNTER per bucket. An insert is one shared-memory
@@ -106,11 +139,14 @@ __device__ __forceinline__ uint32_t hit_mask(const uint4& cur, uint32_t key, uin
 // lane-instructions per row pair (profiles/r1_join.md).
 // All global loads of a partition (its build rows and the first round of probe rows) are issued
 // before anything else, so the clear and the inserts run under that latency.
+// kAgg: the fused join -> aggregate pipeline (no output columns, no output-range reservation).
+template <bool kAgg>
 __global__ void __launch_bounds__(kThreads, kProbeCtasPerSm)
 join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ roff,
                   const uint2* __restrict__ lpairs, const int64_t* __restrict__ loff,
                   int64_t nparts, uint32_t* __restrict__ out_fk, uint32_t* __restrict__ out_y,
-                  uint32_t* __restrict__ out_x, int64_t out_cap, JoinState* __restrict__ st) {
+                  uint32_t* __restrict__ out_x, int64_t out_cap, JoinState* __restrict__ st,
+                  uint32_t y_thr, bool filter_y) {
   extern __shared__ __align__(16) uint32_t tab[];  // keys [kSlots] | values [kSlots] | counts [kBuckets]
   uint32_t* tk = tab;
   uint32_t* tv = tab + kSlots;
@@ -120,6 +156,7 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
   __shared__ unsigned long long s_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt = lanemask_lt();
+  unsigned long long agg_rows = 0, agg_y = 0, agg_x = 0;  // kAgg: this thread's share of the aggregates
 
   for (int64_t p = blockIdx.x; p < nparts; p += gridDim.x) {
     const int64_t r0 = roff[p], r1 = roff[p + 1];
@@ -187,7 +224,7 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
           const uint32_t h1 = bucket_hash(lk[q]), h2 = bucket_hash2(lk[q]);
           const uint32_t n1 = cnt[h1], n2 = cnt[h2];
           const uint4 c1 = tk4[h1], c2 = tk4[h2];
-          const bool active = q * kThreads + tid < nprobe;
+          const bool active = q * kThreads + tid < nprobe && (!kAgg || !filter_y || ly[q] < y_thr);
           const uint32_t hit1 = active ? hit_mask(c1, lk[q], n1) : 0u;
           const uint32_t hit2 = (active && h2 != h1) ? hit_mask(c2, lk[q], n2) : 0u;
           m[q] = __popc(hit1) + __popc(hit2);
@@ -216,6 +253,19 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
               } while (n > 4u);
             }
           }
+        }
+        if (kAgg) {  // every output row (fk, y, x) adds y and x to the sums; nothing is stored
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) {
+            if (m[q] == 1) {
+              agg_x += x0[q];
+            } else if (m[q] > 1) {
+              for_each_match(cnt, tk4, tv, lk[q], [&](uint32_t x) { agg_x += x; });
+            }
+            agg_rows += m[q];
+            agg_y += (unsigned long long)ly[q] * m[q];
+          }
+          continue;
         }
         // ---- output positions in (warp, item, lane) order: one 64-bit atomic per CTA and round ----
         uint32_t wtotal = 0;
@@ -286,28 +336,14 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
                 out_x[pp] = x0[q];
               }
             } else if (m[q] > 1) {
-              // the same search path as above: first candidate, second, then the chain
-              const uint32_t h1 = bucket_hash(lk[q]), h2 = bucket_hash2(lk[q]);
-              const bool chain = cnt[h1] > 4u && cnt[h2] > 4u;
-              uint32_t b = h1;
-              for (int step = 0;; ++step) {
-                const uint32_t n = cnt[b];
-                const uint4 cur = tk4[b];
-                uint32_t hit = (step >= 1 && b == h1) ? 0u : hit_mask(cur, lk[q], n);
-                while (hit) {
-                  const int sidx = __ffs(hit) - 1;
-                  hit &= hit - 1;
-                  if ((int64_t)pp < out_cap) {
-                    out_fk[pp] = lk[q];
-                    out_y[pp] = ly[q];
-                    out_x[pp] = tv[b * 4 + sidx];
-                  }
-                  ++pp;
+              for_each_match(cnt, tk4, tv, lk[q], [&](uint32_t x) {
+                if ((int64_t)pp < out_cap) {
+                  out_fk[pp] = lk[q];
+                  out_y[pp] = ly[q];
+                  out_x[pp] = x;
                 }
-                if (step == 0) { b = h2; continue; }
-                if (step == 1 ? !chain : n <= 4u) break;
-                b = (b + 1) & (kBuckets - 1);
-              }
+                ++pp;
+              });
             }
           }
         }
@@ -316,11 +352,29 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
     }
     __syncthreads();
   }
+  if (kAgg) {
+    agg_rows = warp_reduce_sum_u64(agg_rows);
+    agg_y = warp_reduce_sum_u64(agg_y);
+    agg_x = warp_reduce_sum_u64(agg_x);
+    if (lane == 0 && agg_rows) {
+      atomicAdd(&st->out_rows, agg_rows);
+      atomicAdd(&st->sum_y, agg_y);
+      atomicAdd(&st->sum_x, agg_x);
+    }
+  }
 }
 
 __global__ void join_init_kernel(JoinState* st) {
   st->out_rows = 0;
   st->overflow = 0;
+  st->sum_y = 0;
+  st->sum_x = 0;
+}
+__global__ void join_aggr_finish_kernel(const JoinState* __restrict__ st, b2_join_aggr* __restrict__ out) {
+  // a partition buffer that overflowed (skewed slice) makes the result invalid: report ~0 rows
+  out->rows = st->overflow ? ~0ull : st->out_rows;
+  out->sum_y = st->sum_y;
+  out->sum_x = st->sum_x;
 }
 __global__ void join_finish_kernel(const JoinState* __restrict__ st, uint64_t* __restrict__ out_rows) {
   // a partition buffer that overflowed (skewed slice) makes the result invalid: report ~0
@@ -379,10 +433,11 @@ constexpr int kMaxSliceBits = 6;
 
 int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& rin, int64_t nr,
               uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
-              uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+              uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s,
+              const JoinAggCfg* agg = nullptr) {
   B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
   B2_REQUIRE(ctx, skip_bits >= 0 && skip_bits <= 8, "hash_skip_bits must be in 0..8");
-  B2_REQUIRE(ctx, d_out_rows != nullptr, "d_out_rows is null");
+  B2_REQUIRE(ctx, agg ? agg->d_out != nullptr : d_out_rows != nullptr, "result pointer is null");
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
              "workspace must be 256 B aligned");
   B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
@@ -406,9 +461,10 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
   if (nl > 0 && nr > 0) {
     static bool attr_done = false;
     if (!attr_done) {
-      B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kTableBytes));
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
       attr_done = true;
     }
     const int64_t nparts = (int64_t)1 << P.bits;
@@ -416,15 +472,25 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
     for (uint32_t slice = 0; slice < (1u << P.slice_bits); ++slice) {
       B2_RETURN_NOT_OK(part_full(ctx, rin, nr, P.bits, part_shl, skip_bits, P.slice_bits, slice,
                                  rout, tmp, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
+      // filter pushdown: the probe side's first radix pass drops the rows that fail L.y < y_thr
       B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
-                                 lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s));
+                                 lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s,
+                                 agg && agg->filter_y, agg ? agg->y_thr : 0u));
       int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
-      join_probe_kernel<<<(unsigned)grid, kThreads, kTableBytes, s>>>(
-          rout, roff, lout, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st);
+      if (agg)
+        join_probe_kernel<true><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+            rout, roff, lout, loff, nparts, nullptr, nullptr, nullptr, 0, st, agg->y_thr, false);
+      else
+        join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+            rout, roff, lout, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false);
       B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
     }
   }
-  join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows);
+  if (agg) {
+    join_aggr_finish_kernel<<<1, 1, 0, s>>>(st, agg->d_out);
+  } else {
+    join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows);
+  }
   B2_LAUNCH_CHECK(ctx, "join_finish_kernel");
   return B2_OK;
 }
@@ -494,7 +560,7 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   join_init_kernel<<<1, 1, 0, s>>>(st);
   B2_LAUNCH_CHECK(ctx, "join_init_kernel");
   if (nl > 0 && nr > 0) {
-    B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kTableBytes));
     const int64_t nseg = (int64_t)1 << seg_bits;
     const int64_t nparts = (int64_t)1 << P.total_bits;
@@ -519,8 +585,8 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
       rp = rout; lp = lout; roff = roff_w; loff = loff_w;
     }
     const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
-    join_probe_kernel<<<(unsigned)grid, kThreads, kTableBytes, s>>>(
-        rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st);
+    join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+        rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false);
     B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
   }
   join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows);
@@ -570,6 +636,26 @@ int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int6
   rin.vals = d_x;
   return join_impl(ctx, lin, nl, rin, nr, d_out_fk, d_out_y, d_out_x, out_capacity, d_out_rows,
                    hash_skip_bits, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b2_join_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
+                         const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, int filter_y,
+                         uint32_t y_threshold, b2_join_aggr* d_out, int hash_skip_bits, void* d_ws,
+                         size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, nl == 0 || (d_fk && d_y), "null left column");
+  B2_REQUIRE(ctx, nr == 0 || (d_pk && d_x), "null right column");
+  PartInput lin, rin;
+  lin.keys = d_fk;
+  lin.vals = d_y;
+  rin.keys = d_pk;
+  rin.vals = d_x;
+  JoinAggCfg agg;
+  agg.y_thr = y_threshold;
+  agg.filter_y = filter_y != 0;
+  agg.d_out = d_out;
+  return join_impl(ctx, lin, nl, rin, nr, nullptr, nullptr, nullptr, 0, nullptr, hash_skip_bits, d_ws,
+                   ws_bytes, static_cast<cudaStream_t>(stream), &agg);
 }
 
 int b2_join_pairs_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, int64_t nl, const uint64_t* d_r_pairs,

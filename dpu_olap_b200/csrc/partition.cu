@@ -125,13 +125,17 @@ __global__ void part_unit_table_kernel(const int64_t* __restrict__ seg_off, int6
 }
 
 // Hash + selection + bucket of one key; returns 0xffffffff for rows outside the hash-space slice.
-__device__ __forceinline__ uint32_t bucket_or_skip(uint32_t key, const PartGeom& g) {
+// kValPred (compile time: the plain passes must not pay for it): also drop rows whose value fails
+// the pushed-down predicate val < g.val_thr.
+template <bool kValPred>
+__device__ __forceinline__ uint32_t bucket_or_skip(uint32_t key, uint32_t val, const PartGeom& g) {
   const uint32_t h = wang_hash_u32(key);
   const uint32_t b = part_bucket(h, g.shl, g.bits);
-  return part_selected(h, g.sel_shl, g.sel_bits, g.sel_val) ? b : 0xffffffffu;
+  const bool keep = part_selected(h, g.sel_shl, g.sel_bits, g.sel_val) && (!kValPred || val < g.val_thr);
+  return keep ? b : 0xffffffffu;
 }
 
-template <bool kAoS>
+template <bool kAoS, bool kValPred>
 __global__ void __launch_bounds__(kThreads, 4)
 part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                  const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
@@ -147,17 +151,24 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   int64_t base = u.row0;
   // full blocks: no per-row bounds checks
   for (; base + (int64_t)kThreads * kU <= u.row1; base += (int64_t)kThreads * kU) {
-    uint32_t key[kU];
-#pragma unroll
-    for (int q = 0; q < kU; ++q) key[q] = load_key<kAoS>(in, base + q * kThreads + tid);
+    uint32_t key[kU], val[kU];
 #pragma unroll
     for (int q = 0; q < kU; ++q) {
-      const uint32_t b = bucket_or_skip(key[q], g);
+      val[q] = 0;
+      if (kValPred) load_row<kAoS>(in, base + q * kThreads + tid, key[q], val[q]);  // the predicate needs the value
+      else key[q] = load_key<kAoS>(in, base + q * kThreads + tid);
+    }
+#pragma unroll
+    for (int q = 0; q < kU; ++q) {
+      const uint32_t b = bucket_or_skip<kValPred>(key[q], val[q], g);
       if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
     }
   }
   for (int64_t row = base + tid; row < u.row1; row += kThreads) {
-    const uint32_t b = bucket_or_skip(load_key<kAoS>(in, row), g);
+    uint32_t key, val = 0;
+    if (kValPred) load_row<kAoS>(in, row, key, val);
+    else key = load_key<kAoS>(in, row);
+    const uint32_t b = bucket_or_skip<kValPred>(key, val, g);
     if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
   }
   __syncthreads();
@@ -170,7 +181,7 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 // 8-byte table read (destination of the bucket's run minus its position in the tile) per row
 // instead of hashing the key again. The first version of this kernel spent 105-111
 // lane-instructions per row (profiles/r1_join.md).
-template <bool kAoS, int kT, int kI, int kCtas>
+template <bool kAoS, int kT, int kI, int kCtas, bool kValPred>
 __global__ void __launch_bounds__(kT, kCtas)
 part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                     const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
@@ -217,7 +228,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
       for (int it = 0; it < kI; ++it) load_row<kAoS>(in, t0 + it * kT + tid, key[it], val[it]);
 #pragma unroll
       for (int it = 0; it < kI; ++it) {
-        const uint32_t b = bucket_or_skip(key[it], g);
+        const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g);
         packed[it] = b;
         if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192
       }
@@ -230,7 +241,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
         packed[it] = 0xffffffffu;
         if (row < u.row1) {
           load_row<kAoS>(in, row, key[it], val[it]);
-          const uint32_t b = bucket_or_skip(key[it], g);
+          const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g);
           if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);
         }
       }
@@ -380,7 +391,7 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     for (int it = 0; it < kLcItems; ++it) {
       const int64_t row = t0 + it * kLcThreads + tid;
       if (row < u.row1) {
-        const uint32_t b = bucket_or_skip(key[it], g);
+        const uint32_t b = bucket_or_skip<false>(key[it], val[it], g);
         if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
       }
     }
@@ -534,19 +545,19 @@ PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
 
 int g_scatter_variant = 0;  // tuning hook (b200olap_tune_scatter_variant)
 
-template <bool kAoS, int kT, int kI, int kCtas>
+template <bool kAoS, int kT, int kI, int kCtas, bool kValPred = false>
 int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const PartInput& in,
                    const int64_t* d_seg_off, const int64_t* unit_first, int64_t nseg, int64_t unit_rows,
                    const PartGeom& g, const uint64_t* scanned, uint2* d_out, int64_t out_cap,
                    unsigned int* d_overflow) {
   static bool attr_done = false;
   if (!attr_done) {
-    B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT, kI, kCtas>,
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)scatter_smem_bytes(kPartMaxBits, kT * kI)));
     attr_done = true;
   }
-  part_scatter_kernel<kAoS, kT, kI, kCtas><<<(unsigned)units, kT, scatter_smem_bytes(bits, kT * kI), s>>>(
+  part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred><<<(unsigned)units, kT, scatter_smem_bytes(bits, kT * kI), s>>>(
       in, d_seg_off, unit_first, nseg, unit_rows, g, scanned, d_out, out_cap, nullptr, d_overflow);
   return B2_OK;
 }
@@ -570,8 +581,12 @@ int part_count_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* 
   B2_LAUNCH_CHECK(ctx, "part_unit_table_kernel");
   B2_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (size_t)L.n_entries * 4, s));
   if (L.max_units > 0) {
-    part_hist_kernel<kAoS><<<(unsigned)L.max_units, kThreads, 0, s>>>(
-        in, d_seg_off, unit_first, nseg, L.unit_rows, g, hist);
+    if (g.val_pred)
+      part_hist_kernel<kAoS, true><<<(unsigned)L.max_units, kThreads, 0, s>>>(
+          in, d_seg_off, unit_first, nseg, L.unit_rows, g, hist);
+    else
+      part_hist_kernel<kAoS, false><<<(unsigned)L.max_units, kThreads, 0, s>>>(
+          in, d_seg_off, unit_first, nseg, L.unit_rows, g, hist);
     B2_LAUNCH_CHECK(ctx, "part_hist_kernel");
   }
   B2_RETURN_NOT_OK(b2_exclusive_scan_u32_u64(ctx, hist, scanned, L.n_entries, base + L.off_scanws,
@@ -607,6 +622,8 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       }
       part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
           in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr);
+    } else if (g.val_pred) {  // pushed-down value predicate: one shape, the default one
+      B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
     } else {
       switch (g_scatter_variant) {
         case 1: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 8, 3>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
@@ -687,7 +704,8 @@ size_t part_full_ws_bytes(int64_t n, int bits) { return full_layout(n, bits).tot
 int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, int sel_shl,
               int sel_bits, uint32_t sel_val, uint2* d_out, uint2* d_tmp, int64_t cap,
               int64_t* d_off, unsigned int* d_overflow, void* d_ws, size_t ws_bytes,
-              cudaStream_t s) {
+              cudaStream_t s, bool val_pred, uint32_t val_thr) {
+  B2_REQUIRE(ctx, !val_pred || in.pairs || in.vals, "a value predicate needs a value column");
   B2_REQUIRE(ctx, bits >= 0 && bits <= 2 * kPartMaxBits, "at most 2^20 partitions");
   const FullLayout F = full_layout(n, bits);
   if (ws_bytes < F.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition", "workspace");
@@ -702,6 +720,8 @@ int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, in
   g1.sel_bits = sel_bits;
   g1.sel_shl = sel_shl;
   g1.sel_val = sel_val;
+  g1.val_pred = val_pred;  // the first pass drops the rows; a second pass only sees survivors
+  g1.val_thr = val_thr;
   if (F.bits2 == 0) {
     return part_pass(ctx, in, n, seg, 1, g1, d_out, cap, d_off, d_overflow, base + F.off_pass,
                      F.pass_bytes, s);

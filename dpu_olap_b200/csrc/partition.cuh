@@ -15,6 +15,10 @@ struct PartGeom {
   int sel_bits = 0;  // selection predicate (hash-space slice), 0 = take every row
   int sel_shl = 0;
   uint32_t sel_val = 0;
+  // value predicate pushed down from a fused pipeline (filter -> join): keep a row iff its VALUE is
+  // below val_thr. Rows that fail are dropped by this pass (counted by neither kernel).
+  bool val_pred = false;
+  uint32_t val_thr = 0;
 };
 
 constexpr int kPartMaxBits = 10;           // per pass (warp-private u16 counters for 1024 bins)
@@ -64,6 +68,8 @@ int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_s
 // partitions, d_off (2^bits + 1 int64) their boundaries. d_tmp (capacity cap rows) is only used
 // by the two-pass path. sel_*: hash-space slice predicate (see PartGeom).
 size_t part_full_ws_bytes(int64_t n, int bits);
+// val_pred / val_thr: value predicate applied by the first pass (see PartGeom).
 int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, int sel_shl,
               int sel_bits, uint32_t sel_val, uint2* d_out, uint2* d_tmp, int64_t cap,
-              int64_t* d_off, unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s);
+              int64_t* d_off, unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s,
+              bool val_pred = false, uint32_t val_thr = 0);

@@ -409,6 +409,24 @@ class Context:
                  "b2_join_u32_dev")
         return outs[0], outs[1], outs[2], out_rows
 
+    def join_aggr_dev(self, fk, y, pk, x, y_threshold: int | None = None, ws=None, out=None, skip_bits: int = 0):
+        """Fused [filter L.y < y_threshold ->] join -> aggregate (b2_join_aggr_u32_dev): returns a
+        3 x int64 device tensor (rows, sum_y, sum_x as uint64 bit patterns); nothing is materialised."""
+        import torch
+        nl, nr = fk.numel(), pk.numel()
+        if out is None:
+            out = torch.empty(3, dtype=torch.int64, device=fk.device)
+        if ws is None:
+            ws = torch.empty(self.join_ws_bytes(nl, nr) + 256, dtype=torch.uint8, device=fk.device)
+        ws_ptr = (_dptr(ws) + 255) // 256 * 256
+        ws_bytes = ws.numel() - (ws_ptr - _dptr(ws))
+        self._ck(self._lib.b2_join_aggr_u32_dev(self._h, _dptr(fk), _dptr(y), nl, _dptr(pk), _dptr(x), nr,
+                                                0 if y_threshold is None else 1,
+                                                0 if y_threshold is None else int(y_threshold), _dptr(out),
+                                                skip_bits, ws_ptr, ws_bytes, self._stream()),
+                 "b2_join_aggr_u32_dev")
+        return out
+
     def join_pairs_dev(self, l_pairs, r_pairs, out_capacity: int, skip_bits: int, ws=None, outs=None,
                        out_rows=None):
         import torch

@@ -285,6 +285,22 @@ int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int6
                     uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
                     uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
                     void* stream);
+/* Fused pipeline [filter ->] join -> aggregate (the reference only hints at
+ * operator fusion, host/aggr/aggr_native.cc:59-65):
+ *   SELECT COUNT(*), SUM(L.y), SUM(R.x) FROM L JOIN R ON L.fk = R.pk [WHERE L.y < y_threshold]
+ * with the join's semantics above. Nothing is materialised: no filtered column, no output columns
+ * (48 GiB at SF=2048) and no output-range bookkeeping — the probe kernel adds every output row's y
+ * and x to its sums. filter_y == 0 ignores y_threshold. Sums are modulo 2^64; rows == ~0 reports a
+ * skewed hash-space slice as b2_join_u32_dev does. Workspace as b2_join_u32_dev. */
+typedef struct b2_join_aggr {
+  uint64_t rows;
+  uint64_t sum_y;
+  uint64_t sum_x;
+} b2_join_aggr;
+int b2_join_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
+                         const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, int filter_y,
+                         uint32_t y_threshold, b2_join_aggr* d_out, int hash_skip_bits, void* d_ws,
+                         size_t ws_bytes, void* stream);
 /* Same join over rows packed as 8-byte pairs, key in the low and payload in the high 32 bits
  * (little endian: {uint32 key; uint32 payload}) — the layout the multi-GPU shuffle delivers. */
 int b2_join_pairs_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, int64_t nl, const uint64_t* d_r_pairs,

@@ -17,7 +17,7 @@ LIB = HERE / "liboracle.so"
 __all__ = ["build", "RandomArrayGenerator", "gen_u32", "iota_u32", "filter_lt", "sum_u32", "take",
            "wang_hash", "bucket", "partition_ids", "join", "sort_rows", "triple_checksum",
            "make_random_batches", "make_fk_batches", "make_index_batches",
-           "filter_lt_nullable", "aggr_nullable", "take_nullable", "pack_bits", "unpack_bits"]
+           "join_aggr", "filter_lt_nullable", "aggr_nullable", "take_nullable", "pack_bits", "unpack_bits"]
 
 _lib = None
 
@@ -160,6 +160,19 @@ def join(fk, y, pk, x):
         if m <= cap:
             return tuple(a[:m].copy() for a in o)
         cap = m
+
+
+def join_aggr(fk, y, pk, x, y_threshold=None) -> dict:
+    """SELECT COUNT(*), SUM(L.y), SUM(R.x) FROM L JOIN R ON fk = pk [WHERE L.y < y_threshold]: the
+    reference's Native operators composed (filter_native.cc:52-66 on the probe side, join_native.cc:31-40,
+    aggr_native.cc:68-73 over the result columns); sums modulo 2^64."""
+    fk, y = _u32(fk), _u32(y)
+    if y_threshold is not None:
+        keep = y < np.uint32(y_threshold) if y_threshold <= 0xFFFFFFFF else np.ones(y.size, bool)
+        fk, y = fk[keep], y[keep]
+    o_fk, o_y, o_x = join(fk, y, pk, x)
+    return {"rows": int(o_fk.size), "sum_y": int(o_y.astype(np.uint64).sum(dtype=np.uint64)),
+            "sum_x": int(o_x.astype(np.uint64).sum(dtype=np.uint64))}
 
 
 def sort_rows(*cols):

@@ -379,6 +379,33 @@ def test_join_heavy_skew_oversized_partition(ctx):
     check_join(ctx, fk, y, pk, x)
 
 
+@pytest.mark.parametrize("nl,nr,domain,thr", [(0, 10, 10, None), (10, 0, 10, 5), (5000, 5000, 5000, None),
+                                              (300_000, 100_000, 100_000, 1 << 30), (200_000, 50_000, 2000, 1 << 31),
+                                              (1 << 21, 1 << 21, 1 << 21, 1 << 30), (30_000, 20_000, 50, None)])
+def test_join_aggregate_fused_pipeline(ctx, nl, nr, domain, thr):
+    """b2_join_aggr_u32_dev == filter (probe side) -> join -> count / sum y / sum x of the oracle."""
+    rng = np.random.default_rng(nl + nr + domain)
+    pk = rng.integers(0, max(domain, 1), size=nr, dtype=np.uint32)       # duplicates when domain < nr
+    x = rng.integers(0, 2**32, size=nr, dtype=np.uint32)
+    fk = rng.integers(0, max(domain, 1) + domain // 4 + 1, size=nl, dtype=np.uint32)  # some probes miss
+    y = rng.integers(0, 2**32, size=nl, dtype=np.uint32)
+    if domain == 50:
+        pk, x, fk, y = pk[:2000], x[:2000], fk[:3000], y[:3000]          # keep the quadratic output small
+    e = lambda a: dev(a) if len(a) else torch.empty(0, dtype=torch.int32, device="cuda")
+    out = ctx.join_aggr_dev(e(fk), e(y), e(pk), e(x), y_threshold=thr)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint64)
+    exp = oracle.join_aggr(fk, y, pk, x, thr)
+    assert {"rows": int(got[0]), "sum_y": int(got[1]), "sum_x": int(got[2])} == exp
+    # and the unfused path agrees: materialise the join, then aggregate its columns
+    if thr is None and len(fk) and len(pk):
+        o_fk, o_y, o_x, rows = ctx.join_dev(e(fk), e(y), e(pk), e(x), out_capacity=max(exp["rows"], 1))
+        torch.cuda.synchronize()
+        n = int(rows.cpu()[0])
+        assert n == exp["rows"]
+        assert int(host(o_x)[:n].astype(np.uint64).sum(dtype=np.uint64)) == exp["sum_x"]
+
+
 def test_join_capacity_overflow_reports_true_count(ctx):
     pk = np.zeros(100, np.uint32)
     fk = np.zeros(100, np.uint32)
