@@ -280,6 +280,61 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
   return B2_OK;
 }
 
+// Fused [filter ->] join -> aggregate over host batches: one upload, no result columns to bring back.
+int b2_join_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* l_lens,
+                          int64_t nl_batches, const uint32_t* const* r_ptrs, const int64_t* r_lens,
+                          int64_t nr_batches, int filter_y, uint32_t y_threshold, b2_join_aggr* out,
+                          b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, nl_batches >= 0 && nr_batches >= 0, "negative batch count");
+  B2_REQUIRE(ctx, out != nullptr, "out is null");
+  B2_REQUIRE(ctx, nl_batches == 0 || (l_ptrs && l_lens), "null left batch table");
+  B2_REQUIRE(ctx, nr_batches == 0 || (r_ptrs && r_lens), "null right batch table");
+  int64_t nl = 0, nr = 0;
+  B2_RETURN_NOT_OK(total_rows(ctx, l_lens, nl_batches, &nl));
+  B2_RETURN_NOT_OK(total_rows(ctx, r_lens, nr_batches, &nr));
+  b2_timings tm{};
+  DevBufs bufs;
+  EventPair up, work;
+  B2_RETURN_NOT_OK(up.init(ctx));
+  B2_RETURN_NOT_OK(work.init(ctx));
+  cudaStream_t s = ctx->s_compute;
+  uint32_t *d_fk, *d_y, *d_pk, *d_x;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_fk, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_y, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_pk, (size_t)nr * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_x, (size_t)nr * 4));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.a, s));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_fk, l_ptrs, l_lens, nl_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_y, l_ptrs + nl_batches, l_lens, nl_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_pk, r_ptrs, r_lens, nr_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_x, r_ptrs + nr_batches, r_lens, nr_batches, s, &tm.h2d_bytes));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.b, s));
+  void* d_ws = nullptr;
+  const size_t ws_bytes = b2_join_ws_bytes(nl, nr);
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_ws, ws_bytes));
+  b2_join_aggr* d_out = nullptr;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_out, sizeof(b2_join_aggr)));
+  B2_CUDA_OK(ctx, cudaEventRecord(work.a, s));
+  B2_RETURN_NOT_OK(b2_join_aggr_u32_dev(ctx, d_fk, d_y, nl, d_pk, d_x, nr, filter_y, y_threshold, d_out, 0,
+                                        d_ws, ws_bytes, s));
+  B2_CUDA_OK(ctx, cudaEventRecord(work.b, s));
+  B2_CUDA_OK(ctx, cudaMemcpyAsync(out, d_out, sizeof(b2_join_aggr), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  if (out->rows == ~0ull) return b2_set_error(ctx, B2_ERR_WORKSPACE, "join", "slice overflow");
+  tm.copy_to_dev_ms = up.ms();
+  tm.dev_work_ms = work.ms();
+  tm.d2h_bytes = sizeof(b2_join_aggr);
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
 int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
                        int64_t capacity_rows, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;

@@ -761,6 +761,24 @@ class JoinGpu:
         self._last = (t1, t2)
         return {self.fk: out[0], self.lpay: out[1], self.rpay: out[2]}
 
+    def RunAggregate(self, y_threshold: int | None = None) -> dict:
+        """Fused pipeline (b2_join_aggr_u32_host): COUNT(*), SUM(left payload), SUM(right payload) of
+        the join, optionally over the probe rows with left payload < y_threshold only — the result
+        columns are never materialised and nothing but three numbers comes back."""
+
+        class _Aggr(C.Structure):
+            _fields_ = [("rows", C.c_uint64), ("sum_y", C.c_uint64), ("sum_x", C.c_uint64)]
+
+        lt, rt = _PtrTable(self._l[0] + self._l[1]), _PtrTable(self._r[0] + self._r[1])
+        out, t = _Aggr(), Timings()
+        self.ctx._ck(self.ctx._lib.b2_join_aggr_u32_host(
+            self.ctx._h, lt.ptrs, lt.lens, len(self._l[0]), rt.ptrs, rt.lens, len(self._r[0]),
+            0 if y_threshold is None else 1, 0 if y_threshold is None else int(y_threshold),
+            C.byref(out), C.byref(t)), "b2_join_aggr_u32_host")
+        self._timers = Timers.from_timings(t)
+        self._last = (t,)
+        return {"rows": int(out.rows), f"sum_{self.lpay}": int(out.sum_y), f"sum_{self.rpay}": int(out.sum_x)}
+
     def Timers(self):
         return self._timers
 

@@ -301,6 +301,12 @@ int b2_join_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y,
                          const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, int filter_y,
                          uint32_t y_threshold, b2_join_aggr* d_out, int hash_skip_bits, void* d_ws,
                          size_t ws_bytes, void* stream);
+/* The same pipeline over host batches (tables laid out as for b2_join_u32_host): one upload, three
+ * numbers back. */
+int b2_join_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* l_lens,
+                          int64_t nl_batches, const uint32_t* const* r_ptrs, const int64_t* r_lens,
+                          int64_t nr_batches, int filter_y, uint32_t y_threshold, b2_join_aggr* out,
+                          b2_timings* timings);
 /* Same join over rows packed as 8-byte pairs, key in the low and payload in the high 32 bits
  * (little endian: {uint32 key; uint32 payload}) — the layout the multi-GPU shuffle delivers. */
 int b2_join_pairs_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, int64_t nl, const uint64_t* d_r_pairs,

@@ -237,3 +237,27 @@ def test_filter_host_into_pinned_inputs_use_the_gather_upload(ctx):
         lib.b2_ctx_set_inputs_pinned(ctx._h, 0)
         for b in batches:
             lib.b2_host_unregister(b.ctypes.data)
+
+
+def test_join_run_aggregate_fused_pipeline(ctx, ops):
+    """JoinGpu.RunAggregate == aggregates of JoinGpu.Run()'s columns (and of the oracle's join), with
+    and without the pushed-down filter on the probe side's payload."""
+    g = oracle.RandomArrayGenerator(42)
+    nb, bs = 8, 1 << 16
+    x = oracle.make_random_batches(g, nb, bs)
+    y = oracle.make_random_batches(g, nb, bs)
+    fk = oracle.make_fk_batches(g, bs, nb, bs)
+    pk = oracle.make_index_batches(nb, bs)
+    left = [{"fk": fk[b], "y": y[b]} for b in range(nb)]
+    right = [{"pk": pk[b], "x": x[b]} for b in range(nb)]
+    j = ops.JoinGpu(ctx, left, right)
+    j.Prepare()
+    cols = j.Run()
+    agg = j.RunAggregate()
+    assert agg == {"rows": cols["fk"].size, "sum_y": int(cols["y"].astype(np.uint64).sum(dtype=np.uint64)),
+                   "sum_x": int(cols["x"].astype(np.uint64).sum(dtype=np.uint64))}
+    assert j.Timers()["copy-from-dpu"] == 0.0 or j._last[0].d2h_bytes == 24
+    thr = 1 << 30
+    exp = oracle.join_aggr(np.concatenate(fk), np.concatenate(y), np.concatenate(pk), np.concatenate(x), thr)
+    assert j.RunAggregate(thr) == exp
+    assert 0 < exp["rows"] < cols["fk"].size
