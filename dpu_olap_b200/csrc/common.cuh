@@ -89,6 +89,16 @@ int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail);
 
 static inline size_t b2_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Function attributes (opt-in dynamic shared memory) are per DEVICE: a process that holds contexts
+// on several GPUs must set them on each. `flags` is a call site's static table, one entry per device.
+constexpr int kB2MaxDevices = 64;
+static inline bool b2_first_use_on_device(const b2_ctx* ctx, bool (&flags)[kB2MaxDevices]) {
+  const int d = ctx->device >= 0 && ctx->device < kB2MaxDevices ? ctx->device : 0;
+  if (flags[d]) return false;
+  flags[d] = true;
+  return true;
+}
+
 // ---- device helpers ----------------------------------------------------------------------
 #ifdef __CUDACC__
 

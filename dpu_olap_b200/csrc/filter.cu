@@ -457,8 +457,9 @@ static inline int64_t tiles_of(int64_t len) { return (len + kTileRows - 1) / kTi
 template <typename Cfg, bool kNullable = false>
 int launch_variant(b2_ctx* ctx, const FilterArgs& a, cudaStream_t s) {
   constexpr int kSmem = kNullable ? Cfg::kSmemBytesNullable : Cfg::kSmemBytes;
-  static int max_ctas = 0;  // per process; every B200 is the same
-  if (max_ctas == 0) {
+  static int max_ctas = 0;  // every B200 is the same, but the attribute must be set on each device
+  static bool seen[kB2MaxDevices] = {};
+  if (b2_first_use_on_device(ctx, seen)) {
     B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg, kNullable>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int per_sm = 0;

@@ -459,13 +459,12 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
   join_init_kernel<<<1, 1, 0, s>>>(st);
   B2_LAUNCH_CHECK(ctx, "join_init_kernel");
   if (nl > 0 && nr > 0) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool seen[kB2MaxDevices] = {};
+    if (b2_first_use_on_device(ctx, seen)) {
       B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
       B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
-      attr_done = true;
     }
     const int64_t nparts = (int64_t)1 << P.bits;
     const int part_shl = skip_bits + P.slice_bits;

@@ -127,11 +127,26 @@ __global__ void part_unit_table_kernel(const int64_t* __restrict__ seg_off, int6
 // Hash + selection + bucket of one key; returns 0xffffffff for rows outside the hash-space slice.
 // kValPred (compile time: the plain passes must not pay for it): also drop rows whose value fails
 // the pushed-down predicate val < g.val_thr.
+// The hash-space slice test as ONE mask-and-compare per row: selected <=> (h & mask) == cmp, with
+// mask = cmp = 0 when every row is taken (part_selected() spelled out costs two shifts more).
+struct SliceSel {
+  uint32_t mask, cmp;
+};
+__device__ __forceinline__ SliceSel slice_sel(const PartGeom& g) {
+  SliceSel s{0u, 0u};
+  if (g.sel_bits > 0) {
+    const int sh = 32 - g.sel_shl - g.sel_bits;
+    s.mask = ((1u << g.sel_bits) - 1u) << sh;
+    s.cmp = g.sel_val << sh;
+  }
+  return s;
+}
 template <bool kValPred>
-__device__ __forceinline__ uint32_t bucket_or_skip(uint32_t key, uint32_t val, const PartGeom& g) {
+__device__ __forceinline__ uint32_t bucket_or_skip(uint32_t key, uint32_t val, const PartGeom& g,
+                                                   const SliceSel& sel) {
   const uint32_t h = wang_hash_u32(key);
   const uint32_t b = part_bucket(h, g.shl, g.bits);
-  const bool keep = part_selected(h, g.sel_shl, g.sel_bits, g.sel_val) && (!kValPred || val < g.val_thr);
+  const bool keep = (h & sel.mask) == sel.cmp && (!kValPred || val < g.val_thr);
   return keep ? b : 0xffffffffu;
 }
 
@@ -142,6 +157,7 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                  PartGeom g, uint32_t* __restrict__ hist) {
   __shared__ uint32_t cnt[1 << kPartMaxBits];
   const int P = 1 << g.bits;
+  const SliceSel sel = slice_sel(g);
   const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
   if (!u.valid) return;
   const uint32_t tid = threadIdx.x;
@@ -160,7 +176,7 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     }
 #pragma unroll
     for (int q = 0; q < kU; ++q) {
-      const uint32_t b = bucket_or_skip<kValPred>(key[q], val[q], g);
+      const uint32_t b = bucket_or_skip<kValPred>(key[q], val[q], g, sel);
       if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
     }
   }
@@ -168,7 +184,7 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     uint32_t key, val = 0;
     if (kValPred) load_row<kAoS>(in, row, key, val);
     else key = load_key<kAoS>(in, row);
-    const uint32_t b = bucket_or_skip<kValPred>(key, val, g);
+    const uint32_t b = bucket_or_skip<kValPred>(key, val, g, sel);
     if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
   }
   __syncthreads();
@@ -194,6 +210,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   constexpr int kBpt = (1 << kPartMaxBits) / kT;  // buckets per thread in the tile scan
   extern __shared__ __align__(16) unsigned char smem[];
   const int P = 1 << g.bits;
+  const SliceSel sel = slice_sel(g);
   const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
   if (!u.valid) return;
   // shared-memory carve-up
@@ -228,7 +245,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
       for (int it = 0; it < kI; ++it) load_row<kAoS>(in, t0 + it * kT + tid, key[it], val[it]);
 #pragma unroll
       for (int it = 0; it < kI; ++it) {
-        const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g);
+        const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g, sel);
         packed[it] = b;
         if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192
       }
@@ -241,7 +258,7 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
         packed[it] = 0xffffffffu;
         if (row < u.row1) {
           load_row<kAoS>(in, row, key[it], val[it]);
-          const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g);
+          const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g, sel);
           if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);
         }
       }
@@ -360,6 +377,7 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   extern __shared__ __align__(16) unsigned char smem[];
   LcSmem& sm = *reinterpret_cast<LcSmem*>(smem);
   const int P = 1 << g.bits;
+  const SliceSel sel = slice_sel(g);
   const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
   if (!u.valid) return;
   constexpr int kW = kLcThreads / 32;
@@ -391,7 +409,7 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     for (int it = 0; it < kLcItems; ++it) {
       const int64_t row = t0 + it * kLcThreads + tid;
       if (row < u.row1) {
-        const uint32_t b = bucket_or_skip<false>(key[it], val[it], g);
+        const uint32_t b = bucket_or_skip<false>(key[it], val[it], g, sel);
         if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
       }
     }
@@ -550,12 +568,11 @@ int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const P
                    const int64_t* d_seg_off, const int64_t* unit_first, int64_t nseg, int64_t unit_rows,
                    const PartGeom& g, const uint64_t* scanned, uint2* d_out, int64_t out_cap,
                    unsigned int* d_overflow) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool seen[kB2MaxDevices] = {};
+  if (b2_first_use_on_device(ctx, seen)) {
     B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)scatter_smem_bytes(kPartMaxBits, kT * kI)));
-    attr_done = true;
   }
   part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred><<<(unsigned)units, kT, scatter_smem_bytes(bits, kT * kI), s>>>(
       in, d_seg_off, unit_first, nseg, unit_rows, g, scanned, d_out, out_cap, nullptr, d_overflow);
@@ -613,12 +630,11 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
   const uint64_t* scanned = reinterpret_cast<const uint64_t*>(base + L.off_scanned);
   if (L.max_units > 0) {
     if (d_bucket_addr) {  // peer destinations: whole 128-byte lines only (line carry)
-      static bool attr_done_p[2] = {false, false};
-      if (!attr_done_p[kAoS]) {
+      static bool seen[kB2MaxDevices] = {};  // one table per template instantiation
+      if (b2_first_use_on_device(ctx, seen)) {
         B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_lines_kernel<kAoS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(LcSmem)));
-        attr_done_p[kAoS] = true;
       }
       part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
           in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr);

@@ -691,3 +691,28 @@ def test_fused_filter_sum(ctx, n, thr):
     # the plain sum is unaffected by the template
     p = ctx.sum_dev(d)
     assert int(p.cpu().numpy().view(np.uint64)[0]) == (oracle.sum_u32(a) if n else 0)
+
+
+def test_second_device_in_the_same_process(ctx):
+    """Function attributes (opt-in shared memory) are per device: a context on another GPU of the
+    same process must work after the first one has launched every kernel."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dpu_olap_b200.ops import Context
+    rng = np.random.default_rng(12)
+    v = rng.integers(0, 2**32, size=4 * 65536, dtype=np.uint32)
+    pk = rng.permutation(200_000).astype(np.uint32)
+    fk = rng.integers(0, 200_000, size=300_000, dtype=np.uint32)
+    ctx.filter_dev(dev(v), 4, 65536, 1 << 30)          # device 0 first
+    ctx.join_dev(dev(fk), dev(fk), dev(pk), dev(pk))
+    torch.cuda.synchronize()
+    with torch.cuda.device(1):
+        c1 = Context(1)
+        d1 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to("cuda:1")
+        out, _, total = c1.filter_dev(d1(v), 4, 65536, 1 << 30)
+        o_fk, o_y, o_x, rows = c1.join_dev(d1(fk), d1(fk), d1(pk), d1(pk))
+        torch.cuda.synchronize()
+        n = int(total.cpu()[0])
+        assert np.array_equal(host(out)[:n], oracle.filter_lt(v))
+        assert int(rows.cpu()[0]) == fk.size
+        c1.close()
