@@ -22,6 +22,10 @@
 //     ranks of a warp's 512 rows cost a single 5-step shuffle scan; one CTA barrier per tile gives
 //     the warp bases; selected rows are compacted IN PLACE into the stage buffer and written out
 //     with fully coalesced stores `lag` iterations later, when the tile's global offset is known.
+//   * Waiting: data arrival (TMA) is the only thing polled on an mbarrier. "Prefix posted" and
+//     "stage drained" go through named hardware barriers (bar.arrive by the signalling warps,
+//     bar.sync by the waiting ones), so a waiting warp is descheduled instead of spinning: the
+//     mbarrier try_wait loops of the first version were 24 % of all executed instructions.
 //   * PREFIX warp: turns tile counts into global output offsets WITHOUT a look-back chain. Each
 //     tile adds its count to the word of its group (32 tiles) and super-group (1024 tiles) with a
 //     fire-and-forget atomic; a word is final when its contributor count is complete. A tile's
@@ -74,8 +78,13 @@ struct FilterArgs {
 };
 
 // Compile-time shape of one kernel variant.
-template <int kComputeThreads_, int kStages_, int kCtasPerSm_, int kLag_>
+template <int kComputeThreads_, int kStages_, int kCtasPerSm_, int kLag_, bool kNamedBars_ = false>
 struct FilterCfg {
+  // kNamedBars: "prefix posted" and "stage drained" are signalled through named hardware barriers
+  // (bar.arrive / bar.sync, ids 2 .. 2 + 2 * stages - 1) instead of mbarriers, so the waiting warps
+  // are descheduled instead of polling (the polling loops were 24 % of all executed instructions)
+  static constexpr bool kNamedBars = kNamedBars_;
+  static_assert(!kNamedBars_ || 2 + 2 * kStages_ <= 16, "named barrier ids");
   static constexpr int kLag = kLag_;  // iterations between compacting a tile and writing it out
   static_assert(kLag_ >= 1 && kStages_ >= kLag_ + 2, "need a stage in flight besides the held ones");
   static constexpr int kComputeThreads = kComputeThreads_;
@@ -153,51 +162,58 @@ filter_lt_u32_kernel(const FilterArgs a) {
 
   if (warp == kW) {
     // ================================ producer ================================
-    if (lane == 0) {
-      const uint64_t policy = l2_evict_first_policy();
-      for (int64_t n = 0;; ++n) {
-        const int s = (int)(n % kS);
-        if (n >= kS) mbar_wait(&ctl.empty[s], (uint32_t)(((n / kS) - 1) & 1));
+    // Lane 0 does the work; with named barriers the whole warp takes part in the waits.
+    const uint64_t policy = l2_evict_first_policy();
+    for (int64_t n = 0;; ++n) {
+      const int s = (int)(n % kS);
+      if (n >= kS) {
+        if (Cfg::kNamedBars) named_bar_sync(2 + kS + s, kCT + 32);
+        else if (lane == 0) mbar_wait(&ctl.empty[s], (uint32_t)(((n / kS) - 1) & 1));
+      }
+      int done = 0;
+      if (lane == 0) {
         const int64_t tile = (a.debug & 4) ? (int64_t)atomicAdd(&a.ws->ticket, 1ull)
                                            : first_tile + n * tile_stride;
         StageInfo& si = ctl.info[s];
         if (tile >= a.ntiles) {
           si.tile = -1;
           mbar_arrive(&ctl.full[s]);
-          break;
-        }
-        int64_t row0;
-        int32_t len;
-        if (a.tile_row0) {
-          row0 = a.tile_row0[tile];
-          len = a.tile_len[tile];
+          done = 1;
         } else {
-          const int64_t b = tile / a.tiles_per_batch, k = tile - b * a.tiles_per_batch;
-          row0 = b * a.batch_len + k * kTile;
-          const int64_t rest = a.batch_len - k * kTile;
-          len = rest < kTile ? (int32_t)rest : kTile;
-        }
-        const uint32_t* src = a.in + row0;
-        const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((len & 3) == 0) &&
-                         !(a.debug & 2);
-        si.tile = tile;
-        si.row0 = row0;
-        si.len = len;
-        // the tile's 512 bytes of validity ride along when they start on a 16-byte boundary
-        const bool vtma = kNullable && tma && len == kTile && (row0 & 127) == 0 &&
-                          (reinterpret_cast<uintptr_t>(a.valid) & 15) == 0;
-        si.tma = (tma ? 1 : 0) | (vtma ? 2 : 0);
-        if (tma) {
-          fence_proxy_async();  // the stage was last touched through the generic proxy
-          mbar_arrive_expect_tx(&ctl.full[s], (uint32_t)len * 4u + (vtma ? (uint32_t)Cfg::kValidBytes : 0u));
-          tma_load_1d(bufs + (size_t)s * kTile, src, (uint32_t)len * 4u, &ctl.full[s], policy);
-          if (vtma)
-            tma_load_1d(vbufs + (size_t)s * (Cfg::kValidBytes / 4), a.valid + (row0 >> 5), Cfg::kValidBytes,
-                        &ctl.full[s], policy);
-        } else {
-          mbar_arrive(&ctl.full[s]);
+          int64_t row0;
+          int32_t len;
+          if (a.tile_row0) {
+            row0 = a.tile_row0[tile];
+            len = a.tile_len[tile];
+          } else {
+            const int64_t b = tile / a.tiles_per_batch, k = tile - b * a.tiles_per_batch;
+            row0 = b * a.batch_len + k * kTile;
+            const int64_t rest = a.batch_len - k * kTile;
+            len = rest < kTile ? (int32_t)rest : kTile;
+          }
+          const uint32_t* src = a.in + row0;
+          const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((len & 3) == 0) &&
+                           !(a.debug & 2);
+          // the tile's 512 bytes of validity ride along when they start on a 16-byte boundary
+          const bool vtma = kNullable && tma && len == kTile && (row0 & 127) == 0 &&
+                            (reinterpret_cast<uintptr_t>(a.valid) & 15) == 0;
+          si.tile = tile;
+          si.row0 = row0;
+          si.len = len;
+          si.tma = (tma ? 1 : 0) | (vtma ? 2 : 0);
+          if (tma) {
+            fence_proxy_async();  // the stage was last touched through the generic proxy
+            mbar_arrive_expect_tx(&ctl.full[s], (uint32_t)len * 4u + (vtma ? (uint32_t)Cfg::kValidBytes : 0u));
+            tma_load_1d(bufs + (size_t)s * kTile, src, (uint32_t)len * 4u, &ctl.full[s], policy);
+            if (vtma)
+              tma_load_1d(vbufs + (size_t)s * (Cfg::kValidBytes / 4), a.valid + (row0 >> 5), Cfg::kValidBytes,
+                          &ctl.full[s], policy);
+          } else {
+            mbar_arrive(&ctl.full[s]);
+          }
         }
       }
+      if (__shfl_sync(0xffffffffu, done, 0)) break;
     }
     return;
   }
@@ -250,9 +266,10 @@ filter_lt_u32_kernel(const FilterArgs a) {
       if (lane == 0) {
         a.incl[tile] = prefix + total;
         ctl.prefix[s] = prefix;
-        mbar_arrive(&ctl.pre[s]);
+        if (!Cfg::kNamedBars) mbar_arrive(&ctl.pre[s]);
       }
       __syncwarp();
+      if (Cfg::kNamedBars) named_bar_arrive(2 + s, kCT + 32);  // after lane 0's store (PTX producer pattern)
     }
     return;
   }
@@ -360,14 +377,19 @@ filter_lt_u32_kernel(const FilterArgs a) {
     // ---- write out the tile compacted kLag iterations ago (its global offset is known by now) ----
     auto write_out = [&](int64_t m) {
       const int ps = (int)(m % kS);
-      mbar_wait(&ctl.pre[ps], (uint32_t)((m / kS) & 1));
+      if (Cfg::kNamedBars) named_bar_sync(2 + ps, kCT + 32);
+      else mbar_wait(&ctl.pre[ps], (uint32_t)((m / kS) & 1));
       const uint32_t* __restrict__ stg = bufs + (size_t)ps * kTile;
       uint32_t* __restrict__ dst = a.out + ctl.prefix[ps];
       const uint32_t cnt_m = ctl.total[ps];
       for (uint32_t i = tid; i < cnt_m; i += kCT) st_stream_u32(dst + i, stg[i]);
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl.empty[ps]);
+      if (Cfg::kNamedBars) {
+        named_bar_arrive(2 + kS + ps, kCT + 32);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl.empty[ps]);
+      }
     };
     if (n >= Cfg::kLag) write_out(n - Cfg::kLag);
     if (!valid) {  // drain: tiles n-kLag+1 .. n-1 were compacted before barrier A
@@ -446,10 +468,12 @@ using Cfg2 = FilterCfg<256, 4, 3, 2>;
 using Cfg3 = FilterCfg<256, 5, 2, 2>;
 using Cfg4 = FilterCfg<256, 5, 2, 1>;
 using Cfg5 = FilterCfg<256, 6, 2, 3>;
-constexpr int kNumVariants = 6;
+using Cfg6 = FilterCfg<256, 4, 3, 2, true>;   // Cfg2 with named barriers for "prefix posted" / "stage drained"
+using Cfg7 = FilterCfg<256, 5, 2, 3, true>;
+constexpr int kNumVariants = 8;
 constexpr int kTileRows = Cfg0::kTile;
 
-int g_filter_variant = 2;  // <256 threads, 4 stages, 3 CTAs/SM, lag 2>: best on B200 (profiles/r1_filter.md)
+int g_filter_variant = 6;  // <256 threads, 4 stages, 3 CTAs/SM, lag 2, named barriers>: best on B200 (profiles/r1_filter.md)
 int g_filter_debug = 0;  // tools/filter_lab.py switches this through b200olap_tune_filter_variant()
 
 static inline int64_t tiles_of(int64_t len) { return (len + kTileRows - 1) / kTileRows; }
@@ -558,13 +582,15 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, const uint32_t* d_valid, in
     a.incl = incl;
     a.debug = g_filter_debug;
     if (d_valid) {  // one shape for the nullable kernel: the default one
-      B2_RETURN_NOT_OK((launch_variant<Cfg2, true>(ctx, a, s)));
+      B2_RETURN_NOT_OK((launch_variant<Cfg6, true>(ctx, a, s)));
     } else switch (g_filter_variant) {
       case 1: B2_RETURN_NOT_OK(launch_variant<Cfg1>(ctx, a, s)); break;
       case 2: B2_RETURN_NOT_OK(launch_variant<Cfg2>(ctx, a, s)); break;
       case 3: B2_RETURN_NOT_OK(launch_variant<Cfg3>(ctx, a, s)); break;
       case 4: B2_RETURN_NOT_OK(launch_variant<Cfg4>(ctx, a, s)); break;
       case 5: B2_RETURN_NOT_OK(launch_variant<Cfg5>(ctx, a, s)); break;
+      case 6: B2_RETURN_NOT_OK(launch_variant<Cfg6>(ctx, a, s)); break;
+      case 7: B2_RETURN_NOT_OK(launch_variant<Cfg7>(ctx, a, s)); break;
       default: B2_RETURN_NOT_OK(launch_variant<Cfg0>(ctx, a, s)); break;
     }
   }

@@ -73,4 +73,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Non-blocking arrival at a named barrier (the producer side of PTX's bar.arrive / bar.sync
+// producer-consumer pattern): the waiting side sits in bar.sync, descheduled by the hardware,
+// instead of polling an mbarrier.
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 #endif  // __CUDACC__
