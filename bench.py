@@ -829,7 +829,8 @@ def main():
                          "frac": achieved / peak,
                          # DRAM bytes per launch per GPU: ncu --set full at SF=128 measured
                          # dram__bytes_read + dram__bytes_write = 0.993 x the algorithmic bytes
-                         # (profiles/r1_ncu_full_final_sf128.csv); scaled to this launch's rows
+                         # (profiles/r1_ncu_full_final_sf128.csv, r1_ncu_full_filter_named_barriers_sf128.csv);
+                         # scaled to this launch's rows
                          "traffic": 0.993 * fres["algorithmic_bytes"] / D.world,
                          "traffic_source": "ncu dram__bytes_{read,write}.sum at SF=128 (0.993 x algorithmic), scaled by rows",
                          "algorithmic_bytes_per_launch": fres["algorithmic_bytes"] / D.world,
