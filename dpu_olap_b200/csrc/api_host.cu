@@ -808,11 +808,11 @@ int b2_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const uint8
   return B2_OK;
 }
 
-int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
-                                        const uint8_t* const* valid_ptrs, const int64_t* valid_bit_offsets,
-                                        const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
-                                        uint32_t* out, int64_t out_capacity, int64_t* out_counts,
-                                        uint64_t* total, b2_timings* timings) {
+static int filter_typed_host_into(b2_ctx* ctx, int dtype, const uint32_t* const* batch_ptrs,
+                                  const uint8_t* const* valid_ptrs, const int64_t* valid_bit_offsets,
+                                  const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                                  uint32_t* out, int64_t out_capacity, int64_t* out_counts,
+                                  uint64_t* total, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
   B2_REQUIRE(ctx, total != nullptr && out_capacity >= 0, "bad result arguments");
   B2_REQUIRE(ctx, nbatches == 0 || out_counts != nullptr, "out_counts is null");
@@ -847,8 +847,8 @@ int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batc
       B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
       tm.h2d_bytes += (int64_t)bits.size();
     }
-    B2_RETURN_NOT_OK(b2_filter_lt_u32_nullable_dev(ctx, d_col, d_valid, nbatches, L.batch_len, threshold,
-                                                   d_out, d_end, d_end + nbatches, nullptr, d_ws, ws_bytes, s));
+    B2_RETURN_NOT_OK(b2_filter_lt_32_dev(ctx, d_col, dtype, threshold, d_valid, nbatches, L.batch_len, d_out,
+                                         d_end, d_end + nbatches, nullptr, d_ws, ws_bytes, s));
     std::vector<int64_t> end((size_t)nbatches + 1);
     B2_CUDA_OK(ctx, cudaMemcpyAsync(end.data(), d_end, (size_t)(nbatches + 1) * 8, cudaMemcpyDeviceToHost, s));
     B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
@@ -870,6 +870,26 @@ int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batc
   tm.kernel_launches = (int32_t)(ctx->launches - launches0);
   if (timings) *timings = tm;
   return B2_OK;
+}
+
+int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
+                                        const uint8_t* const* valid_ptrs, const int64_t* valid_bit_offsets,
+                                        const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
+                                        uint32_t* out, int64_t out_capacity, int64_t* out_counts,
+                                        uint64_t* total, b2_timings* timings) {
+  return filter_typed_host_into(ctx, B2_U32, batch_ptrs, valid_ptrs, valid_bit_offsets, batch_lens, nbatches,
+                                threshold, out, out_capacity, out_counts, total, timings);
+}
+
+int b2_filter_lt_32_host_into(b2_ctx* ctx, const void* const* batch_ptrs, const uint8_t* const* valid_ptrs,
+                              const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
+                              int dtype, uint32_t threshold_bits, void* out, int64_t out_capacity,
+                              int64_t* out_counts, uint64_t* total, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, dtype == B2_U32 || dtype == B2_I32 || dtype == B2_F32, "dtype must be B2_U32, B2_I32 or B2_F32");
+  return filter_typed_host_into(ctx, dtype, reinterpret_cast<const uint32_t* const*>(batch_ptrs), valid_ptrs,
+                                valid_bit_offsets, batch_lens, nbatches, threshold_bits,
+                                static_cast<uint32_t*>(out), out_capacity, out_counts, total, timings);
 }
 
 int b2_take_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* value_ptrs,

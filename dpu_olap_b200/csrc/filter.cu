@@ -123,19 +123,49 @@ struct FilterSmemCtl {
 };
 static_assert(sizeof(FilterSmemCtl) <= 1024, "control block must fit its reservation");
 
-// 1 if a < b (unsigned) else 0.
-__device__ __forceinline__ uint32_t lt_u32(uint32_t a, uint32_t b) { return a < b ? 1u : 0u; }
-
-// acc += inc if v < thr: compare + predicated add, two instructions per row.
-__device__ __forceinline__ void count_lt(uint32_t& acc, uint32_t v, uint32_t thr, uint32_t inc) {
-  asm("{\n\t.reg .pred q;\n\t"
-      "setp.lt.u32 q, %1, %2;\n\t"
-      "@q add.u32 %0, %0, %3;\n\t}"
-      : "+r"(acc)
-      : "r"(v), "r"(thr), "r"(inc));
+// The column's 32-bit type decides how `v < threshold` compares (the reference
+// fixes `#define T uint32_t`, dpu/shared/common.h:3). Values are moved as raw 32-bit words.
+enum { kCmpU32 = B2_U32, kCmpS32 = B2_I32, kCmpF32 = B2_F32 };
+// A bit pattern that is never `< threshold` for any threshold: stands in for rows past the end of a
+// tile and for null rows. (f32: a NaN — every ordered comparison with it is false.)
+template <int kCmp>
+__device__ __forceinline__ constexpr uint32_t never_lt() {
+  return kCmp == kCmpU32 ? 0xffffffffu : (kCmp == kCmpS32 ? 0x7fffffffu : 0x7fc00000u);
+}
+// 1 if a < b in the column's type else 0.
+template <int kCmp>
+__device__ __forceinline__ uint32_t lt_32(uint32_t a, uint32_t b) {
+  if (kCmp == kCmpS32) return (int32_t)a < (int32_t)b ? 1u : 0u;
+  if (kCmp == kCmpF32) return __uint_as_float(a) < __uint_as_float(b) ? 1u : 0u;
+  return a < b ? 1u : 0u;
 }
 
-template <typename Cfg, bool kNullable>
+// acc += inc if v < thr: compare + predicated add, two instructions per row.
+template <int kCmp>
+__device__ __forceinline__ void count_lt(uint32_t& acc, uint32_t v, uint32_t thr, uint32_t inc) {
+  if (kCmp == kCmpS32) {
+    asm("{\n\t.reg .pred q;\n\t"
+        "setp.lt.s32 q, %1, %2;\n\t"
+        "@q add.u32 %0, %0, %3;\n\t}"
+        : "+r"(acc)
+        : "r"(v), "r"(thr), "r"(inc));
+  } else if (kCmp == kCmpF32) {
+    asm("{\n\t.reg .pred q;\n\t.reg .f32 fa, fb;\n\t"
+        "mov.b32 fa, %1;\n\tmov.b32 fb, %2;\n\t"
+        "setp.lt.f32 q, fa, fb;\n\t"
+        "@q add.u32 %0, %0, %3;\n\t}"
+        : "+r"(acc)
+        : "r"(v), "r"(thr), "r"(inc));
+  } else {
+    asm("{\n\t.reg .pred q;\n\t"
+        "setp.lt.u32 q, %1, %2;\n\t"
+        "@q add.u32 %0, %0, %3;\n\t}"
+        : "+r"(acc)
+        : "r"(v), "r"(thr), "r"(inc));
+  }
+}
+
+template <typename Cfg, bool kNullable, int kCmp>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kCtasPerSm)
 filter_lt_u32_kernel(const FilterArgs a) {
   constexpr int kCT = Cfg::kComputeThreads, kS = Cfg::kStages, kW = Cfg::kWarps, kTile = Cfg::kTile;
@@ -311,13 +341,13 @@ filter_lt_u32_kernel(const FilterArgs a) {
           for (int j = 0; j < kVecPerThread; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (!((vw[j] >> e) & 1u)) v[j][e] = 0xffffffffu;  // a null row never matches
+              if (!((vw[j] >> e) & 1u)) v[j][e] = never_lt<kCmp>();  // a null row never matches
         }
         uint32_t cnt_hi = 0;  // two chains halve the dependent-add latency
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) count_lt(j < 2 ? cnt : cnt_hi, v[j][e], a.thr, 1u << (8 * j));
+          for (int e = 0; e < 4; ++e) count_lt<kCmp>(j < 2 ? cnt : cnt_hi, v[j][e], a.thr, 1u << (8 * j));
         cnt += cnt_hi;
       } else {
         const uint32_t* __restrict__ src = a.in + si.row0;
@@ -326,16 +356,16 @@ filter_lt_u32_kernel(const FilterArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const uint32_t i = e0 + j * 128 + e;
-            // rows past the end of the tile never match (0xffffffff < thr is false for every thr)
-            v[j][e] = 0xffffffffu;
+            // rows past the end of the tile never match
+            v[j][e] = never_lt<kCmp>();
             if ((int32_t)i < si.len) {
               v[j][e] = (si.tma & 1) ? buf[i] : ld_stream_u32(src + i);
               if (kNullable) {
                 const int64_t r = si.row0 + i;
-                if (!((__ldg(a.valid + (r >> 5)) >> (r & 31)) & 1u)) v[j][e] = 0xffffffffu;
+                if (!((__ldg(a.valid + (r >> 5)) >> (r & 31)) & 1u)) v[j][e] = never_lt<kCmp>();
               }
             }
-            cnt += ((int32_t)i < si.len ? lt_u32(v[j][e], a.thr) : 0u) << (8 * j);
+            cnt += ((int32_t)i < si.len ? lt_32<kCmp>(v[j][e], a.thr) : 0u) << (8 * j);
           }
         }
       }
@@ -408,14 +438,35 @@ filter_lt_u32_kernel(const FilterArgs a) {
       uint32_t p = buf_s + 4u * (wbase + segbase + ((excl >> (8 * j)) & 0xffu));
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        asm volatile(
-            "{\n\t.reg .pred q;\n\t"
-            "setp.lt.u32 q, %1, %2;\n\t"
-            "@q st.shared.u32 [%0], %1;\n\t"
-            "@q add.u32 %0, %0, 4;\n\t}"
-            : "+r"(p)
-            : "r"(v[j][e]), "r"(a.thr)
-            : "memory");
+        if (kCmp == kCmpS32) {
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t"
+              "setp.lt.s32 q, %1, %2;\n\t"
+              "@q st.shared.u32 [%0], %1;\n\t"
+              "@q add.u32 %0, %0, 4;\n\t}"
+              : "+r"(p)
+              : "r"(v[j][e]), "r"(a.thr)
+              : "memory");
+        } else if (kCmp == kCmpF32) {
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t.reg .f32 fa, fb;\n\t"
+              "mov.b32 fa, %1;\n\tmov.b32 fb, %2;\n\t"
+              "setp.lt.f32 q, fa, fb;\n\t"
+              "@q st.shared.u32 [%0], %1;\n\t"
+              "@q add.u32 %0, %0, 4;\n\t}"
+              : "+r"(p)
+              : "r"(v[j][e]), "r"(a.thr)
+              : "memory");
+        } else {
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t"
+              "setp.lt.u32 q, %1, %2;\n\t"
+              "@q st.shared.u32 [%0], %1;\n\t"
+              "@q add.u32 %0, %0, 4;\n\t}"
+              : "+r"(p)
+              : "r"(v[j][e]), "r"(a.thr)
+              : "memory");
+        }
       }
     }
   }
@@ -478,23 +529,23 @@ int g_filter_debug = 0;  // tools/filter_lab.py switches this through b200olap_t
 
 static inline int64_t tiles_of(int64_t len) { return (len + kTileRows - 1) / kTileRows; }
 
-template <typename Cfg, bool kNullable = false>
+template <typename Cfg, bool kNullable = false, int kCmp = kCmpU32>
 int launch_variant(b2_ctx* ctx, const FilterArgs& a, cudaStream_t s) {
   constexpr int kSmem = kNullable ? Cfg::kSmemBytesNullable : Cfg::kSmemBytes;
   static int max_ctas = 0;  // every B200 is the same, but the attribute must be set on each device
   static bool seen[kB2MaxDevices] = {};
   if (b2_first_use_on_device(ctx, seen)) {
-    B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg, kNullable>,
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg, kNullable, kCmp>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int per_sm = 0;
     B2_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                        &per_sm, filter_lt_u32_kernel<Cfg, kNullable>, Cfg::kThreads, kSmem));
+                        &per_sm, filter_lt_u32_kernel<Cfg, kNullable, kCmp>, Cfg::kThreads, kSmem));
     if (per_sm < 1) return b2_set_error(ctx, B2_ERR_CUDA, "filter kernel", "does not fit an SM");
     if (per_sm > Cfg::kCtasPerSm) per_sm = Cfg::kCtasPerSm;
     max_ctas = per_sm * ctx->sm_count;
   }
   const int64_t grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
-  filter_lt_u32_kernel<Cfg, kNullable><<<(unsigned)grid, Cfg::kThreads, kSmem, s>>>(a);
+  filter_lt_u32_kernel<Cfg, kNullable, kCmp><<<(unsigned)grid, Cfg::kThreads, kSmem, s>>>(a);
   B2_LAUNCH_CHECK(ctx, "filter_lt_u32_kernel");
   return B2_OK;
 }
@@ -527,7 +578,7 @@ int64_t ragged_tiles(const int64_t* h_batch_off, int64_t nbatches) {
   return n;
 }
 
-int filter_launch(b2_ctx* ctx, const uint32_t* d_in, const uint32_t* d_valid, int64_t nbatches, int64_t batch_len,
+int filter_launch(b2_ctx* ctx, int cmp, const uint32_t* d_in, const uint32_t* d_valid, int64_t nbatches, int64_t batch_len,
                   const int64_t* h_batch_off, const int64_t* d_batch_off, uint32_t thr,
                   uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
                   const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, cudaStream_t s) {
@@ -581,7 +632,13 @@ int filter_launch(b2_ctx* ctx, const uint32_t* d_in, const uint32_t* d_valid, in
     a.sgrp = reinterpret_cast<uint64_t*>(base + w.sgrp_off);
     a.incl = incl;
     a.debug = g_filter_debug;
-    if (d_valid) {  // one shape for the nullable kernel: the default one
+    if (cmp == kCmpS32) {  // typed and nullable kernels exist in one shape, the default one
+      if (d_valid) B2_RETURN_NOT_OK((launch_variant<Cfg6, true, kCmpS32>(ctx, a, s)));
+      else B2_RETURN_NOT_OK((launch_variant<Cfg6, false, kCmpS32>(ctx, a, s)));
+    } else if (cmp == kCmpF32) {
+      if (d_valid) B2_RETURN_NOT_OK((launch_variant<Cfg6, true, kCmpF32>(ctx, a, s)));
+      else B2_RETURN_NOT_OK((launch_variant<Cfg6, false, kCmpF32>(ctx, a, s)));
+    } else if (d_valid) {
       B2_RETURN_NOT_OK((launch_variant<Cfg6, true>(ctx, a, s)));
     } else switch (g_filter_variant) {
       case 1: B2_RETURN_NOT_OK(launch_variant<Cfg1>(ctx, a, s)); break;
@@ -633,9 +690,24 @@ int b2_filter_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, in
   B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
   B2_REQUIRE(ctx, nbatches * batch_len == 0 || (d_in && d_out), "null column pointer");
-  return filter_launch(ctx, d_in, nullptr, nbatches, batch_len, nullptr, nullptr, threshold, d_out,
+  return filter_launch(ctx, kCmpU32, d_in, nullptr, nbatches, batch_len, nullptr, nullptr, threshold, d_out,
                        d_batch_end, d_total, d_carry_in, d_ws, ws_bytes,
                        static_cast<cudaStream_t>(stream));
+}
+
+int b2_filter_lt_32_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_t threshold_bits,
+                        const uint8_t* d_valid, int64_t nbatches, int64_t batch_len, void* d_out,
+                        int64_t* d_batch_end, int64_t* d_total, const int64_t* d_carry_in, void* d_ws,
+                        size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, dtype == B2_U32 || dtype == B2_I32 || dtype == B2_F32, "dtype must be B2_U32, B2_I32 or B2_F32");
+  B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
+  B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
+  B2_REQUIRE(ctx, nbatches * batch_len == 0 || (d_in && d_out), "null column pointer");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_valid) & 3) == 0, "validity bitmap must be 4-byte aligned");
+  return filter_launch(ctx, dtype, static_cast<const uint32_t*>(d_in), reinterpret_cast<const uint32_t*>(d_valid),
+                       nbatches, batch_len, nullptr, nullptr, threshold_bits, static_cast<uint32_t*>(d_out),
+                       d_batch_end, d_total, d_carry_in, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int b2_filter_lt_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid,
@@ -647,7 +719,7 @@ int b2_filter_lt_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
   B2_REQUIRE(ctx, nbatches * batch_len == 0 || (d_in && d_out), "null column pointer");
   B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_valid) & 3) == 0, "validity bitmap must be 4-byte aligned");
-  return filter_launch(ctx, d_in, reinterpret_cast<const uint32_t*>(d_valid), nbatches, batch_len, nullptr,
+  return filter_launch(ctx, kCmpU32, d_in, reinterpret_cast<const uint32_t*>(d_valid), nbatches, batch_len, nullptr,
                        nullptr, threshold, d_out, d_batch_end, d_total, d_carry_in, d_ws, ws_bytes,
                        static_cast<cudaStream_t>(stream));
 }
@@ -663,7 +735,7 @@ int b2_filter_lt_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_in, const int64_t
   for (int64_t b = 0; b < nbatches; ++b)
     B2_REQUIRE(ctx, h_batch_off[b + 1] >= h_batch_off[b], "batch offsets must be non-decreasing");
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
-  return filter_launch(ctx, d_in, nullptr, nbatches, 0, h_batch_off, d_batch_off, threshold, d_out,
+  return filter_launch(ctx, kCmpU32, d_in, nullptr, nbatches, 0, h_batch_off, d_batch_off, threshold, d_out,
                        d_batch_end, d_total, d_carry_in, d_ws, ws_bytes,
                        static_cast<cudaStream_t>(stream));
 }

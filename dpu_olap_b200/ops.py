@@ -85,47 +85,68 @@ def _column(batch: Any, name_or_index) -> np.ndarray:
     return _as_u32(batch)
 
 
+# 32-bit column types the filter compares natively (b2_dtype32, include/b200olap.h)
+_DTYPES32 = {np.dtype(np.uint32): 0, np.dtype(np.int32): 1, np.dtype(np.float32): 2}
+
+
+def _threshold_bits(threshold, dtype: np.dtype) -> int:
+    """Bit pattern of the threshold in the column's type."""
+    return int(np.array([threshold], dtype=dtype).view(np.uint32)[0])
+
+
 class _NullableCol:
     """One column of one batch that may carry an Arrow validity bitmap:
     ``values`` is the uint32 data (null slots hold whatever the buffer holds), ``valid`` a uint8
     array holding the bitmap (bit ``offset + r`` = row r, LSB first) or None when there are no nulls."""
 
-    __slots__ = ("values", "valid", "offset", "_keep")
+    __slots__ = ("values", "valid", "offset", "dtype", "_keep")
 
     def __init__(self, values: np.ndarray, valid=None, offset: int = 0, keep=None):
-        self.values, self.valid, self.offset, self._keep = values, valid, int(offset), keep
+        self.dtype = values.dtype                       # the column's own 32-bit type
+        self.values = values.view(np.uint32)            # what crosses the ABI: raw 32-bit words
+        self.valid, self.offset, self._keep = valid, int(offset), keep
 
 
-def _as_nullable(col: Any) -> _NullableCol:
+def _as_nullable(col: Any, typed: bool = False) -> _NullableCol:
+    """typed=True also admits int32 / float32 columns (filter only)."""
+    ok = tuple(_DTYPES32) if typed else (np.dtype(np.uint32),)
     if pa is not None and isinstance(col, (pa.Array, pa.ChunkedArray)):
         if isinstance(col, pa.ChunkedArray):
             col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
-        if col.type != pa.uint32():
-            raise TypeError(f"expected uint32 column, got {col.type}")
-        if col.null_count == 0:
-            return _NullableCol(_as_u32(col))
+        try:
+            dt = np.dtype(col.type.to_pandas_dtype())
+        except NotImplementedError:
+            dt = None
+        if dt not in ok:
+            raise TypeError(f"expected a {' / '.join(str(d) for d in ok)} column, got {col.type}")
         vbuf, dbuf = col.buffers()[0], col.buffers()[1]
-        values = np.frombuffer(dbuf, dtype=np.uint32)[col.offset:col.offset + len(col)]
+        values = (np.frombuffer(dbuf, dtype=dt)[col.offset:col.offset + len(col)] if dbuf is not None
+                  else np.empty(0, dtype=dt))
+        if col.null_count == 0:
+            return _NullableCol(values, keep=col)
         return _NullableCol(values, np.frombuffer(vbuf, dtype=np.uint8), col.offset, keep=col)
     if isinstance(col, np.ma.MaskedArray):
         data = np.ascontiguousarray(np.ma.getdata(col))
-        if data.dtype != np.uint32:
-            raise TypeError(f"expected uint32 column, got {data.dtype}")
+        if data.dtype not in ok:
+            raise TypeError(f"expected a {' / '.join(str(d) for d in ok)} column, got {data.dtype}")
         mask = np.ma.getmaskarray(col)
         if not mask.any():
             return _NullableCol(data)
         return _NullableCol(data, np.packbits(~mask, bitorder="little"), 0)
-    return _NullableCol(_as_u32(col))
+    a = np.asarray(col)
+    if a.dtype not in ok:
+        raise TypeError(f"expected a {' / '.join(str(d) for d in ok)} column, got {a.dtype}")
+    return _NullableCol(np.ascontiguousarray(a))
 
 
-def _nullable_column(batch: Any, name_or_index) -> _NullableCol:
+def _nullable_column(batch: Any, name_or_index, typed: bool = False) -> _NullableCol:
     if pa is not None and isinstance(batch, pa.RecordBatch):
         i = batch.schema.get_field_index(name_or_index) if isinstance(name_or_index, str) else name_or_index
-        return _as_nullable(batch.column(i))
+        return _as_nullable(batch.column(i), typed)
     if isinstance(batch, dict):
         return _as_nullable(batch[name_or_index] if isinstance(name_or_index, str)
-                            else list(batch.values())[name_or_index])
-    return _as_nullable(batch)
+                            else list(batch.values())[name_or_index], typed)
+    return _as_nullable(batch, typed)
 
 
 class _ValidTable:
@@ -298,6 +319,22 @@ class Context:
                                                          threshold, _dptr(out), _dptr(batch_end), _dptr(total),
                                                          0, _dptr(ws), ws.numel(), self._stream()),
                  "b2_filter_lt_u32_nullable_dev")
+        return out, batch_end, total
+
+    def filter_typed_dev(self, col, dtype, threshold, nbatches: int, batch_len: int, valid=None):
+        """Filter `v < threshold` over an int32 / float32 / uint32 column held as a 32-bit device tensor
+        (b2_filter_lt_32_dev). Returns (out (same torch dtype as col), batch_end, total)."""
+        import torch
+        dt = np.dtype(dtype)
+        dev = col.device
+        out = torch.empty(max(nbatches * batch_len, 1), dtype=col.dtype, device=dev)
+        batch_end = torch.empty(max(nbatches, 1), dtype=torch.int64, device=dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        ws = torch.empty(self.filter_ws_bytes(nbatches, batch_len), dtype=torch.uint8, device=dev)
+        self._ck(self._lib.b2_filter_lt_32_dev(self._h, _dptr(col), _DTYPES32[dt], _threshold_bits(threshold, dt),
+                                               _dptr(valid), nbatches, batch_len, _dptr(out), _dptr(batch_end),
+                                               _dptr(total), 0, _dptr(ws), ws.numel(), self._stream()),
+                 "b2_filter_lt_32_dev")
         return out, batch_end, total
 
     def aggr_dev(self, col, valid=None, out=None):
@@ -554,10 +591,14 @@ class FilterGpu:
 
     def __init__(self, ctx: Context, batches: Sequence[Any], threshold: int = FILTER_THRESHOLD):
         self.ctx = ctx
-        self._ncols = [_nullable_column(b, 0) for b in batches]
+        self._ncols = [_nullable_column(b, 0, typed=True) for b in batches]
         self._cols = [c.values for c in self._ncols]
         self._valid = _ValidTable(self._ncols)
-        self.threshold = int(threshold)
+        kinds = {c.dtype for c in self._ncols}
+        if len(kinds) > 1:
+            raise TypeError(f"batches of different types: {sorted(str(k) for k in kinds)}")
+        self.dtype = kinds.pop() if kinds else np.dtype(np.uint32)   # uint32 as the reference; int32 / float32 too
+        self.threshold = threshold if self.dtype.kind == "f" else int(threshold)
         self._timers = None
 
     def Prepare(self) -> None:  # the reference loads the DPU binary here (filter_dpu.cc:23-32)
@@ -583,12 +624,12 @@ class FilterGpu:
         tab = _PtrTable(self._cols)
         counts = (C.c_int64 * max(tab.n, 1))()
         total = C.c_uint64(0)
-        flat = np.empty(sum(a.size for a in self._cols), dtype=np.uint32)
+        flat = np.empty(sum(a.size for a in self._cols), dtype=self.dtype)
         t = Timings()
-        self.ctx._ck(self.ctx._lib.b2_filter_lt_u32_nullable_host_into(
-            self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n, self.threshold,
-            flat.ctypes.data, flat.size, counts, C.byref(total), C.byref(t)),
-            "b2_filter_lt_u32_nullable_host_into")
+        self.ctx._ck(self.ctx._lib.b2_filter_lt_32_host_into(
+            self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n, _DTYPES32[self.dtype],
+            _threshold_bits(self.threshold, self.dtype), flat.ctypes.data, flat.size, counts, C.byref(total),
+            C.byref(t)), "b2_filter_lt_32_host_into")
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         if _count_only:
@@ -598,7 +639,7 @@ class FilterGpu:
 
     def GetResult(self, _count_only: bool = False):
         """One uint32 array per input batch, in batch order (ChunkedArray chunks, :162-166)."""
-        if self._valid.any:
+        if self._valid.any or self.dtype != np.dtype(np.uint32):
             return self._get_result_nullable(_count_only)
         tab, counts, total, t1 = self._run()
         # the reference's Run() is GetResult()->length(): the result is always pulled back

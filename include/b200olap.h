@@ -164,6 +164,15 @@ int b2_filter_lt_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8
                                   int64_t nbatches, int64_t batch_len, uint32_t threshold,
                                   uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
                                   const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, void* stream);
+/* Other 32-bit column types (the reference fixes `#define T uint32_t`, dpu/shared/common.h:3):
+ * the same kernel comparing `v < threshold` as int32 or float32 (IEEE: a NaN row is never selected,
+ * as in Arrow). Values travel as raw 32-bit words; threshold_bits is the threshold's bit pattern;
+ * d_valid as above (NULL = no nulls). */
+enum b2_dtype32 { B2_U32 = 0, B2_I32 = 1, B2_F32 = 2 };
+int b2_filter_lt_32_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_t threshold_bits,
+                        const uint8_t* d_valid, int64_t nbatches, int64_t batch_len, void* d_out,
+                        int64_t* d_batch_end, int64_t* d_total, const int64_t* d_carry_in, void* d_ws,
+                        size_t ws_bytes, void* stream);
 /* Ragged variant: batch b occupies d_in[d_batch_off[b] .. d_batch_off[b+1]) (int64 device array
  * of nbatches+1 entries; host copy h_batch_off is needed to size the launch). Empty batches ok. */
 size_t b2_filter_ragged_ws_bytes(const int64_t* h_batch_off, int64_t nbatches);
@@ -202,6 +211,11 @@ int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batc
                                         const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
                                         uint32_t* out, int64_t out_capacity, int64_t* out_counts,
                                         uint64_t* total, b2_timings* timings);
+/* The same for int32 / float32 columns (see b2_filter_lt_32_dev): raw 32-bit words in and out. */
+int b2_filter_lt_32_host_into(b2_ctx* ctx, const void* const* batch_ptrs, const uint8_t* const* valid_ptrs,
+                              const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
+                              int dtype, uint32_t threshold_bits, void* out, int64_t out_capacity,
+                              int64_t* out_counts, uint64_t* total, b2_timings* timings);
 
 /* ---- Take (replaces dpu/shared/kernels/take.c:12-47) ------------------------------------- */
 /* Batch-local gather, no bounds check (take.c:36, TakeOptions::NoBoundsCheck take_native.cc:27):

@@ -17,7 +17,7 @@ LIB = HERE / "liboracle.so"
 __all__ = ["build", "RandomArrayGenerator", "gen_u32", "iota_u32", "filter_lt", "sum_u32", "take",
            "wang_hash", "bucket", "partition_ids", "join", "sort_rows", "triple_checksum",
            "make_random_batches", "make_fk_batches", "make_index_batches",
-           "join_aggr", "filter_lt_nullable", "aggr_nullable", "take_nullable", "pack_bits", "unpack_bits"]
+           "join_aggr", "filter_lt_typed", "filter_lt_nullable", "aggr_nullable", "take_nullable", "pack_bits", "unpack_bits"]
 
 _lib = None
 
@@ -199,6 +199,16 @@ def filter_lt_nullable(values, valid, thr: int = 1 << 30) -> np.ndarray:
     """Acero filter(less(v, thr)): a null predicate drops the row, so the result has no nulls."""
     v = _u32(values)
     keep = np.asarray(valid, dtype=bool) & (v < np.uint32(thr) if thr <= 0xFFFFFFFF else np.ones(v.size, bool))
+    return v[keep].copy()
+
+
+def filter_lt_typed(values, valid, thr) -> np.ndarray:
+    """The same filter over an int32 / float32 / uint32 column in ITS type's order (Arrow's `less`:
+    signed for int32, IEEE for float32 — a NaN row, like a null one, is never selected)."""
+    v = np.ascontiguousarray(values)
+    assert v.dtype in (np.uint32, np.int32, np.float32)
+    with np.errstate(invalid="ignore"):
+        keep = np.asarray(valid, dtype=bool) & (v < np.asarray(thr, dtype=v.dtype))
     return v[keep].copy()
 
 

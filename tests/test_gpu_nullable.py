@@ -180,3 +180,57 @@ def test_nullable_ragged_batches_are_rejected_loudly(ctx):
     assert e.value.status == 4  # B2_ERR_UNSUPPORTED
     with pytest.raises(ValueError):  # the join has no null semantics here
         ops.JoinGpu(ctx, [{"fk": batches[0], "y": batches[0]}], [{"pk": batches[0], "x": batches[0]}])
+
+
+# ---- other 32-bit types (b2_filter_lt_32_dev) ----------------------------------------------------------
+def typed_column(rng, dtype, n):
+    if dtype == np.float32:
+        v = (rng.standard_normal(n) * 3).astype(np.float32)
+        v[::97] = np.nan
+        v[::101] = np.inf
+        v[::103] = -np.inf
+        v[::107] = -0.0
+        return v
+    info = np.iinfo(dtype)
+    return rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+
+
+@pytest.mark.parametrize("dtype,thr", [(np.int32, -5), (np.int32, 0), (np.int32, 2**31 - 1), (np.int32, -2**31),
+                                        (np.float32, 0.0), (np.float32, -1.5), (np.float32, np.inf),
+                                        (np.float32, np.nan), (np.uint32, 1 << 30)])
+@pytest.mark.parametrize("nb,bl,null_frac", [(6, 65536, 0.0), (5, 4100, 0.3), (3, 12288, 0.5)])
+def test_filter_typed_dev(ctx, dtype, thr, nb, bl, null_frac):
+    rng = np.random.default_rng(nb * bl + int(null_frac * 10))
+    v = typed_column(rng, dtype, nb * bl)
+    valid = rng.random(nb * bl) >= null_frac
+    t = torch.from_numpy(v.view(np.int32)).cuda()
+    out, end, total = ctx.filter_typed_dev(t, dtype, thr, nb, bl, valid=dev_bits(valid) if null_frac else None)
+    torch.cuda.synchronize()
+    exp = [oracle.filter_lt_typed(v[b * bl:(b + 1) * bl], valid[b * bl:(b + 1) * bl], thr) for b in range(nb)]
+    n = int(total.cpu()[0])
+    assert n == sum(e.size for e in exp)
+    assert np.array_equal(end.cpu().numpy()[:nb], np.cumsum([e.size for e in exp]))
+    assert np.array_equal(host(out)[:n], np.concatenate(exp).view(np.uint32))  # bit-exact, NaN payloads included
+
+
+@pytest.mark.parametrize("pa_type,thr", [("int32", -1000), ("float32", 0.25)])
+def test_filter_gpu_other_types_against_arrow(ctx, pa_type, thr):
+    import pyarrow.compute as pc
+    from dpu_olap_b200 import ops
+    rng = np.random.default_rng(31)
+    dtype = np.dtype(pa_type)
+    batches = []
+    for _ in range(4):
+        v = typed_column(rng, dtype.type, 8192 + 3)
+        batches.append(pa.array(v, mask=rng.random(v.size) < 0.25).slice(3, 8192))
+    f = ops.FilterGpu(ctx, batches, threshold=thr)
+    f.Prepare()
+    chunks = f.GetResult()
+    for b, arr in enumerate(batches):
+        exp = pc.filter(arr, pc.less(arr, pa.scalar(thr, arr.type))).to_numpy(zero_copy_only=False).astype(dtype)
+        assert chunks[b].dtype == dtype and np.array_equal(chunks[b].view(np.uint32), exp.view(np.uint32))
+    assert f.Run() == sum(c.size for c in chunks)
+    with pytest.raises(TypeError):
+        ops.SumGpu(ctx, [np.zeros(4, np.float32)])   # aggregates stay uint32
+    with pytest.raises(TypeError):
+        ops.FilterGpu(ctx, [np.zeros(4, np.int32), np.zeros(4, np.float32)])

@@ -62,3 +62,26 @@ def test_bitmap_round_trip_and_arrow_layout():
     sl = arr.slice(5, 900)  # a sliced array keeps the buffer and carries a bit offset
     assert np.array_equal(oracle.unpack_bits(np.frombuffer(sl.buffers()[0], dtype=np.uint8), 900, sl.offset),
                           valid[5:905])
+
+
+@pytest.mark.parametrize("dtype,thr", [(np.int32, -5), (np.int32, 0), (np.int32, 2**31 - 1), (np.int32, -2**31),
+                                        (np.float32, 0.0), (np.float32, -1.5), (np.float32, np.inf),
+                                        (np.float32, np.nan), (np.uint32, 1 << 30)])
+def test_typed_filter_matches_arrow(dtype, thr):
+    rng = np.random.default_rng(5)
+    n = 20_000
+    if dtype == np.float32:
+        v = rng.standard_normal(n).astype(np.float32) * 3
+        v[::97] = np.nan
+        v[::101] = np.inf
+        v[::103] = -np.inf
+        v[::107] = -0.0
+    else:
+        info = np.iinfo(dtype)
+        v = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    valid = rng.random(n) > 0.2
+    arr = pa.array(v, mask=~valid)
+    exp = pc.filter(arr, pc.less(arr, pa.scalar(thr, arr.type)))
+    got = oracle.filter_lt_typed(v, valid, thr)
+    assert got.dtype == v.dtype and np.array_equal(got.view(np.uint32),
+                                                   exp.to_numpy(zero_copy_only=False).astype(dtype).view(np.uint32))
