@@ -422,8 +422,17 @@ def bench_join(ctx, D, args):
     fk = g.foreign_key_dev(JOIN_BATCH, nb_total, JOIN_BATCH, take=(first, nb))
     n = nb * JOIN_BATCH
     info = {}
+    # "SF=2048 and above": beyond SF=2048 the reference generator's uint32 pk counter wraps
+    # (generator.cc:60,66), so every key occurs SF/2048 times and every probe row matches that many
+    # build rows — a true multi-match inner join (Arrow's semantics; the DPU table would overwrite)
+    mult = 1
+    if nb_total * JOIN_BATCH > 1 << 32:
+        if (nb_total * JOIN_BATCH) % (1 << 32):
+            raise SystemExit("beyond SF=2048 the join bench needs SF to be a multiple of 2048")
+        mult = (nb_total * JOIN_BATCH) >> 32
+        info["matches_per_probe_row"] = mult
     if D.world == 1:
-        outs = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(3)]
+        outs = [torch.empty(n * mult, dtype=torch.int32, device="cuda") for _ in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
         free, _ = torch.cuda.mem_get_info()
         full = ctx.join_ws_bytes(n, n)
@@ -433,7 +442,7 @@ def bench_join(ctx, D, args):
         info["sliced"] = ws_bytes < full
 
         def step():
-            ctx.join_dev(fk, y, pk, x, out_capacity=n, ws=ws, outs=outs, out_rows=rows_t)
+            ctx.join_dev(fk, y, pk, x, out_capacity=n * mult, ws=ws, outs=outs, out_rows=rows_t)
         l0 = ctx.launches
         ms = timed_steps(D, step, args.steps, args.warmup)
         info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
@@ -443,7 +452,7 @@ def bench_join(ctx, D, args):
     else:
         G = D.world
         cap = n + n // 8 + 65536  # received rows: hash-uniform, 12.5 % slack
-        outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(3)]
+        outs = [torch.empty(cap * mult, dtype=torch.int32, device="cuda") for _ in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
         exchange = args.join_exchange
         pj = None
@@ -469,7 +478,7 @@ def bench_join(ctx, D, args):
             info["sliced"] = False
 
             def local_join(lr, lseg, rr, rseg, seg_bits, skip_bits):
-                ctx.join_pairs_seg_dev(lr, lseg, rr, rseg, seg_bits, out_capacity=cap, skip_bits=skip_bits,
+                ctx.join_pairs_seg_dev(lr, lseg, rr, rseg, seg_bits, out_capacity=cap * mult, skip_bits=skip_bits,
                                        ws=jws, outs=outs, out_rows=rows_t)
 
             def step():
@@ -512,7 +521,7 @@ def bench_join(ctx, D, args):
                 return rp, roff
 
             def local_join(lr, rr, skip_bits):
-                ctx.join_pairs_dev(lr, rr, out_capacity=cap, skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t)
+                ctx.join_pairs_dev(lr, rr, out_capacity=cap * mult, skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t)
 
             sj = ShardedJoin(D.dist, D.rank, G, route_l, local_join, route_r=route_r, recv_l=lrecv, recv_r=rrecv)
 
@@ -530,13 +539,26 @@ def bench_join(ctx, D, args):
     # row fk points at — verified here for the rows whose pk batch this rank generated
     # (N=1: all of them), plus the row count: every fk matches exactly one pk.
     total_rows = D.sum_int(out_rows)
-    if total_rows != nb_total * JOIN_BATCH:
-        raise SystemExit(f"join self-check failed: {total_rows} rows, expected {nb_total * JOIN_BATCH}")
+    if total_rows != nb_total * JOIN_BATCH * mult:
+        raise SystemExit(f"join self-check failed: {total_rows} rows, expected {nb_total * JOIN_BATCH * mult}")
+    if mult > 1:
+        # wrapped keys: every probe row appears `mult` times in the output, so the output's fk and y
+        # columns must sum to mult x the probe side's (summed over all ranks)
+        def colsum(t, rows):
+            acc = 0
+            for s0 in range(0, rows, 1 << 26):
+                acc += int((t[s0:min(s0 + (1 << 26), rows)].to(torch.int64) & 0xFFFFFFFF).sum())
+            return acc
+        M = 1 << 56  # per-rank residues, so that the int64 all-reduce over <= 8 ranks cannot overflow
+        got = [D.sum_int(colsum(o_fk, out_rows) % M), D.sum_int(colsum(o_y, out_rows) % M)]
+        exp = [D.sum_int(colsum(fk, n) * mult % M), D.sum_int(colsum(y, n) * mult % M)]
+        if [g % M for g in got] != [e % M for e in exp]:
+            raise SystemExit(f"join self-check failed on the multi-match sums: {got} vs {exp}")
     del fk, y, pk  # the check needs x and the output only; free the rest (SF=2048 fills the HBM)
     free_all()
     lo_pk = first * JOIN_BATCH
     bad = 0
-    for s in range(0, out_rows, 1 << 26):
+    for s in range(0, out_rows if mult == 1 else 0, 1 << 26):  # payload identity needs unique keys
         kf = o_fk[s:min(s + (1 << 26), out_rows)].to(torch.int64) & 0xFFFFFFFF
         xo = o_x[s:min(s + (1 << 26), out_rows)]
         m = (kf >= lo_pk) & (kf < lo_pk + n)
@@ -547,7 +569,9 @@ def bench_join(ctx, D, args):
     res = {"ms_per_step": ms, "rows_per_side": rows, "out_rows": total_rows,
            "rows_per_s": rows / (ms * 1e-3),  # probe (L) rows per second
            "items_per_s_reference_convention": 4 * rows / (ms * 1e-3),  # join_benchmark.cc:114-125
-           "algorithmic_bytes_per_row": 28, "achieved_gbs_algorithmic": 28 * rows / D.world / (ms * 1e-3) / 1e9}
+           # 8 B per build row + 8 B per probe row + 12 B per output row (mult output rows per probe row)
+           "algorithmic_bytes_per_row": 16 + 12 * mult,
+           "achieved_gbs_algorithmic": (16 + 12 * mult) * rows / D.world / (ms * 1e-3) / 1e9}
     res.update(info)
     del x, outs, o_fk, o_y, o_x
     free_all()
