@@ -165,6 +165,28 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   __syncthreads();
   constexpr int kU = 8;  // independent loads in flight per thread
   int64_t base = u.row0;
+  if (!kAoS && !kValPred && ((reinterpret_cast<uintptr_t>(in.keys + u.row0) & 15) == 0)) {
+    // key column, 16-byte aligned: four keys per load (a quarter of the load and address
+    // instructions of the per-key loop; the histogram of a key column is instruction-bound)
+    const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(in.keys + u.row0);
+    const int64_t nvec = (u.row1 - u.row0) >> 2;
+    int64_t v = 0;
+    for (; v + (int64_t)kThreads * 4 <= nvec; v += (int64_t)kThreads * 4) {
+      uint4 kk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) kk[q] = ld_stream_v4(k4 + v + q * kThreads + tid);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {kk[q].x, kk[q].y, kk[q].z, kk[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t b = bucket_or_skip<false>(w[e], 0u, g, sel);
+          if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
+        }
+      }
+    }
+    base = u.row0 + (v << 2);  // the rest goes through the per-key loops below
+  }
   // full blocks: no per-row bounds checks
   for (; base + (int64_t)kThreads * kU <= u.row1; base += (int64_t)kThreads * kU) {
     uint32_t key[kU], val[kU];
