@@ -696,7 +696,8 @@ def bench_e2e_filter(ctx, D, args):
     return res
 
 
-def cpu_filter_sample(args, cpu_sf: int, seconds: float, steps: int | None = None, warmup: int = 1):
+def cpu_filter_sample(args, cpu_sf: int, seconds: float, steps: int | None = None, warmup: int = 1,
+                      threads: int | None = None):
     """The reference's CPU path — FilterNative's Acero plan (filter_native.cc:36-84) on Arrow 24 via
     pyarrow — timed Prepare()+Run() per iteration as BM_Filter does (filter_benchmark.cc:30-49)."""
     import numpy as np
@@ -716,7 +717,7 @@ def cpu_filter_sample(args, cpu_sf: int, seconds: float, steps: int | None = Non
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
         list(ex.map(fill, range(nb)))
     batches = [flat[b * FILTER_BATCH:(b + 1) * FILTER_BATCH] for b in range(nb)]
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     pa.set_cpu_count(cores)
     times, sel = [], 0
     t_start = time.perf_counter()
@@ -834,6 +835,10 @@ def main():
     cpu = None
     if D.rank == 0 and D.world == 1 and not args.no_cpu:
         cpu = cpu_filter_sample(args, args.cpu_sf, args.cpu_seconds)
+        # the reference's own default is half the hardware threads (host/system.h:20): report that too
+        half = max(1, (os.cpu_count() or 2) // 2)
+        h = cpu_filter_sample(args, args.cpu_sf, args.cpu_seconds / 3, threads=half)
+        cpu["half_cores"] = {"value": h["value"], "unit": h["unit"], "cores": half, "ms_per_step": h["ms_per_step"]}
 
     if D.rank == 0:
         achieved = fres["algorithmic_bytes"] / D.world / (fres["ms_per_step"] * 1e-3) / 1e9
