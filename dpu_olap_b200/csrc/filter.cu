@@ -194,16 +194,16 @@ filter_lt_u32_kernel(const FilterArgs a) {
     // ================================ producer ================================
     // Lane 0 does the work; with named barriers the whole warp takes part in the waits.
     const uint64_t policy = l2_evict_first_policy();
-    for (int64_t n = 0;; ++n) {
+    for (uint32_t n = 0;; ++n) {  // iterations of one CTA: far below 2^32
       const int s = (int)(n % kS);
-      if (n >= kS) {
+      if (n >= (uint32_t)kS) {
         if (Cfg::kNamedBars) named_bar_sync(2 + kS + s, kCT + 32);
-        else if (lane == 0) mbar_wait(&ctl.empty[s], (uint32_t)(((n / kS) - 1) & 1));
+        else if (lane == 0) mbar_wait(&ctl.empty[s], ((n / kS) - 1) & 1);
       }
       int done = 0;
       if (lane == 0) {
         const int64_t tile = (a.debug & 4) ? (int64_t)atomicAdd(&a.ws->ticket, 1ull)
-                                           : first_tile + n * tile_stride;
+                                           : first_tile + (int64_t)n * tile_stride;
         StageInfo& si = ctl.info[s];
         if (tile >= a.ntiles) {
           si.tile = -1;
@@ -252,9 +252,9 @@ filter_lt_u32_kernel(const FilterArgs a) {
     // ================================ prefix warp ================================
     uint64_t base = a.carry_in ? (uint64_t)*a.carry_in : 0ull;  // rows before super-group `sg`
     int64_t sg = 0;
-    for (int64_t n = 0;; ++n) {
+    for (uint32_t n = 0;; ++n) {
       const int s = (int)(n % kS);
-      const uint32_t par = (uint32_t)((n / kS) & 1);
+      const uint32_t par = (n / kS) & 1;
       mbar_wait(&ctl.full[s], par);
       const int64_t tile = ctl.info[s].tile;
       if (tile < 0) break;
@@ -305,9 +305,9 @@ filter_lt_u32_kernel(const FilterArgs a) {
   }
 
   // ================================ compute warps ================================
-  for (int64_t n = 0;; ++n) {
+  for (uint32_t n = 0;; ++n) {  // 32-bit: the per-tile index arithmetic is on the compute warps' path
     const int s = (int)(n % kS);
-    const uint32_t par = (uint32_t)((n / kS) & 1);
+    const uint32_t par = (n / kS) & 1;
     uint32_t* const buf = bufs + (size_t)s * kTile;
     mbar_wait(&ctl.full[s], par);
     const StageInfo si = ctl.info[s];
@@ -405,10 +405,10 @@ filter_lt_u32_kernel(const FilterArgs a) {
     }
 
     // ---- write out the tile compacted kLag iterations ago (its global offset is known by now) ----
-    auto write_out = [&](int64_t m) {
+    auto write_out = [&](uint32_t m) {
       const int ps = (int)(m % kS);
       if (Cfg::kNamedBars) named_bar_sync(2 + ps, kCT + 32);
-      else mbar_wait(&ctl.pre[ps], (uint32_t)((m / kS) & 1));
+      else mbar_wait(&ctl.pre[ps], (m / kS) & 1);
       const uint32_t* __restrict__ stg = bufs + (size_t)ps * kTile;
       uint32_t* __restrict__ dst = a.out + ctl.prefix[ps];
       const uint32_t cnt_m = ctl.total[ps];
@@ -421,10 +421,10 @@ filter_lt_u32_kernel(const FilterArgs a) {
         if (lane == 0) mbar_arrive(&ctl.empty[ps]);
       }
     };
-    if (n >= Cfg::kLag) write_out(n - Cfg::kLag);
+    if (n >= (uint32_t)Cfg::kLag) write_out(n - Cfg::kLag);
     if (!valid) {  // drain: tiles n-kLag+1 .. n-1 were compacted before barrier A
-      for (int64_t m = n - Cfg::kLag + 1; m < n; ++m)
-        if (m >= 0) write_out(m);
+      for (int m = (int)n - Cfg::kLag + 1; m < (int)n; ++m)
+        if (m >= 0) write_out((uint32_t)m);
       break;
     }
 
