@@ -16,15 +16,18 @@
 //   1. both sides are radix-partitioned on the same hash bits (partition.cu) into partitions of
 //      ~4096 build rows, carrying (key, payload) pairs — the payload travels with the key, so
 //      there is no row-index vector and no take pass;
-//   2. join_probe_kernel: one CTA per partition builds a bucketised table of the build side in
-//      SHARED memory (2048 buckets x 4 keys, 64 KB with the values, load factor ~0.5; 32-bit
-//      atomicCAS on the key word), then streams the probe side through it — one 128-bit read
-//      resolves a row — and writes (fk, y, x) with coalesced stores; the output range of every
-//      4608-row probe round is reserved with one 64-bit atomicAdd.
-//      The "empty" marker of a partition's table is a key that hashes to ANOTHER partition
-//      (wang_hash is a bijection), so all 2^32 key values are legal.
+//   2. join_probe_kernel: one CTA per partition builds a table of the build side in SHARED memory
+//      (2048 buckets x 4 slots, 72 KB with the values and one arrival counter per bucket, mean
+//      2 rows per bucket). An insert is one shared-memory atomicAdd on the counter — it returns the
+//      slot — plus two stores; a row goes to the emptier of its TWO candidate buckets, so chains
+//      are rare. The probe side then streams through: both candidate buckets are read with 128-bit
+//      loads, straight-line, and (fk, y, x) is written with coalesced stores; the output range of
+//      every 4608-row probe round is reserved with one 64-bit atomicAdd. No empty-key marker: all
+//      2^32 key values are legal, and only the 8 KB of counters are cleared per partition.
 //      Build partitions larger than the table (skew, heavy duplicates) are processed in chunks,
 //      each chunk probed by the whole probe partition.
+//      kAgg variant: the fused [filter ->] join -> aggregate pipeline adds every output row's y and
+//      x to per-thread sums instead of storing it (b2_join_aggr_u32_dev).
 //   3. when the workspace is too small to hold both partitioned sides at once (SF=2048 on one
 //      GPU), the join runs in hash-space slices: slice s only partitions and joins the rows whose
 //      top hash bits equal s.
