@@ -247,6 +247,41 @@ static void JoinLargeTest(gpu::GpuSet& sys) {  // join_test.cc:82-121 (128 x 655
   for (const char* c : {"fk", "y", "x"}) EXPECT_TRUE(gs->GetColumnByName(c)->Equals(ns->GetColumnByName(c)));
 }
 
+static void JoinAggregateTest(gpu::GpuSet& sys) {  // fused pipeline vs aggregates of the Native join's columns
+  RandomArrayGenerator rng(42);
+  const int nb = 16, bs = 1 << 16;
+  auto xs = MakeRandomRecordBatches(rng, VSchema("x"), nb, bs);
+  auto ys = MakeRandomRecordBatches(rng, VSchema("y"), nb, bs);
+  auto fks = MakeForeignKeyColumn(rng, bs, nb, bs).ValueOrDie();
+  auto pks = MakeIndexColumn(nb, bs).ValueOrDie();
+  arrow::RecordBatchVector left, right;
+  for (int b = 0; b < nb; ++b) {
+    left.push_back(RecordBatchOf({"fk", "y"}, {fks[b], ys[b]->column(0)}));
+    right.push_back(RecordBatchOf({"pk", "x"}, {pks[b], xs[b]->column(0)}));
+  }
+  join::JoinGpu g{sys, left[0]->schema(), right[0]->schema(), left, right};
+  EXPECT_TRUE(g.Prepare().ok());
+  join::JoinNative n{left[0]->schema(), right[0]->schema(), left, right};
+  auto t = n.Run().ValueOrDie();
+  auto sum_of = [&](const char* name) {
+    auto col = t->GetColumnByName(name);
+    auto c = arrow::compute::Cast(arrow::Datum(col), arrow::uint64()).ValueOrDie();
+    return std::static_pointer_cast<arrow::UInt64Scalar>(arrow::compute::Sum(c).ValueOrDie().scalar())->value;
+  };
+  const b2_join_aggr a = g.RunAggregate().ValueOrDie();
+  EXPECT_EQ(a.rows, (uint64_t)t->num_rows());
+  EXPECT_EQ(a.sum_y, sum_of("y"));
+  EXPECT_EQ(a.sum_x, sum_of("x"));
+  // with the pushed-down filter: the Native join over the pre-filtered probe side
+  const uint32_t thr = 1u << 30;
+  auto mask = arrow::compute::CallFunction("less", {arrow::Datum(t->GetColumnByName("y")),
+                                                    arrow::Datum(std::make_shared<arrow::UInt32Scalar>(thr))}).ValueOrDie();
+  auto ft = arrow::compute::Filter(arrow::Datum(t), mask).ValueOrDie().table();
+  const b2_join_aggr f = g.RunAggregate(true, thr).ValueOrDie();
+  EXPECT_EQ(f.rows, (uint64_t)ft->num_rows());
+  EXPECT_TRUE(f.rows > 0 && f.rows < a.rows);
+}
+
 // ---- PartitionTest (GTEST_SKIP in the reference) ------------------------------------------------------
 static void PartitionSimpleTest(gpu::GpuSet& sys) {  // partition_test.cc:21-57
   arrow::RecordBatchVector batches = {RecordBatchOf({"pk", "x"}, {ArrayOf({0, 2}), ArrayOf({100, 101})}),
@@ -349,7 +384,7 @@ int main(int argc, char** argv) {
       {"TakeTest.LargeTest", TakeLargeTest},       {"FilterTest.Nullable", FilterNullableTest},
       {"SumTest.Nullable", SumNullableTest},       {"TakeTest.Nullable", TakeNullableTest},
       {"JoinTest.SimpleTest", JoinSimpleTest},
-      {"JoinTest.LargeTest", JoinLargeTest},       {"PartitionTest.SimpleTest", PartitionSimpleTest},
+      {"JoinTest.LargeTest", JoinLargeTest},       {"JoinTest.FusedAggregate", JoinAggregateTest},       {"PartitionTest.SimpleTest", PartitionSimpleTest},
       {"PartitionTest.LargeTest", PartitionLargeTest}};
   int bad = 0;
   for (auto& c : cases) {

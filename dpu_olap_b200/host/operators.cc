@@ -249,6 +249,30 @@ arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
   return arrow::Table::Make(schema, {a_fk, a_y, a_x}, static_cast<int64_t>(rows));
 }
 
+// Fused pipeline [filter left payload < threshold ->] join -> COUNT / SUM(left payload) / SUM(right
+// payload): one upload, three numbers back, nothing materialised (b2_join_aggr_u32_host).
+arrow::Result<b2_join_aggr> JoinGpu::RunAggregate(bool filter_left_payload, uint32_t threshold) {
+  b2_ctx* ctx = system_.ctx();
+  if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  const int fk = left_schema_->GetFieldIndex("fk"), pk = right_schema_->GetFieldIndex("pk");
+  if (fk < 0 || pk < 0) return arrow::Status::Invalid("join keys are named fk / pk (join_native.cc:31-36)");
+  if (left_schema_->num_fields() != 2 || right_schema_->num_fields() != 2)
+    return arrow::Status::NotImplemented("one key and one payload column per side");
+  ColumnPtrs l, r;
+  ARROW_RETURN_NOT_OK(l.Append(left_batches_, fk));
+  ARROW_RETURN_NOT_OK(l.Append(left_batches_, 1 - fk));
+  ARROW_RETURN_NOT_OK(r.Append(right_batches_, pk));
+  ARROW_RETURN_NOT_OK(r.Append(right_batches_, 1 - pk));
+  b2_join_aggr out{};
+  b2_timings t{};
+  B2_ARROW_RETURN_NOT_OK(
+      ctx, b2_join_aggr_u32_host(ctx, l.ptrs.data(), l.lens.data(), static_cast<int64_t>(left_batches_.size()),
+                                 r.ptrs.data(), r.lens.data(), static_cast<int64_t>(right_batches_.size()),
+                                 filter_left_payload ? 1 : 0, threshold, &out, &t));
+  timers_->Add(t);
+  return out;
+}
+
 }  // namespace join
 
 // ---- Partition (PartitionDpu, host/partition/partition_dpu.cc:31-135) ---------------------------

@@ -84,6 +84,8 @@ class JoinGpu {
   arrow::Status Prepare();
   // (fk, left payload, right payload); row order unspecified, as JoinDpu's (join_dpu.cc:376-399)
   arrow::Result<std::shared_ptr<arrow::Table>> Run();
+  // fused [filter left payload < threshold ->] join -> COUNT / SUM / SUM, nothing materialised
+  arrow::Result<b2_join_aggr> RunAggregate(bool filter_left_payload = false, uint32_t threshold = 0);
   std::shared_ptr<timer::Timers> Timers() { return timers_; }
 
  private:

@@ -40,7 +40,7 @@ def test_cpp_bench_native_json_shape(host_bins):
 def test_cpp_reference_tests_on_gpu(host_bins):
     r = subprocess.run([str(host_bins["host_test"])], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 of 15 cases failed" in r.stdout
+    assert "0 of 16 cases failed" in r.stdout
 
 
 @pytest.mark.gpu
