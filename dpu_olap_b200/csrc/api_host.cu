@@ -773,7 +773,15 @@ extern "C" {
 int b2_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const uint8_t* const* valid_ptrs,
                      const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
                      b2_aggr_u32* out, b2_timings* timings) {
+  return b2_aggr_32_host(ctx, reinterpret_cast<const void* const*>(batch_ptrs), valid_ptrs, valid_bit_offsets,
+                         batch_lens, nbatches, B2_U32, out, timings);
+}
+
+int b2_aggr_32_host(b2_ctx* ctx, const void* const* batch_ptrs_, const uint8_t* const* valid_ptrs,
+                    const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches, int dtype,
+                    b2_aggr_u32* out, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  const uint32_t* const* batch_ptrs = reinterpret_cast<const uint32_t* const*>(batch_ptrs_);
   B2_REQUIRE(ctx, out != nullptr, "out is null");
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
@@ -798,7 +806,7 @@ int b2_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const uint8
     B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
     tm.h2d_bytes += (int64_t)bits.size();
   }
-  B2_RETURN_NOT_OK(b2_aggr_u32_dev(ctx, d_col, d_valid, L.rows(), d_out, s));
+  B2_RETURN_NOT_OK(b2_aggr_32_dev(ctx, d_col, dtype, d_valid, L.rows(), d_out, s));
   B2_CUDA_OK(ctx, cudaMemcpyAsync(out, d_out, sizeof(b2_aggr_u32), cudaMemcpyDeviceToHost, s));
   B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
   tm.d2h_bytes = sizeof(b2_aggr_u32);

@@ -17,26 +17,36 @@ namespace {
 constexpr int kAggThreads = 512;
 constexpr int kAggUnroll = 8;  // 128-bit loads in flight per thread, as the sum kernel
 
+// kSigned: the column is int32 — sum into int64 (sign-extended), min / max in signed order; the
+// results travel as bit patterns in the same b2_aggr_u32 fields.
+template <bool kSigned>
 struct AggAcc {
   uint64_t sum = 0;
   uint32_t cnt = 0;  // flushed into the 64-bit total by the caller's reduction
-  uint32_t mn = 0xffffffffu;
-  uint32_t mx = 0;
+  uint32_t mn = kSigned ? 0x7fffffffu : 0xffffffffu;
+  uint32_t mx = kSigned ? 0x80000000u : 0u;
 };
 
-__device__ __forceinline__ void agg_row(AggAcc& a, uint32_t v, bool valid) {
+template <bool kSigned>
+__device__ __forceinline__ void agg_row(AggAcc<kSigned>& a, uint32_t v, bool valid) {
   if (valid) {
-    a.sum += v;
     a.cnt += 1;
-    a.mn = min(a.mn, v);
-    a.mx = max(a.mx, v);
+    if (kSigned) {
+      a.sum += (uint64_t)(int64_t)(int32_t)v;
+      a.mn = (uint32_t)min((int32_t)a.mn, (int32_t)v);
+      a.mx = (uint32_t)max((int32_t)a.mx, (int32_t)v);
+    } else {
+      a.sum += v;
+      a.mn = min(a.mn, v);
+      a.mx = max(a.mx, v);
+    }
   }
 }
 
 // One pass: 128-bit value loads, one 32-bit bitmap word per 8 threads (valid == nullptr: no nulls).
 // The first `head` rows (until 16 B alignment AND a nibble boundary of the bitmap) and the tail are
 // done row by row by CTA 0.
-template <bool kHasValid>
+template <bool kHasValid, bool kSigned>
 __global__ void __launch_bounds__(kAggThreads, 2)
 aggr_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ valid_, int64_t n,
                 int64_t head, b2_aggr_u32* __restrict__ out) {
@@ -44,7 +54,7 @@ aggr_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ va
   const int64_t nvec = (n - head) >> 2;
   const int64_t tail_start = head + (nvec << 2);
   const uint4* __restrict__ vin = reinterpret_cast<const uint4*>(in + head);
-  AggAcc acc;
+  AggAcc<kSigned> acc;
   uint64_t cnt = 0;
   const int64_t chunk = (int64_t)kAggThreads * kAggUnroll;
   for (int64_t base = (int64_t)blockIdx.x * chunk; base < nvec; base += (int64_t)gridDim.x * chunk) {
@@ -107,7 +117,10 @@ aggr_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ va
   __shared__ uint64_t s_sum[kAggThreads / 32], s_cnt[kAggThreads / 32];
   __shared__ uint32_t s_mn[kAggThreads / 32], s_mx[kAggThreads / 32];
   const uint64_t wsum = warp_reduce_sum_u64(acc.sum), wcnt = warp_reduce_sum_u64(cnt);
-  const uint32_t wmn = __reduce_min_sync(0xffffffffu, acc.mn), wmx = __reduce_max_sync(0xffffffffu, acc.mx);
+  const uint32_t wmn = kSigned ? (uint32_t)__reduce_min_sync(0xffffffffu, (int32_t)acc.mn)
+                               : __reduce_min_sync(0xffffffffu, acc.mn);
+  const uint32_t wmx = kSigned ? (uint32_t)__reduce_max_sync(0xffffffffu, (int32_t)acc.mx)
+                               : __reduce_max_sync(0xffffffffu, acc.mx);
   if (lane_id() == 0) {
     s_sum[threadIdx.x >> 5] = wsum;
     s_cnt[threadIdx.x >> 5] = wcnt;
@@ -119,22 +132,31 @@ aggr_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ va
     const bool in_range = threadIdx.x < kAggThreads / 32;
     const uint64_t a = warp_reduce_sum_u64(in_range ? s_sum[threadIdx.x] : 0);
     const uint64_t c = warp_reduce_sum_u64(in_range ? s_cnt[threadIdx.x] : 0);
-    const uint32_t lo = __reduce_min_sync(0xffffffffu, in_range ? s_mn[threadIdx.x] : 0xffffffffu);
-    const uint32_t hi = __reduce_max_sync(0xffffffffu, in_range ? s_mx[threadIdx.x] : 0u);
+    const AggAcc<kSigned> none;  // identity elements of min / max for lanes without a warp
+    const uint32_t mn_l = in_range ? s_mn[threadIdx.x] : none.mn, mx_l = in_range ? s_mx[threadIdx.x] : none.mx;
+    const uint32_t lo = kSigned ? (uint32_t)__reduce_min_sync(0xffffffffu, (int32_t)mn_l)
+                                : __reduce_min_sync(0xffffffffu, mn_l);
+    const uint32_t hi = kSigned ? (uint32_t)__reduce_max_sync(0xffffffffu, (int32_t)mx_l)
+                                : __reduce_max_sync(0xffffffffu, mx_l);
     if (threadIdx.x == 0 && c > 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&out->sum), (unsigned long long)a);
       atomicAdd(reinterpret_cast<unsigned long long*>(&out->count), (unsigned long long)c);
-      atomicMin(&out->min, lo);
-      atomicMax(&out->max, hi);
+      if (kSigned) {
+        atomicMin(reinterpret_cast<int*>(&out->min), (int)lo);
+        atomicMax(reinterpret_cast<int*>(&out->max), (int)hi);
+      } else {
+        atomicMin(&out->min, lo);
+        atomicMax(&out->max, hi);
+      }
     }
   }
 }
 
-__global__ void aggr_init_kernel(b2_aggr_u32* out) {
+__global__ void aggr_init_kernel(b2_aggr_u32* out, bool is_signed) {
   out->sum = 0;
   out->count = 0;
-  out->min = 0xffffffffu;
-  out->max = 0;
+  out->min = is_signed ? 0x7fffffffu : 0xffffffffu;
+  out->max = is_signed ? 0x80000000u : 0u;
 }
 
 // ---- take ------------------------------------------------------------------------------------
@@ -209,14 +231,25 @@ extern "C" {
 
 int b2_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid, int64_t n,
                     b2_aggr_u32* d_out, void* stream) {
+  return b2_aggr_32_dev(ctx, d_in, B2_U32, d_valid, n, d_out, stream);
+}
+
+int b2_aggr_32_dev(b2_ctx* ctx, const void* d_in_, int dtype, const uint8_t* d_valid, int64_t n,
+                   b2_aggr_u32* d_out, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  if (dtype == B2_F32)
+    return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "float32 aggregates",
+                        "rounding and the sign of zero depend on the summation order, in Arrow too");
+  B2_REQUIRE(ctx, dtype == B2_U32 || dtype == B2_I32, "dtype must be B2_U32 or B2_I32");
+  const bool is_signed = dtype == B2_I32;
+  const uint32_t* d_in = static_cast<const uint32_t*>(d_in_);
   B2_REQUIRE(ctx, n >= 0, "n must be >= 0");
   B2_REQUIRE(ctx, d_out != nullptr, "d_out is null");
   B2_REQUIRE(ctx, n == 0 || d_in != nullptr, "d_in is null");
   B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_in) & 3) == 0, "d_in must be 4-byte aligned");
   B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_valid) & 3) == 0, "validity bitmap must be 4-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  aggr_init_kernel<<<1, 1, 0, s>>>(d_out);
+  aggr_init_kernel<<<1, 1, 0, s>>>(d_out, is_signed);
   B2_LAUNCH_CHECK(ctx, "aggr_init_kernel");
   if (n == 0) return B2_OK;
   // scalar head: rows until the values are 16 B aligned; with a bitmap the vector body must also
@@ -231,10 +264,11 @@ int b2_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid, i
   if (head == n) want = (n + kAggThreads - 1) / kAggThreads;  // row-by-row path: one row per thread and step
   int grid = ctx->sm_count * 2;
   if (want < grid) grid = want > 0 ? (int)want : 1;
-  if (d_valid)
-    aggr_u32_kernel<true><<<grid, kAggThreads, 0, s>>>(d_in, reinterpret_cast<const uint32_t*>(d_valid), n, head, d_out);
-  else
-    aggr_u32_kernel<false><<<grid, kAggThreads, 0, s>>>(d_in, nullptr, n, head, d_out);
+  const uint32_t* vb = reinterpret_cast<const uint32_t*>(d_valid);
+  if (d_valid && is_signed) aggr_u32_kernel<true, true><<<grid, kAggThreads, 0, s>>>(d_in, vb, n, head, d_out);
+  else if (d_valid) aggr_u32_kernel<true, false><<<grid, kAggThreads, 0, s>>>(d_in, vb, n, head, d_out);
+  else if (is_signed) aggr_u32_kernel<false, true><<<grid, kAggThreads, 0, s>>>(d_in, nullptr, n, head, d_out);
+  else aggr_u32_kernel<false, false><<<grid, kAggThreads, 0, s>>>(d_in, nullptr, n, head, d_out);
   B2_LAUNCH_CHECK(ctx, "aggr_u32_kernel");
   return B2_OK;
 }

@@ -337,14 +337,14 @@ class Context:
                  "b2_filter_lt_32_dev")
         return out, batch_end, total
 
-    def aggr_dev(self, col, valid=None, out=None):
+    def aggr_dev(self, col, valid=None, out=None, dtype=np.uint32):
         """sum / count / min / max of the valid rows in one pass; returns a 3 x int64 device tensor
-        laid out as b2_aggr_u32 (decode with :func:`decode_aggr`)."""
+        laid out as b2_aggr_u32 (decode with :func:`decode_aggr`). dtype: uint32 or int32."""
         import torch
         if out is None:
             out = torch.empty(3, dtype=torch.int64, device=col.device)
-        self._ck(self._lib.b2_aggr_u32_dev(self._h, _dptr(col), _dptr(valid), col.numel(), _dptr(out),
-                                           self._stream()), "b2_aggr_u32_dev")
+        self._ck(self._lib.b2_aggr_32_dev(self._h, _dptr(col), _DTYPES32[np.dtype(dtype)], _dptr(valid),
+                                          col.numel(), _dptr(out), self._stream()), "b2_aggr_32_dev")
         return out
 
     def take_nullable_dev(self, values, values_valid, values_len: int, indices, indices_valid, idx_len: int,
@@ -559,17 +559,22 @@ class AggrResult(C.Structure):
     """b2_aggr_u32 (include/b200olap.h)."""
     _fields_ = [("sum", C.c_uint64), ("count", C.c_uint64), ("min", C.c_uint32), ("max", C.c_uint32)]
 
-    def as_dict(self) -> dict:
-        """Arrow's scalars: every aggregate of zero valid rows is null (None); count never is."""
+    def as_dict(self, dtype=np.uint32) -> dict:
+        """Arrow's scalars: every aggregate of zero valid rows is null (None); count never is.
+        int32 columns: the fields hold int64 / int32 bit patterns."""
         empty = self.count == 0
-        return {"sum": None if empty else int(self.sum), "count": int(self.count),
-                "min": None if empty else int(self.min), "max": None if empty else int(self.max)}
+        sgn = np.dtype(dtype) == np.dtype(np.int32)
+        s = int(self.sum) - (1 << 64) if sgn and self.sum >> 63 else int(self.sum)
+        lo = int(self.min) - (1 << 32) if sgn and self.min >> 31 else int(self.min)
+        hi = int(self.max) - (1 << 32) if sgn and self.max >> 31 else int(self.max)
+        return {"sum": None if empty else s, "count": int(self.count),
+                "min": None if empty else lo, "max": None if empty else hi}
 
 
-def decode_aggr(t) -> dict:
+def decode_aggr(t, dtype=np.uint32) -> dict:
     """Decode the device tensor returned by :meth:`Context.aggr_dev`."""
     raw = t.cpu().numpy().tobytes()
-    return AggrResult.from_buffer_copy(raw[:C.sizeof(AggrResult)]).as_dict()
+    return AggrResult.from_buffer_copy(raw[:C.sizeof(AggrResult)]).as_dict(dtype)
 
 
 def wang_hash(key: int) -> int:
@@ -668,9 +673,13 @@ class SumGpu:
 
     def __init__(self, ctx: Context, batches: Sequence[Any]):
         self.ctx = ctx
-        self._ncols = [_nullable_column(b, 0) for b in batches]
+        self._ncols = [_nullable_column(b, 0, typed=True) for b in batches]
         self._cols = [c.values for c in self._ncols]
         self._valid = _ValidTable(self._ncols)
+        kinds = {c.dtype for c in self._ncols} or {np.dtype(np.uint32)}
+        if len(kinds) > 1 or next(iter(kinds)) == np.dtype(np.float32):
+            raise TypeError(f"aggregates take uint32 or int32 columns, got {sorted(str(k) for k in kinds)}")
+        self.dtype = kinds.pop()
         self._timers = None
 
     def Prepare(self) -> None:
@@ -681,15 +690,16 @@ class SumGpu:
         tab = _PtrTable(self._cols)
         out = AggrResult()
         t = Timings()
-        self.ctx._ck(self.ctx._lib.b2_aggr_u32_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
-                                                    tab.lens, tab.n, C.byref(out), C.byref(t)),
-                     "b2_aggr_u32_host")
+        self.ctx._ck(self.ctx._lib.b2_aggr_32_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
+                                                   tab.lens, tab.n, _DTYPES32[self.dtype], C.byref(out),
+                                                   C.byref(t)), "b2_aggr_32_host")
         self._timers = Timers.from_timings(t)
         self._last = (t,)
-        return out.as_dict()
+        return out.as_dict(self.dtype)
 
     def Run(self):
-        if self._valid.any:  # nullable column: Arrow's sum skips nulls, and is null if all rows are
+        if self._valid.any or self.dtype != np.dtype(np.uint32):
+            # nullable / int32 column: Arrow's sum skips nulls, and is null if all rows are
             return self.Aggregates()["sum"]
         tab = _PtrTable(self._cols)
         out = C.c_uint64(0)

@@ -49,6 +49,10 @@ enum b2_status {
   B2_ERR_OVERFLOW = 6      /* result does not fit the caller-provided output capacity */
 };
 
+/* 32-bit column types of the typed entry points (the reference fixes `#define T uint32_t`,
+ * dpu/shared/common.h:3; uint32 is what every other entry point means). */
+enum b2_dtype32 { B2_U32 = 0, B2_I32 = 1, B2_F32 = 2 };
+
 typedef struct b2_ctx b2_ctx;
 
 /* Phase timings of the last *_host call, in milliseconds. Names follow the reference's timers
@@ -129,12 +133,21 @@ typedef struct b2_aggr_u32 {
 } b2_aggr_u32;
 int b2_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid, int64_t n,
                     b2_aggr_u32* d_out, void* stream);
+/* The same for an int32 column (dtype B2_I32: sum is an int64, min / max are in signed order, all
+ * returned as bit patterns in the same struct; count == 0: min = INT32_MAX, max = INT32_MIN).
+ * B2_F32 is rejected (B2_ERR_UNSUPPORTED): a float sum's rounding and the sign of a zero min / max
+ * depend on the evaluation order, in Arrow itself too, so there is nothing bit-exact to match. */
+int b2_aggr_32_dev(b2_ctx* ctx, const void* d_in, int dtype, const uint8_t* d_valid, int64_t n,
+                   b2_aggr_u32* d_out, void* stream);
 /* Host batches in, aggregates out. valid_ptrs[b] = validity bitmap of batch b starting at bit
  * valid_bit_offsets[b] (Arrow buffer #0 and the array's offset); valid_ptrs, valid_ptrs[b] and
  * valid_bit_offsets may each be NULL (no nulls / offset 0). */
 int b2_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const uint8_t* const* valid_ptrs,
                      const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
                      b2_aggr_u32* out, b2_timings* timings);
+int b2_aggr_32_host(b2_ctx* ctx, const void* const* batch_ptrs, const uint8_t* const* valid_ptrs,
+                    const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches, int dtype,
+                    b2_aggr_u32* out, b2_timings* timings);
 /* SumDpu::Run (host/aggr/aggr_dpu.cc:31-89): batches on the host, result on the host. */
 int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
                     int64_t nbatches, uint64_t* sum, b2_timings* timings);
@@ -168,7 +181,6 @@ int b2_filter_lt_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8
  * the same kernel comparing `v < threshold` as int32 or float32 (IEEE: a NaN row is never selected,
  * as in Arrow). Values travel as raw 32-bit words; threshold_bits is the threshold's bit pattern;
  * d_valid as above (NULL = no nulls). */
-enum b2_dtype32 { B2_U32 = 0, B2_I32 = 1, B2_F32 = 2 };
 int b2_filter_lt_32_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_t threshold_bits,
                         const uint8_t* d_valid, int64_t nbatches, int64_t batch_len, void* d_out,
                         int64_t* d_batch_end, int64_t* d_total, const int64_t* d_carry_in, void* d_ws,

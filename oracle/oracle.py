@@ -215,10 +215,14 @@ def filter_lt_typed(values, valid, thr) -> np.ndarray:
 def aggr_nullable(values, valid) -> dict:
     """cp::Sum / Count / MinMax with default options: nulls are skipped; with no valid row every
     aggregate but the count is null (None)."""
-    v = _u32(values)[np.asarray(valid, dtype=bool)]
+    v = np.ascontiguousarray(values)
+    if v.dtype != np.int32:   # int32 columns sum into int64 and compare signed; everything else is uint32
+        v = _u32(v)
+    v = v[np.asarray(valid, dtype=bool)]
     if v.size == 0:
         return {"sum": None, "count": 0, "min": None, "max": None}
-    return {"sum": int(v.astype(np.uint64).sum(dtype=np.uint64)), "count": int(v.size),
+    wide = np.int64 if v.dtype == np.int32 else np.uint64
+    return {"sum": int(v.astype(wide).sum(dtype=wide)), "count": int(v.size),
             "min": int(v.min()), "max": int(v.max())}
 
 

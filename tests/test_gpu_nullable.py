@@ -231,6 +231,26 @@ def test_filter_gpu_other_types_against_arrow(ctx, pa_type, thr):
         assert chunks[b].dtype == dtype and np.array_equal(chunks[b].view(np.uint32), exp.view(np.uint32))
     assert f.Run() == sum(c.size for c in chunks)
     with pytest.raises(TypeError):
-        ops.SumGpu(ctx, [np.zeros(4, np.float32)])   # aggregates stay uint32
+        ops.SumGpu(ctx, [np.zeros(4, np.float32)])   # float aggregates are order dependent: rejected
     with pytest.raises(TypeError):
         ops.FilterGpu(ctx, [np.zeros(4, np.int32), np.zeros(4, np.float32)])
+
+
+@pytest.mark.parametrize("n,null_frac", [(1, 0.0), (5, 1.0), (100_000, 0.3), ((1 << 21) + 7, 0.0)])
+def test_int32_aggregates(ctx, n, null_frac):
+    import pyarrow.compute as pc
+    from dpu_olap_b200 import ops
+    from dpu_olap_b200.ops import decode_aggr
+    rng = np.random.default_rng(n)
+    v = rng.integers(-2**31, 2**31 - 1, size=n, dtype=np.int32, endpoint=True)
+    valid = rng.random(n) >= null_frac
+    t = torch.from_numpy(v).cuda()
+    got = decode_aggr(ctx.aggr_dev(t, dev_bits(valid) if null_frac else None, dtype=np.int32), np.int32)
+    assert got == oracle.aggr_nullable(v, valid if null_frac else np.ones(n, bool))
+    # the operator class over Arrow int32 batches, against Arrow itself
+    arr = pa.array(v, type=pa.int32(), mask=~valid)
+    s = ops.SumGpu(ctx, [arr])
+    mm = pc.min_max(arr)
+    assert s.Aggregates() == {"sum": pc.sum(arr).as_py(), "count": pc.count(arr).as_py(),
+                              "min": mm["min"].as_py(), "max": mm["max"].as_py()}
+    assert s.Run() == pc.sum(arr).as_py()

@@ -85,3 +85,15 @@ def test_typed_filter_matches_arrow(dtype, thr):
     got = oracle.filter_lt_typed(v, valid, thr)
     assert got.dtype == v.dtype and np.array_equal(got.view(np.uint32),
                                                    exp.to_numpy(zero_copy_only=False).astype(dtype).view(np.uint32))
+
+
+@pytest.mark.parametrize("n,null_frac", [(0, 0.0), (3, 1.0), (1000, 0.2), (70_001, 0.5)])
+def test_int32_aggregates_match_arrow(n, null_frac):
+    rng = np.random.default_rng(300 + n)
+    v = rng.integers(-2**31, 2**31 - 1, size=n, dtype=np.int32, endpoint=True)
+    valid = rng.random(n) >= null_frac
+    arr = pa.array(v, type=pa.int32(), mask=~valid)
+    got = oracle.aggr_nullable(v, valid)
+    mm = pc.min_max(arr)
+    assert got == {"sum": pc.sum(arr).as_py(), "count": pc.count(arr).as_py(),   # Arrow sums int32 into int64
+                   "min": mm["min"].as_py(), "max": mm["max"].as_py()}
