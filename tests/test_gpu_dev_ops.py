@@ -676,6 +676,57 @@ def test_kernels_never_write_outside_their_outputs(ctx):
         assert np.array_equal(got, expp)
 
 
+def test_nullable_and_fused_kernels_never_write_outside_their_outputs(ctx):
+    """The same guard check for the nullable filter / take / aggregate kernels and the fused
+    join -> aggregate pipeline (whose only outputs are 24 bytes and its workspace)."""
+    rng = np.random.default_rng(32)
+    S32, S64 = -559038737, -81985529216486896
+    nb, bl = 3, 4096 + 36
+    v = rng.integers(0, 2**32, size=nb * bl, dtype=np.uint32)
+    valid = rng.random(nb * bl) > 0.05
+    bits = torch.from_numpy(oracle.pack_bits(valid)).cuda()
+    g_out, out = _guarded(int(valid.sum()), torch.int32, S32)   # exactly the selected rows at 100 % selectivity
+    g_end, end = _guarded(nb, torch.int64, S64)
+    g_tot, tot = _guarded(1, torch.int64, S64)
+    ws_n = ctx.filter_ws_bytes(nb, bl)
+    g_ws, ws = _guarded(ws_n, torch.uint8, 0x5A)
+    ctx.filter_nullable_dev(dev(v), bits, nb, bl, 0xFFFFFFFF, out=out, batch_end=end, total=tot, ws=ws)
+    torch.cuda.synchronize()
+    assert int(tot.cpu()[0]) == int((valid & (v < 0xFFFFFFFF)).sum())
+    # (a value equal to 0xFFFFFFFF is not selected, so the output may be a few rows short of `valid.sum()`)
+    assert _guards_intact(g_out, int(valid.sum()), S32) and _guards_intact(g_end, nb, S64)
+    assert _guards_intact(g_tot, 1, S64) and _guards_intact(g_ws, ws_n, 0x5A)
+    # take: 3 x 77 outputs -> a result bitmap of ceil(231 / 32) words
+    vals = rng.integers(0, 2**32, size=3 * 1001, dtype=np.uint32)
+    idx = rng.integers(0, 1001, size=3 * 77, dtype=np.uint32)
+    vv, iv = rng.random(vals.size) > 0.3, rng.random(idx.size) > 0.3
+    g_o, o = _guarded(3 * 77, torch.int32, S32)
+    nwords = (3 * 77 + 31) // 32
+    g_b, ob = _guarded(nwords * 4, torch.uint8, 0x5A)
+    ctx.take_nullable_dev(dev(vals), torch.from_numpy(oracle.pack_bits(vv)).cuda(), 1001, dev(idx),
+                          torch.from_numpy(oracle.pack_bits(iv)).cuda(), 77, 3, out=o, out_valid=ob)
+    torch.cuda.synchronize()
+    assert _guards_intact(g_o, 3 * 77, S32) and _guards_intact(g_b, nwords * 4, 0x5A)
+    # aggregates: a 24-byte result
+    g_a, a = _guarded(3, torch.int64, S64)
+    ctx.aggr_dev(dev(v), bits, out=a)
+    torch.cuda.synchronize()
+    assert _guards_intact(g_a, 3, S64)
+    # fused join -> aggregate: result and workspace
+    n = 60_001
+    pk = rng.integers(0, 30_000, size=n, dtype=np.uint32)
+    fk = rng.integers(0, 35_000, size=n, dtype=np.uint32)
+    x, y = rng.integers(0, 2**32, size=n, dtype=np.uint32), rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    wsn = ctx.join_ws_bytes(n, n) + 256
+    g_w, w = _guarded(wsn, torch.uint8, 0x5A)
+    g_r, r = _guarded(3, torch.int64, S64)
+    ctx.join_aggr_dev(dev(fk), dev(y), dev(pk), dev(x), y_threshold=1 << 31, ws=w, out=r)
+    torch.cuda.synchronize()
+    got = r.cpu().numpy().view(np.uint64)
+    assert {"rows": int(got[0]), "sum_y": int(got[1]), "sum_x": int(got[2])} == oracle.join_aggr(fk, y, pk, x, 1 << 31)
+    assert _guards_intact(g_r, 3, S64) and _guards_intact(g_w, wsn, 0x5A)
+
+
 @pytest.mark.parametrize("n,thr", [(0, 5), (1, 0), (7, 2**31), (4097, 1 << 30), (1_000_003, 42_949_673),
                                    (8 * 1024 * 1024 + 3, 0xFFFFFFFF)])
 def test_fused_filter_sum(ctx, n, thr):
