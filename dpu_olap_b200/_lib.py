@@ -97,6 +97,7 @@ SIGNATURES = {
     "b2_join_aggr_u32_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _u32, _vp, _int, _vp, _sz, _vp]),
     "b2_filter_lt_u32_nullable_dev": (_int, [_vp, _vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2_filter_lt_32_host_into": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _int, _u32, _vp, _i64, _pi64, _pu64, _pt]),
+    "b2_filter_lt_32_ragged_dev": (_int, [_vp, _vp, _int, _u32, _vp, _pi64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2_filter_lt_32_dev": (_int, [_vp, _vp, _int, _u32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2_aggr_32_dev": (_int, [_vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "b2_aggr_32_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _int, _vp, _pt]),

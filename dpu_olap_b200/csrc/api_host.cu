@@ -830,8 +830,6 @@ static int filter_typed_host_into(b2_ctx* ctx, int dtype, const uint32_t* const*
   B2_RETURN_NOT_OK(ensure_streams(ctx));
   Layout L;
   B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
-  if (!L.uniform)
-    return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "nullable filter", "batches must have equal lengths");
   *total = 0;
   b2_timings tm{};
   if (L.rows() > 0) {
@@ -842,12 +840,18 @@ static int filter_typed_host_into(b2_ctx* ctx, int dtype, const uint32_t* const*
     uint8_t* d_valid = nullptr;
     int64_t* d_end = nullptr;
     void* d_ws = nullptr;
-    const size_t ws_bytes = b2_filter_ws_bytes(nbatches, L.batch_len);
+    const size_t ws_bytes = L.uniform ? b2_filter_ws_bytes(nbatches, L.batch_len)
+                                      : b2_filter_ragged_ws_bytes(L.off.data(), nbatches);
     B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_col, (size_t)L.rows() * 4));
     B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_out, (size_t)L.rows() * 4));
     B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_end, (size_t)(nbatches + 1) * 8));
     B2_RETURN_NOT_OK(sc.alloc(ctx, &d_ws, ws_bytes));
     cudaStream_t s = ctx->s_compute;
+    int64_t* d_off = nullptr;
+    if (!L.uniform) {  // ragged batches: the kernel takes its tile geometry from the offset table
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_off, (size_t)(nbatches + 1) * 8));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_off, L.off.data(), (size_t)(nbatches + 1) * 8, cudaMemcpyHostToDevice, s));
+    }
     gather_begin(ctx, nbatches, L.rows());
     B2_RETURN_NOT_OK(upload(ctx, d_col, L, batch_ptrs, 0, nbatches, s, &tm.h2d_bytes));
     if (nullable) {
@@ -855,8 +859,13 @@ static int filter_typed_host_into(b2_ctx* ctx, int dtype, const uint32_t* const*
       B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
       tm.h2d_bytes += (int64_t)bits.size();
     }
-    B2_RETURN_NOT_OK(b2_filter_lt_32_dev(ctx, d_col, dtype, threshold, d_valid, nbatches, L.batch_len, d_out,
-                                         d_end, d_end + nbatches, nullptr, d_ws, ws_bytes, s));
+    if (L.uniform)
+      B2_RETURN_NOT_OK(b2_filter_lt_32_dev(ctx, d_col, dtype, threshold, d_valid, nbatches, L.batch_len, d_out,
+                                           d_end, d_end + nbatches, nullptr, d_ws, ws_bytes, s));
+    else
+      B2_RETURN_NOT_OK(b2_filter_lt_32_ragged_dev(ctx, d_col, dtype, threshold, d_valid, L.off.data(), d_off,
+                                                  nbatches, d_out, d_end, d_end + nbatches, nullptr, d_ws,
+                                                  ws_bytes, s));
     std::vector<int64_t> end((size_t)nbatches + 1);
     B2_CUDA_OK(ctx, cudaMemcpyAsync(end.data(), d_end, (size_t)(nbatches + 1) * 8, cudaMemcpyDeviceToHost, s));
     B2_CUDA_OK(ctx, cudaStreamSynchronize(s));

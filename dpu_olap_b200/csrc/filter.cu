@@ -740,4 +740,21 @@ int b2_filter_lt_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_in, const int64_t
                        static_cast<cudaStream_t>(stream));
 }
 
+int b2_filter_lt_32_ragged_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_t threshold_bits,
+                               const uint8_t* d_valid, const int64_t* h_batch_off, const int64_t* d_batch_off,
+                               int64_t nbatches, void* d_out, int64_t* d_batch_end, int64_t* d_total,
+                               const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, dtype == B2_U32 || dtype == B2_I32 || dtype == B2_F32, "dtype must be B2_U32, B2_I32 or B2_F32");
+  B2_REQUIRE(ctx, nbatches >= 0, "negative size");
+  B2_REQUIRE(ctx, h_batch_off && d_batch_off, "batch offset tables are null");
+  for (int64_t b = 0; b < nbatches; ++b)
+    B2_REQUIRE(ctx, h_batch_off[b + 1] >= h_batch_off[b], "batch offsets must be non-decreasing");
+  B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_valid) & 3) == 0, "validity bitmap must be 4-byte aligned");
+  return filter_launch(ctx, dtype, static_cast<const uint32_t*>(d_in), reinterpret_cast<const uint32_t*>(d_valid),
+                       nbatches, 0, h_batch_off, d_batch_off, threshold_bits, static_cast<uint32_t*>(d_out),
+                       d_batch_end, d_total, d_carry_in, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

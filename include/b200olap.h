@@ -188,6 +188,10 @@ int b2_filter_lt_32_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_t thres
 /* Ragged variant: batch b occupies d_in[d_batch_off[b] .. d_batch_off[b+1]) (int64 device array
  * of nbatches+1 entries; host copy h_batch_off is needed to size the launch). Empty batches ok. */
 size_t b2_filter_ragged_ws_bytes(const int64_t* h_batch_off, int64_t nbatches);
+int b2_filter_lt_32_ragged_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_t threshold_bits,
+                               const uint8_t* d_valid, const int64_t* h_batch_off, const int64_t* d_batch_off,
+                               int64_t nbatches, void* d_out, int64_t* d_batch_end, int64_t* d_total,
+                               const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, void* stream);
 int b2_filter_lt_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_in, const int64_t* h_batch_off,
                                 const int64_t* d_batch_off, int64_t nbatches, uint32_t threshold,
                                 uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
@@ -216,8 +220,8 @@ int b2_filter_lt_u32_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
                                const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
                                uint32_t* out, int64_t out_capacity, int64_t* out_counts,
                                uint64_t* total, b2_timings* timings);
-/* Nullable form of b2_filter_lt_u32_host_into (validity arguments as b2_aggr_u32_host). Batches
- * must have equal lengths (B2_ERR_UNSUPPORTED otherwise); not chunked. */
+/* Nullable form of b2_filter_lt_u32_host_into (validity arguments as b2_aggr_u32_host). Batches may
+ * have different lengths; not chunked. */
 int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
                                         const uint8_t* const* valid_ptrs, const int64_t* valid_bit_offsets,
                                         const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,

@@ -171,13 +171,25 @@ def test_take_gpu_with_arrow_nulls(ctx):
     assert isinstance(res3[0], np.ndarray)
 
 
-def test_nullable_ragged_batches_are_rejected_loudly(ctx):
+def test_nullable_ragged_batches_and_loud_rejections(ctx):
+    import pyarrow.compute as pc
     from dpu_olap_b200 import ops
     from dpu_olap_b200._lib import B2Error
-    batches = [pa.array([1, None, 3], type=pa.uint32()), pa.array([1, None], type=pa.uint32())]
-    with pytest.raises(B2Error) as e:
-        ops.FilterGpu(ctx, batches).GetResult()
+    rng = np.random.default_rng(17)
+    # batches of different lengths (one empty) with nulls: the ragged kernel path with a bitmap
+    batches = []
+    for n in (3, 0, 5000, 4096, 70_001, 1):
+        v, valid = make(rng, n, 0.3)
+        batches.append(pa.array(v, type=pa.uint32(), mask=~valid))
+    chunks = ops.FilterGpu(ctx, batches).GetResult()
+    for arr, got in zip(batches, chunks):
+        exp = pc.filter(arr, pc.less(arr, pa.scalar(1 << 30, pa.uint32())))
+        assert np.array_equal(got, exp.to_numpy(zero_copy_only=False).astype(np.uint32))
+    ragged_take = [pa.array([1, None, 3], type=pa.uint32()), pa.array([1, None], type=pa.uint32())]
+    with pytest.raises(B2Error) as e:   # the nullable take still wants equal batch lengths
+        ops.TakeGpu(ctx, ragged_take, [pa.array([0, None, 1], type=pa.uint32()), pa.array([0, 1], type=pa.uint32())]).Run()
     assert e.value.status == 4  # B2_ERR_UNSUPPORTED
+    batches = ragged_take
     with pytest.raises(ValueError):  # the join has no null semantics here
         ops.JoinGpu(ctx, [{"fk": batches[0], "y": batches[0]}], [{"pk": batches[0], "x": batches[0]}])
 
