@@ -16,8 +16,9 @@ One JSON line on stdout (rank 0). Besides the driver's keys it carries
   e2e           same metric through the host-buffer C ABI (b2_filter_lt_u32_host_into):
                 pinned host batches in, host result out, copies inside the timed region
   cpu_baseline  Arrow Acero (the reference's CPU engine) on this box's host cores, bounded sample
-  ops           the other operators of the path (sum, take, join) and the selectivity sweep,
-                each timed over the same K steps
+  ops           the other operators of the path (sum, take, join), the selectivity sweep, the
+                nullable variants and the fused join->aggregate pipelines, each timed over the same
+                K steps and checked against torch on the device
 """
 from __future__ import annotations
 
