@@ -180,8 +180,12 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
         const uint32_t w[4] = {kk[q].x, kk[q].y, kk[q].z, kk[q].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint32_t b = bucket_or_skip<false>(w[e], 0u, g, sel);
-          if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
+          if (sel.mask == 0) {  // every row is kept: no per-row branch (uniform test)
+            atomicAdd(&cnt[part_bucket(wang_hash_u32(w[e]), g.shl, g.bits)], 1u);
+          } else {
+            const uint32_t b = bucket_or_skip<false>(w[e], 0u, g, sel);
+            if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
+          }
         }
       }
     }
@@ -198,8 +202,12 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     }
 #pragma unroll
     for (int q = 0; q < kU; ++q) {
-      const uint32_t b = bucket_or_skip<kValPred>(key[q], val[q], g, sel);
-      if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
+      if (!kValPred && sel.mask == 0) {
+        atomicAdd(&cnt[part_bucket(wang_hash_u32(key[q]), g.shl, g.bits)], 1u);
+      } else {
+        const uint32_t b = bucket_or_skip<kValPred>(key[q], val[q], g, sel);
+        if (b != 0xffffffffu) atomicAdd(&cnt[b], 1u);
+      }
     }
   }
   for (int64_t row = base + tid; row < u.row1; row += kThreads) {
@@ -265,11 +273,20 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     if (t0 + kTileRows <= u.row1) {  // full tile: no bounds checks
 #pragma unroll
       for (int it = 0; it < kI; ++it) load_row<kAoS>(in, t0 + it * kT + tid, key[it], val[it]);
+      if (!kValPred && sel.mask == 0) {
+        // every row is kept (no slice, no predicate): no per-row branch around the ranking atomic
 #pragma unroll
-      for (int it = 0; it < kI; ++it) {
-        const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g, sel);
-        packed[it] = b;
-        if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192
+        for (int it = 0; it < kI; ++it) {
+          const uint32_t b = part_bucket(wang_hash_u32(key[it]), g.shl, g.bits);
+          packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < kI; ++it) {
+          const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g, sel);
+          packed[it] = b;
+          if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);  // rank < 8192
+        }
       }
     } else {
 #pragma unroll
