@@ -688,8 +688,8 @@ int b2_shuffle_partition_u32_dev(b2_ctx* ctx, const uint32_t* d_key, const uint3
                                  size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
   B2_REQUIRE(ctx, n >= 0, "negative size");
-  B2_REQUIRE(ctx, nranks >= 1 && nranks <= 256 && (nranks & (nranks - 1)) == 0,
-             "nranks must be a power of two <= 256");
+  B2_REQUIRE(ctx, nranks >= 1 && nranks <= 1024 && (nranks & (nranks - 1)) == 0,
+             "nranks must be a power of two <= 1024");
   B2_REQUIRE(ctx, d_dest_off != nullptr, "d_dest_off is null");
   B2_REQUIRE(ctx, n == 0 || (d_key && d_val && d_pairs_out), "null pointer");
   int bits = 0;

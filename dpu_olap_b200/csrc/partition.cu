@@ -550,6 +550,225 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   }
 }
 
+// ---- local scatter that only writes whole 32-byte sectors ------------------------------------------
+// With a fan-out of 512-1024 a bucket's run in one 8192-row tile is 8-16 rows (64-128 B) and starts
+// at an arbitrary 8-byte offset, so most runs begin and end with a PARTIAL 32-byte sector. ncu at
+// 2^27 rows (profiles/r1_scatter_fanout.md): B200's L2 fills a partially written sector from DRAM
+// as soon as the write misses (13.6 M fills, +40 % DRAM reads, 1.46 sectors written per sector of
+// payload) and the LSU backs up behind those stores (lg_throttle 5.2 stall cycles per issue against
+// 0.6 at a fan-out of 256) — the pass takes 1.8x as long per row. This kernel therefore holds back,
+// per bucket, the rows that do not complete a sector (at most 3, in shared memory) and prepends them
+// to the bucket's rows of the next tile; four adjacent lanes store one whole, aligned sector. Only
+// the first and the last sector of a (unit, bucket) run can be partial.
+constexpr int kScRows = 4;                       // rows per 32-byte sector
+constexpr int kScT = 512, kScI = 16;
+constexpr int kScTile = kScT * kScI;             // 8192 rows
+constexpr int kScBpt = (1 << kPartMaxBits) / kScT;  // buckets per thread in the per-bucket phases
+constexpr int kScMaxSec = (kScTile + 3 * (1 << kPartMaxBits)) / kScRows;  // whole sectors one tile can flush
+
+struct ScDesc {       // per bucket and tile, read once per flushed row
+  int32_t sbase;      // stage index of (carried ++ staged) position 0, minus 4 * (first flushed sector)
+  uint32_t dsec;      // destination sector of position 0, minus (first flushed sector); between two
+                      // tiles: the next unwritten sector of the run, counted from the output base
+};
+struct ScSmem {
+  uint2 stage[kScTile];                         // 64 KB: the tile's rows sorted by bucket
+  uint2 carry[(1 << kPartMaxBits) * 3];         // 24 KB: held-back rows (slots 0..ghost-1 are not ours)
+  ScDesc bd[1 << kPartMaxBits];                 // 8 KB
+  uint32_t tile_cnt[1 << kPartMaxBits];         // carried + rows ranked so far
+  int32_t sbase[1 << kPartMaxBits];             // tile_start - carried
+  uint16_t meta[1 << kPartMaxBits];             // first flushed sector (12 bits) | carried << 12 | ghost << 14
+  uint16_t sec_desc[kScMaxSec + 16];            // flushed sector -> bucket | (first sector: carried << 10 | ghost << 12)
+  uint32_t warp_tot[kScT / 32];
+  uint32_t n_sec;
+};
+
+template <bool kAoS>
+__global__ void __launch_bounds__(kScT, 2)
+part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
+                            const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
+                            PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
+                            int64_t out_cap, unsigned int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ScSmem& sm = *reinterpret_cast<ScSmem*>(smem);
+  const int P = 1 << g.bits;
+  const SliceSel sel = slice_sel(g);
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
+  if (!u.valid) return;
+  constexpr int kW = kScT / 32;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t cap = (uint64_t)out_cap;  // rows
+
+#pragma unroll
+  for (int q = 0; q < kScBpt; ++q) {
+    const int p = kScBpt * tid + q;
+    if (p < P) {
+      const uint64_t pos = scanned[u.hbase + (int64_t)p * u.ustride];  // first output row of (unit, bucket)
+      const uint32_t ghost = (uint32_t)(pos & (kScRows - 1));         // rows of that sector that are not ours
+      sm.bd[p].dsec = (uint32_t)(pos >> 2);
+      sm.meta[p] = (uint16_t)((ghost << 12) | (ghost << 14));
+      sm.tile_cnt[p] = ghost;
+    }
+  }
+  __syncthreads();
+
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kScTile) {
+    // ---- load, hash once, rank inside the bucket (ranks continue after the carried rows) ----
+    uint32_t key[kScI], val[kScI], packed[kScI];  // packed = bucket | rank << 16
+    if (t0 + kScTile <= u.row1) {
+#pragma unroll
+      for (int it = 0; it < kScI; ++it) load_row<kAoS>(in, t0 + it * kScT + tid, key[it], val[it]);
+      if (sel.mask == 0) {
+#pragma unroll
+        for (int it = 0; it < kScI; ++it) {
+          const uint32_t b = part_bucket(wang_hash_u32(key[it]), g.shl, g.bits);
+          packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < kScI; ++it) {
+          const uint32_t b = bucket_or_skip<false>(key[it], val[it], g, sel);
+          packed[it] = b;
+          if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < kScI; ++it) {
+        const int64_t row = t0 + it * kScT + tid;
+        key[it] = 0;
+        val[it] = 0;
+        packed[it] = 0xffffffffu;
+        if (row < u.row1) {
+          load_row<kAoS>(in, row, key[it], val[it]);
+          const uint32_t b = bucket_or_skip<false>(key[it], val[it], g, sel);
+          if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- one scan for the staged position and the first flushed sector of every bucket ----
+    {
+      uint32_t mine = 0;
+#pragma unroll
+      for (int q = 0; q < kScBpt; ++q) {
+        const int p = kScBpt * tid + q;
+        if (p < P) {
+          const uint32_t tot = sm.tile_cnt[p];  // carried + new
+          // rows <= 8192 and sectors <= 2816 never carry into each other
+          mine += (tot - ((sm.meta[p] >> 12) & 3u)) | ((tot >> 2) << 16);
+        }
+      }
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) sm.warp_tot[warp] = incl;
+      __syncthreads();
+      const uint32_t w = lane < kW ? sm.warp_tot[lane] : 0;
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < kW; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      const uint32_t all = __shfl_sync(0xffffffffu, wi, kW - 1);
+      if (tid == 0) sm.n_sec = all >> 16;
+      uint32_t excl = __shfl_sync(0xffffffffu, wi - w, warp) + incl - mine;
+#pragma unroll
+      for (int q = 0; q < kScBpt; ++q) {
+        const int p = kScBpt * tid + q;
+        if (p < P) {
+          // re-read rather than keep live across the scan (the row registers fill the budget)
+          const uint32_t tot = sm.tile_cnt[p];
+          const uint32_t cg = sm.meta[p] >> 12;  // carried | ghost << 2
+          const uint32_t tc = tot - (cg & 3u), ns = tot >> 2;
+          const uint32_t start = excl & 0xffffu, so = excl >> 16;
+          const int32_t sb = (int32_t)start - (int32_t)(cg & 3u);
+          sm.sbase[p] = sb;
+          ScDesc d;
+          d.sbase = sb - (int32_t)(so * kScRows);
+          d.dsec = sm.bd[p].dsec - so;
+          sm.bd[p] = d;
+          sm.meta[p] = (uint16_t)(so | (cg << 12));
+          if (ns) sm.sec_desc[so] = (uint16_t)(p | (cg << 10));  // the first sector may hold carried / ghost rows
+          for (uint32_t i = 1; i < ns; ++i) sm.sec_desc[so + i] = (uint16_t)p;
+          excl += tc | (ns << 16);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stage the tile sorted by bucket ----
+#pragma unroll
+    for (int it = 0; it < kScI; ++it) {
+      if (packed[it] != 0xffffffffu) {
+        const uint32_t b = packed[it] & 0xffffu;
+        sm.stage[sm.sbase[b] + (int32_t)(packed[it] >> 16)] = make_uint2(key[it], val[it]);
+      }
+    }
+    __syncthreads();
+
+    // ---- flush whole sectors: four adjacent lanes per 32-byte sector of the destination ----
+    {
+      const uint32_t n_slot = sm.n_sec * kScRows;
+      const uint32_t l = tid & 3;
+      for (uint32_t t = tid; t < n_slot; t += kScT) {  // t = 4 * sector + lane in the sector
+        const uint32_t s = t >> 2;
+        const uint32_t sd = sm.sec_desc[s];
+        const uint32_t b = sd & 1023u, c0 = (sd >> 10) & 3u, ghost = sd >> 12;
+        const ScDesc d = sm.bd[b];
+        const uint2* src = l < c0 ? &sm.carry[b * 3 + l] : &sm.stage[d.sbase + (int32_t)t];
+        const uint2 kv = *src;
+        const uint64_t row = (uint64_t)(d.dsec + s) * kScRows + l;
+        if (l >= ghost) {  // ghost rows belong to the run before ours
+          if (row < cap) st_stream_v2(out + row, kv);
+          else if (overflow) *overflow = 1u;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- hold back the rows that did not complete a sector; advance; reset the counters ----
+#pragma unroll
+    for (int q = 0; q < kScBpt; ++q) {
+      const int p = kScBpt * tid + q;
+      if (p < P) {
+        const uint32_t tot = sm.tile_cnt[p];
+        const uint32_t m = sm.meta[p];
+        const uint32_t so = m & 0xfffu, c0 = (m >> 12) & 3u, ghost = m >> 14;
+        const uint32_t nsec = tot >> 2, rem = tot & 3u;
+        // nothing flushed: append the new rows to the carry; otherwise the tail of the staged rows
+        // becomes the carry (carried < 4 <= 4 * nsec)
+        const uint32_t first = nsec ? 0u : c0;
+        const int32_t from = sm.sbase[p] + (int32_t)(nsec * kScRows);
+#pragma unroll
+        for (uint32_t i = 0; i < 3; ++i)
+          if (i >= first && i < rem) sm.carry[p * 3 + i] = sm.stage[from + (int32_t)i];
+        sm.bd[p].dsec += so + nsec;
+        sm.meta[p] = (uint16_t)((rem << 12) | ((nsec ? 0u : ghost) << 14));
+        sm.tile_cnt[p] = rem;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- end of the unit: the last, partial sector of every bucket ----
+  for (int i = tid; i < P * kScRows; i += kScT) {
+    const int b = i >> 2;
+    const uint32_t l = i & 3;
+    const uint32_t m = sm.meta[b];
+    if (l >= (m >> 14) && l < ((m >> 12) & 3u)) {
+      const uint64_t row = (uint64_t)sm.bd[b].dsec * kScRows + l;
+      if (row < cap) st_stream_v2(out + row, sm.carry[b * 3 + l]);
+      else if (overflow) *overflow = 1u;
+    }
+  }
+}
+
 // part_off[s*P + p] = first output row of (segment s, bucket p); part_off[nseg*P] = total rows.
 __global__ void part_offsets_kernel(const uint64_t* __restrict__ scanned,
                                     const int64_t* __restrict__ unit_first, int64_t nseg, int P,
@@ -601,6 +820,7 @@ PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
 }
 
 int g_scatter_variant = 0;  // tuning hook (b200olap_tune_scatter_variant)
+int g_sectors_min_bits = 10;  // fan-out (log2) from which the whole-sector scatter kernel is used
 
 template <bool kAoS, int kT, int kI, int kCtas, bool kValPred = false>
 int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const PartInput& in,
@@ -668,6 +888,20 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
   const int64_t* unit_first = reinterpret_cast<const int64_t*>(base + L.off_unit_first);
   const uint64_t* scanned = reinterpret_cast<const uint64_t*>(base + L.off_scanned);
   if (L.max_units > 0) {
+    // whole-sector scatter: local destinations, 32-byte aligned output, fan-out at or above the threshold
+    const bool sectors = !d_bucket_addr && !g.val_pred && (reinterpret_cast<uintptr_t>(d_out) & 31) == 0 &&
+                         (uint64_t)out_cap < (1ull << 34) && g.bits >= g_sectors_min_bits;
+    if (sectors) {
+      static bool seen[kB2MaxDevices] = {};
+      if (b2_first_use_on_device(ctx, seen)) {
+        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScSmem)));
+      }
+      part_scatter_sectors_kernel<kAoS><<<(unsigned)L.max_units, kScT, sizeof(ScSmem), s>>>(
+          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
+      B2_LAUNCH_CHECK(ctx, "part_scatter_sectors_kernel");
+      return B2_OK;
+    }
     if (d_bucket_addr) {  // peer destinations: whole 128-byte lines only (line carry)
       static bool seen[kB2MaxDevices] = {};  // one table per template instantiation
       if (b2_first_use_on_device(ctx, seen)) {
@@ -684,6 +918,7 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
         case 1: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 8, 3>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 2: B2_RETURN_NOT_OK((launch_scatter<kAoS, 256, 16, 4>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 3: B2_RETURN_NOT_OK((launch_scatter<kAoS, 1024, 8, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
+        case 8: B2_RETURN_NOT_OK((launch_scatter<kAoS, 1024, 16, 1>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         default: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
       }
     }
@@ -794,8 +1029,13 @@ int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, in
                    d_overflow, base + F.off_pass, F.pass_bytes, s);
 }
 
+extern "C" int b200olap_sectors_min_bits() { return g_sectors_min_bits; }
 extern "C" int b200olap_tune_scatter_variant(int v) {
-  if (v < 0 || v > 3) return B2_ERR_INVALID;
+  if (v >= 100 && v <= 199) {  // 100 + b: whole-sector scatter from a fan-out of 2^b (199 = never)
+    g_sectors_min_bits = v - 100;
+    return B2_OK;
+  }
+  if (v < 0 || (v > 3 && v != 8)) return B2_ERR_INVALID;
   g_scatter_variant = v;
   return B2_OK;
 }
