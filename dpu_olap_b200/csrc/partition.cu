@@ -716,17 +716,35 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     {
       const uint32_t n_slot = sm.n_sec * kScRows;
       const uint32_t l = tid & 3;
-      for (uint32_t t = tid; t < n_slot; t += kScT) {  // t = 4 * sector + lane in the sector
-        const uint32_t s = t >> 2;
-        const uint32_t sd = sm.sec_desc[s];
-        const uint32_t b = sd & 1023u, c0 = (sd >> 10) & 3u, ghost = sd >> 12;
-        const ScDesc d = sm.bd[b];
-        const uint2* src = l < c0 ? &sm.carry[b * 3 + l] : &sm.stage[d.sbase + (int32_t)t];
-        const uint2 kv = *src;
-        const uint64_t row = (uint64_t)(d.dsec + s) * kScRows + l;
-        if (l >= ghost) {  // ghost rows belong to the run before ours
-          if (row < cap) st_stream_v2(out + row, kv);
-          else if (overflow) *overflow = 1u;
+      constexpr int kUn = 4;  // independent slots in flight per thread: the table -> descriptor -> row
+                              // chain is three dependent shared-memory reads
+      for (uint32_t t0s = tid; t0s < n_slot; t0s += kUn * kScT) {  // t = 4 * sector + lane in the sector
+        uint32_t sd[kUn];
+        ScDesc d[kUn];
+        uint2 kv[kUn];
+#pragma unroll
+        for (int k = 0; k < kUn; ++k) {
+          const uint32_t t = t0s + k * kScT;
+          sd[k] = t < n_slot ? sm.sec_desc[t >> 2] : 0u;  // past the end: bucket 0, never stored
+        }
+#pragma unroll
+        for (int k = 0; k < kUn; ++k) d[k] = sm.bd[sd[k] & 1023u];
+#pragma unroll
+        for (int k = 0; k < kUn; ++k) {
+          const uint32_t t = t0s + k * kScT;
+          const uint32_t b = sd[k] & 1023u, c0 = (sd[k] >> 10) & 3u;
+          const uint32_t si = t < n_slot ? (uint32_t)(d[k].sbase + (int32_t)t) : 0u;
+          const uint2* src = l < c0 ? &sm.carry[b * 3 + l] : &sm.stage[si];
+          kv[k] = *src;
+        }
+#pragma unroll
+        for (int k = 0; k < kUn; ++k) {
+          const uint32_t t = t0s + k * kScT;
+          const uint64_t row = (uint64_t)(d[k].dsec + (t >> 2)) * kScRows + l;
+          if (t < n_slot && l >= (sd[k] >> 12)) {  // ghost rows belong to the run before ours
+            if (row < cap) st_stream_v2(out + row, kv[k]);
+            else if (overflow) *overflow = 1u;
+          }
         }
       }
     }
