@@ -838,7 +838,7 @@ PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
 }
 
 int g_scatter_variant = 0;  // tuning hook (b200olap_tune_scatter_variant)
-int g_sectors_min_bits = 10;  // fan-out (log2) from which the whole-sector scatter kernel is used
+int g_sectors_min_bits = 9;  // fan-out (log2) from which the whole-sector scatter kernel is used (measured: join_lab smem:0:b)
 
 template <bool kAoS, int kT, int kI, int kCtas, bool kValPred = false>
 int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const PartInput& in,
@@ -1047,12 +1047,14 @@ int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, in
                    d_overflow, base + F.off_pass, F.pass_bytes, s);
 }
 
+// Tuning hooks (labs and tests only; not part of include/b200olap.h).
 extern "C" int b200olap_sectors_min_bits() { return g_sectors_min_bits; }
+extern "C" int b200olap_tune_sectors_min_bits(int bits) {  // 0 = always, > 10 = never
+  if (bits < 0) return B2_ERR_INVALID;
+  g_sectors_min_bits = bits;
+  return B2_OK;
+}
 extern "C" int b200olap_tune_scatter_variant(int v) {
-  if (v >= 100 && v <= 199) {  // 100 + b: whole-sector scatter from a fan-out of 2^b (199 = never)
-    g_sectors_min_bits = v - 100;
-    return B2_OK;
-  }
   if (v < 0 || (v > 3 && v != 8)) return B2_ERR_INVALID;
   g_scatter_variant = v;
   return B2_OK;
