@@ -227,7 +227,7 @@ part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 // 8-byte table read (destination of the bucket's run minus its position in the tile) per row
 // instead of hashing the key again. The first version of this kernel spent 105-111
 // lane-instructions per row (profiles/r1_join.md).
-template <bool kAoS, int kT, int kI, int kCtas, bool kValPred>
+template <bool kAoS, int kT, int kI, int kCtas, bool kValPred, bool kPre>
 __global__ void __launch_bounds__(kT, kCtas)
 part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                     const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
@@ -267,12 +267,31 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   }
   __syncthreads();
 
-  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kTileRows) {
-    // ---- load, hash once, rank inside the bucket ----
-    uint32_t key[kI], val[kI], packed[kI];  // packed = bucket | rank << 16
+  // kPre: the rows of the NEXT tile are requested right after the current tile is staged (their
+  // registers are free from then on), so the loads fly during the stream-out instead of stalling
+  // the next rank step.
+  uint32_t key[kI], val[kI];
+  auto load_tile = [&](int64_t t0) {
     if (t0 + kTileRows <= u.row1) {  // full tile: no bounds checks
 #pragma unroll
       for (int it = 0; it < kI; ++it) load_row<kAoS>(in, t0 + it * kT + tid, key[it], val[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < kI; ++it) {
+        const int64_t row = t0 + it * kT + tid;
+        key[it] = 0;
+        val[it] = 0;
+        if (row < u.row1) load_row<kAoS>(in, row, key[it], val[it]);
+      }
+    }
+  };
+  if (kPre && u.row0 < u.row1) load_tile(u.row0);
+
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kTileRows) {
+    // ---- (load,) hash once, rank inside the bucket ----
+    if (!kPre) load_tile(t0);
+    uint32_t packed[kI];  // bucket | rank << 16
+    if (t0 + kTileRows <= u.row1) {
       if (!kValPred && sel.mask == 0) {
         // every row is kept (no slice, no predicate): no per-row branch around the ranking atomic
 #pragma unroll
@@ -292,11 +311,8 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 #pragma unroll
       for (int it = 0; it < kI; ++it) {
         const int64_t row = t0 + it * kT + tid;
-        key[it] = 0;
-        val[it] = 0;
         packed[it] = 0xffffffffu;
         if (row < u.row1) {
-          load_row<kAoS>(in, row, key[it], val[it]);
           const uint32_t b = bucket_or_skip<kValPred>(key[it], val[it], g, sel);
           if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&tile_cnt[b], 1u) << 16);
         }
@@ -357,6 +373,8 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
       }
     }
     __syncthreads();
+
+    if (kPre && t0 + kTileRows < u.row1) load_tile(t0 + kTileRows);
 
     // ---- stream out: consecutive threads -> consecutive rows of a bucket's run ----
     const uint32_t total = s_tile_total;
@@ -583,7 +601,7 @@ struct ScSmem {
   uint32_t n_sec;
 };
 
-template <bool kAoS>
+template <bool kAoS, bool kPre>
 __global__ void __launch_bounds__(kScT, 2)
 part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                             const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
@@ -612,12 +630,31 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   }
   __syncthreads();
 
-  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kScTile) {
-    // ---- load, hash once, rank inside the bucket (ranks continue after the carried rows) ----
-    uint32_t key[kScI], val[kScI], packed[kScI];  // packed = bucket | rank << 16
-    if (t0 + kScTile <= u.row1) {
+  // kPre: the rows of the NEXT tile are requested right after the current tile is staged (their
+  // registers are free from then on), so the loads fly during the flush and carry steps instead of
+  // stalling the next rank step.
+  uint32_t key[kScI], val[kScI];
+  auto load_tile = [&](int64_t t0) {
+    if (t0 + kScTile <= u.row1) {  // full tile: no bounds checks
 #pragma unroll
       for (int it = 0; it < kScI; ++it) load_row<kAoS>(in, t0 + it * kScT + tid, key[it], val[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < kScI; ++it) {
+        const int64_t row = t0 + it * kScT + tid;
+        key[it] = 0;
+        val[it] = 0;
+        if (row < u.row1) load_row<kAoS>(in, row, key[it], val[it]);
+      }
+    }
+  };
+  if (kPre && u.row0 < u.row1) load_tile(u.row0);
+
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kScTile) {
+    // ---- (load,) hash once, rank inside the bucket (ranks continue after the carried rows) ----
+    if (!kPre) load_tile(t0);
+    uint32_t packed[kScI];  // bucket | rank << 16
+    if (t0 + kScTile <= u.row1) {
       if (sel.mask == 0) {
 #pragma unroll
         for (int it = 0; it < kScI; ++it) {
@@ -636,11 +673,8 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 #pragma unroll
       for (int it = 0; it < kScI; ++it) {
         const int64_t row = t0 + it * kScT + tid;
-        key[it] = 0;
-        val[it] = 0;
         packed[it] = 0xffffffffu;
         if (row < u.row1) {
-          load_row<kAoS>(in, row, key[it], val[it]);
           const uint32_t b = bucket_or_skip<false>(key[it], val[it], g, sel);
           if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
         }
@@ -711,6 +745,8 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
       }
     }
     __syncthreads();
+
+    if (kPre && t0 + kScTile < u.row1) load_tile(t0 + kScTile);
 
     // ---- flush whole sectors: four adjacent lanes per 32-byte sector of the destination ----
     {
@@ -838,20 +874,21 @@ PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
 }
 
 int g_scatter_variant = 0;  // tuning hook (b200olap_tune_scatter_variant)
+int g_scatter_prefetch = 1;  // request the next tile's rows while the current one is flushed
 int g_sectors_min_bits = 9;  // fan-out (log2) from which the whole-sector scatter kernel is used (measured: join_lab smem:0:b)
 
-template <bool kAoS, int kT, int kI, int kCtas, bool kValPred = false>
+template <bool kAoS, int kT, int kI, int kCtas, bool kValPred = false, bool kPre = false>
 int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const PartInput& in,
                    const int64_t* d_seg_off, const int64_t* unit_first, int64_t nseg, int64_t unit_rows,
                    const PartGeom& g, const uint64_t* scanned, uint2* d_out, int64_t out_cap,
                    unsigned int* d_overflow) {
   static bool seen[kB2MaxDevices] = {};
   if (b2_first_use_on_device(ctx, seen)) {
-    B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred>,
+    B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred, kPre>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)scatter_smem_bytes(kPartMaxBits, kT * kI)));
   }
-  part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred><<<(unsigned)units, kT, scatter_smem_bytes(bits, kT * kI), s>>>(
+  part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred, kPre><<<(unsigned)units, kT, scatter_smem_bytes(bits, kT * kI), s>>>(
       in, d_seg_off, unit_first, nseg, unit_rows, g, scanned, d_out, out_cap, nullptr, d_overflow);
   return B2_OK;
 }
@@ -912,11 +949,17 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
     if (sectors) {
       static bool seen[kB2MaxDevices] = {};
       if (b2_first_use_on_device(ctx, seen)) {
-        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS>,
+        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScSmem)));
+        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScSmem)));
       }
-      part_scatter_sectors_kernel<kAoS><<<(unsigned)L.max_units, kScT, sizeof(ScSmem), s>>>(
-          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
+      if (g_scatter_prefetch)
+        part_scatter_sectors_kernel<kAoS, true><<<(unsigned)L.max_units, kScT, sizeof(ScSmem), s>>>(
+            in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
+      else
+        part_scatter_sectors_kernel<kAoS, false><<<(unsigned)L.max_units, kScT, sizeof(ScSmem), s>>>(
+            in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
       B2_LAUNCH_CHECK(ctx, "part_scatter_sectors_kernel");
       return B2_OK;
     }
@@ -930,14 +973,22 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
           in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr);
     } else if (g.val_pred) {  // pushed-down value predicate: one shape, the default one
-      B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
+      if (g_scatter_prefetch)
+        B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, true, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
+      else
+        B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
     } else {
       switch (g_scatter_variant) {
         case 1: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 8, 3>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 2: B2_RETURN_NOT_OK((launch_scatter<kAoS, 256, 16, 4>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 3: B2_RETURN_NOT_OK((launch_scatter<kAoS, 1024, 8, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 8: B2_RETURN_NOT_OK((launch_scatter<kAoS, 1024, 16, 1>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
-        default: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
+        default:
+          if (g_scatter_prefetch)
+            B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, false, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
+          else
+            B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
+          break;
       }
     }
     B2_LAUNCH_CHECK(ctx, "part_scatter_kernel");
@@ -1052,6 +1103,10 @@ extern "C" int b200olap_sectors_min_bits() { return g_sectors_min_bits; }
 extern "C" int b200olap_tune_sectors_min_bits(int bits) {  // 0 = always, > 10 = never
   if (bits < 0) return B2_ERR_INVALID;
   g_sectors_min_bits = bits;
+  return B2_OK;
+}
+extern "C" int b200olap_tune_scatter_prefetch(int on) {
+  g_scatter_prefetch = on != 0;
   return B2_OK;
 }
 extern "C" int b200olap_tune_scatter_variant(int v) {

@@ -3,8 +3,8 @@
 
     python tools/join_lab.py [--sf 64,512] [--configs smem:0,smem:1,smem:2,smem:3]
 
-`smem:v[:b]` = shared-memory tables after two radix passes, scatter-kernel shape v, whole-sector
-scatter kernel from a fan-out of 2^b (default 10). (Commit 788c869
+`smem:v[:b[:p]]` = shared-memory tables after two radix passes, scatter-kernel shape v, whole-sector
+scatter kernel from a fan-out of 2^b (default 9), next-tile prefetch p = 0 / 1 (default 1). (Commit 788c869
 also had `l2:G:F`, the L2-resident table experiment described in profiles/r1_join_l2.md.)
 """
 import argparse, json, sys
@@ -39,6 +39,8 @@ def main():
             assert ctx._lib.b200olap_tune_scatter_variant(int(f[1]) if len(f) > 1 else 0) == 0
             if len(f) > 2:  # smem:v:b = whole-sector scatter kernel from a fan-out of 2^b
                 assert ctx._lib.b200olap_tune_sectors_min_bits(int(f[2])) == 0
+            if len(f) > 3:  # smem:v:b:p = next-tile prefetch in the scatter kernels off / on
+                assert ctx._lib.b200olap_tune_scatter_prefetch(int(f[3])) == 0
             ws = torch.empty(ctx.join_ws_bytes(n, n) + 256, dtype=torch.uint8, device="cuda")
             step = lambda: ctx.join_dev(fk, y, pk, x, out_capacity=n, ws=ws, outs=outs, out_rows=rows)
             for o in outs:
