@@ -87,3 +87,28 @@ def test_sector_kernel_matches_default_kernel_bytewise(sectors):
     part = np.repeat(np.arange(1024), np.diff(off))
     oa, ob = np.lexsort((va, part)), np.lexsort((vb, part))
     assert np.array_equal(ka[oa], kb[ob]) and np.array_equal(va[oa], vb[ob])
+
+
+@pytest.mark.parametrize("n,parts", [(1, 1024), (5, 512), (8191, 1024), (100_003, 1024), (1_000_001, 512), (70_001, 4)])
+def test_sector_kernel_stays_inside_its_buffers(sectors, n, parts):
+    """Output pairs, boundaries and workspace sit between sentinel guards (the pool has no
+    compute-sanitizer): nothing outside [0, n) rows is written, every row is written exactly once."""
+    from test_gpu_dev_ops import GUARD, _guarded, _guards_intact
+    S64 = -0x0123456789ABCDEF
+    rng = np.random.default_rng(n + parts)
+    key = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    val = np.arange(n, dtype=np.uint32)
+    g_p, pairs = _guarded(n, torch.int64, S64)
+    g_o, off = _guarded(parts + 1, torch.int64, S64)
+    ws_n = int(sectors._lib.b2_shuffle_ws_bytes(n, parts)) + 512
+    g_w, ws = _guarded(ws_n, torch.uint8, 0x5A)
+    assert pairs.data_ptr() % 32 == 0  # else the plain kernel would be chosen
+    sectors.shuffle_partition_dev(dev(key), dev(val), parts, pairs_out=pairs, dest_off=off, ws=ws)
+    torch.cuda.synchronize()
+    assert _guards_intact(g_p, n, S64) and _guards_intact(g_o, parts + 1, S64) and _guards_intact(g_w, ws_n, 0x5A)
+    got = pairs.cpu().numpy().view(np.uint64)
+    gk, gv = (got & 0xFFFFFFFF).astype(np.uint32), (got >> 32).astype(np.uint32)
+    assert np.array_equal(np.sort(gv), val)            # a permutation: every row exactly once
+    assert np.array_equal(gk, key[gv])                 # the key travelled with its value
+    o = off.cpu().numpy()
+    assert np.array_equal(oracle.partition_ids(gk, parts), np.repeat(np.arange(parts, dtype=np.uint32), np.diff(o)))
