@@ -102,6 +102,8 @@ SIGNATURES = {
     "b2_aggr_32_dev": (_int, [_vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "b2_aggr_32_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _int, _vp, _pt]),
     "b2_aggr_u32_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "b2_aggr_64_dev": (_int, [_vp, _vp, _int, _vp, _i64, _vp, _vp]),
+    "b2_aggr_64_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _int, _vp, _pt]),
     "b2_take_u32_nullable_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b2_aggr_u32_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _vp, _pt]),
     "b2_filter_lt_u32_nullable_host_into": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _u32, _vp, _i64, _pi64,

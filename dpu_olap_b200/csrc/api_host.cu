@@ -816,6 +816,53 @@ int b2_aggr_32_host(b2_ctx* ctx, const void* const* batch_ptrs_, const uint8_t* 
   return B2_OK;
 }
 
+int b2_aggr_64_host(b2_ctx* ctx, const void* const* batch_ptrs_, const uint8_t* const* valid_ptrs,
+                    const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches, int dtype,
+                    b2_aggr_u64* out, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  // the upload machinery moves 32-bit words: a batch of n 64-bit values is a batch of 2n words
+  const uint32_t* const* batch_ptrs = reinterpret_cast<const uint32_t* const*>(batch_ptrs_);
+  B2_REQUIRE(ctx, out != nullptr, "out is null");
+  B2_REQUIRE(ctx, nbatches >= 0 && (nbatches == 0 || batch_lens), "bad batch table");
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout L, W;  // rows (validity) and words (upload)
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
+  std::vector<int64_t> wlens((size_t)nbatches);
+  for (int64_t b = 0; b < nbatches; ++b) {
+    B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(batch_ptrs[b]) & 7) == 0, "batches must be 8-byte aligned");
+    wlens[(size_t)b] = batch_lens[b] * 2;
+  }
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, wlens.data(), nbatches, &W));
+  b2_timings tm{};
+  Scratch sc;
+  std::vector<uint8_t> bits;
+  const bool nullable = pack_validity(&bits, L, valid_ptrs, valid_bit_offsets, nbatches);
+  uint32_t* d_col = nullptr;
+  uint8_t* d_valid = nullptr;
+  b2_aggr_u64* d_out = nullptr;
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_col, (size_t)W.rows() * 4));
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_out, sizeof(b2_aggr_u64)));
+  cudaStream_t s = ctx->s_compute;
+  gather_begin(ctx, nbatches, W.rows());
+  B2_RETURN_NOT_OK(upload(ctx, d_col, W, batch_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+  if (nullable) {
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_valid, bits.size()));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
+    tm.h2d_bytes += (int64_t)bits.size();
+  }
+  B2_RETURN_NOT_OK(b2_aggr_64_dev(ctx, d_col, dtype, d_valid, L.rows(), d_out, s));
+  B2_CUDA_OK(ctx, cudaMemcpyAsync(out, d_out, sizeof(b2_aggr_u64), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  tm.d2h_bytes = sizeof(b2_aggr_u64);
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
 static int filter_typed_host_into(b2_ctx* ctx, int dtype, const uint32_t* const* batch_ptrs,
                                   const uint8_t* const* valid_ptrs, const int64_t* valid_bit_offsets,
                                   const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,

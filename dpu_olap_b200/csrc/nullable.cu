@@ -159,6 +159,145 @@ __global__ void aggr_init_kernel(b2_aggr_u32* out, bool is_signed) {
   out->max = is_signed ? 0x80000000u : 0u;
 }
 
+// ---- 64-bit columns ----------------------------------------------------------------------------
+// Same pass over uint64 / int64 values: two values per 128-bit load, two validity bits per vector
+// (vector i covers rows 2i, 2i+1 = bits 2*(i & 15) of bitmap word i >> 4). The sum wraps mod 2^64
+// in both types (Arrow's sum is unchecked); min / max compare in the type's order.
+template <bool kSigned>
+struct AggAcc64 {
+  uint64_t sum = 0;
+  uint32_t cnt = 0;
+  uint64_t mn = kSigned ? 0x7fffffffffffffffull : 0xffffffffffffffffull;
+  uint64_t mx = kSigned ? 0x8000000000000000ull : 0ull;
+};
+template <bool kSigned>
+__device__ __forceinline__ uint64_t min64(uint64_t a, uint64_t b) {
+  return kSigned ? (uint64_t)min((long long)a, (long long)b) : min(a, b);
+}
+template <bool kSigned>
+__device__ __forceinline__ uint64_t max64(uint64_t a, uint64_t b) {
+  return kSigned ? (uint64_t)max((long long)a, (long long)b) : max(a, b);
+}
+template <bool kSigned>
+__device__ __forceinline__ void agg_row64(AggAcc64<kSigned>& a, uint64_t v, bool valid) {
+  if (valid) {
+    a.cnt += 1;
+    a.sum += v;
+    a.mn = min64<kSigned>(a.mn, v);
+    a.mx = max64<kSigned>(a.mx, v);
+  }
+}
+template <bool kSigned>
+__device__ __forceinline__ uint64_t warp_min64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min64<kSigned>(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <bool kSigned>
+__device__ __forceinline__ uint64_t warp_max64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max64<kSigned>(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <bool kHasValid, bool kSigned>
+__global__ void __launch_bounds__(kAggThreads, 2)
+aggr_u64_kernel(const uint64_t* __restrict__ in, const uint32_t* __restrict__ valid_, int64_t n,
+                int64_t head, b2_aggr_u64* __restrict__ out) {
+  const uint32_t* __restrict__ valid = kHasValid ? valid_ : nullptr;
+  const int64_t nvec = (n - head) >> 1;
+  const int64_t tail_start = head + (nvec << 1);
+  const uint4* __restrict__ vin = reinterpret_cast<const uint4*>(in + head);
+  AggAcc64<kSigned> acc;
+  uint64_t cnt = 0;
+  const int64_t chunk = (int64_t)kAggThreads * kAggUnroll;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < nvec; base += (int64_t)gridDim.x * chunk) {
+    uint4 v[kAggUnroll];
+    uint32_t two[kAggUnroll];
+    if (base + chunk <= nvec) {
+#pragma unroll
+      for (int u = 0; u < kAggUnroll; ++u) v[u] = ld_stream_v4(vin + base + u * kAggThreads + threadIdx.x);
+      if (kHasValid) {
+        // head == 0 with a bitmap; base is a multiple of 16 vectors
+        const uint32_t* __restrict__ wp = valid + ((base + threadIdx.x) >> 4);
+#pragma unroll
+        for (int u = 0; u < kAggUnroll; ++u) two[u] = __ldg(wp + u * (kAggThreads / 16));
+#pragma unroll
+        for (int u = 0; u < kAggUnroll; ++u) two[u] = (two[u] >> ((threadIdx.x & 15) * 2)) & 3u;
+      } else {
+#pragma unroll
+        for (int u = 0; u < kAggUnroll; ++u) two[u] = 3u;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kAggUnroll; ++u) {
+        const int64_t i = base + u * kAggThreads + threadIdx.x;
+        two[u] = 0;
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (i < nvec) {
+          v[u] = ld_stream_v4(vin + i);
+          const int64_t r = head + (i << 1);
+          two[u] = kHasValid ? (__ldg(valid + (r >> 5)) >> (r & 31)) & 3u : 3u;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kAggUnroll; ++u) {
+      agg_row64(acc, (uint64_t)v[u].x | ((uint64_t)v[u].y << 32), two[u] & 1u);
+      agg_row64(acc, (uint64_t)v[u].z | ((uint64_t)v[u].w << 32), two[u] & 2u);
+    }
+    cnt += acc.cnt;
+    acc.cnt = 0;
+  }
+  auto scalar_rows = [&](int64_t r0, int64_t r1, int64_t first, int64_t step) {
+    for (int64_t i = r0 + first; i < r1; i += step)
+      agg_row64(acc, in[i], valid ? (__ldg(valid + (i >> 5)) >> (i & 31)) & 1u : 1u);
+  };
+  if (nvec == 0) {
+    scalar_rows(0, n, (int64_t)blockIdx.x * kAggThreads + threadIdx.x, (int64_t)gridDim.x * kAggThreads);
+  } else if (blockIdx.x == 0) {
+    scalar_rows(0, head, threadIdx.x, kAggThreads);
+    scalar_rows(tail_start, n, threadIdx.x, kAggThreads);
+  }
+  cnt += acc.cnt;
+  __shared__ uint64_t s_sum[kAggThreads / 32], s_cnt[kAggThreads / 32], s_mn[kAggThreads / 32], s_mx[kAggThreads / 32];
+  const uint64_t wsum = warp_reduce_sum_u64(acc.sum), wcnt = warp_reduce_sum_u64(cnt);
+  const uint64_t wmn = warp_min64<kSigned>(acc.mn), wmx = warp_max64<kSigned>(acc.mx);
+  if (lane_id() == 0) {
+    s_sum[threadIdx.x >> 5] = wsum;
+    s_cnt[threadIdx.x >> 5] = wcnt;
+    s_mn[threadIdx.x >> 5] = wmn;
+    s_mx[threadIdx.x >> 5] = wmx;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const bool in_range = threadIdx.x < kAggThreads / 32;
+    const AggAcc64<kSigned> none;  // identity elements of min / max for lanes without a warp
+    const uint64_t a = warp_reduce_sum_u64(in_range ? s_sum[threadIdx.x] : 0);
+    const uint64_t c = warp_reduce_sum_u64(in_range ? s_cnt[threadIdx.x] : 0);
+    const uint64_t lo = warp_min64<kSigned>(in_range ? s_mn[threadIdx.x] : none.mn);
+    const uint64_t hi = warp_max64<kSigned>(in_range ? s_mx[threadIdx.x] : none.mx);
+    if (threadIdx.x == 0 && c > 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&out->sum), (unsigned long long)a);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&out->count), (unsigned long long)c);
+      if (kSigned) {
+        atomicMin(reinterpret_cast<long long*>(&out->min), (long long)lo);
+        atomicMax(reinterpret_cast<long long*>(&out->max), (long long)hi);
+      } else {
+        atomicMin(reinterpret_cast<unsigned long long*>(&out->min), (unsigned long long)lo);
+        atomicMax(reinterpret_cast<unsigned long long*>(&out->max), (unsigned long long)hi);
+      }
+    }
+  }
+}
+
+__global__ void aggr64_init_kernel(b2_aggr_u64* out, bool is_signed) {
+  out->sum = 0;
+  out->count = 0;
+  out->min = is_signed ? 0x7fffffffffffffffull : 0xffffffffffffffffull;
+  out->max = is_signed ? 0x8000000000000000ull : 0ull;
+}
+
 // ---- take ------------------------------------------------------------------------------------
 constexpr int kTakeThreads = 256;
 constexpr int kTakeWords = 8;  // 32-output words per warp and iteration (independent gathers in flight)
@@ -270,6 +409,40 @@ int b2_aggr_32_dev(b2_ctx* ctx, const void* d_in_, int dtype, const uint8_t* d_v
   else if (is_signed) aggr_u32_kernel<false, true><<<grid, kAggThreads, 0, s>>>(d_in, nullptr, n, head, d_out);
   else aggr_u32_kernel<false, false><<<grid, kAggThreads, 0, s>>>(d_in, nullptr, n, head, d_out);
   B2_LAUNCH_CHECK(ctx, "aggr_u32_kernel");
+  return B2_OK;
+}
+
+int b2_aggr_64_dev(b2_ctx* ctx, const void* d_in_, int dtype, const uint8_t* d_valid, int64_t n,
+                   b2_aggr_u64* d_out, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  B2_REQUIRE(ctx, dtype == B2_U64 || dtype == B2_I64, "dtype must be B2_U64 or B2_I64");
+  const bool is_signed = dtype == B2_I64;
+  const uint64_t* d_in = static_cast<const uint64_t*>(d_in_);
+  B2_REQUIRE(ctx, n >= 0, "n must be >= 0");
+  B2_REQUIRE(ctx, d_out != nullptr, "d_out is null");
+  B2_REQUIRE(ctx, n == 0 || d_in != nullptr, "d_in is null");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_in) & 7) == 0, "d_in must be 8-byte aligned");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_valid) & 3) == 0, "validity bitmap must be 4-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  aggr64_init_kernel<<<1, 1, 0, s>>>(d_out, is_signed);
+  B2_LAUNCH_CHECK(ctx, "aggr64_init_kernel");
+  if (n == 0) return B2_OK;
+  // scalar head: one row when the values start 8 bytes off a 16-byte boundary; with a bitmap the
+  // vector body must start on an even row, so a misaligned start takes the row-by-row path
+  int64_t head = (reinterpret_cast<uintptr_t>(d_in) & 15) ? 1 : 0;
+  if (d_valid && head != 0) head = n;
+  if (head > n) head = n;
+  const int64_t chunk_rows = (int64_t)kAggThreads * kAggUnroll * 2;
+  int64_t want = (n - head + chunk_rows - 1) / chunk_rows;
+  if (head == n) want = (n + kAggThreads - 1) / kAggThreads;
+  int grid = ctx->sm_count * 2;
+  if (want < grid) grid = want > 0 ? (int)want : 1;
+  const uint32_t* vb = reinterpret_cast<const uint32_t*>(d_valid);
+  if (d_valid && is_signed) aggr_u64_kernel<true, true><<<grid, kAggThreads, 0, s>>>(d_in, vb, n, head, d_out);
+  else if (d_valid) aggr_u64_kernel<true, false><<<grid, kAggThreads, 0, s>>>(d_in, vb, n, head, d_out);
+  else if (is_signed) aggr_u64_kernel<false, true><<<grid, kAggThreads, 0, s>>>(d_in, nullptr, n, head, d_out);
+  else aggr_u64_kernel<false, false><<<grid, kAggThreads, 0, s>>>(d_in, nullptr, n, head, d_out);
+  B2_LAUNCH_CHECK(ctx, "aggr_u64_kernel");
   return B2_OK;
 }
 

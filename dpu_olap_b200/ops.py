@@ -87,6 +87,7 @@ def _column(batch: Any, name_or_index) -> np.ndarray:
 
 # 32-bit column types the filter compares natively (b2_dtype32, include/b200olap.h)
 _DTYPES32 = {np.dtype(np.uint32): 0, np.dtype(np.int32): 1, np.dtype(np.float32): 2}
+_DTYPES64 = {np.dtype(np.uint64): 3, np.dtype(np.int64): 4}  # b2_dtype64 (aggregates only)
 
 
 def _threshold_bits(threshold, dtype: np.dtype) -> int:
@@ -102,14 +103,18 @@ class _NullableCol:
     __slots__ = ("values", "valid", "offset", "dtype", "_keep")
 
     def __init__(self, values: np.ndarray, valid=None, offset: int = 0, keep=None):
-        self.dtype = values.dtype                       # the column's own 32-bit type
-        self.values = values.view(np.uint32)            # what crosses the ABI: raw 32-bit words
+        self.dtype = values.dtype                       # the column's own type
+        # what crosses the ABI: raw 32-bit words (64-bit columns, aggregates only: raw 64-bit words)
+        self.values = values.view(np.uint64 if values.dtype.itemsize == 8 else np.uint32)
         self.valid, self.offset, self._keep = valid, int(offset), keep
 
 
-def _as_nullable(col: Any, typed: bool = False) -> _NullableCol:
-    """typed=True also admits int32 / float32 columns (filter only)."""
+def _as_nullable(col: Any, typed: bool = False, wide: bool = False) -> _NullableCol:
+    """typed=True also admits int32 / float32 columns (filter, aggregates); wide=True also uint64 /
+    int64 columns (aggregates only)."""
     ok = tuple(_DTYPES32) if typed else (np.dtype(np.uint32),)
+    if wide:
+        ok = ok + tuple(_DTYPES64)
     if pa is not None and isinstance(col, (pa.Array, pa.ChunkedArray)):
         if isinstance(col, pa.ChunkedArray):
             col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
@@ -139,14 +144,14 @@ def _as_nullable(col: Any, typed: bool = False) -> _NullableCol:
     return _NullableCol(np.ascontiguousarray(a))
 
 
-def _nullable_column(batch: Any, name_or_index, typed: bool = False) -> _NullableCol:
+def _nullable_column(batch: Any, name_or_index, typed: bool = False, wide: bool = False) -> _NullableCol:
     if pa is not None and isinstance(batch, pa.RecordBatch):
         i = batch.schema.get_field_index(name_or_index) if isinstance(name_or_index, str) else name_or_index
-        return _as_nullable(batch.column(i), typed)
+        return _as_nullable(batch.column(i), typed, wide)
     if isinstance(batch, dict):
         return _as_nullable(batch[name_or_index] if isinstance(name_or_index, str)
-                            else list(batch.values())[name_or_index], typed)
-    return _as_nullable(batch, typed)
+                            else list(batch.values())[name_or_index], typed, wide)
+    return _as_nullable(batch, typed, wide)
 
 
 class _ValidTable:
@@ -339,8 +344,15 @@ class Context:
 
     def aggr_dev(self, col, valid=None, out=None, dtype=np.uint32):
         """sum / count / min / max of the valid rows in one pass; returns a 3 x int64 device tensor
-        laid out as b2_aggr_u32 (decode with :func:`decode_aggr`). dtype: uint32 or int32."""
+        laid out as b2_aggr_u32 (decode with :func:`decode_aggr`). dtype: uint32 or int32; uint64 /
+        int64 (col = int64 tensor): 4 x int64 laid out as b2_aggr_u64."""
         import torch
+        if np.dtype(dtype) in _DTYPES64:
+            if out is None:
+                out = torch.empty(4, dtype=torch.int64, device=col.device)
+            self._ck(self._lib.b2_aggr_64_dev(self._h, _dptr(col), _DTYPES64[np.dtype(dtype)], _dptr(valid),
+                                              col.numel(), _dptr(out), self._stream()), "b2_aggr_64_dev")
+            return out
         if out is None:
             out = torch.empty(3, dtype=torch.int64, device=col.device)
         self._ck(self._lib.b2_aggr_32_dev(self._h, _dptr(col), _DTYPES32[np.dtype(dtype)], _dptr(valid),
@@ -571,9 +583,23 @@ class AggrResult(C.Structure):
                 "min": None if empty else lo, "max": None if empty else hi}
 
 
+class AggrResult64(C.Structure):
+    """b2_aggr_u64 (include/b200olap.h)."""
+    _fields_ = [("sum", C.c_uint64), ("count", C.c_uint64), ("min", C.c_uint64), ("max", C.c_uint64)]
+
+    def as_dict(self, dtype=np.uint64) -> dict:
+        empty = self.count == 0
+        sgn = np.dtype(dtype) == np.dtype(np.int64)
+        dec = lambda v: int(v) - (1 << 64) if sgn and v >> 63 else int(v)
+        return {"sum": None if empty else dec(self.sum), "count": int(self.count),
+                "min": None if empty else dec(self.min), "max": None if empty else dec(self.max)}
+
+
 def decode_aggr(t, dtype=np.uint32) -> dict:
     """Decode the device tensor returned by :meth:`Context.aggr_dev`."""
     raw = t.cpu().numpy().tobytes()
+    if np.dtype(dtype) in _DTYPES64:
+        return AggrResult64.from_buffer_copy(raw[:C.sizeof(AggrResult64)]).as_dict(dtype)
     return AggrResult.from_buffer_copy(raw[:C.sizeof(AggrResult)]).as_dict(dtype)
 
 
@@ -669,16 +695,17 @@ class FilterGpu:
 
 
 class SumGpu:
-    """SumDpu (host/aggr/aggr_dpu.cc:31-89): sum of a uint32 column as uint64."""
+    """SumDpu (host/aggr/aggr_dpu.cc:31-89): sum of a uint32 column as uint64. Also int32 (sum as
+    int64) and uint64 / int64 columns (sum in the column's type, wrapping as Arrow's does)."""
 
     def __init__(self, ctx: Context, batches: Sequence[Any]):
         self.ctx = ctx
-        self._ncols = [_nullable_column(b, 0, typed=True) for b in batches]
+        self._ncols = [_nullable_column(b, 0, typed=True, wide=True) for b in batches]
         self._cols = [c.values for c in self._ncols]
         self._valid = _ValidTable(self._ncols)
         kinds = {c.dtype for c in self._ncols} or {np.dtype(np.uint32)}
         if len(kinds) > 1 or next(iter(kinds)) == np.dtype(np.float32):
-            raise TypeError(f"aggregates take uint32 or int32 columns, got {sorted(str(k) for k in kinds)}")
+            raise TypeError(f"aggregates take uint32 / int32 / uint64 / int64 columns, got {sorted(str(k) for k in kinds)}")
         self.dtype = kinds.pop()
         self._timers = None
 
@@ -688,11 +715,17 @@ class SumGpu:
     def Aggregates(self) -> dict:
         """sum / count / min / max over the valid rows (Arrow semantics: None when no row is valid)."""
         tab = _PtrTable(self._cols)
-        out = AggrResult()
         t = Timings()
-        self.ctx._ck(self.ctx._lib.b2_aggr_32_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
-                                                   tab.lens, tab.n, _DTYPES32[self.dtype], C.byref(out),
-                                                   C.byref(t)), "b2_aggr_32_host")
+        if self.dtype in _DTYPES64:
+            out = AggrResult64()
+            self.ctx._ck(self.ctx._lib.b2_aggr_64_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
+                                                       tab.lens, tab.n, _DTYPES64[self.dtype], C.byref(out),
+                                                       C.byref(t)), "b2_aggr_64_host")
+        else:
+            out = AggrResult()
+            self.ctx._ck(self.ctx._lib.b2_aggr_32_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
+                                                       tab.lens, tab.n, _DTYPES32[self.dtype], C.byref(out),
+                                                       C.byref(t)), "b2_aggr_32_host")
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         return out.as_dict(self.dtype)

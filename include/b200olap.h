@@ -52,6 +52,8 @@ enum b2_status {
 /* 32-bit column types of the typed entry points (the reference fixes `#define T uint32_t`,
  * dpu/shared/common.h:3; uint32 is what every other entry point means). */
 enum b2_dtype32 { B2_U32 = 0, B2_I32 = 1, B2_F32 = 2 };
+/* 64-bit column types (b2_aggr_64_*); the values continue b2_dtype32's. */
+enum b2_dtype64 { B2_U64 = 3, B2_I64 = 4 };
 
 typedef struct b2_ctx b2_ctx;
 
@@ -148,6 +150,23 @@ int b2_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const uint8
 int b2_aggr_32_host(b2_ctx* ctx, const void* const* batch_ptrs, const uint8_t* const* valid_ptrs,
                     const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches, int dtype,
                     b2_aggr_u32* out, b2_timings* timings);
+/* The aggregates over a 64-bit column (dtype B2_U64 / B2_I64; SURVEY.md section 8f-3 "other
+ * fixed-width types" — the reference fixes T = uint32_t, dpu/shared/common.h:3). Arrow semantics
+ * (aggr_native.cc:68-73 with a uint64 / int64 column): the sum has the column's type and wraps
+ * mod 2^64, min / max are in the type's order, null rows are skipped; count == 0: min / max hold the
+ * type's largest / smallest value. int64 results travel as bit patterns. d_in must be 8-byte
+ * aligned. Argument meaning as b2_aggr_32_dev / b2_aggr_32_host. */
+typedef struct b2_aggr_u64 {
+  uint64_t sum;
+  uint64_t count;
+  uint64_t min;
+  uint64_t max;
+} b2_aggr_u64;
+int b2_aggr_64_dev(b2_ctx* ctx, const void* d_in, int dtype, const uint8_t* d_valid, int64_t n,
+                   b2_aggr_u64* d_out, void* stream);
+int b2_aggr_64_host(b2_ctx* ctx, const void* const* batch_ptrs, const uint8_t* const* valid_ptrs,
+                    const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches, int dtype,
+                    b2_aggr_u64* out, b2_timings* timings);
 /* SumDpu::Run (host/aggr/aggr_dpu.cc:31-89): batches on the host, result on the host. */
 int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
                     int64_t nbatches, uint64_t* sum, b2_timings* timings);

@@ -216,6 +216,16 @@ def aggr_nullable(values, valid) -> dict:
     """cp::Sum / Count / MinMax with default options: nulls are skipped; with no valid row every
     aggregate but the count is null (None)."""
     v = np.ascontiguousarray(values)
+    if v.dtype in (np.uint64, np.int64):
+        # 64-bit columns: Arrow's sum has the column's type and wraps (unchecked), min / max in the
+        # type's order
+        v = v[np.asarray(valid, dtype=bool)]
+        if v.size == 0:
+            return {"sum": None, "count": 0, "min": None, "max": None}
+        total = int(v.view(np.uint64).sum(dtype=np.uint64))  # mod 2^64
+        if v.dtype == np.int64 and total >> 63:
+            total -= 1 << 64
+        return {"sum": total, "count": int(v.size), "min": int(v.min()), "max": int(v.max())}
     if v.dtype != np.int32:   # int32 columns sum into int64 and compare signed; everything else is uint32
         v = _u32(v)
     v = v[np.asarray(valid, dtype=bool)]

@@ -97,3 +97,18 @@ def test_int32_aggregates_match_arrow(n, null_frac):
     mm = pc.min_max(arr)
     assert got == {"sum": pc.sum(arr).as_py(), "count": pc.count(arr).as_py(),   # Arrow sums int32 into int64
                    "min": mm["min"].as_py(), "max": mm["max"].as_py()}
+
+
+@pytest.mark.parametrize("dtype", [np.uint64, np.int64])
+@pytest.mark.parametrize("n,null_frac", [(0, 0.0), (1, 0.0), (7, 1.0), (1000, 0.3), (50_000, 0.0)])
+def test_64bit_aggregates_match_arrow(dtype, n, null_frac):
+    """uint64 / int64 columns: Arrow's sum keeps the column's type and wraps mod 2^64."""
+    rng = np.random.default_rng(500 + n)
+    info = np.iinfo(dtype)
+    v = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)  # full range: the sum wraps
+    valid = rng.random(n) >= null_frac
+    arr = pa.array(v, type=pa.from_numpy_dtype(dtype), mask=~valid)
+    got = oracle.aggr_nullable(v, valid)
+    mm = pc.min_max(arr)
+    assert got == {"sum": pc.sum(arr).as_py(), "count": pc.count(arr).as_py(),
+                   "min": mm["min"].as_py(), "max": mm["max"].as_py()}
