@@ -20,7 +20,13 @@
 //                           shared-memory counters returns the rank), scan the 2^bits tile
 //                           counts, stage the tile SORTED BY BUCKET in shared memory, then stream
 //                           it out so that consecutive threads write consecutive addresses of a
-//                           bucket's run.
+//                           bucket's run. The next tile's rows are requested as soon as the
+//                           current tile is staged, so the loads fly during the stream-out.
+//      part_scatter_sectors_kernel  the same pass from a fan-out of 2^9: rows that do not complete
+//                           a 32-byte sector are held back per bucket and only whole, aligned
+//                           sectors are stored (B200's L2 fills a partially written sector from
+//                           DRAM on a write miss: profiles/r1_scatter_fanout.md).
+//      part_scatter_lines_kernel    the multi-GPU shuffle: whole 128-byte lines to peer memory.
 // A pass can be "segmented": each input segment (= a partition of the previous pass) is
 // partitioned independently, which is how the join refines 2^10 coarse partitions into up to
 // 2^20 shared-memory-sized ones while every pass keeps >= 64 B write runs.
