@@ -77,6 +77,8 @@ SIGNATURES = {
                                      _vp, _sz, _vp]),
     "b2_filter_lt_u32_host_into": (_int, [_vp, _pp, _pi64, _i64, _u32, _vp, _i64, _pi64, _pu64, _pt]),
     "b2_take_u32_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "b2_take_64_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "b2_take_64_host": (_int, [_vp, _pp, _pi64, _pp, _pi64, _i64, _pp, _pt]),
     "b2_take_u32_ragged_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "b2_take_u32_host": (_int, [_vp, _pp, _pi64, _pp, _pi64, _i64, _pp, _pt]),
     "b2_wang_hash_u32": (_u32, [_u32]),

@@ -713,6 +713,64 @@ int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64
 
 }  // extern "C"
 
+// 64-bit values: unchunked (upload, one launch per run of equal-shaped batches, download).
+extern "C" int b2_take_64_host(b2_ctx* ctx, const void* const* value_ptrs_, const int64_t* value_lens,
+                               const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
+                               void* const* out_ptrs_, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  // the copy helpers move 32-bit words: a batch of n 64-bit values is a batch of 2n words
+  const uint32_t* const* value_ptrs = reinterpret_cast<const uint32_t* const*>(value_ptrs_);
+  uint32_t* const* out_ptrs = reinterpret_cast<uint32_t* const*>(out_ptrs_);
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout V, I;  // in rows
+  B2_RETURN_NOT_OK(make_layout(ctx, value_ptrs, value_lens, nbatches, &V));
+  B2_RETURN_NOT_OK(make_layout(ctx, idx_ptrs, idx_lens, nbatches, &I));
+  B2_REQUIRE(ctx, nbatches == 0 || out_ptrs != nullptr, "out_ptrs is null");
+  std::vector<int64_t> vw((size_t)nbatches), ow((size_t)nbatches);
+  for (int64_t b = 0; b < nbatches; ++b) {
+    B2_REQUIRE(ctx, idx_lens[b] == 0 || out_ptrs[b] != nullptr, "null output pointer");
+    B2_REQUIRE(ctx, idx_lens[b] == 0 || value_lens[b] > 0, "indices into an empty values batch");
+    B2_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(value_ptrs[b]) | reinterpret_cast<uintptr_t>(out_ptrs[b])) & 7) == 0,
+               "64-bit batches must be 8-byte aligned");
+    vw[(size_t)b] = value_lens[b] * 2;
+    ow[(size_t)b] = idx_lens[b] * 2;
+  }
+  Layout VW, OW;  // in 32-bit words
+  B2_RETURN_NOT_OK(make_layout(ctx, value_ptrs, vw.data(), nbatches, &VW));
+  B2_RETURN_NOT_OK(make_layout(ctx, reinterpret_cast<const uint32_t* const*>(out_ptrs), ow.data(), nbatches, &OW));
+  b2_timings tm{};
+  if (nbatches > 0 && I.rows() > 0) {
+    Scratch sc;
+    uint32_t *d_v = nullptr, *d_i = nullptr, *d_o = nullptr;
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_v, (size_t)VW.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_i, (size_t)I.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_o, (size_t)OW.rows() * 4));
+    cudaStream_t s = ctx->s_compute;
+    gather_begin(ctx, 2 * nbatches, VW.rows() + I.rows());
+    B2_RETURN_NOT_OK(upload(ctx, d_v, VW, value_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+    B2_RETURN_NOT_OK(upload(ctx, d_i, I, idx_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+    // one launch per run of consecutive batches with the same (values, indices) lengths
+    for (int64_t b = 0; b < nbatches;) {
+      int64_t e = b + 1;
+      while (e < nbatches && value_lens[e] == value_lens[b] && idx_lens[e] == idx_lens[b]) ++e;
+      if (idx_lens[b] > 0) {
+        B2_RETURN_NOT_OK(b2_take_64_dev(ctx, d_v + VW.off[(size_t)b], value_lens[b], d_i + I.off[(size_t)b],
+                                        idx_lens[b], e - b, d_o + OW.off[(size_t)b], s));
+      }
+      b = e;
+    }
+    B2_RETURN_NOT_OK(download(ctx, d_o, OW, out_ptrs, 0, nbatches, s, &tm.d2h_bytes));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
 // ---- nullable columns ---------------------------------------------------------
 // Straightforward (unchunked) host entry points: the per-batch Arrow validity bitmaps are packed
 // into ONE bitmap over the packed device column on the host, uploaded with the values, and the

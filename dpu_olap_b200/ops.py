@@ -401,6 +401,15 @@ class Context:
                                            nbatches, _dptr(out), self._stream()), "b2_take_u32_dev")
         return out
 
+    def take64_dev(self, values, values_len: int, indices, idx_len: int, nbatches: int, out=None):
+        """Batch-local gather over 64-bit values (int64 tensor of raw words), 32-bit indices."""
+        import torch
+        if out is None:
+            out = torch.empty(nbatches * idx_len, dtype=torch.int64, device=values.device)
+        self._ck(self._lib.b2_take_64_dev(self._h, _dptr(values), values_len, _dptr(indices), idx_len,
+                                          nbatches, _dptr(out), self._stream()), "b2_take_64_dev")
+        return out
+
     def take_ragged_dev(self, values, values_off: np.ndarray, indices, idx_off: np.ndarray):
         import torch
         dev = values.device
@@ -754,11 +763,17 @@ class TakeGpu:
         if len(batches) != len(indices_batches):
             raise ValueError("values and indices must have the same number of batches")
         self.ctx = ctx
-        self._nvals = [_nullable_column(b, 0) for b in batches]
+        self._nvals = [_nullable_column(b, 0, wide=True) for b in batches]  # uint32, or 64-bit values
         self._nidx = [_nullable_column(b, 0) for b in indices_batches]
         self._vals = [c.values for c in self._nvals]
         self._idx = [c.values for c in self._nidx]
         self._vvalid, self._ivalid = _ValidTable(self._nvals), _ValidTable(self._nidx)
+        kinds = {c.dtype for c in self._nvals}
+        if len(kinds) > 1:
+            raise TypeError(f"value batches of different types: {sorted(str(k) for k in kinds)}")
+        self.dtype = kinds.pop() if kinds else np.dtype(np.uint32)
+        if self.dtype in _DTYPES64 and (self._vvalid.any or self._ivalid.any):
+            raise TypeError("take over 64-bit values handles non-null columns only")
         self._timers = None
 
     def Prepare(self) -> None:
@@ -781,20 +796,26 @@ class TakeGpu:
         return [_to_arrow(o, b) for o, b in zip(outs, bits)]
 
     def Run(self):
-        """One uint32 array per batch (the reference returns a Table of one chunk per batch)."""
+        """One uint32 array per batch (the reference returns a Table of one chunk per batch); 64-bit
+        value batches give arrays of their own type."""
         if self._vvalid.any or self._ivalid.any:
             return self._run_nullable()
         v, i = _PtrTable(self._vals), _PtrTable(self._idx)
         total = sum(a.size for a in self._idx)
-        flat = np.empty(total, dtype=np.uint32)
+        wide = self.dtype in _DTYPES64
+        flat = np.empty(total, dtype=self.dtype if wide else np.uint32)
         ptrs = (C.c_void_p * max(i.n, 1))()
         bounds = [0]
         for b, a in enumerate(self._idx):
-            ptrs[b] = flat.ctypes.data + 4 * bounds[-1]
+            ptrs[b] = flat.ctypes.data + flat.itemsize * bounds[-1]
             bounds.append(bounds[-1] + a.size)
         t = Timings()
-        self.ctx._ck(self.ctx._lib.b2_take_u32_host(self.ctx._h, v.ptrs, v.lens, i.ptrs, i.lens, i.n,
-                                                    ptrs, C.byref(t)), "b2_take_u32_host")
+        if wide:
+            self.ctx._ck(self.ctx._lib.b2_take_64_host(self.ctx._h, v.ptrs, v.lens, i.ptrs, i.lens, i.n,
+                                                       ptrs, C.byref(t)), "b2_take_64_host")
+        else:
+            self.ctx._ck(self.ctx._lib.b2_take_u32_host(self.ctx._h, v.ptrs, v.lens, i.ptrs, i.lens, i.n,
+                                                        ptrs, C.byref(t)), "b2_take_u32_host")
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         return [flat[bounds[b]:bounds[b + 1]] for b in range(i.n)]

@@ -280,6 +280,15 @@ int b2_take_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* value_ptrs,
                               const uint8_t* const* idx_valid_ptrs, const int64_t* idx_valid_bit_offsets,
                               const int64_t* idx_lens, int64_t nbatches, uint32_t* const* out_ptrs,
                               uint8_t* const* out_valid_ptrs, b2_timings* timings);
+/* The same gather over 64-bit values (uint64 / int64 / float64 as raw 8-byte words; SURVEY.md
+ * section 8f-3, the reference fixes T = uint32_t, dpu/shared/common.h:3) with 32-bit indices:
+ *   d_out[b*idx_len + j] = d_values[b*values_len + d_indices[b*idx_len + j]]   (8-byte elements).
+ * d_values and d_out must be 8-byte aligned. b2_take_64_host: batches of any lengths, non-null. */
+int b2_take_64_dev(b2_ctx* ctx, const void* d_values, int64_t values_len, const uint32_t* d_indices,
+                   int64_t idx_len, int64_t nbatches, void* d_out, void* stream);
+int b2_take_64_host(b2_ctx* ctx, const void* const* value_ptrs, const int64_t* value_lens,
+                    const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
+                    void* const* out_ptrs, b2_timings* timings);
 /* TakeDpu::Run (host/take/take_dpu.cc:34-104): out_ptrs[b] has capacity idx_lens[b]. */
 int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64_t* value_lens,
                      const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
