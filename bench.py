@@ -18,7 +18,8 @@ One JSON line on stdout (rank 0). Besides the driver's keys it carries
   cpu_baseline  Arrow Acero (the reference's CPU engine) on this box's host cores, bounded sample
   ops           the other operators of the path (sum, take, join), the selectivity sweep, the
                 nullable variants and the fused join->aggregate pipelines, each timed over the same
-                K steps and checked against torch on the device
+                K steps and checked against torch on the device; `--ops ...,wide` adds the
+                64-bit aggregates and take (opt-in, not in the default run)
 """
 from __future__ import annotations
 
@@ -309,6 +310,57 @@ def bench_take(ctx, D, args):
             # window is touched (profiles/r1_sum_take.md), so the window itself is the traffic
             "window_gbs": (4 * nb_total * TAKE_BATCH + 8 * nidx) / D.world / (ms * 1e-3) / 1e9,
             "reference_convention_rows_per_s": nb_total * TAKE_BATCH / (ms * 1e-3)}
+
+
+def bench_wide(ctx, D, args):
+    """Opt-in (`--ops ...,wide`; not part of the default run): the 64-bit operators of SURVEY.md
+    section 8f-3 on resident columns — one-pass aggregates over a uint64 column and take over 64-bit
+    values with 32-bit indices. Bounded at SF=256; results checked against torch on the device."""
+    import numpy as np
+    import torch
+    from dpu_olap_b200.generator import RandomArrayGenerator
+    from dpu_olap_b200.ops import decode_aggr
+    sf = min(args.sf, 256)
+    nb_total = sf << 7
+    first, nb = shard(nb_total, D)
+    g = RandomArrayGenerator(ctx, 42)
+    words = g.batches_dev(nb_total, FILTER_BATCH, take=(first, nb))  # two 32-bit draws per 64-bit value
+    col = words.view(torch.int64)
+    n = col.numel()
+    rows = nb_total * FILTER_BATCH // 2
+    res = {"sf": sf}
+    aout = torch.empty(4, dtype=torch.int64, device="cuda")
+    ms = timed_steps(D, lambda: ctx.aggr_dev(col, None, out=aout, dtype=np.uint64), args.steps, args.warmup)
+    agg = decode_aggr(aout, np.uint64)
+    flip = torch.tensor(-2**63, dtype=torch.int64, device="cuda")
+    ref_sum = int(col.sum()) % (1 << 64)  # torch's int64 sum wraps like Arrow's unchecked sum
+    ref_min = (int((col ^ flip).min()) + 2**63) % (1 << 64)
+    ref_max = (int((col ^ flip).max()) + 2**63) % (1 << 64)
+    if (agg["sum"], agg["count"], agg["min"], agg["max"]) != (ref_sum, n, ref_min, ref_max):
+        raise SystemExit(f"64-bit aggregate self-check failed on rank {D.rank}")
+    res["aggregates_u64"] = {"ms_per_step": ms, "rows": rows, "rows_per_s": rows / (ms * 1e-3),
+                             "algorithmic_bytes_per_row": 8,
+                             "achieved_gbs": 8 * rows / D.world / (ms * 1e-3) / 1e9, "result_rank0": agg}
+    del words, col
+    free_all()
+    if sf >= D.world:
+        firstb, nbt = shard(sf, D)
+        vl = TAKE_BATCH // 2                                            # 2 Mi 64-bit values = 16 MiB per batch
+        vals = g.batches_dev(sf, TAKE_BATCH, take=(firstb, nbt)).view(torch.int64)
+        idx = g.batches_dev(sf, TAKE_IDX, 0, vl - 1, take=(firstb, nbt))
+        out = torch.empty(nbt * TAKE_IDX, dtype=torch.int64, device="cuda")
+        ms = timed_steps(D, lambda: ctx.take64_dev(vals, vl, idx, TAKE_IDX, nbt, out=out), args.steps, args.warmup)
+        b = nbt // 2
+        ref = vals[b * vl:(b + 1) * vl][idx[b * TAKE_IDX:(b + 1) * TAKE_IDX].to(torch.int64)]
+        if not torch.equal(ref, out[b * TAKE_IDX:(b + 1) * TAKE_IDX]):
+            raise SystemExit(f"64-bit take self-check failed on rank {D.rank}")
+        nidx = sf * TAKE_IDX
+        res["take_u64"] = {"ms_per_step": ms, "indices": nidx, "rows_per_s": nidx / (ms * 1e-3),
+                           "algorithmic_bytes_per_index": 20,
+                           "achieved_gbs": 20 * nidx / D.world / (ms * 1e-3) / 1e9}
+        del vals, idx, out
+        free_all()
+    return res
 
 
 def bench_nullable(ctx, D, args):
@@ -830,6 +882,8 @@ def main():
         extra["nullable"] = bench_nullable(ctx, D, args)
     if "joinsum" in ops:
         extra["join_aggregate"] = bench_join_aggr(ctx, D, args)
+    if "wide" in ops:  # opt-in: the 64-bit aggregates and take
+        extra["wide"] = bench_wide(ctx, D, args)
     e2e = None
     if not args.no_e2e:
         e2e = bench_e2e_filter(ctx, D, args)
