@@ -213,6 +213,112 @@ def free_all():
         time.sleep(settle)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# full-size content checks (torch on the device; independent of the library's kernels)
+# ------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _s64(v: int) -> int:
+    """A 64-bit pattern as the signed Python int torch's int64 arithmetic wants."""
+    v &= _M64
+    return v - (1 << 64) if v >> 63 else v
+
+
+def _lsr(z, k: int):
+    return (z >> k) & ((1 << (64 - k)) - 1)  # logical shift right on int64
+
+
+def _mix64(z):
+    """oracle/olap_oracle.c:mix64 on int64 tensors (products wrap mod 2^64 like the C code's)."""
+    z = z ^ _lsr(z, 33)
+    z = z * _s64(0xff51afd7ed558ccd)
+    z = z ^ _lsr(z, 33)
+    z = z * _s64(0xc4ceb9fe1a85ec53)
+    return z ^ _lsr(z, 33)
+
+
+def triple_checksum_torch(a, b, c, chunk: int = 1 << 26) -> int:
+    """Order-independent 64-bit checksum of the (a, b, c) row multiset: the torch restatement of
+    orc_triple_checksum (oracle/olap_oracle.c:199-211; tests/test_bench_checks.py pins the two to
+    each other). a, b, c: int32 / uint32-as-int32 tensors of equal length, any device."""
+    import torch
+    total = 0
+    n = a.numel()
+    for s0 in range(0, n, chunk):
+        s1 = min(n, s0 + chunk)
+        aa = a[s0:s1].to(torch.int64) & 0xFFFFFFFF
+        bb = b[s0:s1].to(torch.int64) & 0xFFFFFFFF
+        cc = c[s0:s1].to(torch.int64) & 0xFFFFFFFF
+        z = _mix64(((aa << 32) | bb) ^ _mix64(cc + _s64(0x9e3779b97f4a7c15)))
+        total = (total + int(z.sum())) & _M64
+    return total
+
+
+def check_filter_content(col, nb: int, out, end, thr: int, what: str) -> int:
+    """Every selected row and every batch boundary of a filter result, streamed in 2^28-row chunks:
+    torch's boolean selection of chunk k must equal out[pos .. pos + k) and the running per-batch
+    counts must equal batch_end. Returns the number of selected rows."""
+    import torch
+    flip = torch.tensor(-2**31, dtype=torch.int32, device=col.device)
+    tflip = int(thr) - 2**31  # unsigned compare via sign flip
+    pos = 0
+    cb = max(1, (1 << 28) // FILTER_BATCH)
+    for b0 in range(0, nb, cb):
+        b1 = min(nb, b0 + cb)
+        c = col[b0 * FILTER_BATCH:b1 * FILTER_BATCH]
+        m = (c ^ flip) < tflip
+        exp = c[m]
+        k = exp.numel()
+        if not torch.equal(exp, out[pos:pos + k]):
+            raise SystemExit(f"{what}: selected rows of batches [{b0}, {b1}) differ from torch's selection")
+        cum = m.view(b1 - b0, FILTER_BATCH).sum(1).cumsum(0) + pos
+        if not torch.equal(cum, end[b0:b1]):
+            raise SystemExit(f"{what}: batch_end of batches [{b0}, {b1}) differs from torch's counts")
+        pos += k
+        del c, m, exp, cum
+    return pos
+
+
+def ncu_traffic(op: str):
+    """DRAM bytes per row of an operator's kernels from the ncu capture committed for this round
+    (profiles/r2_traffic.json, written by tools/ncu_traffic.py from the ncu CSVs named in it).
+    None when there is no capture — never a constant made up here."""
+    f = ROOT / "profiles" / "r2_traffic.json"
+    try:
+        return json.loads(f.read_text()).get(op)
+    except Exception:
+        return None
+
+
+def filter_traffic(fres: dict, world: int) -> dict:
+    tr = ncu_traffic("filter")
+    if not tr or tr.get("dram_bytes_per_algorithmic_byte") is None:
+        return {"traffic": None, "traffic_source": "no ncu capture committed for this round"}
+    return {"traffic": tr["dram_bytes_per_algorithmic_byte"] * fres["algorithmic_bytes"] / world,
+            "traffic_per_algorithmic_byte": tr["dram_bytes_per_algorithmic_byte"],
+            "traffic_source": tr.get("source", "profiles/r2_traffic.json")}
+
+
+def roofline_block(op: str, algorithmic_bytes: float, ms: float, peak: float, peak_src: str, rows: float,
+                   world: int, note: str, kernel: str) -> dict:
+    """Per-GPU roofline of one operator step: algorithmic bytes / CUDA-event time against the
+    measured copy bandwidth AND the nominal 8 TB/s SURVEY.md section 8(d) names."""
+    achieved = algorithmic_bytes / world / (ms * 1e-3) / 1e9
+    tr = ncu_traffic(op)
+    blk = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src, "kernel": kernel,
+           "algorithmic_bytes_per_launch": algorithmic_bytes / world,
+           "algorithmic_bytes_per_row": algorithmic_bytes / rows, "note": note,
+           "traffic": None, "traffic_source": "no ncu capture committed for this operator"}
+    if tr and tr.get("dram_bytes_per_row") is not None:
+        blk["traffic"] = tr["dram_bytes_per_row"] * rows / world
+        blk["traffic_bytes_per_row"] = tr["dram_bytes_per_row"]
+        blk["traffic_source"] = tr.get("source", "profiles/r2_traffic.json")
+    return blk
+
+
 # ------------------------------------------------------------------------------------------------
 # operators
 # ------------------------------------------------------------------------------------------------
@@ -237,21 +343,15 @@ def bench_filter(ctx, D, args, thresholds):
         ms = timed_steps(D, step, args.steps, args.warmup)
         launches = (ctx.launches - l0) // (args.steps + args.warmup)
         sel_local = int(total.cpu()[0])
-        # independent device-side count of the predicate (unsigned compare via sign flip)
-        cnt = 0
-        flip = torch.tensor(-2**31, dtype=torch.int32, device="cuda")
-        tflip = int(thr) - 2**31
-        for c in col.split(1 << 28):
-            cnt += int(((c ^ flip) < tflip).sum())
-        ends = end.cpu().numpy()
-        ok = (cnt == sel_local) and bool((ends[1:] >= ends[:-1]).all()) and int(ends[-1]) == sel_local
-        if not ok:
+        # full-size CONTENT check: every output row and every batch boundary against torch
+        cnt = check_filter_content(col, nb, out, end, thr, f"filter self-check (rank {D.rank}, thr {thr})")
+        if cnt != sel_local:
             raise SystemExit(f"filter self-check failed on rank {D.rank}: {cnt} vs {sel_local}")
         sel = D.sum_int(sel_local)
         rows = nb_total * FILTER_BATCH
         res[thr] = {"ms_per_step": ms, "rows": rows, "selected": sel, "rows_per_s": rows / (ms * 1e-3),
                     "algorithmic_bytes": 4 * rows + 4 * sel, "launches_per_step": launches,
-                    "rows_per_rank": n}
+                    "rows_per_rank": n, "self_check": "content"}
     del col, out, end, total, ws
     free_all()
     return res
@@ -277,7 +377,7 @@ def bench_sum(ctx, D, args):
     rows = nb_total * SUM_BATCH
     del col
     free_all()
-    return {"ms_per_step": ms, "rows": rows, "rows_per_s": rows / (ms * 1e-3),
+    return {"ms_per_step": ms, "rows": rows, "rows_per_s": rows / (ms * 1e-3), "self_check": "content",
             "achieved_gbs": 4 * rows / D.world / (ms * 1e-3) / 1e9, "algorithmic_bytes_per_row": 4,
             "sum_rank0": got}
 
@@ -295,15 +395,19 @@ def bench_take(ctx, D, args):
     out = torch.empty(nb * TAKE_IDX, dtype=torch.int32, device="cuda")
     ms = timed_steps(D, lambda: ctx.take_dev(vals, TAKE_BATCH, idx, TAKE_IDX, nb, out=out),
                      args.steps, args.warmup)
-    # spot check one batch with torch's gather
-    b = nb // 2
-    ref = vals[b * TAKE_BATCH:(b + 1) * TAKE_BATCH][idx[b * TAKE_IDX:(b + 1) * TAKE_IDX].to(torch.int64)]
-    if not torch.equal(ref, out[b * TAKE_IDX:(b + 1) * TAKE_IDX]):
-        raise SystemExit(f"take self-check failed on rank {D.rank}")
+    # full-size content check: every batch against torch's gather (64 batches per torch call)
+    for b0 in range(0, nb, 64):
+        b1 = min(nb, b0 + 64)
+        gi = idx[b0 * TAKE_IDX:b1 * TAKE_IDX].to(torch.int64).view(b1 - b0, TAKE_IDX)
+        gi = gi + torch.arange(b1 - b0, device="cuda", dtype=torch.int64)[:, None] * TAKE_BATCH
+        ref = vals[b0 * TAKE_BATCH:b1 * TAKE_BATCH][gi.view(-1)]
+        if not torch.equal(ref, out[b0 * TAKE_IDX:b1 * TAKE_IDX]):
+            raise SystemExit(f"take self-check failed on rank {D.rank}, batches [{b0}, {b1})")
+        del gi, ref
     nidx = nb_total * TAKE_IDX
     del vals, idx, out
     free_all()
-    return {"ms_per_step": ms, "indices": nidx, "value_rows": nb_total * TAKE_BATCH,
+    return {"ms_per_step": ms, "indices": nidx, "value_rows": nb_total * TAKE_BATCH, "self_check": "content",
             "rows_per_s": nidx / (ms * 1e-3), "algorithmic_bytes_per_index": 12,
             "achieved_gbs": 12 * nidx / D.world / (ms * 1e-3) / 1e9,
             # what HBM really moves: at 1 index per 8 values nearly every 64 B unit of the batch
@@ -485,14 +589,23 @@ def bench_join(ctx, D, args):
         mult = (nb_total * JOIN_BATCH) >> 32
         info["matches_per_probe_row"] = mult
     if D.world == 1:
-        outs = [torch.empty(n * mult, dtype=torch.int32, device="cuda") for _ in range(3)]
+        # the three output columns are ONE allocation: dead until the probe writes them, the library
+        # uses them as the temporary of the first radix pass (b200olap.h, "adjacent output columns"),
+        # which is what lets SF=2048 run in one hash-space slice on one GPU
+        out_all = torch.empty(3 * n * mult, dtype=torch.int32, device="cuda")
+        outs = [out_all[i * n * mult:(i + 1) * n * mult] for i in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
         free, _ = torch.cuda.mem_get_info()
         full = ctx.join_ws_bytes(n, n)
-        ws_bytes = min(full, max(free - (3 << 30), ctx.join_min_ws_bytes(n, n)))
+        one_go = ctx.join_ws_bytes_adjacent_outputs(n, n)
+        margin = 1 << 30
+        ws_bytes = min(full, max(free - margin, ctx.join_min_ws_bytes(n, n)))
+        if one_go <= ws_bytes < full:
+            ws_bytes = one_go
         ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
         info["workspace_gib"] = round(ws_bytes / 2**30, 2)
-        info["sliced"] = ws_bytes < full
+        info["sliced"] = ws_bytes < one_go
+        info["pass1_temporary"] = "workspace" if ws_bytes >= full else ("output columns" if ws_bytes >= one_go else "workspace (sliced)")
 
         def step():
             ctx.join_dev(fk, y, pk, x, out_capacity=n * mult, ws=ws, outs=outs, out_rows=rows_t)
@@ -501,7 +614,7 @@ def bench_join(ctx, D, args):
         info["launches_per_step"] = (ctx.launches - l0) // (args.steps + args.warmup)
         out_rows = int(rows_t.cpu().numpy().view("uint64")[0])
         o_fk, o_y, o_x = outs
-        del ws
+        del ws, out_all
     else:
         G = D.world
         cap = n + n // 8 + 65536  # received rows: hash-uniform, 12.5 % slack
@@ -607,19 +720,38 @@ def bench_join(ctx, D, args):
         exp = [D.sum_int(colsum(fk, n) * mult % M), D.sum_int(colsum(y, n) * mult % M)]
         if [g % M for g in got] != [e % M for e in exp]:
             raise SystemExit(f"join self-check failed on the multi-match sums: {got} vs {exp}")
-    del fk, y, pk  # the check needs x and the output only; free the rest (SF=2048 fills the HBM)
+    del pk
     free_all()
-    lo_pk = first * JOIN_BATCH
-    bad = 0
-    for s in range(0, out_rows if mult == 1 else 0, 1 << 26):  # payload identity needs unique keys
-        kf = o_fk[s:min(s + (1 << 26), out_rows)].to(torch.int64) & 0xFFFFFFFF
-        xo = o_x[s:min(s + (1 << 26), out_rows)]
-        m = (kf >= lo_pk) & (kf < lo_pk + n)
-        bad += int((x[(kf[m] - lo_pk)] != xo[m]).sum())
-    if bad:
-        raise SystemExit(f"join self-check failed on rank {D.rank}: {bad} rows with a wrong payload")
+    check = "row count + column sums (wrapped keys: the matches of a probe row live on other ranks)"
+    if mult == 1:
+        # full-size CONTENT check, every rank's rows: the order-independent 64-bit checksum of the
+        # output's (fk, y, x) multiset (torch restatement of orc_triple_checksum) against the same
+        # checksum of (fk, y, R.x[fk]) computed from the INPUTS. fk of L batch b lies in pk batch b
+        # (generator.cc:46-57) and pk is the global row number, so the R row a probe row matches is
+        # the one this rank generated itself: x[fk - first pk of the rank]. Summed over all ranks
+        # (mod 2^64) the two must agree — this covers y, x and every rank's share of the output.
+        lo_pk = first * JOIN_BATCH
+        exp = 0
+        for s0 in range(0, n, 1 << 26):
+            s1 = min(n, s0 + (1 << 26))
+            kf = (fk[s0:s1].to(torch.int64) & 0xFFFFFFFF) - lo_pk
+            if int(kf.min()) < 0 or int(kf.max()) >= n:
+                raise SystemExit("join self-check: a foreign key points outside this rank's pk range")
+            exp = (exp + triple_checksum_torch(fk[s0:s1], y[s0:s1], x[kf])) & _M64
+            del kf
+        got = triple_checksum_torch(o_fk[:out_rows], o_y[:out_rows], o_x[:out_rows])
+        # all-reduce as 4 x 16-bit limbs so the int64 sum over <= 8 ranks cannot overflow
+        def allsum64(v):
+            limbs = [D.sum_int((v >> (16 * i)) & 0xFFFF) for i in range(4)]
+            return sum(l << (16 * i) for i, l in enumerate(limbs)) & _M64
+        got_all, exp_all = allsum64(got), allsum64(exp)
+        if got_all != exp_all:
+            raise SystemExit(f"join self-check failed: multiset checksum {got_all:#x} vs expected {exp_all:#x}")
+        check = "content"
+    del fk, y
+    free_all()
     rows = nb_total * JOIN_BATCH
-    res = {"ms_per_step": ms, "rows_per_side": rows, "out_rows": total_rows,
+    res = {"ms_per_step": ms, "rows_per_side": rows, "out_rows": total_rows, "self_check": check,
            "rows_per_s": rows / (ms * 1e-3),  # probe (L) rows per second
            "items_per_s_reference_convention": 4 * rows / (ms * 1e-3),  # join_benchmark.cc:114-125
            # 8 B per build row + 8 B per probe row + 12 B per output row (mult output rows per probe row)
@@ -740,6 +872,9 @@ def bench_e2e_filter(ctx, D, args):
     rows = nb_total * FILTER_BATCH
     res = {"value": rows / (ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": acc["h2d"] * D.world,
            "d2h_bytes_per_step": acc["d2h"] * D.world, "ms_per_step": ms, "sf": e2e_sf, "rows": rows,
+           "steps": steps, "scaling": "weak", "sf_per_gpu": args.e2e_sf,
+           "workload": f"filter SF={args.e2e_sf} per GPU x {D.world} GPU(s) through host buffers (the 64 GiB SF=2048 "
+                       "column does not fit a PCIe-bound leg's time budget); wall clock, max over ranks",
            "api": "b2_filter_lt_u32_host_into (pinned host batches in, pinned host result out; "
                   "upload / kernels / download of 64 MiB groups overlap)",
            "phases_ms": {"copy-to-dpu": t1.copy_to_dev_ms, "dpu-work": t1.dev_work_ms,
@@ -799,6 +934,208 @@ def cpu_filter_sample(args, cpu_sf: int, seconds: float, steps: int | None = Non
                       f"{len(times)} timed runs of Prepare()+Run(), Arrow Acero {pa.__version__} via pyarrow "
                       f"(reference pins Arrow 8.0.0), {cores} threads",
             "ms_per_step": ms, "rows": rows, "selected": sel}
+
+
+
+def _time_cpu(make_op, seconds: float, warmup: int = 1):
+    """Prepare()+Run() per iteration, as the reference's BM_* loops time it; bounded by `seconds`."""
+    times, res = [], None
+    t_start = time.perf_counter()
+    it = 0
+    while True:
+        op = make_op()
+        t0 = time.perf_counter()
+        op.Prepare()
+        res = op.Run()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        it += 1
+        if time.perf_counter() - t_start > seconds and len(times) >= 2:
+            break
+    return 1e3 * sum(times) / len(times), len(times), res
+
+
+def _host_batches(t, batch: int):
+    """A device column as the list of per-batch numpy views the *Native classes take."""
+    import numpy as np
+    a = t.cpu().numpy().view(np.uint32)
+    return [a[i:i + batch] for i in range(0, a.size, batch)]
+
+
+def cpu_ops_samples(ctx, args, seconds: float) -> dict:
+    """the reference's other Native operators timed beside the GPU on this
+    box's host cores — AggrNative (aggr_native.cc:39-93), TakeNative (take_native.cc:18-38),
+    JoinNative (join_native.cc:14-102) — on a bounded sample (SF = --cpu-sf) of the same generator(42)
+    workload, generated on the device (bit-identical) and copied to the host. Results are checked
+    against the oracle / the GPU operator. Arrow Acero 24 via pyarrow, all host threads."""
+    import numpy as np
+    import pyarrow as pa
+
+    import oracle
+    from oracle import arrow_native as an
+    from dpu_olap_b200.generator import RandomArrayGenerator
+    sf = args.cpu_sf
+    cores = os.cpu_count() or 1
+    pa.set_cpu_count(cores)
+    how = f"Arrow Acero {pa.__version__} via pyarrow (reference pins Arrow 8.0.0), {cores} threads, Prepare()+Run()"
+    out = {}
+    # ---- sum ----
+    g = RandomArrayGenerator(ctx, 42)
+    col = _host_batches(g.batches_dev(sf, SUM_BATCH), SUM_BATCH)
+    ms, k, got = _time_cpu(lambda: an.AggrNative(col), seconds / 3)
+    if got != sum(int(b.sum(dtype=np.uint64)) for b in col) % (1 << 64):
+        raise SystemExit("CPU sum self-check failed")
+    rows = sf * SUM_BATCH
+    out["sum"] = {"value": rows / (ms * 1e-3), "unit": "rows/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+                  "sample": f"AggrNative sum at SF={sf} ({sf} batches x {SUM_BATCH} rows), {k} timed runs, {how}"}
+    del col
+    # ---- take ----
+    g = RandomArrayGenerator(ctx, 42)
+    vals = _host_batches(g.batches_dev(sf, TAKE_BATCH), TAKE_BATCH)
+    idx = _host_batches(g.batches_dev(sf, TAKE_IDX, 0, TAKE_BATCH - 1), TAKE_IDX)
+    ms, k, got = _time_cpu(lambda: an.TakeNative(vals, idx), seconds / 3)
+    if not np.array_equal(got[sf // 2], oracle.take(vals[sf // 2], idx[sf // 2])):
+        raise SystemExit("CPU take self-check failed")
+    nidx = sf * TAKE_IDX
+    out["take"] = {"value": nidx / (ms * 1e-3), "unit": "indices/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+                   "sample": f"TakeNative at SF={sf} ({sf} batches: {TAKE_BATCH} values, {TAKE_IDX} indices), "
+                             f"{k} timed runs, {how}"}
+    del vals, idx
+    # ---- join ----
+    g = RandomArrayGenerator(ctx, 42)
+    xd = g.batches_dev(sf, JOIN_BATCH)
+    pkd = g.index_column_dev(sf, JOIN_BATCH)
+    yd = g.batches_dev(sf, JOIN_BATCH)
+    fkd = g.foreign_key_dev(JOIN_BATCH, sf, JOIN_BATCH)
+    exp = triple_checksum_torch(fkd, yd, xd[fkd.to(__import__("torch").int64) & 0xFFFFFFFF])
+    x, pk, y, fk = (_host_batches(t, JOIN_BATCH) for t in (xd, pkd, yd, fkd))
+    del xd, pkd, yd, fkd
+    ms, k, tab = _time_cpu(lambda: an.JoinNative({"fk": fk, "y": y}, {"pk": pk, "x": x}), seconds, warmup=0)
+    import torch
+    cols = [torch.from_numpy(tab.column(c).combine_chunks().to_numpy().view(np.int32)) for c in ("fk", "y", "x")]
+    if tab.num_rows != sf * JOIN_BATCH or triple_checksum_torch(*cols) != exp:
+        raise SystemExit("CPU join self-check failed")
+    rows = sf * JOIN_BATCH
+    out["join"] = {"value": rows / (ms * 1e-3), "unit": "rows/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+                   "sample": f"JoinNative (Acero hashjoin inner fk = pk) at SF={sf}: {rows} rows per side, "
+                             f"{k} timed runs, {how}"}
+    return out
+
+
+def _pinned(t):
+    import torch
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t)
+    return h
+
+
+def bench_e2e_ops(ctx, D, args) -> dict:
+    """e2e for sum / take / join: the same operators through the reference-facing host entry points
+    (b2_sum_u32_host, b2_take_u32_host, b2_join_u32_host + b2_join_fetch_host — what SumGpu / TakeGpu /
+    JoinGpu call) with PINNED HOST batches in and host results out, copies inside the timed region.
+    One GPU, SF = --e2e-sf (bounded by PCIe time), wall clock over `steps` calls."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    from dpu_olap_b200._lib import Timings
+    from dpu_olap_b200.generator import RandomArrayGenerator
+    sf = args.e2e_sf
+    lib, h = ctx._lib, ctx._h
+    steps = max(2, min(args.steps, 5))
+    res = {}
+
+    def table(*cols_and_batch):
+        ptrs, lens = [], []
+        for t, batch in cols_and_batch:
+            for i in range(0, t.numel(), batch):
+                ptrs.append(t.data_ptr() + 4 * i)
+                lens.append(batch)
+        return (C.c_void_p * len(ptrs))(*ptrs), (C.c_int64 * len(lens))(*lens)
+
+    def timed(fn):
+        for _ in range(max(1, min(args.warmup, 2))):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / steps
+
+    def leg(t: Timings, extra=None):
+        d = {"h2d_bytes_per_step": int(t.h2d_bytes), "d2h_bytes_per_step": int(t.d2h_bytes),
+             "phases_ms": {"copy-to-dpu": t.copy_to_dev_ms, "dpu-work": t.dev_work_ms,
+                           "copy-from-dpu": t.copy_from_dev_ms},
+             "gpu_launches_per_step": int(t.kernel_launches), "sf": sf, "steps": steps, "n_gpus": 1}
+        if extra:
+            for k in ("h2d_bytes_per_step", "d2h_bytes_per_step", "gpu_launches_per_step"):
+                d[k] += {"h2d_bytes_per_step": int(extra.h2d_bytes), "d2h_bytes_per_step": int(extra.d2h_bytes),
+                         "gpu_launches_per_step": int(extra.kernel_launches)}[k]
+            for k, v in (("copy-to-dpu", extra.copy_to_dev_ms), ("dpu-work", extra.dev_work_ms),
+                         ("copy-from-dpu", extra.copy_from_dev_ms)):
+                d["phases_ms"][k] += v
+        return d
+
+    # ---- sum ----
+    g = RandomArrayGenerator(ctx, 42)
+    col = _pinned(g.batches_dev(sf, SUM_BATCH))
+    ptrs, lens = table((col, SUM_BATCH))
+    out, t1 = C.c_uint64(0), Timings()
+    ms = timed(lambda: ctx._ck(lib.b2_sum_u32_host(h, ptrs, lens, sf, C.byref(out), C.byref(t1)), "b2_sum_u32_host"))
+    if int(out.value) != int(col.numpy().view(np.uint32).sum(dtype=np.uint64)):
+        raise SystemExit("e2e sum self-check failed")
+    rows = sf * SUM_BATCH
+    res["sum"] = {"value": rows / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "api": "b2_sum_u32_host", **leg(t1)}
+    del col
+    # ---- take ----
+    g = RandomArrayGenerator(ctx, 42)
+    vals = _pinned(g.batches_dev(sf, TAKE_BATCH))
+    idx = _pinned(g.batches_dev(sf, TAKE_IDX, 0, TAKE_BATCH - 1))
+    hout = torch.empty(sf * TAKE_IDX, dtype=torch.int32, pin_memory=True)
+    vptrs, vlens = table((vals, TAKE_BATCH))
+    iptrs, ilens = table((idx, TAKE_IDX))
+    optrs, _ = table((hout, TAKE_IDX))
+    ms = timed(lambda: ctx._ck(lib.b2_take_u32_host(h, vptrs, vlens, iptrs, ilens, sf, optrs, C.byref(t1)),
+                               "b2_take_u32_host"))
+    b = sf // 2
+    ref = vals[b * TAKE_BATCH:(b + 1) * TAKE_BATCH][idx[b * TAKE_IDX:(b + 1) * TAKE_IDX].to(torch.int64)]
+    if not torch.equal(ref, hout[b * TAKE_IDX:(b + 1) * TAKE_IDX]):
+        raise SystemExit("e2e take self-check failed")
+    nidx = sf * TAKE_IDX
+    res["take"] = {"value": nidx / (ms * 1e-3), "unit": "indices/s", "ms_per_step": ms, "api": "b2_take_u32_host",
+                   **leg(t1)}
+    del vals, idx, hout
+    # ---- join ----
+    g = RandomArrayGenerator(ctx, 42)
+    xd = g.batches_dev(sf, JOIN_BATCH)
+    pkd = g.index_column_dev(sf, JOIN_BATCH)
+    yd = g.batches_dev(sf, JOIN_BATCH)
+    fkd = g.foreign_key_dev(JOIN_BATCH, sf, JOIN_BATCH)
+    exp = triple_checksum_torch(fkd, yd, xd[fkd.to(torch.int64) & 0xFFFFFFFF])
+    x, pk, y, fk = (_pinned(t) for t in (xd, pkd, yd, fkd))
+    del xd, pkd, yd, fkd
+    n = sf * JOIN_BATCH
+    lptrs, llens = table((fk, JOIN_BATCH), (y, JOIN_BATCH))
+    rptrs, rlens = table((pk, JOIN_BATCH), (x, JOIN_BATCH))
+    o = [torch.empty(n, dtype=torch.int32, pin_memory=True) for _ in range(3)]
+    nrows, t2 = C.c_uint64(0), Timings()
+
+    def jstep():
+        ctx._ck(lib.b2_join_u32_host(h, lptrs, llens, sf, rptrs, rlens, sf, C.byref(nrows), C.byref(t1)),
+                "b2_join_u32_host")
+        ctx._ck(lib.b2_join_fetch_host(h, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n, C.byref(t2)),
+                "b2_join_fetch_host")
+    ms = timed(jstep)
+    if int(nrows.value) != n or triple_checksum_torch(*[t.cuda() for t in o]) != exp:
+        raise SystemExit("e2e join self-check failed")
+    res["join"] = {"value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms,
+                   "api": "b2_join_u32_host + b2_join_fetch_host (JoinGpu::Run)", **leg(t1, t2)}
+    del x, pk, y, fk, o
+    free_all()
+    return res
 
 
 def run_reference(args):
@@ -887,6 +1224,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e = bench_e2e_filter(ctx, D, args)
+        if D.world == 1:
+            # the other operators through their host entry points (one GPU; the sharded host join is
+            # b2_set_join_u32_host, timed by `--ops ...,setjoin`)
+            for op, leg in bench_e2e_ops(ctx, D, args).items():
+                if extra.get(op):
+                    extra[op]["e2e"] = leg
     cpu = None
     if D.rank == 0 and D.world == 1 and not args.no_cpu:
         cpu = cpu_filter_sample(args, args.cpu_sf, args.cpu_seconds)
@@ -894,6 +1237,32 @@ def main():
         half = max(1, (os.cpu_count() or 2) // 2)
         h = cpu_filter_sample(args, args.cpu_sf, args.cpu_seconds / 3, threads=half)
         cpu["half_cores"] = {"value": h["value"], "unit": h["unit"], "cores": half, "ms_per_step": h["ms_per_step"]}
+        for op, base in cpu_ops_samples(ctx, args, args.cpu_seconds).items():
+            if extra.get(op):
+                extra[op]["cpu_baseline"] = base
+    # per-operator rooflines (against the measured copy bandwidth and the nominal 8 TB/s)
+    if extra.get("sum"):
+        r = extra["sum"]
+        r["roofline"] = roofline_block("sum", 4.0 * r["rows"], r["ms_per_step"], peak, peak_src, r["rows"], D.world,
+                                       "4 B read per row", "sum_u32_kernel")
+    if extra.get("take"):
+        r = extra["take"]
+        r["roofline"] = roofline_block("take", 12.0 * r["indices"], r["ms_per_step"], peak, peak_src, r["indices"],
+                                       D.world, "12 B per index (index + value + output); the DRAM traffic is the "
+                                       "16 MiB batch window, see window_gbs", "take_u32_vec_kernel")
+    if extra.get("join"):
+        r = extra["join"]
+        r["roofline"] = roofline_block(
+            "join", float(r["algorithmic_bytes_per_row"]) * r["rows_per_side"], r["ms_per_step"], peak, peak_src,
+            r["rows_per_side"], D.world,
+            "single-pass ideal 8 B per build row + 8 B per probe row + 12 B per output row; the two-pass radix "
+            "design is modelled at 116 B per row pair (DESIGN.md section 3); time = whole join step "
+            "(all radix passes + probe" + (", + NVLink shuffle" if D.world > 1 else "") + ")",
+            "part_scatter_*_kernel x4 + part_hist_kernel x4 + join_probe_kernel")
+        n1 = ncu_traffic("join_n1_ms")
+        if n1 and D.world > 1 and n1.get(str(args.sf)):
+            r["speedup_vs_n1"] = n1[str(args.sf)] / r["ms_per_step"]
+            r["n1_ms_source"] = n1.get("source")
 
     if D.rank == 0:
         achieved = fres["algorithmic_bytes"] / D.world / (fres["ms_per_step"] * 1e-3) / 1e9
@@ -911,12 +1280,10 @@ def main():
                        "l2": "inputs (>= 8 GiB per GPU) far exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         # DRAM bytes per launch per GPU: ncu --set full at SF=128 measured
-                         # dram__bytes_read + dram__bytes_write = 0.993 x the algorithmic bytes
-                         # (profiles/r1_ncu_full_final_sf128.csv, r1_ncu_full_filter_named_barriers_sf128.csv);
-                         # scaled to this launch's rows
-                         "traffic": 0.993 * fres["algorithmic_bytes"] / D.world,
-                         "traffic_source": "ncu dram__bytes_{read,write}.sum at SF=128 (0.993 x algorithmic), scaled by rows",
+                         "frac_of_nominal_8000": achieved / 8000.0,
+                         # DRAM bytes per launch per GPU from the ncu capture committed for this round
+                         # (profiles/r2_traffic.json names the CSV), scaled to this launch's rows
+                         **filter_traffic(fres, D.world),
                          "algorithmic_bytes_per_launch": fres["algorithmic_bytes"] / D.world,
                          "peak_source": peak_src,
                          "kernel": "filter_lt_u32_kernel",

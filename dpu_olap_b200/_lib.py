@@ -10,10 +10,14 @@ import re
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libb200olap.so"
+import os
+# B200OLAP_LIB: the lab build (libb200olap_lab.so, -DB2_LAB) for tools/filter_lab.py; never set in tests or bench
+LIB_PATH = Path(os.environ["B200OLAP_LIB"]).resolve() if os.environ.get("B200OLAP_LIB") else PKG_DIR / "libb200olap.so"
 HEADER = PKG_DIR.parent / "include" / "b200olap.h"
 
 B2_OK = 0
+# enum b2_tunable
+TUNE_SCATTER_SECTORS_MIN_BITS, TUNE_SCATTER_PREFETCH, TUNE_SCATTER_SHAPE, TUNE_FILTER_VARIANT = range(4)
 STATUS_NAMES = {0: "B2_OK", 1: "B2_ERR_INVALID", 2: "B2_ERR_CUDA", 3: "B2_ERR_OOM",
                 4: "B2_ERR_UNSUPPORTED", 5: "B2_ERR_WORKSPACE", 6: "B2_ERR_OVERFLOW"}
 
@@ -52,6 +56,8 @@ SIGNATURES = {
     "b2_launch_count": (_i64, [_vp]),
     "b2_ctx_device": (_int, [_vp]),
     "b2_ctx_sm_count": (_int, [_vp]),
+    "b2_ctx_set_tunable": (_int, [_vp, _int, _int]),
+    "b2_ctx_get_tunable": (_int, [_vp, _int, C.POINTER(C.c_int)]),
     "b2_gen_u32_dev": (_int, [_vp, _pu64, _pu32, _pu32, _i64, _i64, _vp, _vp]),
     "b2_iota_u32_dev": (_int, [_vp, _u64, _i64, _vp, _vp]),
     "b2_sum_u32_dev": (_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -88,6 +94,7 @@ SIGNATURES = {
     "b2_partition_fetch_host": (_int, [_vp, _pp, _int, _int, _pt]),
     "b2_join_ws_bytes": (_sz, [_i64, _i64]),
     "b2_join_min_ws_bytes": (_sz, [_i64, _i64]),
+    "b2_join_ws_bytes_adjacent_outputs": (_sz, [_i64, _i64]),
     "b2_join_u32_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp,
                                _int, _vp, _sz, _vp]),
     "b2_join_pairs_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _int, _vp,

@@ -251,6 +251,7 @@ extern "C" {
 int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
                     int64_t nbatches, uint64_t* sum, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, sum != nullptr, "sum is null");
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
@@ -324,6 +325,7 @@ int b2_filter_lt_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
                           const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
                           int64_t* out_counts, uint64_t* total, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
   b2_pending_free(ctx);
@@ -425,6 +427,7 @@ int b2_filter_lt_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
 int b2_filter_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int64_t nbatches,
                          b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   b2_pending* pend = ctx->pending;
   if (!pend || pend->kind != b2_pending::kFilter)
@@ -464,6 +467,7 @@ int b2_filter_lt_u32_host_into(b2_ctx* ctx, const uint32_t* const* batch_ptrs,
                                uint32_t* out, int64_t out_capacity, int64_t* out_counts,
                                uint64_t* total, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
   b2_pending_free(ctx);
@@ -620,6 +624,7 @@ int b2_take_u32_host(b2_ctx* ctx, const uint32_t* const* value_ptrs, const int64
                      const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
                      uint32_t* const* out_ptrs, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
   b2_pending_free(ctx);
@@ -718,6 +723,7 @@ extern "C" int b2_take_64_host(b2_ctx* ctx, const void* const* value_ptrs_, cons
                                const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
                                void* const* out_ptrs_, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   // the copy helpers move 32-bit words: a batch of n 64-bit values is a batch of 2n words
   const uint32_t* const* value_ptrs = reinterpret_cast<const uint32_t* const*>(value_ptrs_);
   uint32_t* const* out_ptrs = reinterpret_cast<uint32_t* const*>(out_ptrs_);
@@ -839,6 +845,7 @@ int b2_aggr_32_host(b2_ctx* ctx, const void* const* batch_ptrs_, const uint8_t* 
                     const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches, int dtype,
                     b2_aggr_u32* out, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const uint32_t* const* batch_ptrs = reinterpret_cast<const uint32_t* const*>(batch_ptrs_);
   B2_REQUIRE(ctx, out != nullptr, "out is null");
   const auto t0 = Clock::now();
@@ -878,6 +885,7 @@ int b2_aggr_64_host(b2_ctx* ctx, const void* const* batch_ptrs_, const uint8_t* 
                     const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches, int dtype,
                     b2_aggr_u64* out, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   // the upload machinery moves 32-bit words: a batch of n 64-bit values is a batch of 2n words
   const uint32_t* const* batch_ptrs = reinterpret_cast<const uint32_t* const*>(batch_ptrs_);
   B2_REQUIRE(ctx, out != nullptr, "out is null");
@@ -927,6 +935,7 @@ static int filter_typed_host_into(b2_ctx* ctx, int dtype, const uint32_t* const*
                                   uint32_t* out, int64_t out_capacity, int64_t* out_counts,
                                   uint64_t* total, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, total != nullptr && out_capacity >= 0, "bad result arguments");
   B2_REQUIRE(ctx, nbatches == 0 || out_counts != nullptr, "out_counts is null");
   const auto t0 = Clock::now();
@@ -1008,6 +1017,7 @@ int b2_filter_lt_32_host_into(b2_ctx* ctx, const void* const* batch_ptrs, const 
                               int dtype, uint32_t threshold_bits, void* out, int64_t out_capacity,
                               int64_t* out_counts, uint64_t* total, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, dtype == B2_U32 || dtype == B2_I32 || dtype == B2_F32, "dtype must be B2_U32, B2_I32 or B2_F32");
   return filter_typed_host_into(ctx, dtype, reinterpret_cast<const uint32_t* const*>(batch_ptrs), valid_ptrs,
                                 valid_bit_offsets, batch_lens, nbatches, threshold_bits,
@@ -1021,6 +1031,7 @@ int b2_take_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* value_ptrs,
                               const int64_t* idx_lens, int64_t nbatches, uint32_t* const* out_ptrs,
                               uint8_t* const* out_valid_ptrs, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
   b2_pending_free(ctx);

@@ -94,6 +94,7 @@ int b2_partition_u32_host(b2_ctx* ctx, const uint32_t* const* col_batch_ptrs,
                           const int64_t* batch_lens, int64_t nbatches, int ncols, int key_col,
                           int nparts, int64_t* part_rows, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
   b2_pending_free(ctx);
@@ -165,6 +166,7 @@ int b2_partition_u32_host(b2_ctx* ctx, const uint32_t* const* col_batch_ptrs,
 int b2_partition_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int nparts, int ncols,
                             b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   b2_pending* pend = ctx->pending;
   if (!pend || pend->kind != b2_pending::kPartition)
@@ -200,6 +202,7 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
                      int64_t nl_batches, const uint32_t* const* r_ptrs, const int64_t* r_lens,
                      int64_t nr_batches, uint64_t* out_rows, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
   b2_pending_free(ctx);
@@ -286,6 +289,7 @@ int b2_join_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int6
                           int64_t nr_batches, int filter_y, uint32_t y_threshold, b2_join_aggr* out,
                           b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   const int64_t launches0 = ctx->launches;
   b2_pending_free(ctx);
@@ -338,6 +342,7 @@ int b2_join_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int6
 int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
                        int64_t capacity_rows, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   const auto t0 = Clock::now();
   b2_pending* pend = ctx->pending;
   if (!pend || pend->kind != b2_pending::kJoin)

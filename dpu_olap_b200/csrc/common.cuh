@@ -23,9 +23,14 @@ struct b2_ctx {
   int sm_count = 148;
   int64_t launches = 0;
   std::string last_error;
-  // small persistent device scratch: [0..4095] sum partials (u64) | ticket counters
+  // small persistent device scratch: a ring of per-launch slots (partials | ticket) of the sum kernels
   void* d_small = nullptr;
   size_t small_bytes = 0;
+  uint32_t sum_slot = 0;  // next slot of that ring
+  // kernel-selection knobs (b2_ctx_set_tunable, enum b2_tunable): every setting computes the same result
+  int tune[4] = {9, 1, 0, 6};
+  std::vector<char> site_done;  // per call site: function attributes configured for this ctx's device
+  std::vector<int> site_value;
   // growable device workspace used by the *_host layer
   void* d_ws = nullptr;
   size_t ws_bytes = 0;
@@ -87,15 +92,38 @@ int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail);
     (ctx)->launches++;                                                         \
   } while (0)
 
+// Makes ctx->device current for the duration of an entry point and restores the caller's device on
+// the way out: kernel launches, function attributes and occupancy queries all act on the CURRENT
+// device, and a process may hold contexts on several GPUs (b2_set) or share the thread with torch.
+struct b2_device_scope {
+  int prev = -1;
+  bool switched = false;
+  explicit b2_device_scope(const b2_ctx* ctx) {
+    if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device)
+      switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~b2_device_scope() {
+    if (switched) cudaSetDevice(prev);
+  }
+  b2_device_scope(const b2_device_scope&) = delete;
+  b2_device_scope& operator=(const b2_device_scope&) = delete;
+};
+
 static inline size_t b2_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Function attributes (opt-in dynamic shared memory) are per DEVICE: a process that holds contexts
-// on several GPUs must set them on each. `flags` is a call site's static table, one entry per device.
-constexpr int kB2MaxDevices = 64;
-static inline bool b2_first_use_on_device(const b2_ctx* ctx, bool (&flags)[kB2MaxDevices]) {
-  const int d = ctx->device >= 0 && ctx->device < kB2MaxDevices ? ctx->device : 0;
-  if (flags[d]) return false;
-  flags[d] = true;
+// Function attributes (opt-in dynamic shared memory) and occupancy are per DEVICE and must be set
+// before the first launch there. Every call site that needs them owns a "site" id; the ctx remembers
+// which sites it has configured (and one integer per site, e.g. the grid size derived from the
+// occupancy query). A ctx is bound to one device and driven by one thread, so this needs no locking
+// and is right for processes that hold contexts on several GPUs.
+int b2_new_site();  // ctx.cu: process-wide atomic counter
+static inline bool b2_first_use_on_device(b2_ctx* ctx, int site) {
+  if ((int)ctx->site_done.size() <= site) {
+    ctx->site_done.resize((size_t)site + 1, 0);
+    ctx->site_value.resize((size_t)site + 1, 0);
+  }
+  if (ctx->site_done[(size_t)site]) return false;
+  ctx->site_done[(size_t)site] = 1;
   return true;
 }
 

@@ -5,6 +5,12 @@
 
 void b2_pending_free(b2_ctx* ctx);  // api_host.cu
 
+#include <atomic>
+int b2_new_site() {
+  static std::atomic<int> next{0};
+  return next.fetch_add(1);
+}
+
 int b2_set_error(b2_ctx* ctx, int status, const char* what, const char* detail) {
   if (ctx) {
     ctx->last_error = std::string(b2_strerror(status)) + ": " + (what ? what : "") +
@@ -110,6 +116,12 @@ int b2_ctx_create(int device, b2_ctx** out) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return B2_ERR_CUDA;
   if (device < 0 || device >= n) return B2_ERR_INVALID;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  struct Restore {  // the caller's current device is left as it was (torch shares the thread)
+    int prev, device;
+    ~Restore() { if (prev >= 0 && prev != device) cudaSetDevice(prev); }
+  } restore{prev, device};
   if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2_ERR_CUDA;
@@ -121,7 +133,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   b2_ctx* ctx = new b2_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->small_bytes = 128 * 1024;  // sum partials [4096] | filtered-sum counts [4096] | ticket
+  ctx->small_bytes = 128 * 1024;  // ring of per-launch scratch slots of the sum kernels (sum.cu)
   if (cudaMalloc(&ctx->d_small, ctx->small_bytes) != cudaSuccess ||
       cudaMemset(ctx->d_small, 0, ctx->small_bytes) != cudaSuccess) {
     delete ctx;
@@ -133,7 +145,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
 
 int b2_ctx_destroy(b2_ctx* ctx) {
   if (!ctx) return B2_OK;
-  cudaSetDevice(ctx->device);
+  b2_device_scope dev_scope(ctx);
   b2_pending_free(ctx);
   if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
   if (ctx->s_copy_in) cudaStreamDestroy(ctx->s_copy_in);
@@ -152,6 +164,7 @@ int b2_ctx_destroy(b2_ctx* ctx) {
 
 int b2_ctx_set_inputs_pinned(b2_ctx* ctx, int on) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   ctx->inputs_pinned = on != 0;
   return B2_OK;
 }
@@ -186,6 +199,25 @@ int b2_host_unregister(const void* p) {
   const cudaError_t e = cudaHostUnregister(const_cast<void*>(p));
   cudaGetLastError();
   return (e == cudaSuccess || e == cudaErrorHostMemoryNotRegistered) ? B2_OK : B2_ERR_CUDA;
+}
+
+int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  switch (which) {
+    case B2_TUNE_SCATTER_SECTORS_MIN_BITS: B2_REQUIRE(ctx, value >= 0, "0 = always, > 10 = never"); break;
+    case B2_TUNE_SCATTER_PREFETCH: value = value != 0; break;
+    case B2_TUNE_SCATTER_SHAPE: B2_REQUIRE(ctx, (value >= 0 && value <= 3) || value == 8, "shape 0..3 or 8"); break;
+    case B2_TUNE_FILTER_VARIANT: B2_REQUIRE(ctx, value >= 0 && value <= 7, "variant 0..7"); break;
+    default: return b2_set_error(ctx, B2_ERR_INVALID, "b2_ctx_set_tunable", "unknown tunable");
+  }
+  ctx->tune[which] = value;
+  return B2_OK;
+}
+int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value) {
+  if (!ctx || !value || which < 0 || which > B2_TUNE_FILTER_VARIANT) return B2_ERR_INVALID;
+  *value = ctx->tune[which];
+  return B2_OK;
 }
 
 const char* b2_last_error(const b2_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }

@@ -74,7 +74,11 @@ struct FilterArgs {
   uint64_t* grp;    // [ntiles >> 5]   contributors << 48 | rows selected in the group of 32 tiles
   uint64_t* sgrp;   // [ntiles >> 10]  same for the super-group of 1024 tiles
   uint64_t* incl;   // [ntiles]        out: rows selected in tiles 0..t (+ carry), plain values
-  int debug;  // lab only: 1 = no prefix (wrong offsets), 2 = no TMA, 4 = dynamic tile tickets
+#ifdef B2_LAB
+  int debug;  // lab build only (tools/filter_lab.py): 1 = no prefix (WRONG offsets), 2 = no TMA, 4 = dynamic tile tickets
+#else
+  static constexpr int debug = 0;  // the product build has no such switches: the branches fold away
+#endif
 };
 
 // Compile-time shape of one kernel variant.
@@ -524,16 +528,18 @@ using Cfg7 = FilterCfg<256, 5, 2, 3, true>;
 constexpr int kNumVariants = 8;
 constexpr int kTileRows = Cfg0::kTile;
 
-int g_filter_variant = 6;  // <256 threads, 4 stages, 3 CTAs/SM, lag 2, named barriers>: best on B200 (profiles/r1_filter.md)
-int g_filter_debug = 0;  // tools/filter_lab.py switches this through b200olap_tune_filter_variant()
+// Kernel shape: ctx->tune[B2_TUNE_FILTER_VARIANT], default 6 = <256 threads, 4 stages, 3 CTAs/SM, lag 2,
+// named barriers>: best on B200 (profiles/r1_filter.md). Every shape computes the same result.
+#ifdef B2_LAB
+int g_filter_debug = 0;  // tools/filter_lab.py (lab build, -DB2_LAB) sets this through b200olap_lab_filter_debug()
+#endif
 
 static inline int64_t tiles_of(int64_t len) { return (len + kTileRows - 1) / kTileRows; }
 
 template <typename Cfg, bool kNullable = false, int kCmp = kCmpU32>
 int launch_variant(b2_ctx* ctx, const FilterArgs& a, cudaStream_t s) {
   constexpr int kSmem = kNullable ? Cfg::kSmemBytesNullable : Cfg::kSmemBytes;
-  static int max_ctas = 0;  // every B200 is the same, but the attribute must be set on each device
-  static bool seen[kB2MaxDevices] = {};
+  static const int seen = b2_new_site();  // attribute + grid size are remembered per ctx (= per device)
   if (b2_first_use_on_device(ctx, seen)) {
     B2_CUDA_OK(ctx, cudaFuncSetAttribute(filter_lt_u32_kernel<Cfg, kNullable, kCmp>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -542,8 +548,9 @@ int launch_variant(b2_ctx* ctx, const FilterArgs& a, cudaStream_t s) {
                         &per_sm, filter_lt_u32_kernel<Cfg, kNullable, kCmp>, Cfg::kThreads, kSmem));
     if (per_sm < 1) return b2_set_error(ctx, B2_ERR_CUDA, "filter kernel", "does not fit an SM");
     if (per_sm > Cfg::kCtasPerSm) per_sm = Cfg::kCtasPerSm;
-    max_ctas = per_sm * ctx->sm_count;
+    ctx->site_value[(size_t)seen] = per_sm * ctx->sm_count;
   }
+  const int max_ctas = ctx->site_value[(size_t)seen];
   const int64_t grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
   filter_lt_u32_kernel<Cfg, kNullable, kCmp><<<(unsigned)grid, Cfg::kThreads, kSmem, s>>>(a);
   B2_LAUNCH_CHECK(ctx, "filter_lt_u32_kernel");
@@ -631,7 +638,9 @@ int filter_launch(b2_ctx* ctx, int cmp, const uint32_t* d_in, const uint32_t* d_
     a.grp = reinterpret_cast<uint64_t*>(base + w.grp_off);
     a.sgrp = reinterpret_cast<uint64_t*>(base + w.sgrp_off);
     a.incl = incl;
+#ifdef B2_LAB
     a.debug = g_filter_debug;
+#endif
     if (cmp == kCmpS32) {  // typed and nullable kernels exist in one shape, the default one
       if (d_valid) B2_RETURN_NOT_OK((launch_variant<Cfg6, true, kCmpS32>(ctx, a, s)));
       else B2_RETURN_NOT_OK((launch_variant<Cfg6, false, kCmpS32>(ctx, a, s)));
@@ -640,7 +649,7 @@ int filter_launch(b2_ctx* ctx, int cmp, const uint32_t* d_in, const uint32_t* d_
       else B2_RETURN_NOT_OK((launch_variant<Cfg6, false, kCmpF32>(ctx, a, s)));
     } else if (d_valid) {
       B2_RETURN_NOT_OK((launch_variant<Cfg6, true>(ctx, a, s)));
-    } else switch (g_filter_variant) {
+    } else switch (ctx->tune[B2_TUNE_FILTER_VARIANT]) {
       case 1: B2_RETURN_NOT_OK(launch_variant<Cfg1>(ctx, a, s)); break;
       case 2: B2_RETURN_NOT_OK(launch_variant<Cfg2>(ctx, a, s)); break;
       case 3: B2_RETURN_NOT_OK(launch_variant<Cfg3>(ctx, a, s)); break;
@@ -664,13 +673,14 @@ int filter_launch(b2_ctx* ctx, int cmp, const uint32_t* d_in, const uint32_t* d_
 
 extern "C" {
 
-// Tuning hook (not part of include/b200olap.h): selects the kernel shape used by later calls.
-int b200olap_tune_filter_variant(int variant) {
-  if (variant < 0 || (variant & 0xff) >= kNumVariants) return B2_ERR_INVALID;
-  g_filter_variant = variant & 0xff;
-  g_filter_debug = variant >> 8;
+#ifdef B2_LAB
+// Lab build only (python -m dpu_olap_b200.build --lab): switches that make the kernel compute WRONG
+// offsets on purpose, to time its parts in isolation. Not compiled into the product library.
+int b200olap_lab_filter_debug(int bits) {
+  g_filter_debug = bits;
   return B2_OK;
 }
+#endif
 
 size_t b2_filter_ws_bytes(int64_t nbatches, int64_t batch_len) {
   if (nbatches < 0 || batch_len < 0) return 0;
@@ -687,6 +697,7 @@ int b2_filter_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, in
                          int64_t* d_total, const int64_t* d_carry_in, void* d_ws, size_t ws_bytes,
                          void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
   B2_REQUIRE(ctx, nbatches * batch_len == 0 || (d_in && d_out), "null column pointer");
@@ -700,6 +711,7 @@ int b2_filter_lt_32_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_t thres
                         int64_t* d_batch_end, int64_t* d_total, const int64_t* d_carry_in, void* d_ws,
                         size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, dtype == B2_U32 || dtype == B2_I32 || dtype == B2_F32, "dtype must be B2_U32, B2_I32 or B2_F32");
   B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
@@ -715,6 +727,7 @@ int b2_filter_lt_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8
                                   uint32_t* d_out, int64_t* d_batch_end, int64_t* d_total,
                                   const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
   B2_REQUIRE(ctx, nbatches == 0 || d_batch_end != nullptr, "d_batch_end is null");
   B2_REQUIRE(ctx, nbatches * batch_len == 0 || (d_in && d_out), "null column pointer");
@@ -730,6 +743,7 @@ int b2_filter_lt_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_in, const int64_t
                                 const int64_t* d_carry_in, void* d_ws, size_t ws_bytes,
                                 void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nbatches >= 0, "negative size");
   B2_REQUIRE(ctx, h_batch_off && d_batch_off, "batch offset tables are null");
   for (int64_t b = 0; b < nbatches; ++b)
@@ -745,6 +759,7 @@ int b2_filter_lt_32_ragged_dev(b2_ctx* ctx, const void* d_in, int dtype, uint32_
                                int64_t nbatches, void* d_out, int64_t* d_batch_end, int64_t* d_total,
                                const int64_t* d_carry_in, void* d_ws, size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, dtype == B2_U32 || dtype == B2_I32 || dtype == B2_F32, "dtype must be B2_U32, B2_I32 or B2_F32");
   B2_REQUIRE(ctx, nbatches >= 0, "negative size");
   B2_REQUIRE(ctx, h_batch_off && d_batch_off, "batch offset tables are null");

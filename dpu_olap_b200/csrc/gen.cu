@@ -90,6 +90,7 @@ extern "C" {
 int b2_gen_u32_dev(b2_ctx* ctx, const uint64_t* data_seeds, const uint32_t* lo, const uint32_t* hi,
                    int64_t nbatches, int64_t batch_len, uint32_t* d_out, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nbatches >= 0 && batch_len >= 0, "negative size");
   if (nbatches * batch_len == 0) return B2_OK;
   B2_REQUIRE(ctx, data_seeds && d_out, "null pointer");
@@ -131,6 +132,7 @@ int b2_gen_u32_dev(b2_ctx* ctx, const uint64_t* data_seeds, const uint32_t* lo, 
 
 int b2_iota_u32_dev(b2_ctx* ctx, uint64_t start, int64_t n, uint32_t* d_out, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0, "negative size");
   if (n == 0) return B2_OK;
   B2_REQUIRE(ctx, d_out != nullptr, "null pointer");

@@ -398,7 +398,9 @@ struct JoinPlan {
   size_t off_state, off_roff, off_loff, off_rout, off_lout, off_tmp, off_part, part_bytes, total;
 };
 
-JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits) {
+// ext_tmp: the temporary of the first radix pass lives outside the workspace (in the caller's
+// output columns, see join_impl).
+JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits, bool ext_tmp = false) {
   JoinPlan P;
   P.slice_bits = slice_bits;
   const int64_t nslices = (int64_t)1 << slice_bits;
@@ -418,6 +420,7 @@ JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits) {
   P.cap_r = cap(nr);
   P.cap_l = cap(nl);
   P.cap_tmp = P.two_pass ? std::max(P.cap_r, P.cap_l) : 0;
+  const size_t tmp_bytes = ext_tmp ? 0 : (size_t)P.cap_tmp * 8;
   const size_t noff = (((size_t)1 << P.bits) + 1) * 8;
   size_t o = 0;
   P.off_state = o; o += 256;
@@ -425,7 +428,7 @@ JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits) {
   P.off_loff = o;  o += b2_align_up(noff, 256);
   P.off_rout = o;  o += b2_align_up((size_t)P.cap_r * 8, 256);
   P.off_lout = o;  o += b2_align_up((size_t)P.cap_l * 8, 256);
-  P.off_tmp = o;   o += b2_align_up((size_t)P.cap_tmp * 8, 256);
+  P.off_tmp = o;   o += b2_align_up(tmp_bytes, 256);
   P.part_bytes = std::max(part_full_ws_bytes(nr, P.bits), part_full_ws_bytes(nl, P.bits));
   P.off_part = o;  o += b2_align_up(P.part_bytes, 256);
   P.total = o;
@@ -444,9 +447,27 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
              "workspace must be 256 B aligned");
   B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
+  // Output columns that are ONE allocation (fk | y | x back to back, 32 B aligned) are dead until the
+  // probe kernel writes them, so they serve as the temporary of the first radix pass — the
+  // reference aliases its outputs onto the partitioned left side in the same spirit
+  // (join_dpu.cc:315-322). At SF=2048 on one GPU this is what lets the join run in ONE hash-space
+  // slice: inputs (64 GiB) + outputs (48 GiB) + both partitioned sides (64 GiB) fit, a 32 GiB
+  // temporary on top would not.
+  const bool out_adjacent = !agg && out_capacity > 0 && d_out_y == d_out_fk + out_capacity &&
+                            d_out_x == d_out_y + out_capacity &&
+                            (reinterpret_cast<uintptr_t>(d_out_fk) & 31) == 0 &&
+                            12 * (uint64_t)out_capacity >= 8 * (uint64_t)std::max(nl, nr);
   // pick the smallest number of slices whose plan fits the workspace
   JoinPlan P = make_plan(nl, nr, skip_bits, 0);
   int sb = 0;
+  bool ext_tmp = false;
+  if (P.total > ws_bytes && out_adjacent && P.two_pass) {
+    const JoinPlan Q = make_plan(nl, nr, skip_bits, 0, true);
+    if (Q.total <= ws_bytes) {
+      P = Q;
+      ext_tmp = true;
+    }
+  }
   while (P.total > ws_bytes && sb < kMaxSliceBits) P = make_plan(nl, nr, skip_bits, ++sb);
   if (P.total > ws_bytes)
     return b2_set_error(ctx, B2_ERR_WORKSPACE, "join workspace", "see b2_join_min_ws_bytes()");
@@ -456,13 +477,13 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
   int64_t* loff = reinterpret_cast<int64_t*>(base + P.off_loff);
   uint2* rout = reinterpret_cast<uint2*>(base + P.off_rout);
   uint2* lout = reinterpret_cast<uint2*>(base + P.off_lout);
-  uint2* tmp = P.two_pass ? reinterpret_cast<uint2*>(base + P.off_tmp) : nullptr;
+  uint2* tmp = P.two_pass ? reinterpret_cast<uint2*>(ext_tmp ? (char*)d_out_fk : base + P.off_tmp) : nullptr;
   void* pws = base + P.off_part;
 
   join_init_kernel<<<1, 1, 0, s>>>(st);
   B2_LAUNCH_CHECK(ctx, "join_init_kernel");
   if (nl > 0 && nr > 0) {
-    static bool seen[kB2MaxDevices] = {};
+    static const int seen = b2_new_site();
     if (b2_first_use_on_device(ctx, seen)) {
       B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
@@ -618,6 +639,10 @@ size_t b2_join_ws_bytes(int64_t nl, int64_t nr) {
   if (nl < 0 || nr < 0) return 0;
   return make_plan(nl, nr, 0, 0).total;
 }
+size_t b2_join_ws_bytes_adjacent_outputs(int64_t nl, int64_t nr) {
+  if (nl < 0 || nr < 0) return 0;
+  return make_plan(nl, nr, 0, 0, true).total;
+}
 size_t b2_join_min_ws_bytes(int64_t nl, int64_t nr) {
   if (nl < 0 || nr < 0) return 0;
   return make_plan(nl, nr, 0, kMaxSliceBits).total;
@@ -629,6 +654,7 @@ int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int6
                     uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
                     void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nl == 0 || (d_fk && d_y), "null left column");
   B2_REQUIRE(ctx, nr == 0 || (d_pk && d_x), "null right column");
   PartInput lin, rin;
@@ -645,6 +671,7 @@ int b2_join_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y,
                          uint32_t y_threshold, b2_join_aggr* d_out, int hash_skip_bits, void* d_ws,
                          size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nl == 0 || (d_fk && d_y), "null left column");
   B2_REQUIRE(ctx, nr == 0 || (d_pk && d_x), "null right column");
   PartInput lin, rin;
@@ -665,6 +692,7 @@ int b2_join_pairs_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, int64_t nl, const 
                       int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits, void* d_ws,
                       size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nl == 0 || d_l_pairs, "null left pairs");
   B2_REQUIRE(ctx, nr == 0 || d_r_pairs, "null right pairs");
   PartInput lin, rin;
@@ -687,6 +715,7 @@ int b2_shuffle_partition_u32_dev(b2_ctx* ctx, const uint32_t* d_key, const uint3
                                  int nranks, uint64_t* d_pairs_out, int64_t* d_dest_off, void* d_ws,
                                  size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0, "negative size");
   B2_REQUIRE(ctx, nranks >= 1 && nranks <= 1024 && (nranks & (nranks - 1)) == 0,
              "nranks must be a power of two <= 1024");
@@ -710,6 +739,7 @@ size_t b2_shuffle_p2p_ws_bytes(int64_t n, int bits) {
 int b2_shuffle_p2p_count_dev(b2_ctx* ctx, const uint32_t* d_key, int64_t n, int bits, int64_t* d_bucket_off,
                              void* d_ws, size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0 && bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
   B2_REQUIRE(ctx, d_bucket_off != nullptr && (n == 0 || d_key != nullptr), "null pointer");
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
@@ -732,6 +762,7 @@ int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_
                                int bits, const uint64_t* d_bucket_addr, void* d_ws, size_t ws_bytes,
                                void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0 && bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
   B2_REQUIRE(ctx, d_bucket_addr != nullptr && (n == 0 || (d_key && d_val)), "null pointer");
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
@@ -760,6 +791,7 @@ int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t*
                           uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
                           void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nl == 0 || d_l_pairs, "null left pairs");
   B2_REQUIRE(ctx, nr == 0 || d_r_pairs, "null right pairs");
   B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
@@ -782,6 +814,7 @@ int b2_partition_u32_dev(b2_ctx* ctx, const uint32_t* const* d_cols_in, uint32_t
                          int ncols, int64_t n, int nparts, int skip_bits, int64_t* d_part_off,
                          void* d_ws, size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0 && n < (1ll << 32), "row count must fit the 32-bit row index");
   B2_REQUIRE(ctx, ncols >= 1 && ncols <= 16, "1..16 columns");
   B2_REQUIRE(ctx, nparts >= 1 && nparts <= (1 << (2 * kPartMaxBits)) && (nparts & (nparts - 1)) == 0,

@@ -376,6 +376,7 @@ int b2_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_in, const uint8_t* d_valid, i
 int b2_aggr_32_dev(b2_ctx* ctx, const void* d_in_, int dtype, const uint8_t* d_valid, int64_t n,
                    b2_aggr_u32* d_out, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   if (dtype == B2_F32)
     return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "float32 aggregates",
                         "rounding and the sign of zero depend on the summation order, in Arrow too");
@@ -415,6 +416,7 @@ int b2_aggr_32_dev(b2_ctx* ctx, const void* d_in_, int dtype, const uint8_t* d_v
 int b2_aggr_64_dev(b2_ctx* ctx, const void* d_in_, int dtype, const uint8_t* d_valid, int64_t n,
                    b2_aggr_u64* d_out, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, dtype == B2_U64 || dtype == B2_I64, "dtype must be B2_U64 or B2_I64");
   const bool is_signed = dtype == B2_I64;
   const uint64_t* d_in = static_cast<const uint64_t*>(d_in_);
@@ -451,6 +453,7 @@ int b2_take_u32_nullable_dev(b2_ctx* ctx, const uint32_t* d_values, const uint8_
                              int64_t idx_len, int64_t nbatches, uint32_t* d_out, uint8_t* d_out_valid,
                              void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, values_len >= 0 && idx_len >= 0 && nbatches >= 0, "negative size");
   const int64_t n = nbatches * idx_len;
   if (n == 0) return B2_OK;

@@ -830,19 +830,22 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 }
 
 // part_off[s*P + p] = first output row of (segment s, bucket p); part_off[nseg*P] = total rows.
+// Boundaries are clamped to `clamp` (the capacity of the pass's output): when a skewed hash-space
+// slice overflows its buffer the scatter drops the rows beyond it and raises *overflow; whoever reads
+// the output by these boundaries (a second pass, the probe) must not run past the buffer either.
 __global__ void part_offsets_kernel(const uint64_t* __restrict__ scanned,
                                     const int64_t* __restrict__ unit_first, int64_t nseg, int P,
-                                    int64_t* __restrict__ part_off) {
+                                    int64_t clamp, int64_t* __restrict__ part_off) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = nseg * P;
   if (i > n) return;
   if (i == n) {
-    part_off[n] = (int64_t)scanned[unit_first[nseg] * P];
+    part_off[n] = min((int64_t)scanned[unit_first[nseg] * P], clamp);
     return;
   }
   const int64_t s = i / P, p = i - s * P;
   const int64_t ustride = unit_first[s + 1] - unit_first[s];
-  part_off[i] = (int64_t)scanned[unit_first[s] * P + p * ustride];
+  part_off[i] = min((int64_t)scanned[unit_first[s] * P + p * ustride], clamp);
 }
 
 size_t scatter_smem_bytes(int bits, int tile_rows) {
@@ -879,16 +882,18 @@ PassLayout pass_layout(int64_t n, int64_t nseg, int bits) {
   return L;
 }
 
-int g_scatter_variant = 0;  // tuning hook (b200olap_tune_scatter_variant)
-int g_scatter_prefetch = 1;  // request the next tile's rows while the current one is flushed
-int g_sectors_min_bits = 9;  // fan-out (log2) from which the whole-sector scatter kernel is used (measured: join_lab smem:0:b)
+// Kernel-selection knobs live in the ctx (b2_ctx_set_tunable), not in process-global state:
+//   B2_TUNE_SCATTER_SECTORS_MIN_BITS  fan-out (log2) from which the whole-sector scatter kernel is used (default 9,
+//                                     measured: tools/join_lab.py smem:0:b)
+//   B2_TUNE_SCATTER_PREFETCH          request the next tile's rows while the current one is flushed (default on)
+//   B2_TUNE_SCATTER_SHAPE             threads x rows per thread x CTAs per SM of the plain scatter kernel
 
 template <bool kAoS, int kT, int kI, int kCtas, bool kValPred = false, bool kPre = false>
 int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const PartInput& in,
                    const int64_t* d_seg_off, const int64_t* unit_first, int64_t nseg, int64_t unit_rows,
                    const PartGeom& g, const uint64_t* scanned, uint2* d_out, int64_t out_cap,
                    unsigned int* d_overflow) {
-  static bool seen[kB2MaxDevices] = {};
+  static const int seen = b2_new_site();
   if (b2_first_use_on_device(ctx, seen)) {
     B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_kernel<kAoS, kT, kI, kCtas, kValPred, kPre>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -904,7 +909,7 @@ int launch_scatter(b2_ctx* ctx, int64_t units, int bits, cudaStream_t s, const P
 template <bool kAoS>
 int part_count_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off,
                     int64_t nseg, const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes,
-                    cudaStream_t s) {
+                    cudaStream_t s, int64_t clamp) {
   const int P = 1 << g.bits;
   const PassLayout L = pass_layout(n, nseg, g.bits);
   if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition pass", "workspace");
@@ -930,7 +935,7 @@ int part_count_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* 
                                              ws_bytes - L.off_scanws, s));
   if (d_part_off) {
     const int64_t cnt = nseg * P + 1;
-    part_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(scanned, unit_first, nseg, P,
+    part_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(scanned, unit_first, nseg, P, clamp,
                                                                       d_part_off);
     B2_LAUNCH_CHECK(ctx, "part_offsets_kernel");
   }
@@ -951,16 +956,16 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
   if (L.max_units > 0) {
     // whole-sector scatter: local destinations, 32-byte aligned output, fan-out at or above the threshold
     const bool sectors = !d_bucket_addr && !g.val_pred && (reinterpret_cast<uintptr_t>(d_out) & 31) == 0 &&
-                         (uint64_t)out_cap < (1ull << 34) && g.bits >= g_sectors_min_bits;
+                         (uint64_t)out_cap < (1ull << 34) && g.bits >= ctx->tune[B2_TUNE_SCATTER_SECTORS_MIN_BITS];
     if (sectors) {
-      static bool seen[kB2MaxDevices] = {};
+      static const int seen = b2_new_site();
       if (b2_first_use_on_device(ctx, seen)) {
         B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS, true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScSmem)));
         B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScSmem)));
       }
-      if (g_scatter_prefetch)
+      if (ctx->tune[B2_TUNE_SCATTER_PREFETCH])
         part_scatter_sectors_kernel<kAoS, true><<<(unsigned)L.max_units, kScT, sizeof(ScSmem), s>>>(
             in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
       else
@@ -970,7 +975,7 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       return B2_OK;
     }
     if (d_bucket_addr) {  // peer destinations: whole 128-byte lines only (line carry)
-      static bool seen[kB2MaxDevices] = {};  // one table per template instantiation
+      static const int seen = b2_new_site();  // one table per template instantiation
       if (b2_first_use_on_device(ctx, seen)) {
         B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_lines_kernel<kAoS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -979,18 +984,18 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
           in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr);
     } else if (g.val_pred) {  // pushed-down value predicate: one shape, the default one
-      if (g_scatter_prefetch)
+      if (ctx->tune[B2_TUNE_SCATTER_PREFETCH])
         B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, true, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
       else
         B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
     } else {
-      switch (g_scatter_variant) {
+      switch (ctx->tune[B2_TUNE_SCATTER_SHAPE]) {
         case 1: B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 8, 3>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 2: B2_RETURN_NOT_OK((launch_scatter<kAoS, 256, 16, 4>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 3: B2_RETURN_NOT_OK((launch_scatter<kAoS, 1024, 8, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         case 8: B2_RETURN_NOT_OK((launch_scatter<kAoS, 1024, 16, 1>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow))); break;
         default:
-          if (g_scatter_prefetch)
+          if (ctx->tune[B2_TUNE_SCATTER_PREFETCH])
             B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, false, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
           else
             B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
@@ -1007,11 +1012,13 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
 size_t part_pass_ws_bytes(int64_t n, int64_t nseg, int bits) { return pass_layout(n, nseg, bits).total; }
 
 int part_count(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
-               const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+               const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes, cudaStream_t s,
+               int64_t clamp_rows) {
   B2_REQUIRE(ctx, g.bits >= 0 && g.bits <= kPartMaxBits, "fan-out per pass is limited to 2^10");
   B2_REQUIRE(ctx, nseg >= 1, "at least one segment");
-  if (in.pairs) return part_count_impl<true>(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s);
-  return part_count_impl<false>(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s);
+  if (in.pairs)
+    return part_count_impl<true>(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s, clamp_rows);
+  return part_count_impl<false>(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s, clamp_rows);
 }
 
 int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
@@ -1027,7 +1034,7 @@ int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_s
 int part_pass(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
               const PartGeom& g, uint2* d_out, int64_t out_cap, int64_t* d_part_off,
               unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s) {
-  B2_RETURN_NOT_OK(part_count(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s));
+  B2_RETURN_NOT_OK(part_count(ctx, in, n, d_seg_off, nseg, g, d_part_off, d_ws, ws_bytes, s, out_cap));
   return part_scatter(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, nullptr, d_overflow, d_ws,
                       ws_bytes, s);
 }
@@ -1104,19 +1111,3 @@ int part_full(b2_ctx* ctx, const PartInput& in, int64_t n, int bits, int shl, in
                    d_overflow, base + F.off_pass, F.pass_bytes, s);
 }
 
-// Tuning hooks (labs and tests only; not part of include/b200olap.h).
-extern "C" int b200olap_sectors_min_bits() { return g_sectors_min_bits; }
-extern "C" int b200olap_tune_sectors_min_bits(int bits) {  // 0 = always, > 10 = never
-  if (bits < 0) return B2_ERR_INVALID;
-  g_sectors_min_bits = bits;
-  return B2_OK;
-}
-extern "C" int b200olap_tune_scatter_prefetch(int on) {
-  g_scatter_prefetch = on != 0;
-  return B2_OK;
-}
-extern "C" int b200olap_tune_scatter_variant(int v) {
-  if (v < 0 || (v > 3 && v != 8)) return B2_ERR_INVALID;
-  g_scatter_variant = v;
-  return B2_OK;
-}

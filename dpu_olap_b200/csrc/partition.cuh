@@ -57,8 +57,10 @@ int part_pass(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_
 // scatter. Between them the caller may turn the boundaries into per-bucket destination ADDRESSES
 // (d_bucket_addr, 2^bits byte addresses, single segment only): the fused multi-GPU shuffle points
 // them into the peers' receive buffers. Same n / segments / geometry / workspace for both calls.
+// clamp_rows: boundaries written to d_part_off never exceed it (the capacity of the scatter's output).
 int part_count(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
-               const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes, cudaStream_t s);
+               const PartGeom& g, int64_t* d_part_off, void* d_ws, size_t ws_bytes, cudaStream_t s,
+               int64_t clamp_rows = INT64_MAX);
 int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
                  const PartGeom& g, uint2* d_out, int64_t out_cap, const uint64_t* d_bucket_addr,
                  unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s);

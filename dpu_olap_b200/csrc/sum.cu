@@ -15,8 +15,14 @@ namespace {
 
 constexpr int kSumThreads = 512;
 constexpr int kSumUnroll = 8;               // uint4 loads in flight per thread
-constexpr int kSumMaxCtas = 4096;           // partial slots in ctx->d_small
-constexpr size_t kTicketOffset = 2 * kSumMaxCtas * 8;  // byte offset of the ticket in ctx->d_small (after sums and counts)
+constexpr int kSumMaxCtas = 448;            // CTAs per launch (2 per SM; B200 has 148 SMs)
+// Every launch gets its OWN partials and ticket: ctx->d_small is a ring of kSumSlots scratch slots
+// (sums | counts | ticket), claimed round-robin on the host, so launches of one ctx that are in
+// flight on different streams never share state (up to kSumSlots of them at a time).
+constexpr int kSumSlots = 16;
+constexpr size_t kSumSlotBytes = 2 * kSumMaxCtas * 8 + 1024;  // 8 KB; the ticket sits after sums and counts
+constexpr size_t kTicketOffset = 2 * kSumMaxCtas * 8;
+static_assert(kSumSlots * kSumSlotBytes <= 128 * 1024, "b2_ctx_create allocates 128 KB of small scratch");
 
 __device__ __forceinline__ uint64_t sum4(uint4 v) {
   return ((uint64_t)v.x + v.y) + ((uint64_t)v.z + v.w);
@@ -155,9 +161,9 @@ int sum_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t n, bool filtered, uint
   int grid = ctx->sm_count * 2;
   if (want < grid) grid = want > 0 ? (int)want : 1;
   if (grid > kSumMaxCtas) grid = kSumMaxCtas;
-  uint64_t* partials = static_cast<uint64_t*>(ctx->d_small);  // [kSumMaxCtas] sums | [kSumMaxCtas] counts
-  unsigned int* ticket =
-      reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->d_small) + kTicketOffset);
+  char* slot = static_cast<char*>(ctx->d_small) + (size_t)(ctx->sum_slot++ % kSumSlots) * kSumSlotBytes;
+  uint64_t* partials = reinterpret_cast<uint64_t*>(slot);  // [kSumMaxCtas] sums | [kSumMaxCtas] counts
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(slot + kTicketOffset);
   if (filtered)
     sum_u32_kernel<true><<<grid, kSumThreads, 0, s>>>(d_in, n, thr, partials, ticket, d_sum, d_count);
   else
@@ -170,11 +176,13 @@ int sum_launch(b2_ctx* ctx, const uint32_t* d_in, int64_t n, bool filtered, uint
 extern "C" int b2_sum_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint64_t* d_sum,
                               void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   return sum_launch(ctx, d_in, n, false, 0u, d_sum, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b2_sum_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint32_t threshold,
                                  uint64_t* d_sum, uint64_t* d_count, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   return sum_launch(ctx, d_in, n, true, threshold, d_sum, d_count, static_cast<cudaStream_t>(stream));
 }

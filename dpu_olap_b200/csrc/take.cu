@@ -128,6 +128,7 @@ extern "C" {
 int b2_take_64_dev(b2_ctx* ctx, const void* d_values_, int64_t values_len, const uint32_t* d_indices,
                    int64_t idx_len, int64_t nbatches, void* d_out_, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, values_len >= 0 && idx_len >= 0 && nbatches >= 0, "negative size");
   const int64_t n = nbatches * idx_len;
   if (n == 0) return B2_OK;
@@ -163,6 +164,7 @@ int b2_take_u32_dev(b2_ctx* ctx, const uint32_t* d_values, int64_t values_len,
                     const uint32_t* d_indices, int64_t idx_len, int64_t nbatches, uint32_t* d_out,
                     void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, values_len >= 0 && idx_len >= 0 && nbatches >= 0, "negative size");
   const int64_t n = nbatches * idx_len;
   if (n == 0) return B2_OK;
@@ -196,6 +198,7 @@ int b2_take_u32_ragged_dev(b2_ctx* ctx, const uint32_t* d_values, const int64_t*
                            const uint32_t* d_indices, const int64_t* d_idx_off, int64_t nbatches,
                            int64_t idx_begin, int64_t idx_end, uint32_t* d_out, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, nbatches >= 0 && idx_begin >= 0 && idx_end >= idx_begin, "bad range");
   const int64_t n_idx_total = idx_end - idx_begin;
   if (n_idx_total == 0) return B2_OK;

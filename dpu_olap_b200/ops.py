@@ -27,7 +27,7 @@ from typing import Any, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import Timings, check
+from ._lib import B2Error, Timings, check
 
 try:  # pyarrow is optional for the package, present in the image
     import pyarrow as pa
@@ -234,6 +234,15 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(self._lib.b2_ctx_sm_count(self._h))
+
+    def set_tunable(self, which: int, value: int) -> None:
+        """Kernel-selection knob of this ctx (enum b2_tunable; every setting computes the same result)."""
+        self._ck(self._lib.b2_ctx_set_tunable(self._h, int(which), int(value)), "b2_ctx_set_tunable")
+
+    def get_tunable(self, which: int) -> int:
+        v = C.c_int(0)
+        self._ck(self._lib.b2_ctx_get_tunable(self._h, int(which), C.byref(v)), "b2_ctx_get_tunable")
+        return int(v.value)
 
     # ---- device-resident entry points (torch CUDA tensors) --------------------------------
     @staticmethod
@@ -445,6 +454,19 @@ class Context:
 
     def join_min_ws_bytes(self, nl: int, nr: int) -> int:
         return int(self._lib.b2_join_min_ws_bytes(nl, nr))
+
+    def join_ws_bytes_adjacent_outputs(self, nl: int, nr: int) -> int:
+        """One-go workspace when the three output columns are one allocation (see b200olap.h)."""
+        return int(self._lib.b2_join_ws_bytes_adjacent_outputs(nl, nr))
+
+    @staticmethod
+    def join_rows(out_rows) -> int:
+        """Reads the device row counter of a join; ~0 (a hash-space slice overflowed its buffer:
+        sliced workspace + heavily skewed keys) is an error, not a row count."""
+        n = int(out_rows.cpu().numpy().view("uint64")[0])
+        if n == 0xFFFFFFFFFFFFFFFF:
+            raise B2Error(5, "join", "a hash-space slice overflowed; give the join a larger workspace")
+        return n
 
     def join_dev(self, fk, y, pk, x, out_capacity: int | None = None, ws=None, outs=None,
                  out_rows=None, skip_bits: int = 0):

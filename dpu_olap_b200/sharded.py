@@ -83,27 +83,37 @@ class ShardedJoin:
     last: ExchangeCounts | None = field(default=None, init=False)
 
     def exchange_counts(self, off) -> tuple[list[int], list[int]]:
-        """(send, recv) row counts per peer for one side: one tiny all-to-all plus the host read
-        that sizes the pair exchange (the reference reads the per-DPU histograms back to the host
-        for the same purpose, partitioner.cc:167-180,280-312)."""
+        """(send, recv) row counts per peer for one side: one small all-gather of every rank's send
+        counts plus the host read that sizes the pair exchange (the reference reads the per-DPU
+        histograms back to the host for the same purpose, partitioner.cc:167-180,280-312). Every
+        rank sees the whole G x G matrix, so the capacity check below is decided identically on all
+        ranks: either everybody raises or nobody does (a rank that raised alone would leave its
+        peers hanging in the all-to-all)."""
         import torch
         counts = (off[1:] - off[:-1]).contiguous()
         if self.dist is None:
-            got = counts.clone()
+            allc = counts.view(1, -1)
         else:
-            got = torch.empty_like(counts)
-            self.dist.all_to_all_single(got, counts)
-        return counts.cpu().tolist(), got.cpu().tolist()
+            flat = torch.empty(self.world * counts.numel(), dtype=counts.dtype, device=counts.device)
+            self.dist.all_gather_into_tensor(flat, counts)  # flat output: gloo wants it that way
+            allc = flat.view(self.world, counts.numel())
+        m = allc.cpu()
+        worst = int(m.sum(0).max())
+        self._check_capacity(worst)
+        return m[self.rank].tolist(), m[:, self.rank].tolist()
+
+    def _check_capacity(self, worst: int) -> None:
+        caps = [c for c in (self.capacity,
+                            None if self.recv_l is None else self.recv_l.numel(),
+                            None if self.recv_r is None else self.recv_r.numel()) if c is not None]
+        if caps and worst > min(caps):
+            raise OverflowError(f"a rank would receive {worst} rows, capacity {min(caps)} (skewed keys); "
+                                "raised on every rank")
 
     def _recv_buffer(self, pre, n, like):
         import torch
         if pre is not None:
-            if n > pre.numel():
-                raise OverflowError(f"rank {self.rank}: receive buffer holds {pre.numel()} rows, {n} arrive "
-                                    "(skewed keys)")
-            return pre[:n]
-        if self.capacity is not None and n > self.capacity:
-            raise OverflowError(f"rank {self.rank}: {n} rows arrive, capacity {self.capacity} (skewed keys)")
+            return pre[:n]  # capacity was checked collectively in exchange_counts
         return torch.empty(n, dtype=like.dtype, device=like.device)
 
     def exchange(self, pairs, send, recv, pre=None):

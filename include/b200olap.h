@@ -82,6 +82,18 @@ const char* b2_last_error(const b2_ctx* ctx);
 int64_t b2_launch_count(const b2_ctx* ctx);
 int b2_ctx_device(const b2_ctx* ctx);
 int b2_ctx_sm_count(const b2_ctx* ctx);
+/* Kernel-selection knobs of ONE ctx (no process-global state). Every setting computes the same,
+ * bit-identical result; they exist so that tests can push every input through every kernel variant
+ * and so that a deployment can re-tune thresholds without a rebuild. Defaults are the measured best
+ * on B200 (profiles/r1_filter.md, profiles/r1_scatter_fanout.md). */
+enum b2_tunable {
+  B2_TUNE_SCATTER_SECTORS_MIN_BITS = 0, /* log2 fan-out from which the radix scatter stores whole 32 B sectors (9; 0 = always, 11 = never) */
+  B2_TUNE_SCATTER_PREFETCH = 1,         /* scatter kernels request the next tile while flushing this one (1) */
+  B2_TUNE_SCATTER_SHAPE = 2,            /* plain scatter kernel shape: 0 = 512 thr x 16 rows x 2 CTA/SM, 1, 2, 3, 8 */
+  B2_TUNE_FILTER_VARIANT = 3            /* filter kernel shape 0..7 (6) */
+};
+int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value);
+int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value);
 
 /* ---- pinned host memory (zero-copy Arrow interop at the boundary) -------------------------- */
 /* Arrow buffers live in pageable memory; copies from/to them run at a fraction of the PCIe rate.
@@ -115,7 +127,8 @@ int b2_gen_u32_dev(b2_ctx* ctx, const uint64_t* data_seeds, const uint32_t* lo, 
 int b2_iota_u32_dev(b2_ctx* ctx, uint64_t start, int64_t n, uint32_t* d_out, void* stream);
 
 /* ---- Sum (replaces dpu/aggr/main.c:44-89 + dpu/shared/kernels/aggr.c:16-33) -------------- */
-/* *d_sum = sum of d_in[0..n) as uint64 (mod 2^64). One kernel launch. */
+/* *d_sum = sum of d_in[0..n) as uint64 (mod 2^64). One kernel launch. Every launch has its own
+ * scratch slot (a ring of 16 per ctx), so sums of one ctx may be in flight on different streams. */
 int b2_sum_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t n, uint64_t* d_sum, void* stream);
 /* Fused pipeline filter(v < threshold) -> sum: *d_sum = sum of the rows below the threshold,
  * *d_count (may be NULL) = how many there are. One read of the column, nothing materialised — the
@@ -335,8 +348,15 @@ int b2_partition_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int nparts, 
  * sharded join, 0 otherwise).
  * d_ws: 256 B aligned workspace. b2_join_ws_bytes() is the size at which the join runs in one
  * go; with less (down to b2_join_min_ws_bytes()) it runs in 2..64 hash-space slices, re-reading
- * the inputs once per slice. */
+ * the inputs once per slice.
+ * Adjacent output columns: when d_out_fk, d_out_y, d_out_x are ONE allocation (d_out_y == d_out_fk +
+ * out_capacity, d_out_x == d_out_y + out_capacity, 32 B aligned, 12 * out_capacity >= 8 * max(nl, nr)),
+ * the library uses them as the temporary of the first radix pass — they are dead until the probe
+ * writes them (the reference aliases its outputs onto the partitioned left side the same way,
+ * join_dpu.cc:315-322). b2_join_ws_bytes_adjacent_outputs() is the one-go workspace size then:
+ * 8 * max(nl, nr) bytes less. It is what lets SF=2048 (2^32 rows per side) run unsliced on one B200. */
 size_t b2_join_ws_bytes(int64_t nl, int64_t nr);
+size_t b2_join_ws_bytes_adjacent_outputs(int64_t nl, int64_t nr);
 size_t b2_join_min_ws_bytes(int64_t nl, int64_t nr);
 int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
                     const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, uint32_t* d_out_fk,

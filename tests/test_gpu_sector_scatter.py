@@ -6,6 +6,7 @@ import pytest
 import torch
 
 import oracle
+from dpu_olap_b200._lib import TUNE_SCATTER_SECTORS_MIN_BITS
 from test_gpu_dev_ops import check_join, check_partition, dev, host, run_join
 
 pytestmark = pytest.mark.gpu
@@ -13,10 +14,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture()
 def sectors(ctx):
-    default = int(ctx._lib.b200olap_sectors_min_bits())
-    assert ctx._lib.b200olap_tune_sectors_min_bits(0) == 0  # from a fan-out of 2^0: always
+    default = ctx.get_tunable(TUNE_SCATTER_SECTORS_MIN_BITS)
+    ctx.set_tunable(TUNE_SCATTER_SECTORS_MIN_BITS, 0)  # from a fan-out of 2^0: always
     yield ctx
-    assert ctx._lib.b200olap_tune_sectors_min_bits(default) == 0
+    ctx.set_tunable(TUNE_SCATTER_SECTORS_MIN_BITS, default)
 
 
 @pytest.mark.parametrize("n,nparts,ncols", [(0, 4, 2), (1, 1, 1), (3, 2, 2), (1000, 2, 3), (8192, 1024, 2),
@@ -78,7 +79,7 @@ def test_sector_kernel_matches_default_kernel_bytewise(sectors):
     n = 2_000_003
     cols = [rng.integers(0, 2**32, size=n, dtype=np.uint32), np.arange(n, dtype=np.uint32)]
     a, off_a = sectors.partition_dev([dev(c) for c in cols], 1024)
-    assert sectors._lib.b200olap_tune_sectors_min_bits(99) == 0
+    sectors.set_tunable(TUNE_SCATTER_SECTORS_MIN_BITS, 99)
     b, off_b = sectors.partition_dev([dev(c) for c in cols], 1024)
     torch.cuda.synchronize()
     assert np.array_equal(off_a.cpu().numpy(), off_b.cpu().numpy())

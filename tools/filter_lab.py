@@ -40,8 +40,11 @@ def main():
     flip = torch.tensor(-2**31, dtype=torch.int32, device="cuda")
     results = []
     for variant in [int(v) for v in args.variants.split(",")]:
-        rc = ctx._lib.b200olap_tune_filter_variant(variant)
-        assert rc == 0, rc
+        ctx.set_tunable(3, variant & 0xff)  # B2_TUNE_FILTER_VARIANT
+        if variant >> 8:  # debug bits (no prefix / no TMA / dynamic tickets) exist in the lab build only:
+            # python -m dpu_olap_b200.build --lab, then run with B200OLAP_LIB=dpu_olap_b200/libb200olap_lab.so
+            rc = ctx._lib.b200olap_lab_filter_debug(variant >> 8)
+            assert rc == 0, rc
         for thr in [int(t) for t in args.thresholds.split(",")]:
             def step():
                 ctx.filter_dev(col, nb, bl, thr, out=out, batch_end=end, total=total, ws=ws)

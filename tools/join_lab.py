@@ -36,11 +36,11 @@ def main():
         for cfg in a.configs.split(","):
             f = cfg.split(":")
             assert f[0] == "smem", cfg
-            assert ctx._lib.b200olap_tune_scatter_variant(int(f[1]) if len(f) > 1 else 0) == 0
+            ctx.set_tunable(2, int(f[1]) if len(f) > 1 else 0)   # B2_TUNE_SCATTER_SHAPE
             if len(f) > 2:  # smem:v:b = whole-sector scatter kernel from a fan-out of 2^b
-                assert ctx._lib.b200olap_tune_sectors_min_bits(int(f[2])) == 0
+                ctx.set_tunable(0, int(f[2]))                    # B2_TUNE_SCATTER_SECTORS_MIN_BITS
             if len(f) > 3:  # smem:v:b:p = next-tile prefetch in the scatter kernels off / on
-                assert ctx._lib.b200olap_tune_scatter_prefetch(int(f[3])) == 0
+                ctx.set_tunable(1, int(f[3]))                    # B2_TUNE_SCATTER_PREFETCH
             ws = torch.empty(ctx.join_ws_bytes(n, n) + 256, dtype=torch.uint8, device="cuda")
             step = lambda: ctx.join_dev(fk, y, pk, x, out_capacity=n, ws=ws, outs=outs, out_rows=rows)
             for o in outs:

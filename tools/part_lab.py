@@ -30,8 +30,8 @@ def main():
             ws = torch.empty(int(ctx._lib.b2_shuffle_ws_bytes(n, parts)) + 512, dtype=torch.uint8, device="cuda")
             for v in a.variants.split(","):
                 # "s" = the whole-sector kernel for every fan-out; a number = that shape of the plain kernel
-                assert ctx._lib.b200olap_tune_sectors_min_bits(0 if v == "s" else 99) == 0
-                assert ctx._lib.b200olap_tune_scatter_variant(0 if v == "s" else int(v)) == 0
+                ctx.set_tunable(0, 0 if v == "s" else 99)          # B2_TUNE_SCATTER_SECTORS_MIN_BITS
+                ctx.set_tunable(2, 0 if v == "s" else int(v))       # B2_TUNE_SCATTER_SHAPE
                 step = lambda: ctx.shuffle_partition_dev(key, val, parts, pairs_out=pairs, dest_off=off, ws=ws)
                 for _ in range(2):
                     step()
