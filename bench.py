@@ -629,23 +629,23 @@ def bench_join(ctx, D, args):
             from dpu_olap_b200.sharded import P2PShuffleJoin
             ok = 1
             try:
-                pj = P2PShuffleJoin(ctx, D.dist, D.rank, G, n, cap)
+                pj = P2PShuffleJoin(ctx, D.dist, D.rank, G, n, cap, n_build_total=nb_total * JOIN_BATCH)
             except Exception as e:  # noqa: BLE001 - reported below, and agreed on by all ranks
                 ok = 0
                 info["p2p_unavailable"] = f"{type(e).__name__}: {e}"[:200]
             if D.sum_int(ok) != G:
                 pj, exchange = None, "nccl"
         if exchange == "p2p":
-            jws_bytes = ctx.join_seg_ws_bytes(cap, cap, pj.skip, pj.seg_bits)
+            jws_bytes = ctx.join_seg_cap_ws_bytes(cap, cap, pj.nr_expected, pj.skip, pj.seg_bits)
             if jws_bytes == 0:
                 raise SystemExit("segmented join unsupported at this size; use --join-exchange nccl")
             jws = torch.empty(jws_bytes + 256, dtype=torch.uint8, device="cuda")
             info["workspace_gib"] = round(jws_bytes / 2**30, 2)
             info["sliced"] = False
 
-            def local_join(lr, lseg, rr, rseg, seg_bits, skip_bits):
-                ctx.join_pairs_seg_dev(lr, lseg, rr, rseg, seg_bits, out_capacity=cap * mult, skip_bits=skip_bits,
-                                       ws=jws, outs=outs, out_rows=rows_t)
+            def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort):
+                ctx.join_pairs_seg_cap_dev(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, out_capacity=cap * mult,
+                                           skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t, abort=abort)
 
             def step():
                 pj.step(fk, y, pk, x, local_join)
@@ -655,12 +655,15 @@ def bench_join(ctx, D, args):
             ph = {}
             pj.step(fk, y, pk, x, local_join, phases=ph)  # one extra, synchronised step: where the time goes
             info["phases_ms_rank0_serialised"] = {k: round(v, 3) for k, v in ph.items()}
-            nl_r, nr_r = pj.last_recv
+            nl_r, nr_r = pj.received()
             info["shuffle_rows_received_rank0"] = [nl_r, nr_r]
+            info["host_syncs_per_step"] = 0
             info["shuffle_bytes_sent_per_rank"] = int(16 * n * (G - 1) / G)  # expectation: hash-uniform
             info["shuffle"] = ("fused: b2_shuffle_p2p_scatter stores (key, payload) pairs over NVLink into the "
-                               "peers' symmetric-memory receive buffers, pre-partitioned; collectives left: one "
-                               "all-gather of 2 x 1024 counts + one barrier (dpu_olap_b200.sharded.P2PShuffleJoin)")
+                               "peers' symmetric-memory receive buffers, pre-partitioned; addresses, capacity check "
+                               "and received row counts stay on the device (b2_shuffle_p2p_plan_dev, "
+                               "b2_join_pairs_seg_cap_dev); collectives left: one all-gather of 2 x 1025 boundaries + "
+                               "one barrier (dpu_olap_b200.sharded.P2PShuffleJoin)")
             del jws, pj
         else:
             lp = torch.empty(n, dtype=torch.int64, device="cuda")

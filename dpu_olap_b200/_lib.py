@@ -77,7 +77,11 @@ SIGNATURES = {
     "b2_host_unregister": (_int, [_vp]),
     "b2_shuffle_p2p_ws_bytes": (_sz, [_i64, _int]),
     "b2_shuffle_p2p_count_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
-    "b2_shuffle_p2p_scatter_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "b2_shuffle_p2p_scatter_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    "b2_shuffle_p2p_plan_dev": (_int, [_vp, _vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "b2_join_seg_cap_ws_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
+    "b2_join_pairs_seg_cap_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _vp,
+                                         _int, _vp, _vp, _sz, _vp]),
     "b2_join_seg_ws_bytes": (_sz, [_i64, _i64, _int, _int]),
     "b2_join_pairs_seg_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _i64, _vp, _int,
                                      _vp, _sz, _vp]),
@@ -119,6 +123,20 @@ SIGNATURES = {
                                                    _pu64, _pt]),
     "b2_take_u32_nullable_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _pp, _pp, _pi64, _pi64, _i64, _pp, _pp, _pt]),
     "b2_shuffle_ws_bytes": (_sz, [_i64, _int]),
+    "b2_set_create": (_int, [C.POINTER(C.c_int), _int, C.POINTER(_vp)]),
+    "b2_set_destroy": (_int, [_vp]),
+    "b2_set_size": (_int, [_vp]),
+    "b2_set_ctx": (_vp, [_vp, _int]),
+    "b2_set_peer_access": (_int, [_vp]),
+    "b2_set_last_error": (C.c_char_p, [_vp]),
+    "b2_set_launch_count": (_i64, [_vp]),
+    "b2_set_set_inputs_pinned": (_int, [_vp, _int]),
+    "b2_set_sum_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pu64, _pt]),
+    "b2_set_filter_lt_u32_host": (_int, [_vp, _pp, _pi64, _i64, _u32, _pi64, _pu64, _pt]),
+    "b2_set_filter_fetch_host": (_int, [_vp, _pp, _i64, _pt]),
+    "b2_set_take_u32_host": (_int, [_vp, _pp, _pi64, _pp, _pi64, _i64, _pp, _pt]),
+    "b2_set_join_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pp, _pi64, _i64, _pu64, _pt]),
+    "b2_set_join_fetch_host": (_int, [_vp, _vp, _vp, _vp, _i64, _pt]),
     "b2_shuffle_partition_u32_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
 }
 

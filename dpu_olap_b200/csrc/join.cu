@@ -379,9 +379,11 @@ __global__ void join_aggr_finish_kernel(const JoinState* __restrict__ st, b2_joi
   out->sum_y = st->sum_y;
   out->sum_x = st->sum_x;
 }
-__global__ void join_finish_kernel(const JoinState* __restrict__ st, uint64_t* __restrict__ out_rows) {
-  // a partition buffer that overflowed (skewed slice) makes the result invalid: report ~0
-  *out_rows = st->overflow ? ~0ull : st->out_rows;
+__global__ void join_finish_kernel(const JoinState* __restrict__ st, uint64_t* __restrict__ out_rows,
+                                   const int64_t* __restrict__ abort_flag = nullptr) {
+  // a partition buffer that overflowed (skewed slice) makes the result invalid: report ~0; so does
+  // an exchange that was called off on the device (receive capacity exceeded, b2_shuffle_p2p_plan_dev)
+  *out_rows = (st->overflow || (abort_flag && *abort_flag)) ? ~0ull : st->out_rows;
 }
 
 int ceil_log2_i64(int64_t v) {
@@ -537,8 +539,12 @@ struct SegPlan {
   size_t off_state, off_roff, off_loff, off_rout, off_lout, off_part, part_bytes, total;
 };
 
-bool make_seg_plan(int64_t nl, int64_t nr, int skip_bits, int seg_bits, SegPlan* P) {
-  int bits = ceil_log2_i64((nr + kTargetBuild - 1) / kTargetBuild);
+// nl / nr size the buffers and work units (upper bounds are fine: the real row counts are the last
+// entries of the segment tables on the device); nr_expected (<= 0: nr) picks the number of fine
+// partitions, so a caller that only knows a generous receive CAPACITY still gets ~4096-row tables.
+bool make_seg_plan(int64_t nl, int64_t nr, int skip_bits, int seg_bits, SegPlan* P, int64_t nr_expected = 0) {
+  const int64_t nr_plan = nr_expected > 0 ? std::min(nr_expected, nr) : nr;
+  int bits = ceil_log2_i64((nr_plan + kTargetBuild - 1) / kTargetBuild);
   bits = std::max(bits, seg_bits);
   bits = std::min(bits, 32 - skip_bits);
   // one fine pass refines a coarse bucket at most 2^10-fold; beyond that partitions simply get
@@ -565,7 +571,8 @@ bool make_seg_plan(int64_t nl, int64_t nr, int skip_bits, int seg_bits, SegPlan*
 int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, int64_t nl,
                   const uint2* rpairs, const int64_t* r_seg_off, int64_t nr, int seg_bits,
                   uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
-                  uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+                  uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s,
+                  int64_t nr_expected = 0, const int64_t* d_abort = nullptr) {
   B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
   B2_REQUIRE(ctx, seg_bits >= 0 && seg_bits <= kPartMaxBits && skip_bits >= 0 && skip_bits + seg_bits <= 20,
              "bad skip/segment bits");
@@ -573,7 +580,7 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
              "workspace must be 256 B aligned");
   SegPlan P;
-  if (!make_seg_plan(nl, nr, skip_bits, seg_bits, &P))
+  if (!make_seg_plan(nl, nr, skip_bits, seg_bits, &P, nr_expected))
     return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "segmented join",
                         "build side too large for one fine pass; use b2_join_pairs_dev");
   if (P.total > ws_bytes)
@@ -583,8 +590,10 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   join_init_kernel<<<1, 1, 0, s>>>(st);
   B2_LAUNCH_CHECK(ctx, "join_init_kernel");
   if (nl > 0 && nr > 0) {
-    B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kTableBytes));
+    static const int seen = b2_new_site();
+    if (b2_first_use_on_device(ctx, seen))
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kTableBytes));
     const int64_t nseg = (int64_t)1 << seg_bits;
     const int64_t nparts = (int64_t)1 << P.total_bits;
     const uint2 *rp = rpairs, *lp = lpairs;
@@ -612,9 +621,78 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
         rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false);
     B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
   }
-  join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows);
+  join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows, d_abort);
   B2_LAUNCH_CHECK(ctx, "join_finish_kernel");
   return B2_OK;
+}
+
+
+// ---- fused shuffle: every rank's bucket boundaries -> this rank's destination addresses --------------
+// One CTA, one thread per bucket (2^bits <= 1024). What dpu_olap_b200/sharded.py::p2p_plan did with a
+// dozen eager torch kernels and a host read-back is one launch here, and the capacity check stays
+// on the device.
+__global__ void __launch_bounds__(1024)
+shuffle_plan_kernel(const int64_t* const* __restrict__ off_ptrs, const uint64_t* __restrict__ recv_base, int rank,
+                    int nranks, int bits, int64_t capacity_rows, uint64_t* __restrict__ bucket_addr,
+                    int64_t* __restrict__ seg_off, int64_t* __restrict__ info,
+                    const int64_t* __restrict__ prev_abort) {
+  __shared__ int64_t excl[1025];
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t s_max;
+  const int B = 1 << bits;
+  const int C = B / nranks;  // coarse buckets per destination rank
+  const int b = threadIdx.x;
+  const uint32_t lane = b & 31, warp = b >> 5;
+  int64_t tot = 0, before = 0;  // rows of all ranks / of the lower ranks in bucket b
+  if (b < B) {
+    for (int s = 0; s < nranks; ++s) {
+      const int64_t* o = off_ptrs[s];
+      const int64_t c = o[b + 1] - o[b];
+      if (s < rank) before += c;
+      tot += c;
+    }
+  }
+  int64_t incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  if (b == 0) s_max = 0;
+  __syncthreads();
+  if (warp == 0) {
+    const int64_t w = warp_tot[lane];
+    int64_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;
+  }
+  __syncthreads();
+  const int64_t ex = warp_tot[warp] + incl - tot;
+  if (b < B) excl[b] = ex;
+  if (b == B - 1) excl[B] = ex + tot;
+  __syncthreads();
+  // rows every destination receives; the largest decides whether the exchange may run at all
+  if (b < nranks) atomicMax(reinterpret_cast<unsigned long long*>(&s_max),
+                            (unsigned long long)(excl[(b + 1) * C] - excl[b * C]));
+  __syncthreads();
+  // prev_abort chains the two sides of a join: the second plan's flag covers both
+  const bool overflow = s_max > capacity_rows || (prev_abort && *prev_abort);
+  if (b < B) {
+    const int dest = b / C;
+    // receive buffers are laid out bucket-major, source-minor: every coarse bucket is contiguous
+    bucket_addr[b] = recv_base[dest] + 8ull * (uint64_t)(excl[b] - excl[dest * C] + before);
+  }
+  if (b <= C) seg_off[b] = overflow ? 0 : excl[rank * C + b] - excl[rank * C];
+  if (b == 0) {
+    info[0] = overflow ? 0 : excl[(rank + 1) * C] - excl[rank * C];
+    info[1] = s_max;
+    info[2] = overflow ? 1 : 0;
+  }
 }
 
 __global__ void set_segment_kernel(int64_t* seg_off, int64_t n) {
@@ -758,9 +836,25 @@ int b2_shuffle_p2p_count_dev(b2_ctx* ctx, const uint32_t* d_key, int64_t n, int 
   return part_count(ctx, in, n, seg, 1, g, d_bucket_off, base + 256, ws_bytes - 256, s);
 }
 
+int b2_shuffle_p2p_plan_dev(b2_ctx* ctx, const int64_t* const* d_off_ptrs, const uint64_t* d_recv_base, int rank,
+                            int nranks, int bits, int64_t capacity_rows, uint64_t* d_bucket_addr,
+                            int64_t* d_seg_off, int64_t* d_info, const int64_t* d_prev_abort, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
+  B2_REQUIRE(ctx, nranks >= 1 && (nranks & (nranks - 1)) == 0 && nranks <= (1 << bits),
+             "nranks must be a power of two <= 2^bits");
+  B2_REQUIRE(ctx, rank >= 0 && rank < nranks, "rank out of range");
+  B2_REQUIRE(ctx, d_off_ptrs && d_recv_base && d_bucket_addr && d_seg_off && d_info, "null pointer");
+  shuffle_plan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_off_ptrs, d_recv_base, rank, nranks, bits, capacity_rows, d_bucket_addr, d_seg_off, d_info, d_prev_abort);
+  B2_LAUNCH_CHECK(ctx, "shuffle_plan_kernel");
+  return B2_OK;
+}
+
 int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
-                               int bits, const uint64_t* d_bucket_addr, void* d_ws, size_t ws_bytes,
-                               void* stream) {
+                               int bits, const uint64_t* d_bucket_addr, const int64_t* d_abort, void* d_ws,
+                               size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
   b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0 && bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
@@ -776,13 +870,35 @@ int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_
   PartGeom g;
   g.bits = bits;
   return part_scatter(ctx, in, n, reinterpret_cast<const int64_t*>(base), 1, g, nullptr, 0, d_bucket_addr,
-                      nullptr, base + 256, ws_bytes - 256, static_cast<cudaStream_t>(stream));
+                      nullptr, base + 256, ws_bytes - 256, static_cast<cudaStream_t>(stream), d_abort);
 }
 
 size_t b2_join_seg_ws_bytes(int64_t nl, int64_t nr, int hash_skip_bits, int seg_bits) {
   SegPlan P;
   if (nl < 0 || nr < 0 || !make_seg_plan(nl, nr, hash_skip_bits, seg_bits, &P)) return 0;
   return P.total;
+}
+size_t b2_join_seg_cap_ws_bytes(int64_t nl_cap, int64_t nr_cap, int64_t nr_expected, int hash_skip_bits,
+                                int seg_bits) {
+  SegPlan P;
+  if (nl_cap < 0 || nr_cap < 0 || !make_seg_plan(nl_cap, nr_cap, hash_skip_bits, seg_bits, &P, nr_expected)) return 0;
+  return P.total;
+}
+
+int b2_join_pairs_seg_cap_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl_cap,
+                              const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr_cap,
+                              int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
+                              uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
+                              const int64_t* d_abort, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, nl_cap == 0 || d_l_pairs, "null left pairs");
+  B2_REQUIRE(ctx, nr_cap == 0 || d_r_pairs, "null right pairs");
+  B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
+  return join_seg_impl(ctx, reinterpret_cast<const uint2*>(d_l_pairs), d_l_seg_off, nl_cap,
+                       reinterpret_cast<const uint2*>(d_r_pairs), d_r_seg_off, nr_cap, seg_bits, d_out_fk,
+                       d_out_y, d_out_x, out_capacity, d_out_rows, hash_skip_bits, d_ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream), nr_expected, d_abort);
 }
 
 int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl,

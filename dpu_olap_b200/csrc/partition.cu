@@ -436,9 +436,11 @@ __global__ void __launch_bounds__(kLcThreads, 1)
 part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                           const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
                           PartGeom g, const uint64_t* __restrict__ scanned,
-                          const uint64_t* __restrict__ bucket_addr) {
+                          const uint64_t* __restrict__ bucket_addr, const int64_t* __restrict__ abort_flag) {
   extern __shared__ __align__(16) unsigned char smem[];
   LcSmem& sm = *reinterpret_cast<LcSmem*>(smem);
+  // the exchange was called off on the device (a receive buffer would overflow): store nothing
+  if (abort_flag && *abort_flag) return;
   const int P = 1 << g.bits;
   const SliceSel sel = slice_sel(g);
   const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
@@ -947,7 +949,7 @@ template <bool kAoS>
 int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off,
                       int64_t nseg, const PartGeom& g, uint2* d_out, int64_t out_cap,
                       const uint64_t* d_bucket_addr, unsigned int* d_overflow, void* d_ws,
-                      size_t ws_bytes, cudaStream_t s) {
+                      size_t ws_bytes, cudaStream_t s, const int64_t* d_abort) {
   const PassLayout L = pass_layout(n, nseg, g.bits);
   if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition pass", "workspace");
   char* base = static_cast<char*>(d_ws);
@@ -982,7 +984,7 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
                                              (int)sizeof(LcSmem)));
       }
       part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
-          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr);
+          in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr, d_abort);
     } else if (g.val_pred) {  // pushed-down value predicate: one shape, the default one
       if (ctx->tune[B2_TUNE_SCATTER_PREFETCH])
         B2_RETURN_NOT_OK((launch_scatter<kAoS, 512, 16, 2, true, true>(ctx, L.max_units, g.bits, s, in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow)));
@@ -1023,12 +1025,12 @@ int part_count(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg
 
 int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
                  const PartGeom& g, uint2* d_out, int64_t out_cap, const uint64_t* d_bucket_addr,
-                 unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+                 unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s, const int64_t* d_abort) {
   if (in.pairs)
     return part_scatter_impl<true>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_bucket_addr,
-                                   d_overflow, d_ws, ws_bytes, s);
+                                   d_overflow, d_ws, ws_bytes, s, d_abort);
   return part_scatter_impl<false>(ctx, in, n, d_seg_off, nseg, g, d_out, out_cap, d_bucket_addr,
-                                  d_overflow, d_ws, ws_bytes, s);
+                                  d_overflow, d_ws, ws_bytes, s, d_abort);
 }
 
 int part_pass(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,

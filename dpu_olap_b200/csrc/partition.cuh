@@ -63,7 +63,8 @@ int part_count(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg
                int64_t clamp_rows = INT64_MAX);
 int part_scatter(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off, int64_t nseg,
                  const PartGeom& g, uint2* d_out, int64_t out_cap, const uint64_t* d_bucket_addr,
-                 unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s);
+                 unsigned int* d_overflow, void* d_ws, size_t ws_bytes, cudaStream_t s,
+                 const int64_t* d_abort = nullptr);  // peer mode: *d_abort != 0 on the device = store nothing
 
 // Full partitioning by `bits` hash bits (after discarding `shl`), in one pass (bits <= 10) or two
 // (coarse pass + segmented fine pass). Result: d_out holds the rows grouped into 2^bits

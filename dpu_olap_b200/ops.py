@@ -200,17 +200,27 @@ def _dptr(t) -> int:
 class Context:
     """One B200. Replaces ``dpu::DpuSet::allocate(nr_dpus)`` (dpuext.hpp:710)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self._lib = _lib.lib()  # raises if libb200olap.so is absent — no fallback
-        h = C.c_void_p()
-        check(self._lib.b2_ctx_create(int(device), C.byref(h)), "b2_ctx_create")
-        self._h = h
-        self.device = int(device)
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = C.c_void_p()
+            check(self._lib.b2_ctx_create(int(device), C.byref(h)), "b2_ctx_create")
+            self._h = h
+            self.device = int(device)
+        else:  # a member of a DeviceSet: the set owns it
+            self._h = C.c_void_p(_borrowed)
+            self.device = int(self._lib.b2_ctx_device(self._h))
 
     def close(self) -> None:
         if getattr(self, "_h", None):
-            self._lib.b2_ctx_destroy(self._h)
+            if self._owned:
+                self._lib.b2_ctx_destroy(self._h)
             self._h = None
+
+    def _call(self, name: str, *args) -> None:
+        """b2_<name>(ctx, ...): the host entry point of an operator on this one GPU."""
+        self._ck(getattr(self._lib, "b2_" + name)(self._h, *args), "b2_" + name)
 
     def __del__(self):  # pragma: no cover
         try:
@@ -565,13 +575,40 @@ class Context:
                                                     ptr, nbytes, self._stream()), "b2_shuffle_p2p_count_dev")
         return bucket_off
 
-    def shuffle_p2p_scatter_dev(self, key, val, bits: int, bucket_addr, ws):
+    def shuffle_p2p_scatter_dev(self, key, val, bits: int, bucket_addr, ws, abort=None):
         """Writes the (key, val) pairs of bucket b contiguously from byte address bucket_addr[b]
-        (int64 device tensor of 2^bits addresses — local or peer memory)."""
+        (int64 device tensor of 2^bits addresses — local or peer memory). abort: int64[1] device
+        tensor; non-zero on the device = store nothing (the plan kernel's overflow flag)."""
         ptr, nbytes = self._aligned(ws)
         self._ck(self._lib.b2_shuffle_p2p_scatter_dev(self._h, _dptr(key), _dptr(val), key.numel(), bits,
-                                                      _dptr(bucket_addr), ptr, nbytes, self._stream()),
+                                                      _dptr(bucket_addr), None if abort is None else _dptr(abort),
+                                                      ptr, nbytes, self._stream()),
                  "b2_shuffle_p2p_scatter_dev")
+
+    def shuffle_p2p_plan_dev(self, off_ptrs, recv_base, rank: int, nranks: int, bits: int, capacity_rows: int,
+                             bucket_addr, seg_off, info, prev_abort=None):
+        """b2_shuffle_p2p_plan_dev: every rank's bucket boundaries -> this rank's destination addresses,
+        the coarse-bucket boundaries it receives and {rows received, max over ranks, overflow} — one
+        launch, nothing read back. off_ptrs / recv_base: int64 device tensors of nranks entries."""
+        self._ck(self._lib.b2_shuffle_p2p_plan_dev(self._h, _dptr(off_ptrs), _dptr(recv_base), rank, nranks, bits,
+                                                   int(capacity_rows), _dptr(bucket_addr), _dptr(seg_off),
+                                                   _dptr(info), None if prev_abort is None else _dptr(prev_abort),
+                                                   self._stream()), "b2_shuffle_p2p_plan_dev")
+
+    def join_seg_cap_ws_bytes(self, nl_cap: int, nr_cap: int, nr_expected: int, skip_bits: int, seg_bits: int) -> int:
+        return int(self._lib.b2_join_seg_cap_ws_bytes(nl_cap, nr_cap, nr_expected, skip_bits, seg_bits))
+
+    def join_pairs_seg_cap_dev(self, l_pairs, l_seg_off, r_pairs, r_seg_off, nr_expected: int, seg_bits: int,
+                               out_capacity: int, skip_bits: int, ws, outs, out_rows, abort=None):
+        """b2_join_pairs_seg_cap_dev: l_pairs / r_pairs are whole receive BUFFERS (their sizes are
+        capacities); the rows really there are the last entries of the segment tables, on the device."""
+        ptr, nbytes = self._aligned(ws)
+        self._ck(self._lib.b2_join_pairs_seg_cap_dev(
+            self._h, _dptr(l_pairs), _dptr(l_seg_off), l_pairs.numel(), _dptr(r_pairs), _dptr(r_seg_off),
+            r_pairs.numel(), int(nr_expected), seg_bits, _dptr(outs[0]), _dptr(outs[1]), _dptr(outs[2]),
+            int(out_capacity), _dptr(out_rows), skip_bits, None if abort is None else _dptr(abort), ptr, nbytes,
+            self._stream()), "b2_join_pairs_seg_cap_dev")
+        return outs[0], outs[1], outs[2], out_rows
 
     def join_seg_ws_bytes(self, nl: int, nr: int, skip_bits: int, seg_bits: int) -> int:
         return int(self._lib.b2_join_seg_ws_bytes(nl, nr, skip_bits, seg_bits))
@@ -645,6 +682,73 @@ def join_dest_rank(key: int, nranks: int) -> int:
 # ---------------------------------------------------------------------------------------------
 # operators (host batches in, host results out) — the reference's *Dpu classes
 # ---------------------------------------------------------------------------------------------
+class DeviceSet:
+    """The GPUs of one node behind one handle (b2_set): what ``dpu::DpuSet::allocate(nr_dpus)``
+    (dpuext.hpp:704-739) is to the reference's operators. Pass it to FilterGpu / SumGpu / TakeGpu /
+    JoinGpu in place of a Context: filter, sum and take shard by batch range, the join runs the fused
+    peer-memory shuffle over NVLink — all inside libb200olap.so, one host process, no torch."""
+
+    _SET_OPS = {"sum_u32_host", "filter_lt_u32_host", "filter_fetch_host", "take_u32_host", "join_u32_host",
+                "join_fetch_host"}
+
+    def __init__(self, devices: Sequence[int] | int | None = None):
+        self._lib = _lib.lib()
+        if devices is None:
+            n = C.c_int(0)
+            check(self._lib.b2_device_count(C.byref(n)), "b2_device_count")
+            devices = list(range(n.value))
+        elif isinstance(devices, int):
+            devices = list(range(devices))
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        check(self._lib.b2_set_create(arr, len(devices), C.byref(h)), "b2_set_create")
+        self._h = h
+        self.devices = list(devices)
+        self.members = [Context(_borrowed=self._lib.b2_set_ctx(h, i)) for i in range(len(devices))]
+
+    def __len__(self) -> int:
+        return len(self.devices)
+
+    @property
+    def peer_access(self) -> bool:
+        return bool(self._lib.b2_set_peer_access(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.b2_set_launch_count(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            for m in self.members:
+                m.close()
+            self._lib.b2_set_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, status: int, where: str) -> None:
+        if status != _lib.B2_OK:
+            raise B2Error(status, where, self._lib.b2_set_last_error(self._h).decode(errors="replace"))
+
+    def _call(self, name: str, *args) -> None:
+        """b2_set_<name>(set, ...) where the set shards the operator; otherwise (nullable / typed /
+        64-bit variants) the entry point of member 0."""
+        if name in self._SET_OPS:
+            self._ck(getattr(self._lib, "b2_set_" + name)(self._h, *args), "b2_set_" + name)
+        else:
+            self.members[0]._call(name, *args)
+
+
 FILTER_THRESHOLD = 1 << 30  # predicate v < 2^30: filter.c:25, filter_native.cc:59
 
 
@@ -671,9 +775,8 @@ class FilterGpu:
         counts = (C.c_int64 * max(tab.n, 1))()
         total = C.c_uint64(0)
         t1 = Timings()
-        lib, h = self.ctx._lib, self.ctx._h
-        self.ctx._ck(lib.b2_filter_lt_u32_host(h, tab.ptrs, tab.lens, tab.n, self.threshold, counts,
-                                               C.byref(total), C.byref(t1)), "b2_filter_lt_u32_host")
+        self.ctx._call("filter_lt_u32_host", tab.ptrs, tab.lens, tab.n, self.threshold, counts, C.byref(total),
+                       C.byref(t1))
         return tab, counts, total.value, t1
 
     def Run(self) -> int:
@@ -688,10 +791,9 @@ class FilterGpu:
         total = C.c_uint64(0)
         flat = np.empty(sum(a.size for a in self._cols), dtype=self.dtype)
         t = Timings()
-        self.ctx._ck(self.ctx._lib.b2_filter_lt_32_host_into(
-            self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n, _DTYPES32[self.dtype],
-            _threshold_bits(self.threshold, self.dtype), flat.ctypes.data, flat.size, counts, C.byref(total),
-            C.byref(t)), "b2_filter_lt_32_host_into")
+        self.ctx._call("filter_lt_32_host_into", tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n,
+                       _DTYPES32[self.dtype], _threshold_bits(self.threshold, self.dtype), flat.ctypes.data, flat.size,
+                       counts, C.byref(total), C.byref(t))
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         if _count_only:
@@ -712,8 +814,7 @@ class FilterGpu:
             ptrs[b] = flat.ctypes.data + 4 * off
             off += counts[b]
         t2 = Timings()
-        self.ctx._ck(self.ctx._lib.b2_filter_fetch_host(self.ctx._h, ptrs, tab.n, C.byref(t2)),
-                     "b2_filter_fetch_host")
+        self.ctx._call("filter_fetch_host", ptrs, tab.n, C.byref(t2))
         self._timers = Timers.from_timings(t1, t2)
         self._last = (t1, t2)
         if _count_only:
@@ -749,14 +850,12 @@ class SumGpu:
         t = Timings()
         if self.dtype in _DTYPES64:
             out = AggrResult64()
-            self.ctx._ck(self.ctx._lib.b2_aggr_64_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
-                                                       tab.lens, tab.n, _DTYPES64[self.dtype], C.byref(out),
-                                                       C.byref(t)), "b2_aggr_64_host")
+            self.ctx._call("aggr_64_host", tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n,
+                           _DTYPES64[self.dtype], C.byref(out), C.byref(t))
         else:
             out = AggrResult()
-            self.ctx._ck(self.ctx._lib.b2_aggr_32_host(self.ctx._h, tab.ptrs, self._valid.ptrs, self._valid.offs,
-                                                       tab.lens, tab.n, _DTYPES32[self.dtype], C.byref(out),
-                                                       C.byref(t)), "b2_aggr_32_host")
+            self.ctx._call("aggr_32_host", tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n,
+                           _DTYPES32[self.dtype], C.byref(out), C.byref(t))
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         return out.as_dict(self.dtype)
@@ -768,8 +867,7 @@ class SumGpu:
         tab = _PtrTable(self._cols)
         out = C.c_uint64(0)
         t = Timings()
-        self.ctx._ck(self.ctx._lib.b2_sum_u32_host(self.ctx._h, tab.ptrs, tab.lens, tab.n, C.byref(out),
-                                                   C.byref(t)), "b2_sum_u32_host")
+        self.ctx._call("sum_u32_host", tab.ptrs, tab.lens, tab.n, C.byref(out), C.byref(t))
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         return int(out.value)
@@ -810,9 +908,8 @@ class TakeGpu:
         optrs = (C.c_void_p * max(i.n, 1))(*[o.ctypes.data for o in outs])
         bptrs = (C.c_void_p * max(i.n, 1))(*[b.ctypes.data for b in bits])
         t = Timings()
-        self.ctx._ck(self.ctx._lib.b2_take_u32_nullable_host(
-            self.ctx._h, v.ptrs, self._vvalid.ptrs, self._vvalid.offs, v.lens, i.ptrs, self._ivalid.ptrs,
-            self._ivalid.offs, i.lens, i.n, optrs, bptrs, C.byref(t)), "b2_take_u32_nullable_host")
+        self.ctx._call("take_u32_nullable_host", v.ptrs, self._vvalid.ptrs, self._vvalid.offs, v.lens, i.ptrs,
+                       self._ivalid.ptrs, self._ivalid.offs, i.lens, i.n, optrs, bptrs, C.byref(t))
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         return [_to_arrow(o, b) for o, b in zip(outs, bits)]
@@ -833,11 +930,9 @@ class TakeGpu:
             bounds.append(bounds[-1] + a.size)
         t = Timings()
         if wide:
-            self.ctx._ck(self.ctx._lib.b2_take_64_host(self.ctx._h, v.ptrs, v.lens, i.ptrs, i.lens, i.n,
-                                                       ptrs, C.byref(t)), "b2_take_64_host")
+            self.ctx._call("take_64_host", v.ptrs, v.lens, i.ptrs, i.lens, i.n, ptrs, C.byref(t))
         else:
-            self.ctx._ck(self.ctx._lib.b2_take_u32_host(self.ctx._h, v.ptrs, v.lens, i.ptrs, i.lens, i.n,
-                                                        ptrs, C.byref(t)), "b2_take_u32_host")
+            self.ctx._call("take_u32_host", v.ptrs, v.lens, i.ptrs, i.lens, i.n, ptrs, C.byref(t))
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         return [flat[bounds[b]:bounds[b + 1]] for b in range(i.n)]
@@ -877,13 +972,10 @@ class JoinGpu:
         nlb, nrb = len(self._l[0]), len(self._r[0])
         rows = C.c_uint64(0)
         t1, t2 = Timings(), Timings()
-        lib, h = self.ctx._lib, self.ctx._h
-        self.ctx._ck(lib.b2_join_u32_host(h, lt.ptrs, lt.lens, nlb, rt.ptrs, rt.lens, nrb,
-                                          C.byref(rows), C.byref(t1)), "b2_join_u32_host")
+        self.ctx._call("join_u32_host", lt.ptrs, lt.lens, nlb, rt.ptrs, rt.lens, nrb, C.byref(rows), C.byref(t1))
         n = int(rows.value)
         out = [np.empty(n, dtype=np.uint32) for _ in range(3)]
-        self.ctx._ck(lib.b2_join_fetch_host(h, out[0].ctypes.data, out[1].ctypes.data,
-                                            out[2].ctypes.data, n, C.byref(t2)), "b2_join_fetch_host")
+        self.ctx._call("join_fetch_host", out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, n, C.byref(t2))
         self._timers = Timers.from_timings(t1, t2)
         self._last = (t1, t2)
         return {self.fk: out[0], self.lpay: out[1], self.rpay: out[2]}
@@ -898,10 +990,9 @@ class JoinGpu:
 
         lt, rt = _PtrTable(self._l[0] + self._l[1]), _PtrTable(self._r[0] + self._r[1])
         out, t = _Aggr(), Timings()
-        self.ctx._ck(self.ctx._lib.b2_join_aggr_u32_host(
-            self.ctx._h, lt.ptrs, lt.lens, len(self._l[0]), rt.ptrs, rt.lens, len(self._r[0]),
-            0 if y_threshold is None else 1, 0 if y_threshold is None else int(y_threshold),
-            C.byref(out), C.byref(t)), "b2_join_aggr_u32_host")
+        self.ctx._call("join_aggr_u32_host", lt.ptrs, lt.lens, len(self._l[0]), rt.ptrs, rt.lens, len(self._r[0]),
+                       0 if y_threshold is None else 1, 0 if y_threshold is None else int(y_threshold),
+                       C.byref(out), C.byref(t))
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         return {"rows": int(out.rows), f"sum_{self.lpay}": int(out.sum_y), f"sum_{self.rpay}": int(out.sum_x)}
@@ -936,16 +1027,14 @@ class PartitionGpu:
         lens = (C.c_int64 * max(self._nb, 1))(*[int(a.size) for a in self._cols[names[0]]])
         rows = (C.c_int64 * self.nparts)()
         t1, t2 = Timings(), Timings()
-        lib, h = self.ctx._lib, self.ctx._h
-        self.ctx._ck(lib.b2_partition_u32_host(h, tab.ptrs, lens, self._nb, ncols, names.index(self.key),
-                                               self.nparts, rows, C.byref(t1)), "b2_partition_u32_host")
+        self.ctx._call("partition_u32_host", tab.ptrs, lens, self._nb, ncols, names.index(self.key), self.nparts, rows,
+                       C.byref(t1))
         outs = [{n: np.empty(rows[p], dtype=np.uint32) for n in names} for p in range(self.nparts)]
         ptrs = (C.c_void_p * (self.nparts * ncols))()
         for p in range(self.nparts):
             for c, n in enumerate(names):
                 ptrs[p * ncols + c] = outs[p][n].ctypes.data
-        self.ctx._ck(lib.b2_partition_fetch_host(h, ptrs, self.nparts, ncols, C.byref(t2)),
-                     "b2_partition_fetch_host")
+        self.ctx._call("partition_fetch_host", ptrs, self.nparts, ncols, C.byref(t2))
         self._timers = Timers.from_timings(t1, t2)
         self._last = (t1, t2)
         return outs

@@ -186,21 +186,30 @@ class P2PShuffleJoin:
     """Sharded join whose exchange is FUSED into the routing kernel: every rank scatters its
     (key, payload) pairs straight into the peers' receive buffers with NVLink stores
     (b2_shuffle_p2p_scatter_dev), already grouped into coarse partitions, so there is no separate
-    all-to-all and the receiver skips its first partitioning pass (b2_join_pairs_seg_dev).
+    all-to-all and the receiver skips its first partitioning pass (b2_join_pairs_seg_cap_dev).
+
+    One step enqueues, with NO host synchronisation and no eager tensor arithmetic in between:
+      count L, count R | all-gather of the 2 x 1025 boundaries (also the "everyone has read its
+      receive buffers" barrier) | b2_shuffle_p2p_plan_dev x 2 (addresses, coarse boundaries, the
+      collective overflow flag — all on the device) | scatter L, scatter R over NVLink | barrier |
+      local join of the receive BUFFERS (row counts stay on the device).
     Receive buffers are torch symmetric-memory allocations; their peer addresses come from the
-    rendezvous handle. Collectives left: one all-gather of 2 x 1024 counts and one barrier."""
+    rendezvous handle. This class is plumbing only: every kernel is behind include/b200olap.h."""
 
     BITS = 10  # log2(G) destination bits + coarse bits: one radix pass
 
-    def __init__(self, ctx, dist, rank: int, world: int, n_local: int, capacity: int):
+    def __init__(self, ctx, dist, rank: int, world: int, n_local: int, capacity: int, n_build_total: int | None = None):
         import torch
         import torch.distributed._symmetric_memory as symm
         self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
         self.skip = log2_exact(world)
         self.seg_bits = self.BITS - self.skip
         self.capacity = capacity
+        # build rows a rank receives when the hash spreads evenly: picks the fine partition count
+        self.nr_expected = (n_build_total if n_build_total is not None else n_local * world) // world
         dev = torch.device("cuda", torch.cuda.current_device())
         group = dist.group.WORLD.group_name
+        B = 1 << self.BITS
         self.recv, self.peers = [], []
         for _ in range(2):  # L, R
             t = symm.empty(capacity, dtype=torch.int64, device=dev)
@@ -209,14 +218,36 @@ class P2PShuffleJoin:
             self.peers.append(torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev))
         nbytes = ctx.shuffle_p2p_ws_bytes(n_local, self.BITS) + 256
         self.ws = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-        self.off = [torch.empty((1 << self.BITS) + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.my_off = torch.zeros((2, B + 1), dtype=torch.int64, device=dev)       # count kernels write here
+        self.all_off = torch.zeros((world, 2, B + 1), dtype=torch.int64, device=dev)  # after the all-gather
+        base = self.all_off.data_ptr()
+        stride_rank, stride_side = 2 * (B + 1) * 8, (B + 1) * 8
+        self.off_ptrs = [torch.tensor([base + s * stride_rank + side * stride_side for s in range(world)],
+                                      dtype=torch.int64, device=dev) for side in range(2)]
+        self.addr = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.seg = [torch.empty((1 << self.seg_bits) + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.info = torch.zeros((2, 3), dtype=torch.int64, device=dev)  # {received, max over ranks, overflow} x side
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.last_recv = (0, 0)
 
+    @property
+    def abort(self):
+        """int64[1] device view: non-zero = a receive buffer would have overflowed (on every rank)."""
+        return self.info[1, 2:3]
+
+    def received(self) -> tuple[int, int]:
+        """(L rows, R rows) this rank received in the last step — a host read, for reports only."""
+        h = self.info.cpu()
+        if int(h[1, 2]):
+            raise OverflowError(f"a rank would receive {int(max(h[0, 1], h[1, 1]))} rows, capacity "
+                                f"{self.capacity} (skewed keys); raised on every rank")
+        self.last_recv = (int(h[0, 0]), int(h[1, 0]))
+        return self.last_recv
+
     def step(self, fk, y, pk, x, local_join, phases: dict | None = None):
-        """local_join(l_pairs, l_seg_off, r_pairs, r_seg_off, seg_bits, skip_bits) -> result.
-        phases: if given, every phase is synchronised and its wall time (ms) stored there
-        (diagnostics only — the synchronisation removes all overlap)."""
+        """local_join(l_buf, l_seg_off, r_buf, r_seg_off, nr_expected, seg_bits, skip_bits, abort) -> result,
+        e.g. ctx.join_pairs_seg_cap_dev. phases: if given, every phase is synchronised and its wall
+        time (ms) stored there (diagnostics only — the synchronisation removes all overlap)."""
         import time
 
         import torch
@@ -233,27 +264,22 @@ class P2PShuffleJoin:
         if phases is not None:
             torch.cuda.synchronize()
             t0[0] = time.perf_counter()
-        ctx.shuffle_p2p_count_dev(fk, self.BITS, self.ws[0], self.off[0])
-        ctx.shuffle_p2p_count_dev(pk, self.BITS, self.ws[1], self.off[1])
+        ctx.shuffle_p2p_count_dev(fk, self.BITS, self.ws[0], self.my_off[0])
+        ctx.shuffle_p2p_count_dev(pk, self.BITS, self.ws[1], self.my_off[1])
         mark("count")
-        counts = torch.stack([self.off[0][1:] - self.off[0][:-1], self.off[1][1:] - self.off[1][:-1]])
-        allc = torch.empty((G,) + tuple(counts.shape), dtype=torch.int64, device=counts.device)
         # also a barrier: nobody scatters before every rank is done reading its receive buffers
-        self.dist.all_gather_into_tensor(allc, counts)
-        plans = [p2p_plan(allc[:, side, :].contiguous(), self.peers[side], self.rank, G) for side in range(2)]
-        sizes = torch.stack([plans[0][2], plans[1][2], plans[0][3], plans[1][3]]).cpu().tolist()
-        if max(sizes[2], sizes[3]) > self.capacity:
-            raise OverflowError(f"rank {self.rank}: a rank would receive {max(sizes[2], sizes[3])} rows, "
-                                f"capacity {self.capacity} (skewed keys)")
+        self.dist.all_gather_into_tensor(self.all_off.view(-1), self.my_off.view(-1))
+        ctx.shuffle_p2p_plan_dev(self.off_ptrs[0], self.peers[0], self.rank, G, self.BITS, self.capacity,
+                                 self.addr[0], self.seg[0], self.info[0])
+        ctx.shuffle_p2p_plan_dev(self.off_ptrs[1], self.peers[1], self.rank, G, self.BITS, self.capacity,
+                                 self.addr[1], self.seg[1], self.info[1], prev_abort=self.info[0, 2:3])
         mark("allgather+plan")
-        ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, plans[0][0], self.ws[0])
-        ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, plans[1][0], self.ws[1])
+        ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, self.addr[0], self.ws[0], abort=self.info[0, 2:3])
+        ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[1], self.ws[1], abort=self.abort)
         mark("scatter_nvlink")
         self.dist.all_reduce(self.flag)  # every rank's stores have landed when this completes
         mark("barrier")
-        nl, nr = int(sizes[0]), int(sizes[1])
-        self.last_recv = (nl, nr)
-        out = local_join(self.recv[0][:nl], plans[0][1], self.recv[1][:nr], plans[1][1], self.seg_bits,
-                         self.skip)
+        out = local_join(self.recv[0], self.seg[0], self.recv[1], self.seg[1], self.nr_expected, self.seg_bits,
+                         self.skip, self.abort)
         mark("local_join")
         return out

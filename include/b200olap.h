@@ -95,6 +95,52 @@ enum b2_tunable {
 int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value);
 int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value);
 
+/* ---- device set: the GPUs of one node behind ONE handle ----------------------------------------
+ * Replaces dpu::DpuSet::allocate(nr_dpus) (host/dpuext/dpuext.hpp:704-739): the reference's set owns
+ * every DPU and its operators iterate over them (filter_dpu.cc:127 "batch i -> DPU i"; join_dpu.cc:254
+ * groups of nr_dpus partitions, repartitioned through the HOST, partitioner.cc:350-375). A b2_set owns
+ * one b2_ctx per GPU of ONE process and enables peer access between them:
+ *   - filter / sum / take shard by contiguous batch ranges (one host thread per GPU drives that GPU's
+ *     own pipelined host entry point; no data-path collective);
+ *   - the join routes both sides by the top log2(N) hash bits with the fused peer-store shuffle
+ *     (count -> b2_shuffle_p2p_plan_dev over peer pointers -> NVLink scatter -> local join), ordered
+ *     by CUDA events across devices: no NCCL, no host synchronisation between count and local join.
+ * devices == NULL means 0..n-1. The join needs n to be a power of two and peer access between all
+ * members (b2_set_peer_access); the range-sharded operators take any n. Same threading rule as a
+ * ctx: one host thread per set. b2_set_ctx hands out the member contexts for the *_dev / single-GPU
+ * entry points. Timings: phases of concurrently running members overlap, so the *_ms fields are the
+ * maximum over members, bytes and launches the sum. */
+typedef struct b2_set b2_set;
+int b2_set_create(const int* devices, int n, b2_set** out);
+int b2_set_destroy(b2_set* set);
+int b2_set_size(const b2_set* set);
+b2_ctx* b2_set_ctx(b2_set* set, int i);
+int b2_set_peer_access(const b2_set* set);
+const char* b2_set_last_error(const b2_set* set);
+int64_t b2_set_launch_count(const b2_set* set);
+int b2_set_set_inputs_pinned(b2_set* set, int on);
+/* SumDpu::Run over the whole set (aggr_dpu.cc:31-89; one partial per device added on the host, :82-84). */
+int b2_set_sum_u32_host(b2_set* set, const uint32_t* const* batch_ptrs, const int64_t* batch_lens, int64_t nbatches,
+                        uint64_t* sum, b2_timings* timings);
+/* FilterDpu over the whole set; arguments as b2_filter_lt_u32_host / b2_filter_fetch_host. */
+int b2_set_filter_lt_u32_host(b2_set* set, const uint32_t* const* batch_ptrs, const int64_t* batch_lens,
+                              int64_t nbatches, uint32_t threshold, int64_t* out_counts, uint64_t* total,
+                              b2_timings* timings);
+int b2_set_filter_fetch_host(b2_set* set, uint32_t* const* out_ptrs, int64_t nbatches, b2_timings* timings);
+/* TakeDpu over the whole set; arguments as b2_take_u32_host. */
+int b2_set_take_u32_host(b2_set* set, const uint32_t* const* value_ptrs, const int64_t* value_lens,
+                         const uint32_t* const* idx_ptrs, const int64_t* idx_lens, int64_t nbatches,
+                         uint32_t* const* out_ptrs, b2_timings* timings);
+/* JoinDpu::Run over the whole set; arguments as b2_join_u32_host / b2_join_fetch_host. The result is
+ * fetched GPU by GPU into out_*[0 .. rows) (row order unspecified, as JoinDpu's). Skewed keys that
+ * overflow a receive buffer make the set grow its buffers and repeat the exchange; duplicate build keys
+ * that overflow a GPU's output columns make that GPU repeat its local join with the exact capacity. */
+int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                         const uint32_t* const* r_ptrs, const int64_t* r_lens, int64_t nr_batches,
+                         uint64_t* out_rows, b2_timings* timings);
+int b2_set_join_fetch_host(b2_set* set, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x, int64_t capacity_rows,
+                           b2_timings* timings);
+
 /* ---- pinned host memory (zero-copy Arrow interop at the boundary) -------------------------- */
 /* Arrow buffers live in pageable memory; copies from/to them run at a fraction of the PCIe rate.
  * b2_host_register page-locks an EXISTING buffer in place (e.g. the data buffers of the input
@@ -432,9 +478,29 @@ int b2_shuffle_partition_u32_dev(b2_ctx* ctx, const uint32_t* d_key, const uint3
 size_t b2_shuffle_p2p_ws_bytes(int64_t n, int bits);
 int b2_shuffle_p2p_count_dev(b2_ctx* ctx, const uint32_t* d_key, int64_t n, int bits, int64_t* d_bucket_off,
                              void* d_ws, size_t ws_bytes, void* stream);
+/* Step 2a, on the device: turns every rank's bucket boundaries into THIS rank's destination
+ * addresses (one launch; no host round trip, no eager tensor arithmetic on the step's critical path).
+ *   d_off_ptrs   device array of nranks pointers; entry s -> int64[2^bits + 1], the d_bucket_off of
+ *                source rank s (local copies after an all-gather, or peer pointers inside one process)
+ *   d_recv_base  device array of nranks byte addresses: every rank's receive buffer as THIS rank
+ *                addresses it (CUDA IPC / peer pointers). Layout of a receive buffer: bucket-major,
+ *                source-rank-minor, so every coarse bucket is contiguous
+ *   capacity_rows rows a receive buffer holds
+ * Outputs (device): d_bucket_addr uint64[2^bits] for b2_shuffle_p2p_scatter_dev; d_seg_off
+ * int64[2^(bits - log2 nranks) + 1], boundaries of the coarse buckets THIS rank receives; d_info
+ * int64[3] = {rows this rank receives, largest receive count of any rank, overflow flag}. When any
+ * rank would receive more than capacity_rows the flag is 1 on EVERY rank (all see the same counts),
+ * d_seg_off is all zero, and a scatter / join given &d_info[2] as d_abort stores nothing / reports ~0
+ * rows: skew surfaces as an error on all ranks instead of a buffer overrun on one.
+ * d_prev_abort (may be NULL): an earlier plan's flag, OR-ed into this one — plan the probe side with
+ * NULL, the build side with the probe side's &d_info[2], and hand the build side's flag to the join. */
+int b2_shuffle_p2p_plan_dev(b2_ctx* ctx, const int64_t* const* d_off_ptrs, const uint64_t* d_recv_base, int rank,
+                            int nranks, int bits, int64_t capacity_rows, uint64_t* d_bucket_addr,
+                            int64_t* d_seg_off, int64_t* d_info, const int64_t* d_prev_abort, void* stream);
+/* d_abort (may be NULL): device int64; non-zero = store nothing (see b2_shuffle_p2p_plan_dev). */
 int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
-                               int bits, const uint64_t* d_bucket_addr, void* d_ws, size_t ws_bytes,
-                               void* stream);
+                               int bits, const uint64_t* d_bucket_addr, const int64_t* d_abort, void* d_ws,
+                               size_t ws_bytes, void* stream);
 /* Join of sides that are already grouped into 2^seg_bits coarse buckets on hash bits
  * [hash_skip_bits, hash_skip_bits + seg_bits); d_*_seg_off (int64, 2^seg_bits + 1, device) hold the
  * bucket boundaries in rows. Same output contract as b2_join_pairs_dev. One fine pass refines a
@@ -446,6 +512,19 @@ int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t*
                           uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
                           uint64_t* d_out_rows, int hash_skip_bits, void* d_ws, size_t ws_bytes,
                           void* stream);
+
+/* The same join when the caller only knows CAPACITIES of its receive buffers (the fused shuffle
+ * without a host read-back): nl_cap / nr_cap bound the rows (the real counts are the last entries of
+ * the segment tables, on the device), nr_expected (the build rows a rank receives when the hash
+ * spreads evenly; 0 = nr_cap) picks the number of fine partitions. d_abort (may be NULL): device
+ * int64, non-zero = the exchange was called off, *d_out_rows = UINT64_MAX. */
+size_t b2_join_seg_cap_ws_bytes(int64_t nl_cap, int64_t nr_cap, int64_t nr_expected, int hash_skip_bits,
+                                int seg_bits);
+int b2_join_pairs_seg_cap_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl_cap,
+                              const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr_cap,
+                              int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
+                              uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
+                              const int64_t* d_abort, void* d_ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

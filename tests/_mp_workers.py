@@ -40,11 +40,12 @@ def p2p_join_worker(rank: int, world: int, port: int, nb_total: int, batch: int,
         pj = P2PShuffleJoin(ctx, dist, rank, world, n, cap)
         outs = [torch.empty(cap * mult, dtype=torch.int32, device="cuda") for _ in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
-        jws = torch.empty(ctx.join_seg_ws_bytes(cap, cap, pj.skip, pj.seg_bits) + 256, dtype=torch.uint8, device="cuda")
+        jws = torch.empty(ctx.join_seg_cap_ws_bytes(cap, cap, pj.nr_expected, pj.skip, pj.seg_bits) + 256,
+                          dtype=torch.uint8, device="cuda")
 
-        def local_join(lr, lseg, rr, rseg, seg_bits, skip_bits):
-            ctx.join_pairs_seg_dev(lr, lseg, rr, rseg, seg_bits, out_capacity=cap * mult, skip_bits=skip_bits,
-                                   ws=jws, outs=outs, out_rows=rows_t)
+        def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort):
+            ctx.join_pairs_seg_cap_dev(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, out_capacity=cap * mult,
+                                       skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t, abort=abort)
 
         for _ in range(3):  # repeated steps reuse the receive buffers: the barrier protocol must hold
             outs[0].zero_()

@@ -767,3 +767,83 @@ def test_second_device_in_the_same_process(ctx):
         assert np.array_equal(host(out)[:n], oracle.filter_lt(v))
         assert int(rows.cpu()[0]) == fk.size
         c1.close()
+
+
+@pytest.mark.parametrize("G,rows_per_rank", [(2, 60_000), (8, 30_000), (1, 20_000)])
+def test_p2p_plan_kernel_and_capacity_join_virtual_ranks(ctx, G, rows_per_rank):
+    """The device-side plan (b2_shuffle_p2p_plan_dev) must equal sharded.p2p_plan, and the whole step
+    — count, plan, scatter, join of the receive BUFFERS by capacity — must equal the oracle join with
+    nothing read back in between. A capacity that is too small must call the exchange off on the
+    device: nothing stored, ~0 rows."""
+    from dpu_olap_b200.sharded import log2_exact, p2p_plan
+    BITS = 10
+    B = 1 << BITS
+    skip = log2_exact(G)
+    seg_bits = BITS - skip
+    rng = np.random.default_rng(100 + G)
+    n = G * rows_per_rank
+    pk = rng.permutation(np.arange(n, dtype=np.uint32) * 5 + 1)
+    x = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    fk = pk[rng.integers(0, n, size=n)]
+    fk[:50] = 2  # no match
+    y = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    sl = lambda a, r: a[r * rows_per_rank:(r + 1) * rows_per_rank]
+    d = {r: [dev(sl(a, r)) for a in (fk, y, pk, x)] for r in range(G)}
+    wss = {(r, s): torch.empty(ctx.shuffle_p2p_ws_bytes(rows_per_rank, BITS) + 256, dtype=torch.uint8, device="cuda")
+           for r in range(G) for s in range(2)}
+    all_off = torch.zeros((G, 2, B + 1), dtype=torch.int64, device="cuda")
+    for r in range(G):
+        ctx.shuffle_p2p_count_dev(d[r][0], BITS, wss[r, 0], all_off[r, 0])
+        ctx.shuffle_p2p_count_dev(d[r][2], BITS, wss[r, 1], all_off[r, 1])
+    off_ptrs = [torch.tensor([all_off[s, side].data_ptr() for s in range(G)], dtype=torch.int64, device="cuda")
+                for side in range(2)]
+    for cap in (rows_per_rank * 2 + 1024, rows_per_rank // 2):
+        recv = [[torch.full((max(cap, 1),), -1, dtype=torch.int64, device="cuda") for _ in range(G)] for _ in range(2)]
+        peers = [torch.tensor([t.data_ptr() for t in recv[s]], dtype=torch.int64, device="cuda") for s in range(2)]
+        addr = {(r, s): torch.empty(B, dtype=torch.int64, device="cuda") for r in range(G) for s in range(2)}
+        seg = {(r, s): torch.empty((1 << seg_bits) + 1, dtype=torch.int64, device="cuda") for r in range(G) for s in range(2)}
+        info = {r: torch.zeros((2, 3), dtype=torch.int64, device="cuda") for r in range(G)}
+        for r in range(G):
+            ctx.shuffle_p2p_plan_dev(off_ptrs[0], peers[0], r, G, BITS, cap, addr[r, 0], seg[r, 0], info[r][0])
+            ctx.shuffle_p2p_plan_dev(off_ptrs[1], peers[1], r, G, BITS, cap, addr[r, 1], seg[r, 1], info[r][1],
+                                     prev_abort=info[r][0, 2:3])
+        for r in range(G):
+            ctx.shuffle_p2p_scatter_dev(d[r][0], d[r][1], BITS, addr[r, 0], wss[r, 0], abort=info[r][0, 2:3])
+            ctx.shuffle_p2p_scatter_dev(d[r][2], d[r][3], BITS, addr[r, 1], wss[r, 1], abort=info[r][1, 2:3])
+        torch.cuda.synchronize()
+        counts = [all_off[:, s, 1:] - all_off[:, s, :-1] for s in range(2)]
+        overflow = cap < rows_per_rank
+        for r in range(G):
+            for s in range(2):
+                t_addr, t_seg, t_n, t_max = p2p_plan(counts[s].contiguous(), peers[s], r, G)
+                assert torch.equal(addr[r, s], t_addr)
+                h = info[r][s].cpu().tolist()
+                assert h[1] == int(t_max)
+                if not overflow:
+                    assert torch.equal(seg[r, s], t_seg) and h[0] == int(t_n) and h[2] == 0
+                else:
+                    assert h[2] == 1 and h[0] == 0 and int(seg[r, s].abs().sum()) == 0
+        got = [[], [], []]
+        for r in range(G):
+            nr_expected = n // G
+            ws = torch.empty(ctx.join_seg_cap_ws_bytes(max(cap, 1), max(cap, 1), nr_expected, skip, seg_bits) + 256,
+                             dtype=torch.uint8, device="cuda")
+            outs = [torch.empty(max(cap, 1), dtype=torch.int32, device="cuda") for _ in range(3)]
+            rows = torch.zeros(1, dtype=torch.int64, device="cuda")
+            ctx.join_pairs_seg_cap_dev(recv[0][r], seg[r, 0], recv[1][r], seg[r, 1], nr_expected, seg_bits,
+                                       out_capacity=max(cap, 1), skip_bits=skip, ws=ws, outs=outs, out_rows=rows,
+                                       abort=info[r][1, 2:3])
+            torch.cuda.synchronize()
+            m = int(rows.cpu().numpy().view(np.uint64)[0])
+            if overflow:
+                assert m == 0xFFFFFFFFFFFFFFFF
+                assert all(int((t != -1).sum()) == 0 for t in (recv[0][r], recv[1][r]))  # nothing was stored
+                continue
+            for i, t in enumerate(outs):
+                got[i].append(host(t)[:m])
+        if not overflow:
+            got = oracle.sort_rows(*[np.concatenate(g) for g in got])
+            exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))
+            assert got[0].size == exp[0].size
+            for a, b in zip(got, exp):
+                assert np.array_equal(a, b)
