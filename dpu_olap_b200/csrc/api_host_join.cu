@@ -2,6 +2,7 @@
 // (host/partition/partition_dpu.cc:31-135) and JoinDpu::Run (host/join/join_dpu.cc:158-400) did
 // with DpuSet transfers. Columns are uploaded once, the whole operator runs on the device, and
 // the result stays there until the caller — who can only size its buffers afterwards — fetches it.
+#include <algorithm>
 #include <chrono>
 #include <vector>
 
@@ -335,6 +336,155 @@ int b2_join_aggr_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int6
   tm.d2h_bytes = sizeof(b2_join_aggr);
   tm.total_ms = ms_since(t0);
   tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+// ---- join over any number of payload columns per side (JoinDpu partitions every left value column,
+// join_dpu.cc:127-138, and takes every right non-key column, :325-341) ------------------------------
+// One payload per side travels inside the (key, payload) pair (the benchmark shape: no index vector,
+// no take pass). With more, the pair carries the ROW NUMBER instead and every payload column is
+// gathered afterwards with the take kernel — the reference's own scheme (selection_indices_vector +
+// TakeKernel), minus the host round trips between the steps.
+int b2_join_cols_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                          int nl_payloads, const uint32_t* const* r_ptrs, const int64_t* r_lens, int64_t nr_batches,
+                          int nr_payloads, uint64_t* out_rows, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, nl_payloads >= 0 && nl_payloads <= 64 && nr_payloads >= 0 && nr_payloads <= 64,
+             "0..64 payload columns per side");
+  if (nl_payloads == 1 && nr_payloads == 1)
+    return b2_join_u32_host(ctx, l_ptrs, l_lens, nl_batches, r_ptrs, r_lens, nr_batches, out_rows, timings);
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, nl_batches >= 0 && nr_batches >= 0 && out_rows != nullptr, "bad arguments");
+  B2_REQUIRE(ctx, nl_batches == 0 || (l_ptrs && l_lens), "null left batch table");
+  B2_REQUIRE(ctx, nr_batches == 0 || (r_ptrs && r_lens), "null right batch table");
+  int64_t nl = 0, nr = 0;
+  B2_RETURN_NOT_OK(total_rows(ctx, l_lens, nl_batches, &nl));
+  B2_RETURN_NOT_OK(total_rows(ctx, r_lens, nr_batches, &nr));
+  B2_REQUIRE(ctx, nl < (1ll << 32) && nr < (1ll << 32), "row numbers travel as uint32: at most 2^32 - 1 rows per side");
+  b2_timings tm{};
+  DevBufs bufs;
+  EventPair up, work;
+  B2_RETURN_NOT_OK(up.init(ctx));
+  B2_RETURN_NOT_OK(work.init(ctx));
+  cudaStream_t s = ctx->s_compute;
+  uint32_t *d_fk, *d_lid, *d_pk, *d_rid;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_fk, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_lid, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_pk, (size_t)nr * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_rid, (size_t)nr * 4));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.a, s));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_fk, l_ptrs, l_lens, nl_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_pk, r_ptrs, r_lens, nr_batches, s, &tm.h2d_bytes));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.b, s));
+  B2_CUDA_OK(ctx, cudaEventRecord(work.a, s));
+  B2_RETURN_NOT_OK(b2_iota_u32_dev(ctx, 0, nl, d_lid, s));
+  B2_RETURN_NOT_OK(b2_iota_u32_dev(ctx, 0, nr, d_rid, s));
+  int64_t cap = nl;
+  void* d_ws = nullptr;
+  const size_t ws_bytes = b2_join_ws_bytes(nl, nr);
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_ws, ws_bytes));
+  uint64_t* d_rows = nullptr;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_rows, 8));
+  uint32_t *o_fk = nullptr, *o_lid = nullptr, *o_rid = nullptr;
+  uint64_t rows = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_fk, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_lid, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_rid, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(b2_join_u32_dev(ctx, d_fk, d_lid, nl, d_pk, d_rid, nr, o_fk, o_lid, o_rid, cap, d_rows, 0, d_ws,
+                                     ws_bytes, s));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(&rows, d_rows, 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    if (rows == ~0ull) return b2_set_error(ctx, B2_ERR_WORKSPACE, "join", "slice overflow");
+    if ((int64_t)rows <= cap) break;
+    if (attempt == 1) return b2_set_error(ctx, B2_ERR_OVERFLOW, "join", "output larger than reported");
+    for (uint32_t* p : {o_fk, o_lid, o_rid}) {
+      bufs.release(p);
+      b2_dev_free(ctx, p);
+    }
+    cap = (int64_t)rows;
+  }
+  // the inputs of the join are no longer needed; the payload columns take their place one at a time
+  for (void* p : {(void*)d_fk, (void*)d_pk, (void*)d_lid, (void*)d_rid, d_ws}) {
+    bufs.release(p);
+    b2_dev_free(ctx, p);
+  }
+  b2_pending* pend = new b2_pending();
+  pend->kind = b2_pending::kJoinCols;
+  pend->rows = rows;
+  pend->d_fk = o_fk;
+  pend->dev.push_back(o_fk);
+  bufs.release(o_fk);
+  ctx->pending = pend;
+  uint32_t* d_col = nullptr;
+  const int64_t side_rows[2] = {nl, nr};
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_col, (size_t)std::max(nl, nr) * 4));
+  for (int side = 0; side < 2; ++side) {
+    const int np = side == 0 ? nl_payloads : nr_payloads;
+    const uint32_t* const* ptrs = side == 0 ? l_ptrs : r_ptrs;
+    const int64_t* lens = side == 0 ? l_lens : r_lens;
+    const int64_t nb = side == 0 ? nl_batches : nr_batches;
+    const uint32_t* ids = side == 0 ? o_lid : o_rid;
+    for (int c = 0; c < np; ++c) {
+      uint32_t* d_out = nullptr;
+      B2_RETURN_NOT_OK(b2_dev_alloc(ctx, (void**)&d_out, (size_t)std::max<uint64_t>(rows, 1) * 4));
+      pend->dev.push_back(d_out);
+      pend->d_cols.push_back(d_out);
+      B2_RETURN_NOT_OK(upload_column(ctx, d_col, ptrs + (size_t)(1 + c) * nb, lens, nb, s, &tm.h2d_bytes));
+      if (rows > 0)  // one "batch" = the whole side: the row numbers are global
+        B2_RETURN_NOT_OK(b2_take_u32_dev(ctx, d_col, side_rows[side], ids, (int64_t)rows, 1, d_out, s));
+    }
+  }
+  B2_CUDA_OK(ctx, cudaEventRecord(work.b, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  pend->ncols = 1 + nl_payloads + nr_payloads;
+  *out_rows = rows;
+  tm.copy_to_dev_ms = up.ms();
+  tm.dev_work_ms = work.ms();  // includes the payload uploads interleaved with the gathers
+  tm.d2h_bytes = 8;
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_join_cols_fetch_host(b2_ctx* ctx, uint32_t* const* out_cols, int ncols, int64_t capacity_rows,
+                            b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  const auto t0 = Clock::now();
+  b2_pending* pend = ctx->pending;
+  B2_REQUIRE(ctx, out_cols != nullptr || ncols == 0, "out_cols is null");
+  if (pend && pend->kind == b2_pending::kJoin && ncols == 3)  // the one-payload fast path ran
+    return b2_join_fetch_host(ctx, out_cols[0], out_cols[1], out_cols[2], capacity_rows, timings);
+  if (!pend || pend->kind != b2_pending::kJoinCols)
+    return b2_set_error(ctx, B2_ERR_INVALID, "b2_join_cols_fetch_host", "no pending join result");
+  B2_REQUIRE(ctx, ncols == pend->ncols, "column count differs from the run");
+  if ((uint64_t)capacity_rows < pend->rows)
+    return b2_set_error(ctx, B2_ERR_OVERFLOW, "b2_join_cols_fetch_host", "capacity_rows < result rows");
+  b2_timings tm{};
+  if (pend->rows > 0) {
+    EventPair ev;
+    B2_RETURN_NOT_OK(ev.init(ctx));
+    cudaStream_t s = ctx->s_copy_out;
+    const size_t bytes = (size_t)pend->rows * 4;
+    B2_CUDA_OK(ctx, cudaEventRecord(ev.a, s));
+    for (int c = 0; c < ncols; ++c) {
+      B2_REQUIRE(ctx, out_cols[c] != nullptr, "null output column");
+      const uint32_t* src = c == 0 ? pend->d_fk : pend->d_cols[(size_t)c - 1];
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(out_cols[c], src, bytes, cudaMemcpyDeviceToHost, s));
+      tm.d2h_bytes += (int64_t)bytes;
+    }
+    B2_CUDA_OK(ctx, cudaEventRecord(ev.b, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    tm.copy_from_dev_ms = ev.ms();
+  }
+  tm.total_ms = ms_since(t0);
   if (timings) *timings = tm;
   return B2_OK;
 }

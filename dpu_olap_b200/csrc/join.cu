@@ -687,8 +687,9 @@ shuffle_plan_kernel(const int64_t* const* __restrict__ off_ptrs, const uint64_t*
     // receive buffers are laid out bucket-major, source-minor: every coarse bucket is contiguous
     bucket_addr[b] = recv_base[dest] + 8ull * (uint64_t)(excl[b] - excl[dest * C] + before);
   }
-  if (b <= C) seg_off[b] = overflow ? 0 : excl[rank * C + b] - excl[rank * C];
-  if (b == 0) {
+  if (b < C) seg_off[b] = overflow ? 0 : excl[rank * C + b] - excl[rank * C];
+  if (b == 0) {  // C can be all 1024 buckets (one rank): the closing boundary has no thread of its own
+    seg_off[C] = overflow ? 0 : excl[(rank + 1) * C] - excl[rank * C];
     info[0] = overflow ? 0 : excl[(rank + 1) * C] - excl[rank * C];
     info[1] = s_max;
     info[2] = overflow ? 1 : 0;

@@ -6,7 +6,7 @@
 
 struct b2_ctx;
 struct b2_pending {
-  enum Kind { kNone, kFilter, kPartition, kJoin } kind = kNone;
+  enum Kind { kNone, kFilter, kPartition, kJoin, kJoinCols } kind = kNone;
   std::vector<void*> dev;          // device allocations owned by the pending result
   // filter
   uint32_t* d_out = nullptr;

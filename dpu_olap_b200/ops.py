@@ -942,43 +942,60 @@ class TakeGpu:
 
 
 class JoinGpu:
-    """JoinDpu (host/join/join_dpu.cc:144-400): inner join L.fk = R.pk, output (fk, y, x).
+    """JoinDpu (host/join/join_dpu.cc:144-400): inner join L.fk = R.pk, output fk + every other
+    column of both sides (JoinNative drops pk, join_native.cc:75).
 
-    left batches have columns (fk_name, left payload), right batches (pk_name, right payload);
-    the payload is "the other column", whatever it is called (y / x in the benchmark,
-    v_l / v_r in JoinTest.SimpleTest, join_test.cc:45-64).
+    left batches have columns (fk_name, left payloads...), right batches (pk_name, right payloads...);
+    payloads are "the other columns", whatever they are called (y / x in the benchmark, v_l / v_r in
+    JoinTest.SimpleTest, join_test.cc:45-64). One payload per side is the fast path (the payload
+    travels with the key); any other number goes through row numbers + the take kernel, as JoinDpu's
+    selection vector + TakeKernel does (join_dpu.cc:127-138,325-341).
     """
 
-    def __init__(self, ctx: Context, left_batches: Sequence[Any], right_batches: Sequence[Any],
+    def __init__(self, ctx, left_batches: Sequence[Any], right_batches: Sequence[Any],
                  fk: str = "fk", pk: str = "pk"):
         self.ctx = ctx
         self.fk, self.pk = fk, pk
         ln = _column_names(left_batches[0]) if len(left_batches) else [fk, "y"]
         rn = _column_names(right_batches[0]) if len(right_batches) else [pk, "x"]
-        if len(ln) != 2 or len(rn) != 2:
-            raise ValueError("JoinGpu handles one key and one payload column per side")
-        self.lpay = [c for c in ln if c != fk][0]
-        self.rpay = [c for c in rn if c != pk][0]
-        self._l = ([_column(b, fk) for b in left_batches], [_column(b, self.lpay) for b in left_batches])
-        self._r = ([_column(b, pk) for b in right_batches], [_column(b, self.rpay) for b in right_batches])
+        if fk not in ln or pk not in rn:
+            raise ValueError(f"join keys {fk!r} / {pk!r} not among the columns {ln} / {rn}")
+        self.lpays = [c for c in ln if c != fk]
+        self.rpays = [c for c in rn if c != pk]
+        if set(self.lpays) & set(self.rpays) or fk in self.rpays:
+            raise ValueError("left and right payload columns must have distinct names")
+        self.lpay = self.lpays[0] if len(self.lpays) == 1 else None
+        self.rpay = self.rpays[0] if len(self.rpays) == 1 else None
+        self._l = [[_column(b, c) for b in left_batches] for c in [fk] + self.lpays]
+        self._r = [[_column(b, c) for b in right_batches] for c in [pk] + self.rpays]
         self._timers = None
 
     def Prepare(self) -> None:
         self._timers = Timers()
 
     def Run(self) -> dict:
-        """{fk: array, left payload: array, right payload: array}, row order unspecified."""
-        lt, rt = _PtrTable(self._l[0] + self._l[1]), _PtrTable(self._r[0] + self._r[1])
+        """{fk: array, left payloads..., right payloads...}, row order unspecified."""
+        lt, rt = _PtrTable([a for col in self._l for a in col]), _PtrTable([a for col in self._r for a in col])
         nlb, nrb = len(self._l[0]), len(self._r[0])
         rows = C.c_uint64(0)
         t1, t2 = Timings(), Timings()
-        self.ctx._call("join_u32_host", lt.ptrs, lt.lens, nlb, rt.ptrs, rt.lens, nrb, C.byref(rows), C.byref(t1))
-        n = int(rows.value)
-        out = [np.empty(n, dtype=np.uint32) for _ in range(3)]
-        self.ctx._call("join_fetch_host", out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, n, C.byref(t2))
+        names = [self.fk] + self.lpays + self.rpays
+        if len(self.lpays) == 1 and len(self.rpays) == 1:
+            self.ctx._call("join_u32_host", lt.ptrs, lt.lens, nlb, rt.ptrs, rt.lens, nrb, C.byref(rows), C.byref(t1))
+            n = int(rows.value)
+            out = [np.empty(n, dtype=np.uint32) for _ in range(3)]
+            self.ctx._call("join_fetch_host", out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, n,
+                           C.byref(t2))
+        else:
+            self.ctx._call("join_cols_u32_host", lt.ptrs, lt.lens, nlb, len(self.lpays), rt.ptrs, rt.lens, nrb,
+                           len(self.rpays), C.byref(rows), C.byref(t1))
+            n = int(rows.value)
+            out = [np.empty(n, dtype=np.uint32) for _ in names]
+            ptrs = (C.c_void_p * len(names))(*[o.ctypes.data for o in out])
+            self.ctx._call("join_cols_fetch_host", ptrs, len(names), n, C.byref(t2))
         self._timers = Timers.from_timings(t1, t2)
         self._last = (t1, t2)
-        return {self.fk: out[0], self.lpay: out[1], self.rpay: out[2]}
+        return dict(zip(names, out))
 
     def RunAggregate(self, y_threshold: int | None = None) -> dict:
         """Fused pipeline (b2_join_aggr_u32_host): COUNT(*), SUM(left payload), SUM(right payload) of
@@ -988,6 +1005,8 @@ class JoinGpu:
         class _Aggr(C.Structure):
             _fields_ = [("rows", C.c_uint64), ("sum_y", C.c_uint64), ("sum_x", C.c_uint64)]
 
+        if self.lpay is None or self.rpay is None:
+            raise ValueError("the fused join -> aggregate pipeline takes one payload column per side")
         lt, rt = _PtrTable(self._l[0] + self._l[1]), _PtrTable(self._r[0] + self._r[1])
         out, t = _Aggr(), Timings()
         self.ctx._call("join_aggr_u32_host", lt.ptrs, lt.lens, len(self._l[0]), rt.ptrs, rt.lens, len(self._r[0]),

@@ -445,6 +445,20 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
 int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
                        int64_t capacity_rows, b2_timings* timings);
 
+/* The same join over ANY number of payload columns per side (JoinDpu partitions every left value
+ * column, join_dpu.cc:127-138, and takes every right non-key column, :325-341):
+ *   l_ptrs = [fk batches..., payload 0 batches..., payload 1 batches..., ...]  ((1 + nl_payloads) * nl_batches)
+ *   r_ptrs likewise. Result columns, in order: fk, the left payloads, the right payloads.
+ * One payload per side is the fast path above (the payload travels with the key). Otherwise the pair
+ * carries the row number and every payload column is gathered afterwards with the take kernel — the
+ * reference's selection-vector + TakeKernel scheme without its host round trips. Sides are limited to
+ * 2^32 - 1 rows then. b2_join_cols_fetch_host copies column c to out_cols[c] (capacity_rows each). */
+int b2_join_cols_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                          int nl_payloads, const uint32_t* const* r_ptrs, const int64_t* r_lens, int64_t nr_batches,
+                          int nr_payloads, uint64_t* out_rows, b2_timings* timings);
+int b2_join_cols_fetch_host(b2_ctx* ctx, uint32_t* const* out_cols, int ncols, int64_t capacity_rows,
+                            b2_timings* timings);
+
 /* ---- multi-GPU join exchange (the step that replaces the reference's host-mediated
  *      DPU->host->DPU repartition, partitioner.cc:350-375 + join_dpu.cc:269,293) -------------- */
 /* Destination rank of a key when the join is sharded over nranks (power of two) GPUs:

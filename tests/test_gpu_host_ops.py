@@ -261,3 +261,33 @@ def test_join_run_aggregate_fused_pipeline(ctx, ops):
     exp = oracle.join_aggr(np.concatenate(fk), np.concatenate(y), np.concatenate(pk), np.concatenate(x), thr)
     assert j.RunAggregate(thr) == exp
     assert 0 < exp["rows"] < cols["fk"].size
+
+
+# ---- JoinDpu takes every non-key column of both sides (join_dpu.cc:127-138,325-341) ------------------
+@pytest.mark.parametrize("nlp,nrp", [(2, 1), (1, 3), (3, 2), (0, 1), (2, 0)])
+def test_join_many_payload_columns(ctx, ops, nlp, nrp):
+    rng = np.random.default_rng(10 * nlp + nrp)
+    nb, bs = 6, 30_000
+    n = nb * bs
+    pk = rng.permutation(np.arange(n, dtype=np.uint32) * 3)
+    pk[:1000] = pk[1000:2000]                                   # duplicate build keys
+    fk = rng.integers(0, 3 * n + 50, size=n, dtype=np.uint32)   # a third of the probe rows match
+    lcols = {f"l{c}": rng.integers(0, 2**32, size=n, dtype=np.uint32) for c in range(nlp)}
+    rcols = {f"r{c}": rng.integers(0, 2**32, size=n, dtype=np.uint32) for c in range(nrp)}
+    sl = lambda a, b: a[b * bs:(b + 1) * bs]
+    left = [{"fk": sl(fk, b), **{k: sl(v, b) for k, v in lcols.items()}} for b in range(nb)]
+    right = [{"pk": sl(pk, b), **{k: sl(v, b) for k, v in rcols.items()}} for b in range(nb)]
+    j = ops.JoinGpu(ctx, left, right)
+    j.Prepare()
+    out = j.Run()
+    assert list(out) == ["fk"] + list(lcols) + list(rcols)
+    # expected: the oracle joins row numbers; every payload column follows its side's row number
+    ids = np.arange(n, dtype=np.uint32)
+    e_fk, e_l, e_r = oracle.join(fk, ids, pk, ids)
+    exp = [e_fk] + [v[e_l] for v in lcols.values()] + [v[e_r] for v in rcols.values()]
+    got = [out[k] for k in out]
+    assert got[0].size == e_fk.size
+    order_g = np.lexsort(tuple(reversed(got)))
+    order_e = np.lexsort(tuple(reversed(exp)))
+    for g, e in zip(got, exp):
+        assert np.array_equal(g[order_g], e[order_e])
