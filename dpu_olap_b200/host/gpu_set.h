@@ -1,5 +1,5 @@
 // gpu_set.h — the GPU-side counterpart of dpu::DpuSet (reference host/dpuext/dpuext.hpp:669-739):
-// an RAII owner of one b2_ctx, plus the status mapping that replaces DPU_RETURN_NOT_OK
+// an RAII owner of a b2_set (one b2_ctx per GPU), plus the status mapping that replaces DPU_RETURN_NOT_OK
 // (host/dpuext/status.h:7-12) and the timer::Timers shape the benchmarks read
 // (host/timer/timer.h; filter_benchmark.cc:52-61).
 #pragma once
@@ -15,6 +15,13 @@
 #include <vector>
 
 #include "b200olap.h"
+
+#define B2_SET_RETURN_NOT_OK(set, expr)                                                      \
+  do {                                                                                       \
+    int _b2s = (expr);                                                                       \
+    if (_b2s != B2_OK)                                                                       \
+      return arrow::Status::UnknownError(b2_strerror(_b2s), ": ", b2_set_last_error(set));   \
+  } while (0)
 
 #define B2_ARROW_RETURN_NOT_OK(ctx, expr)                                                    \
   do {                                                                                       \
@@ -99,26 +106,35 @@ class PinnedPool : public std::enable_shared_from_this<PinnedPool> {
   std::vector<std::pair<void*, int64_t>> free_;
 };
 
+// dpu::DpuSet::allocate(nr_dpus) owns every DPU of the system (dpuext.hpp:704-739); GpuSet::allocate
+// (nr_gpus) owns a b2_set: one b2_ctx per GPU of this process with peer access between them. The
+// operator classes shard over all members (filter / sum / take by batch range, the join with the
+// fused peer-store shuffle); ctx() is member 0 for the single-GPU entry points.
 class GpuSet {
  public:
-  static arrow::Result<std::shared_ptr<GpuSet>> allocate(int device = 0) {
-    b2_ctx* ctx = nullptr;
-    const int s = b2_ctx_create(device, &ctx);
-    if (s != B2_OK) return arrow::Status::UnknownError("b2_ctx_create: ", b2_strerror(s));
-    return std::shared_ptr<GpuSet>(new GpuSet(ctx));
+  static arrow::Result<std::shared_ptr<GpuSet>> allocate(int nr_gpus = 1, int first_device = 0) {
+    if (nr_gpus < 1) return arrow::Status::Invalid("nr_gpus must be >= 1");
+    std::vector<int> devs(static_cast<size_t>(nr_gpus));
+    for (int i = 0; i < nr_gpus; ++i) devs[static_cast<size_t>(i)] = first_device + i;
+    b2_set* set = nullptr;
+    const int s = b2_set_create(devs.data(), nr_gpus, &set);
+    if (s != B2_OK) return arrow::Status::UnknownError("b2_set_create: ", b2_strerror(s));
+    return std::shared_ptr<GpuSet>(new GpuSet(set));
   }
-  ~GpuSet() { b2_ctx_destroy(ctx_); }
+  ~GpuSet() { b2_set_destroy(set_); }
   GpuSet(const GpuSet&) = delete;
   GpuSet& operator=(const GpuSet&) = delete;
-  b2_ctx* ctx() const { return ctx_; }
+  b2_set* set() const { return set_; }
+  b2_ctx* ctx() const { return b2_set_ctx(set_, 0); }
+  int size() const { return b2_set_size(set_); }
   PinnedPool& pinned() { return *pinned_; }
   // All record batches given to operators on this GpuSet are page-locked (gpu::PinnedBatches): groups
   // of batches are then uploaded by one gather kernel instead of one DMA per batch.
-  void PromiseInputsPinned(bool on) { b2_ctx_set_inputs_pinned(ctx_, on ? 1 : 0); }
+  void PromiseInputsPinned(bool on) { b2_set_set_inputs_pinned(set_, on ? 1 : 0); }
 
  private:
-  explicit GpuSet(b2_ctx* ctx) : ctx_(ctx), pinned_(std::make_shared<PinnedPool>()) {}
-  b2_ctx* ctx_;
+  explicit GpuSet(b2_set* set) : set_(set), pinned_(std::make_shared<PinnedPool>()) {}
+  b2_set* set_;
   std::shared_ptr<PinnedPool> pinned_;
 };
 

@@ -89,7 +89,8 @@ int main(int argc, char** argv) {
   const int sf = EnvInt("SF", 1);
   const int threads = EnvInt("MAX_THREADS", static_cast<int>(std::thread::hardware_concurrency()));
   if (!InitNative(threads).ok()) return 2;
-  auto sys_r = gpu::GpuSet::allocate(EnvInt("GPU", 0));
+  // NR_GPUS: the whole set, as NR_DPUS in the reference (host/system/system.h:14-20, main_benchmark.cc:7-8)
+  auto sys_r = gpu::GpuSet::allocate(EnvInt("NR_GPUS", 1), EnvInt("GPU", 0));
   gpu::GpuSet* sys = sys_r.ok() ? sys_r->get() : nullptr;
   if (sys) sys->PromiseInputsPinned(true);  // every fixture below pins its batches (gpu::PinnedBatches)
   auto want = [&](const char* n) { return filter.empty() || std::strstr(n, filter.c_str()) != nullptr; };
@@ -228,7 +229,7 @@ int main(int argc, char** argv) {
   // ---- gbench-shaped JSON (stdout, or --benchmark_out=FILE as scripts/run-*.sh use it) ----
   if (!out_path.empty() && !std::freopen(out_path.c_str(), "w", stdout)) return 4;
   std::printf("{\n  \"context\": {\"SF\": \"%d\", \"NR_GPUS\": \"%d\", \"host_threads\": \"%d\", \"arrow\": \"%s\"},\n",
-              sf, sys ? 1 : 0, threads, ARROW_VERSION_STRING);
+              sf, sys ? sys->size() : 0, threads, ARROW_VERSION_STRING);
   std::printf("  \"benchmarks\": [\n");
   for (size_t i = 0; i < results.size(); ++i) {
     const Result& r = results[i];

@@ -7,6 +7,7 @@
 #include <arrow/compute/api.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <vector>
@@ -247,6 +248,32 @@ static void JoinLargeTest(gpu::GpuSet& sys) {  // join_test.cc:82-121 (128 x 655
   for (const char* c : {"fk", "y", "x"}) EXPECT_TRUE(gs->GetColumnByName(c)->Equals(ns->GetColumnByName(c)));
 }
 
+static void JoinManyPayloadsTest(gpu::GpuSet& sys) {  // JoinDpu carries every non-key column (join_dpu.cc:127-138,325-341)
+  const int nb = 8, bs = 64 << 10;
+  RandomArrayGenerator rng(42);
+  auto right = AddColumn("pk", MakeRandomRecordBatches(rng, VSchema("x"), nb, bs), MakeIndexColumn(nb, bs).ValueOrDie());
+  auto x2 = MakeRandomRecordBatches(rng, VSchema("x2"), nb, bs);
+  for (int b = 0; b < nb; ++b) right[b] = right[b]->AddColumn(2, "x2", x2[b]->column(0)).ValueOrDie();
+  auto left = AddColumn("fk", MakeRandomRecordBatches(rng, VSchema("y"), nb, bs),
+                        MakeForeignKeyColumn(rng, bs, nb, bs).ValueOrDie());
+  auto y2 = MakeRandomRecordBatches(rng, VSchema("y2"), nb, bs);
+  auto y3 = MakeRandomRecordBatches(rng, VSchema("y3"), nb, bs);
+  for (int b = 0; b < nb; ++b) {
+    left[b] = left[b]->AddColumn(2, "y2", y2[b]->column(0)).ValueOrDie();
+    left[b] = left[b]->AddColumn(3, "y3", y3[b]->column(0)).ValueOrDie();
+  }
+  join::JoinGpu g{sys, left[0]->schema(), right[0]->schema(), left, right};
+  EXPECT_TRUE(g.Prepare().ok());
+  auto gt = g.Run().ValueOrDie();
+  EXPECT_EQ(gt->num_rows(), static_cast<int64_t>(nb) * bs);
+  EXPECT_EQ(gt->num_columns(), 6);
+  join::JoinNative n{left[0]->schema(), right[0]->schema(), left, right};
+  auto nt = n.Run().ValueOrDie();
+  auto gs = Sorted(gt, {"fk", "y", "y2"}), ns = Sorted(nt, {"fk", "y", "y2"});
+  for (const char* c : {"fk", "y", "y2", "y3", "x", "x2"})
+    EXPECT_TRUE(gs->GetColumnByName(c)->Equals(ns->GetColumnByName(c)));
+}
+
 static void JoinAggregateTest(gpu::GpuSet& sys) {  // fused pipeline vs aggregates of the Native join's columns
   RandomArrayGenerator rng(42);
   const int nb = 16, bs = 1 << 16;
@@ -370,7 +397,8 @@ static int RunCpuCases() {
 int main(int argc, char** argv) {
   if (!InitNative(0).ok()) return 2;
   if (argc > 1 && std::string(argv[1]) == "--cpu") return RunCpuCases();
-  auto sys = gpu::GpuSet::allocate(0);
+  const char* ng = std::getenv("NR_GPUS");  // the same cases over a set of several GPUs
+  auto sys = gpu::GpuSet::allocate(ng ? std::atoi(ng) : 1, 0);
   if (!sys.ok()) {
     std::printf("no GPU: %s\n", sys.status().ToString().c_str());
     return 3;
@@ -384,7 +412,8 @@ int main(int argc, char** argv) {
       {"TakeTest.LargeTest", TakeLargeTest},       {"FilterTest.Nullable", FilterNullableTest},
       {"SumTest.Nullable", SumNullableTest},       {"TakeTest.Nullable", TakeNullableTest},
       {"JoinTest.SimpleTest", JoinSimpleTest},
-      {"JoinTest.LargeTest", JoinLargeTest},       {"JoinTest.FusedAggregate", JoinAggregateTest},       {"PartitionTest.SimpleTest", PartitionSimpleTest},
+      {"JoinTest.LargeTest", JoinLargeTest},       {"JoinTest.ManyPayloads", JoinManyPayloadsTest},
+      {"JoinTest.FusedAggregate", JoinAggregateTest},       {"PartitionTest.SimpleTest", PartitionSimpleTest},
       {"PartitionTest.LargeTest", PartitionLargeTest}};
   int bad = 0;
   for (auto& c : cases) {

@@ -81,6 +81,22 @@ arrow::Result<std::shared_ptr<arrow::ChunkedArray>> FilterGpu::GetResult() {
     B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_u32_nullable_host_into(
                                     ctx, in.ptrs.data(), in.valid.data(), in.valid_off.data(), in.lens.data(),
                                     nb, threshold_, out, rows, counts.data(), &total, &t));
+  } else if (system_.size() > 1) {
+    // several GPUs: every GPU filters its batch range and keeps the result; the chunks can only be
+    // placed once all counts are known (the reference reads "output_buffer_length" first, then pulls
+    // "output_buffer", filter_dpu.cc:57-83)
+    b2_set* set = system_.set();
+    B2_SET_RETURN_NOT_OK(set, b2_set_filter_lt_u32_host(set, in.ptrs.data(), in.lens.data(), nb, threshold_,
+                                                        counts.data(), &total, &t));
+    std::vector<uint32_t*> outs(nb > 0 ? nb : 1);
+    int64_t o = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+      outs[b] = out + o;
+      o += counts[b];
+    }
+    b2_timings t2{};
+    B2_SET_RETURN_NOT_OK(set, b2_set_filter_fetch_host(set, outs.data(), nb, &t2));
+    timers_->Add(t2);
   } else {
     B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_u32_host_into(ctx, in.ptrs.data(), in.lens.data(), nb, threshold_,
                                                            out, rows, counts.data(), &total, &t));
@@ -135,8 +151,10 @@ arrow::Result<uint64_t> SumGpu::Run() {
   }
   uint64_t sum = 0;
   b2_timings t{};
-  B2_ARROW_RETURN_NOT_OK(ctx, b2_sum_u32_host(ctx, in.ptrs.data(), in.lens.data(),
-                                              static_cast<int64_t>(in.ptrs.size()), &sum, &t));
+  b2_set* set = system_.set();  // contiguous batch ranges per GPU, one partial each (aggr_dpu.cc:82-84)
+  B2_SET_RETURN_NOT_OK(set, b2_set_sum_u32_host(set, in.ptrs.data(), in.lens.data(),
+                                                static_cast<int64_t>(in.ptrs.size()), &sum, &t));
+  (void)ctx;
   timers_->Add(t);
   return sum;
 }
@@ -202,8 +220,9 @@ arrow::Result<std::shared_ptr<arrow::Table>> TakeGpu::Run() {
     off += i.lens[b];
   }
   b2_timings t{};
-  B2_ARROW_RETURN_NOT_OK(ctx, b2_take_u32_host(ctx, v.ptrs.data(), v.lens.data(), i.ptrs.data(),
-                                               i.lens.data(), nb, outs.data(), &t));
+  b2_set* set = system_.set();  // batch-local gather: batch ranges per GPU
+  B2_SET_RETURN_NOT_OK(set, b2_set_take_u32_host(set, v.ptrs.data(), v.lens.data(), i.ptrs.data(), i.lens.data(), nb,
+                                                 outs.data(), &t));
   timers_->Add(t);
   return arrow::Table::FromRecordBatches(schema, result);
 }
@@ -220,33 +239,54 @@ arrow::Status JoinGpu::Prepare() {
 
 arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
   b2_ctx* ctx = system_.ctx();
+  b2_set* set = system_.set();
   if (!timers_) timers_ = std::make_shared<timer::Timers>();
   const int fk = left_schema_->GetFieldIndex("fk"), pk = right_schema_->GetFieldIndex("pk");
   if (fk < 0 || pk < 0) return arrow::Status::Invalid("join keys are named fk / pk (join_native.cc:31-36)");
-  if (left_schema_->num_fields() != 2 || right_schema_->num_fields() != 2)
-    return arrow::Status::NotImplemented("one key and one payload column per side");
-  const int ly = 1 - fk, rx = 1 - pk;
-  ColumnPtrs l, r;  // [key batches..., payload batches...]
+  // every non-key column of both sides comes along (join_dpu.cc:127-138,325-341)
+  std::vector<int> lcols, rcols;
+  for (int c = 0; c < left_schema_->num_fields(); ++c)
+    if (c != fk) lcols.push_back(c);
+  for (int c = 0; c < right_schema_->num_fields(); ++c)
+    if (c != pk) rcols.push_back(c);
+  ColumnPtrs l, r;  // [key batches..., payload 0 batches..., payload 1 batches..., ...]
   ARROW_RETURN_NOT_OK(l.Append(left_batches_, fk));
-  ARROW_RETURN_NOT_OK(l.Append(left_batches_, ly));
+  for (int c : lcols) ARROW_RETURN_NOT_OK(l.Append(left_batches_, c));
   ARROW_RETURN_NOT_OK(r.Append(right_batches_, pk));
-  ARROW_RETURN_NOT_OK(r.Append(right_batches_, rx));
+  for (int c : rcols) ARROW_RETURN_NOT_OK(r.Append(right_batches_, c));
+  const int64_t nlb = static_cast<int64_t>(left_batches_.size()), nrb = static_cast<int64_t>(right_batches_.size());
+  // JoinNative drops pk and keeps fk + the payloads of both sides (join_native.cc:75)
+  arrow::FieldVector fields{left_schema_->field(fk)};
+  for (int c : lcols) fields.push_back(left_schema_->field(c));
+  for (int c : rcols) fields.push_back(right_schema_->field(c));
+  const int ncols = static_cast<int>(fields.size());
   uint64_t rows = 0;
   b2_timings t1{}, t2{};
-  B2_ARROW_RETURN_NOT_OK(
-      ctx, b2_join_u32_host(ctx, l.ptrs.data(), l.lens.data(), static_cast<int64_t>(left_batches_.size()),
-                            r.ptrs.data(), r.lens.data(), static_cast<int64_t>(right_batches_.size()),
-                            &rows, &t1));
-  uint32_t *o_fk, *o_y, *o_x;
-  ARROW_ASSIGN_OR_RAISE(auto a_fk, PinnedU32(system_, static_cast<int64_t>(rows), &o_fk));
-  ARROW_ASSIGN_OR_RAISE(auto a_y, PinnedU32(system_, static_cast<int64_t>(rows), &o_y));
-  ARROW_ASSIGN_OR_RAISE(auto a_x, PinnedU32(system_, static_cast<int64_t>(rows), &o_x));
-  B2_ARROW_RETURN_NOT_OK(ctx, b2_join_fetch_host(ctx, o_fk, o_y, o_x, static_cast<int64_t>(rows), &t2));
+  arrow::ArrayVector arrays(static_cast<size_t>(ncols));
+  std::vector<uint32_t*> outs(static_cast<size_t>(ncols));
+  const bool pair_path = lcols.size() == 1 && rcols.size() == 1;
+  if (pair_path) {
+    // the benchmark shape: the payload travels with the key; sharded over every GPU of the set
+    B2_SET_RETURN_NOT_OK(set, b2_set_join_u32_host(set, l.ptrs.data(), l.lens.data(), nlb, r.ptrs.data(),
+                                                   r.lens.data(), nrb, &rows, &t1));
+  } else {
+    // row numbers + take kernel on member 0 (row numbers are local to one device's packed columns)
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_join_cols_u32_host(ctx, l.ptrs.data(), l.lens.data(), nlb,
+                                                      static_cast<int>(lcols.size()), r.ptrs.data(), r.lens.data(),
+                                                      nrb, static_cast<int>(rcols.size()), &rows, &t1));
+  }
+  for (int c = 0; c < ncols; ++c) {
+    ARROW_ASSIGN_OR_RAISE(arrays[static_cast<size_t>(c)],
+                          PinnedU32(system_, static_cast<int64_t>(rows), &outs[static_cast<size_t>(c)]));
+  }
+  if (pair_path) {
+    B2_SET_RETURN_NOT_OK(set, b2_set_join_fetch_host(set, outs[0], outs[1], outs[2], static_cast<int64_t>(rows), &t2));
+  } else {
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_join_cols_fetch_host(ctx, outs.data(), ncols, static_cast<int64_t>(rows), &t2));
+  }
   timers_->Add(t1);
   timers_->Add(t2);
-  // JoinNative drops pk and keeps (fk, left payload, right payload) (join_native.cc:75)
-  auto schema = arrow::schema({left_schema_->field(fk), left_schema_->field(ly), right_schema_->field(rx)});
-  return arrow::Table::Make(schema, {a_fk, a_y, a_x}, static_cast<int64_t>(rows));
+  return arrow::Table::Make(arrow::schema(fields), arrays, static_cast<int64_t>(rows));
 }
 
 // Fused pipeline [filter left payload < threshold ->] join -> COUNT / SUM(left payload) / SUM(right

@@ -40,7 +40,21 @@ def test_cpp_bench_native_json_shape(host_bins):
 def test_cpp_reference_tests_on_gpu(host_bins):
     r = subprocess.run([str(host_bins["host_test"])], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 of 16 cases failed" in r.stdout
+    assert "0 of 17 cases failed" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nr_gpus", [2, 8])
+def test_cpp_reference_tests_on_a_gpu_set(host_bins, nr_gpus):
+    """The same GoogleTest restatements with GpuSet::allocate(NR_GPUS): every operator class shards
+    over the whole set behind the C ABI (JoinTest.LargeTest runs the fused peer-store shuffle)."""
+    import torch
+    if torch.cuda.device_count() < nr_gpus:
+        pytest.skip(f"needs {nr_gpus} GPUs")
+    env = dict(os.environ, NR_GPUS=str(nr_gpus))
+    r = subprocess.run([str(host_bins["host_test"])], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 of 17 cases failed" in r.stdout
 
 
 @pytest.mark.gpu
