@@ -1141,6 +1141,60 @@ def bench_e2e_ops(ctx, D, args) -> dict:
     return res
 
 
+def bench_e2e_set_join(ctx, D, args) -> dict:
+    """The sharded join through the C ABI's device set (b2_set_join_u32_host + b2_set_join_fetch_host:
+    what the C++ JoinGpu calls with GpuSet::allocate(N)): ONE host process drives all N GPUs — upload
+    of each GPU's batch range, count, device-side plan, NVLink scatter, local joins, download — with
+    pinned host batches in and host columns out. Run by rank 0 alone while the other ranks wait."""
+    import ctypes as C
+
+    import torch
+
+    from dpu_olap_b200._lib import Timings
+    from dpu_olap_b200.generator import RandomArrayGenerator
+    from dpu_olap_b200.ops import DeviceSet
+    sf = args.e2e_sf * D.world
+    g = RandomArrayGenerator(ctx, 42)
+    xd = g.batches_dev(sf, JOIN_BATCH)
+    pkd = g.index_column_dev(sf, JOIN_BATCH)
+    yd = g.batches_dev(sf, JOIN_BATCH)
+    fkd = g.foreign_key_dev(JOIN_BATCH, sf, JOIN_BATCH)
+    exp = triple_checksum_torch(fkd, yd, xd[fkd.to(torch.int64) & 0xFFFFFFFF])
+    x, pk, y, fk = (_pinned(t) for t in (xd, pkd, yd, fkd))
+    del xd, pkd, yd, fkd
+    free_all()
+    n = sf * JOIN_BATCH
+
+    def table(*cols):
+        ptrs = [t.data_ptr() + 4 * i for t in cols for i in range(0, t.numel(), JOIN_BATCH)]
+        return (C.c_void_p * len(ptrs))(*ptrs), (C.c_int64 * len(ptrs))(*([JOIN_BATCH] * len(ptrs)))
+    lptrs, llens = table(fk, y)
+    rptrs, rlens = table(pk, x)
+    o = [torch.empty(n, dtype=torch.int32, pin_memory=True) for _ in range(3)]
+    nrows, t1, t2 = C.c_uint64(0), Timings(), Timings()
+    steps = max(2, min(args.steps, 5))
+    with DeviceSet(list(range(D.world))) as ds:
+        def step():
+            ds._call("join_u32_host", lptrs, llens, sf, rptrs, rlens, sf, C.byref(nrows), C.byref(t1))
+            ds._call("join_fetch_host", o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n, C.byref(t2))
+        for _ in range(2):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+    if int(nrows.value) != n or triple_checksum_torch(*[t.cuda() for t in o]) != exp:
+        raise SystemExit("e2e set join self-check failed")
+    res = {"value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "sf": sf, "steps": steps, "n_gpus": D.world,
+           "api": "b2_set_join_u32_host + b2_set_join_fetch_host (one process, N GPUs, CUDA events between devices)",
+           "h2d_bytes_per_step": int(t1.h2d_bytes), "d2h_bytes_per_step": int(t1.d2h_bytes + t2.d2h_bytes),
+           "phases_ms": {"copy-to-dpu": t1.copy_to_dev_ms, "dpu-work": t1.dev_work_ms,
+                         "copy-from-dpu": t2.copy_from_dev_ms},
+           "gpu_launches_per_step": int(t1.kernel_launches), "self_check": "content", "scaling": "weak"}
+    del x, pk, y, fk, o
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", 0))
@@ -1233,6 +1287,15 @@ def main():
             for op, leg in bench_e2e_ops(ctx, D, args).items():
                 if extra.get(op):
                     extra[op]["e2e"] = leg
+        elif extra.get("join"):
+            # N > 1: the sharded join behind the C ABI's device set, driven by rank 0's process alone
+            D.barrier()
+            if D.rank == 0:
+                try:
+                    extra["join"]["e2e"] = bench_e2e_set_join(ctx, D, args)
+                except Exception as e:  # noqa: BLE001 - the device-resident numbers above stand on their own
+                    extra["join"]["e2e"] = {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
+            D.barrier()
     cpu = None
     if D.rank == 0 and D.world == 1 and not args.no_cpu:
         cpu = cpu_filter_sample(args, args.cpu_sf, args.cpu_seconds)
