@@ -1289,12 +1289,20 @@ def main():
                     extra[op]["e2e"] = leg
         elif extra.get("join"):
             # N > 1: the sharded join behind the C ABI's device set, driven by rank 0's process alone
+            # The other ranks wait on the CPU (c10d store), NOT in an NCCL barrier: a spinning collective
+            # kernel of another process sharing a GPU with rank 0's kernels is exactly the co-residency
+            # the B200 profiling notes warn about (context-switch timeouts).
             D.barrier()
+            from datetime import timedelta
+            store = D.dist.distributed_c10d._get_default_store()
             if D.rank == 0:
                 try:
                     extra["join"]["e2e"] = bench_e2e_set_join(ctx, D, args)
                 except Exception as e:  # noqa: BLE001 - the device-resident numbers above stand on their own
                     extra["join"]["e2e"] = {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
+                store.set("b2_set_join_done", "1")
+            else:
+                store.wait(["b2_set_join_done"], timedelta(minutes=20))
             D.barrier()
     cpu = None
     if D.rank == 0 and D.world == 1 and not args.no_cpu:
