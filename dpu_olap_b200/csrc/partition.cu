@@ -587,36 +587,47 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 // to the bucket's rows of the next tile; four adjacent lanes store one whole, aligned sector. Only
 // the first and the last sector of a (unit, bucket) run can be partial.
 constexpr int kScRows = 4;                       // rows per 32-byte sector
-constexpr int kScT = 512, kScI = 16;
-constexpr int kScTile = kScT * kScI;             // 8192 rows
-constexpr int kScBpt = (1 << kPartMaxBits) / kScT;  // buckets per thread in the per-bucket phases
-constexpr int kScMaxSec = (kScTile + 3 * (1 << kPartMaxBits)) / kScRows;  // whole sectors one tile can flush
 
 struct ScDesc {       // per bucket and tile, read once per flushed row
   int32_t sbase;      // stage index of (carried ++ staged) position 0, minus 4 * (first flushed sector)
   uint32_t dsec;      // destination sector of position 0, minus (first flushed sector); between two
                       // tiles: the next unwritten sector of the run, counted from the output base
 };
-struct ScSmem {
-  uint2 stage[kScTile];                         // 64 KB: the tile's rows sorted by bucket
+// Shape of the kernel: kT threads x kI rows per thread per tile. <512, 16> runs two CTAs per SM
+// (8192-row tiles: a bucket's run is 64 B at a fan-out of 1024); <1024, 16> runs one CTA per SM over
+// 16384-row tiles, which doubles the run length (128 B: the memory system takes 128-byte runs at
+// 5.2 TB/s against 4.0 TB/s for 64-byte ones, tools/microbench_scatter_ceiling.cu) and halves the
+// per-bucket bookkeeping per row.
+template <int kT, int kI>
+struct ScShape {
+  static constexpr int kTile = kT * kI;
+  static constexpr int kBpt = (1 << kPartMaxBits) / kT;                              // buckets per thread
+  static constexpr int kMaxSec = (kTile + 3 * (1 << kPartMaxBits)) / kScRows;        // whole sectors one tile can flush
+  static constexpr int kCtas = kT >= 1024 ? 1 : 2;
+};
+template <int kT, int kI>
+struct ScSmemT {
+  uint2 stage[ScShape<kT, kI>::kTile];          // the tile's rows sorted by bucket
   uint2 carry[(1 << kPartMaxBits) * 3];         // 24 KB: held-back rows (slots 0..ghost-1 are not ours)
   ScDesc bd[1 << kPartMaxBits];                 // 8 KB
   uint32_t tile_cnt[1 << kPartMaxBits];         // carried + rows ranked so far
   int32_t sbase[1 << kPartMaxBits];             // tile_start - carried
-  uint16_t meta[1 << kPartMaxBits];             // first flushed sector (12 bits) | carried << 12 | ghost << 14
-  uint16_t sec_desc[kScMaxSec + 16];            // flushed sector -> bucket | (first sector: carried << 10 | ghost << 12)
-  uint32_t warp_tot[kScT / 32];
+  uint32_t meta[1 << kPartMaxBits];             // first flushed sector (16 bits) | carried << 16 | ghost << 18
+  uint16_t sec_desc[ScShape<kT, kI>::kMaxSec + 16];  // flushed sector -> bucket | (first sector: carried << 10 | ghost << 12)
+  uint32_t warp_tot[kT / 32];
   uint32_t n_sec;
 };
 
-template <bool kAoS, bool kPre>
-__global__ void __launch_bounds__(kScT, 2)
+template <bool kAoS, bool kPre, int kScT, int kScI>
+__global__ void __launch_bounds__(kScT, (ScShape<kScT, kScI>::kCtas))
 part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                             const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
                             PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
                             int64_t out_cap, unsigned int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem[];
-  ScSmem& sm = *reinterpret_cast<ScSmem*>(smem);
+  using Shape = ScShape<kScT, kScI>;
+  constexpr int kScTile = Shape::kTile, kScBpt = Shape::kBpt;
+  ScSmemT<kScT, kScI>& sm = *reinterpret_cast<ScSmemT<kScT, kScI>*>(smem);
   const int P = 1 << g.bits;
   const SliceSel sel = slice_sel(g);
   const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
@@ -632,7 +643,7 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
       const uint64_t pos = scanned[u.hbase + (int64_t)p * u.ustride];  // first output row of (unit, bucket)
       const uint32_t ghost = (uint32_t)(pos & (kScRows - 1));         // rows of that sector that are not ours
       sm.bd[p].dsec = (uint32_t)(pos >> 2);
-      sm.meta[p] = (uint16_t)((ghost << 12) | (ghost << 14));
+      sm.meta[p] = (ghost << 16) | (ghost << 18);
       sm.tile_cnt[p] = ghost;
     }
   }
@@ -699,7 +710,7 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
         if (p < P) {
           const uint32_t tot = sm.tile_cnt[p];  // carried + new
           // rows <= 8192 and sectors <= 2816 never carry into each other
-          mine += (tot - ((sm.meta[p] >> 12) & 3u)) | ((tot >> 2) << 16);
+          mine += (tot - ((sm.meta[p] >> 16) & 3u)) | ((tot >> 2) << 16);
         }
       }
       uint32_t incl = mine;
@@ -726,7 +737,7 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
         if (p < P) {
           // re-read rather than keep live across the scan (the row registers fill the budget)
           const uint32_t tot = sm.tile_cnt[p];
-          const uint32_t cg = sm.meta[p] >> 12;  // carried | ghost << 2
+          const uint32_t cg = sm.meta[p] >> 16;  // carried | ghost << 2
           const uint32_t tc = tot - (cg & 3u), ns = tot >> 2;
           const uint32_t start = excl & 0xffffu, so = excl >> 16;
           const int32_t sb = (int32_t)start - (int32_t)(cg & 3u);
@@ -735,7 +746,7 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
           d.sbase = sb - (int32_t)(so * kScRows);
           d.dsec = sm.bd[p].dsec - so;
           sm.bd[p] = d;
-          sm.meta[p] = (uint16_t)(so | (cg << 12));
+          sm.meta[p] = so | (cg << 16);
           if (ns) sm.sec_desc[so] = (uint16_t)(p | (cg << 10));  // the first sector may hold carried / ghost rows
           for (uint32_t i = 1; i < ns; ++i) sm.sec_desc[so + i] = (uint16_t)p;
           excl += tc | (ns << 16);
@@ -801,7 +812,7 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
       if (p < P) {
         const uint32_t tot = sm.tile_cnt[p];
         const uint32_t m = sm.meta[p];
-        const uint32_t so = m & 0xfffu, c0 = (m >> 12) & 3u, ghost = m >> 14;
+        const uint32_t so = m & 0xffffu, c0 = (m >> 16) & 3u, ghost = m >> 18;
         const uint32_t nsec = tot >> 2, rem = tot & 3u;
         // nothing flushed: append the new rows to the carry; otherwise the tail of the staged rows
         // becomes the carry (carried < 4 <= 4 * nsec)
@@ -811,7 +822,7 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
         for (uint32_t i = 0; i < 3; ++i)
           if (i >= first && i < rem) sm.carry[p * 3 + i] = sm.stage[from + (int32_t)i];
         sm.bd[p].dsec += so + nsec;
-        sm.meta[p] = (uint16_t)((rem << 12) | ((nsec ? 0u : ghost) << 14));
+        sm.meta[p] = (rem << 16) | ((nsec ? 0u : ghost) << 18);
         sm.tile_cnt[p] = rem;
       }
     }
@@ -823,7 +834,7 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     const int b = i >> 2;
     const uint32_t l = i & 3;
     const uint32_t m = sm.meta[b];
-    if (l >= (m >> 14) && l < ((m >> 12) & 3u)) {
+    if (l >= (m >> 18) && l < ((m >> 16) & 3u)) {
       const uint64_t row = (uint64_t)sm.bd[b].dsec * kScRows + l;
       if (row < cap) st_stream_v2(out + row, sm.carry[b * 3 + l]);
       else if (overflow) *overflow = 1u;
@@ -960,19 +971,24 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
     const bool sectors = !d_bucket_addr && !g.val_pred && (reinterpret_cast<uintptr_t>(d_out) & 31) == 0 &&
                          (uint64_t)out_cap < (1ull << 34) && g.bits >= ctx->tune[B2_TUNE_SCATTER_SECTORS_MIN_BITS];
     if (sectors) {
-      static const int seen = b2_new_site();
-      if (b2_first_use_on_device(ctx, seen)) {
-        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScSmem)));
-        B2_CUDA_OK(ctx, cudaFuncSetAttribute(part_scatter_sectors_kernel<kAoS, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScSmem)));
+      const bool big = ctx->tune[B2_TUNE_SCATTER_SECTOR_TILE] != 0;
+      const bool pre = ctx->tune[B2_TUNE_SCATTER_PREFETCH] != 0;
+      // four instantiations share one function-pointer type, so each gets its own site id
+      static const int sites[4] = {b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site()};
+      auto go = [&](auto kernel, int site, int threads, size_t smem_bytes) -> int {
+        if (b2_first_use_on_device(ctx, site))
+          B2_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        kernel<<<(unsigned)L.max_units, threads, smem_bytes, s>>>(in, d_seg_off, unit_first, nseg, L.unit_rows, g,
+                                                                 scanned, d_out, out_cap, d_overflow);
+        return B2_OK;
+      };
+      if (big) {
+        if (pre) B2_RETURN_NOT_OK(go(part_scatter_sectors_kernel<kAoS, true, 1024, 16>, sites[0], 1024, sizeof(ScSmemT<1024, 16>)));
+        else B2_RETURN_NOT_OK(go(part_scatter_sectors_kernel<kAoS, false, 1024, 16>, sites[1], 1024, sizeof(ScSmemT<1024, 16>)));
+      } else {
+        if (pre) B2_RETURN_NOT_OK(go(part_scatter_sectors_kernel<kAoS, true, 512, 16>, sites[2], 512, sizeof(ScSmemT<512, 16>)));
+        else B2_RETURN_NOT_OK(go(part_scatter_sectors_kernel<kAoS, false, 512, 16>, sites[3], 512, sizeof(ScSmemT<512, 16>)));
       }
-      if (ctx->tune[B2_TUNE_SCATTER_PREFETCH])
-        part_scatter_sectors_kernel<kAoS, true><<<(unsigned)L.max_units, kScT, sizeof(ScSmem), s>>>(
-            in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
-      else
-        part_scatter_sectors_kernel<kAoS, false><<<(unsigned)L.max_units, kScT, sizeof(ScSmem), s>>>(
-            in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_out, out_cap, d_overflow);
       B2_LAUNCH_CHECK(ctx, "part_scatter_sectors_kernel");
       return B2_OK;
     }

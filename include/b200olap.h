@@ -90,7 +90,8 @@ enum b2_tunable {
   B2_TUNE_SCATTER_SECTORS_MIN_BITS = 0, /* log2 fan-out from which the radix scatter stores whole 32 B sectors (9; 0 = always, 11 = never) */
   B2_TUNE_SCATTER_PREFETCH = 1,         /* scatter kernels request the next tile while flushing this one (1) */
   B2_TUNE_SCATTER_SHAPE = 2,            /* plain scatter kernel shape: 0 = 512 thr x 16 rows x 2 CTA/SM, 1, 2, 3, 8 */
-  B2_TUNE_FILTER_VARIANT = 3            /* filter kernel shape 0..7 (6) */
+  B2_TUNE_FILTER_VARIANT = 3,           /* filter kernel shape 0..7 (6) */
+  B2_TUNE_SCATTER_SECTOR_TILE = 4       /* whole-sector scatter: 0 = 8192-row tiles x 2 CTA/SM, 1 = 16384-row tiles x 1 CTA/SM (1) */
 };
 int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value);
 int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value);

@@ -6,18 +6,21 @@ import pytest
 import torch
 
 import oracle
-from dpu_olap_b200._lib import TUNE_SCATTER_SECTORS_MIN_BITS
+from dpu_olap_b200._lib import TUNE_SCATTER_SECTOR_TILE, TUNE_SCATTER_SECTORS_MIN_BITS
 from test_gpu_dev_ops import check_join, check_partition, dev, host, run_join
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def sectors(ctx):
+@pytest.fixture(params=[0, 1], ids=["tile8192", "tile16384"])
+def sectors(ctx, request):
     default = ctx.get_tunable(TUNE_SCATTER_SECTORS_MIN_BITS)
+    tile = ctx.get_tunable(TUNE_SCATTER_SECTOR_TILE)
     ctx.set_tunable(TUNE_SCATTER_SECTORS_MIN_BITS, 0)  # from a fan-out of 2^0: always
+    ctx.set_tunable(TUNE_SCATTER_SECTOR_TILE, request.param)  # both shapes of the kernel
     yield ctx
     ctx.set_tunable(TUNE_SCATTER_SECTORS_MIN_BITS, default)
+    ctx.set_tunable(TUNE_SCATTER_SECTOR_TILE, tile)
 
 
 @pytest.mark.parametrize("n,nparts,ncols", [(0, 4, 2), (1, 1, 1), (3, 2, 2), (1000, 2, 3), (8192, 1024, 2),

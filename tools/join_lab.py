@@ -41,6 +41,8 @@ def main():
                 ctx.set_tunable(0, int(f[2]))                    # B2_TUNE_SCATTER_SECTORS_MIN_BITS
             if len(f) > 3:  # smem:v:b:p = next-tile prefetch in the scatter kernels off / on
                 ctx.set_tunable(1, int(f[3]))                    # B2_TUNE_SCATTER_PREFETCH
+            if len(f) > 4:  # smem:v:b:p:t = whole-sector kernel over 16384-row tiles, one CTA per SM
+                ctx.set_tunable(4, int(f[4]))                    # B2_TUNE_SCATTER_SECTOR_TILE
             ws = torch.empty(ctx.join_ws_bytes(n, n) + 256, dtype=torch.uint8, device="cuda")
             step = lambda: ctx.join_dev(fk, y, pk, x, out_capacity=n, ws=ws, outs=outs, out_rows=rows)
             for o in outs:
