@@ -843,6 +843,254 @@ part_scatter_sectors_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 }
 
 // part_off[s*P + p] = first output row of (segment s, bucket p); part_off[nseg*P] = total rows.
+// ---- whole-sector scatter, second generation: quad-aligned regions ("quads") -----------------------
+// The source profile of part_scatter_sectors_kernel (profiles/r2_scatter_probe_phases.md) showed the
+// flush as HALF of its instructions: per stored row it looked up the sector's bucket, unpacked the
+// bucket's descriptor, chose between the carry array and the stage, rebuilt the stage index and the
+// 64-bit destination row. This kernel removes the choices instead of speeding them up:
+//   * a bucket's region of the stage starts on a multiple of four slots and holds (rows carried from
+//     the previous tile ++ this tile's rows): the carried rows are copied INTO the stage by the
+//     bucket's thread during the scan step, so the flush reads stage[t] and nothing else;
+//   * every quad of stage slots belongs to one bucket and maps onto one aligned 32-byte sector of the
+//     output, so slot t goes to sector desc[bucket].dsec + t / 4, lane t % 4: one add, one wide
+//     multiply-add for the address;
+//   * "is this slot stored?" is lo <= t < hi with lo / hi precomputed per bucket (the rows of the
+//     first sector that belong to the neighbouring run, and the tail that does not fill a sector).
+// One 1024-thread CTA per SM, 14 rows per thread per tile (the stage, its padding and the carry
+// array fill the 227 KB of shared memory), one bucket per thread in the per-bucket steps.
+constexpr int kQdT = 1024, kQdI = 14;
+constexpr int kQdTile = kQdT * kQdI;                                  // 14336 rows
+constexpr int kQdSlots = kQdTile + 6 * (1 << kPartMaxBits);           // + carried rows + padding to quads
+constexpr int kQdUn = 4;                                              // slots in flight per thread in the flush
+constexpr int kQdRound = kQdT * kQdUn;                                // slots one flush round covers
+static_assert(kQdSlots % kQdRound == 0, "the stage is a whole number of flush rounds");
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {  // explicit shared-window loads: no generic -> shared conversion
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+struct QdDesc {
+  uint32_t dsec;     // destination sector of the region's first quad, minus that quad's index
+  uint16_t lo, hi;   // slots [lo, hi) of the stage are stored
+};
+struct QdSmem {
+  uint2 stage[kQdSlots];                         // 160 KB
+  uint2 carry[(1 << kPartMaxBits) * 3];          // 24 KB: the rows that did not fill a sector
+  QdDesc desc[(1 << kPartMaxBits) + 1];          // 8 KB; the last entry (lo == hi) stores nothing: padding quads point at it
+  uint32_t tile_cnt[1 << kPartMaxBits];          // carried (incl. ghost) + rows ranked so far
+  uint32_t qstart[1 << kPartMaxBits];            // first stage slot of the bucket's region
+  uint32_t dsec_next[1 << kPartMaxBits];         // next unwritten sector of the (unit, bucket) run
+  uint16_t quad_bucket[kQdSlots / 4];            // 10 KB: bucket of every quad
+  uint8_t carried[1 << kPartMaxBits];            // rows in carry[] (ghost rows included)
+  uint8_t ghost[1 << kPartMaxBits];              // leading slots of the run's first sector that are not ours
+  uint32_t warp_tot[kQdT / 32];
+  uint32_t n_slots;
+};
+static_assert(sizeof(QdSmem) <= 227 * 1024, "QdSmem must fit the opt-in shared memory of one CTA");
+
+template <bool kAoS, bool kPre>
+__global__ void __launch_bounds__(kQdT, 1)
+part_scatter_quads_kernel(PartInput in, const int64_t* __restrict__ seg_off,
+                          const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
+                          PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
+                          int64_t out_cap, unsigned int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  QdSmem& sm = *reinterpret_cast<QdSmem*>(smem);
+  const int P = 1 << g.bits;
+  const SliceSel sel = slice_sel(g);
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
+  if (!u.valid) return;
+  constexpr int kW = kQdT / 32;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool mine = (int)tid < P;  // this thread's bucket in the per-bucket steps
+
+  if (mine) {
+    const uint64_t pos = scanned[u.hbase + (int64_t)tid * u.ustride];  // first output row of (unit, bucket)
+    const uint32_t gh = (uint32_t)(pos & (kScRows - 1));               // rows of that sector that are not ours
+    sm.dsec_next[tid] = (uint32_t)(pos >> 2);
+    sm.ghost[tid] = (uint8_t)gh;
+    sm.carried[tid] = (uint8_t)gh;
+    sm.tile_cnt[tid] = gh;
+  }
+  __syncthreads();
+
+  if (tid == 0) {
+    QdDesc none;
+    none.dsec = 0;
+    none.lo = 0;
+    none.hi = 0;
+    sm.desc[1 << kPartMaxBits] = none;
+  }
+  // per-thread constants of the flush: lane in the sector, its byte offset, the last sector it may store,
+  // and the shared-window addresses of the three tables it reads
+  const uint32_t l = tid & 3;
+  unsigned char* out_l = reinterpret_cast<unsigned char*>(out) + 8 * l;
+  const uint32_t qb_base = (uint32_t)__cvta_generic_to_shared(sm.quad_bucket);
+  const uint32_t desc_base = (uint32_t)__cvta_generic_to_shared(sm.desc);
+  const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(sm.stage);
+  const uint64_t cap_rows = (uint64_t)out_cap;
+  const uint32_t cap_sec = cap_rows > l ? (uint32_t)min((cap_rows - l + 3) >> 2, (uint64_t)0xffffffffu) : 0u;
+
+  uint32_t key[kQdI], val[kQdI];
+  auto load_tile = [&](int64_t t0) {
+    if (t0 + kQdTile <= u.row1) {  // full tile: no bounds checks
+#pragma unroll
+      for (int it = 0; it < kQdI; ++it) load_row<kAoS>(in, t0 + it * kQdT + tid, key[it], val[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < kQdI; ++it) {
+        const int64_t row = t0 + it * kQdT + tid;
+        key[it] = 0;
+        val[it] = 0;
+        if (row < u.row1) load_row<kAoS>(in, row, key[it], val[it]);
+      }
+    }
+  };
+  if (kPre && u.row0 < u.row1) load_tile(u.row0);
+
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kQdTile) {
+    // ---- (load,) hash once, rank inside the bucket (ranks continue after the carried rows) ----
+    if (!kPre) load_tile(t0);
+    uint32_t packed[kQdI];  // bucket | rank << 16
+    if (t0 + kQdTile <= u.row1 && sel.mask == 0) {
+#pragma unroll
+      for (int it = 0; it < kQdI; ++it) {
+        const uint32_t b = part_bucket(wang_hash_u32(key[it]), g.shl, g.bits);
+        packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < kQdI; ++it) {
+        const int64_t row = t0 + it * kQdT + tid;
+        packed[it] = 0xffffffffu;
+        if (row < u.row1) {
+          const uint32_t b = bucket_or_skip<false>(key[it], val[it], g, sel);
+          if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- per bucket: region (rounded up to whole quads), descriptor, carried rows into the stage ----
+    uint32_t tot = 0, c0 = 0, gh = 0;
+    if (mine) {
+      tot = sm.tile_cnt[tid];
+      c0 = sm.carried[tid];
+      gh = sm.ghost[tid];
+    }
+    const uint32_t region = (tot + 3u) & ~3u;
+    uint32_t incl = region;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    __syncthreads();
+    {
+      const uint32_t w = sm.warp_tot[lane];  // kW == 32
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < kW; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      const uint32_t all = __shfl_sync(0xffffffffu, wi, kW - 1);
+      if (tid == 0) sm.n_slots = all;
+      const uint32_t q0 = __shfl_sync(0xffffffffu, wi - w, warp) + incl - region;  // first slot of the region
+      if (mine) {
+        const uint32_t nsec = tot >> 2;
+        sm.qstart[tid] = q0;
+        QdDesc d;
+        d.dsec = sm.dsec_next[tid] - (q0 >> 2);
+        d.lo = (uint16_t)(q0 + gh);
+        d.hi = (uint16_t)(q0 + nsec * kScRows);
+        sm.desc[tid] = d;
+        // rows beyond the output's capacity are dropped by the flush (its store is predicated on the
+        // sector); the flag is raised here, once per bucket and tile, not per row
+        if (overflow && ((uint64_t)sm.dsec_next[tid] + nsec) * kScRows > cap_rows) *overflow = 1u;
+        for (uint32_t e = gh; e < c0; ++e) sm.stage[q0 + e] = sm.carry[tid * 3 + e];
+        for (uint32_t q = 0; q < (region >> 2); ++q) sm.quad_bucket[(q0 >> 2) + q] = (uint16_t)tid;
+      }
+      // quads between the last region and the end of the last flush round belong to the sentinel
+      for (uint32_t q = (all >> 2) + tid; q < (((all + kQdRound - 1) / kQdRound * kQdRound) >> 2); q += kQdT)
+        sm.quad_bucket[q] = (uint16_t)(1 << kPartMaxBits);
+    }
+    __syncthreads();
+
+    // ---- stage the tile's rows behind the carried ones ----
+#pragma unroll
+    for (int it = 0; it < kQdI; ++it) {
+      if (packed[it] != 0xffffffffu)
+        sm.stage[sm.qstart[packed[it] & 0xffffu] + (packed[it] >> 16)] = make_uint2(key[it], val[it]);
+    }
+    __syncthreads();
+
+    if (kPre && t0 + kQdTile < u.row1) load_tile(t0 + kQdTile);
+
+    // ---- flush: slot t -> sector desc.dsec + t / 4, lane t % 4; four adjacent lanes = one sector ----
+    // Written with explicit shared-window addresses and predicated stores: the compiler's version of
+    // this loop spent 35 instructions per slot on re-deriving the shared base, the output base and on
+    // four divergent branches per round (profiles/r2_scatter_probe_phases.md); this one spends ~14.
+    {
+      const uint32_t rounds = (sm.n_slots + kQdRound - 1) / kQdRound;
+      uint32_t t = tid;
+      uint64_t out_l64 = reinterpret_cast<uint64_t>(out_l);
+      asm volatile("" : "+l"(out_l64));  // opaque: keep the base in a register pair instead of re-deriving it per store
+      for (uint32_t r = 0; r < rounds; ++r, t += kQdRound) {
+        uint32_t b[kQdUn];
+        uint2 dd[kQdUn], kv[kQdUn];
+#pragma unroll
+        for (int k = 0; k < kQdUn; ++k) b[k] = lds_u16(qb_base + (((t + k * kQdT) >> 2) << 1));
+#pragma unroll
+        for (int k = 0; k < kQdUn; ++k) {
+          dd[k] = lds_v2(desc_base + b[k] * 8u);
+          kv[k] = lds_v2(stage_base + (t + k * kQdT) * 8u);
+        }
+#pragma unroll
+        for (int k = 0; k < kQdUn; ++k) {
+          const uint32_t tk = t + k * kQdT;
+          const uint32_t sector = dd[k].x + (tk >> 2);
+          const bool ok = tk >= (dd[k].y & 0xffffu) && tk < (dd[k].y >> 16) && sector < cap_sec;
+          if (ok) st_stream_v2(reinterpret_cast<uint2*>(out_l64 + (uint64_t)sector * 32u), kv[k]);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- per bucket: the tail that did not fill a sector is carried; advance; reset the counter ----
+    if (mine) {
+      const uint32_t nsec = tot >> 2, rem = tot & 3u;
+      const uint32_t from = sm.qstart[tid] + nsec * kScRows;
+      // nothing flushed: slots below ghost are still not ours; otherwise the tail starts a new sector
+      const uint32_t first = nsec ? 0u : gh;
+      for (uint32_t i = first; i < rem; ++i) sm.carry[tid * 3 + i] = sm.stage[from + i];
+      sm.dsec_next[tid] += nsec;
+      sm.carried[tid] = (uint8_t)rem;
+      if (nsec) sm.ghost[tid] = 0;
+      sm.tile_cnt[tid] = rem;
+    }
+    __syncthreads();
+  }
+
+  // ---- end of the unit: the last, partial sector of every bucket ----
+  for (int i = tid; i < P * kScRows; i += kQdT) {
+    const int b = i >> 2;
+    const uint32_t li = i & 3;
+    if (li >= sm.ghost[b] && li < sm.carried[b]) {
+      const uint64_t row = (uint64_t)sm.dsec_next[b] * kScRows + li;
+      if (row < cap_rows) st_stream_v2(out + row, sm.carry[b * 3 + li]);
+      else if (overflow) *overflow = 1u;
+    }
+  }
+}
+
+
 // Boundaries are clamped to `clamp` (the capacity of the pass's output): when a skewed hash-space
 // slice overflows its buffer the scatter drops the rows beyond it and raises *overflow; whoever reads
 // the output by these boundaries (a second pass, the probe) must not run past the buffer either.
@@ -971,10 +1219,11 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
     const bool sectors = !d_bucket_addr && !g.val_pred && (reinterpret_cast<uintptr_t>(d_out) & 31) == 0 &&
                          (uint64_t)out_cap < (1ull << 34) && g.bits >= ctx->tune[B2_TUNE_SCATTER_SECTORS_MIN_BITS];
     if (sectors) {
-      const bool big = ctx->tune[B2_TUNE_SCATTER_SECTOR_TILE] != 0;
+      const int shape = ctx->tune[B2_TUNE_SCATTER_SECTOR_TILE];
+      const bool big = shape == 1;
       const bool pre = ctx->tune[B2_TUNE_SCATTER_PREFETCH] != 0;
-      // four instantiations share one function-pointer type, so each gets its own site id
-      static const int sites[4] = {b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site()};
+      // the instantiations share one function-pointer type, so each gets its own site id
+      static const int sites[6] = {b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site()};
       auto go = [&](auto kernel, int site, int threads, size_t smem_bytes) -> int {
         if (b2_first_use_on_device(ctx, site))
           B2_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -982,7 +1231,10 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
                                                                  scanned, d_out, out_cap, d_overflow);
         return B2_OK;
       };
-      if (big) {
+      if (shape == 2) {  // quad-aligned regions: the carried rows live in the stage, the flush is three reads and a store
+        if (pre) B2_RETURN_NOT_OK(go(part_scatter_quads_kernel<kAoS, true>, sites[4], kQdT, sizeof(QdSmem)));
+        else B2_RETURN_NOT_OK(go(part_scatter_quads_kernel<kAoS, false>, sites[5], kQdT, sizeof(QdSmem)));
+      } else if (big) {
         if (pre) B2_RETURN_NOT_OK(go(part_scatter_sectors_kernel<kAoS, true, 1024, 16>, sites[0], 1024, sizeof(ScSmemT<1024, 16>)));
         else B2_RETURN_NOT_OK(go(part_scatter_sectors_kernel<kAoS, false, 1024, 16>, sites[1], 1024, sizeof(ScSmemT<1024, 16>)));
       } else {

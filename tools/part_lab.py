@@ -18,8 +18,11 @@ def main():
     p.add_argument("--parts", default="64,256,1024")
     p.add_argument("--variants", default="0,8,s")
     p.add_argument("--reps", type=int, default=5)
+    p.add_argument("--sector-tile", type=int, default=None, help="B2_TUNE_SCATTER_SECTOR_TILE: 0, 1 or 2 (quads kernel)")
     a = p.parse_args()
     ctx = Context(0)
+    if a.sector_tile is not None:
+        ctx.set_tunable(4, a.sector_tile)
     for logn in [int(x) for x in a.logn.split(",")]:
         n = 1 << logn
         key = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
