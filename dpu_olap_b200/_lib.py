@@ -126,6 +126,19 @@ SIGNATURES = {
                                                    _pu64, _pt]),
     "b2_take_u32_nullable_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _pp, _pp, _pi64, _pi64, _i64, _pp, _pp, _pt]),
     "b2_shuffle_ws_bytes": (_sz, [_i64, _int]),
+    "b2_col_upload_host": (_int, [_vp, _pp, _pi64, _i64, C.POINTER(_vp)]),
+    "b2_col_free": (_int, [_vp]),
+    "b2_col_rows": (_i64, [_vp]),
+    "b2_col_nbatches": (_i64, [_vp]),
+    "b2_col_device_ptr": (_vp, [_vp]),
+    "b2_col_batch_offsets": (_int, [_vp, _pi64, _i64]),
+    "b2_col_download_host": (_int, [_vp, _vp, _pp, _i64]),
+    "b2_col_export": (_int, [_vp, _vp]),
+    "b2_col_import": (_int, [_vp, _vp, _pi64, _i64, C.POINTER(_vp)]),
+    "b2_sum_u32_col": (_int, [_vp, _vp, _pu64]),
+    "b2_filter_lt_u32_col": (_int, [_vp, _vp, _u32, C.POINTER(_vp)]),
+    "b2_take_u32_col": (_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "b2_join_u32_col": (_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "b2_set_create": (_int, [C.POINTER(C.c_int), _int, C.POINTER(_vp)]),
     "b2_set_destroy": (_int, [_vp]),
     "b2_set_size": (_int, [_vp]),

@@ -749,6 +749,119 @@ class DeviceSet:
             self.members[0]._call(name, *args)
 
 
+class ArrowArrayStruct(C.Structure):
+    """struct ArrowArray of the Arrow C Data Interface (arrow/c/abi.h)."""
+
+
+ArrowArrayStruct._fields_ = [
+    ("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+    ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)), ("children", C.c_void_p),
+    ("dictionary", C.c_void_p), ("release", C.CFUNCTYPE(None, C.POINTER(ArrowArrayStruct))),
+    ("private_data", C.c_void_p)]
+
+
+class ArrowDeviceArrayStruct(C.Structure):
+    """struct ArrowDeviceArray of the Arrow C Device Data Interface."""
+    _fields_ = [("array", ArrowArrayStruct), ("device_id", C.c_int64), ("device_type", C.c_int32),
+                ("sync_event", C.c_void_p), ("reserved", C.c_int64 * 3)]
+
+
+ARROW_DEVICE_CUDA = 2
+
+
+class DeviceColumn:
+    """A packed uint32 column resident in HBM (b2_col): operators over DeviceColumns leave their
+    results on the device, so FilterGpu -> TakeGpu -> SumGpu style chains cross PCIe once on the way
+    in and not in between (the reference copies in and out around every operator and lists the
+    zero-copy result as future work, arrow_utils.h:28-29). export_arrow() / import_arrow() speak the
+    Arrow C Device Data Interface: zero-copy hand-over to any Arrow consumer on the same GPU."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self._h = ctx, C.c_void_p(handle)
+
+    @classmethod
+    def from_host(cls, ctx: Context, batches: Sequence[Any]) -> "DeviceColumn":
+        tab = _PtrTable([_column(b, 0) if not isinstance(b, np.ndarray) else _as_u32(b) for b in batches])
+        h = C.c_void_p()
+        ctx._ck(ctx._lib.b2_col_upload_host(ctx._h, tab.ptrs, tab.lens, tab.n, C.byref(h)), "b2_col_upload_host")
+        return cls(ctx, h.value)
+
+    @classmethod
+    def import_arrow(cls, ctx: Context, dev_array: ArrowDeviceArrayStruct, batch_lens: Sequence[int] | None = None):
+        """Takes over an ArrowDeviceArray (its release callback moves to the column)."""
+        n = len(batch_lens) if batch_lens else 0
+        lens = (C.c_int64 * max(n, 1))(*(batch_lens or [0]))
+        h = C.c_void_p()
+        ctx._ck(ctx._lib.b2_col_import(ctx._h, C.byref(dev_array), lens if n else None, n, C.byref(h)), "b2_col_import")
+        return cls(ctx, h.value)
+
+    def export_arrow(self) -> ArrowDeviceArrayStruct:
+        """Zero-copy ArrowDeviceArray view; the device memory lives until its release() has run."""
+        a = ArrowDeviceArrayStruct()
+        self.ctx._ck(self.ctx._lib.b2_col_export(self._h, C.byref(a)), "b2_col_export")
+        return a
+
+    @property
+    def rows(self) -> int:
+        return int(self.ctx._lib.b2_col_rows(self._h))
+
+    @property
+    def nbatches(self) -> int:
+        return int(self.ctx._lib.b2_col_nbatches(self._h))
+
+    @property
+    def device_ptr(self) -> int:
+        return int(self.ctx._lib.b2_col_device_ptr(self._h) or 0)
+
+    def batch_offsets(self) -> np.ndarray:
+        out = np.zeros(self.nbatches + 1, dtype=np.int64)
+        self.ctx._ck(self.ctx._lib.b2_col_batch_offsets(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size),
+                     "b2_col_batch_offsets")
+        return out
+
+    def to_host(self) -> list[np.ndarray]:
+        off = self.batch_offsets()
+        outs = [np.empty(int(off[b + 1] - off[b]), dtype=np.uint32) for b in range(self.nbatches)]
+        ptrs = (C.c_void_p * max(self.nbatches, 1))(*[o.ctypes.data for o in outs])
+        self.ctx._ck(self.ctx._lib.b2_col_download_host(self.ctx._h, self._h, ptrs, self.nbatches), "b2_col_download_host")
+        return outs
+
+    # ---- operators: results stay on the device ----
+    def sum(self) -> int:
+        out = C.c_uint64(0)
+        self.ctx._ck(self.ctx._lib.b2_sum_u32_col(self.ctx._h, self._h, C.byref(out)), "b2_sum_u32_col")
+        return int(out.value)
+
+    def filter_lt(self, threshold: int = 1 << 30) -> "DeviceColumn":
+        h = C.c_void_p()
+        self.ctx._ck(self.ctx._lib.b2_filter_lt_u32_col(self.ctx._h, self._h, int(threshold), C.byref(h)),
+                     "b2_filter_lt_u32_col")
+        return DeviceColumn(self.ctx, h.value)
+
+    def take(self, indices: "DeviceColumn") -> "DeviceColumn":
+        h = C.c_void_p()
+        self.ctx._ck(self.ctx._lib.b2_take_u32_col(self.ctx._h, self._h, indices._h, C.byref(h)), "b2_take_u32_col")
+        return DeviceColumn(self.ctx, h.value)
+
+    @staticmethod
+    def join(fk: "DeviceColumn", y: "DeviceColumn", pk: "DeviceColumn", x: "DeviceColumn"):
+        ctx = fk.ctx
+        hs = [C.c_void_p() for _ in range(3)]
+        ctx._ck(ctx._lib.b2_join_u32_col(ctx._h, fk._h, y._h, pk._h, x._h, *[C.byref(h) for h in hs]), "b2_join_u32_col")
+        return tuple(DeviceColumn(ctx, h.value) for h in hs)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self.ctx._lib.b2_col_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 FILTER_THRESHOLD = 1 << 30  # predicate v < 2^30: filter.c:25, filter_native.cc:59
 
 

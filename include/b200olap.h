@@ -161,6 +161,75 @@ int b2_host_free_pinned(void* p);
 int b2_host_register(const void* p, size_t bytes);
 int b2_host_unregister(const void* p);
 
+/* ---- device-resident columns and the Arrow C Device Data Interface ---------------------------------
+ * The reference copies every operator's input to the DPUs and every result back
+ * (arrow_copy_to_dpus / arrow_copy_from_dpus*, host/dpuext/arrow_utils.cc:47-73,147-266) and lists
+ * "results without a copy" as future work itself (arrow_utils.h:28-29). A b2_col is one packed,
+ * non-null uint32 column in HBM plus its batch boundaries (host-side metadata). Operators over b2_cols
+ * leave their results in HBM, so chains such as filter -> take -> sum or join -> sum cross PCIe once
+ * on the way in and not at all in between; b2_col_export / b2_col_import hand a column to, or take one
+ * from, any Arrow consumer on the same GPU as an ArrowDeviceArray WITHOUT a copy:
+ *   device_type = ARROW_DEVICE_CUDA, device_id = the ctx's device, array.buffers = {NULL, device pointer},
+ *   sync_event = cudaEvent_t* recorded after the kernels that produced the column.
+ * The struct definitions below are the ones of the Arrow specification (arrow/c/abi.h), under the
+ * specification's own include guards, so this header and Arrow's can be included together.
+ * Ownership: b2_col_free drops the handle; an exported array keeps the device memory alive until its
+ * release callback has run as well. b2_col_import MOVES the array (its release is set to NULL) and the
+ * column calls the producer's release when it dies. All *_col operators run on the ctx's own compute
+ * stream and are synchronous at return only where they return host data (sum, the filter's chunk
+ * boundaries, the join's row count). */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+#define ARROW_DEVICE_CUDA_HOST 3
+struct ArrowDeviceArray {
+  struct ArrowArray array;
+  int64_t device_id;
+  ArrowDeviceType device_type;
+  void* sync_event;
+  int64_t reserved[3];
+};
+#endif
+typedef struct b2_col b2_col;
+/* Host batches -> one packed device column (the only H2D copy of a chain). */
+int b2_col_upload_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_t* batch_lens, int64_t nbatches,
+                       b2_col** out);
+int b2_col_free(b2_col* col);
+int64_t b2_col_rows(const b2_col* col);
+int64_t b2_col_nbatches(const b2_col* col);
+const uint32_t* b2_col_device_ptr(const b2_col* col);
+/* out[0 .. nbatches]: batch boundaries in rows (capacity >= nbatches + 1). */
+int b2_col_batch_offsets(const b2_col* col, int64_t* out, int64_t capacity);
+/* Batch b of the column -> out_ptrs[b] (the only D2H copy of a chain). Synchronous. */
+int b2_col_download_host(b2_ctx* ctx, const b2_col* col, uint32_t* const* out_ptrs, int64_t nbatches);
+int b2_col_export(b2_col* col, struct ArrowDeviceArray* out);
+/* batch_lens / nbatches describe how the array's rows split into record batches (NULL / 0: one batch). */
+int b2_col_import(b2_ctx* ctx, struct ArrowDeviceArray* in, const int64_t* batch_lens, int64_t nbatches, b2_col** out);
+/* The operators over device columns (semantics of the *_host entry points above). The filter's result
+ * has one chunk per input batch; take is batch-local; the join's three result columns have one chunk. */
+int b2_sum_u32_col(b2_ctx* ctx, const b2_col* col, uint64_t* sum);
+int b2_filter_lt_u32_col(b2_ctx* ctx, const b2_col* col, uint32_t threshold, b2_col** out);
+int b2_take_u32_col(b2_ctx* ctx, const b2_col* values, const b2_col* indices, b2_col** out);
+int b2_join_u32_col(b2_ctx* ctx, const b2_col* fk, const b2_col* y, const b2_col* pk, const b2_col* x, b2_col** out_fk,
+                    b2_col** out_y, b2_col** out_x);
+
 /* ---- synthetic inputs (replaces host/generator for device-resident benchmarks) ----------- */
 /* One array per batch, bit-identical to arrow::random::RandomArrayGenerator's
  * GenerateTypedDataNoNan for uint32 (host/generator/random.cc:103-109):
