@@ -1136,6 +1136,26 @@ def bench_e2e_ops(ctx, D, args) -> dict:
         raise SystemExit("e2e join self-check failed")
     res["join"] = {"value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms,
                    "api": "b2_join_u32_host + b2_join_fetch_host (JoinGpu::Run)", **leg(t1, t2)}
+    # the same join over DEVICE-RESIDENT columns (b2_col, what an Arrow consumer hands over as
+    # ArrowDeviceArrays): the inputs are already in HBM, only the result columns cross PCIe
+    from dpu_olap_b200.ops import DeviceColumn
+    cols = [DeviceColumn.from_host(ctx, [t.numpy().view(np.uint32)]) for t in (fk, y, pk, x)]
+
+    def dstep():
+        outs = DeviceColumn.join(*cols)
+        ptrs = [(C.c_void_p * 1)(t.data_ptr()) for t in o]
+        for c, p in zip(outs, ptrs):
+            ctx._ck(lib.b2_col_download_host(h, c._h, p, 1), "b2_col_download_host")
+            c.close()
+    ms_d = timed(dstep)
+    if triple_checksum_torch(*[t.cuda() for t in o]) != exp:
+        raise SystemExit("e2e device-column join self-check failed")
+    res["join"]["device_inputs"] = {"value": n / (ms_d * 1e-3), "unit": "rows/s", "ms_per_step": ms_d,
+                                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 12 * n,
+                                    "api": "b2_join_u32_col over b2_col inputs (ArrowDeviceArray hand-over), "
+                                           "b2_col_download_host for the three result columns"}
+    for c in cols:
+        c.close()
     del x, pk, y, fk, o
     free_all()
     return res
