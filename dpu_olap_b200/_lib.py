@@ -107,6 +107,10 @@ SIGNATURES = {
     "b2_join_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pp, _pi64, _i64, _pu64, _pt]),
     "b2_join_fetch_host": (_int, [_vp, _vp, _vp, _vp, _i64, _pt]),
     "b2_join_dest_rank": (_int, [_u32, _int]),
+    "b2_join_u32_nullable_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _pp, _pp, _pi64, _pi64, _i64, _pu64, _pt]),
+    "b2_join_table_host": (_int, [_vp, _pp, _pi64, _i64, C.POINTER(C.c_int), _int, _pp, _pi64, _i64,
+                                  C.POINTER(C.c_int), _int, _pu64, _pt]),
+    "b2_join_table_fetch_host": (_int, [_vp, _pp, _int, _i64, _pt]),
     "b2_join_cols_u32_host": (_int, [_vp, _pp, _pi64, _i64, _int, _pp, _pi64, _i64, _int, _pu64, _pt]),
     "b2_join_cols_fetch_host": (_int, [_vp, _pp, _int, _i64, _pt]),
     "b2_join_aggr_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pp, _pi64, _i64, _int, _u32, _vp, _pt]),

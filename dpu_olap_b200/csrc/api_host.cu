@@ -1024,6 +1024,143 @@ int b2_filter_lt_32_host_into(b2_ctx* ctx, const void* const* batch_ptrs, const 
                                 static_cast<uint32_t*>(out), out_capacity, out_counts, total, timings);
 }
 
+// ---- join with NULLABLE keys --------------------------------------------------
+// Arrow's inner hash join (the reference's oracle, join_native.cc:31-36) never matches a null key,
+// on either side; the DPU path has no bitmaps at all. Rows with a null key are dropped ON THE DEVICE
+// before the join, with kernels that already exist: iota -> nullable filter (keeps the row numbers
+// whose key is valid) -> take(key), take(payload) -> the plain join. A side without nulls skips it.
+namespace {
+int drop_null_keys(b2_ctx* ctx, Scratch* sc, const uint32_t* d_key, const uint32_t* d_pay, int64_t n,
+                   const std::vector<uint8_t>& bits, const uint32_t** key_out, const uint32_t** pay_out,
+                   int64_t* n_out, cudaStream_t s) {
+  B2_REQUIRE(ctx, n < (1ll << 32) - 1, "row numbers travel as uint32");
+  uint8_t* d_valid = nullptr;
+  uint32_t *d_iota = nullptr, *d_idx = nullptr, *d_k = nullptr, *d_p = nullptr;
+  int64_t *d_end = nullptr, *d_total = nullptr;
+  void* d_ws = nullptr;
+  B2_RETURN_NOT_OK(sc->alloc(ctx, (void**)&d_valid, bits.size()));
+  B2_RETURN_NOT_OK(sc->alloc(ctx, (void**)&d_iota, (size_t)n * 4));
+  B2_RETURN_NOT_OK(sc->alloc(ctx, (void**)&d_idx, (size_t)n * 4));
+  B2_RETURN_NOT_OK(sc->alloc(ctx, (void**)&d_end, 8));
+  B2_RETURN_NOT_OK(sc->alloc(ctx, (void**)&d_total, 8));
+  const size_t ws_bytes = b2_filter_ws_bytes(1, n);
+  B2_RETURN_NOT_OK(sc->alloc(ctx, &d_ws, ws_bytes));
+  B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
+  B2_RETURN_NOT_OK(b2_iota_u32_dev(ctx, 0, n, d_iota, s));
+  // every row number is below 0xffffffff, so the predicate keeps exactly the rows whose key is valid
+  B2_RETURN_NOT_OK(b2_filter_lt_u32_nullable_dev(ctx, d_iota, d_valid, 1, n, 0xffffffffu, d_idx, d_end, d_total,
+                                                 nullptr, d_ws, ws_bytes, s));
+  int64_t kept = 0;
+  B2_CUDA_OK(ctx, cudaMemcpyAsync(&kept, d_total, 8, cudaMemcpyDeviceToHost, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  B2_RETURN_NOT_OK(sc->alloc(ctx, (void**)&d_k, (size_t)kept * 4));
+  B2_RETURN_NOT_OK(sc->alloc(ctx, (void**)&d_p, (size_t)kept * 4));
+  if (kept > 0) {
+    B2_RETURN_NOT_OK(b2_take_u32_dev(ctx, d_key, n, d_idx, kept, 1, d_k, s));
+    B2_RETURN_NOT_OK(b2_take_u32_dev(ctx, d_pay, n, d_idx, kept, 1, d_p, s));
+  }
+  *key_out = d_k;
+  *pay_out = d_p;
+  *n_out = kept;
+  return B2_OK;
+}
+}  // namespace
+
+int b2_join_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const uint8_t* const* l_key_valid_ptrs,
+                              const int64_t* l_key_valid_bit_offsets, const int64_t* l_lens, int64_t nl_batches,
+                              const uint32_t* const* r_ptrs, const uint8_t* const* r_key_valid_ptrs,
+                              const int64_t* r_key_valid_bit_offsets, const int64_t* r_lens, int64_t nr_batches,
+                              uint64_t* out_rows, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, out_rows != nullptr, "out_rows is null");
+  Layout LL, LR;
+  B2_RETURN_NOT_OK(make_layout(ctx, l_ptrs, l_lens, nl_batches, &LL));
+  B2_RETURN_NOT_OK(make_layout(ctx, r_ptrs, r_lens, nr_batches, &LR));
+  std::vector<uint8_t> lbits, rbits;
+  const bool lnull = pack_validity(&lbits, LL, l_key_valid_ptrs, l_key_valid_bit_offsets, nl_batches);
+  const bool rnull = pack_validity(&rbits, LR, r_key_valid_ptrs, r_key_valid_bit_offsets, nr_batches);
+  if (!lnull && !rnull)  // no bitmap anywhere: the plain join
+    return b2_join_u32_host(ctx, l_ptrs, l_lens, nl_batches, r_ptrs, r_lens, nr_batches, out_rows, timings);
+  cudaStream_t s = ctx->s_compute;
+  Scratch sc;
+  b2_timings tm{};
+  const int64_t nl = LL.rows(), nr = LR.rows();
+  uint32_t *d_fk, *d_y, *d_pk, *d_x;
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_fk, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_y, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_pk, (size_t)nr * 4));
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_x, (size_t)nr * 4));
+  cudaEvent_t e0, e1, e2;
+  B2_RETURN_NOT_OK(sc.event(ctx, &e0, true));
+  B2_RETURN_NOT_OK(sc.event(ctx, &e1, true));
+  B2_RETURN_NOT_OK(sc.event(ctx, &e2, true));
+  B2_CUDA_OK(ctx, cudaEventRecord(e0, s));
+  gather_begin(ctx, 2 * (nl_batches + nr_batches), 2 * (nl + nr));
+  B2_RETURN_NOT_OK(upload(ctx, d_fk, LL, l_ptrs, 0, nl_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload(ctx, d_y, LL, l_ptrs + nl_batches, 0, nl_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload(ctx, d_pk, LR, r_ptrs, 0, nr_batches, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload(ctx, d_x, LR, r_ptrs + nr_batches, 0, nr_batches, s, &tm.h2d_bytes));
+  B2_CUDA_OK(ctx, cudaEventRecord(e1, s));
+  const uint32_t *k_l = d_fk, *p_l = d_y, *k_r = d_pk, *p_r = d_x;
+  int64_t ml = nl, mr = nr;
+  if (lnull) B2_RETURN_NOT_OK(drop_null_keys(ctx, &sc, d_fk, d_y, nl, lbits, &k_l, &p_l, &ml, s));
+  if (rnull) B2_RETURN_NOT_OK(drop_null_keys(ctx, &sc, d_pk, d_x, nr, rbits, &k_r, &p_r, &mr, s));
+  void* d_ws = nullptr;
+  const size_t ws_bytes = b2_join_ws_bytes(ml, mr);
+  B2_RETURN_NOT_OK(sc.alloc(ctx, &d_ws, ws_bytes));
+  uint64_t* d_rows = nullptr;
+  B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_rows, 8));
+  int64_t cap = ml;
+  uint32_t *o_fk = nullptr, *o_y = nullptr, *o_x = nullptr;
+  uint64_t rows = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2_RETURN_NOT_OK(dev_alloc(ctx, (void**)&o_fk, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(dev_alloc(ctx, (void**)&o_y, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(dev_alloc(ctx, (void**)&o_x, (size_t)cap * 4));
+    int rc = b2_join_u32_dev(ctx, k_l, p_l, ml, k_r, p_r, mr, o_fk, o_y, o_x, cap, d_rows, 0, d_ws, ws_bytes, s);
+    if (rc == B2_OK && (cudaMemcpyAsync(&rows, d_rows, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                        cudaStreamSynchronize(s) != cudaSuccess))
+      rc = b2_set_error(ctx, B2_ERR_CUDA, "join row count", cudaGetErrorString(cudaGetLastError()));
+    if (rc == B2_OK && rows == ~0ull) rc = b2_set_error(ctx, B2_ERR_WORKSPACE, "join", "slice overflow");
+    if (rc == B2_OK && (int64_t)rows > cap && attempt == 1)
+      rc = b2_set_error(ctx, B2_ERR_OVERFLOW, "join", "output larger than reported");
+    if (rc != B2_OK || (int64_t)rows > cap) {
+      for (uint32_t* p : {o_fk, o_y, o_x}) b2_dev_free(ctx, p);
+      if (rc != B2_OK) return rc;
+      cap = (int64_t)rows;
+      continue;
+    }
+    break;
+  }
+  B2_CUDA_OK(ctx, cudaEventRecord(e2, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  b2_pending* pend = new b2_pending();
+  pend->kind = b2_pending::kJoin;
+  pend->d_fk = o_fk;
+  pend->d_y = o_y;
+  pend->d_x = o_x;
+  pend->rows = rows;
+  for (uint32_t* p : {o_fk, o_y, o_x}) pend->dev.push_back(p);
+  ctx->pending = pend;
+  *out_rows = rows;
+  float up = 0, work = 0;
+  cudaEventElapsedTime(&up, e0, e1);
+  cudaEventElapsedTime(&work, e1, e2);
+  tm.copy_to_dev_ms = up;
+  tm.dev_work_ms = work;
+  tm.h2d_bytes += (int64_t)(lnull ? lbits.size() : 0) + (int64_t)(rnull ? rbits.size() : 0);
+  tm.d2h_bytes = 8;
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
 int b2_take_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* value_ptrs,
                               const uint8_t* const* value_valid_ptrs, const int64_t* value_valid_bit_offsets,
                               const int64_t* value_lens, const uint32_t* const* idx_ptrs,

@@ -489,6 +489,246 @@ int b2_join_cols_fetch_host(b2_ctx* ctx, uint32_t* const* out_cols, int ncols, i
   return B2_OK;
 }
 
+// ---- join over a typed table: 32- or 64-bit keys, any number of 32- or 64-bit payload columns ---------
+// The reference's table can hold 64-bit keys (HT_64BIT_KEYS, dpu/shared/hashtable/hashtable.h:14-18) and
+// JoinDpu carries every non-key column (join_dpu.cc:127-138,325-341). The radix passes and the probe
+// kernel move 8-byte (key, payload) pairs; wider rows go through them by reference:
+//   * the pair's payload is the ROW NUMBER, every output column is gathered afterwards with the take
+//     kernels (32- and 64-bit);
+//   * a 64-bit key is folded to 32 bits for partitioning and probing — equal keys have equal folds, so
+//     the candidate (left row, right row) pairs are a superset of the result — and every candidate is
+//     verified against the full 64-bit keys; the survivors are compacted with the filter kernel.
+namespace {
+
+__global__ void __launch_bounds__(256)
+fold_u64_kernel(const uint64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const uint64_t k = in[i];
+    out[i] = (uint32_t)k ^ ((uint32_t)(k >> 32) * 0x9E3779B1u);
+  }
+}
+// sel[i] = i when candidate pair i joins two rows with the SAME 64-bit key, else 0xffffffff
+__global__ void __launch_bounds__(256)
+verify_u64_kernel(const uint64_t* __restrict__ lkeys, const uint64_t* __restrict__ rkeys,
+                  const uint32_t* __restrict__ lid, const uint32_t* __restrict__ rid, int64_t n,
+                  uint32_t* __restrict__ sel) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    sel[i] = lkeys[lid[i]] == rkeys[rid[i]] ? (uint32_t)i : 0xffffffffu;
+}
+
+int upload_wide(b2_ctx* ctx, void* d_col, const void* const* ptrs, const int64_t* lens, int64_t nbatches, int bytes,
+                cudaStream_t s, int64_t* total) {
+  char* dst = static_cast<char*>(d_col);
+  for (int64_t b = 0; b < nbatches; ++b) {
+    if (lens[b] == 0) continue;
+    B2_REQUIRE(ctx, ptrs[b] != nullptr, "null batch pointer");
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(dst, ptrs[b], (size_t)lens[b] * bytes, cudaMemcpyHostToDevice, s));
+    dst += (size_t)lens[b] * bytes;
+    *total += lens[b] * bytes;
+  }
+  return B2_OK;
+}
+
+int gather_col(b2_ctx* ctx, const void* d_col, int64_t col_rows, int bytes, const uint32_t* ids, int64_t rows,
+               void* d_out, cudaStream_t s) {
+  if (rows == 0) return B2_OK;
+  if (bytes == 8) return b2_take_64_dev(ctx, d_col, col_rows, ids, rows, 1, d_out, s);
+  return b2_take_u32_dev(ctx, static_cast<const uint32_t*>(d_col), col_rows, ids, rows, 1,
+                         static_cast<uint32_t*>(d_out), s);
+}
+
+}  // namespace
+
+int b2_join_table_host(b2_ctx* ctx, const void* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                       const int* l_col_bytes, int nl_cols, const void* const* r_ptrs, const int64_t* r_lens,
+                       int64_t nr_batches, const int* r_col_bytes, int nr_cols, uint64_t* out_rows,
+                       b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  B2_REQUIRE(ctx, nl_cols >= 1 && nl_cols <= 65 && nr_cols >= 1 && nr_cols <= 65, "1 key + 0..64 payload columns per side");
+  B2_REQUIRE(ctx, l_col_bytes && r_col_bytes && out_rows, "null argument");
+  B2_REQUIRE(ctx, nl_batches >= 0 && nr_batches >= 0, "negative batch count");
+  B2_REQUIRE(ctx, nl_batches == 0 || (l_ptrs && l_lens), "null left batch table");
+  B2_REQUIRE(ctx, nr_batches == 0 || (r_ptrs && r_lens), "null right batch table");
+  for (int c = 0; c < nl_cols; ++c) B2_REQUIRE(ctx, l_col_bytes[c] == 4 || l_col_bytes[c] == 8, "columns are 4 or 8 bytes wide");
+  for (int c = 0; c < nr_cols; ++c) B2_REQUIRE(ctx, r_col_bytes[c] == 4 || r_col_bytes[c] == 8, "columns are 4 or 8 bytes wide");
+  B2_REQUIRE(ctx, l_col_bytes[0] == r_col_bytes[0], "both key columns must have the same width");
+  const int kb = l_col_bytes[0];
+  int64_t nl = 0, nr = 0;
+  B2_RETURN_NOT_OK(total_rows(ctx, l_lens, nl_batches, &nl));
+  B2_RETURN_NOT_OK(total_rows(ctx, r_lens, nr_batches, &nr));
+  B2_REQUIRE(ctx, nl < (1ll << 32) - 1 && nr < (1ll << 32) - 1, "row numbers travel as uint32");
+  b2_timings tm{};
+  DevBufs bufs;
+  EventPair up, work;
+  B2_RETURN_NOT_OK(up.init(ctx));
+  B2_RETURN_NOT_OK(work.init(ctx));
+  cudaStream_t s = ctx->s_compute;
+  const int64_t grid_cap = (int64_t)ctx->sm_count * 16;
+  auto grid_for = [&](int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, grid_cap)); };
+  void *d_lkey = nullptr, *d_rkey = nullptr;
+  uint32_t *d_lk32 = nullptr, *d_rk32 = nullptr, *d_lid = nullptr, *d_rid = nullptr;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_lkey, (size_t)nl * kb));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_rkey, (size_t)nr * kb));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_lid, (size_t)nl * 4));
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_rid, (size_t)nr * 4));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.a, s));
+  B2_RETURN_NOT_OK(upload_wide(ctx, d_lkey, l_ptrs, l_lens, nl_batches, kb, s, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_wide(ctx, d_rkey, r_ptrs, r_lens, nr_batches, kb, s, &tm.h2d_bytes));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.b, s));
+  B2_CUDA_OK(ctx, cudaEventRecord(work.a, s));
+  if (kb == 8) {
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_lk32, (size_t)nl * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_rk32, (size_t)nr * 4));
+    if (nl > 0) {
+      fold_u64_kernel<<<grid_for(nl), 256, 0, s>>>(static_cast<const uint64_t*>(d_lkey), nl, d_lk32);
+      B2_LAUNCH_CHECK(ctx, "fold_u64_kernel");
+    }
+    if (nr > 0) {
+      fold_u64_kernel<<<grid_for(nr), 256, 0, s>>>(static_cast<const uint64_t*>(d_rkey), nr, d_rk32);
+      B2_LAUNCH_CHECK(ctx, "fold_u64_kernel");
+    }
+  } else {
+    d_lk32 = static_cast<uint32_t*>(d_lkey);
+    d_rk32 = static_cast<uint32_t*>(d_rkey);
+  }
+  B2_RETURN_NOT_OK(b2_iota_u32_dev(ctx, 0, nl, d_lid, s));
+  B2_RETURN_NOT_OK(b2_iota_u32_dev(ctx, 0, nr, d_rid, s));
+  void* d_ws = nullptr;
+  const size_t ws_bytes = b2_join_ws_bytes(nl, nr);
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_ws, ws_bytes));
+  uint64_t* d_rows = nullptr;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_rows, 8));
+  int64_t cap = nl;
+  uint32_t *o_k = nullptr, *o_lid = nullptr, *o_rid = nullptr;
+  uint64_t cand = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_k, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_lid, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_rid, (size_t)cap * 4));
+    B2_RETURN_NOT_OK(b2_join_u32_dev(ctx, d_lk32, d_lid, nl, d_rk32, d_rid, nr, o_k, o_lid, o_rid, cap, d_rows, 0, d_ws,
+                                     ws_bytes, s));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(&cand, d_rows, 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    if (cand == ~0ull) return b2_set_error(ctx, B2_ERR_WORKSPACE, "join", "slice overflow");
+    if ((int64_t)cand <= cap) break;
+    if (attempt == 1) return b2_set_error(ctx, B2_ERR_OVERFLOW, "join", "output larger than reported");
+    for (uint32_t* p : {o_k, o_lid, o_rid}) {
+      bufs.release(p);
+      b2_dev_free(ctx, p);
+    }
+    cap = (int64_t)cand;
+  }
+  B2_REQUIRE(ctx, cand < 0xffffffffull, "more than 2^32 - 2 candidate pairs");
+  bufs.release(d_ws);
+  b2_dev_free(ctx, d_ws);
+  int64_t rows = (int64_t)cand;
+  const uint32_t *lids = o_lid, *rids = o_rid;
+  if (kb == 8 && cand > 0) {  // folds collide: keep the candidates whose full keys are equal
+    uint32_t *d_sel = nullptr, *d_surv = nullptr, *d_l2 = nullptr, *d_r2 = nullptr;
+    int64_t *d_end = nullptr, *d_total = nullptr;
+    void* d_fws = nullptr;
+    const size_t fws = b2_filter_ws_bytes(1, (int64_t)cand);
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_sel, (size_t)cand * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_surv, (size_t)cand * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_end, 8));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_total, 8));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_fws, fws));
+    verify_u64_kernel<<<grid_for((int64_t)cand), 256, 0, s>>>(static_cast<const uint64_t*>(d_lkey),
+                                                              static_cast<const uint64_t*>(d_rkey), o_lid, o_rid,
+                                                              (int64_t)cand, d_sel);
+    B2_LAUNCH_CHECK(ctx, "verify_u64_kernel");
+    B2_RETURN_NOT_OK(b2_filter_lt_u32_dev(ctx, d_sel, 1, (int64_t)cand, 0xffffffffu, d_surv, d_end, d_total, nullptr,
+                                          d_fws, fws, s));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(&rows, d_total, 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_l2, (size_t)std::max<int64_t>(rows, 1) * 4));
+    B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_r2, (size_t)std::max<int64_t>(rows, 1) * 4));
+    if (rows > 0) {
+      B2_RETURN_NOT_OK(b2_take_u32_dev(ctx, o_lid, (int64_t)cand, d_surv, rows, 1, d_l2, s));
+      B2_RETURN_NOT_OK(b2_take_u32_dev(ctx, o_rid, (int64_t)cand, d_surv, rows, 1, d_r2, s));
+    }
+    lids = d_l2;
+    rids = d_r2;
+  }
+  // result columns: the key, the left payloads, the right payloads — each gathered by row number
+  b2_pending* pend = new b2_pending();
+  pend->kind = b2_pending::kJoinTable;
+  pend->rows = (uint64_t)rows;
+  ctx->pending = pend;
+  auto add_out = [&](int bytes, void** out) -> int {
+    B2_RETURN_NOT_OK(b2_dev_alloc(ctx, out, (size_t)std::max<int64_t>(rows, 1) * bytes));
+    pend->dev.push_back(*out);
+    pend->t_cols.push_back(*out);
+    pend->t_bytes.push_back(bytes);
+    return B2_OK;
+  };
+  void* d_out = nullptr;
+  B2_RETURN_NOT_OK(add_out(kb, &d_out));
+  B2_RETURN_NOT_OK(gather_col(ctx, d_lkey, nl, kb, lids, rows, d_out, s));
+  void* d_col = nullptr;
+  B2_RETURN_NOT_OK(bufs.alloc(ctx, &d_col, (size_t)std::max(nl, nr) * 8));
+  for (int side = 0; side < 2; ++side) {
+    const int nc = side == 0 ? nl_cols : nr_cols;
+    const int* cb = side == 0 ? l_col_bytes : r_col_bytes;
+    const void* const* ptrs = side == 0 ? l_ptrs : r_ptrs;
+    const int64_t* lens = side == 0 ? l_lens : r_lens;
+    const int64_t nb = side == 0 ? nl_batches : nr_batches;
+    const int64_t n = side == 0 ? nl : nr;
+    for (int c = 1; c < nc; ++c) {
+      B2_RETURN_NOT_OK(add_out(cb[c], &d_out));
+      B2_RETURN_NOT_OK(upload_wide(ctx, d_col, ptrs + (size_t)c * nb, lens, nb, cb[c], s, &tm.h2d_bytes));
+      B2_RETURN_NOT_OK(gather_col(ctx, d_col, n, cb[c], side == 0 ? lids : rids, rows, d_out, s));
+    }
+  }
+  B2_CUDA_OK(ctx, cudaEventRecord(work.b, s));
+  B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  pend->ncols = (int)pend->t_cols.size();
+  *out_rows = (uint64_t)rows;
+  tm.copy_to_dev_ms = up.ms();
+  tm.dev_work_ms = work.ms();
+  tm.d2h_bytes = 8;
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
+int b2_join_table_fetch_host(b2_ctx* ctx, void* const* out_cols, int ncols, int64_t capacity_rows, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  const auto t0 = Clock::now();
+  b2_pending* pend = ctx->pending;
+  if (!pend || pend->kind != b2_pending::kJoinTable)
+    return b2_set_error(ctx, B2_ERR_INVALID, "b2_join_table_fetch_host", "no pending join result");
+  B2_REQUIRE(ctx, ncols == pend->ncols && (out_cols || ncols == 0), "column count differs from the run");
+  if ((uint64_t)capacity_rows < pend->rows)
+    return b2_set_error(ctx, B2_ERR_OVERFLOW, "b2_join_table_fetch_host", "capacity_rows < result rows");
+  b2_timings tm{};
+  if (pend->rows > 0) {
+    EventPair ev;
+    B2_RETURN_NOT_OK(ev.init(ctx));
+    cudaStream_t s = ctx->s_copy_out;
+    B2_CUDA_OK(ctx, cudaEventRecord(ev.a, s));
+    for (int c = 0; c < ncols; ++c) {
+      B2_REQUIRE(ctx, out_cols[c] != nullptr, "null output column");
+      const size_t bytes = (size_t)pend->rows * (size_t)pend->t_bytes[(size_t)c];
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(out_cols[c], pend->t_cols[(size_t)c], bytes, cudaMemcpyDeviceToHost, s));
+      tm.d2h_bytes += (int64_t)bytes;
+    }
+    B2_CUDA_OK(ctx, cudaEventRecord(ev.b, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    tm.copy_from_dev_ms = ev.ms();
+  }
+  tm.total_ms = ms_since(t0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
 int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
                        int64_t capacity_rows, b2_timings* timings) {
   if (!ctx) return B2_ERR_INVALID;

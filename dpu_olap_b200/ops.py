@@ -85,6 +85,27 @@ def _column(batch: Any, name_or_index) -> np.ndarray:
     return _as_u32(batch)
 
 
+def _raw_column(batch: Any, name: str) -> np.ndarray:
+    """One non-null column of one batch as a contiguous numpy array of ITS OWN fixed-width type
+    (4 or 8 bytes per element): what b2_join_table_host moves as raw words."""
+    if pa is not None and isinstance(batch, pa.RecordBatch):
+        col = batch.column(batch.schema.get_field_index(name))
+        if col.null_count:
+            raise ValueError("the typed-table join takes non-null columns")
+        a = col.to_numpy(zero_copy_only=True)
+    else:
+        a = np.ascontiguousarray(np.asarray(batch[name]))
+    if a.dtype.kind not in "uif" or a.dtype.itemsize not in (4, 8):
+        raise TypeError(f"column {name!r}: expected a 32- or 64-bit numeric type, got {a.dtype}")
+    return a
+
+
+def _column_dtype(batch: Any, name: str) -> np.dtype:
+    if pa is not None and isinstance(batch, pa.RecordBatch):
+        return np.dtype(batch.schema.field(name).type.to_pandas_dtype())
+    return np.asarray(batch[name]).dtype
+
+
 # 32-bit column types the filter compares natively (b2_dtype32, include/b200olap.h)
 _DTYPES32 = {np.dtype(np.uint32): 0, np.dtype(np.int32): 1, np.dtype(np.float32): 2}
 _DTYPES64 = {np.dtype(np.uint64): 3, np.dtype(np.int64): 4}  # b2_dtype64 (aggregates only)
@@ -1079,8 +1100,27 @@ class JoinGpu:
             raise ValueError("left and right payload columns must have distinct names")
         self.lpay = self.lpays[0] if len(self.lpays) == 1 else None
         self.rpay = self.rpays[0] if len(self.rpays) == 1 else None
-        self._l = [[_column(b, c) for b in left_batches] for c in [fk] + self.lpays]
-        self._r = [[_column(b, c) for b in right_batches] for c in [pk] + self.rpays]
+        # any column that is not uint32 (64-bit keys, HT_64BIT_KEYS hashtable.h:14-18; int / float /
+        # 64-bit payloads) sends the join through the typed-table entry point
+        self._typed = None
+        if len(left_batches) and len(right_batches):
+            ldt = [_column_dtype(left_batches[0], c) for c in [fk] + self.lpays]
+            rdt = [_column_dtype(right_batches[0], c) for c in [pk] + self.rpays]
+            if any(d != np.dtype(np.uint32) for d in ldt + rdt):
+                if ldt[0].itemsize != rdt[0].itemsize or ldt[0].kind == "f":
+                    raise TypeError(f"join keys must be integers of one width, got {ldt[0]} / {rdt[0]}")
+                self._typed = (ldt, rdt)
+                self._l = [[_raw_column(b, c) for b in left_batches] for c in [fk] + self.lpays]
+                self._r = [[_raw_column(b, c) for b in right_batches] for c in [pk] + self.rpays]
+                self._timers = None
+                return
+        # key columns may carry nulls (a null key never matches, as in Arrow's hash join); payloads may not
+        lkeys = [_nullable_column(b, fk) for b in left_batches]
+        rkeys = [_nullable_column(b, pk) for b in right_batches]
+        self._lkv, self._rkv = _ValidTable(lkeys), _ValidTable(rkeys)
+        self._l = [[c.values for c in lkeys]] + [[_column(b, c) for b in left_batches] for c in self.lpays]
+        self._r = [[c.values for c in rkeys]] + [[_column(b, c) for b in right_batches] for c in self.rpays]
+        self._keep = (lkeys, rkeys)
         self._timers = None
 
     def Prepare(self) -> None:
@@ -1088,12 +1128,40 @@ class JoinGpu:
 
     def Run(self) -> dict:
         """{fk: array, left payloads..., right payloads...}, row order unspecified."""
-        lt, rt = _PtrTable([a for col in self._l for a in col]), _PtrTable([a for col in self._r for a in col])
         nlb, nrb = len(self._l[0]), len(self._r[0])
+        if self._typed is None:
+            lt, rt = _PtrTable([a for col in self._l for a in col]), _PtrTable([a for col in self._r for a in col])
         rows = C.c_uint64(0)
         t1, t2 = Timings(), Timings()
         names = [self.fk] + self.lpays + self.rpays
-        if len(self.lpays) == 1 and len(self.rpays) == 1:
+        if self._typed is not None:
+            ldt, rdt = self._typed
+
+            def raw_table(cols):
+                arrays = [a for col in cols for a in col]
+                ptrs = (C.c_void_p * max(len(arrays), 1))(*[a.ctypes.data for a in arrays])
+                lens = (C.c_int64 * max(len(cols[0]), 1))(*[int(a.size) for a in cols[0]])
+                return ptrs, lens, arrays
+            lp, ll, _k1 = raw_table(self._l)
+            rp, rl, _k2 = raw_table(self._r)
+            lb = (C.c_int * len(ldt))(*[d.itemsize for d in ldt])
+            rb = (C.c_int * len(rdt))(*[d.itemsize for d in rdt])
+            self.ctx._call("join_table_host", lp, ll, nlb, lb, len(ldt), rp, rl, nrb, rb, len(rdt), C.byref(rows),
+                           C.byref(t1))
+            n = int(rows.value)
+            out = [np.empty(n, dtype=d) for d in [ldt[0]] + ldt[1:] + rdt[1:]]
+            ptrs = (C.c_void_p * len(out))(*[o.ctypes.data for o in out])
+            self.ctx._call("join_table_fetch_host", ptrs, len(out), n, C.byref(t2))
+        elif self._lkv.any or self._rkv.any:
+            if len(self.lpays) != 1 or len(self.rpays) != 1:
+                raise ValueError("nullable join keys are supported with one payload column per side")
+            self.ctx._call("join_u32_nullable_host", lt.ptrs, self._lkv.ptrs, self._lkv.offs, lt.lens, nlb, rt.ptrs,
+                           self._rkv.ptrs, self._rkv.offs, rt.lens, nrb, C.byref(rows), C.byref(t1))
+            n = int(rows.value)
+            out = [np.empty(n, dtype=np.uint32) for _ in range(3)]
+            self.ctx._call("join_fetch_host", out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, n,
+                           C.byref(t2))
+        elif len(self.lpays) == 1 and len(self.rpays) == 1:
             self.ctx._call("join_u32_host", lt.ptrs, lt.lens, nlb, rt.ptrs, rt.lens, nrb, C.byref(rows), C.byref(t1))
             n = int(rows.value)
             out = [np.empty(n, dtype=np.uint32) for _ in range(3)]
@@ -1118,8 +1186,8 @@ class JoinGpu:
         class _Aggr(C.Structure):
             _fields_ = [("rows", C.c_uint64), ("sum_y", C.c_uint64), ("sum_x", C.c_uint64)]
 
-        if self.lpay is None or self.rpay is None:
-            raise ValueError("the fused join -> aggregate pipeline takes one payload column per side")
+        if self.lpay is None or self.rpay is None or self._typed is not None:
+            raise ValueError("the fused join -> aggregate pipeline takes uint32 columns, one payload per side")
         lt, rt = _PtrTable(self._l[0] + self._l[1]), _PtrTable(self._r[0] + self._r[1])
         out, t = _Aggr(), Timings()
         self.ctx._call("join_aggr_u32_host", lt.ptrs, lt.lens, len(self._l[0]), rt.ptrs, rt.lens, len(self._r[0]),

@@ -516,6 +516,17 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
 int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
                        int64_t capacity_rows, b2_timings* timings);
 
+/* The same join with NULLABLE key columns: Arrow's inner hash join — the
+ * reference's oracle, join_native.cc:31-36 — never matches a null key on either side (the DPU path has
+ * no bitmaps at all). *_key_valid_ptrs[b] = validity bitmap of batch b's KEY column starting at bit
+ * *_key_valid_bit_offsets[b] (each may be NULL: no nulls / offset 0); payload columns are non-null.
+ * Rows with a null key are dropped on the device before the join (row numbers -> nullable filter ->
+ * take); a side without a bitmap skips that. Result via b2_join_fetch_host. */
+int b2_join_u32_nullable_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const uint8_t* const* l_key_valid_ptrs,
+                              const int64_t* l_key_valid_bit_offsets, const int64_t* l_lens, int64_t nl_batches,
+                              const uint32_t* const* r_ptrs, const uint8_t* const* r_key_valid_ptrs,
+                              const int64_t* r_key_valid_bit_offsets, const int64_t* r_lens, int64_t nr_batches,
+                              uint64_t* out_rows, b2_timings* timings);
 /* The same join over ANY number of payload columns per side (JoinDpu partitions every left value
  * column, join_dpu.cc:127-138, and takes every right non-key column, :325-341):
  *   l_ptrs = [fk batches..., payload 0 batches..., payload 1 batches..., ...]  ((1 + nl_payloads) * nl_batches)
@@ -529,6 +540,21 @@ int b2_join_cols_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int6
                           int nr_payloads, uint64_t* out_rows, b2_timings* timings);
 int b2_join_cols_fetch_host(b2_ctx* ctx, uint32_t* const* out_cols, int ncols, int64_t capacity_rows,
                             b2_timings* timings);
+
+/* The join over a TYPED table: 32- or 64-bit keys (the reference's table can be built with 64-bit keys,
+ * HT_64BIT_KEYS, dpu/shared/hashtable/hashtable.h:14-18) and any number of 32- or 64-bit payload
+ * columns per side (raw words: uint / int / float alike). Column 0 of each side is its key.
+ *   l_ptrs = column-major batch pointers, (nl_cols * nl_batches) entries; l_col_bytes[c] = 4 or 8
+ * Rows travel through the radix passes by reference (the pair carries the row number) and every
+ * result column is gathered afterwards; a 64-bit key is folded to 32 bits for partitioning / probing
+ * and every candidate pair is verified against the full keys on the device. Result columns, in order:
+ * the key, the left payloads, the right payloads, each of its own width; b2_join_table_fetch_host copies
+ * column c to out_cols[c] (capacity_rows elements each). */
+int b2_join_table_host(b2_ctx* ctx, const void* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                       const int* l_col_bytes, int nl_cols, const void* const* r_ptrs, const int64_t* r_lens,
+                       int64_t nr_batches, const int* r_col_bytes, int nr_cols, uint64_t* out_rows,
+                       b2_timings* timings);
+int b2_join_table_fetch_host(b2_ctx* ctx, void* const* out_cols, int ncols, int64_t capacity_rows, b2_timings* timings);
 
 /* ---- multi-GPU join exchange (the step that replaces the reference's host-mediated
  *      DPU->host->DPU repartition, partitioner.cc:350-375 + join_dpu.cc:269,293) -------------- */

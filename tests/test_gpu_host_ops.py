@@ -291,3 +291,53 @@ def test_join_many_payload_columns(ctx, ops, nlp, nrp):
     order_e = np.lexsort(tuple(reversed(exp)))
     for g, e in zip(got, exp):
         assert np.array_equal(g[order_g], e[order_e])
+
+
+# ---- 64-bit keys (HT_64BIT_KEYS, hashtable.h:14-18) and wide / typed payload columns -----------------
+def _fold(k):
+    k = np.asarray(k, dtype=np.uint64)
+    return ((k & np.uint64(0xFFFFFFFF)) ^ (((k >> np.uint64(32)) * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF))).astype(np.uint32)
+
+
+@pytest.mark.parametrize("key_dtype", [np.uint64, np.int64, np.int32])
+def test_join_wide_keys_and_typed_payloads_match_arrow(ctx, ops, key_dtype):
+    import pyarrow as pa
+    rng = np.random.default_rng(int(np.dtype(key_dtype).itemsize))
+    nb, bs = 4, 50_000
+    n = nb * bs
+    if np.dtype(key_dtype).itemsize == 8:
+        pk = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+        pk[1] = pk[0]                                             # a duplicate build key
+        # build keys with the SAME 32-bit fold as other build keys but different values: the probe finds them
+        # as candidates and the 64-bit verification must reject them
+        hi = rng.integers(1, 2**31, size=2000, dtype=np.uint64)
+        lo = (_fold(pk[2:2002]).astype(np.uint64) ^ ((hi * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF)))
+        pk[2002:4002] = (hi << np.uint64(32)) | lo
+        assert np.array_equal(_fold(pk[2002:4002]), _fold(pk[2:2002]))
+        fk = pk[rng.integers(0, n, size=n)]
+        fk[:500] = rng.integers(0, 2**63, size=500, dtype=np.uint64)  # no match
+        pk, fk = pk.astype(key_dtype), fk.astype(key_dtype)
+    else:
+        pk = (rng.permutation(n) - n // 2).astype(key_dtype)       # negative int32 keys too
+        fk = pk[rng.integers(0, n, size=n)]
+    y64 = rng.integers(-2**62, 2**62, size=n, dtype=np.int64)
+    yf = rng.random(n).astype(np.float32)
+    x32 = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    xd = rng.random(n)                                            # float64
+    sl = lambda a, b: a[b * bs:(b + 1) * bs]
+    left = [pa.record_batch([pa.array(sl(fk, b)), pa.array(sl(y64, b)), pa.array(sl(yf, b))], names=["fk", "y64", "yf"])
+            for b in range(nb)]
+    right = [pa.record_batch([pa.array(sl(pk, b)), pa.array(sl(x32, b)), pa.array(sl(xd, b))], names=["pk", "x32", "xd"])
+             for b in range(nb)]
+    j = ops.JoinGpu(ctx, left, right)
+    j.Prepare()
+    out = j.Run()
+    assert list(out) == ["fk", "y64", "yf", "x32", "xd"]
+    assert out["fk"].dtype == np.dtype(key_dtype) and out["y64"].dtype == np.int64 and out["xd"].dtype == np.float64
+    exp = pa.Table.from_batches(left).join(pa.Table.from_batches(right), keys="fk", right_keys="pk", join_type="inner")
+    assert out["fk"].size == exp.num_rows
+    want = [exp.column(c).combine_chunks().to_numpy(zero_copy_only=False) for c in out]
+    got = [out[c] for c in out]
+    og, ow = np.lexsort(tuple(reversed(got))), np.lexsort(tuple(reversed(want)))
+    for g, w in zip(got, want):
+        assert np.array_equal(g[og], w[ow])
