@@ -250,9 +250,13 @@ arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
   for (int c = 0; c < right_schema_->num_fields(); ++c)
     if (c != pk) rcols.push_back(c);
   ColumnPtrs l, r;  // [key batches..., payload 0 batches..., payload 1 batches..., ...]
-  ARROW_RETURN_NOT_OK(l.Append(left_batches_, fk));
+  // key columns may carry nulls: a null key never matches (Arrow's hash join, join_native.cc:31-36)
+  ARROW_RETURN_NOT_OK(l.Append(left_batches_, fk, /*allow_nulls=*/true));
+  ARROW_RETURN_NOT_OK(r.Append(right_batches_, pk, /*allow_nulls=*/true));
+  const bool null_keys = l.has_nulls || r.has_nulls;
+  const std::vector<const uint8_t*> lkv = l.valid, rkv = r.valid;
+  const std::vector<int64_t> lko = l.valid_off, rko = r.valid_off;
   for (int c : lcols) ARROW_RETURN_NOT_OK(l.Append(left_batches_, c));
-  ARROW_RETURN_NOT_OK(r.Append(right_batches_, pk));
   for (int c : rcols) ARROW_RETURN_NOT_OK(r.Append(right_batches_, c));
   const int64_t nlb = static_cast<int64_t>(left_batches_.size()), nrb = static_cast<int64_t>(right_batches_.size());
   // JoinNative drops pk and keeps fk + the payloads of both sides (join_native.cc:75)
@@ -265,7 +269,13 @@ arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
   arrow::ArrayVector arrays(static_cast<size_t>(ncols));
   std::vector<uint32_t*> outs(static_cast<size_t>(ncols));
   const bool pair_path = lcols.size() == 1 && rcols.size() == 1;
-  if (pair_path) {
+  if (null_keys && !pair_path) return arrow::Status::NotImplemented("nullable join keys with one payload column per side");
+  if (pair_path && null_keys) {
+    // rows with a null key are dropped on the device before the join (member 0 of the set)
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_join_u32_nullable_host(ctx, l.ptrs.data(), lkv.data(), lko.data(), l.lens.data(), nlb,
+                                                          r.ptrs.data(), rkv.data(), rko.data(), r.lens.data(), nrb,
+                                                          &rows, &t1));
+  } else if (pair_path) {
     // the benchmark shape: the payload travels with the key; sharded over every GPU of the set
     B2_SET_RETURN_NOT_OK(set, b2_set_join_u32_host(set, l.ptrs.data(), l.lens.data(), nlb, r.ptrs.data(),
                                                    r.lens.data(), nrb, &rows, &t1));
@@ -279,7 +289,9 @@ arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
     ARROW_ASSIGN_OR_RAISE(arrays[static_cast<size_t>(c)],
                           PinnedU32(system_, static_cast<int64_t>(rows), &outs[static_cast<size_t>(c)]));
   }
-  if (pair_path) {
+  if (pair_path && null_keys) {
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_join_fetch_host(ctx, outs[0], outs[1], outs[2], static_cast<int64_t>(rows), &t2));
+  } else if (pair_path) {
     B2_SET_RETURN_NOT_OK(set, b2_set_join_fetch_host(set, outs[0], outs[1], outs[2], static_cast<int64_t>(rows), &t2));
   } else {
     B2_ARROW_RETURN_NOT_OK(ctx, b2_join_cols_fetch_host(ctx, outs.data(), ncols, static_cast<int64_t>(rows), &t2));

@@ -94,7 +94,12 @@ def _raw_column(batch: Any, name: str) -> np.ndarray:
             raise ValueError("the typed-table join takes non-null columns")
         a = col.to_numpy(zero_copy_only=True)
     else:
-        a = np.ascontiguousarray(np.asarray(batch[name]))
+        col = batch[name]
+        if pa is not None and isinstance(col, (pa.Array, pa.ChunkedArray)):
+            if col.null_count:
+                raise ValueError("the typed-table join takes non-null columns")
+            col = (col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col).to_numpy(zero_copy_only=True)
+        a = np.ascontiguousarray(np.asarray(col))
     if a.dtype.kind not in "uif" or a.dtype.itemsize not in (4, 8):
         raise TypeError(f"column {name!r}: expected a 32- or 64-bit numeric type, got {a.dtype}")
     return a
@@ -103,7 +108,12 @@ def _raw_column(batch: Any, name: str) -> np.ndarray:
 def _column_dtype(batch: Any, name: str) -> np.dtype:
     if pa is not None and isinstance(batch, pa.RecordBatch):
         return np.dtype(batch.schema.field(name).type.to_pandas_dtype())
-    return np.asarray(batch[name]).dtype
+    col = batch[name]
+    if pa is not None and isinstance(col, (pa.Array, pa.ChunkedArray)):
+        return np.dtype(col.type.to_pandas_dtype())  # not np.asarray: nulls would turn integers into floats
+    if isinstance(col, np.ma.MaskedArray):
+        return np.ma.getdata(col).dtype
+    return np.asarray(col).dtype
 
 
 # 32-bit column types the filter compares natively (b2_dtype32, include/b200olap.h)

@@ -190,8 +190,11 @@ def test_nullable_ragged_batches_and_loud_rejections(ctx):
         ops.TakeGpu(ctx, ragged_take, [pa.array([0, None, 1], type=pa.uint32()), pa.array([0, 1], type=pa.uint32())]).Run()
     assert e.value.status == 4  # B2_ERR_UNSUPPORTED
     batches = ragged_take
-    with pytest.raises(ValueError):  # the join has no null semantics here
+    with pytest.raises(ValueError):  # nullable PAYLOAD columns have no semantics in the join (keys do, below)
         ops.JoinGpu(ctx, [{"fk": batches[0], "y": batches[0]}], [{"pk": batches[0], "x": batches[0]}])
+    plain = pa.array([7, 8, 9], type=pa.uint32())
+    out = ops.JoinGpu(ctx, [{"fk": batches[0], "y": plain}], [{"pk": batches[0], "x": plain}]).Run()
+    assert sorted(zip(out["fk"].tolist(), out["y"].tolist(), out["x"].tolist())) == [(1, 7, 7), (3, 9, 9)]  # null != null
 
 
 # ---- other 32-bit types (b2_filter_lt_32_dev) ----------------------------------------------------------
