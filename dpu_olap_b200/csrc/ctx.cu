@@ -209,7 +209,7 @@ int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value) {
     case B2_TUNE_SCATTER_PREFETCH: value = value != 0; break;
     case B2_TUNE_SCATTER_SHAPE: B2_REQUIRE(ctx, (value >= 0 && value <= 3) || value == 8, "shape 0..3 or 8"); break;
     case B2_TUNE_FILTER_VARIANT: B2_REQUIRE(ctx, value >= 0 && value <= 7, "variant 0..7"); break;
-    case B2_TUNE_SCATTER_SECTOR_TILE: B2_REQUIRE(ctx, value >= 0 && value <= 2, "0, 1 or 2"); break;
+    case B2_TUNE_SCATTER_SECTOR_TILE: B2_REQUIRE(ctx, value >= 0 && value <= 3, "0 .. 3"); break;
     default: return b2_set_error(ctx, B2_ERR_INVALID, "b2_ctx_set_tunable", "unknown tunable");
   }
   ctx->tune[which] = value;

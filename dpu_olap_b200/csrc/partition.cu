@@ -34,9 +34,12 @@
 // of two 4 B accesses to two columns).
 #include "partition.cuh"
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "scan.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -1091,6 +1094,235 @@ part_scatter_quads_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 }
 
 
+// ---- whole-sector scatter, third generation: the copy engine flushes ("bulk") ----------------------
+// The sector and quad kernels above spend most of their instructions in the flush: every stored row
+// costs a bucket lookup, a descriptor read, an address computation and a predicated 8-byte store
+// (profiles/r2_launches_join_sf1024.csv: 87 lane-instructions per row, 45 % issue utilisation, 3.2 TB/s
+// where the memory system takes the same run lengths at 5.2 TB/s, tools/microbench_scatter_ceiling.cu).
+// Here the flush is ONE instruction per (bucket, tile): the bucket's region of the stage — quad-aligned,
+// carried rows first, as in the quads kernel — is handed to the copy engine as one shared -> global bulk
+// copy of its whole sectors (cp.async.bulk, UBLKCP in SASS), 16-byte aligned at both ends by
+// construction. No sector table, no descriptors, no per-row stores. What is left per row is the load,
+// the hash, one shared-memory atomic for the rank and one shared-memory store into the stage.
+//   * thread p owns bucket p in the per-bucket steps and keeps the bucket's state across tiles in registers
+//     (next output sector, number of held-back rows, how many of the first sector's slots belong to the
+//     neighbouring run: "ghost") and in a private column of a small carry array (the at most 3 rows that
+//     did not complete a sector);
+//   * rank counters are double-buffered: the counter of the next tile is initialised (to the number of
+//     carried rows) in the per-bucket step of this tile, which removes the barrier at the end of a tile:
+//     four barriers per tile (rank | scan | regions | staged);
+//   * the copy engine reads the stage asynchronously: cp.async.bulk.wait_group.read before the barrier
+//     that precedes the next tile's staging, a full tile of work after the copies were issued;
+//   * a (unit, bucket) run's first sector, when shared with the neighbouring run, and its last, partial
+//     sector are written with plain 8-byte stores by the bucket's thread.
+constexpr int kBkT = 1024, kBkI = 16;
+constexpr int kBkTile = kBkT * kBkI;                                  // 16384 rows
+constexpr int kBkSlots = kBkTile + 6 * (1 << kPartMaxBits);           // + carried rows + padding to quads
+struct BkSmem {
+  uint2 stage[kBkSlots];                         // 176 KB
+  uint32_t cnt[2][1 << kPartMaxBits];            // 8 KB: rank counters of this tile / the next tile
+  uint32_t qstart[1 << kPartMaxBits];            // first stage slot of the bucket's region
+  uint2 carry[3][1 << kPartMaxBits];             // 24 KB: the rows that did not complete a sector (private to the bucket's thread)
+  uint32_t warp_tot[kBkT / 32];
+};
+static_assert(sizeof(BkSmem) <= 227 * 1024, "BkSmem must fit the opt-in shared memory of one CTA");
+
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+// Ask the copy engine to bring [p, p + bytes) into L2 (no registers, no completion to wait for).
+__device__ __forceinline__ void l2_prefetch(const void* p, int64_t bytes) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uintptr_t a16 = (a + 15) & ~(uintptr_t)15;
+  bytes -= (int64_t)(a16 - a);
+  bytes &= ~(int64_t)15;
+  if (bytes > 0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"((uint32_t)bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+template <bool kAoS, bool kPre>
+__global__ void __launch_bounds__(kBkT, 1)
+part_scatter_bulk_kernel(PartInput in, const int64_t* __restrict__ seg_off,
+                         const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
+                         PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
+                         int64_t out_cap, unsigned int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem[];  // the window itself starts 1024-byte aligned
+  BkSmem& sm = *reinterpret_cast<BkSmem*>(smem);
+  const int P = 1 << g.bits;
+  const SliceSel sel = slice_sel(g);
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
+  if (!u.valid) return;
+  constexpr int kW = kBkT / 32;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool mine = (int)tid < P;  // this thread's bucket in the per-bucket steps
+  const uint64_t cap_rows = (uint64_t)out_cap;
+  const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(sm.stage);
+
+  // per-bucket state, in registers of the bucket's thread
+  uint32_t dsec_next = 0;  // next unwritten sector of the (unit, bucket) run, counted from `out`
+  uint32_t gh = 0;         // leading slots of the run's first sector that belong to the neighbouring run
+  uint32_t c0 = 0;         // rows held back (ghost slots included)
+  if (mine) {
+    const uint64_t pos = scanned[u.hbase + (int64_t)tid * u.ustride];  // first output row of (unit, bucket)
+    gh = (uint32_t)(pos & (kScRows - 1));
+    dsec_next = (uint32_t)(pos >> 2);
+    c0 = gh;
+    sm.cnt[0][tid] = gh;
+  }
+  __syncthreads();
+
+  uint32_t key[kBkI], val[kBkI];
+  auto load_tile = [&](int64_t t0) {
+#ifdef B2_LAB
+    if (g.lab & 1) {  // experiment: what the pass costs without its DRAM reads (the output is wrong on purpose)
+#pragma unroll
+      for (int it = 0; it < kBkI; ++it) {
+        val[it] = (uint32_t)(t0 + it * kBkT + tid);
+        key[it] = val[it] * 2654435761u;
+      }
+      return;
+    }
+#endif
+    if (t0 + kBkTile <= u.row1) {  // full tile: no bounds checks
+#pragma unroll
+      for (int it = 0; it < kBkI; ++it) load_row<kAoS>(in, t0 + it * kBkT + tid, key[it], val[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < kBkI; ++it) {
+        const int64_t row = t0 + it * kBkT + tid;
+        key[it] = 0;
+        val[it] = 0;
+        if (row < u.row1) load_row<kAoS>(in, row, key[it], val[it]);
+      }
+    }
+  };
+  if (kPre && u.row0 < u.row1) load_tile(u.row0);
+
+  uint32_t par = 0;
+  for (int64_t t0 = u.row0; t0 < u.row1; t0 += kBkTile, par ^= 1u) {
+    // The tile after this one is requested into L2 now (one instruction, no registers): the register
+    // loads that follow this tile's staging then hit L2 instead of waiting for DRAM, whose reads run
+    // under the rank / scan / stage steps (tools/part_lab.py with B2_LAB_SCATTER: the exposed loads were
+    // a quarter of the pass).
+    if (kPre && tid == 0 && t0 + kBkTile < u.row1) {
+      const int64_t n0 = t0 + kBkTile, nn = min((int64_t)kBkTile, u.row1 - n0);
+      if (kAoS) {
+        l2_prefetch(in.pairs + n0, nn * 8);
+      } else {
+        l2_prefetch(in.keys + n0, nn * 4);
+        if (in.vals) l2_prefetch(in.vals + n0, nn * 4);
+      }
+    }
+    // ---- (load,) hash once, rank inside the bucket (ranks continue after the held-back rows) ----
+    if (!kPre) load_tile(t0);
+    uint32_t* cnt = sm.cnt[par];
+    uint32_t packed[kBkI];  // bucket | rank << 16
+    if (t0 + kBkTile <= u.row1 && sel.mask == 0) {
+#pragma unroll
+      for (int it = 0; it < kBkI; ++it) {
+        const uint32_t b = part_bucket(wang_hash_u32(key[it]), g.shl, g.bits);
+        packed[it] = b | (atomicAdd(&cnt[b], 1u) << 16);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < kBkI; ++it) {
+        const int64_t row = t0 + it * kBkT + tid;
+        packed[it] = 0xffffffffu;
+        if (row < u.row1) {
+          const uint32_t b = bucket_or_skip<false>(key[it], val[it], g, sel);
+          if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&cnt[b], 1u) << 16);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- per bucket: region of the stage (rounded up to whole quads), next tile's counter ----
+    const uint32_t tot = mine ? cnt[tid] : 0u;  // held back (incl. ghost) + this tile's rows
+    const uint32_t region = (tot + 3u) & ~3u;
+    uint32_t incl = region;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    if (mine) sm.cnt[par ^ 1u][tid] = tot & 3u;  // what this tile will hold back
+    bulk_wait_read();  // the copies of the previous tile have read the stage (issued a tile of work ago)
+    __syncthreads();
+    uint32_t q0;
+    {
+      const uint32_t w = sm.warp_tot[lane];  // kW == 32
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < kW; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      q0 = __shfl_sync(0xffffffffu, wi - w, warp) + incl - region;  // first slot of the region
+      if (mine) sm.qstart[tid] = q0;
+    }
+    __syncthreads();
+
+    // ---- stage the tile's rows behind the held-back ones ----
+#pragma unroll
+    for (int it = 0; it < kBkI; ++it) {
+      if (packed[it] != 0xffffffffu)
+        sm.stage[sm.qstart[packed[it] & 0xffffu] + (packed[it] >> 16)] = make_uint2(key[it], val[it]);
+    }
+    if (mine) {
+      for (uint32_t e = gh; e < c0; ++e) sm.stage[q0 + e] = sm.carry[e][tid];
+    }
+    fence_proxy_async();  // the copy engine reads what this thread staged
+    __syncthreads();
+
+    if (kPre && t0 + kBkTile < u.row1) load_tile(t0 + kBkTile);
+
+    // ---- flush: one bulk copy per bucket; hold back the tail ----
+    if (mine) {
+      const uint32_t nsec = tot >> 2, rem = tot & 3u;
+      if (nsec) {
+        if (((uint64_t)dsec_next + nsec) * kScRows > cap_rows) {
+          if (overflow) *overflow = 1u;  // rows beyond the output's capacity are dropped
+        } else {
+          uint32_t first = 0;
+          if (gh) {  // the run's first sector is shared with the neighbouring run: plain stores
+            for (uint32_t e = gh; e < kScRows; ++e)
+              st_stream_v2(out + ((uint64_t)dsec_next * kScRows + e), sm.stage[q0 + e]);
+            first = 1;
+          }
+#ifdef B2_LAB
+          if (g.lab & 2) first = nsec;  // experiment: what the pass costs without its DRAM writes
+#endif
+          if (nsec > first) {
+            bulk_store(reinterpret_cast<unsigned char*>(out) + ((uint64_t)dsec_next + first) * 32u,
+                       stage_base + (q0 + first * kScRows) * 8u, (nsec - first) * 32u);
+            bulk_commit();
+          }
+        }
+        dsec_next += nsec;
+        gh = 0;
+      }
+      const uint32_t from = q0 + nsec * kScRows;
+      for (uint32_t e = 0; e < rem; ++e) sm.carry[e][tid] = sm.stage[from + e];
+      c0 = rem;
+    }
+  }
+
+  // ---- end of the unit: the last, partial sector of every bucket ----
+  if (mine && c0 > gh) {
+    const uint64_t row = (uint64_t)dsec_next * kScRows;
+    if (row + c0 > cap_rows) {
+      if (overflow) *overflow = 1u;
+    } else {
+      for (uint32_t e = gh; e < c0; ++e) st_stream_v2(out + row + e, sm.carry[e][tid]);
+    }
+  }
+  bulk_wait_read();  // shared memory must outlive the copy engine's reads
+}
+
 // Boundaries are clamped to `clamp` (the capacity of the pass's output): when a skewed hash-space
 // slice overflows its buffer the scatter drops the rows beyond it and raises *overflow; whoever reads
 // the output by these boundaries (a second pass, the probe) must not run past the buffer either.
@@ -1206,14 +1438,20 @@ int part_count_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* 
 // Phase 2: scatter, to d_out (local) or to the per-bucket byte addresses in d_bucket_addr (peer).
 template <bool kAoS>
 int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t* d_seg_off,
-                      int64_t nseg, const PartGeom& g, uint2* d_out, int64_t out_cap,
+                      int64_t nseg, const PartGeom& g_in, uint2* d_out, int64_t out_cap,
                       const uint64_t* d_bucket_addr, unsigned int* d_overflow, void* d_ws,
                       size_t ws_bytes, cudaStream_t s, const int64_t* d_abort) {
-  const PassLayout L = pass_layout(n, nseg, g.bits);
+  const PassLayout L = pass_layout(n, nseg, g_in.bits);
   if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "partition pass", "workspace");
   char* base = static_cast<char*>(d_ws);
   const int64_t* unit_first = reinterpret_cast<const int64_t*>(base + L.off_unit_first);
   const uint64_t* scanned = reinterpret_cast<const uint64_t*>(base + L.off_scanned);
+#ifdef B2_LAB
+  PartGeom g = g_in;
+  if (const char* e = getenv("B2_LAB_SCATTER")) g.lab = atoi(e);
+#else
+  const PartGeom& g = g_in;
+#endif
   if (L.max_units > 0) {
     // whole-sector scatter: local destinations, 32-byte aligned output, fan-out at or above the threshold
     const bool sectors = !d_bucket_addr && !g.val_pred && (reinterpret_cast<uintptr_t>(d_out) & 31) == 0 &&
@@ -1223,7 +1461,8 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       const bool big = shape == 1;
       const bool pre = ctx->tune[B2_TUNE_SCATTER_PREFETCH] != 0;
       // the instantiations share one function-pointer type, so each gets its own site id
-      static const int sites[6] = {b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site()};
+      static const int sites[8] = {b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(),
+                                   b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site()};
       auto go = [&](auto kernel, int site, int threads, size_t smem_bytes) -> int {
         if (b2_first_use_on_device(ctx, site))
           B2_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -1231,7 +1470,10 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
                                                                  scanned, d_out, out_cap, d_overflow);
         return B2_OK;
       };
-      if (shape == 2) {  // quad-aligned regions: the carried rows live in the stage, the flush is three reads and a store
+      if (shape == 3) {  // quad-aligned regions flushed by the copy engine: one bulk copy per (bucket, tile)
+        if (pre) B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, true>, sites[6], kBkT, sizeof(BkSmem)));
+        else B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, false>, sites[7], kBkT, sizeof(BkSmem)));
+      } else if (shape == 2) {  // quad-aligned regions: the carried rows live in the stage, the flush is three reads and a store
         if (pre) B2_RETURN_NOT_OK(go(part_scatter_quads_kernel<kAoS, true>, sites[4], kQdT, sizeof(QdSmem)));
         else B2_RETURN_NOT_OK(go(part_scatter_quads_kernel<kAoS, false>, sites[5], kQdT, sizeof(QdSmem)));
       } else if (big) {

@@ -19,6 +19,9 @@ struct PartGeom {
   // below val_thr. Rows that fail are dropped by this pass (counted by neither kernel).
   bool val_pred = false;
   uint32_t val_thr = 0;
+#ifdef B2_LAB
+  int lab = 0;  // tools/part_lab.py experiments (env B2_LAB_SCATTER): 1 = synthetic rows instead of loads, 2 = no flush
+#endif
 };
 
 constexpr int kPartMaxBits = 10;           // per pass (warp-private u16 counters for 1024 bins)

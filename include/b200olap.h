@@ -92,7 +92,8 @@ enum b2_tunable {
   B2_TUNE_SCATTER_SHAPE = 2,            /* plain scatter kernel shape: 0 = 512 thr x 16 rows x 2 CTA/SM, 1, 2, 3, 8 */
   B2_TUNE_FILTER_VARIANT = 3,           /* filter kernel shape 0..7 (6) */
   B2_TUNE_SCATTER_SECTOR_TILE = 4       /* whole-sector scatter: 0 = 8192-row tiles x 2 CTA/SM, 1 = 16384-row tiles x 1 CTA/SM,
-                                           2 = quad-aligned regions, 14336-row tiles x 1 CTA/SM */
+                                           2 = quad-aligned regions, 14336-row tiles x 1 CTA/SM,
+                                           3 = quad-aligned regions flushed by the copy engine (cp.async.bulk), 16384-row tiles */
 };
 int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value);
 int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value);

@@ -12,7 +12,7 @@ from test_gpu_dev_ops import check_join, check_partition, dev, host, run_join
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["tile8192", "tile16384", "quads"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["tile8192", "tile16384", "quads", "bulk"])
 def sectors(ctx, request):
     default = ctx.get_tunable(TUNE_SCATTER_SECTORS_MIN_BITS)
     tile = ctx.get_tunable(TUNE_SCATTER_SECTOR_TILE)
