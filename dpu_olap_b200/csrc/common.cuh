@@ -28,7 +28,7 @@ struct b2_ctx {
   size_t small_bytes = 0;
   uint32_t sum_slot = 0;  // next slot of that ring
   // kernel-selection knobs (b2_ctx_set_tunable, enum b2_tunable): every setting computes the same result
-  int tune[5] = {9, 1, 0, 6, 1};
+  int tune[6] = {8, 1, 0, 6, 3, 2048};
   std::vector<char> site_done;  // per call site: function attributes configured for this ctx's device
   std::vector<int> site_value;
   // growable device workspace used by the *_host layer
@@ -161,6 +161,16 @@ __device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Ask the copy engine to bring [p, p + bytes) into L2 (UBLKPF in SASS): no registers, no completion to
+// wait for. The range is shrunk to 16-byte alignment at both ends (the edges come with the demand loads).
+__device__ __forceinline__ void l2_prefetch(const void* p, int64_t bytes) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uintptr_t a16 = (a + 15) & ~(uintptr_t)15;
+  bytes -= (int64_t)(a16 - a);
+  bytes &= ~(int64_t)15;
+  if (bytes > 0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"((uint32_t)bytes) : "memory");
+}
 // Single-word (status|value) tile descriptors of the decoupled look-back scan: a relaxed
 // gpu-scope 64-bit access is atomic, so no fence is needed between status and value.
 __device__ __forceinline__ uint64_t ld_relaxed_gpu_u64(const uint64_t* p) {

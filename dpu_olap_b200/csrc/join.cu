@@ -49,6 +49,20 @@ constexpr int kItems = 9;                      // rows per thread per round (bui
 constexpr int kRound = kThreads * kItems;      // 4608 rows: mean partition + 8 sigma in one round
 constexpr int kProbeCtasPerSm = 2;             // 3 CTAs/SM (40 registers, spills) measured 5 % slower
 
+// Perfect-hash path of the probe kernel. wang_hash_u32 is a BIJECTION on 32-bit keys (odd
+// multiplications and xor-shifts only), and every row of a partition has the same hash bits above the
+// low `rest` ones (the GPU / slice / partition fields). So two DIFFERENT keys of one partition differ
+// in the low `rest` bits of their hash: those bits index a table without collisions, whatever the key
+// set is. With rest <= 13 the table (2^rest entries of (key, value)) fits the shared memory the
+// bucketised table uses, an insert is ONE 64-bit shared-memory exchange, a probe is ONE 64-bit load and
+// a compare: no candidate buckets, no arrival counters, no chains (the bucketised probe loop issued
+// ~98 lane-instructions per row and kept the shared-memory pipe 73 % busy, profiles/r2_join_probe.md).
+// Only EQUAL keys can meet in an entry: the exchange hands the displaced row back, the partition is
+// then known to hold duplicate build keys and is redone by the bucketised path, which enumerates them.
+// Empty entries hold a key that cannot occur in the partition (0 or 1: their hashes differ above bit 13).
+constexpr int kDirectMaxBits = 13;             // 8192 entries x 8 B = 64 KB <= kTableBytes
+static_assert((8u << kDirectMaxBits) <= (unsigned)kTableBytes, "the perfect-hash table shares the bucketised table's memory");
+
 struct JoinState {  // lives in the workspace header
   unsigned long long out_rows;
   unsigned int overflow;
@@ -149,7 +163,7 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
                   const uint2* __restrict__ lpairs, const int64_t* __restrict__ loff,
                   int64_t nparts, uint32_t* __restrict__ out_fk, uint32_t* __restrict__ out_y,
                   uint32_t* __restrict__ out_x, int64_t out_cap, JoinState* __restrict__ st,
-                  uint32_t y_thr, bool filter_y) {
+                  uint32_t y_thr, bool filter_y, int rest_bits) {
   extern __shared__ __align__(16) uint32_t tab[];  // keys [kSlots] | values [kSlots] | counts [kBuckets]
   uint32_t* tk = tab;
   uint32_t* tv = tab + kSlots;
@@ -157,15 +171,134 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
   const uint4* tk4 = reinterpret_cast<const uint4*>(tab);
   __shared__ uint32_t warp_cnt[kWarps];
   __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_dup;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt = lanemask_lt();
   unsigned long long agg_rows = 0, agg_y = 0, agg_x = 0;  // kAgg: this thread's share of the aggregates
+
+  // One round of probe rows whose match count is 0 or 1 (m[q]), in (warp, item, lane) order: the CTA
+  // reserves its output range with one 64-bit atomic, ranks come from one ballot per item, positions
+  // are 32-bit offsets from the warp's base, rows at or beyond out_cap are dropped.
+  auto emit_unique = [&](const uint32_t (&lk)[kItems], const uint32_t (&ly)[kItems], const uint32_t (&x0)[kItems],
+                         const uint32_t (&m)[kItems]) {
+    uint32_t wtotal = 0;
+#pragma unroll
+    for (int q = 0; q < kItems; ++q) wtotal += __popc(__ballot_sync(0xffffffffu, m[q] == 1));
+    if (lane == 0) warp_cnt[warp] = wtotal;
+    __syncthreads();
+    {
+      const uint32_t w = lane < kWarps ? warp_cnt[lane] : 0;
+      uint32_t incl = w;
+#pragma unroll
+      for (int o = 1; o < kWarps; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, kWarps - 1);
+      wtotal = __shfl_sync(0xffffffffu, incl - w, warp);  // now: this warp's offset in the round
+      if (tid == 0 && total > 0) s_base = atomicAdd(&st->out_rows, (unsigned long long)total);
+    }
+    __syncthreads();
+    const unsigned long long pos = s_base + wtotal;
+    const uint32_t room = (int64_t)pos < out_cap ? (uint32_t)min(out_cap - (int64_t)pos, (int64_t)kRound) : 0u;
+    uint32_t* __restrict__ pf = out_fk + pos;
+    uint32_t* __restrict__ py = out_y + pos;
+    uint32_t* __restrict__ px = out_x + pos;
+    uint32_t run = 0;
+#pragma unroll
+    for (int q = 0; q < kItems; ++q) {
+      const uint32_t one = __ballot_sync(0xffffffffu, m[q] == 1);
+      const uint32_t off = run + __popc(one & lt);
+      if (m[q] == 1 && off < room) {
+        st_stream_u32(pf + off, lk[q]);
+        st_stream_u32(py + off, ly[q]);
+        st_stream_u32(px + off, x0[q]);
+      }
+      run += __popc(one);
+    }
+    // warp_cnt / s_base are rewritten only after the next round's first barrier
+  };
 
   for (int64_t p = blockIdx.x; p < nparts; p += gridDim.x) {
     const int64_t r0 = roff[p], r1 = roff[p + 1];
     const int64_t l0 = loff[p], l1 = loff[p + 1];
     if (r1 == r0 || l1 == l0) continue;  // inner join: nothing to emit
 
+    // The partition this CTA takes next is requested into L2 now (two copy-engine instructions by one
+    // thread of the last warp): its loads, issued at the top of the next iteration, then hit L2 instead
+    // of waiting for DRAM with only two CTAs per SM to hide it.
+    if (tid == kThreads - 32 && p + gridDim.x < nparts) {
+      const int64_t pn = p + gridDim.x;
+      const int64_t nr0 = roff[pn], nr1 = roff[pn + 1], nl0 = loff[pn], nl1 = loff[pn + 1];
+      if (nr1 > nr0 && nl1 > nl0) {
+        l2_prefetch(rpairs + nr0, min(nr1 - nr0, (int64_t)kMaxBuild) * 8);
+        l2_prefetch(lpairs + nl0, min(nl1 - nl0, (int64_t)kRound) * 8);
+      }
+    }
+    if (rest_bits > 0) {
+      // ---- perfect-hash path: entry = low rest_bits of wang_hash(key) ----
+      unsigned long long* t64 = reinterpret_cast<unsigned long long*>(tab);
+      const uint32_t mask = (1u << rest_bits) - 1u;
+      uint32_t lk[kItems], ly[kItems];
+      bool dup = false;
+      {
+        uint32_t rk[kItems], rv[kItems];
+        const uint32_t nb0 = (uint32_t)min(r1 - r0, (int64_t)kRound);
+        load_round(rpairs + r0, nb0, tid, rk, rv);
+        load_round(lpairs + l0, (uint32_t)min(l1 - l0, (int64_t)kRound), tid, lk, ly);
+        const uint32_t k0 = __ldg(reinterpret_cast<const uint32_t*>(rpairs + r0));  // any key of the partition
+        __syncthreads();  // the previous partition is done with the table
+        // a key whose hash differs from the partition's above the entry bits cannot occur in it
+        const uint32_t mk = ((wang_hash_u32(0u) ^ wang_hash_u32(k0)) >> rest_bits) != 0u ? 0u : 1u;
+        for (uint32_t i = tid; i < (1u << rest_bits) / 2; i += kThreads)
+          reinterpret_cast<uint4*>(tab)[i] = make_uint4(mk, 0u, mk, 0u);
+        if (tid == 0) s_dup = 0;
+        __syncthreads();
+        for (int64_t base = r0; base < r1; base += kRound) {
+          const uint32_t nb = (uint32_t)min(r1 - base, (int64_t)kRound);
+          if (base > r0) load_round(rpairs + base, nb, tid, rk, rv);
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) {
+            if (q * kThreads + tid < nb) {
+              const unsigned long long old = atomicExch(&t64[wang_hash_u32(rk[q]) & mask],
+                                                        (unsigned long long)rk[q] | ((unsigned long long)rv[q] << 32));
+              dup |= (uint32_t)old != mk;  // only an equal key can have been there
+            }
+          }
+        }
+        if (dup) s_dup = 1;
+      }
+      __syncthreads();
+      if (s_dup == 0) {
+        for (int64_t t0 = l0; t0 < l1; t0 += kRound) {
+          const uint32_t nprobe = (uint32_t)min(l1 - t0, (int64_t)kRound);
+          if (t0 > l0) load_round(lpairs + t0, nprobe, tid, lk, ly);
+          uint32_t x0[kItems], m[kItems];
+#pragma unroll
+          for (int q = 0; q < kItems; ++q) {
+            const unsigned long long e = t64[wang_hash_u32(lk[q]) & mask];
+            const bool active = q * kThreads + tid < nprobe && (!kAgg || !filter_y || ly[q] < y_thr);
+            m[q] = (active && (uint32_t)e == lk[q]) ? 1u : 0u;
+            x0[q] = (uint32_t)(e >> 32);
+          }
+          if (kAgg) {
+#pragma unroll
+            for (int q = 0; q < kItems; ++q) {
+              if (m[q]) {
+                agg_x += x0[q];
+                agg_y += ly[q];
+                agg_rows += 1;
+              }
+            }
+          } else {
+            emit_unique(lk, ly, x0, m);
+          }
+        }
+        __syncthreads();
+        continue;
+      }
+      // duplicate build keys: the bucketised path below redoes this partition (nothing was emitted)
+    }
     for (int64_t c0 = r0; c0 < r1; c0 += kMaxBuild) {
       const uint32_t nbuild = (uint32_t)min((int64_t)kMaxBuild, r1 - c0);
       uint32_t lk[kItems], ly[kItems];
@@ -392,8 +525,16 @@ int ceil_log2_i64(int64_t v) {
   return b;
 }
 
+// Entry bits of the perfect-hash path for a partitioning that consumed `used` hash bits (0 = the
+// bucketised table: too many bits left for a shared-memory table).
+int direct_rest_bits(int used) {
+  const int rest = 32 - used;
+  return rest >= 1 && rest <= kDirectMaxBits ? rest : 0;
+}
+
 struct JoinPlan {
   int bits;        // fine partition bits
+  int rest_bits;   // perfect-hash entry bits (0: bucketised table)
   int slice_bits;  // log2 number of hash-space slices
   int64_t cap_r, cap_l, cap_tmp;
   bool two_pass;
@@ -402,7 +543,8 @@ struct JoinPlan {
 
 // ext_tmp: the temporary of the first radix pass lives outside the workspace (in the caller's
 // output columns, see join_impl).
-JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits, bool ext_tmp = false) {
+JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits, bool ext_tmp = false,
+                   int direct_min_rows = 2048) {
   JoinPlan P;
   P.slice_bits = slice_bits;
   const int64_t nslices = (int64_t)1 << slice_bits;
@@ -411,7 +553,14 @@ JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits, bool e
   bits = std::max(bits, 1);
   bits = std::min(bits, 2 * kPartMaxBits);
   bits = std::min(bits, 32 - skip_bits - slice_bits);
+  // a few more partition bits than the table size asks for make the perfect-hash path possible
+  // (<= 13 hash bits left), as long as partitions keep >= 1024 build rows
+  const int direct_bits = 32 - skip_bits - slice_bits - kDirectMaxBits;
+  if (direct_min_rows > 0 && direct_bits > bits && direct_bits <= 2 * kPartMaxBits &&
+      (nr_slice >> direct_bits) >= direct_min_rows)
+    bits = direct_bits;
   P.bits = std::max(bits, 1);
+  P.rest_bits = direct_min_rows > 0 ? direct_rest_bits(skip_bits + slice_bits + P.bits) : 0;
   P.two_pass = P.bits > kPartMaxBits;
   // slices are hash-uniform in expectation; leave 12.5 % + 64 Ki rows of slack for skew
   auto cap = [&](int64_t n) {
@@ -460,17 +609,18 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
                             (reinterpret_cast<uintptr_t>(d_out_fk) & 31) == 0 &&
                             12 * (uint64_t)out_capacity >= 8 * (uint64_t)std::max(nl, nr);
   // pick the smallest number of slices whose plan fits the workspace
-  JoinPlan P = make_plan(nl, nr, skip_bits, 0);
+  const int dmin = ctx->tune[B2_TUNE_JOIN_DIRECT_MIN_ROWS];
+  JoinPlan P = make_plan(nl, nr, skip_bits, 0, false, dmin);
   int sb = 0;
   bool ext_tmp = false;
   if (P.total > ws_bytes && out_adjacent && P.two_pass) {
-    const JoinPlan Q = make_plan(nl, nr, skip_bits, 0, true);
+    const JoinPlan Q = make_plan(nl, nr, skip_bits, 0, true, dmin);
     if (Q.total <= ws_bytes) {
       P = Q;
       ext_tmp = true;
     }
   }
-  while (P.total > ws_bytes && sb < kMaxSliceBits) P = make_plan(nl, nr, skip_bits, ++sb);
+  while (P.total > ws_bytes && sb < kMaxSliceBits) P = make_plan(nl, nr, skip_bits, ++sb, false, dmin);
   if (P.total > ws_bytes)
     return b2_set_error(ctx, B2_ERR_WORKSPACE, "join workspace", "see b2_join_min_ws_bytes()");
   char* base = static_cast<char*>(d_ws);
@@ -504,10 +654,10 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
       int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
       if (agg)
         join_probe_kernel<true><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
-            rout, roff, lout, loff, nparts, nullptr, nullptr, nullptr, 0, st, agg->y_thr, false);
+            rout, roff, lout, loff, nparts, nullptr, nullptr, nullptr, 0, st, agg->y_thr, false, P.rest_bits);
       else
         join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
-            rout, roff, lout, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false);
+            rout, roff, lout, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false, P.rest_bits);
       B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
     }
   }
@@ -618,7 +768,8 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
     }
     const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
     join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
-        rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false);
+        rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false,
+        ctx->tune[B2_TUNE_JOIN_DIRECT_MIN_ROWS] > 0 ? direct_rest_bits(skip_bits + P.total_bits) : 0);
     B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
   }
   join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows, d_abort);

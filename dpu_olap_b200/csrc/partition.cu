@@ -297,6 +297,15 @@ part_scatter_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   if (kPre && u.row0 < u.row1) load_tile(u.row0);
 
   for (int64_t t0 = u.row0; t0 < u.row1; t0 += kTileRows) {
+    if (kPre && tid == 0 && t0 + kTileRows < u.row1) {  // the next tile goes to L2 now, to registers after this tile is staged
+      const int64_t n0 = t0 + kTileRows, nn = min((int64_t)kTileRows, u.row1 - n0);
+      if (kAoS) {
+        l2_prefetch(in.pairs + n0, nn * 8);
+      } else {
+        l2_prefetch(in.keys + n0, nn * 4);
+        if (in.vals) l2_prefetch(in.vals + n0, nn * 4);
+      }
+    }
     // ---- (load,) hash once, rank inside the bucket ----
     if (!kPre) load_tile(t0);
     uint32_t packed[kI];  // bucket | rank << 16
@@ -463,6 +472,15 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   __syncthreads();
 
   for (int64_t t0 = u.row0; t0 < u.row1; t0 += kLcTile) {
+    if (tid == 0 && t0 + kLcTile < u.row1) {  // the next tile goes to L2 while this one is ranked, staged and sent
+      const int64_t n0 = t0 + kLcTile, nn = min((int64_t)kLcTile, u.row1 - n0);
+      if (kAoS) {
+        l2_prefetch(in.pairs + n0, nn * 8);
+      } else {
+        l2_prefetch(in.keys + n0, nn * 4);
+        if (in.vals) l2_prefetch(in.vals + n0, nn * 4);
+      }
+    }
     // ---- load, hash once, rank inside the bucket ----
     uint32_t key[kLcItems], val[kLcItems], packed[kLcItems];  // packed = bucket | rank << 16
 #pragma unroll
@@ -1130,15 +1148,6 @@ static_assert(sizeof(BkSmem) <= 227 * 1024, "BkSmem must fit the opt-in shared m
 __device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
                : "memory");
-}
-// Ask the copy engine to bring [p, p + bytes) into L2 (no registers, no completion to wait for).
-__device__ __forceinline__ void l2_prefetch(const void* p, int64_t bytes) {
-  uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uintptr_t a16 = (a + 15) & ~(uintptr_t)15;
-  bytes -= (int64_t)(a16 - a);
-  bytes &= ~(int64_t)15;
-  if (bytes > 0)
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"((uint32_t)bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

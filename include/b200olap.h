@@ -87,13 +87,16 @@ int b2_ctx_sm_count(const b2_ctx* ctx);
  * and so that a deployment can re-tune thresholds without a rebuild. Defaults are the measured best
  * on B200 (profiles/r1_filter.md, profiles/r1_scatter_fanout.md). */
 enum b2_tunable {
-  B2_TUNE_SCATTER_SECTORS_MIN_BITS = 0, /* log2 fan-out from which the radix scatter stores whole 32 B sectors (9; 0 = always, 11 = never) */
+  B2_TUNE_SCATTER_SECTORS_MIN_BITS = 0, /* log2 fan-out from which the radix scatter stores whole 32 B sectors (8; 0 = always, 11 = never) */
   B2_TUNE_SCATTER_PREFETCH = 1,         /* scatter kernels request the next tile while flushing this one (1) */
   B2_TUNE_SCATTER_SHAPE = 2,            /* plain scatter kernel shape: 0 = 512 thr x 16 rows x 2 CTA/SM, 1, 2, 3, 8 */
   B2_TUNE_FILTER_VARIANT = 3,           /* filter kernel shape 0..7 (6) */
-  B2_TUNE_SCATTER_SECTOR_TILE = 4       /* whole-sector scatter: 0 = 8192-row tiles x 2 CTA/SM, 1 = 16384-row tiles x 1 CTA/SM,
+  B2_TUNE_SCATTER_SECTOR_TILE = 4,      /* whole-sector scatter: 0 = 8192-row tiles x 2 CTA/SM, 1 = 16384-row tiles x 1 CTA/SM,
                                            2 = quad-aligned regions, 14336-row tiles x 1 CTA/SM,
                                            3 = quad-aligned regions flushed by the copy engine (cp.async.bulk), 16384-row tiles */
+  B2_TUNE_JOIN_DIRECT_MIN_ROWS = 5      /* perfect-hash probe path (join.cu): used when <= 13 hash bits are left below the partition
+                                           bits; the planner adds partition bits to get there while partitions keep at least this
+                                           many build rows (2048). 0 = path off, 1 = always when the bits allow (tests). */
 };
 int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value);
 int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value);

@@ -3,8 +3,10 @@
 
     python tools/join_lab.py [--sf 64,512] [--configs smem:0,smem:1,smem:2,smem:3]
 
-`smem:v[:b[:p]]` = shared-memory tables after two radix passes, scatter-kernel shape v, whole-sector
-scatter kernel from a fan-out of 2^b (default 9), next-tile prefetch p = 0 / 1 (default 1). (Commit 788c869
+`smem:v[:b[:p[:t[:d]]]]` = shared-memory tables after two radix passes, scatter-kernel shape v, whole-sector
+scatter kernel from a fan-out of 2^b (default 8), next-tile prefetch p = 0 / 1 (default 1), sector-kernel
+variant t (default 3 = bulk flush), perfect-hash probe path from d build rows per partition (0 = off).
+Settings are sticky from one config to the next: spell every field out when comparing. (Commit 788c869
 also had `l2:G:F`, the L2-resident table experiment described in profiles/r1_join_l2.md.)
 """
 import argparse, json, sys
@@ -43,6 +45,8 @@ def main():
                 ctx.set_tunable(1, int(f[3]))                    # B2_TUNE_SCATTER_PREFETCH
             if len(f) > 4:  # smem:v:b:p:t = whole-sector kernel over 16384-row tiles, one CTA per SM
                 ctx.set_tunable(4, int(f[4]))                    # B2_TUNE_SCATTER_SECTOR_TILE
+            if len(f) > 5:  # smem:v:b:p:t:d = perfect-hash probe path from d build rows per partition (0 = off)
+                ctx.set_tunable(5, int(f[5]))                    # B2_TUNE_JOIN_DIRECT_MIN_ROWS
             ws = torch.empty(ctx.join_ws_bytes(n, n) + 256, dtype=torch.uint8, device="cuda")
             step = lambda: ctx.join_dev(fk, y, pk, x, out_capacity=n, ws=ws, outs=outs, out_rows=rows)
             for o in outs:
