@@ -53,15 +53,23 @@ constexpr int kProbeCtasPerSm = 2;             // 3 CTAs/SM (40 registers, spill
 // multiplications and xor-shifts only), and every row of a partition has the same hash bits above the
 // low `rest` ones (the GPU / slice / partition fields). So two DIFFERENT keys of one partition differ
 // in the low `rest` bits of their hash: those bits index a table without collisions, whatever the key
-// set is. With rest <= 13 the table (2^rest entries of (key, value)) fits the shared memory the
-// bucketised table uses, an insert is ONE 64-bit shared-memory exchange, a probe is ONE 64-bit load and
-// a compare: no candidate buckets, no arrival counters, no chains (the bucketised probe loop issued
-// ~98 lane-instructions per row and kept the shared-memory pipe 73 % busy, profiles/r2_join_probe.md).
-// Only EQUAL keys can meet in an entry: the exchange hands the displaced row back, the partition is
-// then known to hold duplicate build keys and is redone by the bucketised path, which enumerates them.
-// Empty entries hold a key that cannot occur in the partition (0 or 1: their hashes differ above bit 13).
-constexpr int kDirectMaxBits = 13;             // 8192 entries x 8 B = 64 KB <= kTableBytes
-static_assert((8u << kDirectMaxBits) <= (unsigned)kTableBytes, "the perfect-hash table shares the bucketised table's memory");
+// set is — and whoever sits in the entry a probe key maps to IS that key, so the table stores no keys
+// at all: one 32-bit value per entry plus one occupancy bit. With rest <= 14 that is 64 KB + 2 KB, the
+// shared memory the bucketised table uses, for partitions of up to 16384 distinct keys (four times the
+// bucketised table's rows: both radix passes get away with a fan-out of 512 at SF=2048). An insert is
+// one store and one shared-memory atomicOr on the occupancy word, a probe two 32-bit loads and a bit
+// test: no candidate buckets, no arrival counters, no key compares, no chains (the bucketised probe
+// loop issued ~98 lane-instructions per row and kept the shared-memory pipe 73 % busy,
+// profiles/r2_join_probe.md). Only the 2 KB of occupancy bits are cleared per partition.
+// Only EQUAL keys can meet in an entry: the atomicOr finds the bit set, the partition is then known to
+// hold duplicate build keys and is redone by the bucketised path, which enumerates them.
+// PRECONDITION: every row handed to the kernel shares the hash bits above `rest` with its partition.
+// The partitioner guarantees it for the bits it consumed itself; bits skipped on the caller's word
+// (hash_skip_bits) are only trusted where the library routed the rows (the segmented entry points
+// behind the fused shuffle), see join_impl / join_seg_impl.
+constexpr int kDirectMaxBits = 14;             // 16384 values x 4 B + 512 occupancy words = 66 KB <= kTableBytes
+static_assert((4u << kDirectMaxBits) + (1u << kDirectMaxBits) / 8 <= (unsigned)kTableBytes,
+              "the perfect-hash table shares the bucketised table's memory");
 
 struct JoinState {  // lives in the workspace header
   unsigned long long out_rows;
@@ -236,9 +244,9 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
       }
     }
     if (rest_bits > 0) {
-      // ---- perfect-hash path: entry = low rest_bits of wang_hash(key) ----
-      unsigned long long* t64 = reinterpret_cast<unsigned long long*>(tab);
+      // ---- perfect-hash path: entry = low rest_bits of wang_hash(key); values | occupancy bits ----
       const uint32_t mask = (1u << rest_bits) - 1u;
+      uint32_t* occ = tab + (1u << rest_bits);
       uint32_t lk[kItems], ly[kItems];
       bool dup = false;
       {
@@ -246,12 +254,10 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
         const uint32_t nb0 = (uint32_t)min(r1 - r0, (int64_t)kRound);
         load_round(rpairs + r0, nb0, tid, rk, rv);
         load_round(lpairs + l0, (uint32_t)min(l1 - l0, (int64_t)kRound), tid, lk, ly);
-        const uint32_t k0 = __ldg(reinterpret_cast<const uint32_t*>(rpairs + r0));  // any key of the partition
         __syncthreads();  // the previous partition is done with the table
-        // a key whose hash differs from the partition's above the entry bits cannot occur in it
-        const uint32_t mk = ((wang_hash_u32(0u) ^ wang_hash_u32(k0)) >> rest_bits) != 0u ? 0u : 1u;
-        for (uint32_t i = tid; i < (1u << rest_bits) / 2; i += kThreads)
-          reinterpret_cast<uint4*>(tab)[i] = make_uint4(mk, 0u, mk, 0u);
+        for (uint32_t i = tid; i < (1u << rest_bits) / 128; i += kThreads)
+          reinterpret_cast<uint4*>(occ)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (rest_bits < 7 && tid < 4) occ[tid] = 0u;
         if (tid == 0) s_dup = 0;
         __syncthreads();
         for (int64_t base = r0; base < r1; base += kRound) {
@@ -260,9 +266,10 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
 #pragma unroll
           for (int q = 0; q < kItems; ++q) {
             if (q * kThreads + tid < nb) {
-              const unsigned long long old = atomicExch(&t64[wang_hash_u32(rk[q]) & mask],
-                                                        (unsigned long long)rk[q] | ((unsigned long long)rv[q] << 32));
-              dup |= (uint32_t)old != mk;  // only an equal key can have been there
+              const uint32_t idx = wang_hash_u32(rk[q]) & mask;
+              tab[idx] = rv[q];
+              const uint32_t bit = 1u << (idx & 31u);
+              dup |= (atomicOr(&occ[idx >> 5], bit) & bit) != 0u;  // only an equal key can have been there
             }
           }
         }
@@ -276,10 +283,11 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
           uint32_t x0[kItems], m[kItems];
 #pragma unroll
           for (int q = 0; q < kItems; ++q) {
-            const unsigned long long e = t64[wang_hash_u32(lk[q]) & mask];
+            const uint32_t idx = wang_hash_u32(lk[q]) & mask;
+            const uint32_t w = occ[idx >> 5];
+            x0[q] = tab[idx];
             const bool active = q * kThreads + tid < nprobe && (!kAgg || !filter_y || ly[q] < y_thr);
-            m[q] = (active && (uint32_t)e == lk[q]) ? 1u : 0u;
-            x0[q] = (uint32_t)(e >> 32);
+            m[q] = active ? (w >> (idx & 31u)) & 1u : 0u;
           }
           if (kAgg) {
 #pragma unroll
@@ -294,8 +302,7 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
             emit_unique(lk, ly, x0, m);
           }
         }
-        __syncthreads();
-        continue;
+        continue;  // the next partition's first barrier separates its table writes from these reads
       }
       // duplicate build keys: the bucketised path below redoes this partition (nothing was emitted)
     }
@@ -556,11 +563,17 @@ JoinPlan make_plan(int64_t nl, int64_t nr, int skip_bits, int slice_bits, bool e
   // a few more partition bits than the table size asks for make the perfect-hash path possible
   // (<= 13 hash bits left), as long as partitions keep >= 1024 build rows
   const int direct_bits = 32 - skip_bits - slice_bits - kDirectMaxBits;
-  if (direct_min_rows > 0 && direct_bits > bits && direct_bits <= 2 * kPartMaxBits &&
+  if (direct_min_rows > 0 && skip_bits == 0 && direct_bits > bits && direct_bits <= 2 * kPartMaxBits &&
       (nr_slice >> direct_bits) >= direct_min_rows)
     bits = direct_bits;
+  // ... and fewer bits than the bucketised table would want are enough when the perfect-hash table
+  // (2^14 entries) still holds a partition's expected rows: both radix passes get cheaper
+  if (direct_min_rows > 0 && skip_bits == 0 && direct_bits >= 1 && direct_bits < bits &&
+      ((nr_slice + ((int64_t)1 << direct_bits) - 1) >> direct_bits) <= ((int64_t)1 << kDirectMaxBits))
+    bits = direct_bits;
   P.bits = std::max(bits, 1);
-  P.rest_bits = direct_min_rows > 0 ? direct_rest_bits(skip_bits + slice_bits + P.bits) : 0;
+  // bits skipped on the caller's word are not trusted (see the precondition of the perfect-hash path)
+  P.rest_bits = direct_min_rows > 0 && skip_bits == 0 ? direct_rest_bits(slice_bits + P.bits) : 0;
   P.two_pass = P.bits > kPartMaxBits;
   // slices are hash-uniform in expectation; leave 12.5 % + 64 Ki rows of slack for skew
   auto cap = [&](int64_t n) {
@@ -685,14 +698,15 @@ part_gather_kernel(const uint2* __restrict__ pairs, int64_t n, const uint32_t* _
 // bucket boundaries in d_*_seg_off. Only the fine pass is left (or nothing at all when the coarse
 // buckets are already table-sized).
 struct SegPlan {
-  int total_bits, fine_bits;
+  int total_bits, fine_bits, rest_bits;
   size_t off_state, off_roff, off_loff, off_rout, off_lout, off_part, part_bytes, total;
 };
 
 // nl / nr size the buffers and work units (upper bounds are fine: the real row counts are the last
 // entries of the segment tables on the device); nr_expected (<= 0: nr) picks the number of fine
 // partitions, so a caller that only knows a generous receive CAPACITY still gets ~4096-row tables.
-bool make_seg_plan(int64_t nl, int64_t nr, int skip_bits, int seg_bits, SegPlan* P, int64_t nr_expected = 0) {
+bool make_seg_plan(int64_t nl, int64_t nr, int skip_bits, int seg_bits, SegPlan* P, int64_t nr_expected = 0,
+                   bool direct = true) {
   const int64_t nr_plan = nr_expected > 0 ? std::min(nr_expected, nr) : nr;
   int bits = ceil_log2_i64((nr_plan + kTargetBuild - 1) / kTargetBuild);
   bits = std::max(bits, seg_bits);
@@ -700,7 +714,13 @@ bool make_seg_plan(int64_t nl, int64_t nr, int skip_bits, int seg_bits, SegPlan*
   // one fine pass refines a coarse bucket at most 2^10-fold; beyond that partitions simply get
   // larger than the table and the probe kernel builds them in chunks
   bits = std::min(bits, seg_bits + kPartMaxBits);
+  // the perfect-hash table holds 2^14 distinct keys: fewer, larger partitions when it applies
+  const int direct_bits = 32 - skip_bits - kDirectMaxBits;
+  if (direct && direct_bits >= seg_bits && direct_bits < bits &&
+      ((nr_plan + ((int64_t)1 << direct_bits) - 1) >> direct_bits) <= ((int64_t)1 << kDirectMaxBits))
+    bits = direct_bits;
   P->total_bits = bits;
+  P->rest_bits = direct ? direct_rest_bits(skip_bits + bits) : 0;
   P->fine_bits = bits - seg_bits;
   const size_t noff = (((size_t)1 << bits) + 1) * 8;
   size_t o = 0;
@@ -730,7 +750,9 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
              "workspace must be 256 B aligned");
   SegPlan P;
-  if (!make_seg_plan(nl, nr, skip_bits, seg_bits, &P, nr_expected))
+  // the rows were routed here by their top skip_bits hash bits and grouped on the next seg_bits (the
+  // entry point's contract), so the perfect-hash path may rely on them
+  if (!make_seg_plan(nl, nr, skip_bits, seg_bits, &P, nr_expected, ctx->tune[B2_TUNE_JOIN_DIRECT_MIN_ROWS] > 0))
     return b2_set_error(ctx, B2_ERR_UNSUPPORTED, "segmented join",
                         "build side too large for one fine pass; use b2_join_pairs_dev");
   if (P.total > ws_bytes)
@@ -769,7 +791,7 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
     const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
     join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
         rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false,
-        ctx->tune[B2_TUNE_JOIN_DIRECT_MIN_ROWS] > 0 ? direct_rest_bits(skip_bits + P.total_bits) : 0);
+        P.rest_bits);
     B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
   }
   join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows, d_abort);
@@ -865,17 +887,18 @@ int b2_join_dest_rank(uint32_t key, int nranks) {
   return (int)(wang_hash_u32(key) >> (32 - bits));
 }
 
+// Sizes cover the plan with and without the perfect-hash path (a ctx tunable decides between them).
 size_t b2_join_ws_bytes(int64_t nl, int64_t nr) {
   if (nl < 0 || nr < 0) return 0;
-  return make_plan(nl, nr, 0, 0).total;
+  return std::max(make_plan(nl, nr, 0, 0).total, make_plan(nl, nr, 0, 0, false, 0).total);
 }
 size_t b2_join_ws_bytes_adjacent_outputs(int64_t nl, int64_t nr) {
   if (nl < 0 || nr < 0) return 0;
-  return make_plan(nl, nr, 0, 0, true).total;
+  return std::max(make_plan(nl, nr, 0, 0, true).total, make_plan(nl, nr, 0, 0, true, 0).total);
 }
 size_t b2_join_min_ws_bytes(int64_t nl, int64_t nr) {
   if (nl < 0 || nr < 0) return 0;
-  return make_plan(nl, nr, 0, kMaxSliceBits).total;
+  return std::max(make_plan(nl, nr, 0, kMaxSliceBits).total, make_plan(nl, nr, 0, kMaxSliceBits, false, 0).total);
 }
 
 int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
@@ -1026,15 +1049,19 @@ int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_
 }
 
 size_t b2_join_seg_ws_bytes(int64_t nl, int64_t nr, int hash_skip_bits, int seg_bits) {
-  SegPlan P;
-  if (nl < 0 || nr < 0 || !make_seg_plan(nl, nr, hash_skip_bits, seg_bits, &P)) return 0;
-  return P.total;
+  SegPlan P, Q;  // enough for the plan with and without the perfect-hash path (a ctx tunable decides)
+  if (nl < 0 || nr < 0 || !make_seg_plan(nl, nr, hash_skip_bits, seg_bits, &P) ||
+      !make_seg_plan(nl, nr, hash_skip_bits, seg_bits, &Q, 0, false))
+    return 0;
+  return std::max(P.total, Q.total);
 }
 size_t b2_join_seg_cap_ws_bytes(int64_t nl_cap, int64_t nr_cap, int64_t nr_expected, int hash_skip_bits,
                                 int seg_bits) {
-  SegPlan P;
-  if (nl_cap < 0 || nr_cap < 0 || !make_seg_plan(nl_cap, nr_cap, hash_skip_bits, seg_bits, &P, nr_expected)) return 0;
-  return P.total;
+  SegPlan P, Q;
+  if (nl_cap < 0 || nr_cap < 0 || !make_seg_plan(nl_cap, nr_cap, hash_skip_bits, seg_bits, &P, nr_expected) ||
+      !make_seg_plan(nl_cap, nr_cap, hash_skip_bits, seg_bits, &Q, nr_expected, false))
+    return 0;
+  return std::max(P.total, Q.total);
 }
 
 int b2_join_pairs_seg_cap_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl_cap,

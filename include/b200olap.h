@@ -94,9 +94,9 @@ enum b2_tunable {
   B2_TUNE_SCATTER_SECTOR_TILE = 4,      /* whole-sector scatter: 0 = 8192-row tiles x 2 CTA/SM, 1 = 16384-row tiles x 1 CTA/SM,
                                            2 = quad-aligned regions, 14336-row tiles x 1 CTA/SM,
                                            3 = quad-aligned regions flushed by the copy engine (cp.async.bulk), 16384-row tiles */
-  B2_TUNE_JOIN_DIRECT_MIN_ROWS = 5      /* perfect-hash probe path (join.cu): used when <= 13 hash bits are left below the partition
+  B2_TUNE_JOIN_DIRECT_MIN_ROWS = 5      /* perfect-hash probe path (join.cu): used when <= 14 hash bits are left below the partition
                                            bits; the planner adds partition bits to get there while partitions keep at least this
-                                           many build rows (2048). 0 = path off, 1 = always when the bits allow (tests). */
+                                           many build rows (2048), and takes fewer when 2^14-row partitions are enough. 0 = path off, 1 = always when the bits allow (tests). */
 };
 int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value);
 int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value);
@@ -618,7 +618,10 @@ int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_
                                size_t ws_bytes, void* stream);
 /* Join of sides that are already grouped into 2^seg_bits coarse buckets on hash bits
  * [hash_skip_bits, hash_skip_bits + seg_bits); d_*_seg_off (int64, 2^seg_bits + 1, device) hold the
- * bucket boundaries in rows. Same output contract as b2_join_pairs_dev. One fine pass refines a
+ * bucket boundaries in rows. PRECONDITION (the fused shuffle establishes it): every row of both sides
+ * has the same top hash_skip_bits bits of wang_hash(key), and sits in the coarse bucket its next
+ * seg_bits hash bits name — the probe kernel's perfect-hash table identifies a key by its remaining
+ * hash bits alone (csrc/join.cu). Same output contract as b2_join_pairs_dev. One fine pass refines a
  * coarse bucket at most 2^10-fold; build sides beyond 2^(seg_bits + 22) rows still join correctly
  * (oversized partitions are built in chunks) but more slowly. */
 size_t b2_join_seg_ws_bytes(int64_t nl, int64_t nr, int hash_skip_bits, int seg_bits);
