@@ -1133,17 +1133,22 @@ part_scatter_quads_kernel(PartInput in, const int64_t* __restrict__ seg_off,
 //     that precedes the next tile's staging, a full tile of work after the copies were issued;
 //   * a (unit, bucket) run's first sector, when shared with the neighbouring run, and its last, partial
 //     sector are written with plain 8-byte stores by the bucket's thread.
-constexpr int kBkT = 1024, kBkI = 16;
-constexpr int kBkTile = kBkT * kBkI;                                  // 16384 rows
-constexpr int kBkSlots = kBkTile + 6 * (1 << kPartMaxBits);           // + carried rows + padding to quads
-struct BkSmem {
-  uint2 stage[kBkSlots];                         // 176 KB
-  uint32_t cnt[2][1 << kPartMaxBits];            // 8 KB: rank counters of this tile / the next tile
-  uint32_t qstart[1 << kPartMaxBits];            // first stage slot of the bucket's region
-  uint2 carry[3][1 << kPartMaxBits];             // 24 KB: the rows that did not complete a sector (private to the bucket's thread)
+// Two shapes: kBkT = 1024 threads, one CTA per SM, 16384-row tiles, up to 1024 buckets; kBkT = 512 threads,
+// two CTAs per SM, 8192-row tiles, up to 512 buckets — the same 16 rows per bucket and tile at a fan-out
+// of 512, with one CTA's rank / scan / stage steps running under the other's loads and copies.
+template <int kBkT>
+struct BkSmemT {
+  static constexpr int kBuckets = kBkT;                  // one bucket per thread in the per-bucket steps
+  static constexpr int kTile = kBkT * 16;
+  static constexpr int kSlots = kTile + 6 * kBuckets;    // + carried rows + padding to quads
+  uint2 stage[kSlots];                           // 176 KB / 88 KB
+  uint32_t cnt[2][kBuckets];                     // rank counters of this tile / the next tile
+  uint32_t qstart[kBuckets];                     // first stage slot of the bucket's region
+  uint2 carry[3][kBuckets];                      // the rows that did not complete a sector (private to the bucket's thread)
   uint32_t warp_tot[kBkT / 32];
 };
-static_assert(sizeof(BkSmem) <= 227 * 1024, "BkSmem must fit the opt-in shared memory of one CTA");
+static_assert(sizeof(BkSmemT<1024>) <= 227 * 1024, "must fit the opt-in shared memory of one CTA");
+static_assert(2 * (sizeof(BkSmemT<512>) + 1024) <= 227 * 1024, "two CTAs of the small shape per SM");
 
 __device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
@@ -1152,13 +1157,15 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-template <bool kAoS, bool kPre>
-__global__ void __launch_bounds__(kBkT, 1)
+template <bool kAoS, bool kPre, int kBkT>
+__global__ void __launch_bounds__(kBkT, (kBkT >= 1024 ? 1 : 2))
 part_scatter_bulk_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                          const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
                          PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
                          int64_t out_cap, unsigned int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem[];  // the window itself starts 1024-byte aligned
+  using BkSmem = BkSmemT<kBkT>;
+  constexpr int kBkI = 16, kBkTile = BkSmem::kTile;
   BkSmem& sm = *reinterpret_cast<BkSmem*>(smem);
   const int P = 1 << g.bits;
   const SliceSel sel = slice_sel(g);
@@ -1263,7 +1270,7 @@ part_scatter_bulk_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     __syncthreads();
     uint32_t q0;
     {
-      const uint32_t w = sm.warp_tot[lane];  // kW == 32
+      const uint32_t w = lane < kW ? sm.warp_tot[lane] : 0u;
       uint32_t wi = w;
 #pragma unroll
       for (int o = 1; o < kW; o <<= 1) {
@@ -1470,8 +1477,8 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       const bool big = shape == 1;
       const bool pre = ctx->tune[B2_TUNE_SCATTER_PREFETCH] != 0;
       // the instantiations share one function-pointer type, so each gets its own site id
-      static const int sites[8] = {b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(),
-                                   b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site()};
+      static const int sites[10] = {b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(),
+                                    b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site(), b2_new_site()};
       auto go = [&](auto kernel, int site, int threads, size_t smem_bytes) -> int {
         if (b2_first_use_on_device(ctx, site))
           B2_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -1480,8 +1487,14 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
         return B2_OK;
       };
       if (shape == 3) {  // quad-aligned regions flushed by the copy engine: one bulk copy per (bucket, tile)
-        if (pre) B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, true>, sites[6], kBkT, sizeof(BkSmem)));
-        else B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, false>, sites[7], kBkT, sizeof(BkSmem)));
+        const bool small = g.bits <= 9 && ctx->tune[B2_TUNE_SCATTER_SHAPE] != 8;  // two 512-thread CTAs per SM
+        if (small) {
+          if (pre) B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, true, 512>, sites[8], 512, sizeof(BkSmemT<512>)));
+          else B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, false, 512>, sites[9], 512, sizeof(BkSmemT<512>)));
+        } else {
+          if (pre) B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, true, 1024>, sites[6], 1024, sizeof(BkSmemT<1024>)));
+          else B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, false, 1024>, sites[7], 1024, sizeof(BkSmemT<1024>)));
+        }
       } else if (shape == 2) {  // quad-aligned regions: the carried rows live in the stage, the flush is three reads and a store
         if (pre) B2_RETURN_NOT_OK(go(part_scatter_quads_kernel<kAoS, true>, sites[4], kQdT, sizeof(QdSmem)));
         else B2_RETURN_NOT_OK(go(part_scatter_quads_kernel<kAoS, false>, sites[5], kQdT, sizeof(QdSmem)));
