@@ -742,7 +742,7 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
                   const uint2* rpairs, const int64_t* r_seg_off, int64_t nr, int seg_bits,
                   uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
                   uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s,
-                  int64_t nr_expected = 0, const int64_t* d_abort = nullptr) {
+                  int64_t nr_expected = 0, const int64_t* d_abort = nullptr, cudaEvent_t l_ready = nullptr) {
   B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
   B2_REQUIRE(ctx, seg_bits >= 0 && seg_bits <= kPartMaxBits && skip_bits >= 0 && skip_bits + seg_bits <= 20,
              "bad skip/segment bits");
@@ -784,9 +784,13 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
       void* pws = base + P.off_part;
       B2_RETURN_NOT_OK(part_pass(ctx, rin, nr, r_seg_off, nseg, g, rout, nr, roff_w, &st->overflow, pws,
                                  P.part_bytes, s));
+      // the probe side may still be in flight (its NVLink scatter runs under the build side's fine pass)
+      if (l_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(s, l_ready, 0));
       B2_RETURN_NOT_OK(part_pass(ctx, lin, nl, l_seg_off, nseg, g, lout, nl, loff_w, &st->overflow, pws,
                                  P.part_bytes, s));
       rp = rout; lp = lout; roff = roff_w; loff = loff_w;
+    } else if (l_ready) {
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(s, l_ready, 0));
     }
     const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
     join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
@@ -1078,6 +1082,24 @@ int b2_join_pairs_seg_cap_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int6
                        reinterpret_cast<const uint2*>(d_r_pairs), d_r_seg_off, nr_cap, seg_bits, d_out_fk,
                        d_out_y, d_out_x, out_capacity, d_out_rows, hash_skip_bits, d_ws, ws_bytes,
                        static_cast<cudaStream_t>(stream), nr_expected, d_abort);
+}
+
+int b2_join_pairs_seg_cap_ev_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl_cap,
+                                 const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr_cap,
+                                 int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
+                                 uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
+                                 const int64_t* d_abort, void* l_ready_event, void* d_ws, size_t ws_bytes,
+                                 void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, nl_cap == 0 || d_l_pairs, "null left pairs");
+  B2_REQUIRE(ctx, nr_cap == 0 || d_r_pairs, "null right pairs");
+  B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
+  return join_seg_impl(ctx, reinterpret_cast<const uint2*>(d_l_pairs), d_l_seg_off, nl_cap,
+                       reinterpret_cast<const uint2*>(d_r_pairs), d_r_seg_off, nr_cap, seg_bits, d_out_fk,
+                       d_out_y, d_out_x, out_capacity, d_out_rows, hash_skip_bits, d_ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream), nr_expected, d_abort,
+                       static_cast<cudaEvent_t>(l_ready_event));
 }
 
 int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl,

@@ -227,7 +227,11 @@ class P2PShuffleJoin:
         self.addr = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
         self.seg = [torch.empty((1 << self.seg_bits) + 1, dtype=torch.int64, device=dev) for _ in range(2)]
         self.info = torch.zeros((2, 3), dtype=torch.int64, device=dev)  # {received, max over ranks, overflow} x side
-        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.flag = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.side = torch.cuda.Stream(device=dev)  # the probe side's scatter runs here, under the build side's fine pass
+        self.ev_r = torch.cuda.Event()
+        self.ev_l = torch.cuda.Event()
+        self.overlap = True
         self.last_recv = (0, 0)
 
     @property
@@ -245,8 +249,8 @@ class P2PShuffleJoin:
         return self.last_recv
 
     def step(self, fk, y, pk, x, local_join, phases: dict | None = None):
-        """local_join(l_buf, l_seg_off, r_buf, r_seg_off, nr_expected, seg_bits, skip_bits, abort) -> result,
-        e.g. ctx.join_pairs_seg_cap_dev. phases: if given, every phase is synchronised and its wall
+        """local_join(l_buf, l_seg_off, r_buf, r_seg_off, nr_expected, seg_bits, skip_bits, abort, l_ready) ->
+        result, e.g. ctx.join_pairs_seg_cap_dev (l_ready: event to wait for before reading the probe side, or None). phases: if given, every phase is synchronised and its wall
         time (ms) stored there (diagnostics only — the synchronisation removes all overlap)."""
         import time
 
@@ -274,12 +278,27 @@ class P2PShuffleJoin:
         ctx.shuffle_p2p_plan_dev(self.off_ptrs[1], self.peers[1], self.rank, G, self.BITS, self.capacity,
                                  self.addr[1], self.seg[1], self.info[1], prev_abort=self.info[0, 2:3])
         mark("allgather+plan")
-        ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, self.addr[0], self.ws[0], abort=self.info[0, 2:3])
+        if not self.overlap or phases is not None:
+            ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, self.addr[0], self.ws[0], abort=self.abort)
+            ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[1], self.ws[1], abort=self.abort)
+            mark("scatter_nvlink")
+            self.dist.all_reduce(self.flag[0:1])  # every rank's stores have landed when this completes
+            mark("barrier")
+            out = local_join(self.recv[0], self.seg[0], self.recv[1], self.seg[1], self.nr_expected, self.seg_bits,
+                             self.skip, self.abort, None)
+            mark("local_join")
+            return out
+        # Build side first; once every rank's build rows have landed, this rank's fine partitioning pass
+        # over them runs under the probe side's NVLink scatter (side stream). The join waits for the probe
+        # side (event) only after the build side's pass has been enqueued.
+        main = torch.cuda.current_stream()
         ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[1], self.ws[1], abort=self.abort)
-        mark("scatter_nvlink")
-        self.dist.all_reduce(self.flag)  # every rank's stores have landed when this completes
-        mark("barrier")
-        out = local_join(self.recv[0], self.seg[0], self.recv[1], self.seg[1], self.nr_expected, self.seg_bits,
-                         self.skip, self.abort)
-        mark("local_join")
-        return out
+        self.ev_r.record(main)
+        self.dist.all_reduce(self.flag[1:2])          # build rows of every rank have landed
+        self.side.wait_event(self.ev_r)               # the link is the build side's until then
+        with torch.cuda.stream(self.side):
+            ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, self.addr[0], self.ws[0], abort=self.abort)
+            self.dist.all_reduce(self.flag[0:1])      # probe rows of every rank have landed
+            self.ev_l.record(self.side)
+        return local_join(self.recv[0], self.seg[0], self.recv[1], self.seg[1], self.nr_expected, self.seg_bits,
+                          self.skip, self.abort, self.ev_l)

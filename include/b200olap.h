@@ -643,6 +643,16 @@ int b2_join_pairs_seg_cap_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int6
                               int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
                               uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
                               const int64_t* d_abort, void* d_ws, size_t ws_bytes, void* stream);
+/* ... and when the probe side may still be arriving: l_ready_event (a cudaEvent_t, may be NULL) is
+ * waited for on `stream` AFTER the build side's fine partitioning pass has been enqueued and before
+ * anything reads d_l_pairs / d_l_seg_off, so the caller can run the probe side's NVLink scatter (on
+ * another stream, recording the event once every peer's stores have landed) under that pass. */
+int b2_join_pairs_seg_cap_ev_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl_cap,
+                                 const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr_cap,
+                                 int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
+                                 uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
+                                 const int64_t* d_abort, void* l_ready_event, void* d_ws, size_t ws_bytes,
+                                 void* stream);
 
 #ifdef __cplusplus
 }

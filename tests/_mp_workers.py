@@ -43,9 +43,10 @@ def p2p_join_worker(rank: int, world: int, port: int, nb_total: int, batch: int,
         jws = torch.empty(ctx.join_seg_cap_ws_bytes(cap, cap, pj.nr_expected, pj.skip, pj.seg_bits) + 256,
                           dtype=torch.uint8, device="cuda")
 
-        def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort):
+        def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort, l_ready):
             ctx.join_pairs_seg_cap_dev(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, out_capacity=cap * mult,
-                                       skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t, abort=abort)
+                                       skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t, abort=abort,
+                                       l_ready=l_ready)
 
         for _ in range(3):  # repeated steps reuse the receive buffers: the barrier protocol must hold
             outs[0].zero_()
