@@ -36,6 +36,7 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "scan.cuh"
@@ -74,9 +75,16 @@ struct Unit {
 // segments before s; empty segments own no unit.
 __device__ __forceinline__ Unit find_unit(const int64_t* __restrict__ seg_off,
                                           const int64_t* __restrict__ unit_first, int64_t nseg,
+                                          int64_t unit_rows, int P, int64_t id);
+__device__ __forceinline__ Unit find_unit(const int64_t* __restrict__ seg_off,
+                                          const int64_t* __restrict__ unit_first, int64_t nseg,
                                           int64_t unit_rows, int P) {
+  return find_unit(seg_off, unit_first, nseg, unit_rows, P, (int64_t)blockIdx.x);
+}
+__device__ __forceinline__ Unit find_unit(const int64_t* __restrict__ seg_off,
+                                          const int64_t* __restrict__ unit_first, int64_t nseg,
+                                          int64_t unit_rows, int P, int64_t id) {
   Unit u;
-  const int64_t id = blockIdx.x;
   u.valid = id < unit_first[nseg];
   if (!u.valid) return u;
   int64_t lo = 0, hi = nseg;  // last s with unit_first[s] <= id
@@ -455,10 +463,14 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
   if (abort_flag && *abort_flag) return;
   const int P = 1 << g.bits;
   const SliceSel sel = slice_sel(g);
-  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
-  if (!u.valid) return;
   constexpr int kW = kLcThreads / 32;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // A grid smaller than the number of work units walks them (a CTA budget: the rest of the SMs stay
+  // free for a kernel of another stream, e.g. the build side's fine pass under the probe side's scatter).
+  for (int64_t unit_id = blockIdx.x;; unit_id += gridDim.x) {
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P, unit_id);
+  if (!u.valid) return;
+  __syncthreads();  // the previous unit's last reads of the carry buffers
 
   if ((int)tid < P) {
     const int p = tid;
@@ -595,6 +607,7 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
         st_stream_v2(reinterpret_cast<uint2*>(sm.gline[b] + 8ull * l), sm.carry[b * kLineRows + l]);
     }
   }
+  }  // units of this CTA
 }
 
 // ---- local scatter that only writes whole 32-byte sectors ------------------------------------------
@@ -1515,7 +1528,9 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(LcSmem)));
       }
-      part_scatter_lines_kernel<kAoS><<<(unsigned)L.max_units, kLcThreads, sizeof(LcSmem), s>>>(
+      const int budget = ctx->tune[B2_TUNE_PEER_SCATTER_CTAS];
+      const int64_t grid = budget > 0 ? std::min<int64_t>(L.max_units, budget) : L.max_units;
+      part_scatter_lines_kernel<kAoS><<<(unsigned)grid, kLcThreads, sizeof(LcSmem), s>>>(
           in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned, d_bucket_addr, d_abort);
     } else if (g.val_pred) {  // pushed-down value predicate: one shape, the default one
       if (ctx->tune[B2_TUNE_SCATTER_PREFETCH])

@@ -15,8 +15,12 @@ split sizes, capacity checks, the all-to-all itself — runs unchanged on CPU te
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Any, Callable
+
+
+TUNE_PEER_SCATTER_CTAS = 6  # enum b2_tunable (include/b200olap.h)
 
 
 def shard_range(nbatches: int, rank: int, world: int) -> tuple[int, int]:
@@ -232,6 +236,10 @@ class P2PShuffleJoin:
         self.ev_r = torch.cuda.Event()
         self.ev_l = torch.cuda.Event()
         self.overlap = True
+        # CTA budget of the probe side's scatter while the build side's fine pass wants SMs too (0 = all)
+        # measured on 8 B200 at SF=2048 (tools/n8_overlap_sweep.sh): all SMs 20.1 ms, 96 CTAs 19.0 ms, 64 CTAs 22.2 ms
+        # per join step; with 2 ranks the scatter is not link-bound and keeps every SM
+        self.probe_scatter_ctas = int(os.environ.get("B2_PROBE_SCATTER_CTAS", "96" if world >= 8 else "0"))
         self.last_recv = (0, 0)
 
     @property
@@ -297,7 +305,11 @@ class P2PShuffleJoin:
         self.dist.all_reduce(self.flag[1:2])          # build rows of every rank have landed
         self.side.wait_event(self.ev_r)               # the link is the build side's until then
         with torch.cuda.stream(self.side):
+            if self.probe_scatter_ctas:
+                ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, self.probe_scatter_ctas)
             ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, self.addr[0], self.ws[0], abort=self.abort)
+            if self.probe_scatter_ctas:
+                ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, 0)
             self.dist.all_reduce(self.flag[0:1])      # probe rows of every rank have landed
             self.ev_l.record(self.side)
         return local_join(self.recv[0], self.seg[0], self.recv[1], self.seg[1], self.nr_expected, self.seg_bits,

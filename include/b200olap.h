@@ -94,6 +94,9 @@ enum b2_tunable {
   B2_TUNE_SCATTER_SECTOR_TILE = 4,      /* whole-sector scatter: 0 = 8192-row tiles x 2 CTA/SM, 1 = 16384-row tiles x 1 CTA/SM,
                                            2 = quad-aligned regions, 14336-row tiles x 1 CTA/SM,
                                            3 = quad-aligned regions flushed by the copy engine (cp.async.bulk), 16384-row tiles */
+  B2_TUNE_PEER_SCATTER_CTAS = 6,        /* CTA budget of the peer (NVLink) scatter kernel: 0 = one CTA per work unit (all SMs);
+                                           n > 0 = at most n CTAs walk the units and leave the other SMs to kernels of
+                                           other streams (the overlapped sharded join sets it around the probe side's scatter) */
   B2_TUNE_JOIN_DIRECT_MIN_ROWS = 5      /* perfect-hash probe path (join.cu): used when <= 14 hash bits are left below the partition
                                            bits; the planner adds partition bits to get there while partitions keep at least this
                                            many build rows (2048), and takes fewer when 2^14-row partitions are enough. 0 = path off, 1 = always when the bits allow (tests). */
