@@ -247,13 +247,20 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
       // ---- perfect-hash path: entry = low rest_bits of wang_hash(key); values | occupancy bits ----
       const uint32_t mask = (1u << rest_bits) - 1u;
       uint32_t* occ = tab + (1u << rest_bits);
+      const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab), occ_s = tab_s + (4u << rest_bits);
       uint32_t lk[kItems], ly[kItems];
-      bool dup = false;
+      uint32_t dup = 0;
+      // rounds after the first of either side are requested into L2 one round ahead (the partition-level
+      // request above only covers the first round of each side)
+      auto prefetch_round = [&](const uint2* base, int64_t from, int64_t end) {
+        if (tid == kThreads - 64 && from < end) l2_prefetch(base + from, min(end - from, (int64_t)kRound) * 8);
+      };
       {
         uint32_t rk[kItems], rv[kItems];
         const uint32_t nb0 = (uint32_t)min(r1 - r0, (int64_t)kRound);
         load_round(rpairs + r0, nb0, tid, rk, rv);
         load_round(lpairs + l0, (uint32_t)min(l1 - l0, (int64_t)kRound), tid, lk, ly);
+        prefetch_round(rpairs, r0 + kRound, r1);
         __syncthreads();  // the previous partition is done with the table
         for (uint32_t i = tid; i < (1u << rest_bits) / 128; i += kThreads)
           reinterpret_cast<uint4*>(occ)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -263,13 +270,17 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
         for (int64_t base = r0; base < r1; base += kRound) {
           const uint32_t nb = (uint32_t)min(r1 - base, (int64_t)kRound);
           if (base > r0) load_round(rpairs + base, nb, tid, rk, rv);
+          prefetch_round(rpairs, base + 2 * kRound, r1);
+          if (base + kRound >= r1) prefetch_round(lpairs, l0 + kRound, l1);
 #pragma unroll
           for (int q = 0; q < kItems; ++q) {
-            if (q * kThreads + tid < nb) {
+            if (nb == (uint32_t)kRound || q * kThreads + tid < nb) {
               const uint32_t idx = wang_hash_u32(rk[q]) & mask;
-              tab[idx] = rv[q];
               const uint32_t bit = 1u << (idx & 31u);
-              dup |= (atomicOr(&occ[idx >> 5], bit) & bit) != 0u;  // only an equal key can have been there
+              uint32_t old;
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_s + idx * 4u), "r"(rv[q]) : "memory");
+              asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(occ_s + (idx >> 5) * 4u), "r"(bit) : "memory");
+              dup |= old & bit;  // only an equal key can have been there
             }
           }
         }
@@ -280,13 +291,16 @@ join_probe_kernel(const uint2* __restrict__ rpairs, const int64_t* __restrict__ 
         for (int64_t t0 = l0; t0 < l1; t0 += kRound) {
           const uint32_t nprobe = (uint32_t)min(l1 - t0, (int64_t)kRound);
           if (t0 > l0) load_round(lpairs + t0, nprobe, tid, lk, ly);
+          if (t0 > l0) prefetch_round(lpairs, t0 + kRound, l1);
           uint32_t x0[kItems], m[kItems];
 #pragma unroll
           for (int q = 0; q < kItems; ++q) {
             const uint32_t idx = wang_hash_u32(lk[q]) & mask;
-            const uint32_t w = occ[idx >> 5];
-            x0[q] = tab[idx];
-            const bool active = q * kThreads + tid < nprobe && (!kAgg || !filter_y || ly[q] < y_thr);
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(occ_s + (idx >> 5) * 4u));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x0[q]) : "r"(tab_s + idx * 4u));
+            const bool active = (nprobe == (uint32_t)kRound || q * kThreads + tid < nprobe) &&
+                                (!kAgg || !filter_y || ly[q] < y_thr);
             m[q] = active ? (w >> (idx & 31u)) & 1u : 0u;
           }
           if (kAgg) {
