@@ -643,10 +643,10 @@ def bench_join(ctx, D, args):
             info["workspace_gib"] = round(jws_bytes / 2**30, 2)
             info["sliced"] = False
 
-            def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort, l_ready):
+            def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort, phase_bits):
                 ctx.join_pairs_seg_cap_dev(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, out_capacity=cap * mult,
                                            skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t, abort=abort,
-                                           l_ready=l_ready)
+                                           phases=phase_bits)
 
             def step():
                 pj.step(fk, y, pk, x, local_join)
@@ -656,9 +656,11 @@ def bench_join(ctx, D, args):
             ph = {}
             pj.step(fk, y, pk, x, local_join, phases=ph)  # one extra, synchronised step: where the time goes
             info["phases_ms_rank0_serialised"] = {k: round(v, 3) for k, v in ph.items()}
-            info["overlap"] = ("timed steps: build-side scatter | barrier | probe-side scatter on a second stream "
-                               "UNDER the build side's fine partitioning pass | probe-side pass + probe; the "
-                               "serialised phase list above comes from one extra, synchronised step")
+            info["overlap"] = (f"timed steps: build-side scatter | barrier | probe-side scatter in {pj.shares} share(s) "
+                               f"on a second stream ({pj.probe_scatter_ctas or 'all'} CTAs) UNDER the build side's fine "
+                               "pass and the previous share's fine pass + probe; the serialised phase list above "
+                               "comes from one extra, synchronised step")
+            info["probe_shares"] = pj.shares
             info["nvlink_gbs_per_direction_serialised"] = round(
                 16 * n * (G - 1) / G / (ph["scatter_nvlink"] * 1e-3) / 1e9, 1) if ph.get("scatter_nvlink") else None
             nl_r, nr_r = pj.received()

@@ -83,8 +83,8 @@ SIGNATURES = {
     "b2_join_seg_cap_ws_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "b2_join_pairs_seg_cap_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _vp,
                                          _int, _vp, _vp, _sz, _vp]),
-    "b2_join_pairs_seg_cap_ev_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _vp,
-                                            _int, _vp, _vp, _vp, _sz, _vp]),
+    "b2_join_pairs_seg_cap_phased_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _i64,
+                                                _vp, _int, _vp, _int, _vp, _sz, _vp]),
     "b2_join_seg_ws_bytes": (_sz, [_i64, _i64, _int, _int]),
     "b2_join_pairs_seg_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _i64, _vp, _int,
                                      _vp, _sz, _vp]),

@@ -756,11 +756,12 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
                   const uint2* rpairs, const int64_t* r_seg_off, int64_t nr, int seg_bits,
                   uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
                   uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s,
-                  int64_t nr_expected = 0, const int64_t* d_abort = nullptr, cudaEvent_t l_ready = nullptr) {
+                  int64_t nr_expected = 0, const int64_t* d_abort = nullptr, int phases = 7) {
   B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
   B2_REQUIRE(ctx, seg_bits >= 0 && seg_bits <= kPartMaxBits && skip_bits >= 0 && skip_bits + seg_bits <= 20,
              "bad skip/segment bits");
-  B2_REQUIRE(ctx, d_out_rows && l_seg_off && r_seg_off, "null pointer");
+  B2_REQUIRE(ctx, r_seg_off && (l_seg_off || !(phases & 2)) && (d_out_rows || !(phases & 4)), "null pointer");
+  B2_REQUIRE(ctx, phases >= 1 && phases <= 7, "phases: 1 build | 2 probe | 4 finish");
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
              "workspace must be 256 B aligned");
   SegPlan P;
@@ -773,9 +774,11 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
     return b2_set_error(ctx, B2_ERR_WORKSPACE, "segmented join workspace", "see b2_join_seg_ws_bytes()");
   char* base = static_cast<char*>(d_ws);
   JoinState* st = reinterpret_cast<JoinState*>(base + P.off_state);
-  join_init_kernel<<<1, 1, 0, s>>>(st);
-  B2_LAUNCH_CHECK(ctx, "join_init_kernel");
-  if (nl > 0 && nr > 0) {
+  if (phases & 1) {
+    join_init_kernel<<<1, 1, 0, s>>>(st);
+    B2_LAUNCH_CHECK(ctx, "join_init_kernel");
+  }
+  if ((nl > 0 || !(phases & 2)) && nr > 0) {
     static const int seen = b2_new_site();
     if (b2_first_use_on_device(ctx, seen))
       B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -796,24 +799,27 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
       int64_t* roff_w = reinterpret_cast<int64_t*>(base + P.off_roff);
       int64_t* loff_w = reinterpret_cast<int64_t*>(base + P.off_loff);
       void* pws = base + P.off_part;
-      B2_RETURN_NOT_OK(part_pass(ctx, rin, nr, r_seg_off, nseg, g, rout, nr, roff_w, &st->overflow, pws,
-                                 P.part_bytes, s));
-      // the probe side may still be in flight (its NVLink scatter runs under the build side's fine pass)
-      if (l_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(s, l_ready, 0));
-      B2_RETURN_NOT_OK(part_pass(ctx, lin, nl, l_seg_off, nseg, g, lout, nl, loff_w, &st->overflow, pws,
-                                 P.part_bytes, s));
+      // build phase: the build side's fine pass; its result stays in the workspace for every probe phase
+      if (phases & 1)
+        B2_RETURN_NOT_OK(part_pass(ctx, rin, nr, r_seg_off, nseg, g, rout, nr, roff_w, &st->overflow, pws,
+                                   P.part_bytes, s));
+      if (phases & 2)
+        B2_RETURN_NOT_OK(part_pass(ctx, lin, nl, l_seg_off, nseg, g, lout, nl, loff_w, &st->overflow, pws,
+                                   P.part_bytes, s));
       rp = rout; lp = lout; roff = roff_w; loff = loff_w;
-    } else if (l_ready) {
-      B2_CUDA_OK(ctx, cudaStreamWaitEvent(s, l_ready, 0));
     }
-    const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
-    join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
-        rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false,
-        P.rest_bits);
-    B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
+    if (phases & 2) {  // probe phase: may run several times, each over another share of the probe side
+      const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
+      join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+          rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false,
+          P.rest_bits);
+      B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
+    }
   }
-  join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows, d_abort);
-  B2_LAUNCH_CHECK(ctx, "join_finish_kernel");
+  if (phases & 4) {
+    join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows, d_abort);
+    B2_LAUNCH_CHECK(ctx, "join_finish_kernel");
+  }
   return B2_OK;
 }
 
@@ -1098,22 +1104,21 @@ int b2_join_pairs_seg_cap_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int6
                        static_cast<cudaStream_t>(stream), nr_expected, d_abort);
 }
 
-int b2_join_pairs_seg_cap_ev_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl_cap,
-                                 const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr_cap,
-                                 int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
-                                 uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
-                                 const int64_t* d_abort, void* l_ready_event, void* d_ws, size_t ws_bytes,
-                                 void* stream) {
+int b2_join_pairs_seg_cap_phased_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off,
+                                     int64_t nl_cap, const uint64_t* d_r_pairs, const int64_t* d_r_seg_off,
+                                     int64_t nr_cap, int64_t nr_expected, int seg_bits, uint32_t* d_out_fk,
+                                     uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                                     uint64_t* d_out_rows, int hash_skip_bits, const int64_t* d_abort, int phases,
+                                     void* d_ws, size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
   b2_device_scope dev_scope(ctx);
-  B2_REQUIRE(ctx, nl_cap == 0 || d_l_pairs, "null left pairs");
+  B2_REQUIRE(ctx, nl_cap == 0 || d_l_pairs || !(phases & 2), "null left pairs");
   B2_REQUIRE(ctx, nr_cap == 0 || d_r_pairs, "null right pairs");
-  B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x), "null output column");
+  B2_REQUIRE(ctx, out_capacity == 0 || (d_out_fk && d_out_y && d_out_x) || !(phases & 2), "null output column");
   return join_seg_impl(ctx, reinterpret_cast<const uint2*>(d_l_pairs), d_l_seg_off, nl_cap,
                        reinterpret_cast<const uint2*>(d_r_pairs), d_r_seg_off, nr_cap, seg_bits, d_out_fk,
                        d_out_y, d_out_x, out_capacity, d_out_rows, hash_skip_bits, d_ws, ws_bytes,
-                       static_cast<cudaStream_t>(stream), nr_expected, d_abort,
-                       static_cast<cudaEvent_t>(l_ready_event));
+                       static_cast<cudaStream_t>(stream), nr_expected, d_abort, phases);
 }
 
 int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl,

@@ -630,18 +630,16 @@ class Context:
         return int(self._lib.b2_join_seg_cap_ws_bytes(nl_cap, nr_cap, nr_expected, skip_bits, seg_bits))
 
     def join_pairs_seg_cap_dev(self, l_pairs, l_seg_off, r_pairs, r_seg_off, nr_expected: int, seg_bits: int,
-                               out_capacity: int, skip_bits: int, ws, outs, out_rows, abort=None, l_ready=None):
-        """b2_join_pairs_seg_cap_ev_dev: l_pairs / r_pairs are whole receive BUFFERS (their sizes are
+                               out_capacity: int, skip_bits: int, ws, outs, out_rows, abort=None, phases: int = 7):
+        """b2_join_pairs_seg_cap_phased_dev: l_pairs / r_pairs are whole receive BUFFERS (their sizes are
         capacities); the rows really there are the last entries of the segment tables, on the device.
-        l_ready: a recorded torch.cuda.Event the current stream waits for before it touches the probe side
-        (after the build side's fine pass has been enqueued)."""
+        phases: 1 build | 2 probe (repeatable, one share of the probe side per call) | 4 finish."""
         ptr, nbytes = self._aligned(ws)
-        self._ck(self._lib.b2_join_pairs_seg_cap_ev_dev(
+        self._ck(self._lib.b2_join_pairs_seg_cap_phased_dev(
             self._h, _dptr(l_pairs), _dptr(l_seg_off), l_pairs.numel(), _dptr(r_pairs), _dptr(r_seg_off),
             r_pairs.numel(), int(nr_expected), seg_bits, _dptr(outs[0]), _dptr(outs[1]), _dptr(outs[2]),
-            int(out_capacity), _dptr(out_rows), skip_bits, None if abort is None else _dptr(abort),
-            None if l_ready is None else int(l_ready.cuda_event), ptr, nbytes,
-            self._stream()), "b2_join_pairs_seg_cap_ev_dev")
+            int(out_capacity), _dptr(out_rows), skip_bits, None if abort is None else _dptr(abort), int(phases),
+            ptr, nbytes, self._stream()), "b2_join_pairs_seg_cap_phased_dev")
         return outs[0], outs[1], outs[2], out_rows
 
     def join_seg_ws_bytes(self, nl: int, nr: int, skip_bits: int, seg_bits: int) -> int:

@@ -190,19 +190,24 @@ class P2PShuffleJoin:
     """Sharded join whose exchange is FUSED into the routing kernel: every rank scatters its
     (key, payload) pairs straight into the peers' receive buffers with NVLink stores
     (b2_shuffle_p2p_scatter_dev), already grouped into coarse partitions, so there is no separate
-    all-to-all and the receiver skips its first partitioning pass (b2_join_pairs_seg_cap_dev).
+    all-to-all and the receiver skips its first partitioning pass (b2_join_pairs_seg_cap_phased_dev).
 
     One step enqueues, with NO host synchronisation and no eager tensor arithmetic in between:
-      count L, count R | all-gather of the 2 x 1025 boundaries (also the "everyone has read its
-      receive buffers" barrier) | b2_shuffle_p2p_plan_dev x 2 (addresses, coarse boundaries, the
-      collective overflow flag — all on the device) | scatter L, scatter R over NVLink | barrier |
-      local join of the receive BUFFERS (row counts stay on the device).
-    Receive buffers are torch symmetric-memory allocations; their peer addresses come from the
-    rendezvous handle. This class is plumbing only: every kernel is behind include/b200olap.h."""
+      counts | all-gather of the boundaries (also the "everyone has read its receive buffers" barrier) |
+      b2_shuffle_p2p_plan_dev per side (addresses, coarse boundaries, the collective overflow flag — all
+      on the device) | build side over NVLink | barrier | on a second stream: the probe side over NVLink
+      in `probe_shares` shares, a barrier and an event after each | on the main stream: the build side's
+      fine pass (UNDER the first share's transfer), then per share: wait for its event, fine pass +
+      probe (under the next share's transfer).
+    The probe side's scatter kernel runs with a CTA budget while it shares the GPU (b2_tunable
+    B2_TUNE_PEER_SCATTER_CTAS). Receive buffers are torch symmetric-memory allocations; their peer
+    addresses come from the rendezvous handle. This class is plumbing only: every kernel is behind
+    include/b200olap.h."""
 
     BITS = 10  # log2(G) destination bits + coarse bits: one radix pass
 
-    def __init__(self, ctx, dist, rank: int, world: int, n_local: int, capacity: int, n_build_total: int | None = None):
+    def __init__(self, ctx, dist, rank: int, world: int, n_local: int, capacity: int, n_build_total: int | None = None,
+                 probe_shares: int | None = None):
         import torch
         import torch.distributed._symmetric_memory as symm
         self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
@@ -211,59 +216,73 @@ class P2PShuffleJoin:
         self.capacity = capacity
         # build rows a rank receives when the hash spreads evenly: picks the fine partition count
         self.nr_expected = (n_build_total if n_build_total is not None else n_local * world) // world
+        # shares of the probe side (sides 0 .. S-1; side S is the build side). One share is the measured
+        # best: 8 B200, SF=2048, 96-CTA budget: 19.0 ms per step with one share, 19.8 ms with two (the
+        # probe kernel builds its tables once per share and the concurrent kernels take SMs from each
+        # other), 22.2 ms with three (profiles/r2_multi_gpu.md).
+        S = probe_shares if probe_shares is not None else int(os.environ.get("B2_PROBE_SHARES", "1"))
+        self.shares = S = max(1, S)
+        self.share_rows = n_local if S == 1 else ((n_local + S - 1) // S + 1023) // 1024 * 1024
+        cap_share = capacity if S == 1 else (capacity + S - 1) // S + 65536
+        self.caps = [cap_share] * S + [capacity]
         dev = torch.device("cuda", torch.cuda.current_device())
         group = dist.group.WORLD.group_name
         B = 1 << self.BITS
-        self.recv, self.peers = [], []
-        for _ in range(2):  # L, R
-            t = symm.empty(capacity, dtype=torch.int64, device=dev)
+        self.recv, self.peers, self.ws = [], [], []
+        for side in range(S + 1):
+            t = symm.empty(self.caps[side], dtype=torch.int64, device=dev)
             hdl = symm.rendezvous(t, group)
             self.recv.append(t)
             self.peers.append(torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev))
-        nbytes = ctx.shuffle_p2p_ws_bytes(n_local, self.BITS) + 256
-        self.ws = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-        self.my_off = torch.zeros((2, B + 1), dtype=torch.int64, device=dev)       # count kernels write here
-        self.all_off = torch.zeros((world, 2, B + 1), dtype=torch.int64, device=dev)  # after the all-gather
+            n_side = n_local if side == S else min(self.share_rows, n_local)
+            self.ws.append(torch.empty(ctx.shuffle_p2p_ws_bytes(n_side, self.BITS) + 256, dtype=torch.uint8, device=dev))
+        self.my_off = torch.zeros((S + 1, B + 1), dtype=torch.int64, device=dev)           # count kernels write here
+        self.all_off = torch.zeros((world, S + 1, B + 1), dtype=torch.int64, device=dev)   # after the all-gather
         base = self.all_off.data_ptr()
-        stride_rank, stride_side = 2 * (B + 1) * 8, (B + 1) * 8
+        stride_rank, stride_side = (S + 1) * (B + 1) * 8, (B + 1) * 8
         self.off_ptrs = [torch.tensor([base + s * stride_rank + side * stride_side for s in range(world)],
-                                      dtype=torch.int64, device=dev) for side in range(2)]
-        self.addr = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
-        self.seg = [torch.empty((1 << self.seg_bits) + 1, dtype=torch.int64, device=dev) for _ in range(2)]
-        self.info = torch.zeros((2, 3), dtype=torch.int64, device=dev)  # {received, max over ranks, overflow} x side
-        self.flag = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.side = torch.cuda.Stream(device=dev)  # the probe side's scatter runs here, under the build side's fine pass
+                                      dtype=torch.int64, device=dev) for side in range(S + 1)]
+        self.addr = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(S + 1)]
+        self.seg = [torch.empty((1 << self.seg_bits) + 1, dtype=torch.int64, device=dev) for _ in range(S + 1)]
+        self.info = torch.zeros((S + 1, 3), dtype=torch.int64, device=dev)  # {received, max over ranks, overflow} x side
+        self.flag = torch.zeros(S + 1, dtype=torch.int32, device=dev)
+        self.side = torch.cuda.Stream(device=dev)  # the probe side's scatters run here
         self.ev_r = torch.cuda.Event()
-        self.ev_l = torch.cuda.Event()
+        self.ev_l = [torch.cuda.Event() for _ in range(S)]
         self.overlap = True
-        # CTA budget of the probe side's scatter while the build side's fine pass wants SMs too (0 = all)
-        # measured on 8 B200 at SF=2048 (tools/n8_overlap_sweep.sh): all SMs 20.1 ms, 96 CTAs 19.0 ms, 64 CTAs 22.2 ms
-        # per join step; with 2 ranks the scatter is not link-bound and keeps every SM
+        # CTA budget of the probe side's scatter while the fine passes / probe want SMs too (0 = all).
+        # Measured on 8 B200 at SF=2048 (tools/n8_overlap_sweep.sh, one share): all SMs 20.1 ms, 96 CTAs
+        # 19.0 ms, 64 CTAs 22.2 ms per join step; with 2 ranks the scatter is not link-bound.
         self.probe_scatter_ctas = int(os.environ.get("B2_PROBE_SCATTER_CTAS", "96" if world >= 8 else "0"))
         self.last_recv = (0, 0)
 
     @property
     def abort(self):
         """int64[1] device view: non-zero = a receive buffer would have overflowed (on every rank)."""
-        return self.info[1, 2:3]
+        return self.info[self.shares, 2:3]
 
     def received(self) -> tuple[int, int]:
         """(L rows, R rows) this rank received in the last step — a host read, for reports only."""
         h = self.info.cpu()
-        if int(h[1, 2]):
-            raise OverflowError(f"a rank would receive {int(max(h[0, 1], h[1, 1]))} rows, capacity "
-                                f"{self.capacity} (skewed keys); raised on every rank")
-        self.last_recv = (int(h[0, 0]), int(h[1, 0]))
+        S = self.shares
+        if int(h[S, 2]):
+            raise OverflowError(f"a rank would receive {int(h[:, 1].max())} rows of one side / share, capacities "
+                                f"{self.caps} (skewed keys); raised on every rank")
+        self.last_recv = (int(h[:S, 0].sum()), int(h[S, 0]))
         return self.last_recv
 
+    def _share(self, t, i: int):
+        return t if self.shares == 1 else t[i * self.share_rows: min((i + 1) * self.share_rows, t.numel())]
+
     def step(self, fk, y, pk, x, local_join, phases: dict | None = None):
-        """local_join(l_buf, l_seg_off, r_buf, r_seg_off, nr_expected, seg_bits, skip_bits, abort, l_ready) ->
-        result, e.g. ctx.join_pairs_seg_cap_dev (l_ready: event to wait for before reading the probe side, or None). phases: if given, every phase is synchronised and its wall
-        time (ms) stored there (diagnostics only — the synchronisation removes all overlap)."""
+        """local_join(l_buf, l_seg_off, r_buf, r_seg_off, nr_expected, seg_bits, skip_bits, abort, phase_bits) ->
+        result, e.g. ctx.join_pairs_seg_cap_dev(..., phases=phase_bits): 1 = build, 2 = probe one share,
+        4 = finish. phases: if given, every phase of the step is synchronised and its wall time (ms) stored
+        there (diagnostics only — the synchronisation removes all overlap)."""
         import time
 
         import torch
-        ctx, G = self.ctx, self.world
+        ctx, G, S = self.ctx, self.world, self.shares
         t0 = [time.perf_counter()]
 
         def mark(name):
@@ -273,44 +292,55 @@ class P2PShuffleJoin:
                 phases[name] = phases.get(name, 0.0) + (now - t0[0]) * 1e3
                 t0[0] = now
 
+        def join_phase(i: int, bits: int):
+            return local_join(self.recv[i], self.seg[i], self.recv[S], self.seg[S], self.nr_expected, self.seg_bits,
+                              self.skip, self.abort, bits)
+
         if phases is not None:
             torch.cuda.synchronize()
             t0[0] = time.perf_counter()
-        ctx.shuffle_p2p_count_dev(fk, self.BITS, self.ws[0], self.my_off[0])
-        ctx.shuffle_p2p_count_dev(pk, self.BITS, self.ws[1], self.my_off[1])
+        for i in range(S):
+            ctx.shuffle_p2p_count_dev(self._share(fk, i), self.BITS, self.ws[i], self.my_off[i])
+        ctx.shuffle_p2p_count_dev(pk, self.BITS, self.ws[S], self.my_off[S])
         mark("count")
         # also a barrier: nobody scatters before every rank is done reading its receive buffers
         self.dist.all_gather_into_tensor(self.all_off.view(-1), self.my_off.view(-1))
-        ctx.shuffle_p2p_plan_dev(self.off_ptrs[0], self.peers[0], self.rank, G, self.BITS, self.capacity,
-                                 self.addr[0], self.seg[0], self.info[0])
-        ctx.shuffle_p2p_plan_dev(self.off_ptrs[1], self.peers[1], self.rank, G, self.BITS, self.capacity,
-                                 self.addr[1], self.seg[1], self.info[1], prev_abort=self.info[0, 2:3])
+        for side in range(S + 1):  # the overflow flag chains through the sides: the last one covers all
+            ctx.shuffle_p2p_plan_dev(self.off_ptrs[side], self.peers[side], self.rank, G, self.BITS, self.caps[side],
+                                     self.addr[side], self.seg[side], self.info[side],
+                                     prev_abort=None if side == 0 else self.info[side - 1, 2:3])
         mark("allgather+plan")
         if not self.overlap or phases is not None:
-            ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, self.addr[0], self.ws[0], abort=self.abort)
-            ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[1], self.ws[1], abort=self.abort)
+            ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[S], self.ws[S], abort=self.abort)
+            for i in range(S):
+                ctx.shuffle_p2p_scatter_dev(self._share(fk, i), self._share(y, i), self.BITS, self.addr[i], self.ws[i],
+                                            abort=self.abort)
             mark("scatter_nvlink")
             self.dist.all_reduce(self.flag[0:1])  # every rank's stores have landed when this completes
             mark("barrier")
-            out = local_join(self.recv[0], self.seg[0], self.recv[1], self.seg[1], self.nr_expected, self.seg_bits,
-                             self.skip, self.abort, None)
+            out = None
+            for i in range(S):
+                out = join_phase(i, (1 if i == 0 else 0) | 2 | (4 if i == S - 1 else 0))
             mark("local_join")
             return out
-        # Build side first; once every rank's build rows have landed, this rank's fine partitioning pass
-        # over them runs under the probe side's NVLink scatter (side stream). The join waits for the probe
-        # side (event) only after the build side's pass has been enqueued.
         main = torch.cuda.current_stream()
-        ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[1], self.ws[1], abort=self.abort)
+        ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[S], self.ws[S], abort=self.abort)
         self.ev_r.record(main)
-        self.dist.all_reduce(self.flag[1:2])          # build rows of every rank have landed
-        self.side.wait_event(self.ev_r)               # the link is the build side's until then
+        self.dist.all_reduce(self.flag[S:S + 1])       # build rows of every rank have landed
+        self.side.wait_event(self.ev_r)                # the link is the build side's until then
         with torch.cuda.stream(self.side):
-            if self.probe_scatter_ctas:
-                ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, self.probe_scatter_ctas)
-            ctx.shuffle_p2p_scatter_dev(fk, y, self.BITS, self.addr[0], self.ws[0], abort=self.abort)
-            if self.probe_scatter_ctas:
-                ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, 0)
-            self.dist.all_reduce(self.flag[0:1])      # probe rows of every rank have landed
-            self.ev_l.record(self.side)
-        return local_join(self.recv[0], self.seg[0], self.recv[1], self.seg[1], self.nr_expected, self.seg_bits,
-                          self.skip, self.abort, self.ev_l)
+            for i in range(S):
+                if self.probe_scatter_ctas:
+                    ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, self.probe_scatter_ctas)
+                ctx.shuffle_p2p_scatter_dev(self._share(fk, i), self._share(y, i), self.BITS, self.addr[i], self.ws[i],
+                                            abort=self.abort)
+                if self.probe_scatter_ctas:
+                    ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, 0)
+                self.dist.all_reduce(self.flag[i:i + 1])   # this share's rows of every rank have landed
+                self.ev_l[i].record(self.side)
+        join_phase(0, 1)                               # build side's fine pass, under share 0's transfer
+        out = None
+        for i in range(S):
+            main.wait_event(self.ev_l[i])
+            out = join_phase(i, 2 | (4 if i == S - 1 else 0))
+        return out

@@ -646,16 +646,22 @@ int b2_join_pairs_seg_cap_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int6
                               int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
                               uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
                               const int64_t* d_abort, void* d_ws, size_t ws_bytes, void* stream);
-/* ... and when the probe side may still be arriving: l_ready_event (a cudaEvent_t, may be NULL) is
- * waited for on `stream` AFTER the build side's fine partitioning pass has been enqueued and before
- * anything reads d_l_pairs / d_l_seg_off, so the caller can run the probe side's NVLink scatter (on
- * another stream, recording the event once every peer's stores have landed) under that pass. */
-int b2_join_pairs_seg_cap_ev_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl_cap,
-                                 const uint64_t* d_r_pairs, const int64_t* d_r_seg_off, int64_t nr_cap,
-                                 int64_t nr_expected, int seg_bits, uint32_t* d_out_fk, uint32_t* d_out_y,
-                                 uint32_t* d_out_x, int64_t out_capacity, uint64_t* d_out_rows, int hash_skip_bits,
-                                 const int64_t* d_abort, void* l_ready_event, void* d_ws, size_t ws_bytes,
-                                 void* stream);
+/* ... and in PHASES, for a probe side that is still arriving while the build side is already there:
+ *   phases & 1  build:  reset the join state, fine partitioning pass of the build side (kept in d_ws)
+ *   phases & 2  probe:  fine pass of d_l_pairs + probe; may be called several times, each with another
+ *                       share of the probe side (its own buffer and segment table); output rows append
+ *   phases & 4  finish: publish *d_out_rows
+ * 7 = b2_join_pairs_seg_cap_dev. Same d_ws, build-side arguments, nr_expected and bit counts in every
+ * call; nl_cap may differ per probe call (the workspace must cover the largest). Between the calls the
+ * caller orders its stream after the probe share's arrival (cudaStreamWaitEvent): the probe side's
+ * NVLink scatter then runs under the build side's fine pass, and the second share's scatter under the
+ * first share's probe (dpu_olap_b200/sharded.py::P2PShuffleJoin). */
+int b2_join_pairs_seg_cap_phased_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off,
+                                     int64_t nl_cap, const uint64_t* d_r_pairs, const int64_t* d_r_seg_off,
+                                     int64_t nr_cap, int64_t nr_expected, int seg_bits, uint32_t* d_out_fk,
+                                     uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                                     uint64_t* d_out_rows, int hash_skip_bits, const int64_t* d_abort, int phases,
+                                     void* d_ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def p2p_join_worker(rank: int, world: int, port: int, nb_total: int, batch: int, out_dir: str, dup: bool):
+def p2p_join_worker(rank: int, world: int, port: int, nb_total: int, batch: int, out_dir: str, dup: bool,
+                    shares: int | None = None):
     """One rank of P2PShuffleJoin.step over generator(42) inputs, sharded by batch range. Writes this
     rank's output rows to out_dir/out_{rank}.npy (the parent compares the union with the oracle)."""
     try:
@@ -37,16 +38,16 @@ def p2p_join_worker(rank: int, world: int, port: int, nb_total: int, batch: int,
         n = per * batch
         cap = n + n // 4 + 65536
         mult = 2 if dup else 1
-        pj = P2PShuffleJoin(ctx, dist, rank, world, n, cap)
+        pj = P2PShuffleJoin(ctx, dist, rank, world, n, cap, probe_shares=shares)
         outs = [torch.empty(cap * mult, dtype=torch.int32, device="cuda") for _ in range(3)]
         rows_t = torch.empty(1, dtype=torch.int64, device="cuda")
         jws = torch.empty(ctx.join_seg_cap_ws_bytes(cap, cap, pj.nr_expected, pj.skip, pj.seg_bits) + 256,
                           dtype=torch.uint8, device="cuda")
 
-        def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort, l_ready):
+        def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort, phase_bits):
             ctx.join_pairs_seg_cap_dev(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, out_capacity=cap * mult,
                                        skip_bits=skip_bits, ws=jws, outs=outs, out_rows=rows_t, abort=abort,
-                                       l_ready=l_ready)
+                                       phases=phase_bits)
 
         for _ in range(3):  # repeated steps reuse the receive buffers: the barrier protocol must hold
             outs[0].zero_()

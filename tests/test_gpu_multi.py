@@ -30,14 +30,16 @@ def _ngpus() -> int:
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("world,dup", [(2, False), (2, True), (4, False), (8, False)])
-def test_p2p_shuffle_join_real_ranks(tmp_path, world, dup):
+@pytest.mark.parametrize("world,dup,shares", [(2, False, 1), (2, True, 1), (2, False, 2), (2, True, 3), (4, False, None),
+                                              (8, False, None)])
+def test_p2p_shuffle_join_real_ranks(tmp_path, world, dup, shares):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     nb, batch = 32, 65536
-    mp.spawn(_mp_workers.p2p_join_worker, args=(world, _free_port(), nb, batch, str(tmp_path), dup), nprocs=world,
-             join=True)
+    # shares: the probe side crosses NVLink in that many parts, each joined while the next is in flight
+    mp.spawn(_mp_workers.p2p_join_worker, args=(world, _free_port(), nb, batch, str(tmp_path), dup, shares),
+             nprocs=world, join=True)
     errs = sorted(tmp_path.glob("error_*.txt"))
     assert not errs, errs[0].read_text()
     ins = [np.load(tmp_path / f"in_{r}.npy") for r in range(world)]
