@@ -52,6 +52,14 @@ struct Scratch {
   std::vector<void*> dev;
   std::vector<cudaEvent_t> events;
   ~Scratch() {
+    // An entry point may leave through an error path while kernels and DMAs are still in flight on
+    // the ctx's streams: nothing they use is released (or recycled by the next call) before they
+    // have drained. On the success path the streams are idle already and this costs microseconds.
+    if (owner) {
+      b2_device_scope sc(owner);
+      for (cudaStream_t st : {owner->s_copy_in, owner->s_compute, owner->s_copy_out})
+        if (st) cudaStreamSynchronize(st);
+    }
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     for (void* p : dev) b2_dev_free(owner, p);  // back to the ctx's recycling pool
   }

@@ -905,7 +905,8 @@ extern "C" {
 uint32_t b2_wang_hash_u32(uint32_t key) { return wang_hash_u32(key); }
 
 int b2_join_dest_rank(uint32_t key, int nranks) {
-  if (nranks <= 1) return 0;
+  if (nranks < 1 || (nranks & (nranks - 1)) != 0) return -1;  // the hash routes over a power of two
+  if (nranks == 1) return 0;
   int bits = 0;
   while ((1 << bits) < nranks) ++bits;
   return (int)(wang_hash_u32(key) >> (32 - bits));

@@ -566,7 +566,7 @@ int b2_join_table_fetch_host(b2_ctx* ctx, void* const* out_cols, int ncols, int6
 /* ---- multi-GPU join exchange (the step that replaces the reference's host-mediated
  *      DPU->host->DPU repartition, partitioner.cc:350-375 + join_dpu.cc:269,293) -------------- */
 /* Destination rank of a key when the join is sharded over nranks (power of two) GPUs:
- * top log2(nranks) bits of wang_hash(key). */
+ * top log2(nranks) bits of wang_hash(key); -1 when nranks is not a power of two. */
 int b2_join_dest_rank(uint32_t key, int nranks);
 /* Route n (key, val) rows by destination rank: d_pairs_out receives the rows as 8-byte pairs
  * grouped by destination, d_dest_off (int64, nranks+1) the group boundaries — the send counts of
