@@ -1143,7 +1143,10 @@ def bench_e2e_ops(ctx, D, args) -> dict:
     if int(nrows.value) != n or triple_checksum_torch(*[t.cuda() for t in o]) != exp:
         raise SystemExit("e2e join self-check failed")
     res["join"] = {"value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms,
-                   "api": "b2_join_u32_host + b2_join_fetch_host (JoinGpu::Run)", **leg(t1, t2)}
+                   "api": "b2_join_u32_host + b2_join_fetch_host (JoinGpu::Run)", **leg(t1, t2),
+                   "phases_note": "the build side's radix passes run under the probe side's upload (two "
+                                  "streams), so dpu-work includes waiting for that upload and the phases "
+                                  "do not add up to ms_per_step"}
     # the same join over DEVICE-RESIDENT columns (b2_col, what an Arrow consumer hands over as
     # ArrowDeviceArrays): the inputs are already in HBM, only the result columns cross PCIe
     from dpu_olap_b200.ops import DeviceColumn

@@ -28,6 +28,11 @@ struct DevBufs {  // returns everything not released to the ctx's recycling pool
   b2_ctx* owner = nullptr;
   std::vector<void*> bufs;
   ~DevBufs() {
+    if (owner) {  // error paths leave with work in flight: nothing it uses is recycled before it has drained
+      b2_device_scope sc(owner);
+      for (cudaStream_t st : {owner->s_copy_in, owner->s_compute, owner->s_copy_out})
+        if (st) cudaStreamSynchronize(st);
+    }
     for (void* p : bufs)
       if (p) b2_dev_free(owner, p);
   }
@@ -226,12 +231,20 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
   B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_y, (size_t)nl * 4));
   B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_pk, (size_t)nr * 4));
   B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_x, (size_t)nr * 4));
-  B2_CUDA_OK(ctx, cudaEventRecord(up.a, s));
-  B2_RETURN_NOT_OK(upload_column(ctx, d_fk, l_ptrs, l_lens, nl_batches, s, &tm.h2d_bytes));
-  B2_RETURN_NOT_OK(upload_column(ctx, d_y, l_ptrs + nl_batches, l_lens, nl_batches, s, &tm.h2d_bytes));
-  B2_RETURN_NOT_OK(upload_column(ctx, d_pk, r_ptrs, r_lens, nr_batches, s, &tm.h2d_bytes));
-  B2_RETURN_NOT_OK(upload_column(ctx, d_x, r_ptrs + nr_batches, r_lens, nr_batches, s, &tm.h2d_bytes));
-  B2_CUDA_OK(ctx, cudaEventRecord(up.b, s));
+  // The build side goes up first, on the copy stream; its radix passes run on the compute stream
+  // while the probe side is still crossing PCIe (the reference moves each column four times and
+  // strictly one after the other, join_dpu.cc:168-400).
+  cudaStream_t sc = ctx->s_copy_in;
+  EventPair landed;  // a: build side on the device, b: probe side on the device
+  B2_RETURN_NOT_OK(landed.init(ctx));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.a, sc));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_pk, r_ptrs, r_lens, nr_batches, sc, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_x, r_ptrs + nr_batches, r_lens, nr_batches, sc, &tm.h2d_bytes));
+  B2_CUDA_OK(ctx, cudaEventRecord(landed.a, sc));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_fk, l_ptrs, l_lens, nl_batches, sc, &tm.h2d_bytes));
+  B2_RETURN_NOT_OK(upload_column(ctx, d_y, l_ptrs + nl_batches, l_lens, nl_batches, sc, &tm.h2d_bytes));
+  B2_CUDA_OK(ctx, cudaEventRecord(landed.b, sc));
+  B2_CUDA_OK(ctx, cudaEventRecord(up.b, sc));
 
   // PK-FK joins produce at most nl rows; duplicate build keys can produce more, in which case the
   // join is re-run with the exact capacity it reported.
@@ -243,13 +256,22 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
   B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&d_rows, 8));
   uint32_t *o_fk = nullptr, *o_y = nullptr, *o_x = nullptr;
   uint64_t rows = 0;
+  B2_CUDA_OK(ctx, cudaStreamWaitEvent(s, landed.a, 0));
   B2_CUDA_OK(ctx, cudaEventRecord(work.a, s));
   for (int attempt = 0; attempt < 2; ++attempt) {
     B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_fk, (size_t)cap * 4));
     B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_y, (size_t)cap * 4));
     B2_RETURN_NOT_OK(bufs.alloc(ctx, (void**)&o_x, (size_t)cap * 4));
-    B2_RETURN_NOT_OK(b2_join_u32_dev(ctx, d_fk, d_y, nl, d_pk, d_x, nr, o_fk, o_y, o_x, cap, d_rows,
-                                     0, d_ws, ws_bytes, s));
+    if (attempt == 0) {
+      B2_RETURN_NOT_OK(b2_join_u32_phased_dev(ctx, d_fk, d_y, nl, d_pk, d_x, nr, o_fk, o_y, o_x, cap, d_rows, 0, 1,
+                                              d_ws, ws_bytes, s));
+      B2_CUDA_OK(ctx, cudaStreamWaitEvent(s, landed.b, 0));
+      B2_RETURN_NOT_OK(b2_join_u32_phased_dev(ctx, d_fk, d_y, nl, d_pk, d_x, nr, o_fk, o_y, o_x, cap, d_rows, 0, 2,
+                                              d_ws, ws_bytes, s));
+    } else {
+      B2_RETURN_NOT_OK(b2_join_u32_dev(ctx, d_fk, d_y, nl, d_pk, d_x, nr, o_fk, o_y, o_x, cap, d_rows,
+                                       0, d_ws, ws_bytes, s));
+    }
     B2_CUDA_OK(ctx, cudaMemcpyAsync(&rows, d_rows, 8, cudaMemcpyDeviceToHost, s));
     B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
     if (rows == ~0ull) return b2_set_error(ctx, B2_ERR_WORKSPACE, "join", "slice overflow");

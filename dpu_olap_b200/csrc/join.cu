@@ -618,7 +618,11 @@ constexpr int kMaxSliceBits = 6;
 int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& rin, int64_t nr,
               uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
               uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s,
-              const JoinAggCfg* agg = nullptr) {
+              const JoinAggCfg* agg = nullptr, int phases = 3) {
+  // phases: 1 = reset + the build side's radix passes (only rin has to be there), 2 = the probe side's
+  // passes, the probe and the result; 3 = both. A sliced join (workspace-bound) does all its work in
+  // phase 2, slice by slice.
+  B2_REQUIRE(ctx, phases >= 1 && phases <= 3, "phases: 1 build | 2 probe");
   B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
   B2_REQUIRE(ctx, skip_bits >= 0 && skip_bits <= 8, "hash_skip_bits must be in 0..8");
   B2_REQUIRE(ctx, agg ? agg->d_out != nullptr : d_out_rows != nullptr, "result pointer is null");
@@ -659,8 +663,10 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
   uint2* tmp = P.two_pass ? reinterpret_cast<uint2*>(ext_tmp ? (char*)d_out_fk : base + P.off_tmp) : nullptr;
   void* pws = base + P.off_part;
 
-  join_init_kernel<<<1, 1, 0, s>>>(st);
-  B2_LAUNCH_CHECK(ctx, "join_init_kernel");
+  if (phases & 1) {
+    join_init_kernel<<<1, 1, 0, s>>>(st);
+    B2_LAUNCH_CHECK(ctx, "join_init_kernel");
+  }
   if (nl > 0 && nr > 0) {
     static const int seen = b2_new_site();
     if (b2_first_use_on_device(ctx, seen)) {
@@ -672,8 +678,10 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
     const int64_t nparts = (int64_t)1 << P.bits;
     const int part_shl = skip_bits + P.slice_bits;
     for (uint32_t slice = 0; slice < (1u << P.slice_bits); ++slice) {
-      B2_RETURN_NOT_OK(part_full(ctx, rin, nr, P.bits, part_shl, skip_bits, P.slice_bits, slice,
-                                 rout, tmp, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
+      if (P.slice_bits == 0 ? (phases & 1) : (phases & 2))
+        B2_RETURN_NOT_OK(part_full(ctx, rin, nr, P.bits, part_shl, skip_bits, P.slice_bits, slice,
+                                   rout, tmp, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
+      if (!(phases & 2)) break;
       // filter pushdown: the probe side's first radix pass drops the rows that fail L.y < y_thr
       B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
                                  lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s,
@@ -688,6 +696,7 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
       B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
     }
   }
+  if (!(phases & 2)) return B2_OK;
   if (agg) {
     join_aggr_finish_kernel<<<1, 1, 0, s>>>(st, agg->d_out);
   } else {
@@ -942,6 +951,24 @@ int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int6
   rin.vals = d_x;
   return join_impl(ctx, lin, nl, rin, nr, d_out_fk, d_out_y, d_out_x, out_capacity, d_out_rows,
                    hash_skip_bits, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b2_join_u32_phased_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
+                           const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, uint32_t* d_out_fk,
+                           uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                           uint64_t* d_out_rows, int hash_skip_bits, int phases, void* d_ws, size_t ws_bytes,
+                           void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, nl == 0 || (d_fk && d_y), "null left column");
+  B2_REQUIRE(ctx, nr == 0 || (d_pk && d_x), "null right column");
+  PartInput lin, rin;
+  lin.keys = d_fk;
+  lin.vals = d_y;
+  rin.keys = d_pk;
+  rin.vals = d_x;
+  return join_impl(ctx, lin, nl, rin, nr, d_out_fk, d_out_y, d_out_x, out_capacity, d_out_rows,
+                   hash_skip_bits, d_ws, ws_bytes, static_cast<cudaStream_t>(stream), nullptr, phases);
 }
 
 int b2_join_aggr_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,

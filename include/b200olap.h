@@ -482,6 +482,16 @@ int b2_partition_fetch_host(b2_ctx* ctx, uint32_t* const* out_ptrs, int nparts, 
 size_t b2_join_ws_bytes(int64_t nl, int64_t nr);
 size_t b2_join_ws_bytes_adjacent_outputs(int64_t nl, int64_t nr);
 size_t b2_join_min_ws_bytes(int64_t nl, int64_t nr);
+/* b2_join_u32_phased_dev: the same join in two calls, so a caller can start on the build side while
+ * the probe side is still being uploaded (b2_join_u32_host does: the probe side's H2D copy runs under
+ * the build side's radix passes). phases & 1: reset + build side's passes (reads d_pk / d_x only);
+ * phases & 2: probe side's passes, probe, *d_out_rows. Same arguments and workspace in both calls;
+ * 3 = b2_join_u32_dev. */
+int b2_join_u32_phased_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
+                           const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, uint32_t* d_out_fk,
+                           uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
+                           uint64_t* d_out_rows, int hash_skip_bits, int phases, void* d_ws, size_t ws_bytes,
+                           void* stream);
 int b2_join_u32_dev(b2_ctx* ctx, const uint32_t* d_fk, const uint32_t* d_y, int64_t nl,
                     const uint32_t* d_pk, const uint32_t* d_x, int64_t nr, uint32_t* d_out_fk,
                     uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
