@@ -28,7 +28,7 @@ struct b2_ctx {
   size_t small_bytes = 0;
   uint32_t sum_slot = 0;  // next slot of that ring
   // kernel-selection knobs (b2_ctx_set_tunable, enum b2_tunable): every setting computes the same result
-  int tune[7] = {8, 1, 0, 6, 3, 2048, 0};
+  int tune[8] = {8, 1, 0, 6, 3, 2048, 0, 0};
   std::vector<char> site_done;  // per call site: function attributes configured for this ctx's device
   std::vector<int> site_value;
   // growable device workspace used by the *_host layer

@@ -1170,34 +1170,50 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-template <bool kAoS, bool kPre, int kBkT>
+// kPeer: the fused multi-GPU shuffle. Bucket p of THIS rank starts at bucket_addr[p], a byte address inside
+// another GPU's receive buffer (the bulk copies then cross NVLink), this unit's run where the units before
+// it in the segment end; sectors are counted from the address itself; the receive capacity was checked
+// by the plan kernel (abort_flag); a grid smaller than the number of work units walks them (CTA budget).
+template <bool kAoS, bool kPre, int kBkT, bool kPeer = false>
 __global__ void __launch_bounds__(kBkT, (kBkT >= 1024 ? 1 : 2))
 part_scatter_bulk_kernel(PartInput in, const int64_t* __restrict__ seg_off,
                          const int64_t* __restrict__ unit_first, int64_t nseg, int64_t unit_rows,
                          PartGeom g, const uint64_t* __restrict__ scanned, uint2* __restrict__ out,
-                         int64_t out_cap, unsigned int* __restrict__ overflow) {
+                         int64_t out_cap, unsigned int* __restrict__ overflow,
+                         const uint64_t* __restrict__ bucket_addr = nullptr,
+                         const int64_t* __restrict__ abort_flag = nullptr) {
   extern __shared__ __align__(16) unsigned char smem[];  // the window itself starts 1024-byte aligned
   using BkSmem = BkSmemT<kBkT>;
   constexpr int kBkI = 16, kBkTile = BkSmem::kTile;
   BkSmem& sm = *reinterpret_cast<BkSmem*>(smem);
+  if (kPeer && abort_flag && *abort_flag) return;  // the exchange was called off on the device: store nothing
   const int P = 1 << g.bits;
   const SliceSel sel = slice_sel(g);
-  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P);
-  if (!u.valid) return;
   constexpr int kW = kBkT / 32;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool mine = (int)tid < P;  // this thread's bucket in the per-bucket steps
-  const uint64_t cap_rows = (uint64_t)out_cap;
+  const uint64_t cap_rows = kPeer ? ~0ull : (uint64_t)out_cap;
   const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(sm.stage);
+  for (int64_t unit_id = blockIdx.x;; unit_id += gridDim.x) {
+  const Unit u = find_unit(seg_off, unit_first, nseg, unit_rows, P, unit_id);
+  if (!u.valid) return;
 
   // per-bucket state, in registers of the bucket's thread
-  uint32_t dsec_next = 0;  // next unwritten sector of the (unit, bucket) run, counted from `out`
+  uint32_t dsec_next = 0;  // next unwritten sector of the (unit, bucket) run, counted from `out` (kPeer: from obase)
+  unsigned char* obase = reinterpret_cast<unsigned char*>(out);  // kPeer: the bucket's run start, sector-aligned down
   uint32_t gh = 0;         // leading slots of the run's first sector that belong to the neighbouring run
   uint32_t c0 = 0;         // rows held back (ghost slots included)
   if (mine) {
     const uint64_t pos = scanned[u.hbase + (int64_t)tid * u.ustride];  // first output row of (unit, bucket)
-    gh = (uint32_t)(pos & (kScRows - 1));
-    dsec_next = (uint32_t)(pos >> 2);
+    if (kPeer) {
+      const uint64_t a0 = bucket_addr[tid] + 8ull * (pos - scanned[u.hbase0 + (int64_t)tid * u.ustride]);
+      gh = (uint32_t)((a0 >> 3) & (kScRows - 1));
+      obase = reinterpret_cast<unsigned char*>(a0 - 8ull * gh);
+      dsec_next = 0;
+    } else {
+      gh = (uint32_t)(pos & (kScRows - 1));
+      dsec_next = (uint32_t)(pos >> 2);
+    }
     c0 = gh;
     sm.cnt[0][tid] = gh;
   }
@@ -1319,14 +1335,14 @@ part_scatter_bulk_kernel(PartInput in, const int64_t* __restrict__ seg_off,
           uint32_t first = 0;
           if (gh) {  // the run's first sector is shared with the neighbouring run: plain stores
             for (uint32_t e = gh; e < kScRows; ++e)
-              st_stream_v2(out + ((uint64_t)dsec_next * kScRows + e), sm.stage[q0 + e]);
+              st_stream_v2(reinterpret_cast<uint2*>(obase) + ((uint64_t)dsec_next * kScRows + e), sm.stage[q0 + e]);
             first = 1;
           }
 #ifdef B2_LAB
           if (g.lab & 2) first = nsec;  // experiment: what the pass costs without its DRAM writes
 #endif
           if (nsec > first) {
-            bulk_store(reinterpret_cast<unsigned char*>(out) + ((uint64_t)dsec_next + first) * 32u,
+            bulk_store(obase + ((uint64_t)dsec_next + first) * 32u,
                        stage_base + (q0 + first * kScRows) * 8u, (nsec - first) * 32u);
             bulk_commit();
           }
@@ -1346,10 +1362,13 @@ part_scatter_bulk_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     if (row + c0 > cap_rows) {
       if (overflow) *overflow = 1u;
     } else {
-      for (uint32_t e = gh; e < c0; ++e) st_stream_v2(out + row + e, sm.carry[e][tid]);
+      for (uint32_t e = gh; e < c0; ++e) st_stream_v2(reinterpret_cast<uint2*>(obase) + row + e, sm.carry[e][tid]);
     }
   }
   bulk_wait_read();  // shared memory must outlive the copy engine's reads
+  if (!kPeer) return;  // one work unit per CTA
+  __syncthreads();     // the next unit re-initialises the counters and the stage
+  }  // units of this CTA
 }
 
 // Boundaries are clamped to `clamp` (the capacity of the pass's output): when a skewed hash-space
@@ -1500,13 +1519,20 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
         return B2_OK;
       };
       if (shape == 3) {  // quad-aligned regions flushed by the copy engine: one bulk copy per (bucket, tile)
+        auto go_bulk = [&](auto kernel, int site, int threads, size_t smem_bytes) -> int {
+          if (b2_first_use_on_device(ctx, site))
+            B2_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+          kernel<<<(unsigned)L.max_units, threads, smem_bytes, s>>>(in, d_seg_off, unit_first, nseg, L.unit_rows, g,
+                                                                   scanned, d_out, out_cap, d_overflow, nullptr, nullptr);
+          return B2_OK;
+        };
         const bool small = g.bits <= 9 && ctx->tune[B2_TUNE_SCATTER_SHAPE] != 8;  // two 512-thread CTAs per SM
         if (small) {
-          if (pre) B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, true, 512>, sites[8], 512, sizeof(BkSmemT<512>)));
-          else B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, false, 512>, sites[9], 512, sizeof(BkSmemT<512>)));
+          if (pre) B2_RETURN_NOT_OK(go_bulk(part_scatter_bulk_kernel<kAoS, true, 512>, sites[8], 512, sizeof(BkSmemT<512>)));
+          else B2_RETURN_NOT_OK(go_bulk(part_scatter_bulk_kernel<kAoS, false, 512>, sites[9], 512, sizeof(BkSmemT<512>)));
         } else {
-          if (pre) B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, true, 1024>, sites[6], 1024, sizeof(BkSmemT<1024>)));
-          else B2_RETURN_NOT_OK(go(part_scatter_bulk_kernel<kAoS, false, 1024>, sites[7], 1024, sizeof(BkSmemT<1024>)));
+          if (pre) B2_RETURN_NOT_OK(go_bulk(part_scatter_bulk_kernel<kAoS, true, 1024>, sites[6], 1024, sizeof(BkSmemT<1024>)));
+          else B2_RETURN_NOT_OK(go_bulk(part_scatter_bulk_kernel<kAoS, false, 1024>, sites[7], 1024, sizeof(BkSmemT<1024>)));
         }
       } else if (shape == 2) {  // quad-aligned regions: the carried rows live in the stage, the flush is three reads and a store
         if (pre) B2_RETURN_NOT_OK(go(part_scatter_quads_kernel<kAoS, true>, sites[4], kQdT, sizeof(QdSmem)));
@@ -1519,6 +1545,20 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
         else B2_RETURN_NOT_OK(go(part_scatter_sectors_kernel<kAoS, false, 512, 16>, sites[3], 512, sizeof(ScSmemT<512, 16>)));
       }
       B2_LAUNCH_CHECK(ctx, "part_scatter_sectors_kernel");
+      return B2_OK;
+    }
+    if (d_bucket_addr && ctx->tune[B2_TUNE_PEER_SCATTER_KERNEL] == 1) {
+      // peer destinations through the copy engine: whole 32-byte sectors, one bulk copy per (bucket, tile)
+      static const int site_a = b2_new_site(), site_s = b2_new_site();
+      const int budget = ctx->tune[B2_TUNE_PEER_SCATTER_CTAS];
+      const int64_t grid = budget > 0 ? std::min<int64_t>(L.max_units, budget) : L.max_units;
+      auto kernel = part_scatter_bulk_kernel<kAoS, true, 1024, true>;
+      if (b2_first_use_on_device(ctx, kAoS ? site_a : site_s))
+        B2_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(BkSmemT<1024>)));
+      kernel<<<(unsigned)grid, 1024, sizeof(BkSmemT<1024>), s>>>(in, d_seg_off, unit_first, nseg, L.unit_rows, g, scanned,
+                                                                nullptr, 0, nullptr, d_bucket_addr, d_abort);
+      B2_LAUNCH_CHECK(ctx, "part_scatter_bulk_kernel (peer)");
       return B2_OK;
     }
     if (d_bucket_addr) {  // peer destinations: whole 128-byte lines only (line carry)

@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 from typing import Any, Callable
 
 
-TUNE_PEER_SCATTER_CTAS = 6  # enum b2_tunable (include/b200olap.h)
+TUNE_PEER_SCATTER_CTAS, TUNE_PEER_SCATTER_KERNEL = 6, 7  # enum b2_tunable (include/b200olap.h)
 
 
 def shard_range(nbatches: int, rank: int, world: int) -> tuple[int, int]:
@@ -254,6 +254,8 @@ class P2PShuffleJoin:
         # Measured on 8 B200 at SF=2048 (tools/n8_overlap_sweep.sh, one share): all SMs 20.1 ms, 96 CTAs
         # 19.0 ms, 64 CTAs 22.2 ms per join step; with 2 ranks the scatter is not link-bound.
         self.probe_scatter_ctas = int(os.environ.get("B2_PROBE_SCATTER_CTAS", "96" if world >= 8 else "0"))
+        if os.environ.get("B2_PEER_SCATTER_KERNEL"):  # 0 = whole lines stored by the threads, 1 = bulk sectors
+            ctx.set_tunable(TUNE_PEER_SCATTER_KERNEL, int(os.environ["B2_PEER_SCATTER_KERNEL"]))
         self.last_recv = (0, 0)
 
     @property

@@ -97,6 +97,8 @@ enum b2_tunable {
   B2_TUNE_PEER_SCATTER_CTAS = 6,        /* CTA budget of the peer (NVLink) scatter kernel: 0 = one CTA per work unit (all SMs);
                                            n > 0 = at most n CTAs walk the units and leave the other SMs to kernels of
                                            other streams (the overlapped sharded join sets it around the probe side's scatter) */
+  B2_TUNE_PEER_SCATTER_KERNEL = 7,      /* peer (NVLink) scatter: 0 = whole 128-byte lines stored by the threads (line carry),
+                                           1 = whole 32-byte sectors, one copy-engine bulk copy per (bucket, tile) */
   B2_TUNE_JOIN_DIRECT_MIN_ROWS = 5      /* perfect-hash probe path (join.cu): used when <= 14 hash bits are left below the partition
                                            bits; the planner adds partition bits to get there while partitions keep at least this
                                            many build rows (2048), and takes fewer when 2^14-row partitions are enough. 0 = path off, 1 = always when the bits allow (tests). */

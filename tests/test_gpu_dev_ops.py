@@ -465,12 +465,25 @@ def test_join_skip_bits_matches_shuffle_routing(ctx):
 
 
 # ---- fused multi-GPU shuffle, emulated with virtual ranks on one GPU -------------------------------
+@pytest.fixture(params=[0, 1, 2], ids=["lines", "bulk", "bulk-budget"])
+def peer_kernel(ctx, request):
+    """Both peer scatter kernels (whole 128-byte lines stored by the threads / whole sectors through the
+    copy engine), the second also with a CTA budget (3 persistent CTAs walk all work units)."""
+    from dpu_olap_b200._lib import TUNE_PEER_SCATTER_CTAS, TUNE_PEER_SCATTER_KERNEL
+    ctx.set_tunable(TUNE_PEER_SCATTER_KERNEL, 1 if request.param else 0)
+    ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, 3 if request.param == 2 else 0)
+    yield ctx
+    ctx.set_tunable(TUNE_PEER_SCATTER_KERNEL, 0)
+    ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, 0)
+
+
 @pytest.mark.parametrize("G,rows_per_rank", [(2, 70_000), (4, 300_000), (8, 40_000), (1, 50_000)])
-def test_p2p_shuffle_and_segmented_join_virtual_ranks(ctx, G, rows_per_rank):
+def test_p2p_shuffle_and_segmented_join_virtual_ranks(peer_kernel, G, rows_per_rank):
     """Every virtual rank counts, scatters straight into the (local stand-ins for the) peers'
     receive buffers, and joins what it received with the segmented join; the union of the G
     results must equal the oracle join of the whole input, and every received row must belong to
     its rank and sit in its coarse bucket."""
+    ctx = peer_kernel
     from dpu_olap_b200.sharded import log2_exact, p2p_plan
     BITS = 10
     skip = log2_exact(G)
