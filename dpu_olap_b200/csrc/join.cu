@@ -14,22 +14,27 @@
 //
 // B200 design:
 //   1. both sides are radix-partitioned on the same hash bits (partition.cu) into partitions of
-//      ~4096 build rows, carrying (key, payload) pairs — the payload travels with the key, so
-//      there is no row-index vector and no take pass;
-//   2. join_probe_kernel: one CTA per partition builds a table of the build side in SHARED memory
-//      (2048 buckets x 4 slots, 72 KB with the values and one arrival counter per bucket, mean
-//      2 rows per bucket). An insert is one shared-memory atomicAdd on the counter — it returns the
-//      slot — plus two stores; a row goes to the emptier of its TWO candidate buckets, so chains
-//      are rare. The probe side then streams through: both candidate buckets are read with 128-bit
-//      loads, straight-line, and (fk, y, x) is written with coalesced stores; the output range of
-//      every 4608-row probe round is reserved with one 64-bit atomicAdd. No empty-key marker: all
-//      2^32 key values are legal, and only the 8 KB of counters are cleared per partition.
-//      Build partitions larger than the table (skew, heavy duplicates) are processed in chunks,
-//      each chunk probed by the whole probe partition.
+//      ~4096 build rows (up to 16384 on the perfect-hash path), carrying (key, payload) pairs — the
+//      payload travels with the key, so there is no row-index vector and no take pass;
+//   2. join_probe_kernel: one CTA per partition, table in SHARED memory, (fk, y, x) written with
+//      coalesced stores, the output range of every 4608-row probe round reserved with one 64-bit
+//      atomicAdd; the next partition's rows (and the next round's) are requested into L2 ahead of time.
+//      Perfect-hash path (large joins: <= 14 hash bits left below the partition bits): the partition
+//      hash is a bijection, so the remaining hash bits identify a key inside its partition — the
+//      table is one value and one occupancy bit per entry, no keys, no collisions; an insert is a
+//      store and an atom.or, a probe two loads and a bit test (see kDirectMaxBits below).
+//      Bucketised path (small joins, and partitions with duplicate build keys): 2048 buckets x 4 slots,
+//      72 KB with the values and one arrival counter per bucket (mean 2 rows per bucket). An insert is
+//      one shared-memory atomicAdd on the counter — it returns the slot — plus two stores; a row goes
+//      to the emptier of its TWO candidate buckets, so chains are rare; a probe reads both candidates
+//      with 128-bit loads, straight-line. No empty-key marker: all 2^32 key values are legal, and only
+//      the 8 KB of counters are cleared per partition. Build partitions larger than the table (skew,
+//      heavy duplicates) are processed in chunks, each chunk probed by the whole probe partition.
 //      kAgg variant: the fused [filter ->] join -> aggregate pipeline adds every output row's y and
 //      x to per-thread sums instead of storing it (b2_join_aggr_u32_dev).
-//   3. when the workspace is too small to hold both partitioned sides at once (SF=2048 on one
-//      GPU), the join runs in hash-space slices: slice s only partitions and joins the rows whose
+//   3. when the workspace is too small to hold both partitioned sides at once, the join runs in
+//      hash-space slices (SF=2048 on one GPU fits in one: the output columns serve as the first
+//      pass's temporary): slice s only partitions and joins the rows whose
 //      top hash bits equal s.
 #include <algorithm>
 

@@ -16,17 +16,25 @@
 //   2. exclusive scan       the histogram is laid out (segment, bucket, unit)-major, so one flat
 //                           scan (scan.cu, decoupled look-back) yields the global destination of
 //                           every (bucket, unit) run — no per-partition mutex, no host round trip.
-//   3. part_scatter_kernel  per tile: rank rows inside their bucket (atomicAdd on the tile's
-//                           shared-memory counters returns the rank), scan the 2^bits tile
-//                           counts, stage the tile SORTED BY BUCKET in shared memory, then stream
-//                           it out so that consecutive threads write consecutive addresses of a
-//                           bucket's run. The next tile's rows are requested as soon as the
-//                           current tile is staged, so the loads fly during the stream-out.
-//      part_scatter_sectors_kernel  the same pass from a fan-out of 2^9: rows that do not complete
-//                           a 32-byte sector are held back per bucket and only whole, aligned
-//                           sectors are stored (B200's L2 fills a partially written sector from
-//                           DRAM on a write miss: profiles/r1_scatter_fanout.md).
-//      part_scatter_lines_kernel    the multi-GPU shuffle: whole 128-byte lines to peer memory.
+//   3. scatter              per tile: rank rows inside their bucket (atomicAdd on the tile's
+//                           shared-memory counters returns the rank), scan the 2^bits tile counts,
+//                           stage the tile SORTED BY BUCKET in shared memory, then write every
+//                           bucket's run out. The tile after the current one is requested into L2 by
+//                           the copy engine (cp.async.bulk.prefetch.L2) at the top of the tile, so the
+//                           register loads issued once the tile is staged hit L2 and the DRAM reads
+//                           run under the rank / scan / stage steps.
+//      part_scatter_bulk_kernel     fan-outs from 2^8 (the join's passes): rows that do not complete a
+//                           32-byte sector are held back per bucket (B200's L2 fills a partially
+//                           written sector from DRAM on a write miss) and a bucket's whole sectors
+//                           leave as ONE shared -> global bulk copy per tile (UBLKCP): the stores are
+//                           the copy engine's, asynchronous to the SM. 512 threads x 2 CTAs/SM up to
+//                           2^9 buckets, 1024 threads x 1 CTA/SM at 2^10; peer mode for the shuffle.
+//      part_scatter_kernel          small fan-outs: consecutive threads write consecutive rows of a run.
+//      part_scatter_lines_kernel    the multi-GPU shuffle: whole 128-byte lines to peer memory over
+//                           NVLink, optionally with a CTA budget (persistent walk over the work units).
+//      part_scatter_sectors_kernel, part_scatter_quads_kernel: earlier whole-sector kernels with the
+//                           flush done by the threads; selectable (B2_TUNE_SCATTER_SECTOR_TILE) and
+//                           parity-tested, slower than the bulk kernel (profiles/r2_scatter_bulk.md).
 // A pass can be "segmented": each input segment (= a partition of the previous pass) is
 // partitioned independently, which is how the join refines 2^10 coarse partitions into up to
 // 2^20 shared-memory-sized ones while every pass keeps >= 64 B write runs.
