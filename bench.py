@@ -1364,6 +1364,12 @@ def main():
             "design is modelled at 116 B per row pair (DESIGN.md section 3); time = whole join step "
             "(all radix passes + probe" + (", + NVLink shuffle" if D.world > 1 else "") + ")",
             "part_scatter_*_kernel x4 + part_hist_kernel x4 + join_probe_kernel")
+        jt = ncu_traffic("join")
+        if jt and jt.get("kernels") and D.world == 1:
+            # per-kernel times and DRAM rates of the same command under ncu (cold-cache, serialised launches:
+            # the SHARE of the step is what carries over, profiles/r2_launches_bench_sf2048.csv)
+            r["roofline"]["kernels_ncu"] = jt["kernels"]
+            r["roofline"]["kernels_ncu_source"] = jt.get("source")
         n1 = ncu_traffic("join_n1_ms")
         if n1 and D.world > 1 and n1.get(str(args.sf)):
             r["speedup_vs_n1"] = n1[str(args.sf)] / r["ms_per_step"]

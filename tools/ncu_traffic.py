@@ -57,6 +57,27 @@ def summarise(path: Path, pattern: str, rows: float, steps: int) -> dict:
             "source": str(path.relative_to(ROOT)) if path.is_absolute() else str(path)}
 
 
+def per_kernel(path: Path, pattern: str, steps: int) -> dict:
+    """name -> launches per step, mean ms per launch, DRAM GB per launch, TB/s of DRAM traffic (kernels of
+    at least 0.05 ms), for the operator's per-kernel table in the bench line."""
+    agg: dict = {}
+    for l in read_launches(path):
+        if not re.search(pattern, l["kernel"]):
+            continue
+        name = re.sub(r"\(.*", "", l["kernel"]).replace("<unnamed>::", "").replace("void ", "").strip()
+        a = agg.setdefault(name, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += l.get("gpu__time_duration.sum", 0.0)
+        a[2] += l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0)
+    out = {}
+    for name, (n, ns, by) in agg.items():
+        if ns / n < 5e4:
+            continue
+        out[name] = {"launches_per_step": n / steps, "ms_per_launch": round(ns / n / 1e6, 3),
+                     "dram_gb_per_launch": round(by / n / 1e9, 2), "dram_tbs": round(by / ns / 1e3, 2)}
+    return out
+
+
 def main():
     p = argparse.ArgumentParser()
     for op in KERNELS:
@@ -80,6 +101,8 @@ def main():
             sel = float(eval(a.filter_selected, {}))  # noqa: S307
             alg = 4 * rows + 4 * sel
             s["dram_bytes_per_algorithmic_byte"] = (s["dram_read_bytes"] + s["dram_write_bytes"]) / (alg * s["steps"])
+        if op == "join":
+            s["kernels"] = per_kernel(Path(f), pat, getattr(a, f"{op}_steps"))
         out[op] = s
     if a.join_n1_ms:
         out["join_n1_ms"] = {k: float(v) for k, v in (kv.split(":") for kv in a.join_n1_ms.split(","))}
