@@ -39,6 +39,16 @@ class Timings(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class JoinPhases(C.Structure):
+    """b2_join_phases (include/b200olap.h): the join's phase timers, milliseconds."""
+    _fields_ = [("partition_build_ms", C.c_double), ("partition_probe_ms", C.c_double),
+                ("probe_ms", C.c_double), ("take_ms", C.c_double),
+                ("intervals", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 _vp, _i64, _u64, _u32, _int, _sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
 _pp = C.POINTER(C.c_void_p)          # array of pointers
 _pi64 = C.POINTER(C.c_int64)
@@ -122,6 +132,11 @@ SIGNATURES = {
     "b2_filter_lt_u32_nullable_dev": (_int, [_vp, _vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2_filter_lt_32_host_into": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _int, _u32, _vp, _i64, _pi64, _pu64, _pt]),
     "b2_filter_lt_32_ragged_dev": (_int, [_vp, _vp, _int, _u32, _vp, _pi64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b2_join_trace": (_int, [_vp, _int]),
+    "b2_join_last_phases": (_int, [_vp, C.POINTER(JoinPhases)]),
+    "b2_filter_64_ws_bytes": (_sz, [_i64]),
+    "b2_filter_lt_64_dev": (_int, [_vp, _vp, _int, _u64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b2_filter_lt_64_host_into": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _int, _u64, _vp, _i64, _pi64, _pu64, _pt]),
     "b2_filter_lt_32_dev": (_int, [_vp, _vp, _int, _u32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2_aggr_32_dev": (_int, [_vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "b2_aggr_32_host": (_int, [_vp, _pp, _pp, _pi64, _pi64, _i64, _int, _vp, _pt]),

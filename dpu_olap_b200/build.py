@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libb200olap.so"
 
 SOURCES = ["ctx.cu", "sum.cu", "filter.cu", "take.cu", "gen.cu", "scan.cu", "partition.cu",
-           "join.cu", "nullable.cu", "api_host.cu", "api_host_join.cu", "set.cu", "col.cu"]
+           "join.cu", "nullable.cu", "api_host.cu", "api_host_join.cu", "set.cu", "col.cu", "filter64.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1032,6 +1032,80 @@ int b2_filter_lt_32_host_into(b2_ctx* ctx, const void* const* batch_ptrs, const 
                                 static_cast<uint32_t*>(out), out_capacity, out_counts, total, timings);
 }
 
+int b2_filter_lt_64_host_into(b2_ctx* ctx, const void* const* batch_ptrs_, const uint8_t* const* valid_ptrs,
+                              const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
+                              int dtype, uint64_t threshold_bits, void* out, int64_t out_capacity,
+                              int64_t* out_counts, uint64_t* total, b2_timings* timings) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, dtype == B2_U64 || dtype == B2_I64 || dtype == B2_F64, "dtype must be B2_U64, B2_I64 or B2_F64");
+  B2_REQUIRE(ctx, total != nullptr && out_capacity >= 0, "bad result arguments");
+  B2_REQUIRE(ctx, nbatches >= 0 && (nbatches == 0 || (batch_lens && out_counts)), "bad batch table");
+  // the upload machinery moves 32-bit words: a batch of n 64-bit values is a batch of 2n words
+  const uint32_t* const* batch_ptrs = reinterpret_cast<const uint32_t* const*>(batch_ptrs_);
+  const auto t0 = Clock::now();
+  const int64_t launches0 = ctx->launches;
+  b2_pending_free(ctx);
+  B2_RETURN_NOT_OK(ensure_streams(ctx));
+  Layout L, W;  // rows (validity, boundaries) and words (upload)
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, batch_lens, nbatches, &L));
+  std::vector<int64_t> wlens((size_t)nbatches);
+  for (int64_t b = 0; b < nbatches; ++b) {
+    B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(batch_ptrs[b]) & 7) == 0, "batches must be 8-byte aligned");
+    wlens[(size_t)b] = batch_lens[b] * 2;
+  }
+  B2_RETURN_NOT_OK(make_layout(ctx, batch_ptrs, wlens.data(), nbatches, &W));
+  *total = 0;
+  b2_timings tm{};
+  if (L.rows() > 0) {
+    Scratch sc;
+    std::vector<uint8_t> bits;
+    const bool nullable = pack_validity(&bits, L, valid_ptrs, valid_bit_offsets, nbatches);
+    uint32_t* d_col = nullptr;
+    uint64_t* d_out = nullptr;
+    uint8_t* d_valid = nullptr;
+    int64_t *d_end = nullptr, *d_off = nullptr;
+    void* d_ws = nullptr;
+    const size_t ws_bytes = b2_filter_64_ws_bytes(L.rows());
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_col, (size_t)W.rows() * 4));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_out, (size_t)L.rows() * 8));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_end, (size_t)(nbatches + 1) * 8));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_off, (size_t)(nbatches + 1) * 8));
+    B2_RETURN_NOT_OK(sc.alloc(ctx, &d_ws, ws_bytes));
+    cudaStream_t s = ctx->s_compute;
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d_off, L.off.data(), (size_t)(nbatches + 1) * 8, cudaMemcpyHostToDevice, s));
+    gather_begin(ctx, nbatches, W.rows());
+    B2_RETURN_NOT_OK(upload(ctx, d_col, W, batch_ptrs, 0, nbatches, s, &tm.h2d_bytes));
+    if (nullable) {
+      B2_RETURN_NOT_OK(sc.alloc(ctx, (void**)&d_valid, bits.size()));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(d_valid, bits.data(), bits.size(), cudaMemcpyHostToDevice, s));
+      tm.h2d_bytes += (int64_t)bits.size();
+    }
+    B2_RETURN_NOT_OK(b2_filter_lt_64_dev(ctx, d_col, dtype, threshold_bits, d_valid, L.rows(), d_off, nbatches, 0,
+                                         d_out, d_end, d_end + nbatches, d_ws, ws_bytes, s));
+    std::vector<int64_t> end((size_t)nbatches + 1);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(end.data(), d_end, (size_t)(nbatches + 1) * 8, cudaMemcpyDeviceToHost, s));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    for (int64_t b = 0; b < nbatches; ++b) out_counts[b] = end[(size_t)b] - (b ? end[(size_t)b - 1] : 0);
+    *total = (uint64_t)end[(size_t)nbatches];
+    tm.d2h_bytes = (nbatches + 1) * 8;
+    if ((int64_t)*total > out_capacity)
+      return b2_set_error(ctx, B2_ERR_OVERFLOW, "64-bit filter", "result exceeds out_capacity");
+    if (*total > 0) {
+      B2_REQUIRE(ctx, out != nullptr, "out is null");
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(out, d_out, (size_t)*total * 8, cudaMemcpyDeviceToHost, s));
+      B2_CUDA_OK(ctx, cudaStreamSynchronize(s));
+      tm.d2h_bytes += (int64_t)*total * 8;
+    }
+  } else {
+    for (int64_t b = 0; b < nbatches; ++b) out_counts[b] = 0;
+  }
+  tm.total_ms = ms_since(t0);
+  tm.kernel_launches = (int32_t)(ctx->launches - launches0);
+  if (timings) *timings = tm;
+  return B2_OK;
+}
+
 // ---- join with NULLABLE keys --------------------------------------------------
 // Arrow's inner hash join (the reference's oracle, join_native.cc:31-36) never matches a null key,
 // on either side; the DPU path has no bitmaps at all. Rows with a null key are dropped ON THE DEVICE

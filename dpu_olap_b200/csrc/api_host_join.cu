@@ -458,8 +458,10 @@ int b2_join_cols_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int6
       pend->dev.push_back(d_out);
       pend->d_cols.push_back(d_out);
       B2_RETURN_NOT_OK(upload_column(ctx, d_col, ptrs + (size_t)(1 + c) * nb, lens, nb, s, &tm.h2d_bytes));
-      if (rows > 0)  // one "batch" = the whole side: the row numbers are global
+      if (rows > 0) {  // one "batch" = the whole side: the row numbers are global
+        b2_trace_scope tr(ctx, B2_PHASE_TAKE, s);
         B2_RETURN_NOT_OK(b2_take_u32_dev(ctx, d_col, side_rows[side], ids, (int64_t)rows, 1, d_out, s));
+      }
     }
   }
   B2_CUDA_OK(ctx, cudaEventRecord(work.b, s));
@@ -554,6 +556,7 @@ int upload_wide(b2_ctx* ctx, void* d_col, const void* const* ptrs, const int64_t
 int gather_col(b2_ctx* ctx, const void* d_col, int64_t col_rows, int bytes, const uint32_t* ids, int64_t rows,
                void* d_out, cudaStream_t s) {
   if (rows == 0) return B2_OK;
+  b2_trace_scope tr(ctx, B2_PHASE_TAKE, s);
   if (bytes == 8) return b2_take_64_dev(ctx, d_col, col_rows, ids, rows, 1, d_out, s);
   return b2_take_u32_dev(ctx, static_cast<const uint32_t*>(d_col), col_rows, ids, rows, 1,
                          static_cast<uint32_t*>(d_out), s);

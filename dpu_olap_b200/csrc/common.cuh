@@ -53,6 +53,27 @@ struct b2_ctx {
   size_t cache_bytes[kCacheSlots] = {};
   std::vector<std::pair<void*, size_t>> pool_free;   // idle blocks of the recycling allocator
   std::vector<std::pair<void*, size_t>> pool_live;   // blocks handed out
+  // join phase trace (b2_join_trace / b2_join_last_phases): CUDA events at the phase boundaries of the
+  // joins launched through this ctx; events are created once and reused
+  bool trace_join = false;
+  std::vector<cudaEvent_t> trace_events;
+  size_t trace_used = 0;
+  struct Mark { int phase; size_t ev0, ev1; };
+  std::vector<Mark> trace_marks;
+};
+// Phases of the join trace. Scoped marks: the constructor records the start event on `s`, the
+// destructor the end event; nothing happens unless the ctx traces (no events, no host cost).
+enum b2_trace_phase { B2_PHASE_PART_BUILD = 0, B2_PHASE_PART_PROBE = 1, B2_PHASE_PROBE = 2, B2_PHASE_TAKE = 3,
+                      B2_PHASE_COUNT = 4 };
+void b2_trace_reset(b2_ctx* ctx);
+struct b2_trace_scope {
+  b2_ctx* ctx;
+  cudaStream_t s;
+  size_t mark = ~(size_t)0;
+  b2_trace_scope(b2_ctx* ctx, int phase, cudaStream_t s);
+  ~b2_trace_scope();
+  b2_trace_scope(const b2_trace_scope&) = delete;
+  b2_trace_scope& operator=(const b2_trace_scope&) = delete;
 };
 // Recycling device allocator of the *_host entry points: b2_dev_free keeps the block for the next
 // b2_dev_alloc of a similar size (cudaMalloc / cudaFree of GiB-sized buffers per call cost

@@ -81,7 +81,62 @@ int b2_ctx_cached(b2_ctx* ctx, int slot, size_t bytes, void** out) {
   return B2_OK;
 }
 
+// ---- join phase trace ----------------------------------------------------------------------------------
+void b2_trace_reset(b2_ctx* ctx) {
+  ctx->trace_marks.clear();
+  ctx->trace_used = 0;
+}
+static bool trace_event(b2_ctx* ctx, size_t* idx) {
+  if (ctx->trace_used == ctx->trace_events.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return false;
+    ctx->trace_events.push_back(e);
+  }
+  *idx = ctx->trace_used++;
+  return true;
+}
+b2_trace_scope::b2_trace_scope(b2_ctx* c, int phase, cudaStream_t st) : ctx(c), s(st) {
+  if (!ctx || !ctx->trace_join) return;
+  size_t e0, e1;
+  if (!trace_event(ctx, &e0) || !trace_event(ctx, &e1)) return;
+  if (cudaEventRecord(ctx->trace_events[e0], s) != cudaSuccess) return;
+  mark = ctx->trace_marks.size();
+  ctx->trace_marks.push_back({phase, e0, e1});
+}
+b2_trace_scope::~b2_trace_scope() {
+  if (mark == ~(size_t)0) return;
+  if (cudaEventRecord(ctx->trace_events[ctx->trace_marks[mark].ev1], s) != cudaSuccess)
+    ctx->trace_marks[mark].phase = -1;  // never ended: skipped by b2_join_last_phases
+}
+
 extern "C" {
+
+int b2_join_trace(b2_ctx* ctx, int on) {
+  if (!ctx) return B2_ERR_INVALID;
+  ctx->trace_join = on != 0;
+  b2_trace_reset(ctx);  // whatever an earlier join left behind is not "the last join" of the new trace
+  return B2_OK;
+}
+
+int b2_join_last_phases(b2_ctx* ctx, b2_join_phases* out) {
+  if (!ctx || !out) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  *out = b2_join_phases{};
+  double ms[B2_PHASE_COUNT] = {};
+  for (const b2_ctx::Mark& m : ctx->trace_marks) {
+    if (m.phase < 0 || m.phase >= B2_PHASE_COUNT) continue;
+    float t = 0.f;
+    B2_CUDA_OK(ctx, cudaEventSynchronize(ctx->trace_events[m.ev1]));
+    B2_CUDA_OK(ctx, cudaEventElapsedTime(&t, ctx->trace_events[m.ev0], ctx->trace_events[m.ev1]));
+    ms[m.phase] += (double)t;
+    out->intervals++;
+  }
+  out->partition_build_ms = ms[B2_PHASE_PART_BUILD];
+  out->partition_probe_ms = ms[B2_PHASE_PART_PROBE];
+  out->probe_ms = ms[B2_PHASE_PROBE];
+  out->take_ms = ms[B2_PHASE_TAKE];
+  return B2_OK;
+}
 
 int b2_version(void) { return B2_VERSION; }
 
@@ -158,6 +213,7 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   for (auto& blk : ctx->pool_free) cudaFree(blk.first);
   for (auto& blk : ctx->pool_live) cudaFree(blk.first);
   if (ctx->d_small) cudaFree(ctx->d_small);
+  for (cudaEvent_t e : ctx->trace_events) cudaEventDestroy(e);
   delete ctx;
   return B2_OK;
 }

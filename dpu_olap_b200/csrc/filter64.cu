@@ -1,0 +1,219 @@
+// filter64.cu — order-preserving `v < threshold` over 64-bit columns (uint64 / int64 / float64).
+//
+// SURVEY.md section 8f-3 ("other fixed-width types": the reference fixes `#define T uint32_t`,
+// dpu/shared/common.h:3, and its kernel_filter, dpu/shared/kernels/filter.c:57-177, moves 4-byte
+// items). Semantics are those of the reference's oracle, the Acero filter plan with
+// less(field, literal) (host/filter/filter_native.cc:52-66) over a 64-bit column: rows keep their
+// order, a null row is dropped, a NaN row is never selected, the result has no nulls.
+//
+// This is the generality path, not the headline: a counted two-pass compaction instead of the 32-bit
+// kernel's single pass (csrc/filter.cu), 8 + 8 + 8 s bytes per row (s = selectivity) where one pass
+// would move 8 + 8 s:
+//   1. filter64_count_kernel    selected rows per 2048-row tile (16 KB), one CTA per tile
+//   2. exclusive scan           of the tile counts (csrc/scan.cu, decoupled look-back)
+//   3. filter64_compact_kernel  re-reads the tile, ranks the selected rows in row order (one ballot
+//                               per 256 rows, a 64-entry scan of the (slice, warp) counts) and writes
+//                               them behind the tile's offset
+//   4. filter64_end_kernel      batch_end[b] = rows selected up to the end of batch b (one warp per
+//                               batch recounts the part of the tile the boundary cuts), and the total
+#include <algorithm>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSlices = 8;                       // rows per thread and tile
+constexpr int kTile = kThreads * kSlices;        // 2048 rows = 16 KB
+constexpr int kWarps = kThreads / 32;
+
+template <int kType>
+__device__ __forceinline__ bool lt64(uint64_t a, uint64_t thr) {
+  if (kType == B2_I64) return (long long)a < (long long)thr;
+  if (kType == B2_F64) return __longlong_as_double((long long)a) < __longlong_as_double((long long)thr);
+  return a < thr;
+}
+
+// Is row `i` of the packed column selected? (bit i of the packed validity bitmap, when there is one)
+template <int kType>
+__device__ __forceinline__ bool selected(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid,
+                                         int64_t i, uint64_t thr, uint64_t* v) {
+  *v = in[i];
+  bool ok = lt64<kType>(*v, thr);
+  if (valid) ok = ok && ((valid[i >> 3] >> (i & 7)) & 1);
+  return ok;
+}
+
+template <int kType>
+__global__ void __launch_bounds__(kThreads)
+filter64_count_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid, int64_t n, uint64_t thr,
+                      int64_t ntiles, uint32_t* __restrict__ tile_cnt) {
+  __shared__ uint32_t wsum[kWarps];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * kTile;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < kSlices; ++j) {
+      const int64_t i = base + j * kThreads + tid;
+      uint64_t v;
+      if (i < n && selected<kType>(in, valid, i, thr, &v)) ++c;
+    }
+    c = warp_reduce_sum_u32(c);
+    if (lane == 0) wsum[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t s = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += wsum[w];
+      tile_cnt[t] = s;
+    }
+    __syncthreads();
+  }
+}
+
+template <int kType>
+__global__ void __launch_bounds__(kThreads)
+filter64_compact_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid, int64_t n, uint64_t thr,
+                        int64_t ntiles, const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ out) {
+  __shared__ uint32_t cnt[kSlices * kWarps];  // selected rows of (slice j, warp w), in row order j * 8 + w
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = lanemask_lt();
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * kTile;
+    uint64_t v[kSlices];
+    uint32_t rank[kSlices];  // rank inside the warp's 32 rows of slice j, or ~0: not selected
+#pragma unroll
+    for (int j = 0; j < kSlices; ++j) {
+      const int64_t i = base + j * kThreads + tid;
+      const bool ok = i < n && selected<kType>(in, valid, i, thr, &v[j]);
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      rank[j] = ok ? (uint32_t)__popc(m & lt) : 0xffffffffu;
+      if (lane == 0) cnt[j * kWarps + warp] = (uint32_t)__popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 64 counts, two per lane
+      const uint32_t a = cnt[2 * lane], b = cnt[2 * lane + 1];
+      uint32_t incl = a + b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+      }
+      const uint32_t excl = incl - a - b;
+      cnt[2 * lane] = excl;
+      cnt[2 * lane + 1] = excl + a;
+    }
+    __syncthreads();
+    uint64_t* dst = out + tile_off[t];
+#pragma unroll
+    for (int j = 0; j < kSlices; ++j)
+      if (rank[j] != 0xffffffffu) dst[cnt[j * kWarps + warp] + rank[j]] = v[j];
+    __syncthreads();
+  }
+}
+
+// One warp per batch: rows selected in [0, batch_off[b + 1]) = offset of the tile the boundary falls
+// into + the selected rows of that tile before the boundary. The last warp also writes the total.
+template <int kType>
+__global__ void __launch_bounds__(kThreads)
+filter64_end_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid, int64_t n, uint64_t thr,
+                    int64_t ntiles, const uint64_t* __restrict__ tile_off, const int64_t* __restrict__ batch_off,
+                    int64_t nbatches, int64_t batch_len, int64_t* __restrict__ batch_end,
+                    int64_t* __restrict__ total) {
+  const int64_t b = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  if (b == 0 && lane == 0 && total) *total = (int64_t)tile_off[ntiles];
+  if (b >= nbatches) return;
+  const int64_t r = batch_off ? batch_off[b + 1] : (b + 1) * batch_len;  // first row after batch b
+  const int64_t t = r / kTile;
+  uint32_t c = 0;
+  for (int64_t i = t * kTile + lane; i < r; i += 32) {
+    uint64_t v;
+    if (selected<kType>(in, valid, i, thr, &v)) ++c;
+  }
+  c = warp_reduce_sum_u32(c);
+  if (lane == 0) batch_end[b] = (int64_t)tile_off[min(t, ntiles)] + c;
+}
+
+struct F64Layout {
+  int64_t ntiles;
+  size_t off_cnt, off_scan, off_scanws, total;
+};
+F64Layout f64_layout(int64_t n) {
+  F64Layout L;
+  L.ntiles = (n + kTile - 1) / kTile;
+  size_t o = 0;
+  L.off_cnt = o;    o += b2_align_up((size_t)(L.ntiles + 1) * 4, 256);
+  L.off_scan = o;   o += b2_align_up((size_t)(L.ntiles + 1) * 8, 256);
+  L.off_scanws = o; o += b2_align_up(b2_scan_ws_bytes(L.ntiles + 1), 256);
+  L.total = o;
+  return L;
+}
+
+template <int kType>
+int filter64_impl(b2_ctx* ctx, const uint64_t* d_in, const uint8_t* d_valid, int64_t n, uint64_t thr,
+                  const int64_t* d_batch_off, int64_t nbatches, int64_t batch_len, uint64_t* d_out,
+                  int64_t* d_batch_end, int64_t* d_total, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+  const F64Layout L = f64_layout(n);
+  if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "64-bit filter", "use b2_filter_64_ws_bytes()");
+  char* base = static_cast<char*>(d_ws);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(base + L.off_cnt);
+  uint64_t* off = reinterpret_cast<uint64_t*>(base + L.off_scan);
+  B2_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, (size_t)(L.ntiles + 1) * 4, s));
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(L.ntiles, (int64_t)ctx->sm_count * 8));
+  if (L.ntiles > 0) {
+    filter64_count_kernel<kType><<<grid, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, cnt);
+    B2_LAUNCH_CHECK(ctx, "filter64_count_kernel");
+  }
+  // ntiles + 1 entries: the last one is the total
+  B2_RETURN_NOT_OK(b2_exclusive_scan_u32_u64(ctx, cnt, off, L.ntiles + 1, base + L.off_scanws,
+                                             ws_bytes - L.off_scanws, s));
+  if (L.ntiles > 0) {
+    filter64_compact_kernel<kType><<<grid, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, off, d_out);
+    B2_LAUNCH_CHECK(ctx, "filter64_compact_kernel");
+  }
+  const int64_t warps = std::max<int64_t>(nbatches, 1);
+  filter64_end_kernel<kType><<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, s>>>(
+      d_in, d_valid, n, thr, L.ntiles, off, d_batch_off, nbatches, batch_len, d_batch_end, d_total);
+  B2_LAUNCH_CHECK(ctx, "filter64_end_kernel");
+  return B2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t b2_filter_64_ws_bytes(int64_t n) { return n < 0 ? 0 : f64_layout(n).total; }
+
+int b2_filter_lt_64_dev(b2_ctx* ctx, const void* d_in, int dtype, uint64_t threshold_bits, const uint8_t* d_valid,
+                        int64_t n, const int64_t* d_batch_off, int64_t nbatches, int64_t batch_len, void* d_out,
+                        int64_t* d_batch_end, int64_t* d_total, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, n >= 0 && nbatches >= 0 && batch_len >= 0, "negative size");
+  B2_REQUIRE(ctx, dtype == B2_U64 || dtype == B2_I64 || dtype == B2_F64, "dtype must be B2_U64, B2_I64 or B2_F64");
+  B2_REQUIRE(ctx, n == 0 || (d_in && d_out), "null column");
+  B2_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_in) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 7) == 0,
+             "64-bit columns must be 8-byte aligned");
+  B2_REQUIRE(ctx, nbatches == 0 || d_batch_end, "d_batch_end is null");
+  B2_REQUIRE(ctx, d_batch_off != nullptr || nbatches * batch_len == n, "uniform batches must cover the column");
+  B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "workspace must be 256 B aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint64_t* in = static_cast<const uint64_t*>(d_in);
+  uint64_t* out = static_cast<uint64_t*>(d_out);
+  switch (dtype) {
+    case B2_I64:
+      return filter64_impl<B2_I64>(ctx, in, d_valid, n, threshold_bits, d_batch_off, nbatches, batch_len, out,
+                                   d_batch_end, d_total, d_ws, ws_bytes, s);
+    case B2_F64:
+      return filter64_impl<B2_F64>(ctx, in, d_valid, n, threshold_bits, d_batch_off, nbatches, batch_len, out,
+                                   d_batch_end, d_total, d_ws, ws_bytes, s);
+    default:
+      return filter64_impl<B2_U64>(ctx, in, d_valid, n, threshold_bits, d_batch_off, nbatches, batch_len, out,
+                                   d_batch_end, d_total, d_ws, ws_bytes, s);
+  }
+}
+
+}  // extern "C"

@@ -669,6 +669,7 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
   void* pws = base + P.off_part;
 
   if (phases & 1) {
+    if (ctx->trace_join) b2_trace_reset(ctx);
     join_init_kernel<<<1, 1, 0, s>>>(st);
     B2_LAUNCH_CHECK(ctx, "join_init_kernel");
   }
@@ -683,14 +684,19 @@ int join_impl(b2_ctx* ctx, const PartInput& lin, int64_t nl, const PartInput& ri
     const int64_t nparts = (int64_t)1 << P.bits;
     const int part_shl = skip_bits + P.slice_bits;
     for (uint32_t slice = 0; slice < (1u << P.slice_bits); ++slice) {
-      if (P.slice_bits == 0 ? (phases & 1) : (phases & 2))
+      if (P.slice_bits == 0 ? (phases & 1) : (phases & 2)) {
+        b2_trace_scope tr(ctx, B2_PHASE_PART_BUILD, s);
         B2_RETURN_NOT_OK(part_full(ctx, rin, nr, P.bits, part_shl, skip_bits, P.slice_bits, slice,
                                    rout, tmp, P.cap_r, roff, &st->overflow, pws, P.part_bytes, s));
+      }
       if (!(phases & 2)) break;
-      // filter pushdown: the probe side's first radix pass drops the rows that fail L.y < y_thr
-      B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
-                                 lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s,
-                                 agg && agg->filter_y, agg ? agg->y_thr : 0u));
+      {  // filter pushdown: the probe side's first radix pass drops the rows that fail L.y < y_thr
+        b2_trace_scope tr(ctx, B2_PHASE_PART_PROBE, s);
+        B2_RETURN_NOT_OK(part_full(ctx, lin, nl, P.bits, part_shl, skip_bits, P.slice_bits, slice,
+                                   lout, tmp, P.cap_l, loff, &st->overflow, pws, P.part_bytes, s,
+                                   agg && agg->filter_y, agg ? agg->y_thr : 0u));
+      }
+      b2_trace_scope tr(ctx, B2_PHASE_PROBE, s);
       int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
       if (agg)
         join_probe_kernel<true><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
@@ -789,6 +795,7 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   char* base = static_cast<char*>(d_ws);
   JoinState* st = reinterpret_cast<JoinState*>(base + P.off_state);
   if (phases & 1) {
+    if (ctx->trace_join) b2_trace_reset(ctx);
     join_init_kernel<<<1, 1, 0, s>>>(st);
     B2_LAUNCH_CHECK(ctx, "join_init_kernel");
   }
@@ -814,15 +821,20 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
       int64_t* loff_w = reinterpret_cast<int64_t*>(base + P.off_loff);
       void* pws = base + P.off_part;
       // build phase: the build side's fine pass; its result stays in the workspace for every probe phase
-      if (phases & 1)
+      if (phases & 1) {
+        b2_trace_scope tr(ctx, B2_PHASE_PART_BUILD, s);
         B2_RETURN_NOT_OK(part_pass(ctx, rin, nr, r_seg_off, nseg, g, rout, nr, roff_w, &st->overflow, pws,
                                    P.part_bytes, s));
-      if (phases & 2)
+      }
+      if (phases & 2) {
+        b2_trace_scope tr(ctx, B2_PHASE_PART_PROBE, s);
         B2_RETURN_NOT_OK(part_pass(ctx, lin, nl, l_seg_off, nseg, g, lout, nl, loff_w, &st->overflow, pws,
                                    P.part_bytes, s));
+      }
       rp = rout; lp = lout; roff = roff_w; loff = loff_w;
     }
     if (phases & 2) {  // probe phase: may run several times, each over another share of the probe side
+      b2_trace_scope tr(ctx, B2_PHASE_PROBE, s);
       const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
       join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
           rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false,

@@ -164,6 +164,15 @@ class Timers {
     d2h_bytes += t.d2h_bytes;
     kernel_launches += t.kernel_launches;
   }
+  // JoinDpu's timer names (join_dpu.cc:146-148); the probe kernel builds a partition's table and
+  // probes it in one launch, so "probe" covers the reference's "build" + "probe"
+  void Add(const b2_join_phases& p) {
+    Acc("partitionKernel", p.partition_build_ms + p.partition_probe_ms);
+    Acc("partitionKernel-build-side", p.partition_build_ms);
+    Acc("partitionKernel-probe-side", p.partition_probe_ms);
+    Acc("probe", p.probe_ms);
+    Acc("take", p.take_ms);
+  }
   const std::map<std::string, std::shared_ptr<Timer>>& get() const { return timers_; }
   int64_t h2d_bytes = 0, d2h_bytes = 0, kernel_launches = 0;
 

@@ -242,6 +242,13 @@ static void JoinLargeTest(gpu::GpuSet& sys) {  // join_test.cc:82-121 (128 x 655
   EXPECT_TRUE(g.Prepare().ok());
   auto gt = g.Run().ValueOrDie();
   EXPECT_EQ(gt->num_rows(), static_cast<int64_t>(nb) * bs);  // :115-116
+  // JoinDpu's phase timers (join_dpu.cc:146-148) come back through the ABI (b2_join_last_phases)
+  const auto& timers = g.Timers()->get();
+  for (const char* name : {"partitionKernel", "probe"}) {
+    auto it = timers.find(name);
+    EXPECT_TRUE(it != timers.end() && it->second->Result().count() > 0);
+  }
+  EXPECT_TRUE(timers.count("take") == 1);
   join::JoinNative n{left[0]->schema(), right[0]->schema(), left, right};
   auto nt = n.Run().ValueOrDie();
   auto gs = Sorted(gt, {"fk", "y"}), ns = Sorted(nt, {"fk", "y"});

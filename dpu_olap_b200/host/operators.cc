@@ -266,6 +266,8 @@ arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
   const int ncols = static_cast<int>(fields.size());
   uint64_t rows = 0;
   b2_timings t1{}, t2{};
+  // phase timers: every member's local join is traced, the slowest member per phase is reported
+  for (int i = 0; i < system_.size(); ++i) b2_join_trace(b2_set_ctx(set, i), 1);
   arrow::ArrayVector arrays(static_cast<size_t>(ncols));
   std::vector<uint32_t*> outs(static_cast<size_t>(ncols));
   const bool pair_path = lcols.size() == 1 && rcols.size() == 1;
@@ -298,6 +300,18 @@ arrow::Result<std::shared_ptr<arrow::Table>> JoinGpu::Run() {
   }
   timers_->Add(t1);
   timers_->Add(t2);
+  b2_join_phases slowest{};
+  for (int i = 0; i < system_.size(); ++i) {
+    b2_ctx* m = b2_set_ctx(set, i);
+    b2_join_phases p{};
+    B2_ARROW_RETURN_NOT_OK(m, b2_join_last_phases(m, &p));
+    slowest.partition_build_ms = std::max(slowest.partition_build_ms, p.partition_build_ms);
+    slowest.partition_probe_ms = std::max(slowest.partition_probe_ms, p.partition_probe_ms);
+    slowest.probe_ms = std::max(slowest.probe_ms, p.probe_ms);
+    slowest.take_ms = std::max(slowest.take_ms, p.take_ms);
+    b2_join_trace(m, 0);
+  }
+  timers_->Add(slowest);
   return arrow::Table::Make(arrow::schema(fields), arrays, static_cast<int64_t>(rows));
 }
 

@@ -27,7 +27,7 @@ from typing import Any, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import B2Error, Timings, check
+from ._lib import B2Error, JoinPhases, Timings, check
 
 try:  # pyarrow is optional for the package, present in the image
     import pyarrow as pa
@@ -47,6 +47,15 @@ class Timers(dict):
             out["copy-from-dpu"] += t.copy_from_dev_ms
             out["total"] += t.total_ms
         return out
+
+    def add_join_phases(self, p: dict) -> None:
+        """JoinDpu's timer names (join_dpu.cc:146-148). The probe kernel builds each partition's table
+        and probes it in one launch, so "probe" covers the reference's "build" + "probe"."""
+        self["partitionKernel"] = p["partition_build_ms"] + p["partition_probe_ms"]
+        self["partitionKernel-build-side"] = p["partition_build_ms"]
+        self["partitionKernel-probe-side"] = p["partition_probe_ms"]
+        self["probe"] = p["probe_ms"]
+        self["take"] = p["take_ms"]
 
     def get(self, *a):  # reference: timers->get() returns the map
         return self if not a else dict.get(self, *a)
@@ -118,12 +127,14 @@ def _column_dtype(batch: Any, name: str) -> np.dtype:
 
 # 32-bit column types the filter compares natively (b2_dtype32, include/b200olap.h)
 _DTYPES32 = {np.dtype(np.uint32): 0, np.dtype(np.int32): 1, np.dtype(np.float32): 2}
-_DTYPES64 = {np.dtype(np.uint64): 3, np.dtype(np.int64): 4}  # b2_dtype64 (aggregates only)
+_DTYPES64 = {np.dtype(np.uint64): 3, np.dtype(np.int64): 4}  # b2_dtype64 (aggregates, take, filter)
+_DTYPES64_FILTER = {**_DTYPES64, np.dtype(np.float64): 5}       # the filter also compares float64
 
 
 def _threshold_bits(threshold, dtype: np.dtype) -> int:
     """Bit pattern of the threshold in the column's type."""
-    return int(np.array([threshold], dtype=dtype).view(np.uint32)[0])
+    dtype = np.dtype(dtype)
+    return int(np.array([threshold], dtype=dtype).view(np.uint64 if dtype.itemsize == 8 else np.uint32)[0])
 
 
 class _NullableCol:
@@ -140,12 +151,14 @@ class _NullableCol:
         self.valid, self.offset, self._keep = valid, int(offset), keep
 
 
-def _as_nullable(col: Any, typed: bool = False, wide: bool = False) -> _NullableCol:
+def _as_nullable(col: Any, typed: bool = False, wide: bool = False, f64: bool = False) -> _NullableCol:
     """typed=True also admits int32 / float32 columns (filter, aggregates); wide=True also uint64 /
-    int64 columns (aggregates only)."""
+    int64 columns (aggregates, take, filter); f64=True also float64 (filter)."""
     ok = tuple(_DTYPES32) if typed else (np.dtype(np.uint32),)
     if wide:
         ok = ok + tuple(_DTYPES64)
+    if f64:
+        ok = ok + (np.dtype(np.float64),)
     if pa is not None and isinstance(col, (pa.Array, pa.ChunkedArray)):
         if isinstance(col, pa.ChunkedArray):
             col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
@@ -175,14 +188,15 @@ def _as_nullable(col: Any, typed: bool = False, wide: bool = False) -> _Nullable
     return _NullableCol(np.ascontiguousarray(a))
 
 
-def _nullable_column(batch: Any, name_or_index, typed: bool = False, wide: bool = False) -> _NullableCol:
+def _nullable_column(batch: Any, name_or_index, typed: bool = False, wide: bool = False,
+                     f64: bool = False) -> _NullableCol:
     if pa is not None and isinstance(batch, pa.RecordBatch):
         i = batch.schema.get_field_index(name_or_index) if isinstance(name_or_index, str) else name_or_index
-        return _as_nullable(batch.column(i), typed, wide)
+        return _as_nullable(batch.column(i), typed, wide, f64)
     if isinstance(batch, dict):
         return _as_nullable(batch[name_or_index] if isinstance(name_or_index, str)
-                            else list(batch.values())[name_or_index], typed, wide)
-    return _as_nullable(batch, typed, wide)
+                            else list(batch.values())[name_or_index], typed, wide, f64)
+    return _as_nullable(batch, typed, wide, f64)
 
 
 class _ValidTable:
@@ -252,6 +266,16 @@ class Context:
     def _call(self, name: str, *args) -> None:
         """b2_<name>(ctx, ...): the host entry point of an operator on this one GPU."""
         self._ck(getattr(self._lib, "b2_" + name)(self._h, *args), "b2_" + name)
+
+    def join_trace(self, on: bool = True) -> None:
+        """b2_join_trace: later joins of this context record CUDA events at their phase boundaries."""
+        self._ck(self._lib.b2_join_trace(self._h, 1 if on else 0), "b2_join_trace")
+
+    def join_last_phases(self) -> dict:
+        """b2_join_last_phases: phase timers of the last traced join (waits for its events)."""
+        p = JoinPhases()
+        self._ck(self._lib.b2_join_last_phases(self._h, C.byref(p)), "b2_join_last_phases")
+        return p.as_dict()
 
     def __del__(self):  # pragma: no cover
         try:
@@ -390,6 +414,30 @@ class Context:
                                                _dptr(valid), nbatches, batch_len, _dptr(out), _dptr(batch_end),
                                                _dptr(total), 0, _dptr(ws), ws.numel(), self._stream()),
                  "b2_filter_lt_32_dev")
+        return out, batch_end, total
+
+    def filter64_dev(self, col, dtype, threshold, valid=None, batch_off=None, nbatches: int = 1,
+                     batch_len: int | None = None, out=None, batch_end=None, total=None, ws=None):
+        """b2_filter_lt_64_dev over a device column of 64-bit values (an int64 torch tensor holding the bit
+        patterns). Batches: batch_off (int64 device tensor, nbatches + 1) or nbatches x batch_len rows."""
+        import torch
+        dt = np.dtype(dtype)
+        n = col.numel()
+        if batch_off is None and batch_len is None:
+            nbatches, batch_len = 1, n
+        if out is None:
+            out = torch.empty(max(n, 1), dtype=torch.int64, device=col.device)
+        if batch_end is None:
+            batch_end = torch.empty(max(nbatches, 1), dtype=torch.int64, device=col.device)
+        if total is None:
+            total = torch.empty(1, dtype=torch.int64, device=col.device)
+        if ws is None:
+            ws = torch.empty(int(self._lib.b2_filter_64_ws_bytes(n)) + 256, dtype=torch.uint8, device=col.device)
+        ptr, nbytes = self._aligned(ws)
+        self._ck(self._lib.b2_filter_lt_64_dev(self._h, _dptr(col), _DTYPES64_FILTER[dt], _threshold_bits(threshold, dt),
+                                               _dptr(valid), n, _dptr(batch_off), nbatches,
+                                               0 if batch_len is None else batch_len, _dptr(out), _dptr(batch_end),
+                                               _dptr(total), ptr, nbytes, self._stream()), "b2_filter_lt_64_dev")
         return out, batch_end, total
 
     def aggr_dev(self, col, valid=None, out=None, dtype=np.uint32):
@@ -772,6 +820,15 @@ class DeviceSet:
         if status != _lib.B2_OK:
             raise B2Error(status, where, self._lib.b2_set_last_error(self._h).decode(errors="replace"))
 
+    def join_trace(self, on: bool = True) -> None:
+        for m in self.members:
+            m.join_trace(on)
+
+    def join_last_phases(self) -> dict:
+        """The slowest member per phase: the members run their local joins side by side."""
+        per = [m.join_last_phases() for m in self.members]
+        return {k: max(p[k] for p in per) for k in per[0]}
+
     def _call(self, name: str, *args) -> None:
         """b2_set_<name>(set, ...) where the set shards the operator; otherwise (nullable / typed /
         64-bit variants) the entry point of member 0."""
@@ -902,13 +959,14 @@ class FilterGpu:
 
     def __init__(self, ctx: Context, batches: Sequence[Any], threshold: int = FILTER_THRESHOLD):
         self.ctx = ctx
-        self._ncols = [_nullable_column(b, 0, typed=True) for b in batches]
+        self._ncols = [_nullable_column(b, 0, typed=True, wide=True, f64=True) for b in batches]
         self._cols = [c.values for c in self._ncols]
         self._valid = _ValidTable(self._ncols)
         kinds = {c.dtype for c in self._ncols}
         if len(kinds) > 1:
             raise TypeError(f"batches of different types: {sorted(str(k) for k in kinds)}")
-        self.dtype = kinds.pop() if kinds else np.dtype(np.uint32)   # uint32 as the reference; int32 / float32 too
+        # uint32 as the reference; int32 / float32 and uint64 / int64 / float64 too
+        self.dtype = kinds.pop() if kinds else np.dtype(np.uint32)
         self.threshold = threshold if self.dtype.kind == "f" else int(threshold)
         self._timers = None
 
@@ -936,9 +994,14 @@ class FilterGpu:
         total = C.c_uint64(0)
         flat = np.empty(sum(a.size for a in self._cols), dtype=self.dtype)
         t = Timings()
-        self.ctx._call("filter_lt_32_host_into", tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n,
-                       _DTYPES32[self.dtype], _threshold_bits(self.threshold, self.dtype), flat.ctypes.data, flat.size,
-                       counts, C.byref(total), C.byref(t))
+        if self.dtype.itemsize == 8:  # counted two-pass compaction (csrc/filter64.cu)
+            self.ctx._call("filter_lt_64_host_into", tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n,
+                           _DTYPES64_FILTER[self.dtype], _threshold_bits(self.threshold, self.dtype), flat.ctypes.data,
+                           flat.size, counts, C.byref(total), C.byref(t))
+        else:
+            self.ctx._call("filter_lt_32_host_into", tab.ptrs, self._valid.ptrs, self._valid.offs, tab.lens, tab.n,
+                           _DTYPES32[self.dtype], _threshold_bits(self.threshold, self.dtype), flat.ctypes.data,
+                           flat.size, counts, C.byref(total), C.byref(t))
         self._timers = Timers.from_timings(t)
         self._last = (t,)
         if _count_only:
@@ -1145,6 +1208,7 @@ class JoinGpu:
         rows = C.c_uint64(0)
         t1, t2 = Timings(), Timings()
         names = [self.fk] + self.lpays + self.rpays
+        self.ctx.join_trace(True)
         if self._typed is not None:
             ldt, rdt = self._typed
 
@@ -1186,6 +1250,8 @@ class JoinGpu:
             ptrs = (C.c_void_p * len(names))(*[o.ctypes.data for o in out])
             self.ctx._call("join_cols_fetch_host", ptrs, len(names), n, C.byref(t2))
         self._timers = Timers.from_timings(t1, t2)
+        self._timers.add_join_phases(self.ctx.join_last_phases())
+        self.ctx.join_trace(False)
         self._last = (t1, t2)
         return dict(zip(names, out))
 
@@ -1201,10 +1267,13 @@ class JoinGpu:
             raise ValueError("the fused join -> aggregate pipeline takes uint32 columns, one payload per side")
         lt, rt = _PtrTable(self._l[0] + self._l[1]), _PtrTable(self._r[0] + self._r[1])
         out, t = _Aggr(), Timings()
+        self.ctx.join_trace(True)
         self.ctx._call("join_aggr_u32_host", lt.ptrs, lt.lens, len(self._l[0]), rt.ptrs, rt.lens, len(self._r[0]),
                        0 if y_threshold is None else 1, 0 if y_threshold is None else int(y_threshold),
                        C.byref(out), C.byref(t))
         self._timers = Timers.from_timings(t)
+        self._timers.add_join_phases(self.ctx.join_last_phases())
+        self.ctx.join_trace(False)
         self._last = (t,)
         return {"rows": int(out.rows), f"sum_{self.lpay}": int(out.sum_y), f"sum_{self.rpay}": int(out.sum_x)}
 

@@ -53,7 +53,7 @@ enum b2_status {
  * dpu/shared/common.h:3; uint32 is what every other entry point means). */
 enum b2_dtype32 { B2_U32 = 0, B2_I32 = 1, B2_F32 = 2 };
 /* 64-bit column types (b2_aggr_64_*); the values continue b2_dtype32's. */
-enum b2_dtype64 { B2_U64 = 3, B2_I64 = 4 };
+enum b2_dtype64 { B2_U64 = 3, B2_I64 = 4, B2_F64 = 5 /* filter only */ };
 
 typedef struct b2_ctx b2_ctx;
 
@@ -385,6 +385,26 @@ int b2_filter_lt_u32_nullable_host_into(b2_ctx* ctx, const uint32_t* const* batc
                                         const int64_t* batch_lens, int64_t nbatches, uint32_t threshold,
                                         uint32_t* out, int64_t out_capacity, int64_t* out_counts,
                                         uint64_t* total, b2_timings* timings);
+/* 64-bit columns (dtype B2_U64 / B2_I64 / B2_F64; SURVEY.md section 8f-3 "other fixed-width types" — the
+ * reference fixes T = uint32_t, dpu/shared/common.h:3): `v < threshold` in the column's type, rows keep
+ * their order, a null row is dropped, a NaN row is never selected (the Acero filter plan of the
+ * reference's oracle, filter_native.cc:52-66, over a 64-bit column). A counted two-pass compaction
+ * (csrc/filter64.cu), not the single-pass 32-bit kernel. d_in / d_out: n packed 64-bit values, 8-byte
+ * aligned; threshold_bits: the threshold's bit pattern; d_valid: validity bitmap over the packed column
+ * or NULL; batches: d_batch_off (device, nbatches + 1 row offsets) or NULL = nbatches x batch_len rows;
+ * d_batch_end[b] = rows selected up to the end of batch b, *d_total = rows selected (both on the
+ * device). d_ws: b2_filter_64_ws_bytes(n) bytes, 256 B aligned. */
+size_t b2_filter_64_ws_bytes(int64_t n);
+int b2_filter_lt_64_dev(b2_ctx* ctx, const void* d_in, int dtype, uint64_t threshold_bits, const uint8_t* d_valid,
+                        int64_t n, const int64_t* d_batch_off, int64_t nbatches, int64_t batch_len, void* d_out,
+                        int64_t* d_batch_end, int64_t* d_total, void* d_ws, size_t ws_bytes, void* stream);
+/* ... over host batches of any lengths (validity arguments as b2_aggr_u32_host): upload, filter,
+ * download; out receives the selected values back to back (out_capacity values), out_counts[b] the
+ * rows of batch b. Not chunked. */
+int b2_filter_lt_64_host_into(b2_ctx* ctx, const void* const* batch_ptrs, const uint8_t* const* valid_ptrs,
+                              const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
+                              int dtype, uint64_t threshold_bits, void* out, int64_t out_capacity,
+                              int64_t* out_counts, uint64_t* total, b2_timings* timings);
 /* The same for int32 / float32 columns (see b2_filter_lt_32_dev): raw 32-bit words in and out. */
 int b2_filter_lt_32_host_into(b2_ctx* ctx, const void* const* batch_ptrs, const uint8_t* const* valid_ptrs,
                               const int64_t* valid_bit_offsets, const int64_t* batch_lens, int64_t nbatches,
@@ -534,6 +554,25 @@ int b2_join_u32_host(b2_ctx* ctx, const uint32_t* const* l_ptrs, const int64_t* 
                      int64_t nr_batches, uint64_t* out_rows, b2_timings* timings);
 int b2_join_fetch_host(b2_ctx* ctx, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x,
                        int64_t capacity_rows, b2_timings* timings);
+
+/* Join phase timers (the reference's JoinDpu timers "build" / "probe" / "take" / "partitionKernel",
+ * host/join/join_dpu.cc:146-148, read by join_benchmark.cc). b2_join_trace(ctx, 1) makes every join
+ * launched through the ctx — *_dev and *_host entry points alike — record CUDA events at its phase
+ * boundaries on the stream it runs on; b2_join_last_phases waits for the events of the LAST join and
+ * reports the time between them, summed per phase (a sliced join, or a probe side fed in shares, has
+ * several intervals per phase). Where the DPU design has "build" and "probe" as separate launches,
+ * the probe kernel here builds a partition's table and probes it in one go: probe_ms covers both.
+ * Off by default (no events, no cost). */
+typedef struct b2_join_phases {
+  double partition_build_ms; /* radix passes over the build side (R: pk, x) */
+  double partition_probe_ms; /* radix passes over the probe side (L: fk, y), incl. a pushed-down filter */
+  double probe_ms;           /* table build + probe + output rows */
+  double take_ms;            /* payload gathers of the multi-column / typed-table joins */
+  int32_t intervals;         /* intervals summed */
+  int32_t reserved;
+} b2_join_phases;
+int b2_join_trace(b2_ctx* ctx, int on);
+int b2_join_last_phases(b2_ctx* ctx, b2_join_phases* out);
 
 /* The same join with NULLABLE key columns: Arrow's inner hash join — the
  * reference's oracle, join_native.cc:31-36 — never matches a null key on either side (the DPU path has

@@ -47,9 +47,14 @@ def test_take_gpu_column_types():
         ops.TakeGpu(None, [np.zeros(4, np.uint32)], [])
 
 
-def test_filter_gpu_is_32bit_only():
-    for dt in (np.uint32, np.int32, np.float32):
-        ops.FilterGpu(None, [np.zeros(4, dt)])
-    for bad in (np.uint64, np.int64, np.float64):
+def test_filter_gpu_column_types():
+    for dt in (np.uint32, np.int32, np.float32, np.uint64, np.int64, np.float64):
+        f = ops.FilterGpu(None, [np.zeros(4, dt), pa.array(np.zeros(3, dt))])
+        assert f.dtype == np.dtype(dt)
+    for bad in (np.uint16, np.int8, np.float16):
         with pytest.raises(TypeError):
             ops.FilterGpu(None, [np.zeros(4, bad)])
+    with pytest.raises(TypeError):   # mixed widths
+        ops.FilterGpu(None, [np.zeros(4, np.uint32), np.zeros(4, np.uint64)])
+    with pytest.raises(TypeError):   # mixed types of one width
+        ops.FilterGpu(None, [np.zeros(4, np.int64), np.zeros(4, np.float64)])
