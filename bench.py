@@ -445,7 +445,39 @@ def bench_wide(ctx, D, args):
     res["aggregates_u64"] = {"ms_per_step": ms, "rows": rows, "rows_per_s": rows / (ms * 1e-3),
                              "algorithmic_bytes_per_row": 8,
                              "achieved_gbs": 8 * rows / D.world / (ms * 1e-3) / 1e9, "result_rank0": agg}
-    del words, col
+    # ---- filter over the same uint64 column: v < 2^62 (25 % selected), batches of 32768 rows ----
+    from dpu_olap_b200._lib import TUNE_FILTER64_KERNEL
+    thr = 1 << 62
+    bl = FILTER_BATCH // 2
+    fout = torch.empty(n, dtype=torch.int64, device="cuda")
+    fend = torch.empty(nb, dtype=torch.int64, device="cuda")
+    ftot = torch.empty(1, dtype=torch.int64, device="cuda")
+    fws = torch.empty(int(ctx._lib.b2_filter_64_ws_bytes(n)) + 256, dtype=torch.uint8, device="cuda")
+    fres = {}
+    for kern, name in ((1, "two_pass"), (0, "single_pass")):   # the default kernel last: its output is checked
+        ctx.set_tunable(TUNE_FILTER64_KERNEL, kern)
+        fres[name] = timed_steps(D, lambda: ctx.filter64_dev(col, np.uint64, thr, nbatches=nb, batch_len=bl, out=fout,
+                                                             batch_end=fend, total=ftot, ws=fws),
+                                 args.steps, args.warmup)
+    sel = 0
+    chunk = 1 << 27
+    for r0 in range(0, n, chunk):   # content check, streamed: unsigned v < 2^62  <=>  0 <= signed v < 2^62
+        c = col[r0:r0 + chunk]
+        ref = c[(c >= 0) & (c < thr)]
+        if not torch.equal(ref, fout[sel:sel + ref.numel()]):
+            raise SystemExit(f"64-bit filter self-check failed on rank {D.rank}, rows [{r0}, {r0 + chunk})")
+        sel += ref.numel()
+        del c, ref
+    if sel != int(ftot.item()) or sel != int(fend[-1].item()):
+        raise SystemExit(f"64-bit filter self-check failed on rank {D.rank}: total")
+    sel_all = D.sum_int(sel)
+    ms = fres["single_pass"]
+    res["filter_u64"] = {"ms_per_step": ms, "rows": rows, "selected": sel_all, "rows_per_s": rows / (ms * 1e-3),
+                         "algorithmic_bytes_per_row": 8 + 8 * sel_all / rows, "self_check": "content",
+                         "achieved_gbs": (8 * rows + 8 * sel_all) / D.world / (ms * 1e-3) / 1e9,
+                         "two_pass_ms_per_step": fres["two_pass"],
+                         "kernel": "filter64_single_pass_kernel (decoupled look-back; csrc/filter64.cu)"}
+    del words, col, fout, fend, ftot, fws
     free_all()
     if sf >= D.world:
         firstb, nbt = shard(sf, D)

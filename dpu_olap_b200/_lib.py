@@ -18,7 +18,8 @@ HEADER = PKG_DIR.parent / "include" / "b200olap.h"
 B2_OK = 0
 # enum b2_tunable
 (TUNE_SCATTER_SECTORS_MIN_BITS, TUNE_SCATTER_PREFETCH, TUNE_SCATTER_SHAPE, TUNE_FILTER_VARIANT,
- TUNE_SCATTER_SECTOR_TILE, TUNE_JOIN_DIRECT_MIN_ROWS, TUNE_PEER_SCATTER_CTAS, TUNE_PEER_SCATTER_KERNEL) = range(8)
+ TUNE_SCATTER_SECTOR_TILE, TUNE_JOIN_DIRECT_MIN_ROWS, TUNE_PEER_SCATTER_CTAS, TUNE_PEER_SCATTER_KERNEL,
+ TUNE_FILTER64_KERNEL) = range(9)
 STATUS_NAMES = {0: "B2_OK", 1: "B2_ERR_INVALID", 2: "B2_ERR_CUDA", 3: "B2_ERR_OOM",
                 4: "B2_ERR_UNSUPPORTED", 5: "B2_ERR_WORKSPACE", 6: "B2_ERR_OVERFLOW"}
 

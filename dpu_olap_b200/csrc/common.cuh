@@ -28,7 +28,7 @@ struct b2_ctx {
   size_t small_bytes = 0;
   uint32_t sum_slot = 0;  // next slot of that ring
   // kernel-selection knobs (b2_ctx_set_tunable, enum b2_tunable): every setting computes the same result
-  int tune[8] = {8, 1, 0, 6, 3, 2048, 0, 0};
+  int tune[12] = {8, 1, 0, 6, 3, 2048, 0, 0, 0, 0, 0, 0};
   std::vector<char> site_done;  // per call site: function attributes configured for this ctx's device
   std::vector<int> site_value;
   // growable device workspace used by the *_host layer
@@ -162,6 +162,11 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {
 __device__ __forceinline__ uint2 ld_stream_v2(const uint2* p) {
   uint2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
+  uint64_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {

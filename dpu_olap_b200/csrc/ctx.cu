@@ -269,13 +269,14 @@ int b2_ctx_set_tunable(b2_ctx* ctx, int which, int value) {
     case B2_TUNE_PEER_SCATTER_KERNEL: B2_REQUIRE(ctx, value == 0 || value == 1, "0 = lines, 1 = bulk sectors"); break;
     case B2_TUNE_PEER_SCATTER_CTAS: B2_REQUIRE(ctx, value >= 0, "0 = one CTA per work unit"); break;
     case B2_TUNE_JOIN_DIRECT_MIN_ROWS: B2_REQUIRE(ctx, value >= 0, "0 = off, n = minimum build rows per partition"); break;
+    case B2_TUNE_FILTER64_KERNEL: B2_REQUIRE(ctx, value == 0 || value == 1, "0 = single pass, 1 = two passes"); break;
     default: return b2_set_error(ctx, B2_ERR_INVALID, "b2_ctx_set_tunable", "unknown tunable");
   }
   ctx->tune[which] = value;
   return B2_OK;
 }
 int b2_ctx_get_tunable(const b2_ctx* ctx, int which, int* value) {
-  if (!ctx || !value || which < 0 || which > B2_TUNE_PEER_SCATTER_KERNEL) return B2_ERR_INVALID;
+  if (!ctx || !value || which < 0 || which > B2_TUNE_FILTER64_KERNEL) return B2_ERR_INVALID;
   *value = ctx->tune[which];
   return B2_OK;
 }

@@ -6,19 +6,25 @@
 // less(field, literal) (host/filter/filter_native.cc:52-66) over a 64-bit column: rows keep their
 // order, a null row is dropped, a NaN row is never selected, the result has no nulls.
 //
-// This is the generality path, not the headline: a counted two-pass compaction instead of the 32-bit
-// kernel's single pass (csrc/filter.cu), 8 + 8 + 8 s bytes per row (s = selectivity) where one pass
-// would move 8 + 8 s:
-//   1. filter64_count_kernel    selected rows per 2048-row tile (16 KB), one CTA per tile
-//   2. exclusive scan           of the tile counts (csrc/scan.cu, decoupled look-back)
-//   3. filter64_compact_kernel  re-reads the tile, ranks the selected rows in row order (one ballot
-//                               per 256 rows, a 64-entry scan of the (slice, warp) counts) and writes
-//                               them behind the tile's offset
-//   4. filter64_end_kernel      batch_end[b] = rows selected up to the end of batch b (one warp per
-//                               batch recounts the part of the tile the boundary cuts), and the total
+// Two kernels compute the same result (ctx tunable B2_TUNE_FILTER64_KERNEL):
+//   0  filter64_single_pass_kernel (default): one CTA per 2048-row tile (16 KB), tiles handed out by
+//      an atomic ticket. The CTA loads its tile (eight independent 8-byte loads per thread), ranks
+//      the selected rows in row order (one ballot per 256 rows, a 64-entry scan of the (slice, warp)
+//      counts), obtains the rows selected before the tile with the decoupled look-back of
+//      lookback.cuh (the reference's serial handshake between tasklets, filter.c:28-55, without the
+//      serialisation: a tile only waits for its predecessors' COUNTS), stages the selected rows
+//      compacted in shared memory and writes them out as one contiguous run. Every row is read once
+//      and every selected row written once: 8 + 8 s bytes per row (s = selectivity).
+//   1  counted two-pass compaction: filter64_count_kernel (selected rows per tile), an exclusive scan
+//      of the tile counts (csrc/scan.cu), filter64_compact_kernel (re-reads the tile and writes the
+//      selected rows behind the tile's offset): 8 + 8 + 8 s bytes per row. Kept as the cross-check.
+// Both leave the exclusive prefix of every tile (and the total as entry ntiles) in the workspace;
+// filter64_end_kernel turns them into batch_end[b] = rows selected up to the end of batch b (one warp
+// per batch recounts the part of the tile the boundary cuts) and the total.
 #include <algorithm>
 
 #include "common.cuh"
+#include "lookback.cuh"
 #include "scan.cuh"
 
 namespace {
@@ -33,6 +39,41 @@ __device__ __forceinline__ bool lt64(uint64_t a, uint64_t thr) {
   if (kType == B2_I64) return (long long)a < (long long)thr;
   if (kType == B2_F64) return __longlong_as_double((long long)a) < __longlong_as_double((long long)thr);
   return a < thr;
+}
+
+// A tile's rows as the kernels hold them: thread t owns rows base + j * 256 + t. All loads are issued
+// before the first value is looked at (eight independent 8-byte loads in flight per thread); rows past
+// the end of the column are not loaded and never selected.
+template <int kType>
+__device__ __forceinline__ void load_tile(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid,
+                                          int64_t base, int64_t n, uint32_t tid, uint64_t thr,
+                                          uint64_t (&v)[kSlices], bool (&ok)[kSlices]) {
+  uint32_t vb[kSlices];
+  if (base + kTile <= n) {
+#pragma unroll
+    for (int j = 0; j < kSlices; ++j) v[j] = ld_stream_u64(in + base + j * kThreads + tid);
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < kSlices; ++j) vb[j] = valid[(base + j * kThreads + tid) >> 3];
+    }
+#pragma unroll
+    for (int j = 0; j < kSlices; ++j) {
+      ok[j] = lt64<kType>(v[j], thr);
+      if (valid) ok[j] = ok[j] && ((vb[j] >> ((base + j * kThreads + tid) & 7)) & 1);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kSlices; ++j) {
+      const int64_t i = base + j * kThreads + tid;
+      v[j] = i < n ? ld_stream_u64(in + i) : 0ull;
+      vb[j] = (valid && i < n) ? valid[i >> 3] : 0xffu;
+    }
+#pragma unroll
+    for (int j = 0; j < kSlices; ++j) {
+      const int64_t i = base + j * kThreads + tid;
+      ok[j] = i < n && lt64<kType>(v[j], thr) && ((vb[j] >> (i & 7)) & 1);
+    }
+  }
 }
 
 // Is row `i` of the packed column selected? (bit i of the packed validity bitmap, when there is one)
@@ -54,12 +95,11 @@ filter64_count_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t base = t * kTile;
     uint32_t c = 0;
+    uint64_t v[kSlices];
+    bool ok[kSlices];
+    load_tile<kType>(in, valid, base, n, tid, thr, v, ok);
 #pragma unroll
-    for (int j = 0; j < kSlices; ++j) {
-      const int64_t i = base + j * kThreads + tid;
-      uint64_t v;
-      if (i < n && selected<kType>(in, valid, i, thr, &v)) ++c;
-    }
+    for (int j = 0; j < kSlices; ++j) c += ok[j] ? 1u : 0u;
     c = warp_reduce_sum_u32(c);
     if (lane == 0) wsum[warp] = c;
     __syncthreads();
@@ -83,13 +123,13 @@ filter64_compact_kernel(const uint64_t* __restrict__ in, const uint8_t* __restri
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t base = t * kTile;
     uint64_t v[kSlices];
+    bool ok[kSlices];
     uint32_t rank[kSlices];  // rank inside the warp's 32 rows of slice j, or ~0: not selected
+    load_tile<kType>(in, valid, base, n, tid, thr, v, ok);
 #pragma unroll
     for (int j = 0; j < kSlices; ++j) {
-      const int64_t i = base + j * kThreads + tid;
-      const bool ok = i < n && selected<kType>(in, valid, i, thr, &v[j]);
-      const uint32_t m = __ballot_sync(0xffffffffu, ok);
-      rank[j] = ok ? (uint32_t)__popc(m & lt) : 0xffffffffu;
+      const uint32_t m = __ballot_sync(0xffffffffu, ok[j]);
+      rank[j] = ok[j] ? (uint32_t)__popc(m & lt) : 0xffffffffu;
       if (lane == 0) cnt[j * kWarps + warp] = (uint32_t)__popc(m);
     }
     __syncthreads();
@@ -112,6 +152,68 @@ filter64_compact_kernel(const uint64_t* __restrict__ in, const uint8_t* __restri
       if (rank[j] != 0xffffffffu) dst[cnt[j * kWarps + warp] + rank[j]] = v[j];
     __syncthreads();
   }
+}
+
+struct F64Head {
+  unsigned long long ticket;  // next tile
+  unsigned long long pad[7];
+};
+
+template <int kType>
+__global__ void __launch_bounds__(kThreads)
+filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid, int64_t n,
+                            uint64_t thr, int64_t ntiles, F64Head* __restrict__ head, uint64_t* __restrict__ desc,
+                            uint64_t* __restrict__ tile_off, uint64_t* __restrict__ out) {
+  __shared__ uint64_t stage[kTile];           // the tile's selected rows, compacted
+  __shared__ uint32_t cnt[kSlices * kWarps];  // selected rows of (slice j, warp w), in row order j * 8 + w
+  __shared__ int64_t s_tile;
+  __shared__ uint64_t s_excl;
+  __shared__ uint32_t s_total;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = lanemask_lt();
+  if (tid == 0) s_tile = (int64_t)atomicAdd(&head->ticket, 1ull);  // launch order: predecessors are resident
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t base = tile * kTile;
+  uint64_t v[kSlices];
+  bool ok[kSlices];
+  uint32_t rank[kSlices];  // rank inside the warp's 32 rows of slice j, or ~0: not selected
+  load_tile<kType>(in, valid, base, n, tid, thr, v, ok);
+#pragma unroll
+  for (int j = 0; j < kSlices; ++j) {
+    const uint32_t m = __ballot_sync(0xffffffffu, ok[j]);
+    rank[j] = ok[j] ? (uint32_t)__popc(m & lt) : 0xffffffffu;
+    if (lane == 0) cnt[j * kWarps + warp] = (uint32_t)__popc(m);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the 64 counts (two per lane), then the look-back
+    const uint32_t a = cnt[2 * lane], b = cnt[2 * lane + 1];
+    uint32_t incl = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    const uint32_t excl = incl - a - b;
+    cnt[2 * lane] = excl;
+    cnt[2 * lane + 1] = excl + a;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint64_t prefix = lookback(desc, tile, (uint64_t)total, nullptr);
+    if (lane == 0) {
+      s_excl = prefix;
+      s_total = total;
+      tile_off[tile] = prefix;
+      if (tile == ntiles - 1) tile_off[ntiles] = prefix + total;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kSlices; ++j)
+    if (rank[j] != 0xffffffffu) stage[cnt[j * kWarps + warp] + rank[j]] = v[j];
+  __syncthreads();
+  const uint32_t total = s_total;
+  uint64_t* __restrict__ dst = out + s_excl;
+  for (uint32_t i = tid; i < total; i += kThreads) dst[i] = stage[i];
 }
 
 // One warp per batch: rows selected in [0, batch_off[b + 1]) = offset of the tile the boundary falls
@@ -139,7 +241,10 @@ filter64_end_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__
 
 struct F64Layout {
   int64_t ntiles;
-  size_t off_cnt, off_scan, off_scanws, total;
+  // two-pass: tile counts | tile offsets | scan workspace; single pass: head | descriptors | tile offsets
+  size_t off_cnt, off_scan, off_scanws, two_pass_total;
+  size_t off_head, off_desc, off_tileoff, single_total;
+  size_t total;
 };
 F64Layout f64_layout(int64_t n) {
   F64Layout L;
@@ -148,7 +253,13 @@ F64Layout f64_layout(int64_t n) {
   L.off_cnt = o;    o += b2_align_up((size_t)(L.ntiles + 1) * 4, 256);
   L.off_scan = o;   o += b2_align_up((size_t)(L.ntiles + 1) * 8, 256);
   L.off_scanws = o; o += b2_align_up(b2_scan_ws_bytes(L.ntiles + 1), 256);
-  L.total = o;
+  L.two_pass_total = o;
+  o = 0;
+  L.off_head = o;    o += 256;
+  L.off_desc = o;    o += b2_align_up((size_t)(L.ntiles + 1) * 8, 256);
+  L.off_tileoff = o; o += b2_align_up((size_t)(L.ntiles + 1) * 8, 256);
+  L.single_total = o;
+  L.total = std::max(L.two_pass_total, L.single_total);
   return L;
 }
 
@@ -158,21 +269,37 @@ int filter64_impl(b2_ctx* ctx, const uint64_t* d_in, const uint8_t* d_valid, int
                   int64_t* d_batch_end, int64_t* d_total, void* d_ws, size_t ws_bytes, cudaStream_t s) {
   const F64Layout L = f64_layout(n);
   if (ws_bytes < L.total) return b2_set_error(ctx, B2_ERR_WORKSPACE, "64-bit filter", "use b2_filter_64_ws_bytes()");
+  B2_REQUIRE(ctx, L.ntiles < (1ll << 31), "column too large for one launch");
   char* base = static_cast<char*>(d_ws);
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(base + L.off_cnt);
-  uint64_t* off = reinterpret_cast<uint64_t*>(base + L.off_scan);
-  B2_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, (size_t)(L.ntiles + 1) * 4, s));
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(L.ntiles, (int64_t)ctx->sm_count * 8));
-  if (L.ntiles > 0) {
-    filter64_count_kernel<kType><<<grid, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, cnt);
-    B2_LAUNCH_CHECK(ctx, "filter64_count_kernel");
-  }
-  // ntiles + 1 entries: the last one is the total
-  B2_RETURN_NOT_OK(b2_exclusive_scan_u32_u64(ctx, cnt, off, L.ntiles + 1, base + L.off_scanws,
-                                             ws_bytes - L.off_scanws, s));
-  if (L.ntiles > 0) {
-    filter64_compact_kernel<kType><<<grid, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, off, d_out);
-    B2_LAUNCH_CHECK(ctx, "filter64_compact_kernel");
+  const uint64_t* off = nullptr;  // exclusive prefix per tile, entry ntiles = the total
+  if (ctx->tune[B2_TUNE_FILTER64_KERNEL] == 0) {
+    F64Head* head = reinterpret_cast<F64Head*>(base + L.off_head);
+    uint64_t* desc = reinterpret_cast<uint64_t*>(base + L.off_desc);
+    uint64_t* tile_off = reinterpret_cast<uint64_t*>(base + L.off_tileoff);
+    B2_CUDA_OK(ctx, cudaMemsetAsync(base, 0, L.single_total, s));  // ticket, descriptors, total of an empty column
+    if (L.ntiles > 0) {
+      filter64_single_pass_kernel<kType><<<(unsigned)L.ntiles, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, head,
+                                                                                 desc, tile_off, d_out);
+      B2_LAUNCH_CHECK(ctx, "filter64_single_pass_kernel");
+    }
+    off = tile_off;
+  } else {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(base + L.off_cnt);
+    uint64_t* scanned = reinterpret_cast<uint64_t*>(base + L.off_scan);
+    B2_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, (size_t)(L.ntiles + 1) * 4, s));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(L.ntiles, (int64_t)ctx->sm_count * 8));
+    if (L.ntiles > 0) {
+      filter64_count_kernel<kType><<<grid, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, cnt);
+      B2_LAUNCH_CHECK(ctx, "filter64_count_kernel");
+    }
+    // ntiles + 1 entries: the last one is the total
+    B2_RETURN_NOT_OK(b2_exclusive_scan_u32_u64(ctx, cnt, scanned, L.ntiles + 1, base + L.off_scanws,
+                                               ws_bytes - L.off_scanws, s));
+    if (L.ntiles > 0) {
+      filter64_compact_kernel<kType><<<grid, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, scanned, d_out);
+      B2_LAUNCH_CHECK(ctx, "filter64_compact_kernel");
+    }
+    off = scanned;
   }
   const int64_t warps = std::max<int64_t>(nbatches, 1);
   filter64_end_kernel<kType><<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, s>>>(

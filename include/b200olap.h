@@ -99,6 +99,8 @@ enum b2_tunable {
                                            other streams (the overlapped sharded join sets it around the probe side's scatter) */
   B2_TUNE_PEER_SCATTER_KERNEL = 7,      /* peer (NVLink) scatter: 0 = whole 128-byte lines stored by the threads (line carry),
                                            1 = whole 32-byte sectors, one copy-engine bulk copy per (bucket, tile) */
+  B2_TUNE_FILTER64_KERNEL = 8,          /* 64-bit filter (filter64.cu): 0 = single pass with decoupled look-back (8 + 8 s bytes per row),
+                                           1 = counted two-pass compaction (8 + 8 + 8 s) */
   B2_TUNE_JOIN_DIRECT_MIN_ROWS = 5      /* perfect-hash probe path (join.cu): used when <= 14 hash bits are left below the partition
                                            bits; the planner adds partition bits to get there while partitions keep at least this
                                            many build rows (2048), and takes fewer when 2^14-row partitions are enough. 0 = path off, 1 = always when the bits allow (tests). */

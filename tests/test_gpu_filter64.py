@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 _TILE = 2048  # rows per CTA tile of csrc/filter64.cu
 
 
+@pytest.fixture(params=[0, 1], ids=["single_pass", "two_pass"], autouse=True)
+def kernel(request, ctx):
+    """Every test runs through both kernels of csrc/filter64.cu (B2_TUNE_FILTER64_KERNEL)."""
+    from dpu_olap_b200._lib import TUNE_FILTER64_KERNEL
+    ctx.set_tunable(TUNE_FILTER64_KERNEL, request.param)
+    yield request.param
+    ctx.set_tunable(TUNE_FILTER64_KERNEL, 0)
+
+
 def _column(rng, dtype, n):
     if dtype == np.float64:
         v = rng.standard_normal(n) * 1e3
@@ -129,3 +138,21 @@ def test_filter_gpu_over_64bit_batches(ctx, dtype, thr, nulls):
         want_rows += len(exp)
     assert f.Run() == want_rows
     assert f.Timers() is not None
+
+
+def test_filter_64_single_pass_many_tiles_in_flight(ctx, kernel):
+    """2^25 rows = 16384 tiles: far more tiles than resident CTAs, so the look-back chain crosses many
+    waves; selectivity swings between runs of all-selected and none-selected tiles."""
+    n = 1 << 25
+    rng = np.random.default_rng(77)
+    v = rng.integers(-1000, 1000, size=n, dtype=np.int64)
+    v[: n // 4] = -5000                      # a long run of full tiles
+    v[n // 2: n // 2 + n // 8] = 5000        # and one of empty tiles
+    col = torch.from_numpy(v).cuda()
+    out, end, total = ctx.filter64_dev(col, np.int64, 0, nbatches=512, batch_len=n // 512)
+    torch.cuda.synchronize()
+    keep = v < 0
+    k = int(total.item())
+    assert k == int(keep.sum())
+    assert torch.equal(out[:k], col[torch.from_numpy(keep).cuda()])
+    assert np.array_equal(end.cpu().numpy(), np.cumsum(keep.reshape(512, -1).sum(axis=1)))
