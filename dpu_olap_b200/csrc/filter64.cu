@@ -21,6 +21,9 @@
 // Both leave the exclusive prefix of every tile (and the total as entry ntiles) in the workspace;
 // filter64_end_kernel turns them into batch_end[b] = rows selected up to the end of batch b (one warp
 // per batch recounts the part of the tile the boundary cuts) and the total.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -33,6 +36,7 @@ constexpr int kThreads = 256;
 constexpr int kSlices = 8;                       // rows per thread and tile
 constexpr int kTile = kThreads * kSlices;        // 2048 rows = 16 KB
 constexpr int kWarps = kThreads / 32;
+constexpr int kPrefetchTiles = 1;                // single-pass kernel: L2 request this many generations ahead
 
 template <int kType>
 __device__ __forceinline__ bool lt64(uint64_t a, uint64_t thr) {
@@ -41,39 +45,46 @@ __device__ __forceinline__ bool lt64(uint64_t a, uint64_t thr) {
   return a < thr;
 }
 
-// A tile's rows as the kernels hold them: thread t owns rows base + j * 256 + t. All loads are issued
-// before the first value is looked at (eight independent 8-byte loads in flight per thread); rows past
-// the end of the column are not loaded and never selected.
-template <int kType>
-__device__ __forceinline__ void load_tile(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid,
-                                          int64_t base, int64_t n, uint32_t tid, uint64_t thr,
+// A thread's rows of a tile: r0 + j * kStride, j = 0 .. 7. All loads are issued before the first value
+// is looked at (eight independent 8-byte loads in flight per thread); rows past the end of the column
+// are not loaded and never selected. `full`: the whole tile lies inside the column.
+template <int kType, int kStride>
+__device__ __forceinline__ void load_rows(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid,
+                                          int64_t r0, int64_t n, bool full, uint64_t thr,
                                           uint64_t (&v)[kSlices], bool (&ok)[kSlices]) {
   uint32_t vb[kSlices];
-  if (base + kTile <= n) {
+  if (full) {
 #pragma unroll
-    for (int j = 0; j < kSlices; ++j) v[j] = ld_stream_u64(in + base + j * kThreads + tid);
+    for (int j = 0; j < kSlices; ++j) v[j] = ld_stream_u64(in + r0 + j * kStride);
     if (valid) {
 #pragma unroll
-      for (int j = 0; j < kSlices; ++j) vb[j] = valid[(base + j * kThreads + tid) >> 3];
+      for (int j = 0; j < kSlices; ++j) vb[j] = valid[(r0 + j * kStride) >> 3];
     }
 #pragma unroll
     for (int j = 0; j < kSlices; ++j) {
       ok[j] = lt64<kType>(v[j], thr);
-      if (valid) ok[j] = ok[j] && ((vb[j] >> ((base + j * kThreads + tid) & 7)) & 1);
+      if (valid) ok[j] = ok[j] && ((vb[j] >> ((r0 + j * kStride) & 7)) & 1);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < kSlices; ++j) {
-      const int64_t i = base + j * kThreads + tid;
+      const int64_t i = r0 + j * kStride;
       v[j] = i < n ? ld_stream_u64(in + i) : 0ull;
       vb[j] = (valid && i < n) ? valid[i >> 3] : 0xffu;
     }
 #pragma unroll
     for (int j = 0; j < kSlices; ++j) {
-      const int64_t i = base + j * kThreads + tid;
+      const int64_t i = r0 + j * kStride;
       ok[j] = i < n && lt64<kType>(v[j], thr) && ((vb[j] >> (i & 7)) & 1);
     }
   }
+}
+// The two-pass kernels' layout: thread t owns rows base + j * 256 + t.
+template <int kType>
+__device__ __forceinline__ void load_tile(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid,
+                                          int64_t base, int64_t n, uint32_t tid, uint64_t thr,
+                                          uint64_t (&v)[kSlices], bool (&ok)[kSlices]) {
+  load_rows<kType, kThreads>(in, valid, base + tid, n, base + kTile <= n, thr, v, ok);
 }
 
 // Is row `i` of the packed column selected? (bit i of the packed validity bitmap, when there is one)
@@ -155,65 +166,154 @@ filter64_compact_kernel(const uint64_t* __restrict__ in, const uint8_t* __restri
 }
 
 struct F64Head {
-  unsigned long long ticket;  // next tile
+  unsigned long long ticket;  // CTA start ranks
   unsigned long long pad[7];
 };
 
+// Workspace words of the single-pass kernel (all zeroed per launch): the hierarchical counted sums of
+// lookback.cuh, as the 32-bit kernel uses them (filter.cu).
+struct F64Sums {
+  uint32_t* agg;       // [ntiles]            kAggFlag | rows selected in the tile
+  uint64_t* grp;       // [ntiles / 32 + 1]   contributors << 48 | rows selected in the group of 32 tiles
+  uint64_t* sgrp;      // [ntiles / 1024 + 1] the same per super-group of 1024 tiles
+  uint64_t* tile_off;  // [ntiles + 1]        out: rows selected before tile t; entry ntiles = the total
+};
+
+// Persistent CTAs, tiles dealt round-robin: the CTA that started v-th owns tiles v, v + G, v + 2G, ...
+// (G = grid size <= the number of CTAs the device holds at once), so all CTAs work on the same
+// generation of G consecutive tiles and nothing a tile waits for is far behind. Warp w of a CTA owns
+// rows [256 w, 256 w + 256) of the tile, so the ranks of a warp's selected rows need no shared memory
+// and the CTA-wide step is a sum over eight warp totals. Iteration k of a CTA, two barriers:
+//   A  issue the loads of tile k (registers); ask the copy engine for tile k + pf (L2 request)
+//   B  warp 0: global offset of tile k - 2 from the counted sums — the full super-groups before it (a
+//      running register), the <= 31 full groups before its group, the <= 31 tile counts before it in
+//      its group: two loads per lane, waiting only for earlier tiles to have been COUNTED, which the
+//      other CTAs did a whole iteration ago
+//   C  write tile k - 2's staged rows out as one contiguous run (under the latency of A's loads)
+//   D  rank tile k's selected rows inside each warp (one ballot per 32 rows), post the warp totals
+//   E  publish tile k's count (one store, two fire-and-forget adds)
+//   F  stage tile k's selected rows, compacted, in the buffer tile k - 2 just left
 template <int kType>
 __global__ void __launch_bounds__(kThreads)
 filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid, int64_t n,
-                            uint64_t thr, int64_t ntiles, F64Head* __restrict__ head, uint64_t* __restrict__ desc,
-                            uint64_t* __restrict__ tile_off, uint64_t* __restrict__ out) {
-  __shared__ uint64_t stage[kTile];           // the tile's selected rows, compacted
-  __shared__ uint32_t cnt[kSlices * kWarps];  // selected rows of (slice j, warp w), in row order j * 8 + w
-  __shared__ int64_t s_tile;
-  __shared__ uint64_t s_excl;
-  __shared__ uint32_t s_total;
+                            uint64_t thr, int64_t ntiles, F64Head* __restrict__ head, const F64Sums w,
+                            uint64_t* __restrict__ out, int pf) {
+  __shared__ uint64_t stage[2][kTile];  // a tile's selected rows, compacted
+  __shared__ uint32_t wtot[kWarps];     // selected rows per warp of the tile being ranked
+  __shared__ uint32_t s_total[2];
+  __shared__ uint64_t s_prefix;
+  __shared__ uint32_t s_first;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt = lanemask_lt();
-  if (tid == 0) s_tile = (int64_t)atomicAdd(&head->ticket, 1ull);  // launch order: predecessors are resident
+  if (tid == 0) s_first = (uint32_t)atomicAdd(&head->ticket, 1ull);
   __syncthreads();
-  const int64_t tile = s_tile;
-  const int64_t base = tile * kTile;
-  uint64_t v[kSlices];
-  bool ok[kSlices];
-  uint32_t rank[kSlices];  // rank inside the warp's 32 rows of slice j, or ~0: not selected
-  load_tile<kType>(in, valid, base, n, tid, thr, v, ok);
+  const int64_t stride = gridDim.x;
+  const int64_t first = s_first;
+  uint64_t base_sg = 0;  // warp 0: rows selected in the super-groups before `sg`
+  int64_t sg = 0;
+  for (int64_t k = 0;; ++k) {
+    const int64_t tile = first + k * stride;
+    const int64_t old = tile - 2 * stride;  // the tile leaving the pipeline in this iteration
+    const bool have = tile < ntiles;
+    if (old >= ntiles) break;  // the CTA's last tile has left the pipeline
+    const bool have_old = k >= 2;
+    const uint32_t b = (uint32_t)k & 1;
+    uint64_t v[kSlices];
+    uint32_t vbyte = 0xffu;  // lane l: byte l of the 32 validity bytes of the warp's 256 rows
+    const int64_t r0 = tile * kTile + warp * (kTile / kWarps) + lane;  // this thread's rows: r0 + 32 j
+    const bool full = (tile + 1) * kTile <= n;
+    if (have) {  // A: loads only — nothing looks at the values before D
+      const int64_t next = tile + pf * stride;
+      if (tid == 0 && pf > 0 && next < ntiles)
+        l2_prefetch(in + next * kTile, (int64_t)sizeof(uint64_t) * min((int64_t)kTile, n - next * kTile));
+      if (full) {
 #pragma unroll
-  for (int j = 0; j < kSlices; ++j) {
-    const uint32_t m = __ballot_sync(0xffffffffu, ok[j]);
-    rank[j] = ok[j] ? (uint32_t)__popc(m & lt) : 0xffffffffu;
-    if (lane == 0) cnt[j * kWarps + warp] = (uint32_t)__popc(m);
-  }
-  __syncthreads();
-  if (warp == 0) {  // exclusive scan of the 64 counts (two per lane), then the look-back
-    const uint32_t a = cnt[2 * lane], b = cnt[2 * lane + 1];
-    uint32_t incl = a + b;
+        for (int j = 0; j < kSlices; ++j) v[j] = ld_stream_u64(in + r0 + j * 32);
+      } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += x;
+        for (int j = 0; j < kSlices; ++j) v[j] = r0 + j * 32 < n ? ld_stream_u64(in + r0 + j * 32) : 0ull;
+      }
+      if (valid) {
+        const int64_t vb = ((r0 - lane) >> 3) + lane;
+        if (vb * 8 < n) vbyte = valid[vb];
+      }
     }
-    const uint32_t excl = incl - a - b;
-    cnt[2 * lane] = excl;
-    cnt[2 * lane + 1] = excl + a;
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint64_t prefix = lookback(desc, tile, (uint64_t)total, nullptr);
-    if (lane == 0) {
-      s_excl = prefix;
-      s_total = total;
-      tile_off[tile] = prefix;
-      if (tile == ntiles - 1) tile_off[ntiles] = prefix + total;
+    if (have_old && warp == 0) {  // B
+      while (sg < (old >> kSuperShift)) {  // super-groups not folded into the base yet
+        uint64_t sw = 0;
+        if (lane == 0)
+          while (((sw = ld_relaxed_gpu_u64(w.sgrp + sg)) >> 48) != (1u << kSuperShift)) __nanosleep(100);
+        base_sg += __shfl_sync(0xffffffffu, sw, 0) & kSumMask;
+        ++sg;
+      }
+      const int64_t g0 = sg << (kSuperShift - kGroupShift);   // first group of the super-group
+      const int ng = (int)((old >> kGroupShift) - g0);         // full groups before the tile's group
+      const int64_t t0 = (old >> kGroupShift) << kGroupShift;  // first tile of the tile's group
+      const int na = (int)(old - t0);                          // tiles of the group before the tile
+      uint64_t prefix;
+      uint32_t ns = 32;
+      while (true) {
+        uint64_t gw = 0;
+        uint32_t aw = kAggFlag;
+        if ((int)lane < ng) gw = ld_relaxed_gpu_u64(w.grp + g0 + lane);
+        if ((int)lane < na) aw = ld_relaxed_gpu_u32(w.agg + t0 + lane);
+        const bool ready = ((int)lane >= ng || (gw >> 48) == (1u << kGroupShift)) && (aw & kAggFlag);
+        if (__all_sync(0xffffffffu, ready)) {
+          prefix = base_sg + warp_reduce_sum_u64((gw & kSumMask) + (aw & ~kAggFlag));
+          break;
+        }
+        __nanosleep(ns);
+        if (ns < 256) ns <<= 1;
+      }
+      if (lane == 0) {
+        s_prefix = prefix;
+        w.tile_off[old] = prefix;
+        if (old == ntiles - 1) w.tile_off[ntiles] = prefix + s_total[b];
+      }
+    }
+    __syncthreads();  // #1: offset posted; tile k - 1's staging and total (previous iteration) are visible too
+    if (have_old) {   // C
+      const uint32_t total = s_total[b];
+      uint64_t* __restrict__ dst = out + s_prefix;
+      const uint64_t* __restrict__ src = stage[b];
+      for (uint32_t i = tid; i < total; i += kThreads) dst[i] = src[i];
+    }
+    uint32_t rank[kSlices];  // position among the warp's selected rows, or ~0: not selected
+    if (have) {              // D
+      uint32_t run = 0;
+#pragma unroll
+      for (int j = 0; j < kSlices; ++j) {
+        bool ok = lt64<kType>(v[j], thr) && (full || r0 + j * 32 < n);
+        if (valid) {  // row 32 j + lane of the warp's 256: bit lane & 7 of byte 4 j + lane / 8
+          const uint32_t byte = __shfl_sync(0xffffffffu, vbyte, 4 * j + (lane >> 3));
+          ok = ok && ((byte >> (lane & 7)) & 1);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        rank[j] = ok ? run + (uint32_t)__popc(m & lt) : 0xffffffffu;
+        run += (uint32_t)__popc(m);
+      }
+      if (lane == 0) wtot[warp] = run;
+    }
+    __syncthreads();  // #2: warp totals posted; stage[b] has been read out
+    if (have) {       // E, F
+      uint32_t before = 0, total = 0;
+#pragma unroll
+      for (int x = 0; x < kWarps; ++x) {
+        const uint32_t t = wtot[x];
+        before += x < (int)warp ? t : 0u;
+        total += t;
+      }
+      if (tid == 0) {
+        s_total[b] = total;
+        st_relaxed_gpu_u32(w.agg + tile, kAggFlag | total);
+        red_add_relaxed_gpu_u64(w.grp + (tile >> kGroupShift), (1ull << 48) | total);
+        red_add_relaxed_gpu_u64(w.sgrp + (tile >> kSuperShift), (1ull << 48) | total);
+      }
+#pragma unroll
+      for (int j = 0; j < kSlices; ++j)
+        if (rank[j] != 0xffffffffu) stage[b][before + rank[j]] = v[j];
     }
   }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < kSlices; ++j)
-    if (rank[j] != 0xffffffffu) stage[cnt[j * kWarps + warp] + rank[j]] = v[j];
-  __syncthreads();
-  const uint32_t total = s_total;
-  uint64_t* __restrict__ dst = out + s_excl;
-  for (uint32_t i = tid; i < total; i += kThreads) dst[i] = stage[i];
 }
 
 // One warp per batch: rows selected in [0, batch_off[b + 1]) = offset of the tile the boundary falls
@@ -241,9 +341,9 @@ filter64_end_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__
 
 struct F64Layout {
   int64_t ntiles;
-  // two-pass: tile counts | tile offsets | scan workspace; single pass: head | descriptors | tile offsets
+  // two-pass: tile counts | tile offsets | scan workspace; single pass: head | counted sums | tile offsets
   size_t off_cnt, off_scan, off_scanws, two_pass_total;
-  size_t off_head, off_desc, off_tileoff, single_total;
+  size_t off_head, off_agg, off_grp, off_sgrp, off_tileoff, single_total;
   size_t total;
 };
 F64Layout f64_layout(int64_t n) {
@@ -256,7 +356,9 @@ F64Layout f64_layout(int64_t n) {
   L.two_pass_total = o;
   o = 0;
   L.off_head = o;    o += 256;
-  L.off_desc = o;    o += b2_align_up((size_t)(L.ntiles + 1) * 8, 256);
+  L.off_agg = o;     o += b2_align_up((size_t)(L.ntiles + 1) * 4, 256);
+  L.off_grp = o;     o += b2_align_up((size_t)((L.ntiles >> kGroupShift) + 1) * 8, 256);
+  L.off_sgrp = o;    o += b2_align_up((size_t)((L.ntiles >> kSuperShift) + 1) * 8, 256);
   L.off_tileoff = o; o += b2_align_up((size_t)(L.ntiles + 1) * 8, 256);
   L.single_total = o;
   L.total = std::max(L.two_pass_total, L.single_total);
@@ -274,12 +376,33 @@ int filter64_impl(b2_ctx* ctx, const uint64_t* d_in, const uint8_t* d_valid, int
   const uint64_t* off = nullptr;  // exclusive prefix per tile, entry ntiles = the total
   if (ctx->tune[B2_TUNE_FILTER64_KERNEL] == 0) {
     F64Head* head = reinterpret_cast<F64Head*>(base + L.off_head);
-    uint64_t* desc = reinterpret_cast<uint64_t*>(base + L.off_desc);
-    uint64_t* tile_off = reinterpret_cast<uint64_t*>(base + L.off_tileoff);
-    B2_CUDA_OK(ctx, cudaMemsetAsync(base, 0, L.single_total, s));  // ticket, descriptors, total of an empty column
+    F64Sums w;
+    w.agg = reinterpret_cast<uint32_t*>(base + L.off_agg);
+    w.grp = reinterpret_cast<uint64_t*>(base + L.off_grp);
+    w.sgrp = reinterpret_cast<uint64_t*>(base + L.off_sgrp);
+    w.tile_off = reinterpret_cast<uint64_t*>(base + L.off_tileoff);
+    uint64_t* tile_off = w.tile_off;
+    B2_CUDA_OK(ctx, cudaMemsetAsync(base, 0, L.single_total, s));  // start ranks, counted sums, total of an empty column
     if (L.ntiles > 0) {
-      filter64_single_pass_kernel<kType><<<(unsigned)L.ntiles, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, head,
-                                                                                 desc, tile_off, d_out);
+      // every CTA waits for tiles of the others: the grid must be resident as a whole
+      static const int seen = b2_new_site();
+      if (b2_first_use_on_device(ctx, seen)) {
+        int per_sm = 0;
+        B2_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter64_single_pass_kernel<kType>,
+                                                                      kThreads, 0));
+        if (per_sm < 1) return b2_set_error(ctx, B2_ERR_CUDA, "64-bit filter kernel", "does not fit an SM");
+        ctx->site_value[(size_t)seen] = per_sm * ctx->sm_count;
+      }
+      int64_t grid = std::min<int64_t>(L.ntiles, ctx->site_value[(size_t)seen]);
+      int pf = kPrefetchTiles;
+#ifdef B2_LAB
+      if (const char* e = getenv("B2_LAB_F64")) {  // "prefetch distance,CTAs per SM" (tools/filter64_lab.py)
+        int ctas = 0;
+        if (sscanf(e, "%d,%d", &pf, &ctas) == 2 && ctas > 0) grid = std::min<int64_t>(grid, (int64_t)ctas * ctx->sm_count);
+      }
+#endif
+      filter64_single_pass_kernel<kType><<<(unsigned)grid, kThreads, 0, s>>>(d_in, d_valid, n, thr, L.ntiles, head, w,
+                                                                             d_out, pf);
       B2_LAUNCH_CHECK(ctx, "filter64_single_pass_kernel");
     }
     off = tile_off;
