@@ -181,27 +181,83 @@ struct F64Sums {
 
 // Persistent CTAs, tiles dealt round-robin: the CTA that started v-th owns tiles v, v + G, v + 2G, ...
 // (G = grid size <= the number of CTAs the device holds at once), so all CTAs work on the same
-// generation of G consecutive tiles and nothing a tile waits for is far behind. Warp w of a CTA owns
-// rows [256 w, 256 w + 256) of the tile, so the ranks of a warp's selected rows need no shared memory
-// and the CTA-wide step is a sum over eight warp totals. Iteration k of a CTA, two barriers:
+// generation of G consecutive tiles. Warp w of a CTA owns rows [256 w, 256 w + 256) of the tile, so the
+// ranks of a warp's selected rows need no shared memory and the CTA-wide step is a sum over eight
+// warp totals.
+//
+// A tile's global offset follows from the counted sums — the full super-groups before it (a running
+// register), the <= 31 full groups before its group, the <= 31 tile counts before it in its group:
+// two loads per lane — once every EARLIER tile has been counted. Nothing forces a CTA to wait for
+// that: the selected rows of a counted tile sit compacted in a shared-memory ring (kRing rows) with a
+// queue entry (ring position, rows), and a tile is RETIRED (offset computed, rows written out as one
+// contiguous run) in a later iteration, whenever its offset has become computable. Only when the ring
+// cannot take another full tile, or the queue is full, or the CTA has run out of tiles, does warp 0
+// block for the oldest entry. At 25 % selected the ring holds eight tiles, so a CTA can run up to
+// eight generations ahead of the slowest one; at 100 % it degrades to a lag of one tile.
+//
+// Iteration k of a CTA, two barriers:
 //   A  issue the loads of tile k (registers); ask the copy engine for tile k + pf (L2 request)
-//   B  warp 0: global offset of tile k - 2 from the counted sums — the full super-groups before it (a
-//      running register), the <= 31 full groups before its group, the <= 31 tile counts before it in
-//      its group: two loads per lane, waiting only for earlier tiles to have been COUNTED, which the
-//      other CTAs did a whole iteration ago
-//   C  write tile k - 2's staged rows out as one contiguous run (under the latency of A's loads)
+//   B  warp 0: offsets of the queue entries that can (or must) be retired
+//   C  write the retired tiles' rows out (under the latency of A's loads)
 //   D  rank tile k's selected rows inside each warp (one ballot per 32 rows), post the warp totals
-//   E  publish tile k's count (one store, two fire-and-forget adds)
-//   F  stage tile k's selected rows, compacted, in the buffer tile k - 2 just left
+//   E  publish tile k's count (one store, two fire-and-forget adds), queue entry
+//   F  stage tile k's selected rows in the ring
+constexpr int kRing = 4096;  // rows of the staging ring (32 KB): at least one tile
+constexpr int kQueue = 16;   // tiles a CTA may have counted but not written out
+static_assert(kRing >= kTile && (kRing & (kRing - 1)) == 0 && (kQueue & (kQueue - 1)) == 0, "ring geometry");
+
+struct F64Prefix {  // warp 0's running state
+  uint64_t base_sg = 0;  // rows selected in the super-groups before `sg`
+  int64_t sg = 0;
+};
+// Executed by warp 0: global offset of `tile` if every earlier tile has been counted (waits for that
+// when `block`). Returns false when it has not (and !block).
+__device__ __forceinline__ bool f64_tile_offset(const F64Sums& w, F64Prefix& st, int64_t tile, bool block,
+                                                uint32_t lane, uint64_t* prefix) {
+  while (st.sg < (tile >> kSuperShift)) {  // super-groups not folded into the base yet
+    uint64_t sw = 0;
+    if (lane == 0) {
+      while (((sw = ld_relaxed_gpu_u64(w.sgrp + st.sg)) >> 48) != (1u << kSuperShift)) {
+        if (!block) break;
+        __nanosleep(64);
+      }
+    }
+    sw = __shfl_sync(0xffffffffu, sw, 0);
+    if ((sw >> 48) != (1u << kSuperShift)) return false;
+    st.base_sg += sw & kSumMask;
+    ++st.sg;
+  }
+  const int64_t g0 = st.sg << (kSuperShift - kGroupShift);  // first group of the super-group
+  const int ng = (int)((tile >> kGroupShift) - g0);          // full groups before the tile's group
+  const int64_t t0 = (tile >> kGroupShift) << kGroupShift;   // first tile of the tile's group
+  const int na = (int)(tile - t0);                           // tiles of the group before the tile
+  uint32_t ns = 32;
+  while (true) {
+    uint64_t gw = 0;
+    uint32_t aw = kAggFlag;
+    if ((int)lane < ng) gw = ld_relaxed_gpu_u64(w.grp + g0 + lane);
+    if ((int)lane < na) aw = ld_relaxed_gpu_u32(w.agg + t0 + lane);
+    const bool ready = ((int)lane >= ng || (gw >> 48) == (1u << kGroupShift)) && (aw & kAggFlag);
+    if (__all_sync(0xffffffffu, ready)) {
+      *prefix = st.base_sg + warp_reduce_sum_u64((gw & kSumMask) + (aw & ~kAggFlag));
+      return true;
+    }
+    if (!block) return false;
+    __nanosleep(ns);
+    if (ns < 256) ns <<= 1;
+  }
+}
+
 template <int kType>
 __global__ void __launch_bounds__(kThreads)
 filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __restrict__ valid, int64_t n,
                             uint64_t thr, int64_t ntiles, F64Head* __restrict__ head, const F64Sums w,
                             uint64_t* __restrict__ out, int pf) {
-  __shared__ uint64_t stage[2][kTile];  // a tile's selected rows, compacted
-  __shared__ uint32_t wtot[kWarps];     // selected rows per warp of the tile being ranked
-  __shared__ uint32_t s_total[2];
-  __shared__ uint64_t s_prefix;
+  __shared__ uint64_t ring[kRing];       // selected rows of the counted tiles, compacted, in tile order
+  __shared__ uint64_t q_prefix[kQueue];  // queue entry -> global offset (filled when retired)
+  __shared__ uint32_t q_total[kQueue];   // queue entry -> rows
+  __shared__ uint32_t wtot[kWarps];      // selected rows per warp of the tile being ranked
+  __shared__ uint32_t s_nret;
   __shared__ uint32_t s_first;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt = lanemask_lt();
@@ -209,15 +265,14 @@ filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __re
   __syncthreads();
   const int64_t stride = gridDim.x;
   const int64_t first = s_first;
-  uint64_t base_sg = 0;  // warp 0: rows selected in the super-groups before `sg`
-  int64_t sg = 0;
+  F64Prefix st;
+  // uniform across the CTA: queue entries [qh, qt) are pending, entry e belongs to tile first + e * stride;
+  // their rows occupy ring positions [r_tail, r_tail + used), oldest first
+  uint32_t qh = 0, qt = 0, r_tail = 0, used = 0;
   for (int64_t k = 0;; ++k) {
     const int64_t tile = first + k * stride;
-    const int64_t old = tile - 2 * stride;  // the tile leaving the pipeline in this iteration
     const bool have = tile < ntiles;
-    if (old >= ntiles) break;  // the CTA's last tile has left the pipeline
-    const bool have_old = k >= 2;
-    const uint32_t b = (uint32_t)k & 1;
+    if (!have && qh == qt) break;
     uint64_t v[kSlices];
     uint32_t vbyte = 0xffu;  // lane l: byte l of the 32 validity bytes of the warp's 256 rows
     const int64_t r0 = tile * kTile + warp * (kTile / kWarps) + lane;  // this thread's rows: r0 + 32 j
@@ -238,52 +293,47 @@ filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __re
         if (vb * 8 < n) vbyte = valid[vb];
       }
     }
-    if (have_old && warp == 0) {  // B
-      while (sg < (old >> kSuperShift)) {  // super-groups not folded into the base yet
-        uint64_t sw = 0;
-        if (lane == 0)
-          while (((sw = ld_relaxed_gpu_u64(w.sgrp + sg)) >> 48) != (1u << kSuperShift)) __nanosleep(100);
-        base_sg += __shfl_sync(0xffffffffu, sw, 0) & kSumMask;
-        ++sg;
-      }
-      const int64_t g0 = sg << (kSuperShift - kGroupShift);   // first group of the super-group
-      const int ng = (int)((old >> kGroupShift) - g0);         // full groups before the tile's group
-      const int64_t t0 = (old >> kGroupShift) << kGroupShift;  // first tile of the tile's group
-      const int na = (int)(old - t0);                          // tiles of the group before the tile
-      uint64_t prefix;
-      uint32_t ns = 32;
-      while (true) {
-        uint64_t gw = 0;
-        uint32_t aw = kAggFlag;
-        if ((int)lane < ng) gw = ld_relaxed_gpu_u64(w.grp + g0 + lane);
-        if ((int)lane < na) aw = ld_relaxed_gpu_u32(w.agg + t0 + lane);
-        const bool ready = ((int)lane >= ng || (gw >> 48) == (1u << kGroupShift)) && (aw & kAggFlag);
-        if (__all_sync(0xffffffffu, ready)) {
-          prefix = base_sg + warp_reduce_sum_u64((gw & kSumMask) + (aw & ~kAggFlag));
-          break;
+    if (warp == 0) {  // B: retire what can be retired; block only for what must be
+      __syncwarp();   // lane 0 pushed the newest queue entry
+      uint32_t nret = 0, u = used;
+      while (qh + nret != qt) {
+        const uint32_t e = (qh + nret) & (kQueue - 1);
+        const bool must = !have || u + kTile > kRing || qt - (qh + nret) == kQueue;
+        const int64_t t = first + (int64_t)(qh + nret) * stride;
+        uint64_t prefix;
+        if (!f64_tile_offset(w, st, t, must, lane, &prefix)) break;
+        const uint32_t total = q_total[e];
+        if (lane == 0) {
+          q_prefix[e] = prefix;
+          w.tile_off[t] = prefix;
+          if (t == ntiles - 1) w.tile_off[ntiles] = prefix + total;
         }
-        __nanosleep(ns);
-        if (ns < 256) ns <<= 1;
+        u -= total;
+        ++nret;
       }
-      if (lane == 0) {
-        s_prefix = prefix;
-        w.tile_off[old] = prefix;
-        if (old == ntiles - 1) w.tile_off[ntiles] = prefix + s_total[b];
-      }
+      if (lane == 0) s_nret = nret;
     }
-    __syncthreads();  // #1: offset posted; tile k - 1's staging and total (previous iteration) are visible too
-    if (have_old) {   // C
-      const uint32_t total = s_total[b];
-      uint64_t* __restrict__ dst = out + s_prefix;
-      const uint64_t* __restrict__ src = stage[b];
-      for (uint32_t i = tid; i < total; i += kThreads) dst[i] = src[i];
+    __syncthreads();  // #1: retired offsets posted; the previous iteration's staging and queue entry are visible
+    {                 // C
+      const uint32_t nret = s_nret;
+      for (uint32_t x = 0; x < nret; ++x) {
+        const uint32_t e = (qh + x) & (kQueue - 1);
+        const uint32_t total = q_total[e];
+        uint64_t* __restrict__ dst = out + q_prefix[e];
+        for (uint32_t i = tid; i < total; i += kThreads) dst[i] = ring[(r_tail + i) & (kRing - 1)];
+        r_tail = (r_tail + total) & (kRing - 1);
+        used -= total;
+      }
+      qh += nret;
     }
     uint32_t rank[kSlices];  // position among the warp's selected rows, or ~0: not selected
     if (have) {              // D
+      const uint32_t lrow = warp * (kTile / kWarps) + lane;  // this thread's first row inside the tile
+      const uint32_t limit = full ? (uint32_t)kTile : (uint32_t)(n - tile * kTile);
       uint32_t run = 0;
 #pragma unroll
       for (int j = 0; j < kSlices; ++j) {
-        bool ok = lt64<kType>(v[j], thr) && (full || r0 + j * 32 < n);
+        bool ok = lt64<kType>(v[j], thr) && lrow + 32 * j < limit;
         if (valid) {  // row 32 j + lane of the warp's 256: bit lane & 7 of byte 4 j + lane / 8
           const uint32_t byte = __shfl_sync(0xffffffffu, vbyte, 4 * j + (lane >> 3));
           ok = ok && ((byte >> (lane & 7)) & 1);
@@ -294,7 +344,7 @@ filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __re
       }
       if (lane == 0) wtot[warp] = run;
     }
-    __syncthreads();  // #2: warp totals posted; stage[b] has been read out
+    __syncthreads();  // #2: warp totals posted; the retired rows have left the ring
     if (have) {       // E, F
       uint32_t before = 0, total = 0;
 #pragma unroll
@@ -304,14 +354,17 @@ filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __re
         total += t;
       }
       if (tid == 0) {
-        s_total[b] = total;
+        q_total[qt & (kQueue - 1)] = total;
         st_relaxed_gpu_u32(w.agg + tile, kAggFlag | total);
         red_add_relaxed_gpu_u64(w.grp + (tile >> kGroupShift), (1ull << 48) | total);
         red_add_relaxed_gpu_u64(w.sgrp + (tile >> kSuperShift), (1ull << 48) | total);
       }
+      const uint32_t at = r_tail + used + before;  // the ring's head + the share of the warps before this one
 #pragma unroll
       for (int j = 0; j < kSlices; ++j)
-        if (rank[j] != 0xffffffffu) stage[b][before + rank[j]] = v[j];
+        if (rank[j] != 0xffffffffu) ring[(at + rank[j]) & (kRing - 1)] = v[j];
+      used += total;
+      ++qt;
     }
   }
 }
