@@ -181,9 +181,10 @@ struct F64Sums {
 
 // Persistent CTAs, tiles dealt round-robin: the CTA that started v-th owns tiles v, v + G, v + 2G, ...
 // (G = grid size <= the number of CTAs the device holds at once), so all CTAs work on the same
-// generation of G consecutive tiles. Warp w of a CTA owns rows [256 w, 256 w + 256) of the tile, so the
-// ranks of a warp's selected rows need no shared memory and the CTA-wide step is a sum over eight
-// warp totals.
+// generation of G consecutive tiles. Warp w of a CTA owns rows [256 w, 256 w + 256) of the tile in four
+// segments of 64 rows; a lane owns two adjacent rows of each segment (one 128-bit load). Its per-segment
+// counts (0..2) travel as the four bytes of ONE register through a single five-step shuffle scan, which
+// ranks all 256 rows of the warp; the CTA-wide step is a sum over eight warp totals.
 //
 // A tile's global offset follows from the counted sums — the full super-groups before it (a running
 // register), the <= 31 full groups before its group, the <= 31 tile counts before it in its group:
@@ -199,7 +200,7 @@ struct F64Sums {
 //   A  issue the loads of tile k (registers); ask the copy engine for tile k + pf (L2 request)
 //   B  warp 0: offsets of the queue entries that can (or must) be retired
 //   C  write the retired tiles' rows out (under the latency of A's loads)
-//   D  rank tile k's selected rows inside each warp (one ballot per 32 rows), post the warp totals
+//   D  rank tile k's selected rows inside each warp (packed scan), post the warp totals
 //   E  publish tile k's count (one store, two fire-and-forget adds), queue entry
 //   F  stage tile k's selected rows in the ring
 constexpr int kRing = 4096;  // rows of the staging ring (32 KB): at least one tile
@@ -256,40 +257,52 @@ filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __re
   __shared__ uint64_t ring[kRing];       // selected rows of the counted tiles, compacted, in tile order
   __shared__ uint64_t q_prefix[kQueue];  // queue entry -> global offset (filled when retired)
   __shared__ uint32_t q_total[kQueue];   // queue entry -> rows
-  __shared__ uint32_t wtot[kWarps];      // selected rows per warp of the tile being ranked
+  __shared__ __align__(16) uint32_t wtot[kWarps];  // selected rows per warp of the tile being ranked
   __shared__ uint32_t s_nret;
   __shared__ uint32_t s_first;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt = lanemask_lt();
   if (tid == 0) s_first = (uint32_t)atomicAdd(&head->ticket, 1ull);
   __syncthreads();
   const int64_t stride = gridDim.x;
   const int64_t first = s_first;
+  const bool al16 = (reinterpret_cast<uintptr_t>(in) & 15) == 0;  // row pairs can be loaded as 128-bit words
   F64Prefix st;
   // uniform across the CTA: queue entries [qh, qt) are pending, entry e belongs to tile first + e * stride;
   // their rows occupy ring positions [r_tail, r_tail + used), oldest first
   uint32_t qh = 0, qt = 0, r_tail = 0, used = 0;
+  // this thread's rows inside a tile: lrow + 64 j + e (j = 0..3 segments of 64 rows per warp, e = 0, 1)
+  const uint32_t lrow = warp * (kTile / kWarps) + 2 * lane;
   for (int64_t k = 0;; ++k) {
     const int64_t tile = first + k * stride;
     const bool have = tile < ntiles;
     if (!have && qh == qt) break;
-    uint64_t v[kSlices];
+    uint64_t v[kSlices];     // v[2 j + e]
     uint32_t vbyte = 0xffu;  // lane l: byte l of the 32 validity bytes of the warp's 256 rows
-    const int64_t r0 = tile * kTile + warp * (kTile / kWarps) + lane;  // this thread's rows: r0 + 32 j
-    const bool full = (tile + 1) * kTile <= n;
+    const int64_t row0 = tile * kTile;
+    const uint32_t limit = (tile + 1) * kTile <= n ? (uint32_t)kTile : (uint32_t)(have ? n - row0 : 0);
     if (have) {  // A: loads only — nothing looks at the values before D
-      const int64_t next = tile + pf * stride;
-      if (tid == 0 && pf > 0 && next < ntiles)
-        l2_prefetch(in + next * kTile, (int64_t)sizeof(uint64_t) * min((int64_t)kTile, n - next * kTile));
-      if (full) {
+      if (warp == 0) {
+        const int64_t next = tile + pf * stride;
+        if (lane == 0 && pf > 0 && next < ntiles)
+          l2_prefetch(in + next * kTile, (int64_t)sizeof(uint64_t) * min((int64_t)kTile, n - next * kTile));
+      }
+      const uint64_t* p = in + row0 + lrow;
+      if (limit == kTile && al16) {
 #pragma unroll
-        for (int j = 0; j < kSlices; ++j) v[j] = ld_stream_u64(in + r0 + j * 32);
+        for (int j = 0; j < kSlices / 2; ++j) {
+          const uint4 q = ld_stream_v4(reinterpret_cast<const uint4*>(p + 64 * j));
+          v[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+          v[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < kSlices; ++j) v[j] = r0 + j * 32 < n ? ld_stream_u64(in + r0 + j * 32) : 0ull;
+        for (int j = 0; j < kSlices / 2; ++j) {
+          v[2 * j] = lrow + 64 * j < limit ? ld_stream_u64(p + 64 * j) : 0ull;
+          v[2 * j + 1] = lrow + 64 * j + 1 < limit ? ld_stream_u64(p + 64 * j + 1) : 0ull;
+        }
       }
       if (valid) {
-        const int64_t vb = ((r0 - lane) >> 3) + lane;
+        const int64_t vb = ((row0 + warp * (kTile / kWarps)) >> 3) + lane;
         if (vb * 8 < n) vbyte = valid[vb];
       }
     }
@@ -319,39 +332,60 @@ filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __re
       for (uint32_t x = 0; x < nret; ++x) {
         const uint32_t e = (qh + x) & (kQueue - 1);
         const uint32_t total = q_total[e];
-        uint64_t* __restrict__ dst = out + q_prefix[e];
-        for (uint32_t i = tid; i < total; i += kThreads) dst[i] = ring[(r_tail + i) & (kRing - 1)];
+        uint64_t* __restrict__ dst = out + q_prefix[e] + tid;
+#pragma unroll 1
+        for (uint32_t i = tid; i < total; i += kThreads, dst += kThreads) *dst = ring[(r_tail + i) & (kRing - 1)];
         r_tail = (r_tail + total) & (kRing - 1);
         used -= total;
       }
       qh += nret;
     }
-    uint32_t rank[kSlices];  // position among the warp's selected rows, or ~0: not selected
-    if (have) {              // D
-      const uint32_t lrow = warp * (kTile / kWarps) + lane;  // this thread's first row inside the tile
-      const uint32_t limit = full ? (uint32_t)kTile : (uint32_t)(n - tile * kTile);
-      uint32_t run = 0;
+    // D: which of this lane's 8 rows are selected (bit 2 j + e), how many per segment (byte j of c: 0..2),
+    // and ONE packed shuffle scan over the lanes for all four segments
+    uint32_t okm = 0, pos = 0;
+    if (have) {
 #pragma unroll
-      for (int j = 0; j < kSlices; ++j) {
-        bool ok = lt64<kType>(v[j], thr) && lrow + 32 * j < limit;
-        if (valid) {  // row 32 j + lane of the warp's 256: bit lane & 7 of byte 4 j + lane / 8
-          const uint32_t byte = __shfl_sync(0xffffffffu, vbyte, 4 * j + (lane >> 3));
-          ok = ok && ((byte >> (lane & 7)) & 1);
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        rank[j] = ok ? run + (uint32_t)__popc(m & lt) : 0xffffffffu;
-        run += (uint32_t)__popc(m);
+      for (int x = 0; x < kSlices; ++x) okm |= lt64<kType>(v[x], thr) ? 1u << x : 0u;
+      if (limit != kTile) {  // the column's last tile: rows past its end are not selected
+#pragma unroll
+        for (int x = 0; x < kSlices; ++x)
+          if (lrow + 64 * (x >> 1) + (x & 1) >= limit) okm &= ~(1u << x);
       }
-      if (lane == 0) wtot[warp] = run;
+      if (valid) {  // rows 64 j + 2 lane + e of the warp's 256: bits 2 (lane & 3) + e of byte 8 j + lane / 4
+        uint32_t vm = 0;
+#pragma unroll
+        for (int j = 0; j < kSlices / 2; ++j) {
+          const uint32_t byte = __shfl_sync(0xffffffffu, vbyte, 8 * j + (lane >> 2));
+          vm |= ((byte >> (2 * (lane & 3))) & 3u) << (2 * j);
+        }
+        okm &= vm;
+      }
+      const uint32_t pair = (okm & 0x55u) + ((okm >> 1) & 0x55u);  // 2-bit counts of the four segments
+      const uint32_t c = (pair & 3u) | ((pair & 0xcu) << 6) | ((pair & 0x30u) << 12) | ((pair & 0xc0u) << 18);
+      uint32_t incl = c;  // bytewise: no segment of 64 rows overflows a byte
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const uint32_t seg = __shfl_sync(0xffffffffu, incl, 31);  // rows selected per segment (<= 64 each)
+      // position of this lane's first selected row of segment j among the warp's selected rows:
+      // rows of the segments before (<= 192) + rows of the lanes before in this segment (<= 62)
+      pos = (incl - c) + ((seg << 8) + (seg << 16) + (seg << 24));
+      if (lane == 0) wtot[warp] = (seg & 0xff) + ((seg >> 8) & 0xff) + ((seg >> 16) & 0xff) + (seg >> 24);
     }
     __syncthreads();  // #2: warp totals posted; the retired rows have left the ring
     if (have) {       // E, F
       uint32_t before = 0, total = 0;
+      {
+        static_assert(kWarps == 8, "two 128-bit loads");
+        const uint4 a = *reinterpret_cast<const uint4*>(wtot), c = *reinterpret_cast<const uint4*>(wtot + 4);
+        const uint32_t t[kWarps] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-      for (int x = 0; x < kWarps; ++x) {
-        const uint32_t t = wtot[x];
-        before += x < (int)warp ? t : 0u;
-        total += t;
+        for (int x = 0; x < kWarps; ++x) {
+          before += x < (int)warp ? t[x] : 0u;
+          total += t[x];
+        }
       }
       if (tid == 0) {
         q_total[qt & (kQueue - 1)] = total;
@@ -361,8 +395,11 @@ filter64_single_pass_kernel(const uint64_t* __restrict__ in, const uint8_t* __re
       }
       const uint32_t at = r_tail + used + before;  // the ring's head + the share of the warps before this one
 #pragma unroll
-      for (int j = 0; j < kSlices; ++j)
-        if (rank[j] != 0xffffffffu) ring[(at + rank[j]) & (kRing - 1)] = v[j];
+      for (int j = 0; j < kSlices / 2; ++j) {
+        uint32_t at_j = at + ((pos >> (8 * j)) & 0xffu);
+        if (okm & (1u << (2 * j))) ring[at_j++ & (kRing - 1)] = v[2 * j];
+        if (okm & (2u << (2 * j))) ring[at_j & (kRing - 1)] = v[2 * j + 1];
+      }
       used += total;
       ++qt;
     }
