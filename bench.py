@@ -476,7 +476,7 @@ def bench_wide(ctx, D, args):
                          "algorithmic_bytes_per_row": 8 + 8 * sel_all / rows, "self_check": "content",
                          "achieved_gbs": (8 * rows + 8 * sel_all) / D.world / (ms * 1e-3) / 1e9,
                          "two_pass_ms_per_step": fres["two_pass"],
-                         "kernel": "filter64_single_pass_kernel (decoupled look-back; csrc/filter64.cu)"}
+                         "kernel": "filter64_single_pass_kernel (counted sums, ring of counted tiles; csrc/filter64.cu)"}
     del words, col, fout, fend, ftot, fws
     free_all()
     if sf >= D.world:
