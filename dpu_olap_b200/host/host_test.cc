@@ -8,8 +8,11 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <limits>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "generator.h"
@@ -182,6 +185,69 @@ static void FilterNullableTest(gpu::GpuSet& sys) {
     EXPECT_EQ(gr->null_count(), 0);
     EXPECT_TRUE(gr->length() > 0 && gr->length() < 6 * 8192);
   }
+}
+// Other fixed-width column types (the reference fixes T = uint32_t): the typed
+// FilterGpu against Arrow's filter(less(column, threshold)), batch by batch, with nulls and a sliced
+// batch (bit offset in the validity bitmap), NaN and infinities in the float columns.
+template <typename ArrowType>
+static void FilterTypedCase(gpu::GpuSet& sys, std::shared_ptr<arrow::Scalar> threshold, uint32_t seed) {
+  using CType = typename ArrowType::c_type;
+  auto type = arrow::TypeTraits<ArrowType>::type_singleton();
+  auto schema = arrow::schema({arrow::field("v", type, /*nullable=*/true)});
+  arrow::RecordBatchVector batches;
+  uint64_t x = seed;
+  const int lens[] = {65536, 1, 0, 4097, 30000};
+  for (int rows : lens) {
+    typename arrow::TypeTraits<ArrowType>::BuilderType bld;
+    for (int r = 0; r < rows + 3; ++r) {
+      x = x * 6364136223846793005ull + 1442695040888963407ull;
+      const uint64_t h = x ^ (x >> 29);
+      if ((h >> 7) % 5 == 0) { (void)bld.AppendNull(); continue; }
+      CType v;
+      if (std::is_floating_point<CType>::value) {
+        const int k = (int)((h >> 11) % 64);
+        v = k == 0 ? std::numeric_limits<CType>::quiet_NaN()
+            : k == 1 ? std::numeric_limits<CType>::infinity()
+            : k == 2 ? -std::numeric_limits<CType>::infinity()
+                     : (CType)((double)(int64_t)(h >> 20) / 1e9 - 8000.0);
+      } else {
+        std::memcpy(&v, &h, sizeof(CType));
+      }
+      (void)bld.Append(v);
+    }
+    auto arr = bld.Finish().ValueOrDie()->Slice(3, rows);
+    batches.push_back(arrow::RecordBatch::Make(schema, rows, {arr}));
+  }
+  filter::FilterGpu g{sys, batches, threshold};
+  EXPECT_TRUE(g.Prepare().ok());
+  auto gr = g.GetResult().ValueOrDie();
+  EXPECT_EQ(gr->num_chunks(), (int)batches.size());
+  EXPECT_TRUE(gr->type()->Equals(*type));
+  int64_t selected = 0;
+  for (size_t b = 0; b < batches.size(); ++b) {
+    auto col = batches[b]->column(0);
+    auto thr = arrow::compute::Cast(arrow::Datum(threshold), type).ValueOrDie();
+    auto mask = arrow::compute::CallFunction("less", {arrow::Datum(col), thr}).ValueOrDie();
+    auto want = arrow::compute::Filter(arrow::Datum(col), mask).ValueOrDie().make_array();
+    EXPECT_EQ(want->null_count(), 0);
+    // bit patterns, not values: NaN never passes, -0.0 stays -0.0
+    auto got = gr->chunk((int)b);
+    EXPECT_EQ(got->length(), want->length());
+    if (got->length() == want->length() && got->length() > 0)
+      EXPECT_TRUE(std::memcmp(got->data()->template GetValues<CType>(1), want->data()->template GetValues<CType>(1),
+                              (size_t)got->length() * sizeof(CType)) == 0);
+    selected += want->length();
+  }
+  EXPECT_EQ((int64_t)g.Run().ValueOrDie(), selected);
+  EXPECT_TRUE(selected > 0);
+}
+static void FilterTypedTest(gpu::GpuSet& sys) {
+  FilterTypedCase<arrow::Int32Type>(sys, arrow::MakeScalar((int32_t)-12345), 1);
+  FilterTypedCase<arrow::FloatType>(sys, arrow::MakeScalar(0.5f), 2);
+  FilterTypedCase<arrow::UInt64Type>(sys, arrow::MakeScalar((uint64_t)1 << 62), 3);
+  FilterTypedCase<arrow::Int64Type>(sys, arrow::MakeScalar((int64_t)-(1ll << 40)), 4);
+  FilterTypedCase<arrow::DoubleType>(sys, arrow::MakeScalar(250.0), 5);
+  FilterTypedCase<arrow::Int64Type>(sys, arrow::MakeScalar((uint32_t)(1u << 30)), 6);  // threshold cast to the column's type
 }
 static void SumNullableTest(gpu::GpuSet& sys) {
   auto batches = NullableBatches("v", 5, 50000, 4, 0xffffffffu, 3, 11);
@@ -417,6 +483,7 @@ int main(int argc, char** argv) {
       {"SumTest.SimpleTest", SumSimpleTest},
       {"SumTest.LargeTest", SumLargeTest},         {"TakeTest.SimpleTest", TakeSimpleTest},
       {"TakeTest.LargeTest", TakeLargeTest},       {"FilterTest.Nullable", FilterNullableTest},
+      {"FilterTest.TypedColumns", FilterTypedTest},
       {"SumTest.Nullable", SumNullableTest},       {"TakeTest.Nullable", TakeNullableTest},
       {"JoinTest.SimpleTest", JoinSimpleTest},
       {"JoinTest.LargeTest", JoinLargeTest},       {"JoinTest.ManyPayloads", JoinManyPayloadsTest},

@@ -4,7 +4,10 @@
 // arrow::AllocateBuffer and filled by the library (filter_dpu.cc:34-39,79-83).
 #include "operators.h"
 
+#include <arrow/compute/api.h>
+
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 namespace upmemeval {
@@ -61,9 +64,80 @@ arrow::Status FilterGpu::Prepare() {
   return arrow::Status::OK();
 }
 
+// int32 / float32 and 64-bit columns: one call on member 0 (b2_filter_lt_32_host_into /
+// b2_filter_lt_64_host_into take the validity bitmaps too), result chunks sliced from one pinned slab.
+arrow::Result<std::shared_ptr<arrow::ChunkedArray>> FilterGpu::GetTypedResult(
+    const std::shared_ptr<arrow::DataType>& type) {
+  b2_ctx* ctx = system_.ctx();
+  int dtype = -1;
+  switch (type->id()) {
+    case arrow::Type::UINT32: dtype = B2_U32; break;
+    case arrow::Type::INT32: dtype = B2_I32; break;
+    case arrow::Type::FLOAT: dtype = B2_F32; break;
+    case arrow::Type::UINT64: dtype = B2_U64; break;
+    case arrow::Type::INT64: dtype = B2_I64; break;
+    case arrow::Type::DOUBLE: dtype = B2_F64; break;
+    default: return arrow::Status::TypeError("FilterGpu: no kernel for ", type->ToString(), " columns");
+  }
+  const int width = type->byte_width();
+  // the threshold in the column's type, as raw bits
+  std::shared_ptr<arrow::Scalar> thr = typed_threshold_ ? typed_threshold_ : arrow::MakeScalar(threshold_);
+  if (!thr->type->Equals(*type)) {
+    ARROW_ASSIGN_OR_RAISE(auto cast, arrow::compute::Cast(arrow::Datum(thr), type));
+    thr = cast.scalar();
+  }
+  if (!thr->is_valid) return arrow::Status::Invalid("FilterGpu: null threshold");
+  uint64_t bits = 0;
+  const auto view = static_cast<const arrow::internal::PrimitiveScalarBase&>(*thr).view();
+  if (static_cast<int>(view.size()) != width) return arrow::Status::Invalid("FilterGpu: threshold width");
+  std::memcpy(&bits, view.data(), view.size());
+  std::vector<const void*> ptrs;
+  std::vector<const uint8_t*> valid;
+  std::vector<int64_t> lens, valid_off;
+  int64_t rows = 0;
+  for (const auto& b : batches_) {
+    const auto& col = b->column(0);
+    if (!col->type()->Equals(*type)) return arrow::Status::TypeError("FilterGpu: batches of different types");
+    const uint8_t* base = col->data()->buffers[1] ? col->data()->buffers[1]->data() : nullptr;
+    ptrs.push_back(base ? base + col->offset() * width : nullptr);
+    lens.push_back(b->num_rows());
+    const bool nulls = col->null_count() != 0;
+    valid.push_back(nulls ? col->null_bitmap_data() : nullptr);
+    valid_off.push_back(nulls ? col->offset() : 0);
+    rows += b->num_rows();
+  }
+  const int64_t nb = static_cast<int64_t>(ptrs.size());
+  ARROW_ASSIGN_OR_RAISE(auto slab, system_.pinned().Acquire(std::max<int64_t>(rows, 1) * width));
+  void* out = const_cast<uint8_t*>(slab->data());
+  std::vector<int64_t> counts(nb > 0 ? nb : 1);
+  uint64_t total = 0;
+  b2_timings t{};
+  if (width == 8) {
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_64_host_into(ctx, ptrs.data(), valid.data(), valid_off.data(), lens.data(),
+                                                          nb, dtype, bits, out, rows, counts.data(), &total, &t));
+  } else {
+    B2_ARROW_RETURN_NOT_OK(ctx, b2_filter_lt_32_host_into(ctx, ptrs.data(), valid.data(), valid_off.data(), lens.data(),
+                                                          nb, dtype, static_cast<uint32_t>(bits), out, rows,
+                                                          counts.data(), &total, &t));
+  }
+  arrow::ArrayVector chunks;
+  int64_t off = 0;
+  for (int64_t b = 0; b < nb; ++b) {
+    auto piece = arrow::SliceBuffer(slab, off * width, counts[b] * width);
+    chunks.push_back(arrow::MakeArray(arrow::ArrayData::Make(type, counts[b], {nullptr, std::move(piece)}, 0)));
+    off += counts[b];
+  }
+  timers_->Add(t);
+  return arrow::ChunkedArray::Make(std::move(chunks), type);
+}
+
 arrow::Result<std::shared_ptr<arrow::ChunkedArray>> FilterGpu::GetResult() {
   b2_ctx* ctx = system_.ctx();
   if (!timers_) timers_ = std::make_shared<timer::Timers>();
+  if (!batches_.empty() && batches_[0]->num_columns() > 0) {
+    const auto& type = batches_[0]->column(0)->type();
+    if (typed_threshold_ || type->id() != arrow::Type::UINT32) return GetTypedResult(type);
+  }
   ColumnPtrs in;
   ARROW_RETURN_NOT_OK(in.Append(batches_, 0, /*allow_nulls=*/true));
   const int64_t nb = static_cast<int64_t>(in.ptrs.size());

@@ -20,6 +20,11 @@ class FilterGpu {
  public:
   FilterGpu(gpu::GpuSet& system, arrow::RecordBatchVector batches, uint32_t threshold = 1u << 30)
       : system_(system), batches_(std::move(batches)), threshold_(threshold) {}
+  // Columns of the other fixed-width types the library filters (int32 / float32, uint64 / int64 /
+  // float64; the reference fixes T = uint32_t, dpu/shared/common.h:3): `v < threshold` in the column's
+  // type, the threshold cast to it. Nullable columns welcome; the result keeps the column's type.
+  FilterGpu(gpu::GpuSet& system, arrow::RecordBatchVector batches, std::shared_ptr<arrow::Scalar> threshold)
+      : system_(system), batches_(std::move(batches)), threshold_(0), typed_threshold_(std::move(threshold)) {}
   arrow::Status Prepare();
   arrow::Result<std::shared_ptr<arrow::ChunkedArray>> GetResult();
   arrow::Result<uint64_t> Run();
@@ -28,7 +33,9 @@ class FilterGpu {
  private:
   gpu::GpuSet& system_;
   arrow::RecordBatchVector batches_;
+  arrow::Result<std::shared_ptr<arrow::ChunkedArray>> GetTypedResult(const std::shared_ptr<arrow::DataType>& type);
   uint32_t threshold_;
+  std::shared_ptr<arrow::Scalar> typed_threshold_;
   std::shared_ptr<timer::Timers> timers_;
 };
 }  // namespace filter

@@ -40,7 +40,7 @@ def test_cpp_bench_native_json_shape(host_bins):
 def test_cpp_reference_tests_on_gpu(host_bins):
     r = subprocess.run([str(host_bins["host_test"])], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 of 17 cases failed" in r.stdout
+    assert "0 of 18 cases failed" in r.stdout
 
 
 @pytest.mark.gpu
@@ -54,7 +54,7 @@ def test_cpp_reference_tests_on_a_gpu_set(host_bins, nr_gpus):
     env = dict(os.environ, NR_GPUS=str(nr_gpus))
     r = subprocess.run([str(host_bins["host_test"])], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 of 17 cases failed" in r.stdout
+    assert "0 of 18 cases failed" in r.stdout
 
 
 @pytest.mark.gpu
