@@ -813,7 +813,7 @@ def bench_join_aggr(ctx, D, args):
     import torch
     from dpu_olap_b200.generator import RandomArrayGenerator
     if D.world != 1:
-        return None
+        return bench_join_aggr_sharded(ctx, D, args)
     nb = args.sf
     g = RandomArrayGenerator(ctx, 42)
     x = g.batches_dev(nb, JOIN_BATCH)
@@ -852,6 +852,95 @@ def bench_join_aggr(ctx, D, args):
         res[name] = {"ms_per_step": ms, "rows_per_s": n / (ms * 1e-3), "out_rows": got[0],
                      "launches_per_step": (ctx.launches - l0) // (args.steps + args.warmup)}
     del x, pk, y, fk, ws
+    free_all()
+    return res
+
+
+def bench_join_aggr_sharded(ctx, D, args):
+    """The fused pipeline over N GPUs: the join's exchange (P2PShuffleJoin: rows stored straight into the
+    peers' receive buffers over NVLink), then every rank's local join adds the payloads of its output rows
+    (b2_join_aggr_pairs_seg_cap_phased_dev; the predicate on L.y is evaluated by the probe kernel, the rows
+    cross the link unfiltered) and ONE 24-byte all-reduce combines the ranks' sums. Nothing is materialised."""
+    import torch
+    from dpu_olap_b200.generator import RandomArrayGenerator
+    from dpu_olap_b200.sharded import P2PShuffleJoin
+    G = D.world
+    nb_total = args.sf
+    if nb_total < G or nb_total * JOIN_BATCH > 1 << 32:
+        return None
+    first, nb = shard(nb_total, D)
+    g = RandomArrayGenerator(ctx, 42)
+    x = g.batches_dev(nb_total, JOIN_BATCH, take=(first, nb))
+    pk = g.index_column_dev(nb_total, JOIN_BATCH, take=(first, nb))
+    y = g.batches_dev(nb_total, JOIN_BATCH, take=(first, nb))
+    fk = g.foreign_key_dev(JOIN_BATCH, nb_total, JOIN_BATCH, take=(first, nb))
+    n = nb * JOIN_BATCH
+    cap = n + n // 8 + 65536
+    ok, pj, why = 1, None, None
+    try:
+        pj = P2PShuffleJoin(ctx, D.dist, D.rank, G, n, cap, n_build_total=nb_total * JOIN_BATCH)
+    except Exception as e:  # noqa: BLE001 - agreed on by all ranks below
+        ok, why = 0, f"{type(e).__name__}: {e}"[:200]
+    if D.sum_int(ok) != G:
+        return {"unavailable": why or "a peer rank could not set up symmetric memory"}
+    jws_bytes = ctx.join_seg_cap_ws_bytes(cap, cap, pj.nr_expected, pj.skip, pj.seg_bits)
+    jws = torch.empty(jws_bytes + 256, dtype=torch.uint8, device="cuda")
+    part = torch.zeros(3, dtype=torch.int64, device="cuda")    # this rank's rows / sum_y / sum_x
+    total = torch.zeros(3, dtype=torch.int64, device="cuda")   # all ranks' (int64 adds wrap mod 2^64 as uint64 sums do)
+    thr = 1 << 30
+    # expected aggregates with torch: fk matches exactly one pk = its global row number; pk batch b (and
+    # with it x batch b) lives on rank b // nb, so every rank's x is broadcast once and gathered from
+    flip = torch.tensor(-2**31, dtype=torch.int32, device="cuda")
+    exp = {None: [0, 0, 0], thr: [0, 0, 0]}
+    keep_all = (y ^ flip) < (thr - 2**31)
+    xbuf = torch.empty(n, dtype=torch.int32, device="cuda")
+    fk64 = fk.to(torch.int64) & 0xFFFFFFFF
+    for src in range(G):
+        if src == D.rank:
+            xbuf.copy_(x)
+        D.dist.broadcast(xbuf, src=src)
+        for s0 in range(0, n, 1 << 26):
+            s1 = min(n, s0 + (1 << 26))
+            f = fk64[s0:s1] - src * n
+            here = (f >= 0) & (f < n)
+            xx = (xbuf[f.clamp(0, n - 1)].to(torch.int64) & 0xFFFFFFFF) * here
+            exp[None][2] += int(xx.sum())
+            exp[thr][2] += int((xx * keep_all[s0:s1]).sum())
+            del f, here, xx
+    for s0 in range(0, n, 1 << 26):
+        s1 = min(n, s0 + (1 << 26))
+        yy = y[s0:s1].to(torch.int64) & 0xFFFFFFFF
+        exp[None][0] += s1 - s0
+        exp[None][1] += int(yy.sum())
+        exp[thr][0] += int(keep_all[s0:s1].sum())
+        exp[thr][1] += int((yy * keep_all[s0:s1]).sum())
+        del yy
+    del xbuf, fk64, keep_all
+
+    def all_sum_u64(v: int) -> int:  # sums of up to 2^64 do not fit the int64 all-reduce: reduce the halves
+        return ((D.sum_int(v >> 32) << 32) + D.sum_int(v & 0xFFFFFFFF)) % (1 << 64)
+
+    res = {"rows_per_side": nb_total * JOIN_BATCH, "workspace_gib": round(jws_bytes / 2**30, 2), "sliced": False,
+           "exchange": "P2PShuffleJoin (fused NVLink scatter), local b2_join_aggr_pairs_seg_cap_phased_dev, "
+                       "one 24-byte all-reduce"}
+    for name, t in (("join_sum", None), ("filter_join_sum", thr)):
+        def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort, phase_bits, t=t):
+            ctx.join_aggr_pairs_seg_cap_dev(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits=skip_bits,
+                                            ws=jws, out=part, y_threshold=t, abort=abort, phases=phase_bits)
+
+        def step():
+            pj.step(fk, y, pk, x, local_join)
+            total.copy_(part)
+            D.dist.all_reduce(total)
+        l0 = ctx.launches
+        ms = timed_steps(D, step, args.steps, args.warmup)
+        got = [int(v) for v in total.cpu().numpy().view("uint64")]
+        want = [all_sum_u64(v % (1 << 64)) for v in exp[t]]
+        if got != want:
+            raise SystemExit(f"sharded {name} self-check failed on rank {D.rank}: {got} vs {want}")
+        res[name] = {"ms_per_step": ms, "rows_per_s": nb_total * JOIN_BATCH / (ms * 1e-3), "out_rows": got[0],
+                     "launches_per_step": (ctx.launches - l0) // (args.steps + args.warmup), "self_check": "content"}
+    del x, pk, y, fk, jws, pj
     free_all()
     return res
 

@@ -98,6 +98,8 @@ SIGNATURES = {
                                          _int, _vp, _vp, _sz, _vp]),
     "b2_join_pairs_seg_cap_phased_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _i64,
                                                 _vp, _int, _vp, _int, _vp, _sz, _vp]),
+    "b2_join_aggr_pairs_seg_cap_phased_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _int, _int, _u32, _vp,
+                                                     _int, _vp, _int, _vp, _sz, _vp]),
     "b2_join_seg_ws_bytes": (_sz, [_i64, _i64, _int, _int]),
     "b2_join_pairs_seg_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _i64, _vp, _int,
                                      _vp, _sz, _vp]),
@@ -176,6 +178,7 @@ SIGNATURES = {
     "b2_set_filter_fetch_host": (_int, [_vp, _pp, _i64, _pt]),
     "b2_set_take_u32_host": (_int, [_vp, _pp, _pi64, _pp, _pi64, _i64, _pp, _pt]),
     "b2_set_join_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pp, _pi64, _i64, _pu64, _pt]),
+    "b2_set_join_aggr_u32_host": (_int, [_vp, _pp, _pi64, _i64, _pp, _pi64, _i64, _int, _u32, _vp, _pt]),
     "b2_set_join_fetch_host": (_int, [_vp, _vp, _vp, _vp, _i64, _pt]),
     "b2_shuffle_partition_u32_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -532,9 +532,11 @@ __global__ void join_init_kernel(JoinState* st) {
   st->sum_y = 0;
   st->sum_x = 0;
 }
-__global__ void join_aggr_finish_kernel(const JoinState* __restrict__ st, b2_join_aggr* __restrict__ out) {
-  // a partition buffer that overflowed (skewed slice) makes the result invalid: report ~0 rows
-  out->rows = st->overflow ? ~0ull : st->out_rows;
+__global__ void join_aggr_finish_kernel(const JoinState* __restrict__ st, b2_join_aggr* __restrict__ out,
+                                        const int64_t* __restrict__ abort_flag = nullptr) {
+  // a partition buffer that overflowed (skewed slice) or an exchange that was called off on the device
+  // makes the result invalid: report ~0 rows
+  out->rows = (st->overflow || (abort_flag && *abort_flag)) ? ~0ull : st->out_rows;
   out->sum_y = st->sum_y;
   out->sum_x = st->sum_x;
 }
@@ -776,11 +778,13 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
                   const uint2* rpairs, const int64_t* r_seg_off, int64_t nr, int seg_bits,
                   uint32_t* d_out_fk, uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
                   uint64_t* d_out_rows, int skip_bits, void* d_ws, size_t ws_bytes, cudaStream_t s,
-                  int64_t nr_expected = 0, const int64_t* d_abort = nullptr, int phases = 7) {
+                  int64_t nr_expected = 0, const int64_t* d_abort = nullptr, int phases = 7,
+                  const JoinAggCfg* agg = nullptr) {
   B2_REQUIRE(ctx, nl >= 0 && nr >= 0 && out_capacity >= 0, "negative size");
   B2_REQUIRE(ctx, seg_bits >= 0 && seg_bits <= kPartMaxBits && skip_bits >= 0 && skip_bits + seg_bits <= 20,
              "bad skip/segment bits");
-  B2_REQUIRE(ctx, r_seg_off && (l_seg_off || !(phases & 2)) && (d_out_rows || !(phases & 4)), "null pointer");
+  B2_REQUIRE(ctx, r_seg_off && (l_seg_off || !(phases & 2)) && (d_out_rows || agg || !(phases & 4)), "null pointer");
+  B2_REQUIRE(ctx, !agg || agg->d_out, "null aggregate result");
   B2_REQUIRE(ctx, phases >= 1 && phases <= 7, "phases: 1 build | 2 probe | 4 finish");
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
              "workspace must be 256 B aligned");
@@ -801,9 +805,12 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
   }
   if ((nl > 0 || !(phases & 2)) && nr > 0) {
     static const int seen = b2_new_site();
-    if (b2_first_use_on_device(ctx, seen))
+    if (b2_first_use_on_device(ctx, seen)) {
       B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kTableBytes));
+      B2_CUDA_OK(ctx, cudaFuncSetAttribute(join_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kTableBytes));
+    }
     const int64_t nseg = (int64_t)1 << seg_bits;
     const int64_t nparts = (int64_t)1 << P.total_bits;
     const uint2 *rp = rpairs, *lp = lpairs;
@@ -836,14 +843,19 @@ int join_seg_impl(b2_ctx* ctx, const uint2* lpairs, const int64_t* l_seg_off, in
     if (phases & 2) {  // probe phase: may run several times, each over another share of the probe side
       b2_trace_scope tr(ctx, B2_PHASE_PROBE, s);
       const int64_t grid = std::min<int64_t>(nparts, (int64_t)ctx->sm_count * kProbeCtasPerSm);
-      join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
-          rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false,
-          P.rest_bits);
+      if (agg)  // the rows crossed the link unfiltered: the probe kernel evaluates L.y < y_thr itself
+        join_probe_kernel<true><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+            rp, roff, lp, loff, nparts, nullptr, nullptr, nullptr, 0, st, agg->y_thr, agg->filter_y, P.rest_bits);
+      else
+        join_probe_kernel<false><<<(unsigned)grid, kThreads, kTableBytes, s>>>(
+            rp, roff, lp, loff, nparts, d_out_fk, d_out_y, d_out_x, out_capacity, st, 0u, false,
+            P.rest_bits);
       B2_LAUNCH_CHECK(ctx, "join_probe_kernel");
     }
   }
   if (phases & 4) {
-    join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows, d_abort);
+    if (agg) join_aggr_finish_kernel<<<1, 1, 0, s>>>(st, agg->d_out, d_abort);
+    else join_finish_kernel<<<1, 1, 0, s>>>(st, d_out_rows, d_abort);
     B2_LAUNCH_CHECK(ctx, "join_finish_kernel");
   }
   return B2_OK;
@@ -1164,6 +1176,27 @@ int b2_join_pairs_seg_cap_phased_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, con
                        reinterpret_cast<const uint2*>(d_r_pairs), d_r_seg_off, nr_cap, seg_bits, d_out_fk,
                        d_out_y, d_out_x, out_capacity, d_out_rows, hash_skip_bits, d_ws, ws_bytes,
                        static_cast<cudaStream_t>(stream), nr_expected, d_abort, phases);
+}
+
+int b2_join_aggr_pairs_seg_cap_phased_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off,
+                                          int64_t nl_cap, const uint64_t* d_r_pairs, const int64_t* d_r_seg_off,
+                                          int64_t nr_cap, int64_t nr_expected, int seg_bits, int filter_y,
+                                          uint32_t y_threshold, b2_join_aggr* d_out, int hash_skip_bits,
+                                          const int64_t* d_abort, int phases, void* d_ws, size_t ws_bytes,
+                                          void* stream) {
+  if (!ctx) return B2_ERR_INVALID;
+  b2_device_scope dev_scope(ctx);
+  B2_REQUIRE(ctx, nl_cap == 0 || d_l_pairs || !(phases & 2), "null left pairs");
+  B2_REQUIRE(ctx, nr_cap == 0 || d_r_pairs, "null right pairs");
+  B2_REQUIRE(ctx, d_out != nullptr, "null aggregate result");
+  JoinAggCfg agg;
+  agg.filter_y = filter_y != 0;
+  agg.y_thr = y_threshold;
+  agg.d_out = d_out;
+  return join_seg_impl(ctx, reinterpret_cast<const uint2*>(d_l_pairs), d_l_seg_off, nl_cap,
+                       reinterpret_cast<const uint2*>(d_r_pairs), d_r_seg_off, nr_cap, seg_bits, nullptr, nullptr,
+                       nullptr, 0, nullptr, hash_skip_bits, d_ws, ws_bytes, static_cast<cudaStream_t>(stream),
+                       nr_expected, d_abort, phases, &agg);
 }
 
 int b2_join_pairs_seg_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off, int64_t nl,

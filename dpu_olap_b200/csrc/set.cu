@@ -34,7 +34,7 @@ struct Member {
   int64_t recv_cap = 0;                    // rows each holds
   char* tables = nullptr;                  // off[2][B+1] | off_ptrs[2][n] | recv_base[2][n] | addr[2][B] | seg[2][B+1] | info[2][3]
   cudaEvent_t ev_count = nullptr, ev_scatter = nullptr, ev_t0 = nullptr, ev_up = nullptr, ev_work = nullptr;
-  int64_t* h_info = nullptr;  // pinned: info[2][3] | rows
+  int64_t* h_info = nullptr;  // pinned: info[2][3] | rows (or the member's b2_join_aggr: rows | sum_y | sum_x)
   // pending join result
   uint32_t* o_all = nullptr;  // fk | y | x, one allocation (adjacent output columns)
   int64_t o_cap = 0;
@@ -145,7 +145,7 @@ int ensure_join_state(b2_set* set, int64_t cap) {
       B2_CUDA_OK(mb.ctx, cudaEventCreate(&mb.ev_t0));
       B2_CUDA_OK(mb.ctx, cudaEventCreate(&mb.ev_up));
       B2_CUDA_OK(mb.ctx, cudaEventCreate(&mb.ev_work));
-      B2_CUDA_OK(mb.ctx, cudaHostAlloc(&mb.h_info, 64, cudaHostAllocPortable));
+      B2_CUDA_OK(mb.ctx, cudaHostAlloc(&mb.h_info, 128, cudaHostAllocPortable));
       bases_changed = true;
     }
     if (mb.recv_cap < cap) {
@@ -386,15 +386,29 @@ int b2_set_take_u32_host(b2_set* set, const uint32_t* const* value_ptrs, const i
 }
 
 // ---- join -----------------------------------------------------------------------------------------
-int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+// The sharded join; with `agg` the fused join -> aggregate pipeline: same exchange, every member's local
+// join adds its output rows' payloads instead of materialising them, the host adds the members' sums.
+struct SetJoinAgg {
+  int filter_y;
+  uint32_t y_threshold;
+  b2_join_aggr* out;
+};
+static int set_join_core(b2_set* set, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
                          const uint32_t* const* r_ptrs, const int64_t* r_lens, int64_t nr_batches,
-                         uint64_t* out_rows, b2_timings* timings) {
+                         uint64_t* out_rows, b2_timings* timings, const SetJoinAgg* agg) {
   if (!set || !out_rows || nl_batches < 0 || nr_batches < 0) return B2_ERR_INVALID;
   const auto t0 = Clock::now();
   const int n = set->n();
   set->join_pending = false;
   for (auto& mb : set->m) free_join_result(mb);
   if (n == 1) {  // one device: the single-context join, whose result stays pending in that ctx
+    if (agg) {
+      const int rc = b2_join_aggr_u32_host(set->m[0].ctx, l_ptrs, l_lens, nl_batches, r_ptrs, r_lens, nr_batches,
+                                           agg->filter_y, agg->y_threshold, agg->out, timings);
+      if (rc != B2_OK) return set_fail(set, rc, set->m[0].ctx, "b2_join_aggr_u32_host");
+      *out_rows = agg->out->rows;
+      return B2_OK;
+    }
     const int rc = b2_join_u32_host(set->m[0].ctx, l_ptrs, l_lens, nl_batches, r_ptrs, r_lens, nr_batches, out_rows,
                                     timings);
     if (rc != B2_OK) return set_fail(set, rc, set->m[0].ctx, "b2_join_u32_host");
@@ -526,7 +540,7 @@ int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64
       const int64_t* info = reinterpret_cast<const int64_t*>(mb.tables + T.info);
       // PK-FK joins produce at most one row per received probe row; duplicate build keys can produce
       // more, in which case this member's local join is re-run below with the count it reported
-      if (!mb.o_all || mb.o_cap < cap) {
+      if (!agg && (!mb.o_all || mb.o_cap < cap)) {
         if (mb.o_all) b2_dev_free(ctx, mb.o_all);
         mb.o_all = nullptr;
         B2_RETURN_NOT_OK(b2_dev_alloc(ctx, (void**)&mb.o_all, (size_t)cap * 12));
@@ -539,12 +553,18 @@ int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64
       uint64_t* d_rows = nullptr;
       B2_RETURN_NOT_OK(b2_dev_alloc(ctx, (void**)&d_rows, 256));
       cleanup.extra[g].push_back(d_rows);
-      B2_RETURN_NOT_OK(b2_join_pairs_seg_cap_dev(ctx, mb.recv[0], seg, cap, mb.recv[1], seg + (B + 1), cap, nr_expected,
-                                                 seg_bits, mb.o_all, mb.o_all + mb.o_cap, mb.o_all + 2 * mb.o_cap,
-                                                 mb.o_cap, d_rows, skip, info + 5, jws, jws_bytes, s));
+      if (agg)  // d_rows receives a b2_join_aggr: rows | sum_y | sum_x
+        B2_RETURN_NOT_OK(b2_join_aggr_pairs_seg_cap_phased_dev(
+            ctx, mb.recv[0], seg, cap, mb.recv[1], seg + (B + 1), cap, nr_expected, seg_bits, agg->filter_y,
+            agg->y_threshold, reinterpret_cast<b2_join_aggr*>(d_rows), skip, info + 5, 7, jws, jws_bytes, s));
+      else
+        B2_RETURN_NOT_OK(b2_join_pairs_seg_cap_dev(ctx, mb.recv[0], seg, cap, mb.recv[1], seg + (B + 1), cap,
+                                                   nr_expected, seg_bits, mb.o_all, mb.o_all + mb.o_cap,
+                                                   mb.o_all + 2 * mb.o_cap, mb.o_cap, d_rows, skip, info + 5, jws,
+                                                   jws_bytes, s));
       B2_CUDA_OK(ctx, cudaEventRecord(mb.ev_work, s));
       B2_CUDA_OK(ctx, cudaMemcpyAsync(mb.h_info, info, 48, cudaMemcpyDeviceToHost, s));
-      B2_CUDA_OK(ctx, cudaMemcpyAsync(mb.h_info + 6, d_rows, 8, cudaMemcpyDeviceToHost, s));
+      B2_CUDA_OK(ctx, cudaMemcpyAsync(mb.h_info + 6, d_rows, agg ? sizeof(b2_join_aggr) : 8, cudaMemcpyDeviceToHost, s));
     }
     bool overflow = false;
     int64_t need = 0;
@@ -568,7 +588,7 @@ int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64
   for (int g = 0; g < n; ++g) {
     Member& mb = set->m[(size_t)g];
     if (mb.rows == ~0ull) return set_fail(set, B2_ERR_WORKSPACE, nullptr, "join: a partition buffer overflowed");
-    if ((int64_t)mb.rows <= mb.o_cap) continue;
+    if (agg || (int64_t)mb.rows <= mb.o_cap) continue;  // nothing is materialised: no capacity to outgrow
     b2_ctx* ctx = mb.ctx;
     b2_device_scope sc(ctx);
     cudaStream_t s = ctx->s_compute;
@@ -610,10 +630,36 @@ int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64
     merge_timings(&acc, t);
   }
   *out_rows = total;
-  set->join_pending = true;
+  if (agg) {
+    b2_join_aggr sum{};
+    for (auto& mb : set->m) {  // h_info + 6: this member's b2_join_aggr
+      sum.rows += (uint64_t)mb.h_info[6];
+      sum.sum_y += (uint64_t)mb.h_info[7];
+      sum.sum_x += (uint64_t)mb.h_info[8];
+    }
+    *agg->out = sum;
+  } else {
+    set->join_pending = true;
+  }
   acc.total_ms = ms_since(t0);
   if (timings) *timings = acc;
   return B2_OK;
+}
+
+int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                         const uint32_t* const* r_ptrs, const int64_t* r_lens, int64_t nr_batches,
+                         uint64_t* out_rows, b2_timings* timings) {
+  return set_join_core(set, l_ptrs, l_lens, nl_batches, r_ptrs, r_lens, nr_batches, out_rows, timings, nullptr);
+}
+
+int b2_set_join_aggr_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                              const uint32_t* const* r_ptrs, const int64_t* r_lens, int64_t nr_batches, int filter_y,
+                              uint32_t y_threshold, b2_join_aggr* out, b2_timings* timings) {
+  if (!out) return B2_ERR_INVALID;
+  *out = b2_join_aggr{};
+  const SetJoinAgg agg{filter_y, y_threshold, out};
+  uint64_t rows = 0;
+  return set_join_core(set, l_ptrs, l_lens, nl_batches, r_ptrs, r_lens, nr_batches, &rows, timings, &agg);
 }
 
 int b2_set_join_fetch_host(b2_set* set, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x, int64_t capacity_rows,

@@ -405,10 +405,14 @@ arrow::Result<b2_join_aggr> JoinGpu::RunAggregate(bool filter_left_payload, uint
   ARROW_RETURN_NOT_OK(r.Append(right_batches_, 1 - pk));
   b2_join_aggr out{};
   b2_timings t{};
-  B2_ARROW_RETURN_NOT_OK(
-      ctx, b2_join_aggr_u32_host(ctx, l.ptrs.data(), l.lens.data(), static_cast<int64_t>(left_batches_.size()),
-                                 r.ptrs.data(), r.lens.data(), static_cast<int64_t>(right_batches_.size()),
-                                 filter_left_payload ? 1 : 0, threshold, &out, &t));
+  // sharded over every GPU of the set (one member: the single-context pipeline, filter pushed into the
+  // probe side's first radix pass)
+  b2_set* set = system_.set();
+  (void)ctx;
+  B2_SET_RETURN_NOT_OK(
+      set, b2_set_join_aggr_u32_host(set, l.ptrs.data(), l.lens.data(), static_cast<int64_t>(left_batches_.size()),
+                                     r.ptrs.data(), r.lens.data(), static_cast<int64_t>(right_batches_.size()),
+                                     filter_left_payload ? 1 : 0, threshold, &out, &t));
   timers_->Add(t);
   return out;
 }

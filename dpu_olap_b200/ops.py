@@ -690,6 +690,21 @@ class Context:
             ptr, nbytes, self._stream()), "b2_join_pairs_seg_cap_phased_dev")
         return outs[0], outs[1], outs[2], out_rows
 
+    def join_aggr_pairs_seg_cap_dev(self, l_pairs, l_seg_off, r_pairs, r_seg_off, nr_expected: int, seg_bits: int,
+                                    skip_bits: int, ws, out, y_threshold: int | None = None, abort=None,
+                                    phases: int = 7):
+        """b2_join_aggr_pairs_seg_cap_phased_dev: the fused join -> aggregate pipeline over the receive buffers
+        of the shuffle (arguments as join_pairs_seg_cap_dev); out = 3 x int64 device tensor (rows, sum of the
+        left payloads, sum of the right payloads as uint64 bit patterns), written by phases & 4."""
+        ptr, nbytes = self._aligned(ws)
+        self._ck(self._lib.b2_join_aggr_pairs_seg_cap_phased_dev(
+            self._h, _dptr(l_pairs), _dptr(l_seg_off), l_pairs.numel(), _dptr(r_pairs), _dptr(r_seg_off),
+            r_pairs.numel(), int(nr_expected), seg_bits, 0 if y_threshold is None else 1,
+            0 if y_threshold is None else int(y_threshold), _dptr(out), skip_bits,
+            None if abort is None else _dptr(abort), int(phases), ptr, nbytes, self._stream()),
+            "b2_join_aggr_pairs_seg_cap_phased_dev")
+        return out
+
     def join_seg_ws_bytes(self, nl: int, nr: int, skip_bits: int, seg_bits: int) -> int:
         return int(self._lib.b2_join_seg_ws_bytes(nl, nr, skip_bits, seg_bits))
 
@@ -769,7 +784,7 @@ class DeviceSet:
     peer-memory shuffle over NVLink — all inside libb200olap.so, one host process, no torch."""
 
     _SET_OPS = {"sum_u32_host", "filter_lt_u32_host", "filter_fetch_host", "take_u32_host", "join_u32_host",
-                "join_fetch_host"}
+                "join_fetch_host", "join_aggr_u32_host"}
 
     def __init__(self, devices: Sequence[int] | int | None = None):
         self._lib = _lib.lib()

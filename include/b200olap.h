@@ -153,6 +153,14 @@ int b2_set_join_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64
                          uint64_t* out_rows, b2_timings* timings);
 int b2_set_join_fetch_host(b2_set* set, uint32_t* out_fk, uint32_t* out_y, uint32_t* out_x, int64_t capacity_rows,
                            b2_timings* timings);
+/* The fused pipeline [filter left payload < y_threshold ->] join -> COUNT / SUM / SUM over the whole set
+ * (arguments as b2_join_aggr_u32_host): the same exchange as b2_set_join_u32_host, every GPU's local
+ * join adds its output rows' payloads instead of materialising them, the partial results are added on
+ * the host (as SumDpu adds its per-device partials, aggr_dpu.cc:82-84). */
+struct b2_join_aggr;
+int b2_set_join_aggr_u32_host(b2_set* set, const uint32_t* const* l_ptrs, const int64_t* l_lens, int64_t nl_batches,
+                              const uint32_t* const* r_ptrs, const int64_t* r_lens, int64_t nr_batches, int filter_y,
+                              uint32_t y_threshold, struct b2_join_aggr* out, b2_timings* timings);
 
 /* ---- pinned host memory (zero-copy Arrow interop at the boundary) -------------------------- */
 /* Arrow buffers live in pageable memory; copies from/to them run at a fraction of the PCIe rate.
@@ -715,6 +723,17 @@ int b2_join_pairs_seg_cap_phased_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, con
                                      uint32_t* d_out_y, uint32_t* d_out_x, int64_t out_capacity,
                                      uint64_t* d_out_rows, int hash_skip_bits, const int64_t* d_abort, int phases,
                                      void* d_ws, size_t ws_bytes, void* stream);
+/* The fused join -> aggregate pipeline (b2_join_aggr_u32_dev) over the receiving half of the shuffle:
+ * same buffers, segment tables, phases and abort flag as b2_join_pairs_seg_cap_phased_dev, no output
+ * columns — the probe kernel adds every output row's payloads to its sums and, with filter_y, only
+ * counts probe rows whose payload is < y_threshold (the rows crossed the link unfiltered, so the
+ * predicate is evaluated here). phases & 4 publishes *d_out (rows == ~0: overflow or aborted exchange). */
+int b2_join_aggr_pairs_seg_cap_phased_dev(b2_ctx* ctx, const uint64_t* d_l_pairs, const int64_t* d_l_seg_off,
+                                          int64_t nl_cap, const uint64_t* d_r_pairs, const int64_t* d_r_seg_off,
+                                          int64_t nr_cap, int64_t nr_expected, int seg_bits, int filter_y,
+                                          uint32_t y_threshold, b2_join_aggr* d_out, int hash_skip_bits,
+                                          const int64_t* d_abort, int phases, void* d_ws, size_t ws_bytes,
+                                          void* stream);
 
 #ifdef __cplusplus
 }

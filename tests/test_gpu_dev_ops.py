@@ -851,9 +851,27 @@ def test_p2p_plan_kernel_and_capacity_join_virtual_ranks(ctx, G, rows_per_rank):
             if overflow:
                 assert m == 0xFFFFFFFFFFFFFFFF
                 assert all(int((t != -1).sum()) == 0 for t in (recv[0][r], recv[1][r]))  # nothing was stored
+                agg = torch.zeros(3, dtype=torch.int64, device="cuda")
+                ctx.join_aggr_pairs_seg_cap_dev(recv[0][r], seg[r, 0], recv[1][r], seg[r, 1], nr_expected, seg_bits,
+                                                skip_bits=skip, ws=ws, out=agg, abort=info[r][1, 2:3])
+                assert int(agg.cpu().numpy().view(np.uint64)[0]) == 0xFFFFFFFFFFFFFFFF
                 continue
             for i, t in enumerate(outs):
                 got[i].append(host(t)[:m])
+            # the fused join -> aggregate pipeline over the same receive buffers (plain and with the
+            # predicate on the left payload evaluated by the probe kernel), phased like the sharded step
+            for thr in (None, 1 << 30):
+                agg = torch.full((3,), -1, dtype=torch.int64, device="cuda")
+                for bits in (1, 2, 4):
+                    ctx.join_aggr_pairs_seg_cap_dev(recv[0][r], seg[r, 0], recv[1][r], seg[r, 1], nr_expected, seg_bits,
+                                                    skip_bits=skip, ws=ws, out=agg, y_threshold=thr,
+                                                    abort=info[r][1, 2:3], phases=bits)
+                torch.cuda.synchronize()
+                a = agg.cpu().numpy().view(np.uint64)
+                keep = np.ones(m, bool) if thr is None else host(outs[1])[:m] < thr
+                assert int(a[0]) == int(keep.sum())
+                assert int(a[1]) == int(host(outs[1])[:m][keep].astype(np.uint64).sum(dtype=np.uint64))
+                assert int(a[2]) == int(host(outs[2])[:m][keep].astype(np.uint64).sum(dtype=np.uint64))
         if not overflow:
             got = oracle.sort_rows(*[np.concatenate(g) for g in got])
             exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))

@@ -50,6 +50,13 @@ def _check_join(dset, fk, y, pk, x):
     assert got[0].size == exp[0].size
     for a, b in zip(got, exp):
         assert np.array_equal(a, b)
+    # the fused join -> aggregate pipeline over the same set (b2_set_join_aggr_u32_host): every member adds
+    # the payloads of its local join's rows, the host adds the members' sums
+    for thr in (None, 1 << 30):
+        keep = np.ones(exp[0].size, bool) if thr is None else exp[1] < thr
+        want = {"rows": int(keep.sum()), "sum_y": int(exp[1][keep].astype(np.uint64).sum(dtype=np.uint64)),
+                "sum_x": int(exp[2][keep].astype(np.uint64).sum(dtype=np.uint64))}
+        assert j.RunAggregate(thr) == want
     return out, j
 
 
