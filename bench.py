@@ -892,30 +892,31 @@ def bench_join_aggr_sharded(ctx, D, args):
     # with it x batch b) lives on rank b // nb, so every rank's x is broadcast once and gathered from
     flip = torch.tensor(-2**31, dtype=torch.int32, device="cuda")
     exp = {None: [0, 0, 0], thr: [0, 0, 0]}
-    keep_all = (y ^ flip) < (thr - 2**31)
     xbuf = torch.empty(n, dtype=torch.int32, device="cuda")
-    fk64 = fk.to(torch.int64) & 0xFFFFFFFF
+    chunk = 1 << 26
     for src in range(G):
         if src == D.rank:
             xbuf.copy_(x)
         D.dist.broadcast(xbuf, src=src)
-        for s0 in range(0, n, 1 << 26):
-            s1 = min(n, s0 + (1 << 26))
-            f = fk64[s0:s1] - src * n
+        for s0 in range(0, n, chunk):
+            s1 = min(n, s0 + chunk)
+            f = (fk[s0:s1].to(torch.int64) & 0xFFFFFFFF) - src * n
             here = (f >= 0) & (f < n)
+            keep = (y[s0:s1] ^ flip) < (thr - 2**31)
             xx = (xbuf[f.clamp(0, n - 1)].to(torch.int64) & 0xFFFFFFFF) * here
             exp[None][2] += int(xx.sum())
-            exp[thr][2] += int((xx * keep_all[s0:s1]).sum())
-            del f, here, xx
-    for s0 in range(0, n, 1 << 26):
-        s1 = min(n, s0 + (1 << 26))
+            exp[thr][2] += int((xx * keep).sum())
+            del f, here, xx, keep
+    for s0 in range(0, n, chunk):
+        s1 = min(n, s0 + chunk)
         yy = y[s0:s1].to(torch.int64) & 0xFFFFFFFF
+        keep = (y[s0:s1] ^ flip) < (thr - 2**31)
         exp[None][0] += s1 - s0
         exp[None][1] += int(yy.sum())
-        exp[thr][0] += int(keep_all[s0:s1].sum())
-        exp[thr][1] += int((yy * keep_all[s0:s1]).sum())
-        del yy
-    del xbuf, fk64, keep_all
+        exp[thr][0] += int(keep.sum())
+        exp[thr][1] += int((yy * keep).sum())
+        del yy, keep
+    del xbuf
 
     def all_sum_u64(v: int) -> int:  # sums of up to 2^64 do not fit the int64 all-reduce: reduce the halves
         return ((D.sum_int(v >> 32) << 32) + D.sum_int(v & 0xFFFFFFFF)) % (1 << 64)
