@@ -859,8 +859,9 @@ def bench_join_aggr(ctx, D, args):
 def bench_join_aggr_sharded(ctx, D, args):
     """The fused pipeline over N GPUs: the join's exchange (P2PShuffleJoin: rows stored straight into the
     peers' receive buffers over NVLink), then every rank's local join adds the payloads of its output rows
-    (b2_join_aggr_pairs_seg_cap_phased_dev; the predicate on L.y is evaluated by the probe kernel, the rows
-    cross the link unfiltered) and ONE 24-byte all-reduce combines the ranks' sums. Nothing is materialised."""
+    (b2_join_aggr_pairs_seg_cap_phased_dev) and ONE 24-byte all-reduce combines the ranks' sums. The predicate on
+    L.y is applied in front of the link (b2_shuffle_p2p_count_lt_dev / _scatter_lt_dev): the rows that fail
+    it are neither counted nor sent. Nothing is materialised."""
     import torch
     from dpu_olap_b200.generator import RandomArrayGenerator
     from dpu_olap_b200.sharded import P2PShuffleJoin
@@ -922,15 +923,15 @@ def bench_join_aggr_sharded(ctx, D, args):
         return ((D.sum_int(v >> 32) << 32) + D.sum_int(v & 0xFFFFFFFF)) % (1 << 64)
 
     res = {"rows_per_side": nb_total * JOIN_BATCH, "workspace_gib": round(jws_bytes / 2**30, 2), "sliced": False,
-           "exchange": "P2PShuffleJoin (fused NVLink scatter), local b2_join_aggr_pairs_seg_cap_phased_dev, "
-                       "one 24-byte all-reduce"}
+           "exchange": "P2PShuffleJoin (fused NVLink scatter, the predicate on L.y applied in front of the link), "
+                       "local b2_join_aggr_pairs_seg_cap_phased_dev, one 24-byte all-reduce"}
     for name, t in (("join_sum", None), ("filter_join_sum", thr)):
         def local_join(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits, abort, phase_bits, t=t):
             ctx.join_aggr_pairs_seg_cap_dev(l_buf, lseg, r_buf, rseg, nr_expected, seg_bits, skip_bits=skip_bits,
                                             ws=jws, out=part, y_threshold=t, abort=abort, phases=phase_bits)
 
-        def step():
-            pj.step(fk, y, pk, x, local_join)
+        def step(t=t):
+            pj.step(fk, y, pk, x, local_join, probe_lt=t)   # the predicate is applied in front of the link
             total.copy_(part)
             D.dist.all_reduce(total)
         l0 = ctx.launches

@@ -90,6 +90,8 @@ SIGNATURES = {
     "b2_shuffle_p2p_ws_bytes": (_sz, [_i64, _int]),
     "b2_shuffle_p2p_count_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "b2_shuffle_p2p_scatter_dev": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    "b2_shuffle_p2p_count_lt_dev": (_int, [_vp, _vp, _vp, _i64, _int, _int, _u32, _vp, _vp, _sz, _vp]),
+    "b2_shuffle_p2p_scatter_lt_dev": (_int, [_vp, _vp, _vp, _i64, _int, _int, _u32, _vp, _vp, _vp, _sz, _vp]),
     "b2_shuffle_p2p_plan_dev": (_int, [_vp, _vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
     "b2_join_u32_phased_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _int, _int, _vp, _sz,
                                       _vp]),

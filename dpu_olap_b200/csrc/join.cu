@@ -1072,10 +1072,17 @@ size_t b2_shuffle_p2p_ws_bytes(int64_t n, int bits) {
 
 int b2_shuffle_p2p_count_dev(b2_ctx* ctx, const uint32_t* d_key, int64_t n, int bits, int64_t* d_bucket_off,
                              void* d_ws, size_t ws_bytes, void* stream) {
+  return b2_shuffle_p2p_count_lt_dev(ctx, d_key, nullptr, n, bits, 0, 0u, d_bucket_off, d_ws, ws_bytes, stream);
+}
+
+int b2_shuffle_p2p_count_lt_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n, int bits,
+                                int filter_val, uint32_t val_threshold, int64_t* d_bucket_off, void* d_ws,
+                                size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
   b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0 && bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
   B2_REQUIRE(ctx, d_bucket_off != nullptr && (n == 0 || d_key != nullptr), "null pointer");
+  B2_REQUIRE(ctx, !filter_val || n == 0 || d_val != nullptr, "the predicate needs the value column");
   B2_REQUIRE(ctx, d_ws != nullptr && (reinterpret_cast<uintptr_t>(d_ws) & 255) == 0,
              "workspace must be 256 B aligned");
   if (ws_bytes < b2_shuffle_p2p_ws_bytes(n, bits))
@@ -1087,8 +1094,11 @@ int b2_shuffle_p2p_count_dev(b2_ctx* ctx, const uint32_t* d_key, int64_t n, int 
   B2_LAUNCH_CHECK(ctx, "set_segment_kernel");
   PartInput in;
   in.keys = d_key;
+  in.vals = filter_val ? d_val : nullptr;
   PartGeom g;
   g.bits = bits;
+  g.val_pred = filter_val != 0;  // rows that fail `value < val_threshold` are not counted ...
+  g.val_thr = val_threshold;
   return part_count(ctx, in, n, seg, 1, g, d_bucket_off, base + 256, ws_bytes - 256, s);
 }
 
@@ -1111,6 +1121,13 @@ int b2_shuffle_p2p_plan_dev(b2_ctx* ctx, const int64_t* const* d_off_ptrs, const
 int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
                                int bits, const uint64_t* d_bucket_addr, const int64_t* d_abort, void* d_ws,
                                size_t ws_bytes, void* stream) {
+  return b2_shuffle_p2p_scatter_lt_dev(ctx, d_key, d_val, n, bits, 0, 0u, d_bucket_addr, d_abort, d_ws, ws_bytes,
+                                       stream);
+}
+
+int b2_shuffle_p2p_scatter_lt_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n, int bits,
+                                  int filter_val, uint32_t val_threshold, const uint64_t* d_bucket_addr,
+                                  const int64_t* d_abort, void* d_ws, size_t ws_bytes, void* stream) {
   if (!ctx) return B2_ERR_INVALID;
   b2_device_scope dev_scope(ctx);
   B2_REQUIRE(ctx, n >= 0 && bits >= 0 && bits <= kPartMaxBits, "bits must be in 0..10");
@@ -1125,6 +1142,8 @@ int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_
   in.vals = d_val;
   PartGeom g;
   g.bits = bits;
+  g.val_pred = filter_val != 0;  // ... and never cross the link
+  g.val_thr = val_threshold;
   return part_scatter(ctx, in, n, reinterpret_cast<const int64_t*>(base), 1, g, nullptr, 0, d_bucket_addr,
                       nullptr, base + 256, ws_bytes - 256, static_cast<cudaStream_t>(stream), d_abort);
 }

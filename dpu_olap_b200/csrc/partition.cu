@@ -175,6 +175,15 @@ __device__ __forceinline__ uint32_t bucket_or_skip(uint32_t key, uint32_t val, c
   return keep ? b : 0xffffffffu;
 }
 
+// The same with the value predicate decided at run time (the peer scatter kernel has one shape).
+__device__ __forceinline__ uint32_t bucket_or_skip_rt(uint32_t key, uint32_t val, const PartGeom& g,
+                                                      const SliceSel& sel) {
+  const uint32_t h = wang_hash_u32(key);
+  const uint32_t b = part_bucket(h, g.shl, g.bits);
+  const bool keep = (h & sel.mask) == sel.cmp && (!g.val_pred || val < g.val_thr);
+  return keep ? b : 0xffffffffu;
+}
+
 template <bool kAoS, bool kValPred>
 __global__ void __launch_bounds__(kThreads, 4)
 part_hist_kernel(PartInput in, const int64_t* __restrict__ seg_off,
@@ -515,7 +524,7 @@ part_scatter_lines_kernel(PartInput in, const int64_t* __restrict__ seg_off,
     for (int it = 0; it < kLcItems; ++it) {
       const int64_t row = t0 + it * kLcThreads + tid;
       if (row < u.row1) {
-        const uint32_t b = bucket_or_skip<false>(key[it], val[it], g, sel);
+        const uint32_t b = bucket_or_skip_rt(key[it], val[it], g, sel);  // a pushed-down predicate drops rows here
         if (b != 0xffffffffu) packed[it] = b | (atomicAdd(&sm.tile_cnt[b], 1u) << 16);
       }
     }
@@ -1555,7 +1564,7 @@ int part_scatter_impl(b2_ctx* ctx, const PartInput& in, int64_t n, const int64_t
       B2_LAUNCH_CHECK(ctx, "part_scatter_sectors_kernel");
       return B2_OK;
     }
-    if (d_bucket_addr && ctx->tune[B2_TUNE_PEER_SCATTER_KERNEL] == 1) {
+    if (d_bucket_addr && ctx->tune[B2_TUNE_PEER_SCATTER_KERNEL] == 1 && !g.val_pred) {
       // peer destinations through the copy engine: whole 32-byte sectors, one bulk copy per (bucket, tile)
       static const int site_a = b2_new_site(), site_s = b2_new_site();
       const int budget = ctx->tune[B2_TUNE_PEER_SCATTER_CTAS];

@@ -489,7 +489,9 @@ static int set_join_core(b2_set* set, const uint32_t* const* l_ptrs, const int64
     B2_RETURN_NOT_OK(upload_column(ctx, I.x, r_ptrs + nr_batches + rb0, r_lens + rb0, rnb, s, &t.h2d_bytes));
     B2_CUDA_OK(ctx, cudaEventRecord(mb.ev_up, s));
     int64_t* off = reinterpret_cast<int64_t*>(mb.tables + T.off);
-    B2_RETURN_NOT_OK(b2_shuffle_p2p_count_dev(ctx, I.fk, I.nl, kShuffleBits, off, I.ws[0], I.ws_bytes[0], s));
+    // filter -> join -> aggregate: the predicate on the left payload is applied in front of the link
+    B2_RETURN_NOT_OK(b2_shuffle_p2p_count_lt_dev(ctx, I.fk, I.y, I.nl, kShuffleBits, agg && agg->filter_y,
+                                                 agg ? agg->y_threshold : 0u, off, I.ws[0], I.ws_bytes[0], s));
     B2_RETURN_NOT_OK(b2_shuffle_p2p_count_dev(ctx, I.pk, I.nr, kShuffleBits, off + (B + 1), I.ws[1], I.ws_bytes[1], s));
     B2_CUDA_OK(ctx, cudaEventRecord(mb.ev_count, s));
     return (int)B2_OK;
@@ -519,8 +521,9 @@ static int set_join_core(b2_set* set, const uint32_t* const* l_ptrs, const int64
                                                nullptr, s));
       B2_RETURN_NOT_OK(b2_shuffle_p2p_plan_dev(ctx, off_ptrs + n, recv_base + n, g, n, kShuffleBits, cap, addr + B,
                                                seg + (B + 1), info + 3, info + 2, s));
-      B2_RETURN_NOT_OK(b2_shuffle_p2p_scatter_dev(ctx, I.fk, I.y, I.nl, kShuffleBits, addr, info + 2, I.ws[0],
-                                                  I.ws_bytes[0], s));
+      B2_RETURN_NOT_OK(b2_shuffle_p2p_scatter_lt_dev(ctx, I.fk, I.y, I.nl, kShuffleBits, agg && agg->filter_y,
+                                                     agg ? agg->y_threshold : 0u, addr, info + 2, I.ws[0],
+                                                     I.ws_bytes[0], s));
       B2_RETURN_NOT_OK(b2_shuffle_p2p_scatter_dev(ctx, I.pk, I.x, I.nr, kShuffleBits, addr + B, info + 5, I.ws[1],
                                                   I.ws_bytes[1], s));
       B2_CUDA_OK(ctx, cudaEventRecord(mb.ev_scatter, s));

@@ -644,25 +644,33 @@ class Context:
         ptr = (_dptr(ws) + 255) // 256 * 256
         return ptr, ws.numel() - (ptr - _dptr(ws))
 
-    def shuffle_p2p_count_dev(self, key, bits: int, ws, bucket_off=None):
-        """Rows per bucket (top `bits` bits of wang_hash): returns int64[2^bits + 1] boundaries."""
+    def shuffle_p2p_count_dev(self, key, bits: int, ws, bucket_off=None, val=None, val_lt: int | None = None):
+        """Rows per bucket (top `bits` bits of wang_hash): returns int64[2^bits + 1] boundaries. val_lt: only
+        rows with val < val_lt are counted (b2_shuffle_p2p_count_lt_dev: a predicate pushed in front of the link)."""
         import torch
         if bucket_off is None:
             bucket_off = torch.empty((1 << bits) + 1, dtype=torch.int64, device=key.device)
         ptr, nbytes = self._aligned(ws)
-        self._ck(self._lib.b2_shuffle_p2p_count_dev(self._h, _dptr(key), key.numel(), bits, _dptr(bucket_off),
-                                                    ptr, nbytes, self._stream()), "b2_shuffle_p2p_count_dev")
+        if val_lt is None:
+            self._ck(self._lib.b2_shuffle_p2p_count_dev(self._h, _dptr(key), key.numel(), bits, _dptr(bucket_off),
+                                                        ptr, nbytes, self._stream()), "b2_shuffle_p2p_count_dev")
+        else:
+            self._ck(self._lib.b2_shuffle_p2p_count_lt_dev(self._h, _dptr(key), _dptr(val), key.numel(), bits, 1,
+                                                           int(val_lt), _dptr(bucket_off), ptr, nbytes, self._stream()),
+                     "b2_shuffle_p2p_count_lt_dev")
         return bucket_off
 
-    def shuffle_p2p_scatter_dev(self, key, val, bits: int, bucket_addr, ws, abort=None):
+    def shuffle_p2p_scatter_dev(self, key, val, bits: int, bucket_addr, ws, abort=None, val_lt: int | None = None):
         """Writes the (key, val) pairs of bucket b contiguously from byte address bucket_addr[b]
         (int64 device tensor of 2^bits addresses — local or peer memory). abort: int64[1] device
-        tensor; non-zero on the device = store nothing (the plan kernel's overflow flag)."""
+        tensor; non-zero on the device = store nothing (the plan kernel's overflow flag). val_lt: only rows
+        with val < val_lt are sent (the count must have used the same predicate)."""
         ptr, nbytes = self._aligned(ws)
-        self._ck(self._lib.b2_shuffle_p2p_scatter_dev(self._h, _dptr(key), _dptr(val), key.numel(), bits,
-                                                      _dptr(bucket_addr), None if abort is None else _dptr(abort),
-                                                      ptr, nbytes, self._stream()),
-                 "b2_shuffle_p2p_scatter_dev")
+        self._ck(self._lib.b2_shuffle_p2p_scatter_lt_dev(self._h, _dptr(key), _dptr(val), key.numel(), bits,
+                                                         0 if val_lt is None else 1, 0 if val_lt is None else int(val_lt),
+                                                         _dptr(bucket_addr), None if abort is None else _dptr(abort),
+                                                         ptr, nbytes, self._stream()),
+                 "b2_shuffle_p2p_scatter_lt_dev")
 
     def shuffle_p2p_plan_dev(self, off_ptrs, recv_base, rank: int, nranks: int, bits: int, capacity_rows: int,
                              bucket_addr, seg_off, info, prev_abort=None):

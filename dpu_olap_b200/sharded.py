@@ -276,11 +276,13 @@ class P2PShuffleJoin:
     def _share(self, t, i: int):
         return t if self.shares == 1 else t[i * self.share_rows: min((i + 1) * self.share_rows, t.numel())]
 
-    def step(self, fk, y, pk, x, local_join, phases: dict | None = None):
+    def step(self, fk, y, pk, x, local_join, phases: dict | None = None, probe_lt: int | None = None):
         """local_join(l_buf, l_seg_off, r_buf, r_seg_off, nr_expected, seg_bits, skip_bits, abort, phase_bits) ->
         result, e.g. ctx.join_pairs_seg_cap_dev(..., phases=phase_bits): 1 = build, 2 = probe one share,
         4 = finish. phases: if given, every phase of the step is synchronised and its wall time (ms) stored
-        there (diagnostics only — the synchronisation removes all overlap)."""
+        there (diagnostics only — the synchronisation removes all overlap). probe_lt: a predicate on the
+        probe side's payload pushed in front of the link (filter -> join pipelines): rows with y >= probe_lt
+        are neither counted nor sent (b2_shuffle_p2p_count_lt_dev / b2_shuffle_p2p_scatter_lt_dev)."""
         import time
 
         import torch
@@ -302,7 +304,8 @@ class P2PShuffleJoin:
             torch.cuda.synchronize()
             t0[0] = time.perf_counter()
         for i in range(S):
-            ctx.shuffle_p2p_count_dev(self._share(fk, i), self.BITS, self.ws[i], self.my_off[i])
+            ctx.shuffle_p2p_count_dev(self._share(fk, i), self.BITS, self.ws[i], self.my_off[i],
+                                      val=self._share(y, i), val_lt=probe_lt)
         ctx.shuffle_p2p_count_dev(pk, self.BITS, self.ws[S], self.my_off[S])
         mark("count")
         # also a barrier: nobody scatters before every rank is done reading its receive buffers
@@ -316,7 +319,7 @@ class P2PShuffleJoin:
             ctx.shuffle_p2p_scatter_dev(pk, x, self.BITS, self.addr[S], self.ws[S], abort=self.abort)
             for i in range(S):
                 ctx.shuffle_p2p_scatter_dev(self._share(fk, i), self._share(y, i), self.BITS, self.addr[i], self.ws[i],
-                                            abort=self.abort)
+                                            abort=self.abort, val_lt=probe_lt)
             mark("scatter_nvlink")
             self.dist.all_reduce(self.flag[0:1])  # every rank's stores have landed when this completes
             mark("barrier")
@@ -335,7 +338,7 @@ class P2PShuffleJoin:
                 if self.probe_scatter_ctas:
                     ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, self.probe_scatter_ctas)
                 ctx.shuffle_p2p_scatter_dev(self._share(fk, i), self._share(y, i), self.BITS, self.addr[i], self.ws[i],
-                                            abort=self.abort)
+                                            abort=self.abort, val_lt=probe_lt)
                 if self.probe_scatter_ctas:
                     ctx.set_tunable(TUNE_PEER_SCATTER_CTAS, 0)
                 self.dist.all_reduce(self.flag[i:i + 1])   # this share's rows of every rank have landed

@@ -680,6 +680,16 @@ int b2_shuffle_p2p_plan_dev(b2_ctx* ctx, const int64_t* const* d_off_ptrs, const
 int b2_shuffle_p2p_scatter_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n,
                                int bits, const uint64_t* d_bucket_addr, const int64_t* d_abort, void* d_ws,
                                size_t ws_bytes, void* stream);
+/* The same two steps with a predicate pushed in front of the link (the fused pipeline filter -> join ->
+ * aggregate over N GPUs): rows whose VALUE fails `value < val_threshold` are neither counted nor sent, so
+ * a 25 % predicate moves a quarter of the probe side over NVLink. filter_val == 0: exactly the calls
+ * above (d_val may then be NULL in the count). Count and scatter must agree on the predicate. */
+int b2_shuffle_p2p_count_lt_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n, int bits,
+                                int filter_val, uint32_t val_threshold, int64_t* d_bucket_off, void* d_ws,
+                                size_t ws_bytes, void* stream);
+int b2_shuffle_p2p_scatter_lt_dev(b2_ctx* ctx, const uint32_t* d_key, const uint32_t* d_val, int64_t n, int bits,
+                                  int filter_val, uint32_t val_threshold, const uint64_t* d_bucket_addr,
+                                  const int64_t* d_abort, void* d_ws, size_t ws_bytes, void* stream);
 /* Join of sides that are already grouped into 2^seg_bits coarse buckets on hash bits
  * [hash_skip_bits, hash_skip_bits + seg_bits); d_*_seg_off (int64, 2^seg_bits + 1, device) hold the
  * bucket boundaries in rows. PRECONDITION (the fused shuffle establishes it): every row of both sides

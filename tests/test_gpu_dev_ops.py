@@ -873,6 +873,43 @@ def test_p2p_plan_kernel_and_capacity_join_virtual_ranks(ctx, G, rows_per_rank):
                 assert int(a[1]) == int(host(outs[1])[:m][keep].astype(np.uint64).sum(dtype=np.uint64))
                 assert int(a[2]) == int(host(outs[2])[:m][keep].astype(np.uint64).sum(dtype=np.uint64))
         if not overflow:
+            # the same exchange with the predicate y < 2^30 pushed in front of the "link" (count_lt / scatter_lt):
+            # only the surviving probe rows are counted, planned for and stored; the aggregate of the join over
+            # what arrived equals the filtered aggregate of the full join
+            thr = 1 << 30
+            off2 = torch.zeros((G, B + 1), dtype=torch.int64, device="cuda")
+            for r in range(G):
+                ctx.shuffle_p2p_count_dev(d[r][0], BITS, wss[r, 0], off2[r], val=d[r][1], val_lt=thr)
+            sent = (off2[:, 1:] - off2[:, :-1]).sum().item()
+            assert sent == int((y < thr).sum())
+            optr = torch.tensor([off2[s].data_ptr() for s in range(G)], dtype=torch.int64, device="cuda")
+            recv2 = [torch.full((cap,), -1, dtype=torch.int64, device="cuda") for _ in range(G)]
+            peers2 = torch.tensor([t.data_ptr() for t in recv2], dtype=torch.int64, device="cuda")
+            tot = np.zeros(3, np.uint64)
+            addr2, seg2, info2 = {}, {}, {}
+            for r in range(G):
+                addr2[r] = torch.empty(B, dtype=torch.int64, device="cuda")
+                seg2[r] = torch.empty((1 << seg_bits) + 1, dtype=torch.int64, device="cuda")
+                info2[r] = torch.zeros(3, dtype=torch.int64, device="cuda")
+                ctx.shuffle_p2p_plan_dev(optr, peers2, r, G, BITS, cap, addr2[r], seg2[r], info2[r])
+            for r in range(G):
+                ctx.shuffle_p2p_scatter_dev(d[r][0], d[r][1], BITS, addr2[r], wss[r, 0], abort=info2[r][2:3], val_lt=thr)
+            for r in range(G):
+                agg = torch.zeros(3, dtype=torch.int64, device="cuda")
+                ws = torch.empty(ctx.join_seg_cap_ws_bytes(cap, cap, n // G, skip, seg_bits) + 256, dtype=torch.uint8,
+                                 device="cuda")
+                ctx.join_aggr_pairs_seg_cap_dev(recv2[r], seg2[r], recv[1][r], seg[r, 1], n // G, seg_bits,
+                                                skip_bits=skip, ws=ws, out=agg, abort=info2[r][2:3])
+                torch.cuda.synchronize()
+                tot += agg.cpu().numpy().view(np.uint64)
+                arrived = recv2[r].cpu().numpy()
+                arrived = arrived[arrived != -1].view(np.uint32).reshape(-1, 2)
+                assert arrived.shape[0] == int(info2[r][0].item()) and bool((arrived[:, 1] < thr).all())
+            e_fk, e_y, e_x = oracle.join(fk, y, pk, x)
+            keep = e_y < thr
+            assert int(tot[0]) == int(keep.sum())
+            assert int(tot[1]) == int(e_y[keep].astype(np.uint64).sum(dtype=np.uint64))
+            assert int(tot[2]) == int(e_x[keep].astype(np.uint64).sum(dtype=np.uint64))
             got = oracle.sort_rows(*[np.concatenate(g) for g in got])
             exp = oracle.sort_rows(*oracle.join(fk, y, pk, x))
             assert got[0].size == exp[0].size
