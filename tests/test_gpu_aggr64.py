@@ -80,4 +80,5 @@ def test_sum_gpu_rejects_mixed_widths(ctx):
     with pytest.raises(TypeError):
         ops.SumGpu(ctx, [np.zeros(4, np.uint32), np.zeros(4, np.uint64)])
     with pytest.raises(TypeError):
-        ops.FilterGpu(ctx, [np.zeros(4, np.uint64)])   # the filter is 32-bit only
+        ops.FilterGpu(ctx, [np.zeros(4, np.uint32), np.zeros(4, np.uint64)])   # one width per operator
+    assert ops.FilterGpu(ctx, [np.zeros(4, np.uint64)]).dtype == np.dtype(np.uint64)   # 64-bit filters: csrc/filter64.cu
