@@ -331,7 +331,13 @@ int b2_sum_u32_host(b2_ctx* ctx, const uint32_t* const* batch_ptrs, const int64_
  * d_out indices, d_batch_end and d_total are all offset by it, so a column can be filtered in
  * several calls (streamed chunks) that append to one compacted result without a host round trip
  * (pass call k's d_total as call k+1's d_carry_in).
- * d_ws: workspace of b2_filter_ws_bytes() bytes. */
+ * d_ws: workspace of b2_filter_ws_bytes() bytes.
+ * Concurrency: the filter kernels (32- and 64-bit) are persistent grids sized to what the GPU holds at
+ * once, and a CTA may wait for tiles counted by any other CTA of its grid. Two filter launches that
+ * overlap on one GPU (different streams, no ordering between them) can each hold the SM slots the
+ * other's unstarted CTAs need and never finish: order filter launches on one GPU (one stream, or
+ * events between streams). Kernels that end on their own may share the GPU with a filter; they delay
+ * it, they cannot block it. */
 size_t b2_filter_ws_bytes(int64_t nbatches, int64_t batch_len);
 int b2_filter_lt_u32_dev(b2_ctx* ctx, const uint32_t* d_in, int64_t nbatches, int64_t batch_len,
                          uint32_t threshold, uint32_t* d_out, int64_t* d_batch_end,
