@@ -203,10 +203,11 @@ def filter_lt_nullable(values, valid, thr: int = 1 << 30) -> np.ndarray:
 
 
 def filter_lt_typed(values, valid, thr) -> np.ndarray:
-    """The same filter over an int32 / float32 / uint32 column in ITS type's order (Arrow's `less`:
-    signed for int32, IEEE for float32 — a NaN row, like a null one, is never selected)."""
+    """The same filter over a uint32 / int32 / float32 or uint64 / int64 / float64 column in ITS type's
+    order (Arrow's `less`: signed for the int types, IEEE for the float types — a NaN row, like a null
+    one, is never selected)."""
     v = np.ascontiguousarray(values)
-    assert v.dtype in (np.uint32, np.int32, np.float32)
+    assert v.dtype in (np.uint32, np.int32, np.float32, np.uint64, np.int64, np.float64)
     with np.errstate(invalid="ignore"):
         keep = np.asarray(valid, dtype=bool) & (v < np.asarray(thr, dtype=v.dtype))
     return v[keep].copy()

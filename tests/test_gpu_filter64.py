@@ -1,5 +1,5 @@
 """Filter over 64-bit columns (b2_filter_lt_64_dev / b2_filter_lt_64_host_into, FilterGpu over uint64 /
-int64 / float64 batches; csrc/filter64.cu) against numpy and against Arrow's filter — the reference's
+int64 / float64 batches; csrc/filter64.cu) against the oracle (oracle.filter_lt_typed) and against Arrow's filter — the reference's
 oracle is the Acero plan filter(less(field, literal)) of host/filter/filter_native.cc:52-66. Rows keep
 their order, null rows are dropped, NaN rows are never selected."""
 import numpy as np
@@ -7,6 +7,8 @@ import pyarrow as pa
 import pyarrow.compute as pc
 import pytest
 import torch
+
+import oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -54,8 +56,7 @@ def test_filter_64_dev_one_batch(ctx, dtype, n, sel):
     obuf = torch.full((n + 16,), -7, dtype=torch.int64, device="cuda")
     out, end, total = ctx.filter64_dev(col, dtype, thr, out=obuf[8: 8 + max(n, 1)])
     torch.cuda.synchronize()
-    with np.errstate(invalid="ignore"):
-        exp = v[v < np.array(thr, dtype=dtype)]
+    exp = oracle.filter_lt_typed(v, np.ones(n, bool), thr)   # pinned against Arrow in tests/test_oracle_nullable.py
     k = int(total.item())
     assert k == exp.size and int(end[0].item()) == k
     assert np.array_equal(out[:k].cpu().numpy().view(np.uint64), exp.view(np.uint64))   # bit patterns: -0.0 stays -0.0
@@ -83,7 +84,7 @@ def test_filter_64_dev_ragged_batches_and_nulls(ctx, dtype, lens, nulls):
         keep = (v < np.array(thr, dtype=dtype)) & valid
     k = int(total.item())
     assert k == int(keep.sum())
-    assert np.array_equal(out[:k].cpu().numpy().view(np.uint64), v[keep].view(np.uint64))
+    assert np.array_equal(out[:k].cpu().numpy().view(np.uint64), oracle.filter_lt_typed(v, valid, thr).view(np.uint64))
     exp_end = np.concatenate([[0], np.cumsum(keep)])[off[1:]]
     assert np.array_equal(end.cpu().numpy(), exp_end)
 

@@ -87,6 +87,33 @@ def test_typed_filter_matches_arrow(dtype, thr):
                                                    exp.to_numpy(zero_copy_only=False).astype(dtype).view(np.uint32))
 
 
+@pytest.mark.parametrize("dtype,thr", [(np.uint64, 1 << 62), (np.uint64, 0), (np.uint64, 2**64 - 1),
+                                       (np.int64, -(1 << 40)), (np.int64, 0), (np.int64, 2**63 - 1),
+                                       (np.float64, 0.5), (np.float64, -0.0), (np.float64, np.inf)])
+def test_typed_filter_64_matches_arrow(dtype, thr):
+    """The restatement the 64-bit GPU filter is compared with (tests/test_gpu_filter64.py): numpy's `<` in
+    the column's type, nulls dropped — against Arrow's filter(less(column, scalar)), bit pattern by bit
+    pattern (NaN never passes, -0.0 stays -0.0, -0.0 < 0.0 is false)."""
+    rng = np.random.default_rng(6)
+    n = 20_000
+    if dtype == np.float64:
+        v = rng.standard_normal(n) * 3
+        v[::97] = np.nan
+        v[::101] = np.inf
+        v[::103] = -np.inf
+        v[::107] = -0.0
+        v[::109] = 0.0
+    else:
+        info = np.iinfo(dtype)
+        v = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    valid = rng.random(n) > 0.2
+    arr = pa.array(v, mask=~valid)
+    exp = pc.filter(arr, pc.less(arr, pa.scalar(thr, arr.type)))
+    got = oracle.filter_lt_typed(v, valid, thr)
+    assert got.dtype == v.dtype and np.array_equal(got.view(np.uint64),
+                                                   exp.to_numpy(zero_copy_only=False).astype(dtype).view(np.uint64))
+
+
 @pytest.mark.parametrize("n,null_frac", [(0, 0.0), (3, 1.0), (1000, 0.2), (70_001, 0.5)])
 def test_int32_aggregates_match_arrow(n, null_frac):
     rng = np.random.default_rng(300 + n)
