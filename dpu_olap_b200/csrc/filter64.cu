@@ -7,14 +7,15 @@
 // order, a null row is dropped, a NaN row is never selected, the result has no nulls.
 //
 // Two kernels compute the same result (ctx tunable B2_TUNE_FILTER64_KERNEL):
-//   0  filter64_single_pass_kernel (default): one CTA per 2048-row tile (16 KB), tiles handed out by
-//      an atomic ticket. The CTA loads its tile (eight independent 8-byte loads per thread), ranks
-//      the selected rows in row order (one ballot per 256 rows, a 64-entry scan of the (slice, warp)
-//      counts), obtains the rows selected before the tile with the decoupled look-back of
-//      lookback.cuh (the reference's serial handshake between tasklets, filter.c:28-55, without the
-//      serialisation: a tile only waits for its predecessors' COUNTS), stages the selected rows
-//      compacted in shared memory and writes them out as one contiguous run. Every row is read once
-//      and every selected row written once: 8 + 8 s bytes per row (s = selectivity).
+//   0  filter64_single_pass_kernel (default): persistent CTAs over 2048-row tiles (16 KB) dealt
+//      round-robin. A CTA loads its tile (row pairs as 128-bit words), ranks the selected rows of each
+//      warp with one packed shuffle scan, publishes the tile's count as counted sums (lookback.cuh:
+//      groups of 32 and 1024 tiles, the scheme of the 32-bit kernel) and parks the selected rows
+//      compacted in a shared-memory ring; a parked tile is written out as one contiguous run once its
+//      global offset is computable, i.e. once every earlier tile has been COUNTED (the reference's
+//      serial handshake between tasklets, filter.c:28-55, without the serialisation). Every row is
+//      read once and every selected row written once: 8 + 8 s bytes per row (s = selectivity).
+//      History and measurements: profiles/r2_filter64.md.
 //   1  counted two-pass compaction: filter64_count_kernel (selected rows per tile), an exclusive scan
 //      of the tile counts (csrc/scan.cu), filter64_compact_kernel (re-reads the tile and writes the
 //      selected rows behind the tile's offset): 8 + 8 + 8 s bytes per row. Kept as the cross-check.
